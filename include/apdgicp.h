@@ -1,0 +1,241 @@
+/*
+ * apdgicp.h — C-ABI of the B200-native FastAPDGICP registration path.
+ *
+ * This is the drop-in boundary: everything the reference class
+ * fast_gicp::FastAPDGICP<pcl::PointXYZINormal, pcl::PointXYZINormal>
+ * (reference fast_apdgicp/include/fast_gicp/gicp/fast_apdgicp.hpp:19-122) and
+ * its optimizer base LsqRegistration (lsq_registration.hpp:15-85) do on the hot
+ * path is reachable through these entry points. The C++ shim
+ * go-rio_b200/include/fast_gicp/gicp/fast_apdgicp.hpp re-creates the reference
+ * class on top of them; INTEGRATION.md shows the binding.
+ *
+ * Rules of the boundary
+ *  - extern "C", opaque handle, plain pointers and sizes, int status returns.
+ *  - No exception and no C++ type crosses it. All buffers are caller-owned
+ *    HOST memory unless a parameter is explicitly named `d_*` (device).
+ *  - One CUDA stream per handle. Calls on one handle are not thread-safe,
+ *    calls on different handles are (the reference has the same contract: one
+ *    instance per nodelet callback thread).
+ *  - There is no CPU fallback: every compute entry point fails with
+ *    APD_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Matrix conventions
+ *  - 4x4 transforms and 4x4 covariances are COLUMN-MAJOR (Eigen's default
+ *    layout, so Eigen::Matrix4f::data() / Matrix4d::data() can be passed as is).
+ *  - H is 6x6 column-major (symmetric, so the order is immaterial), b is 6.
+ */
+#ifndef APDGICP_H_
+#define APDGICP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APD_ABI_VERSION 1
+
+/* status codes */
+enum {
+  APD_OK = 0,
+  APD_ERR_INVALID = 1,   /* bad argument / state (e.g. align without clouds) */
+  APD_ERR_CUDA = 2,      /* CUDA runtime error, see apd_last_error           */
+  APD_ERR_TOO_FEW = 3,   /* cloud has fewer than k points (reference: UB,
+                            fast_apdgicp_impl.hpp:364-369; here: an error)   */
+  APD_ERR_UNSUPPORTED = 4,
+  APD_ERR_COMM = 5       /* NCCL error                                       */
+};
+
+/* reference gicp_settings.hpp:6 — same order, same values */
+enum {
+  APD_REG_NONE = 0,
+  APD_REG_MIN_EIG = 1,
+  APD_REG_NORMALIZED_MIN_EIG = 2,
+  APD_REG_PLANE = 3,
+  APD_REG_FROBENIUS = 4
+};
+
+/* reference lsq_registration.hpp:13 — same order */
+enum { APD_OPT_GAUSS_NEWTON = 0, APD_OPT_LEVENBERG_MARQUARDT = 1 };
+
+/* Every tunable the reference class holds on this path.
+ * Defaults (apd_default_params) are the reference constructors' values:
+ * fast_apdgicp_impl.hpp:14-28, fast_apdgicp.hpp:116-118,
+ * lsq_registration_impl.hpp:11-24. */
+typedef struct apd_params {
+  int32_t k_correspondences;           /* setCorrespondenceRandomness, 20     */
+  int32_t regularization;              /* setRegularizationMethod, PLANE      */
+  double max_correspondence_distance;  /* pcl corr_dist_threshold_, FLT_MAX   */
+  double dist_var;                     /* setDistVar, 0.86                    */
+  double azimuth_var;                  /* setAzimuthVar (degrees), 0.5        */
+  double elevation_var;                /* setElevationVar (degrees), 1.0      */
+  int32_t max_iterations;              /* pcl max_iterations_, 64             */
+  int32_t optimizer;                   /* lsq_optimizer_type_, LM             */
+  double rotation_epsilon;             /* setRotationEpsilon, 2e-3            */
+  double transformation_epsilon;       /* setTransformationEpsilon, 5e-4      */
+  int32_t lm_max_iterations;           /* lm_max_iterations_, 10              */
+  int32_t lm_debug_print;              /* setDebugPrint, 0                    */
+  double lm_init_lambda_factor;        /* setInitialLambdaFactor, 1e-9        */
+  int32_t maha_fp64;                   /* 0: store the per-point Mahalanobis
+                                          matrix as 6 x fp32 (24 B, default),
+                                          1: as 6 x fp64 (48 B). Arithmetic is
+                                          fp64 either way.                    */
+  int32_t reserved;
+} apd_params;
+
+typedef struct apd_handle apd_handle;
+
+/* ---- life cycle ------------------------------------------------------- */
+int apd_abi_version(void);
+int apd_default_params(apd_params* out);
+/* reference FastAPDGICP::FastAPDGICP (fast_apdgicp_impl.hpp:14-28) */
+int apd_create(int device, apd_handle** out);
+int apd_destroy(apd_handle* h);
+/* text of the last error on this handle ("" if none). Never NULL. */
+const char* apd_last_error(const apd_handle* h);
+/* setters of fast_apdgicp_impl.hpp:34-65 + lsq_registration_impl.hpp:30-42 +
+ * the pcl::Registration setters used by registrations.cpp:41-48 */
+int apd_set_params(apd_handle* h, const apd_params* p);
+int apd_get_params(const apd_handle* h, apd_params* out);
+
+/* ---- clouds ----------------------------------------------------------- */
+/* reference setInputSource / setInputTarget (fast_apdgicp_impl.hpp:115-135).
+ * `pts` is host AoS: point i starts at pts + i*stride_bytes; three floats
+ * x,y,z at +xyz_off; one float cluster label (pcl normal_x, written by the
+ * DBSCAN stage, preprocessing_nodelet_ntu.cpp:561-567) at +label_off, or
+ * label_off < 0 for "all zero". For pcl::PointXYZINormal: stride 48,
+ * xyz_off 0, label_off 16.
+ * cache_key: the reference early-outs on pointer identity (:116,:128); pass
+ * the cloud pointer value (or any id); 0 disables the early-out. Setting a
+ * cloud drops its cached covariances. */
+int apd_set_source(apd_handle* h, const void* pts, int32_t n, int32_t stride_bytes,
+                   int32_t xyz_off, int32_t label_off, uint64_t cache_key);
+int apd_set_target(apd_handle* h, const void* pts, int32_t n, int32_t stride_bytes,
+                   int32_t xyz_off, int32_t label_off, uint64_t cache_key);
+/* same, but the cloud is already on the device as float4 {x,y,z,label}[n]
+ * (no reference equivalent; used for HBM-resident benchmarking and sharding) */
+int apd_set_source_device(apd_handle* h, const void* d_xyzl, int32_t n);
+int apd_set_target_device(apd_handle* h, const void* d_xyzl, int32_t n);
+
+/* reference swapSourceAndTarget / clearSource / clearTarget (:89-112) */
+int apd_swap_source_and_target(apd_handle* h);
+int apd_clear_source(apd_handle* h);
+int apd_clear_target(apd_handle* h);
+
+/* reference set/get{Source,Target}Covariances (:138-145, hpp:73-79):
+ * n column-major 4x4 doubles (128 B each). Getters compute the covariances
+ * first if they are stale (the reference getter would return an empty vector
+ * before the first align; computing is a superset). */
+int apd_set_source_covariances(apd_handle* h, const double* covs4x4, int32_t n);
+int apd_set_target_covariances(apd_handle* h, const double* covs4x4, int32_t n);
+int apd_get_source_covariances(apd_handle* h, double* covs4x4, int32_t n);
+int apd_get_target_covariances(apd_handle* h, double* covs4x4, int32_t n);
+/* parity hook: the k neighbour indices of every point, ordered by (d2, index);
+ * out is int32[n*k]. which: 0 source, 1 target. */
+int apd_get_neighbors(apd_handle* h, int32_t which, int32_t* out, int32_t n, int32_t k);
+
+/* ---- the hot path ----------------------------------------------------- */
+/* pcl::Registration::align(output, guess) -> FastAPDGICP::computeTransformation
+ * (fast_apdgicp_impl.hpp:148-157) -> LsqRegistration::computeTransformation
+ * (lsq_registration_impl.hpp:55-80).
+ * guess: float[16] column-major, NULL = identity.
+ * T_out: float[16] final_transformation_. T_out_f64: optional double[16], the
+ * fp64 pose before the float cast. H_out: optional double[36] final_hessian_.
+ * converged/iterations: hasConverged() / nr_iterations_ (= index of the last
+ * outer iteration, as the reference sets it at :68) — optional.
+ * aligned_xyz: optional float[3*n_source], the transformed source cloud
+ * (pcl::transformPointCloud at :79), packed xyz. */
+int apd_align(apd_handle* h, const float* guess, float* T_out, double* T_out_f64,
+              double* H_out, int32_t* converged, int32_t* iterations, float* aligned_xyz);
+
+/* FastAPDGICP::linearize (:224-307) incl. update_correspondences (:160-220);
+ * T: double[16] column-major. H (36), b (6) may both be NULL (error only).
+ * Equivalent to LsqRegistration::evaluateCost when T comes from a float pose.
+ * Computes stale covariances first, as align does. */
+int apd_linearize(apd_handle* h, const double* T, double* H, double* b, double* err);
+/* FastAPDGICP::compute_error (:310-346): uses the correspondences and
+ * Mahalanobis matrices of the LAST linearize. */
+int apd_compute_error(apd_handle* h, const double* T, double* err);
+/* FastAPDGICP::update_correspondences (:160-220) alone. */
+int apd_update_correspondences(apd_handle* h, const double* T);
+/* parity hook: correspondences_ (int32[n], -1 = none) and sq_distances_
+ * (float[n]); either may be NULL. */
+int apd_get_correspondences(apd_handle* h, int32_t* idx, float* sq_dist, int32_t n);
+/* parity hook: mahalanobis_ as n column-major 4x4 doubles */
+int apd_get_mahalanobis(apd_handle* h, double* maha4x4, int32_t n);
+
+/* pcl::Registration::getFitnessScore(max_range) [PCL 1.10 registration.hpp]
+ * over final_transformation_ (or T if not NULL, float[16]); also returns the
+ * number of points with d2 <= max_range, and — for the status message of
+ * scan_matching_odometry_nodelet.cpp:677-689 — the number of points whose
+ * 1-NN squared distance is < inlier_sq_thr. */
+int apd_fitness(apd_handle* h, const float* T, double max_range, double* score,
+                int32_t* n_in_range, double inlier_sq_thr, int32_t* n_inliers);
+
+/* LM trace of the last apd_align: rows of {outer, inner, y0, yi, rho, lambda,
+ * |d|, accepted} as 8 doubles, the columns of the reference's lm_debug_print_
+ * table (lsq_registration_impl.hpp:148-154). Returns the number of rows
+ * written (<= max_rows) in *n_rows. */
+int apd_get_lm_trace(apd_handle* h, double* rows, int32_t max_rows, int32_t* n_rows);
+
+/* ---- batched registrations (config C3; no reference equivalent: the loop
+ * detector runs candidates serially, loop_detector.cpp:222-236) ---------- */
+typedef struct apd_pair {
+  const void* source;  /* host AoS, same layout arguments as apd_set_source  */
+  int32_t n_source;
+  const void* target;
+  int32_t n_target;
+  const float* guess;  /* float[16] column-major or NULL                     */
+} apd_pair;
+
+typedef struct apd_result {
+  float T[16];         /* final_transformation_, column-major                */
+  double fitness;      /* getFitnessScore(max_range = DBL_MAX)               */
+  int32_t converged;
+  int32_t iterations;
+  int32_t status;      /* APD_OK or an error code for this pair              */
+  int32_t n_inliers;   /* correspondences != -1 at the last linearize        */
+} apd_result;
+
+/* Runs n_pairs independent clear/set/align sequences on `device`, pipelined
+ * over `n_streams` internal handles (H2D of pair i+1 overlaps the kernels of
+ * pair i). */
+int apd_align_batch(int device, const apd_params* p, const apd_pair* pairs, int32_t n_pairs,
+                    int32_t stride_bytes, int32_t xyz_off, int32_t label_off,
+                    int32_t n_streams, int32_t with_fitness, apd_result* results);
+
+/* ---- source-sharded registration (config C4; no reference equivalent) --- */
+/* The handle holds source points [shard_begin, shard_begin+n_source) of a
+ * cloud of n_source_total points and the FULL target. After apd_comm_init,
+ * linearize / compute_error all-reduce their 28 / 1 doubles over NCCL, and
+ * cl_weight uses n_source_total (reference: 1/correspondences_.size(),
+ * fast_apdgicp_impl.hpp:273). id128 is an ncclUniqueId (128 bytes). */
+int apd_comm_unique_id(void* id128);
+int apd_comm_init(apd_handle* h, const void* id128, int32_t rank, int32_t nranks,
+                  int64_t n_source_total);
+int apd_comm_destroy(apd_handle* h);
+
+/* ---- instrumentation --------------------------------------------------- */
+/* CUDA stream of the handle (cudaStream_t as void*), for event timing. */
+void* apd_stream(apd_handle* h);
+/* Kernel launches issued by this handle since creation (bench.py's
+ * gpu_launches), and device milliseconds of the last call per kernel class
+ * (CUDA events, only recorded when profiling is enabled). */
+int64_t apd_launch_count(const apd_handle* h);
+enum {
+  APD_K_GRID = 0,      /* grid build (bounds, count, scan, scatter)          */
+  APD_K_KNN_COV = 1,   /* exact kNN + covariance + regularisation            */
+  APD_K_CORR = 2,      /* update_correspondences                             */
+  APD_K_LINEARIZE = 3, /* linearize H/b/err reduction                        */
+  APD_K_ERROR = 4,     /* compute_error reduction                            */
+  APD_K_FITNESS = 5,
+  APD_K_COUNT = 6
+};
+int apd_set_profiling(apd_handle* h, int32_t enabled);
+int apd_get_kernel_ms(apd_handle* h, double* ms /* [APD_K_COUNT] */, int64_t* launches /* [APD_K_COUNT] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APDGICP_H_ */

@@ -1,0 +1,116 @@
+"""Independent NumPy/SciPy restatement of the FastAPDGICP math, written from the
+reference source (fast_apdgicp_impl.hpp:160-411, lsq_registration_impl.hpp) without
+looking at oracle/: np.linalg.svd instead of the oracle's Jacobi solver,
+np.linalg.inv instead of adjugates, scipy cKDTree (fp64) instead of the fp32
+kd-tree. It pins the oracle's arithmetic; it is TEST INFRASTRUCTURE.
+"""
+import numpy as np
+from scipy.spatial import cKDTree
+
+
+def knn_sets(cloud_xyz, k):
+    tree = cKDTree(cloud_xyz.astype(np.float64))
+    d, idx = tree.query(cloud_xyz.astype(np.float64), k=k + 1)
+    return d, idx
+
+
+def covariances(cloud, nbr_idx, reg="PLANE"):
+    """fast_apdgicp_impl.hpp:366-405. nbr_idx [n,k] neighbour indices (incl. self)."""
+    P = cloud[:, :3].astype(np.float64)[nbr_idx]            # [n,k,3]
+    k = nbr_idx.shape[1]
+    C = np.einsum("nki,nkj->nij", P - P.mean(axis=1, keepdims=True), P - P.mean(axis=1, keepdims=True)) / k
+    if reg == "NONE":
+        return C
+    if reg == "FROBENIUS":
+        Ci = np.linalg.inv(C + 1e-3 * np.eye(3))
+        nrm = np.sqrt((Ci ** 2).sum(axis=(1, 2)))[:, None, None]
+        return np.linalg.inv(Ci / nrm)
+    U, S, Vt = np.linalg.svd(C)
+    if reg == "PLANE":
+        vals = np.tile(np.array([1.0, 1.0, 1e-3]), (C.shape[0], 1))
+    elif reg == "MIN_EIG":
+        vals = np.maximum(S, 1e-3)
+    elif reg == "NORMALIZED_MIN_EIG":
+        vals = np.maximum(S / S[:, :1], 1e-3)
+    else:
+        raise ValueError(reg)
+    return np.einsum("nij,nj,nkj->nik", U, vals, Vt.transpose(0, 2, 1))
+
+
+def noise_cov(pt32, dist_var, az_var, el_var):
+    """fast_apdgicp_impl.hpp:193-210 for float32 points pt32 [n,3]."""
+    p = pt32.astype(np.float64)
+    dist = np.sqrt((p ** 2).sum(axis=1))
+    s = np.stack([dist * dist_var / 400, dist * np.sin(az_var / 180 * np.pi), dist * np.sin(el_var / 180 * np.pi)], axis=1)
+    rho = np.sqrt(pt32[:, 0] * pt32[:, 0] + pt32[:, 1] * pt32[:, 1]).astype(np.float32)
+    el = np.arctan2(rho.astype(np.float64), p[:, 2]).astype(np.float32).astype(np.float64)
+    az = np.arctan2(p[:, 1], p[:, 0]).astype(np.float32).astype(np.float64)
+    ce, se, ca, sa = np.cos(el), np.sin(el), np.cos(az), np.sin(az)
+    n = p.shape[0]
+    Ry = np.zeros((n, 3, 3)); Rz = np.zeros((n, 3, 3))
+    Ry[:, 0, 0] = ce; Ry[:, 0, 2] = se; Ry[:, 1, 1] = 1; Ry[:, 2, 0] = -se; Ry[:, 2, 2] = ce
+    Rz[:, 0, 0] = ca; Rz[:, 0, 1] = -sa; Rz[:, 1, 0] = sa; Rz[:, 1, 1] = ca; Rz[:, 2, 2] = 1
+    A = (Rz @ Ry) * s[:, None, :]
+    return A @ A.transpose(0, 2, 1)
+
+
+def transform_f32(T, xyz32):
+    Tf = T.astype(np.float32)
+    x, y, z = xyz32[:, 0], xyz32[:, 1], xyz32[:, 2]
+    out = np.empty_like(xyz32, dtype=np.float32)
+    for r in range(3):
+        out[:, r] = ((Tf[r, 0] * x + Tf[r, 1] * y).astype(np.float32) + Tf[r, 2] * z).astype(np.float32) + Tf[r, 3]
+    return out
+
+
+def mahalanobis(T, src, tgt, cov_src, cov_tgt, corr, dist_var=0.86, az_var=0.5, el_var=1.0):
+    """fast_apdgicp_impl.hpp:193-218 given the correspondences."""
+    pt = transform_f32(T, src[:, :3])
+    cov_r = noise_cov(pt, dist_var, az_var, el_var)
+    R = T[:3, :3]
+    valid = corr >= 0
+    M = np.zeros((src.shape[0], 3, 3))
+    cB = cov_tgt[np.where(valid, corr, 0)]
+    RCR = (cB + cov_r) + R @ (cov_src + cov_r) @ R.T
+    M[valid] = np.linalg.inv(RCR[valid])
+    return M
+
+
+def linearize(T, src, tgt, cov_src, corr, M):
+    """fast_apdgicp_impl.hpp:247-304 given correspondences and Mahalanobis."""
+    n = src.shape[0]
+    valid = corr >= 0
+    a = src[:, :3].astype(np.float64)
+    b = tgt[np.where(valid, corr, 0), :3].astype(np.float64)
+    tA = a @ T[:3, :3].T + T[:3, 3]
+    e = b - tA
+    sv = np.linalg.svd(cov_src, compute_uv=False)
+    geo = sv[:, 2] / sv[:, 0]
+    cl = np.where(tgt[np.where(valid, corr, 0), 3] == src[:, 3], 1.0 / n, 0.0)
+    q = np.einsum("ni,nij,nj->n", e, M, e)
+    err = ((1.0 + geo + cl) * q)[valid].sum()
+    J = np.zeros((n, 3, 6))
+    J[:, 0, 1] = -tA[:, 2]; J[:, 0, 2] = tA[:, 1]
+    J[:, 1, 0] = tA[:, 2];  J[:, 1, 2] = -tA[:, 0]
+    J[:, 2, 0] = -tA[:, 1]; J[:, 2, 1] = tA[:, 0]
+    J[:, 0, 3] = J[:, 1, 4] = J[:, 2, 5] = -1.0
+    H = np.einsum("nia,nij,njb->nab", J, M, J)[valid].sum(axis=0)
+    bb = np.einsum("nia,nij,nj->na", J, M, e)[valid].sum(axis=0)
+    return err, H, bb
+
+
+def so3_exp(w):
+    th2 = w @ w
+    if th2 < 1e-10:
+        im = 0.5 - th2 / 48 + th2 * th2 / 3840
+        re = 1 - th2 / 8 + th2 * th2 / 384
+    else:
+        th = np.sqrt(th2)
+        im = np.sin(th / 2) / th
+        re = np.cos(th / 2)
+    qw, qx, qy, qz = re, im * w[0], im * w[1], im * w[2]
+    return np.array([
+        [1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)],
+        [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
+        [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)],
+    ])
