@@ -1,0 +1,1057 @@
+// C-ABI of the B200 FastAPDGICP library (include/apdgicp.h) and the host side
+// of the registration: cloud staging, grid sizing, the LM / GN outer loop
+// (reference lsq_registration_impl.hpp:55-173) driving the CUDA kernels, the
+// batched and the source-sharded (NCCL) variants.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/apdgicp.h"
+#include "host_math.hpp"
+#include "kernels.cuh"
+
+using namespace apd;
+
+namespace {
+
+// ------------------------------------------------------------------ NCCL ----
+// Loaded lazily with dlopen so that the library has no link-time dependency on
+// NCCL (the single-GPU drop-in use case never needs it).
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) {
+      err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+      return false;
+    }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) {
+      err = "libnccl is missing required symbols";
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclSum = 0;      // ncclSum
+
+// -------------------------------------------------------------- buffers ----
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;  // grow with slack so repeated set_* calls rarely reallocate
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return e;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) return e;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Cloud {
+  int n = 0;
+  bool present = false;
+  uint64_t key = 0;
+  float bbox[6] = {0, 0, 0, 0, 0, 0};
+  DevBuf pts, spts, label, inv_perm, cov, geo, geo64, cell_start;
+  PinnedBuf stage;                  // host AoS -> float4 staging for the H2D copy
+  cudaEvent_t staged = nullptr;     // completion of the last H2D out of `stage`
+  const float4* ext_pts = nullptr;  // user-owned device cloud (apd_set_*_device)
+  GridDesc g{};
+  int ncells = 0;
+  bool grid_valid = false;
+  bool cov_valid = false;
+  bool geo_valid = false;
+  CloudDev view() const {
+    CloudDev c;
+    c.n = n;
+    c.pts = ext_pts ? ext_pts : pts.as<const float4>();
+    c.g = g;
+    c.ncells = ncells;
+    c.cell_start = cell_start.as<uint32_t>();
+    c.spts = spts.as<float4>();
+    c.label = label.as<float>();
+    c.inv_perm = inv_perm.as<int>();
+    c.cov = cov.as<double>();
+    c.geo = geo.as<float>();
+    c.geo64 = geo64.as<double>();
+    return c;
+  }
+  void release() {
+    pts.release(); spts.release(); label.release(); inv_perm.release(); cov.release(); geo.release(); geo64.release(); cell_start.release();
+    stage.release();
+    if (staged) cudaEventDestroy(staged);
+    staged = nullptr;
+  }
+};
+
+struct ProfEvent {
+  cudaEvent_t a, b;
+  int cls;
+  int64_t launches;
+};
+
+}  // namespace
+
+struct apd_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  apd_params params{};
+  std::string error;
+  Cloud src, tgt;
+  // per-linearisation state (sorted order of the source)
+  DevBuf corr, sqd, mahaA, mahaB;
+  int corr_n = -1;          // number of source points the buffers describe (-1: none yet)
+  int corr_fp64 = 0;
+  // scratch
+  DevBuf work, scratch, partials, small;  // small: out28 + ticket + fitness
+  PinnedBuf h_small;
+  // results of the last align
+  hm::Pose final_pose = hm::Pose::identity();
+  float final_T[16];        // column-major
+  double final_H[36];       // row-major == column-major (symmetric)
+  bool converged = false;
+  int nr_iterations = 0;
+  double lm_lambda = -1.0;
+  std::vector<double> trace;  // rows of 8
+  // sharding
+  ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  int64_t n_source_total = 0;
+  // instrumentation
+  int64_t launches = 0;
+  bool profiling = false;
+  std::vector<ProfEvent> pending;
+  std::vector<cudaEvent_t> event_pool;
+  double k_ms[APD_K_COUNT] = {0};
+  int64_t k_launches[APD_K_COUNT] = {0};
+  int max_reduce_blocks = 148 * 4;
+  double cells_per_point = 8.0;
+};
+
+namespace {
+
+#define APD_CUDA(h, expr)                                                                 \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      (h)->error = std::string(#expr) + ": " + cudaGetErrorString(_e);                    \
+      return APD_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+int fail(apd_handle* h, int code, const char* msg) {
+  h->error = msg;
+  return code;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// --- profiling: CUDA events around each kernel class --------------------------
+struct ProfScope {
+  apd_handle* h;
+  int cls;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int64_t l0;
+  ProfScope(apd_handle* h_, int cls_) : h(h_), cls(cls_), l0(h_->launches) {
+    if (!h->profiling) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!h->event_pool.empty()) {
+        e = h->event_pool.back();
+        h->event_pool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+      return e;
+    };
+    a = get();
+    b = get();
+    cudaEventRecord(a, h->stream);
+  }
+  ~ProfScope() {
+    if (!h->profiling) {
+      h->k_launches[cls] += h->launches - l0;
+      return;
+    }
+    cudaEventRecord(b, h->stream);
+    h->pending.push_back(ProfEvent{a, b, cls, h->launches - l0});
+  }
+};
+void flush_prof(apd_handle* h) {
+  if (h->pending.empty()) return;
+  cudaStreamSynchronize(h->stream);
+  for (auto& p : h->pending) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    h->k_ms[p.cls] += ms;
+    h->k_launches[p.cls] += p.launches;
+    h->event_pool.push_back(p.a);
+    h->event_pool.push_back(p.b);
+  }
+  h->pending.clear();
+}
+
+PoseD to_pose_d(const hm::Pose& p) {
+  PoseD T;
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) T.r[r * 3 + c] = p(r, c);
+    T.t[r] = p(r, 3);
+  }
+  return T;
+}
+PoseF colmajor_f32_to_pose_f(const float* T) {
+  PoseF f;
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) f.r[r * 3 + c] = T[c * 4 + r];
+    f.t[r] = T[3 * 4 + r];
+  }
+  return f;
+}
+
+// host AoS -> pinned float4 staging + bounding box
+void stage_cloud(const void* pts, int n, int stride, int xyz_off, int label_off, float4* dst, float bbox[6]) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  const char* base = reinterpret_cast<const char*>(pts);
+  for (int i = 0; i < n; i++) {
+    const char* p = base + (size_t)i * stride;
+    float xyz[3], l = 0.f;
+    std::memcpy(xyz, p + xyz_off, 12);
+    if (label_off >= 0) std::memcpy(&l, p + label_off, 4);
+    dst[i] = make_float4(xyz[0], xyz[1], xyz[2], l);
+    for (int a = 0; a < 3; a++) {
+      if (xyz[a] < mn[a]) mn[a] = xyz[a];
+      if (xyz[a] > mx[a]) mx[a] = xyz[a];
+    }
+  }
+  for (int a = 0; a < 3; a++) {
+    bbox[a] = mn[a];
+    bbox[3 + a] = mx[a];
+  }
+}
+
+// Grid sizing: cell edge so that the bounding box holds ~cells_per_point * n
+// cells (radar clouds live on surfaces, so occupied cells hold several points),
+// at most 2048 cells per axis (bounds the fp32 cell-coordinate error the search
+// margin covers) and 2^28 cells in total.
+void size_grid(const float bbox[6], int n, double cells_per_point, GridDesc& g, int& ncells) {
+  double ext[3];
+  for (int a = 0; a < 3; a++) {
+    ext[a] = (double)bbox[3 + a] - (double)bbox[a];
+    if (!(ext[a] > 0.0) || !std::isfinite(ext[a])) ext[a] = 0.0;
+  }
+  const double emax = std::max(std::max(ext[0], ext[1]), std::max(ext[2], 1e-3));
+  const double target = std::max(64.0, cells_per_point * (double)n);
+  double vol = 1.0;
+  for (int a = 0; a < 3; a++) vol *= std::max(ext[a], emax * 1e-3);
+  double cell = std::cbrt(vol / target);
+  cell = std::max(cell, emax / 2040.0);
+  long long d[3];
+  for (int iter = 0; iter < 200; iter++) {
+    long long tot = 1;
+    bool too_wide = false;
+    for (int a = 0; a < 3; a++) {
+      d[a] = (long long)std::floor(ext[a] / cell) + 1;
+      if (d[a] > 2048) too_wide = true;
+      tot *= d[a];
+    }
+    if (!too_wide && (double)tot <= 2.0 * target && tot <= (1ll << 28)) break;
+    cell *= 1.2599210498948732;  // 2^(1/3)
+  }
+  g.ox = bbox[0];
+  g.oy = bbox[1];
+  g.oz = bbox[2];
+  g.inv_cell = (float)(1.0 / cell);
+  g.cell = (float)(1.0 / (double)g.inv_cell);
+  // dims from the SAME fp32 expression the kernels use, so the max corner maps inside
+  auto dim = [&](float mx, float o) { return (int)std::floor((mx - o) * g.inv_cell) + 1; };
+  g.nx = std::max(1, dim(bbox[3], g.ox));
+  g.ny = std::max(1, dim(bbox[4], g.oy));
+  g.nz = std::max(1, dim(bbox[5], g.oz));
+  ncells = g.nx * g.ny * g.nz;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int ensure_grid(apd_handle* h, Cloud& c) {
+  if (c.grid_valid) return APD_OK;
+  if (!c.present || c.n <= 0) return fail(h, APD_ERR_INVALID, "cloud not set");
+  size_grid(c.bbox, c.n, h->cells_per_point, c.g, c.ncells);
+  const size_t n = (size_t)c.n;
+  APD_CUDA(h, c.spts.ensure(n * sizeof(float4)));
+  APD_CUDA(h, c.label.ensure(n * sizeof(float)));
+  APD_CUDA(h, c.inv_perm.ensure(n * sizeof(int)));
+  APD_CUDA(h, c.cell_start.ensure(((size_t)c.ncells + 1) * sizeof(uint32_t)));
+  // scratch: keys x2, vals x2, hist, scan tmp
+  const int sblocks = (c.n + kSortTile - 1) / kSortTile;
+  const size_t hist_elems = (size_t)256 * sblocks;
+  const size_t scan_elems = std::max(scan_tmp_elems_for((size_t)c.ncells + 1), scan_tmp_elems_for(hist_elems));
+  const size_t kv = align_up(n * sizeof(uint32_t), 256);
+  const size_t total = 4 * kv + align_up(hist_elems * 4, 256) + align_up(scan_elems * 4, 256);
+  APD_CUDA(h, h->work.ensure(total));
+  GridWork w;
+  char* p = h->work.as<char>();
+  w.keys[0] = (uint32_t*)p; p += kv;
+  w.keys[1] = (uint32_t*)p; p += kv;
+  w.vals[0] = (uint32_t*)p; p += kv;
+  w.vals[1] = (uint32_t*)p; p += kv;
+  w.hist = (uint32_t*)p; p += align_up(hist_elems * 4, 256);
+  w.scan_tmp = (uint32_t*)p;
+  w.scan_tmp_elems = scan_elems;
+  {
+    ProfScope ps(h, APD_K_GRID);
+    launch_grid_build(c.view(), w, h->stream, &h->launches);
+  }
+  APD_CUDA(h, cudaGetLastError());
+  c.grid_valid = true;
+  return APD_OK;
+}
+
+// FastAPDGICP::calculate_covariances (:351-411)
+int ensure_covariances_of(apd_handle* h, Cloud& c) {
+  int rc = ensure_grid(h, c);
+  if (rc != APD_OK) return rc;
+  if (c.cov_valid && c.geo_valid) return APD_OK;
+  APD_CUDA(h, c.cov.ensure((size_t)c.n * 6 * sizeof(double)));
+  APD_CUDA(h, c.geo.ensure((size_t)c.n * sizeof(float)));
+  APD_CUDA(h, c.geo64.ensure((size_t)c.n * sizeof(double)));
+  if (!c.cov_valid) {
+    const int k = h->params.k_correspondences;
+    if (k < 1 || k > 32) return fail(h, APD_ERR_UNSUPPORTED, "k_correspondences must be in [1, 32]");
+    if (c.n < k) return fail(h, APD_ERR_TOO_FEW, "cloud has fewer points than k_correspondences");
+    ProfScope ps(h, APD_K_KNN_COV);
+    launch_knn_cov(c.view(), k, nullptr, h->stream, &h->launches);
+    launch_regularize(c.view(), h->params.regularization, h->stream, &h->launches);
+    c.cov_valid = true;
+    c.geo_valid = true;
+  } else if (!c.geo_valid) {
+    ProfScope ps(h, APD_K_KNN_COV);
+    launch_geo_weight(c.view(), h->stream, &h->launches);
+    c.geo_valid = true;
+  }
+  APD_CUDA(h, cudaGetLastError());
+  return APD_OK;
+}
+
+int ensure_covariances(apd_handle* h) {
+  if (!h->src.present || !h->tgt.present) return fail(h, APD_ERR_INVALID, "source or target cloud not set");
+  int rc = ensure_covariances_of(h, h->src);  // :149-151
+  if (rc != APD_OK) return rc;
+  return ensure_covariances_of(h, h->tgt);    // :152-154
+}
+
+int ensure_small(apd_handle* h) {
+  // [0..27] out28, [32..34] fitness out3, then tickets (uint) at double index 40, 41
+  if (!h->small.p) {
+    APD_CUDA(h, h->small.ensure(64 * sizeof(double)));
+    APD_CUDA(h, cudaMemsetAsync(h->small.p, 0, 64 * sizeof(double), h->stream));
+  }
+  if (!h->partials.p) APD_CUDA(h, h->partials.ensure((size_t)h->max_reduce_blocks * kReduceVals * sizeof(double)));
+  APD_CUDA(h, h->h_small.ensure(64 * sizeof(double)));
+  return APD_OK;
+}
+
+CorrOut corr_view(apd_handle* h) {
+  CorrOut c;
+  c.corr = h->corr.as<int>();
+  c.sqd = h->sqd.as<float>();
+  c.mahaA = h->mahaA.p;
+  c.mahaB = h->mahaB.p;
+  c.maha_fp64 = h->corr_fp64;
+  return c;
+}
+
+// FastAPDGICP::update_correspondences (:160-220)
+int do_update_correspondences(apd_handle* h, const hm::Pose& T) {
+  const size_t n = (size_t)h->src.n;
+  const int fp64 = h->params.maha_fp64 ? 1 : 0;
+  APD_CUDA(h, h->corr.ensure(n * sizeof(int)));
+  APD_CUDA(h, h->sqd.ensure(n * sizeof(float)));
+  APD_CUDA(h, h->mahaA.ensure(n * (fp64 ? sizeof(double2) : sizeof(float4))));
+  APD_CUDA(h, h->mahaB.ensure(n * (fp64 ? 2 * sizeof(double2) : sizeof(float2))));
+  h->corr_fp64 = fp64;
+  NoiseParams np;
+  np.dist_var = h->params.dist_var;
+  np.sin_az = std::sin(h->params.azimuth_var / 180 * M_PI);    // :196
+  np.sin_el = std::sin(h->params.elevation_var / 180 * M_PI);  // :197
+  const double thr = h->params.max_correspondence_distance;
+  np.thr_sq = thr * thr;  // :183 (double product)
+  np.search_limit = (float)thr;
+  {
+    ProfScope ps(h, APD_K_CORR);
+    launch_update_correspondences(h->src.view(), h->tgt.view(), to_pose_d(T), np, corr_view(h), h->stream, &h->launches);
+  }
+  APD_CUDA(h, cudaGetLastError());
+  h->corr_n = h->src.n;
+  return APD_OK;
+}
+
+// Launches K4/K5, all-reduces across shards if a communicator is set, and
+// brings the 28 doubles back. out: H (row-major 36, optional), b (6, optional), err.
+int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, double* b6, double* err) {
+  int rc = ensure_small(h);
+  if (rc != APD_OK) return rc;
+  double* d_out = h->small.as<double>();
+  ReduceWork w;
+  w.partials = h->partials.as<double>();
+  w.ticket = reinterpret_cast<unsigned int*>(d_out + 40);
+  w.max_blocks = h->max_reduce_blocks;
+  const double n_total = h->comm ? (double)h->n_source_total : (double)h->src.n;
+  {
+    ProfScope ps(h, want_hb ? APD_K_LINEARIZE : APD_K_ERROR);
+    launch_linearize(h->src.view(), h->tgt.view(), to_pose_d(T), corr_view(h), n_total, want_hb, w, d_out, h->stream, &h->launches);
+  }
+  APD_CUDA(h, cudaGetLastError());
+  if (h->comm) {
+    ncclResult_t r = want_hb ? g_nccl.AllReduce(d_out, d_out, kReduceVals, kNcclFloat64, kNcclSum, h->comm, h->stream)
+                             : g_nccl.AllReduce(d_out + 27, d_out + 27, 1, kNcclFloat64, kNcclSum, h->comm, h->stream);
+    if (r != 0) return fail(h, APD_ERR_COMM, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclAllReduce failed");
+  }
+  double* hs = reinterpret_cast<double*>(h->h_small.p);
+  APD_CUDA(h, cudaMemcpyAsync(hs, d_out, kReduceVals * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (want_hb) {
+    if (H36) hm::unpack_upper(hs, H36);
+    if (b6) std::memcpy(b6, hs + 21, 6 * sizeof(double));
+  }
+  *err = hs[27];
+  return APD_OK;
+}
+
+// FastAPDGICP::linearize (:224-307)
+int do_linearize(apd_handle* h, const hm::Pose& T, double* H36, double* b6, double* err) {
+  int rc = do_update_correspondences(h, T);  // :226
+  if (rc != APD_OK) return rc;
+  return reduce_pass(h, T, H36 != nullptr && b6 != nullptr, H36, b6, err);
+}
+
+void trace_row(apd_handle* h, int outer, int inner, double y0, double yi, double rho, double lambda, double dn, bool accepted) {
+  const double row[8] = {(double)outer, (double)inner, y0, yi, rho, lambda, dn, accepted ? 1.0 : 0.0};
+  h->trace.insert(h->trace.end(), row, row + 8);
+}
+
+// LsqRegistration::step_gn (lsq_registration_impl.hpp:107-123)
+int step_gn(apd_handle* h, int outer, hm::Pose& x0, hm::Pose& delta) {
+  double H[36], b[6], y0;
+  int rc = do_linearize(h, x0, H, b, &y0);
+  if (rc != APD_OK) return rc;
+  double nb[6], d[6];
+  for (int i = 0; i < 6; i++) nb[i] = -b[i];
+  hm::ldlt_solve6(H, nb, d);
+  delta = hm::delta_from_twist(d);
+  x0 = hm::compose(delta, x0);
+  std::memcpy(h->final_H, H, sizeof(H));
+  double dn = 0;
+  for (int i = 0; i < 6; i++) dn += d[i] * d[i];
+  trace_row(h, outer, 0, y0, y0, 0.0, 0.0, std::sqrt(dn), true);
+  return APD_OK;
+}
+
+// LsqRegistration::step_lm (lsq_registration_impl.hpp:127-173); *ok = its return value
+int step_lm(apd_handle* h, int outer, hm::Pose& x0, hm::Pose& delta, bool* ok) {
+  double H[36], b[6], y0;
+  int rc = do_linearize(h, x0, H, b, &y0);  // :130
+  if (rc != APD_OK) return rc;
+  if (h->lm_lambda < 0.0) {  // :131-133
+    double mx = 0.0;
+    for (int i = 0; i < 6; i++) mx = std::max(mx, std::fabs(H[i * 6 + i]));
+    h->lm_lambda = h->params.lm_init_lambda_factor * mx;
+  }
+  double nu = 2.0;
+  for (int i = 0; i < h->params.lm_max_iterations; i++) {  // :136
+    double Hl[36], nb[6], d[6];
+    std::memcpy(Hl, H, sizeof(H));
+    for (int j = 0; j < 6; j++) {
+      Hl[j * 6 + j] += h->lm_lambda;
+      nb[j] = -b[j];
+    }
+    hm::ldlt_solve6(Hl, nb, d);  // :137-138
+    delta = hm::delta_from_twist(d);  // :140-142
+    const hm::Pose xi = hm::compose(delta, x0);  // :144
+    double yi;
+    rc = reduce_pass(h, xi, false, nullptr, nullptr, &yi);  // compute_error(xi) :145
+    if (rc != APD_OK) return rc;
+    double denom = 0.0, dn = 0.0;
+    for (int j = 0; j < 6; j++) {
+      denom += d[j] * (h->lm_lambda * d[j] - b[j]);
+      dn += d[j] * d[j];
+    }
+    const double rho = (y0 - yi) / denom;  // :146
+    if (h->params.lm_debug_print) {       // :148-154
+      if (i == 0) std::printf("--- LM optimization ---\n%5s %15s %15s %15s %15s %15s %5s\n", "i", "y0", "yi", "rho", "lambda", "|delta|", "dec");
+      std::printf("%5d %15g %15g %15g %15g %15g %5c\n", i, y0, yi, rho, h->lm_lambda, std::sqrt(dn), rho > 0.0 ? 'x' : ' ');
+    }
+    trace_row(h, outer, i, y0, yi, rho, h->lm_lambda, std::sqrt(dn), !(rho < 0));
+    if (rho < 0) {  // :156-164
+      if (hm::is_converged(delta, h->params.rotation_epsilon, h->params.transformation_epsilon)) {
+        *ok = true;
+        return APD_OK;
+      }
+      h->lm_lambda = nu * h->lm_lambda;
+      nu = 2 * nu;
+      continue;
+    }
+    x0 = xi;  // :166-169
+    h->lm_lambda = h->lm_lambda * std::max(1.0 / 3.0, 1 - std::pow(2 * rho - 1, 3));
+    std::memcpy(h->final_H, H, sizeof(H));
+    *ok = true;
+    return APD_OK;
+  }
+  *ok = false;  // :172
+  return APD_OK;
+}
+
+int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t stride, int32_t xyz_off, int32_t label_off, uint64_t key) {
+  if (!pts || n < 0 || stride < 12 || xyz_off < 0) return fail(h, APD_ERR_INVALID, "bad cloud arguments");
+  if (c.present && key != 0 && key == c.key) return APD_OK;  // pointer-identity early-out (:116,:128)
+  DeviceGuard dg(h->device);
+  // the previous H2D out of this staging buffer must have completed before it is overwritten
+  if (c.staged) APD_CUDA(h, cudaEventSynchronize(c.staged));
+  else APD_CUDA(h, cudaEventCreateWithFlags(&c.staged, cudaEventDisableTiming));
+  APD_CUDA(h, c.stage.ensure((size_t)std::max(n, 1) * sizeof(float4)));
+  stage_cloud(pts, n, stride, xyz_off, label_off, reinterpret_cast<float4*>(c.stage.p), c.bbox);
+  APD_CUDA(h, c.pts.ensure((size_t)std::max(n, 1) * sizeof(float4)));
+  APD_CUDA(h, cudaMemcpyAsync(c.pts.p, c.stage.p, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  APD_CUDA(h, cudaEventRecord(c.staged, h->stream));
+  c.ext_pts = nullptr;
+  c.n = n;
+  c.present = true;
+  c.key = key;
+  c.grid_valid = false;
+  c.cov_valid = false;  // source_covs_.clear() (:122,:133)
+  c.geo_valid = false;
+  return APD_OK;
+}
+
+int set_cloud_device(apd_handle* h, Cloud& c, const void* d_xyzl, int32_t n) {
+  if (!d_xyzl || n < 0) return fail(h, APD_ERR_INVALID, "bad cloud arguments");
+  DeviceGuard dg(h->device);
+  int rc = ensure_small(h);
+  if (rc != APD_OK) return rc;
+  float* d_b = reinterpret_cast<float*>(h->small.as<double>() + 48);
+  launch_bounds(reinterpret_cast<const float4*>(d_xyzl), n, d_b, h->stream, &h->launches);
+  unsigned int enc[6];
+  APD_CUDA(h, cudaMemcpyAsync(enc, d_b, sizeof(enc), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int a = 0; a < 6; a++) {
+    unsigned int u = enc[a];
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    std::memcpy(&c.bbox[a], &u, 4);
+  }
+  c.ext_pts = reinterpret_cast<const float4*>(d_xyzl);
+  c.n = n;
+  c.present = true;
+  c.key = 0;
+  c.grid_valid = false;
+  c.cov_valid = false;
+  c.geo_valid = false;
+  return APD_OK;
+}
+
+int set_covs(apd_handle* h, Cloud& c, const double* covs, int32_t n) {
+  if (!c.present || n != c.n || !covs) return fail(h, APD_ERR_INVALID, "covariance count does not match the cloud");
+  DeviceGuard dg(h->device);
+  int rc = ensure_grid(h, c);
+  if (rc != APD_OK) return rc;
+  APD_CUDA(h, c.cov.ensure((size_t)n * 6 * sizeof(double)));
+  APD_CUDA(h, c.geo.ensure((size_t)n * sizeof(float)));
+  APD_CUDA(h, c.geo64.ensure((size_t)n * sizeof(double)));
+  APD_CUDA(h, h->scratch.ensure((size_t)n * 16 * sizeof(double)));
+  APD_CUDA(h, cudaMemcpyAsync(h->scratch.p, covs, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  launch_cov_import(c.view(), h->scratch.as<double>(), h->stream, &h->launches);
+  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  c.cov_valid = true;
+  c.geo_valid = false;
+  return APD_OK;
+}
+
+int get_covs(apd_handle* h, Cloud& c, double* covs, int32_t n) {
+  if (!c.present || n != c.n || !covs) return fail(h, APD_ERR_INVALID, "covariance count does not match the cloud");
+  DeviceGuard dg(h->device);
+  int rc = ensure_covariances_of(h, c);
+  if (rc != APD_OK) return rc;
+  APD_CUDA(h, h->scratch.ensure((size_t)n * 16 * sizeof(double)));
+  launch_cov_export(c.view(), h->scratch.as<double>(), h->stream, &h->launches);
+  APD_CUDA(h, cudaMemcpyAsync(covs, h->scratch.p, (size_t)n * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  flush_prof(h);
+  return APD_OK;
+}
+
+void default_params(apd_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->k_correspondences = 20;
+  p->regularization = APD_REG_PLANE;
+  p->max_correspondence_distance = (double)std::numeric_limits<float>::max();
+  p->dist_var = 0.86;
+  p->azimuth_var = 0.5;
+  p->elevation_var = 1.0;
+  p->max_iterations = 64;
+  p->optimizer = APD_OPT_LEVENBERG_MARQUARDT;
+  p->rotation_epsilon = 2e-3;
+  p->transformation_epsilon = 5e-4;
+  p->lm_max_iterations = 10;
+  p->lm_debug_print = 0;
+  p->lm_init_lambda_factor = 1e-9;
+  p->maha_fp64 = 0;
+}
+
+int do_align(apd_handle* h, const float* guess) {
+  int rc = ensure_covariances(h);  // FastAPDGICP::computeTransformation (:148-157)
+  if (rc != APD_OK) return rc;
+  hm::Pose x0 = guess ? hm::from_colmajor_f32(guess) : hm::Pose::identity();  // lsq :56
+  h->lm_lambda = -1.0;   // :58
+  h->converged = false;  // :59
+  h->trace.clear();
+  h->nr_iterations = 0;
+  for (int i = 0; i < h->params.max_iterations && !h->converged; i++) {  // :67
+    h->nr_iterations = i;                                                 // :68
+    hm::Pose delta;
+    bool ok = true;
+    if (h->params.optimizer == APD_OPT_GAUSS_NEWTON) rc = step_gn(h, i, x0, delta);
+    else rc = step_lm(h, i, x0, delta, &ok);
+    if (rc != APD_OK) return rc;
+    if (!ok) {
+      std::fprintf(stderr, "lm not converged!!\n");  // :72
+      break;
+    }
+    h->converged = hm::is_converged(delta, h->params.rotation_epsilon, h->params.transformation_epsilon);  // :75
+  }
+  h->final_pose = x0;
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) h->final_T[c * 4 + r] = (float)x0(r, c);  // :78
+  return APD_OK;
+}
+
+int do_fitness(apd_handle* h, const float* T, double max_range, double* score, int32_t* n_in_range, double inlier_sq_thr, int32_t* n_inliers) {
+  if (!h->src.present || !h->tgt.present) return fail(h, APD_ERR_INVALID, "source or target cloud not set");
+  int rc = ensure_grid(h, h->src);
+  if (rc != APD_OK) return rc;
+  rc = ensure_grid(h, h->tgt);
+  if (rc != APD_OK) return rc;
+  rc = ensure_small(h);
+  if (rc != APD_OK) return rc;
+  double* d_small = h->small.as<double>();
+  const PoseF Tf = colmajor_f32_to_pose_f(T ? T : h->final_T);
+  {
+    ProfScope ps(h, APD_K_FITNESS);
+    launch_fitness(h->src.view(), h->tgt.view(), Tf, max_range, inlier_sq_thr, h->partials.as<double>(), h->max_reduce_blocks, d_small + 32,
+                   reinterpret_cast<unsigned int*>(d_small + 41), h->stream, &h->launches);
+  }
+  APD_CUDA(h, cudaGetLastError());
+  double* hs = reinterpret_cast<double*>(h->h_small.p) + 32;
+  APD_CUDA(h, cudaMemcpyAsync(hs, d_small + 32, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int nr = (int)hs[1];
+  if (score) *score = nr > 0 ? hs[0] / nr : std::numeric_limits<double>::max();
+  if (n_in_range) *n_in_range = nr;
+  if (n_inliers) *n_inliers = (int)hs[2];
+  return APD_OK;
+}
+
+}  // namespace
+
+// =============================================================== C-ABI =====
+extern "C" {
+
+int apd_abi_version(void) { return APD_ABI_VERSION; }
+
+int apd_default_params(apd_params* out) {
+  if (!out) return APD_ERR_INVALID;
+  default_params(out);
+  return APD_OK;
+}
+
+int apd_create(int device, apd_handle** out) {
+  if (!out) return APD_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return APD_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return APD_ERR_CUDA;
+  if (prop.major != 10) return APD_ERR_CUDA;  // sm_100a only: no other code path exists
+  apd_handle* h = new apd_handle();
+  h->device = device;
+  default_params(&h->params);
+  DeviceGuard dg(device);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return APD_ERR_CUDA;
+  }
+  h->max_reduce_blocks = prop.multiProcessorCount * 4;
+  if (const char* e = std::getenv("APD_CELLS_PER_POINT")) {
+    const double v = std::atof(e);
+    if (v > 0.01 && v < 1000.0) h->cells_per_point = v;
+  }
+  for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+  for (int i = 0; i < 36; i++) h->final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity()
+  *out = h;
+  return APD_OK;
+}
+
+int apd_destroy(apd_handle* h) {
+  if (!h) return APD_OK;
+  DeviceGuard dg(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  h->src.release(); h->tgt.release();
+  h->corr.release(); h->sqd.release(); h->mahaA.release(); h->mahaB.release();
+  h->work.release(); h->scratch.release(); h->partials.release(); h->small.release();
+  h->h_small.release();
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return APD_OK;
+}
+
+const char* apd_last_error(const apd_handle* h) { return h ? h->error.c_str() : "null handle"; }
+
+int apd_set_params(apd_handle* h, const apd_params* p) {
+  if (!h || !p) return APD_ERR_INVALID;
+  const bool cov_dep = p->k_correspondences != h->params.k_correspondences || p->regularization != h->params.regularization;
+  if (p->regularization < APD_REG_NONE || p->regularization > APD_REG_FROBENIUS) return fail(h, APD_ERR_INVALID, "bad regularization");
+  h->params = *p;
+  (void)cov_dep;  // reference: changing k / regularisation does NOT drop cached covariances either
+  return APD_OK;
+}
+int apd_get_params(const apd_handle* h, apd_params* out) {
+  if (!h || !out) return APD_ERR_INVALID;
+  *out = h->params;
+  return APD_OK;
+}
+
+int apd_set_source(apd_handle* h, const void* pts, int32_t n, int32_t stride, int32_t xyz_off, int32_t label_off, uint64_t key) {
+  if (!h) return APD_ERR_INVALID;
+  return set_cloud(h, h->src, pts, n, stride, xyz_off, label_off, key);
+}
+int apd_set_target(apd_handle* h, const void* pts, int32_t n, int32_t stride, int32_t xyz_off, int32_t label_off, uint64_t key) {
+  if (!h) return APD_ERR_INVALID;
+  return set_cloud(h, h->tgt, pts, n, stride, xyz_off, label_off, key);
+}
+int apd_set_source_device(apd_handle* h, const void* d, int32_t n) {
+  if (!h) return APD_ERR_INVALID;
+  return set_cloud_device(h, h->src, d, n);
+}
+int apd_set_target_device(apd_handle* h, const void* d, int32_t n) {
+  if (!h) return APD_ERR_INVALID;
+  return set_cloud_device(h, h->tgt, d, n);
+}
+
+int apd_swap_source_and_target(apd_handle* h) {  // :89-98
+  if (!h) return APD_ERR_INVALID;
+  std::swap(h->src, h->tgt);
+  h->corr_n = -1;  // correspondences_.clear()
+  return APD_OK;
+}
+int apd_clear_source(apd_handle* h) {  // :101-105
+  if (!h) return APD_ERR_INVALID;
+  h->src.present = false; h->src.n = 0; h->src.key = 0; h->src.ext_pts = nullptr;
+  h->src.grid_valid = h->src.cov_valid = h->src.geo_valid = false;
+  return APD_OK;
+}
+int apd_clear_target(apd_handle* h) {  // :108-112
+  if (!h) return APD_ERR_INVALID;
+  h->tgt.present = false; h->tgt.n = 0; h->tgt.key = 0; h->tgt.ext_pts = nullptr;
+  h->tgt.grid_valid = h->tgt.cov_valid = h->tgt.geo_valid = false;
+  return APD_OK;
+}
+
+int apd_set_source_covariances(apd_handle* h, const double* covs, int32_t n) { return h ? set_covs(h, h->src, covs, n) : APD_ERR_INVALID; }
+int apd_set_target_covariances(apd_handle* h, const double* covs, int32_t n) { return h ? set_covs(h, h->tgt, covs, n) : APD_ERR_INVALID; }
+int apd_get_source_covariances(apd_handle* h, double* covs, int32_t n) { return h ? get_covs(h, h->src, covs, n) : APD_ERR_INVALID; }
+int apd_get_target_covariances(apd_handle* h, double* covs, int32_t n) { return h ? get_covs(h, h->tgt, covs, n) : APD_ERR_INVALID; }
+
+int apd_get_neighbors(apd_handle* h, int32_t which, int32_t* out, int32_t n, int32_t k) {
+  if (!h || !out) return APD_ERR_INVALID;
+  Cloud& c = which == 0 ? h->src : h->tgt;
+  if (!c.present || n != c.n || k != h->params.k_correspondences) return fail(h, APD_ERR_INVALID, "neighbour query does not match the cloud / k");
+  if (k < 1 || k > 32) return fail(h, APD_ERR_UNSUPPORTED, "k_correspondences must be in [1, 32]");
+  if (c.n < k) return fail(h, APD_ERR_TOO_FEW, "cloud has fewer points than k_correspondences");
+  DeviceGuard dg(h->device);
+  int rc = ensure_grid(h, c);
+  if (rc != APD_OK) return rc;
+  const size_t nb_bytes = align_up((size_t)n * k * sizeof(int32_t), 256);
+  APD_CUDA(h, h->scratch.ensure(nb_bytes + (size_t)n * 6 * sizeof(double)));
+  CloudDev v = c.view();
+  v.cov = reinterpret_cast<double*>(h->scratch.as<char>() + nb_bytes);  // raw covariances go to scratch
+  launch_knn_cov(v, k, h->scratch.as<int32_t>(), h->stream, &h->launches);
+  APD_CUDA(h, cudaGetLastError());
+  APD_CUDA(h, cudaMemcpyAsync(out, h->scratch.p, (size_t)n * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int apd_align(apd_handle* h, const float* guess, float* T_out, double* T_out_f64, double* H_out, int32_t* converged,
+              int32_t* iterations, float* aligned_xyz) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  int rc = do_align(h, guess);
+  if (rc != APD_OK) return rc;
+  if (T_out) std::memcpy(T_out, h->final_T, sizeof(h->final_T));
+  if (T_out_f64)
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) T_out_f64[c * 4 + r] = h->final_pose(r, c);
+  if (H_out) std::memcpy(H_out, h->final_H, sizeof(h->final_H));
+  if (converged) *converged = h->converged ? 1 : 0;
+  if (iterations) *iterations = h->nr_iterations;
+  if (aligned_xyz) {  // pcl::transformPointCloud(*input_, output, final_transformation_) (lsq :79)
+    const size_t bytes = (size_t)h->src.n * 3 * sizeof(float);
+    APD_CUDA(h, h->scratch.ensure(bytes));
+    launch_transform_cloud(h->src.view().pts, h->src.n, colmajor_f32_to_pose_f(h->final_T), h->scratch.as<float>(), h->stream, &h->launches);
+    APD_CUDA(h, cudaMemcpyAsync(aligned_xyz, h->scratch.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  flush_prof(h);
+  return APD_OK;
+}
+
+int apd_linearize(apd_handle* h, const double* T, double* H, double* b, double* err) {
+  if (!h || !T || !err) return APD_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  int rc = ensure_covariances(h);
+  if (rc != APD_OK) return rc;
+  double Hr[36];
+  rc = do_linearize(h, hm::from_colmajor_f64(T), (H && b) ? Hr : nullptr, b, err);
+  if (rc == APD_OK && H && b) std::memcpy(H, Hr, sizeof(Hr));  // symmetric: row-major == column-major
+  flush_prof(h);
+  return rc;
+}
+
+int apd_compute_error(apd_handle* h, const double* T, double* err) {
+  if (!h || !T || !err) return APD_ERR_INVALID;
+  if (h->corr_n != h->src.n || !h->src.present) return fail(h, APD_ERR_INVALID, "compute_error needs a prior linearize on the same clouds");
+  DeviceGuard dg(h->device);
+  int rc = reduce_pass(h, hm::from_colmajor_f64(T), false, nullptr, nullptr, err);
+  flush_prof(h);
+  return rc;
+}
+
+int apd_update_correspondences(apd_handle* h, const double* T) {
+  if (!h || !T) return APD_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  int rc = ensure_covariances(h);
+  if (rc != APD_OK) return rc;
+  rc = do_update_correspondences(h, hm::from_colmajor_f64(T));
+  if (rc != APD_OK) return rc;
+  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  flush_prof(h);
+  return APD_OK;
+}
+
+int apd_get_correspondences(apd_handle* h, int32_t* idx, float* sq_dist, int32_t n) {
+  if (!h) return APD_ERR_INVALID;
+  if (h->corr_n != n || n != h->src.n) return fail(h, APD_ERR_INVALID, "no correspondences for this source cloud");
+  DeviceGuard dg(h->device);
+  const size_t ib = align_up((size_t)n * sizeof(int32_t), 256);
+  APD_CUDA(h, h->scratch.ensure(2 * ib));
+  int32_t* d_idx = h->scratch.as<int32_t>();
+  float* d_sq = reinterpret_cast<float*>(h->scratch.as<char>() + ib);
+  launch_corr_export(h->src.view(), h->tgt.view(), corr_view(h), d_idx, d_sq, nullptr, h->stream, &h->launches);
+  if (idx) APD_CUDA(h, cudaMemcpyAsync(idx, d_idx, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (sq_dist) APD_CUDA(h, cudaMemcpyAsync(sq_dist, d_sq, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int apd_get_mahalanobis(apd_handle* h, double* maha, int32_t n) {
+  if (!h || !maha) return APD_ERR_INVALID;
+  if (h->corr_n != n || n != h->src.n) return fail(h, APD_ERR_INVALID, "no correspondences for this source cloud");
+  DeviceGuard dg(h->device);
+  APD_CUDA(h, h->scratch.ensure((size_t)n * 16 * sizeof(double)));
+  launch_corr_export(h->src.view(), h->tgt.view(), corr_view(h), nullptr, nullptr, h->scratch.as<double>(), h->stream, &h->launches);
+  APD_CUDA(h, cudaMemcpyAsync(maha, h->scratch.p, (size_t)n * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int apd_fitness(apd_handle* h, const float* T, double max_range, double* score, int32_t* n_in_range, double inlier_sq_thr, int32_t* n_inliers) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  int rc = do_fitness(h, T, max_range, score, n_in_range, inlier_sq_thr, n_inliers);
+  flush_prof(h);
+  return rc;
+}
+
+int apd_get_lm_trace(apd_handle* h, double* rows, int32_t max_rows, int32_t* n_rows) {
+  if (!h || !rows || !n_rows) return APD_ERR_INVALID;
+  const int n = std::min<int>(max_rows, (int)(h->trace.size() / 8));
+  std::memcpy(rows, h->trace.data(), (size_t)n * 8 * sizeof(double));
+  *n_rows = n;
+  return APD_OK;
+}
+
+// ---- batched registrations ---------------------------------------------------
+int apd_align_batch(int device, const apd_params* p, const apd_pair* pairs, int32_t n_pairs, int32_t stride, int32_t xyz_off,
+                    int32_t label_off, int32_t n_streams, int32_t with_fitness, apd_result* results) {
+  if (!pairs || !results || n_pairs < 0) return APD_ERR_INVALID;
+  if (n_streams < 1) n_streams = 1;
+  if (n_streams > 32) n_streams = 32;
+  if (n_streams > n_pairs) n_streams = std::max(1, n_pairs);
+  std::vector<apd_handle*> hs(n_streams, nullptr);
+  for (int s = 0; s < n_streams; s++) {
+    int rc = apd_create(device, &hs[s]);
+    if (rc != APD_OK) {
+      for (auto* h : hs) apd_destroy(h);
+      return rc;
+    }
+    if (p) apd_set_params(hs[s], p);
+  }
+  std::atomic<int> next(0);
+  auto worker = [&](int s) {
+    cudaSetDevice(device);
+    apd_handle* h = hs[s];
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n_pairs) break;
+      const apd_pair& pr = pairs[i];
+      apd_result& r = results[i];
+      std::memset(&r, 0, sizeof(r));
+      // the reference benchmark protocol: clearTarget; clearSource; setInputTarget; setInputSource; align (align.cpp:57-83)
+      apd_clear_target(h);
+      apd_clear_source(h);
+      int rc = apd_set_target(h, pr.target, pr.n_target, stride, xyz_off, label_off, 0);
+      if (rc == APD_OK) rc = apd_set_source(h, pr.source, pr.n_source, stride, xyz_off, label_off, 0);
+      int32_t conv = 0, it = 0;
+      if (rc == APD_OK) rc = apd_align(h, pr.guess, r.T, nullptr, nullptr, &conv, &it, nullptr);
+      r.converged = conv;
+      r.iterations = it;
+      r.fitness = 0.0;
+      if (rc == APD_OK && with_fitness) rc = apd_fitness(h, nullptr, DBL_MAX, &r.fitness, nullptr, 0.25, &r.n_inliers);
+      r.status = rc;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int s = 0; s < n_streams; s++) th.emplace_back(worker, s);
+  for (auto& t : th) t.join();
+  for (auto* h : hs) apd_destroy(h);
+  return APD_OK;
+}
+
+// ---- source-sharded registration ------------------------------------------------
+int apd_comm_unique_id(void* id128) {
+  std::string err;
+  if (!id128 || !g_nccl.load(err)) return APD_ERR_COMM;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return APD_ERR_COMM;
+  std::memcpy(id128, &id, sizeof(id));
+  return APD_OK;
+}
+int apd_comm_init(apd_handle* h, const void* id128, int32_t rank, int32_t nranks, int64_t n_source_total) {
+  if (!h || !id128 || rank < 0 || rank >= nranks) return APD_ERR_INVALID;
+  if (!g_nccl.load(h->error)) return APD_ERR_COMM;
+  DeviceGuard dg(h->device);
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  ncclResult_t r = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+  if (r != 0) return fail(h, APD_ERR_COMM, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclCommInitRank failed");
+  h->comm_rank = rank;
+  h->comm_size = nranks;
+  h->n_source_total = n_source_total;
+  return APD_OK;
+}
+int apd_comm_destroy(apd_handle* h) {
+  if (!h) return APD_ERR_INVALID;
+  if (h->comm) {
+    DeviceGuard dg(h->device);
+    cudaStreamSynchronize(h->stream);
+    g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
+  h->comm_size = 1;
+  h->comm_rank = 0;
+  return APD_OK;
+}
+
+// ---- instrumentation -------------------------------------------------------------
+void* apd_stream(apd_handle* h) { return h ? (void*)h->stream : nullptr; }
+int64_t apd_launch_count(const apd_handle* h) { return h ? h->launches : 0; }
+int apd_set_profiling(apd_handle* h, int32_t enabled) {
+  if (!h) return APD_ERR_INVALID;
+  flush_prof(h);
+  h->profiling = enabled != 0;
+  for (int i = 0; i < APD_K_COUNT; i++) { h->k_ms[i] = 0; h->k_launches[i] = 0; }
+  return APD_OK;
+}
+int apd_get_kernel_ms(apd_handle* h, double* ms, int64_t* launches) {
+  if (!h) return APD_ERR_INVALID;
+  flush_prof(h);
+  for (int i = 0; i < APD_K_COUNT; i++) {
+    if (ms) ms[i] = h->k_ms[i];
+    if (launches) launches[i] = h->k_launches[i];
+  }
+  return APD_OK;
+}
+
+}  // extern "C"

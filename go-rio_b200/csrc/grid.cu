@@ -1,0 +1,250 @@
+// K0 — uniform-grid build: cell keys + per-cell counts, exclusive scan,
+// STABLE radix sort of (cell, original index) and the reorder into the
+// cell-sorted layout. Replaces the FLANN kd-tree build the reference does in
+// setInputSource / setInputTarget (fast_apdgicp_impl.hpp:121,132).
+// The sort is stable (ties keep original-index order) so the sorted layout — and
+// with it every later reduction order — is bit-deterministic.
+#include "kernels.cuh"
+
+namespace apd {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------- bounds ----
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(kThreads) bounds_kernel(const float4* __restrict__ pts, int n, unsigned int* __restrict__ out6) {
+  float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+    mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      atomicMin(&out6[a], f2ord(mn[a]));
+      atomicMax(&out6[3 + a], f2ord(mx[a]));
+    }
+  }
+}
+
+// ------------------------------------------------------------ keys/counts ----
+__global__ void __launch_bounds__(kThreads) cell_keys_kernel(const float4* __restrict__ pts, int n, GridDesc g,
+                                                             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                             uint32_t* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  const int cx = cell_coord(p.x, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(p.y, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(p.z, g.oz, g.inv_cell, g.nz);
+  const uint32_t key = (uint32_t)((cz * g.ny + cy) * g.nx + cx);
+  keys[i] = key;
+  vals[i] = (uint32_t)i;
+  atomicAdd(&counts[key], 1u);
+}
+
+// ------------------------------------------------------------------ scan ----
+// exclusive scan of 2048-element tiles; tile totals go to block_sums
+__global__ void __launch_bounds__(kThreads) scan_tiles_kernel(const uint32_t* in, uint32_t* out,  // may alias (in-place)
+                                                              size_t n, uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t warp_tot[kThreads / 32];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * 8;
+  uint32_t v[8];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    v[j] = (base + j < n) ? in[base + j] : 0u;
+    sum += v[j];
+  }
+  // inclusive warp scan of the per-thread sums
+  uint32_t inc = sum;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  uint32_t warp_off = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; w++) {
+    const uint32_t t = warp_tot[w];
+    if (w < warp) warp_off += t;
+    total += t;
+  }
+  uint32_t run = warp_off + inc - sum;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (base + j < n) out[base + j] = run;
+    run += v[j];
+  }
+  if (threadIdx.x == 0 && block_sums) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kThreads) scan_add_kernel(uint32_t* __restrict__ out, size_t n, const uint32_t* __restrict__ block_sums) {
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * 8;
+  const uint32_t off = block_sums[blockIdx.x];
+  if (off == 0) return;
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    if (base + j < n) out[base + j] += off;
+}
+
+void exclusive_scan(uint32_t* data, size_t n, uint32_t* tmp, cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  const size_t blocks = (n + kScanTile - 1) / kScanTile;
+  if (blocks == 1) {
+    scan_tiles_kernel<<<1, kThreads, 0, s>>>(data, data, n, nullptr);
+    (*launches)++;
+    return;
+  }
+  scan_tiles_kernel<<<(unsigned)blocks, kThreads, 0, s>>>(data, data, n, tmp);
+  (*launches)++;
+  exclusive_scan(tmp, blocks, tmp + blocks, s, launches);
+  scan_add_kernel<<<(unsigned)blocks, kThreads, 0, s>>>(data, n, tmp);
+  (*launches)++;
+}
+
+// ------------------------------------------------------------ radix sort ----
+__global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift,
+                                                              uint32_t* __restrict__ hist, int nblocks) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kSortTile;
+#pragma unroll
+  for (int j = 0; j < kSortTile / kThreads; j++) {
+    const int i = base + j * kThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n,
+                                                                 int shift, const uint32_t* __restrict__ hist_scanned, int nblocks) {
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kIters = kSortTile / kThreads;  // 8 iterations of 32 keys per warp
+  __shared__ uint32_t wcnt[kWarps][256];
+  for (int j = threadIdx.x; j < kWarps * 256; j += kThreads) (&wcnt[0][0])[j] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wbase = blockIdx.x * kSortTile + warp * (32 * kIters);
+  uint32_t key[kIters], val[kIters], rank[kIters];
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int it = 0; it < kIters; it++) {
+    const int i = wbase + it * 32 + lane;
+    const bool ok = i < n;
+    key[it] = ok ? keys_in[i] : 0xffffffffu;
+    val[it] = ok ? vals_in[i] : 0u;
+    const uint32_t d = ok ? ((key[it] >> shift) & 255u) : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    uint32_t before = 0;
+    if (ok) before = wcnt[warp][d];
+    __syncwarp();
+    rank[it] = before + __popc(peers & lt);
+    if (ok && (peers & lt) == 0) wcnt[warp][d] = before + __popc(peers);  // lowest lane of the peer group
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;  // 256 threads <-> 256 digits
+    uint32_t run = hist_scanned[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) {
+      const uint32_t t = wcnt[w][d];
+      wcnt[w][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kIters; it++) {
+    const int i = wbase + it * 32 + lane;
+    if (i < n) {
+      const uint32_t d = (key[it] >> shift) & 255u;
+      const uint32_t pos = wcnt[warp][d] + rank[it];
+      keys_out[pos] = key[it];
+      vals_out[pos] = val[it];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- reorder ----
+__global__ void __launch_bounds__(kThreads) reorder_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ vals, int n,
+                                                           float4* __restrict__ spts, float* __restrict__ label, int* __restrict__ inv_perm) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int idx = (int)vals[s];
+  const float4 p = pts[idx];
+  spts[s] = make_float4(p.x, p.y, p.z, __int_as_float(idx));
+  label[s] = p.w;
+  inv_perm[idx] = s;
+}
+
+}  // namespace
+
+size_t scan_tmp_elems_for(size_t n) {
+  size_t total = 0;
+  while (n > (size_t)kScanTile) {
+    n = (n + kScanTile - 1) / kScanTile;
+    total += n;
+  }
+  return total + 8;
+}
+
+void launch_bounds(const float4* pts, int n, float* d_out6, cudaStream_t s, int64_t* launches) {
+  // d_out6 is used as 6 ordered-uint32 slots; the caller decodes them
+  static const unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+  cudaMemcpyAsync(d_out6, init, sizeof(init), cudaMemcpyHostToDevice, s);
+  const int blocks = min(148 * 8, (n + kThreads - 1) / kThreads);
+  bounds_kernel<<<max(1, blocks), kThreads, 0, s>>>(pts, n, reinterpret_cast<unsigned int*>(d_out6));
+  (*launches)++;
+}
+
+void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int64_t* launches) {
+  const int n = c.n;
+  if (n <= 0) return;
+  cudaMemsetAsync(c.cell_start, 0, sizeof(uint32_t) * ((size_t)c.ncells + 1), s);
+  const int pblocks = (n + kThreads - 1) / kThreads;
+  cell_keys_kernel<<<pblocks, kThreads, 0, s>>>(c.pts, n, c.g, w.keys[0], w.vals[0], c.cell_start);
+  (*launches)++;
+  exclusive_scan(c.cell_start, (size_t)c.ncells + 1, w.scan_tmp, s, launches);
+
+  int bits = 1;
+  while ((1ll << bits) < (long long)c.ncells) bits++;
+  const int passes = (bits + 7) / 8;
+  const int sblocks = (n + kSortTile - 1) / kSortTile;
+  int cur = 0;
+  for (int p = 0; p < passes; p++) {
+    radix_hist_kernel<<<sblocks, kThreads, 0, s>>>(w.keys[cur], n, p * 8, w.hist, sblocks);
+    (*launches)++;
+    exclusive_scan(w.hist, (size_t)256 * sblocks, w.scan_tmp, s, launches);
+    radix_scatter_kernel<<<sblocks, kThreads, 0, s>>>(w.keys[cur], w.vals[cur], w.keys[cur ^ 1], w.vals[cur ^ 1], n, p * 8, w.hist, sblocks);
+    (*launches)++;
+    cur ^= 1;
+  }
+  reorder_kernel<<<pblocks, kThreads, 0, s>>>(c.pts, w.vals[cur], n, c.spts, c.label, c.inv_perm);
+  (*launches)++;
+}
+
+}  // namespace apd

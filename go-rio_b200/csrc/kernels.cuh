@@ -1,0 +1,95 @@
+// Host-callable launchers of the CUDA kernels (one translation unit per stage).
+#pragma once
+#include "common.cuh"
+
+namespace apd {
+
+// ---- grid.cu ---------------------------------------------------------------
+// Device view of one cloud (all arrays in cell-sorted order, see common.cuh).
+struct CloudDev {
+  int n = 0;
+  const float4* pts = nullptr;  // ORIGINAL order {x,y,z,label}
+  GridDesc g{};
+  int ncells = 0;
+  uint32_t* cell_start = nullptr;  // [ncells+1]
+  float4* spts = nullptr;          // [n] {x,y,z,bits(orig idx)}
+  float* label = nullptr;          // [n]
+  int* inv_perm = nullptr;         // [n] orig idx -> sorted pos
+  double* cov = nullptr;           // [n*6]
+  float* geo = nullptr;            // [n]
+  double* geo64 = nullptr;         // [n] same value unrounded (read when the Mahalanobis storage is fp64)
+};
+
+// scratch for the grid build (sized by grid_work_bytes, carved by the caller)
+struct GridWork {
+  uint32_t* keys[2];
+  uint32_t* vals[2];
+  uint32_t* hist;       // [256 * sort_blocks]
+  uint32_t* scan_tmp;   // block sums for the multi-level scan
+  size_t scan_tmp_elems;
+};
+constexpr int kSortTile = 2048;  // keys per block in the radix sort
+constexpr int kScanTile = 2048;  // elements per block in the scan
+size_t scan_tmp_elems_for(size_t n);
+
+// bounding box of a device-resident cloud: out6 = {minx,miny,minz,maxx,maxy,maxz}
+void launch_bounds(const float4* pts, int n, float* d_out6, cudaStream_t s, int64_t* launches);
+// keys/counts -> scan -> stable radix sort by cell -> reorder. Fills cell_start,
+// spts, label, inv_perm of `c` (c.pts, c.n, c.g, c.ncells must be set).
+void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int64_t* launches);
+
+// ---- knn_cov.cu --------------------------------------------------------------
+// exact kNN (k <= 32, ties by (d2, index)) + covariance of the k neighbours
+// (reference fast_apdgicp_impl.hpp:361-372), one warp per point; then the
+// regularisation (:374-405) and the geometric weight (:266-269), one thread per
+// point. neighbors: optional int32[n*k] in ORIGINAL point order / original ids.
+void launch_knn_cov(const CloudDev& c, int k, int32_t* neighbors, cudaStream_t s, int64_t* launches);
+void launch_regularize(const CloudDev& c, int regularization, cudaStream_t s, int64_t* launches);
+// geo weight only (after set*Covariances)
+void launch_geo_weight(const CloudDev& c, cudaStream_t s, int64_t* launches);
+// covariance layout conversion for the getters/setters: sorted sym6 <-> 4x4 col-major in original order
+void launch_cov_export(const CloudDev& c, double* d_out4x4, cudaStream_t s, int64_t* launches);
+void launch_cov_import(const CloudDev& c, const double* d_in4x4, cudaStream_t s, int64_t* launches);
+
+// ---- corr.cu -----------------------------------------------------------------
+struct NoiseParams {
+  double dist_var;      // distance_variance_
+  double sin_az;        // sin(azimuth_variance_ / 180 * pi)
+  double sin_el;        // sin(elevation_variance_ / 180 * pi)
+  double thr_sq;        // corr_dist_threshold_^2 (double product)
+  float search_limit;   // radius (m) beyond which no correspondence can pass the threshold; inf if none
+};
+struct CorrOut {
+  int* corr;      // [n_src] sorted order of the source
+  float* sqd;     // [n_src]
+  void* mahaA;    // float4[n] or double2[n] {xx,xy | ...} see common.cuh
+  void* mahaB;    // float2[n] or double2[2n]
+  int maha_fp64;
+};
+// reference update_correspondences (fast_apdgicp_impl.hpp:160-220)
+void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const NoiseParams& np,
+                                   const CorrOut& out, cudaStream_t s, int64_t* launches);
+// getFitnessScore + inlier count: d_out = {sum d2 (double), n_in_range (as double), n_inliers (as double)}
+void launch_fitness(const CloudDev& src, const CloudDev& tgt, const PoseF& T, double max_range, double inlier_sq_thr,
+                    double* d_partials, int max_blocks, double* d_out3, unsigned int* d_ticket, cudaStream_t s,
+                    int64_t* launches);
+// hooks: correspondences / mahalanobis back to original order and ids
+void launch_corr_export(const CloudDev& src, const CloudDev& tgt, const CorrOut& c, int32_t* d_idx, float* d_sqd,
+                        double* d_maha4x4, cudaStream_t s, int64_t* launches);
+// transformed source cloud in original order (pcl::transformPointCloud)
+void launch_transform_cloud(const float4* pts, int n, const PoseF& T, float* d_xyz, cudaStream_t s, int64_t* launches);
+
+// ---- linearize.cu --------------------------------------------------------------
+constexpr int kReduceVals = 28;  // 21 (upper H) + 6 (b) + 1 (err)
+struct ReduceWork {
+  double* partials;     // [max_blocks * 28]
+  unsigned int* ticket; // last-block-done counter (zeroed once; the kernel resets it)
+  int max_blocks;
+};
+// reference linearize (:247-304) / compute_error (:313-343) given the stored
+// correspondences and Mahalanobis matrices. out28 = 21 upper-triangular H
+// entries (row-major, r<=c), 6 b, 1 err. cl_weight = 1 / n_total.
+void launch_linearize(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const CorrOut& c, double n_total,
+                      bool want_hb, const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches);
+
+}  // namespace apd

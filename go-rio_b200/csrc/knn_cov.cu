@@ -1,0 +1,284 @@
+// K1/K2 — exact k-nearest-neighbour search on the uniform grid (one warp per
+// point) fused with the neighbourhood covariance, then regularisation and the
+// per-point geometric weight (one thread per point).
+// Replaces FastAPDGICP::calculate_covariances (reference
+// fast_apdgicp_impl.hpp:351-411) and hoists the loop-invariant JacobiSVD the
+// reference redoes per point in every linearize / compute_error (:266-269,
+// :330-333) to once per cloud.
+#include "kernels.cuh"
+
+namespace apd {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned long long kInfKey = 0xffffffffffffffffull;
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+  return __shfl_sync(kFull, v, src);
+}
+__device__ __forceinline__ unsigned long long shfl_up64(unsigned long long v, int d) {
+  return __shfl_up_sync(kFull, v, d);
+}
+
+// Warp-wide candidate scan. Every lane passes one segment [b, b+cnt) of the
+// cell-sorted point array (cnt may be 0). The segments are flattened so that
+// all 32 lanes test candidates even when segments are short (sparse cells).
+// The warp keeps the k best (d2, idx) keys sorted ascending, one per lane.
+__device__ __forceinline__ void scan_segments(const float4* __restrict__ spts, float qx, float qy, float qz, int lane, int k,
+                                              int b, int cnt, unsigned long long& mykey, unsigned long long& kth) {
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(kFull, incl, 31);
+  const int excl = incl - cnt;
+  for (int base = 0; base < total; base += 32) {
+    const int t = base + lane;
+    const bool valid = t < total;
+    const int tt = valid ? t : total - 1;
+    // segment containing flat index tt: first lane whose inclusive prefix > tt
+    int j = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(kFull, incl, j + step - 1);
+      if (v <= tt) j += step;
+    }
+    const int bj = __shfl_sync(kFull, b, j);
+    const int ej = __shfl_sync(kFull, excl, j);
+    const float4 p = spts[bj + (tt - ej)];
+    const float d2 = sqdist_rn(qx, qy, qz, p.x, p.y, p.z);
+    const unsigned long long key = pack_key(d2, __float_as_int(p.w));
+    unsigned mask = __ballot_sync(kFull, valid && key < kth);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const unsigned long long ck = shfl64(key, src);
+      if (ck < kth) {  // warp-uniform
+        const int pos = __popc(__ballot_sync(kFull, mykey < ck));
+        const unsigned long long up = shfl_up64(mykey, 1);
+        if (lane < k) {
+          if (lane > pos) mykey = up;
+          else if (lane == pos) mykey = ck;
+        }
+        kth = shfl64(mykey, k - 1);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) knn_cov_kernel(const float4* __restrict__ spts, const float4* __restrict__ pts,
+                                                           const uint32_t* __restrict__ cell_start, GridDesc g, int n, int k,
+                                                           double* __restrict__ cov, int32_t* __restrict__ neighbors) {
+  const int w = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const float4 q = spts[w];
+  const int qi = __float_as_int(q.w);
+  const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz);
+
+  unsigned long long mykey = kInfKey, kth = kInfKey;
+
+  // ring 0+1: the 3x3x3 cube as 9 x-rows
+  {
+    int b = 0, cnt = 0;
+    if (lane < 9) {
+      const int y = cy + (lane % 3) - 1, z = cz + (lane / 3) - 1;
+      if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+        const int row = (z * g.ny + y) * g.nx;
+        b = (int)cell_start[row + x0];
+        cnt = (int)cell_start[row + x1 + 1] - b;
+      }
+    }
+    scan_segments(spts, q.x, q.y, q.z, lane, k, b, cnt, mykey, kth);
+  }
+  // shells r = 2, 3, ... until the k-th distance is provably final:
+  // every unscanned point is at least (r - 0.002) cells away.
+  for (int r = 1;; r++) {
+    const float lb = ((float)r - 0.002f) * g.cell;
+    const float kd2 = __uint_as_float((unsigned)(kth >> 32));
+    if (kth != kInfKey && kd2 < lb * lb) break;
+    if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
+    const int rr = r + 1;  // shell to scan now
+    const int side = 2 * rr + 1;
+    const int nslots = 2 * side * side;
+    for (int sbase = 0; sbase < nslots; sbase += 32) {
+      const int slot = sbase + lane;
+      int b = 0, cnt = 0;
+      if (slot < nslots) {
+        const int rowid = slot >> 1, which = slot & 1;
+        const int dy = rowid % side - rr, dz = rowid / side - rr;
+        const int y = cy + dy, z = cz + dz;
+        if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+          const bool border = (dy == rr) || (dy == -rr) || (dz == rr) || (dz == -rr);
+          const int row = (z * g.ny + y) * g.nx;
+          int x0 = 1, x1 = 0;
+          if (border) {
+            if (which == 0) { x0 = max(cx - rr, 0); x1 = min(cx + rr, g.nx - 1); }
+          } else {
+            const int x = which == 0 ? cx - rr : cx + rr;
+            if (x >= 0 && x < g.nx) { x0 = x; x1 = x; }
+          }
+          if (x0 <= x1) {
+            b = (int)cell_start[row + x0];
+            cnt = (int)cell_start[row + x1 + 1] - b;
+          }
+        }
+      }
+      if (__ballot_sync(kFull, cnt > 0)) scan_segments(spts, q.x, q.y, q.z, lane, k, b, cnt, mykey, kth);
+    }
+  }
+
+  // covariance of the k neighbours (reference :366-372): fp64, centred, / k
+  const int nidx = (lane < k) ? (int)(unsigned)(mykey & 0xffffffffull) : 0;
+  if (neighbors && lane < k) neighbors[(size_t)qi * k + lane] = nidx;
+  double x = 0.0, y = 0.0, z = 0.0;
+  if (lane < k) {
+    const float4 p = pts[nidx];
+    x = (double)p.x; y = (double)p.y; z = (double)p.z;
+  }
+  const double inv_k = 1.0 / (double)k;
+  const double mx = warp_sum(x) / (double)k, my = warp_sum(y) / (double)k, mz = warp_sum(z) / (double)k;
+  (void)inv_k;
+  double dx = 0.0, dy = 0.0, dz = 0.0;
+  if (lane < k) { dx = x - mx; dy = y - my; dz = z - mz; }
+  const double cxx = warp_sum(dx * dx) / (double)k;
+  const double cxy = warp_sum(dx * dy) / (double)k;
+  const double cxz = warp_sum(dx * dz) / (double)k;
+  const double cyy = warp_sum(dy * dy) / (double)k;
+  const double cyz = warp_sum(dy * dz) / (double)k;
+  const double czz = warp_sum(dz * dz) / (double)k;
+  if (lane < 6) {
+    const double v = lane == 0 ? cxx : lane == 1 ? cxy : lane == 2 ? cxz : lane == 3 ? cyy : lane == 4 ? cyz : czz;
+    cov[(size_t)w * 6 + lane] = v;
+  }
+}
+
+__device__ __forceinline__ double geo_weight_of(const Sym3& C) {
+  double l[3], V[9];
+  jacobi_eig3(C, l, V);
+  return fabs(l[2]) / fabs(l[0]);  // sigma3 / sigma1 (reference :268-269)
+}
+
+__global__ void __launch_bounds__(kThreads) regularize_kernel(double* __restrict__ cov, float* __restrict__ geo, double* __restrict__ geo64, int n, int reg) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  Sym3 C;
+#pragma unroll
+  for (int e = 0; e < 6; e++) C.v[e] = cov[(size_t)i * 6 + e];
+  Sym3 out = C;
+  if (reg == 0) {  // NONE (:374-376)
+  } else if (reg == 4) {  // FROBENIUS (:377-383)
+    Sym3 Cl = C;
+    Cl.v[0] += 1e-3; Cl.v[3] += 1e-3; Cl.v[5] += 1e-3;
+    Sym3 Ci = sym_inverse(Cl);
+    const double nrm = sqrt(Ci.v[0] * Ci.v[0] + Ci.v[3] * Ci.v[3] + Ci.v[5] * Ci.v[5] +
+                            2.0 * (Ci.v[1] * Ci.v[1] + Ci.v[2] * Ci.v[2] + Ci.v[4] * Ci.v[4]));
+#pragma unroll
+    for (int e = 0; e < 6; e++) Ci.v[e] /= nrm;
+    out = sym_inverse(Ci);
+  } else {  // SVD-based (:384-407); symmetric PSD input, so U = V up to the sign of negative eigenvalues
+    double l[3], V[9];
+    jacobi_eig3(C, l, V);
+    double val[3], sg[3];
+#pragma unroll
+    for (int e = 0; e < 3; e++) sg[e] = l[e] < 0.0 ? -1.0 : 1.0;
+    const double s0 = fabs(l[0]);
+    if (reg == 3) { val[0] = 1.0; val[1] = 1.0; val[2] = 1e-3; }                                   // PLANE
+    else if (reg == 1) { for (int e = 0; e < 3; e++) val[e] = fmax(fabs(l[e]), 1e-3); }              // MIN_EIG
+    else { for (int e = 0; e < 3; e++) val[e] = fmax(fabs(l[e]) / s0, 1e-3); }                       // NORMALIZED_MIN_EIG
+    // U diag(val) V^T with U = V * diag(sg); stored symmetric (upper triangle)
+    const int R[6] = {0, 0, 0, 1, 1, 2}, Cc[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+    for (int e = 0; e < 6; e++) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < 3; j++) s += sg[j] * V[R[e] * 3 + j] * val[j] * V[Cc[e] * 3 + j];
+      out.v[e] = s;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 6; e++) cov[(size_t)i * 6 + e] = out.v[e];
+  const double gw = geo_weight_of(out);
+  geo[i] = (float)gw;
+  geo64[i] = gw;
+}
+
+__global__ void __launch_bounds__(kThreads) geo_weight_kernel(const double* __restrict__ cov, float* __restrict__ geo, double* __restrict__ geo64, int n) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  Sym3 C;
+#pragma unroll
+  for (int e = 0; e < 6; e++) C.v[e] = cov[(size_t)i * 6 + e];
+  const double gw = geo_weight_of(C);
+  geo[i] = (float)gw;
+  geo64[i] = gw;
+}
+
+// sorted sym6 -> column-major 4x4 (128 B) at the ORIGINAL index
+__global__ void __launch_bounds__(kThreads) cov_export_kernel(const double* __restrict__ cov, const float4* __restrict__ spts, int n,
+                                                              double* __restrict__ out) {
+  const int s = blockIdx.x * kThreads + threadIdx.x;
+  if (s >= n) return;
+  const int idx = __float_as_int(spts[s].w);
+  const double* c = cov + (size_t)s * 6;
+  double* o = out + (size_t)idx * 16;
+  o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = 0.0;
+  o[4] = c[1]; o[5] = c[3]; o[6] = c[4]; o[7] = 0.0;
+  o[8] = c[2]; o[9] = c[4]; o[10] = c[5]; o[11] = 0.0;
+  o[12] = 0.0; o[13] = 0.0; o[14] = 0.0; o[15] = 0.0;
+}
+
+// column-major 4x4 at the original index -> sorted sym6 (symmetrised)
+__global__ void __launch_bounds__(kThreads) cov_import_kernel(const double* __restrict__ in, const float4* __restrict__ spts, int n,
+                                                              double* __restrict__ cov) {
+  const int s = blockIdx.x * kThreads + threadIdx.x;
+  if (s >= n) return;
+  const int idx = __float_as_int(spts[s].w);
+  const double* m = in + (size_t)idx * 16;
+  double* c = cov + (size_t)s * 6;
+  c[0] = m[0];
+  c[1] = 0.5 * (m[1] + m[4]);
+  c[2] = 0.5 * (m[2] + m[8]);
+  c[3] = m[5];
+  c[4] = 0.5 * (m[6] + m[9]);
+  c[5] = m[10];
+}
+
+}  // namespace
+
+void launch_knn_cov(const CloudDev& c, int k, int32_t* neighbors, cudaStream_t s, int64_t* launches) {
+  if (c.n <= 0) return;
+  const long long threads = (long long)c.n * 32;
+  const int blocks = (int)((threads + kThreads - 1) / kThreads);
+  knn_cov_kernel<<<blocks, kThreads, 0, s>>>(c.spts, c.pts, c.cell_start, c.g, c.n, k, c.cov, neighbors);
+  (*launches)++;
+}
+void launch_regularize(const CloudDev& c, int regularization, cudaStream_t s, int64_t* launches) {
+  if (c.n <= 0) return;
+  regularize_kernel<<<(c.n + kThreads - 1) / kThreads, kThreads, 0, s>>>(c.cov, c.geo, c.geo64, c.n, regularization);
+  (*launches)++;
+}
+void launch_geo_weight(const CloudDev& c, cudaStream_t s, int64_t* launches) {
+  if (c.n <= 0) return;
+  geo_weight_kernel<<<(c.n + kThreads - 1) / kThreads, kThreads, 0, s>>>(c.cov, c.geo, c.geo64, c.n);
+  (*launches)++;
+}
+void launch_cov_export(const CloudDev& c, double* d_out4x4, cudaStream_t s, int64_t* launches) {
+  if (c.n <= 0) return;
+  cov_export_kernel<<<(c.n + kThreads - 1) / kThreads, kThreads, 0, s>>>(c.cov, c.spts, c.n, d_out4x4);
+  (*launches)++;
+}
+void launch_cov_import(const CloudDev& c, const double* d_in4x4, cudaStream_t s, int64_t* launches) {
+  if (c.n <= 0) return;
+  cov_import_kernel<<<(c.n + kThreads - 1) / kThreads, kThreads, 0, s>>>(d_in4x4, c.spts, c.n, c.cov);
+  (*launches)++;
+}
+
+}  // namespace apd

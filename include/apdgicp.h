@@ -36,6 +36,12 @@ extern "C" {
 
 #define APD_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define APD_API __attribute__((visibility("default")))
+#else
+#define APD_API
+#endif
+
 /* status codes */
 enum {
   APD_OK = 0,
@@ -87,17 +93,17 @@ typedef struct apd_params {
 typedef struct apd_handle apd_handle;
 
 /* ---- life cycle ------------------------------------------------------- */
-int apd_abi_version(void);
-int apd_default_params(apd_params* out);
+APD_API int apd_abi_version(void);
+APD_API int apd_default_params(apd_params* out);
 /* reference FastAPDGICP::FastAPDGICP (fast_apdgicp_impl.hpp:14-28) */
-int apd_create(int device, apd_handle** out);
-int apd_destroy(apd_handle* h);
+APD_API int apd_create(int device, apd_handle** out);
+APD_API int apd_destroy(apd_handle* h);
 /* text of the last error on this handle ("" if none). Never NULL. */
-const char* apd_last_error(const apd_handle* h);
+APD_API const char* apd_last_error(const apd_handle* h);
 /* setters of fast_apdgicp_impl.hpp:34-65 + lsq_registration_impl.hpp:30-42 +
  * the pcl::Registration setters used by registrations.cpp:41-48 */
-int apd_set_params(apd_handle* h, const apd_params* p);
-int apd_get_params(const apd_handle* h, apd_params* out);
+APD_API int apd_set_params(apd_handle* h, const apd_params* p);
+APD_API int apd_get_params(const apd_handle* h, apd_params* out);
 
 /* ---- clouds ----------------------------------------------------------- */
 /* reference setInputSource / setInputTarget (fast_apdgicp_impl.hpp:115-135).
@@ -109,31 +115,31 @@ int apd_get_params(const apd_handle* h, apd_params* out);
  * cache_key: the reference early-outs on pointer identity (:116,:128); pass
  * the cloud pointer value (or any id); 0 disables the early-out. Setting a
  * cloud drops its cached covariances. */
-int apd_set_source(apd_handle* h, const void* pts, int32_t n, int32_t stride_bytes,
+APD_API int apd_set_source(apd_handle* h, const void* pts, int32_t n, int32_t stride_bytes,
                    int32_t xyz_off, int32_t label_off, uint64_t cache_key);
-int apd_set_target(apd_handle* h, const void* pts, int32_t n, int32_t stride_bytes,
+APD_API int apd_set_target(apd_handle* h, const void* pts, int32_t n, int32_t stride_bytes,
                    int32_t xyz_off, int32_t label_off, uint64_t cache_key);
 /* same, but the cloud is already on the device as float4 {x,y,z,label}[n]
  * (no reference equivalent; used for HBM-resident benchmarking and sharding) */
-int apd_set_source_device(apd_handle* h, const void* d_xyzl, int32_t n);
-int apd_set_target_device(apd_handle* h, const void* d_xyzl, int32_t n);
+APD_API int apd_set_source_device(apd_handle* h, const void* d_xyzl, int32_t n);
+APD_API int apd_set_target_device(apd_handle* h, const void* d_xyzl, int32_t n);
 
 /* reference swapSourceAndTarget / clearSource / clearTarget (:89-112) */
-int apd_swap_source_and_target(apd_handle* h);
-int apd_clear_source(apd_handle* h);
-int apd_clear_target(apd_handle* h);
+APD_API int apd_swap_source_and_target(apd_handle* h);
+APD_API int apd_clear_source(apd_handle* h);
+APD_API int apd_clear_target(apd_handle* h);
 
 /* reference set/get{Source,Target}Covariances (:138-145, hpp:73-79):
  * n column-major 4x4 doubles (128 B each). Getters compute the covariances
  * first if they are stale (the reference getter would return an empty vector
  * before the first align; computing is a superset). */
-int apd_set_source_covariances(apd_handle* h, const double* covs4x4, int32_t n);
-int apd_set_target_covariances(apd_handle* h, const double* covs4x4, int32_t n);
-int apd_get_source_covariances(apd_handle* h, double* covs4x4, int32_t n);
-int apd_get_target_covariances(apd_handle* h, double* covs4x4, int32_t n);
+APD_API int apd_set_source_covariances(apd_handle* h, const double* covs4x4, int32_t n);
+APD_API int apd_set_target_covariances(apd_handle* h, const double* covs4x4, int32_t n);
+APD_API int apd_get_source_covariances(apd_handle* h, double* covs4x4, int32_t n);
+APD_API int apd_get_target_covariances(apd_handle* h, double* covs4x4, int32_t n);
 /* parity hook: the k neighbour indices of every point, ordered by (d2, index);
  * out is int32[n*k]. which: 0 source, 1 target. */
-int apd_get_neighbors(apd_handle* h, int32_t which, int32_t* out, int32_t n, int32_t k);
+APD_API int apd_get_neighbors(apd_handle* h, int32_t which, int32_t* out, int32_t n, int32_t k);
 
 /* ---- the hot path ----------------------------------------------------- */
 /* pcl::Registration::align(output, guess) -> FastAPDGICP::computeTransformation
@@ -146,38 +152,38 @@ int apd_get_neighbors(apd_handle* h, int32_t which, int32_t* out, int32_t n, int
  * outer iteration, as the reference sets it at :68) — optional.
  * aligned_xyz: optional float[3*n_source], the transformed source cloud
  * (pcl::transformPointCloud at :79), packed xyz. */
-int apd_align(apd_handle* h, const float* guess, float* T_out, double* T_out_f64,
+APD_API int apd_align(apd_handle* h, const float* guess, float* T_out, double* T_out_f64,
               double* H_out, int32_t* converged, int32_t* iterations, float* aligned_xyz);
 
 /* FastAPDGICP::linearize (:224-307) incl. update_correspondences (:160-220);
  * T: double[16] column-major. H (36), b (6) may both be NULL (error only).
  * Equivalent to LsqRegistration::evaluateCost when T comes from a float pose.
  * Computes stale covariances first, as align does. */
-int apd_linearize(apd_handle* h, const double* T, double* H, double* b, double* err);
+APD_API int apd_linearize(apd_handle* h, const double* T, double* H, double* b, double* err);
 /* FastAPDGICP::compute_error (:310-346): uses the correspondences and
  * Mahalanobis matrices of the LAST linearize. */
-int apd_compute_error(apd_handle* h, const double* T, double* err);
+APD_API int apd_compute_error(apd_handle* h, const double* T, double* err);
 /* FastAPDGICP::update_correspondences (:160-220) alone. */
-int apd_update_correspondences(apd_handle* h, const double* T);
+APD_API int apd_update_correspondences(apd_handle* h, const double* T);
 /* parity hook: correspondences_ (int32[n], -1 = none) and sq_distances_
  * (float[n]); either may be NULL. */
-int apd_get_correspondences(apd_handle* h, int32_t* idx, float* sq_dist, int32_t n);
+APD_API int apd_get_correspondences(apd_handle* h, int32_t* idx, float* sq_dist, int32_t n);
 /* parity hook: mahalanobis_ as n column-major 4x4 doubles */
-int apd_get_mahalanobis(apd_handle* h, double* maha4x4, int32_t n);
+APD_API int apd_get_mahalanobis(apd_handle* h, double* maha4x4, int32_t n);
 
 /* pcl::Registration::getFitnessScore(max_range) [PCL 1.10 registration.hpp]
  * over final_transformation_ (or T if not NULL, float[16]); also returns the
  * number of points with d2 <= max_range, and — for the status message of
  * scan_matching_odometry_nodelet.cpp:677-689 — the number of points whose
  * 1-NN squared distance is < inlier_sq_thr. */
-int apd_fitness(apd_handle* h, const float* T, double max_range, double* score,
+APD_API int apd_fitness(apd_handle* h, const float* T, double max_range, double* score,
                 int32_t* n_in_range, double inlier_sq_thr, int32_t* n_inliers);
 
 /* LM trace of the last apd_align: rows of {outer, inner, y0, yi, rho, lambda,
  * |d|, accepted} as 8 doubles, the columns of the reference's lm_debug_print_
  * table (lsq_registration_impl.hpp:148-154). Returns the number of rows
  * written (<= max_rows) in *n_rows. */
-int apd_get_lm_trace(apd_handle* h, double* rows, int32_t max_rows, int32_t* n_rows);
+APD_API int apd_get_lm_trace(apd_handle* h, double* rows, int32_t max_rows, int32_t* n_rows);
 
 /* ---- batched registrations (config C3; no reference equivalent: the loop
  * detector runs candidates serially, loop_detector.cpp:222-236) ---------- */
@@ -201,7 +207,7 @@ typedef struct apd_result {
 /* Runs n_pairs independent clear/set/align sequences on `device`, pipelined
  * over `n_streams` internal handles (H2D of pair i+1 overlaps the kernels of
  * pair i). */
-int apd_align_batch(int device, const apd_params* p, const apd_pair* pairs, int32_t n_pairs,
+APD_API int apd_align_batch(int device, const apd_params* p, const apd_pair* pairs, int32_t n_pairs,
                     int32_t stride_bytes, int32_t xyz_off, int32_t label_off,
                     int32_t n_streams, int32_t with_fitness, apd_result* results);
 
@@ -211,18 +217,18 @@ int apd_align_batch(int device, const apd_params* p, const apd_pair* pairs, int3
  * linearize / compute_error all-reduce their 28 / 1 doubles over NCCL, and
  * cl_weight uses n_source_total (reference: 1/correspondences_.size(),
  * fast_apdgicp_impl.hpp:273). id128 is an ncclUniqueId (128 bytes). */
-int apd_comm_unique_id(void* id128);
-int apd_comm_init(apd_handle* h, const void* id128, int32_t rank, int32_t nranks,
+APD_API int apd_comm_unique_id(void* id128);
+APD_API int apd_comm_init(apd_handle* h, const void* id128, int32_t rank, int32_t nranks,
                   int64_t n_source_total);
-int apd_comm_destroy(apd_handle* h);
+APD_API int apd_comm_destroy(apd_handle* h);
 
 /* ---- instrumentation --------------------------------------------------- */
 /* CUDA stream of the handle (cudaStream_t as void*), for event timing. */
-void* apd_stream(apd_handle* h);
+APD_API void* apd_stream(apd_handle* h);
 /* Kernel launches issued by this handle since creation (bench.py's
  * gpu_launches), and device milliseconds of the last call per kernel class
  * (CUDA events, only recorded when profiling is enabled). */
-int64_t apd_launch_count(const apd_handle* h);
+APD_API int64_t apd_launch_count(const apd_handle* h);
 enum {
   APD_K_GRID = 0,      /* grid build (bounds, count, scan, scatter)          */
   APD_K_KNN_COV = 1,   /* exact kNN + covariance + regularisation            */
@@ -232,8 +238,8 @@ enum {
   APD_K_FITNESS = 5,
   APD_K_COUNT = 6
 };
-int apd_set_profiling(apd_handle* h, int32_t enabled);
-int apd_get_kernel_ms(apd_handle* h, double* ms /* [APD_K_COUNT] */, int64_t* launches /* [APD_K_COUNT] */);
+APD_API int apd_set_profiling(apd_handle* h, int32_t enabled);
+APD_API int apd_get_kernel_ms(apd_handle* h, double* ms /* [APD_K_COUNT] */, int64_t* launches /* [APD_K_COUNT] */);
 
 #ifdef __cplusplus
 }

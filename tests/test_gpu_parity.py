@@ -1,0 +1,398 @@
+"""GPU parity tests: the CUDA library (through its C-ABI) against the CPU oracle
+on identical seeded inputs. Bars: bit-exact neighbour indices and
+correspondences; covariances <= 1e-9 abs where the normal is well conditioned;
+H / b / err within 1e-10 relative (fp64 Mahalanobis storage) or 1e-6 (fp32
+storage; north_star's bar is 1e-5); pose within 1e-6 m / 1e-6 rad; equal
+convergence flag and iteration counts."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import DEPLOYED, moved_copy, pose_err, rel
+from oracle_binding import Oracle
+
+pytestmark = pytest.mark.gpu
+
+REGS = {"NONE": 0, "MIN_EIG": 1, "NORMALIZED_MIN_EIG": 2, "PLANE": 3, "FROBENIUS": 4}
+
+
+def make(gorio, src, tgt, **kw):
+    g = gorio.FastAPDGICP(0)
+    o = Oracle(search=1)
+    g.set_params(**kw)
+    o.set_params(**kw)
+    for r in (g, o):
+        r.set_input_target(tgt)
+        r.set_input_source(src)
+    return g, o
+
+
+@pytest.fixture(scope="module")
+def c1(synth):
+    return synth.scan_pair(1000, 1000)
+
+
+@pytest.fixture(scope="module")
+def c2(synth):
+    return synth.submap_pair(2000)
+
+
+@pytest.fixture(scope="module")
+def c2_small(synth):
+    return synth.submap_pair(2001, n_source=800, n_frames=6, n_per_frame=1500)
+
+
+# ---------------------------------------------------------------- kNN ----
+@pytest.mark.parametrize("k", [1, 5, 20, 32])
+def test_knn_indices_bit_exact(gorio, c1, k):
+    src, tgt, _ = c1
+    g, o = make(gorio, src, tgt, k_correspondences=k)
+    o.get_source_covariances(); o.get_target_covariances()
+    for which in (0, 1):
+        assert np.array_equal(g.get_neighbors(which), o.get_neighbors(which))
+
+
+def test_knn_indices_bit_exact_submap(gorio, c2):
+    src, tgt, _ = c2
+    g, o = make(gorio, src, tgt)
+    o.get_target_covariances()
+    assert np.array_equal(g.get_neighbors(1), o.get_neighbors(1))
+
+
+def test_knn_clustered_and_degenerate_geometry(gorio):
+    """dense blob + far outliers + a coplanar sheet + a collinear run: ring expansion and tie handling"""
+    rng = np.random.default_rng(7)
+    blob = rng.normal(0, 0.05, (3000, 3))
+    far = rng.uniform(-400, 400, (40, 3))
+    sheet = np.stack([rng.uniform(0, 10, 500), rng.uniform(0, 10, 500), np.full(500, 3.0)], axis=1)
+    line = np.stack([np.arange(100) * 0.25, np.zeros(100), np.zeros(100)], axis=1) + 20.0  # exact distance ties
+    xyz = np.concatenate([blob, far, sheet, line]).astype(np.float32)
+    xyz = np.unique(xyz, axis=0)
+    rng.shuffle(xyz)
+    cloud = np.concatenate([xyz, np.zeros((xyz.shape[0], 1), np.float32)], axis=1)
+    g, o = make(gorio, cloud[:500], cloud)
+    o.get_target_covariances()
+    assert np.array_equal(g.get_neighbors(1), o.get_neighbors(1))
+
+
+# --------------------------------------------------------- covariances ----
+@pytest.mark.parametrize("reg", list(REGS))
+def test_covariances(gorio, c1, reg):
+    src, tgt, _ = c1
+    g, o = make(gorio, src, tgt, regularization=REGS[reg])
+    Cg, Co = g.get_target_covariances(), o.get_target_covariances()
+    assert np.abs(Cg[:, 3, :]).max() == 0 and np.abs(Cg[:, :, 3]).max() == 0
+    if reg in ("PLANE", "MIN_EIG", "NORMALIZED_MIN_EIG"):
+        o2 = Oracle(search=1); o2.set_params(regularization=0); o2.set_input_target(tgt); o2.set_input_source(src)
+        S = np.linalg.svd(o2.get_target_covariances()[:, :3, :3], compute_uv=False)
+        ok = (S[:, 1] - S[:, 2]) / S[:, 0] > 1e-6
+        assert ok.mean() > 0.99
+        assert np.abs(Cg[ok] - Co[ok]).max() < 1e-9
+    else:
+        assert rel(Cg, Co) < 1e-12
+    # symmetric storage
+    assert np.abs(Cg - Cg.transpose(0, 2, 1)).max() == 0
+
+
+def test_set_get_covariances_roundtrip(gorio, c1):
+    src, tgt, _ = c1
+    g, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(src.shape[0], 3, 3))
+    C = np.zeros((src.shape[0], 4, 4))
+    C[:, :3, :3] = A @ A.transpose(0, 2, 1) + 0.05 * np.eye(3)
+    for r in (g, o):
+        r.set_source_covariances(C)
+    assert np.abs(g.get_source_covariances() - C).max() < 1e-15
+    T = np.eye(4)
+    eg, Hg, bg = g.linearize(T)
+    eo, Ho, bo = o.linearize(T)
+    assert abs(eg - eo) / eo < 1e-10 and rel(Hg, Ho) < 1e-10 and rel(bg, bo) < 1e-9
+
+
+# ----------------------------------------------- correspondences, H, b ----
+POSES = [
+    ([0, 0, 0], [0, 0, 0]),
+    ([0.3, -0.2, 0.05], [0.2, -0.3, 1.5]),
+    ([-1.5, 2.0, 0.3], [1.0, 2.0, -8.0]),
+    ([40.0, -30.0, 5.0], [0.0, 0.0, 90.0]),  # mostly outside the target's bounding box
+]
+
+
+@pytest.mark.parametrize("fp64", [1, 0])
+@pytest.mark.parametrize("pose", range(len(POSES)))
+@pytest.mark.parametrize("thr", [2.0, None])
+def test_linearize_parity(gorio, synth, c1, pose, thr, fp64):
+    src, tgt, _ = c1
+    kw = dict(maha_fp64=fp64)
+    if thr is not None:
+        kw["max_correspondence_distance"] = thr
+    g, o = make(gorio, src, tgt, **kw)
+    t, rpy = POSES[pose]
+    T = synth.make_pose(t, np.deg2rad(rpy))
+    eg, Hg, bg = g.linearize(T)
+    eo, Ho, bo = o.linearize(T)
+    cg, sg = g.get_correspondences()
+    co, so = o.get_correspondences()
+    assert np.array_equal(cg, co)                      # bit-exact, including -1
+    assert np.array_equal(sg[co >= 0], so[co >= 0])    # fp32 d2 bit-exact where matched
+    if thr is None:
+        assert (co >= 0).all()
+    if (co >= 0).sum() == 0:
+        assert eg == 0.0 and np.abs(Hg).max() == 0.0
+        return
+    tol = 1e-10 if fp64 else 1e-6
+    assert rel(g.get_mahalanobis(), o.get_mahalanobis()) < (1e-9 if fp64 else 2e-7)
+    assert abs(eg - eo) / abs(eo) < tol
+    assert rel(Hg, Ho) < tol
+    assert rel(bg, bo) < (tol * 10)
+    assert np.array_equal(Hg, Hg.T)
+    # compute_error at trial poses keeps the stale correspondences / Mahalanobis
+    for d in ([0.02, 0, 0], [0, -0.05, 0.01]):
+        T2 = synth.make_pose(d, [0, 0, 0.002]) @ T
+        assert abs(g.compute_error(T2) - o.compute_error(T2)) / abs(o.compute_error(T2)) < tol
+    # err-only linearize (H == nullptr, :278-280)
+    assert abs(g.linearize(T, want_hb=False) - eo) / abs(eo) < tol
+
+
+def test_linearize_parity_submap(gorio, synth, c2):
+    src, tgt, Tgt = c2
+    g, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+    for T in (np.eye(4), Tgt):
+        eg, Hg, bg = g.linearize(T)
+        eo, Ho, bo = o.linearize(T)
+        assert np.array_equal(g.get_correspondences()[0], o.get_correspondences()[0])
+        assert abs(eg - eo) / eo < 1e-10 and rel(Hg, Ho) < 1e-10 and rel(bg, bo) < 1e-9
+
+
+def test_cluster_label_weight(gorio, synth, c1):
+    """cl_weight = 1/N when source.normal_x == target.normal_x (:271-273)"""
+    src, tgt, _ = c1
+    s2 = src.copy(); s2[:, 3] = -5.0  # no label ever matches
+    g, o = make(gorio, s2, tgt, **DEPLOYED, maha_fp64=1)
+    g2, o2 = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+    e_none, e_lab = g.linearize(np.eye(4), want_hb=False), g2.linearize(np.eye(4), want_hb=False)
+    assert e_lab > e_none
+    assert abs(e_none - o.linearize(np.eye(4), want_hb=False)) / e_none < 1e-10
+    assert abs(e_lab - o2.linearize(np.eye(4), want_hb=False)) / e_lab < 1e-10
+
+
+def test_linearize_is_bit_deterministic(gorio, c2_small):
+    src, tgt, _ = c2_small
+    outs = []
+    for _ in range(3):
+        g = gorio.FastAPDGICP(0)
+        g.set_params(**DEPLOYED)
+        g.set_input_target(tgt); g.set_input_source(src)
+        e, H, b = g.linearize(np.eye(4))
+        outs.append((e, H.copy(), b.copy(), g.align()["T64"]))
+    for e, H, b, T in outs[1:]:
+        assert e == outs[0][0] and np.array_equal(H, outs[0][1]) and np.array_equal(b, outs[0][2]) and np.array_equal(T, outs[0][3])
+
+
+# ----------------------------------------------------------------- align ----
+def _check_align(g, o, guess=None, pose_tol=1e-6):
+    rg, ro = g.align(guess), o.align(guess)
+    dt, dr = pose_err(rg["T64"], ro["T64"])
+    assert dt < pose_tol and dr < pose_tol, (dt, dr)
+    assert rg["converged"] == ro["converged"] and rg["iterations"] == ro["iterations"]
+    tg, to = g.lm_trace(), o.lm_trace()
+    assert tg.shape == to.shape
+    assert np.array_equal(tg[:, [0, 1, 7]], to[:, [0, 1, 7]])  # same LM path (outer, inner, accept)
+    assert np.abs(rg["T"].astype(np.float64) - rg["T64"]).max() < 1e-5
+    assert rel(rg["H"], ro["H"]) < 1e-8
+    return rg, ro
+
+
+@pytest.mark.parametrize("params", [DEPLOYED, dict(max_correspondence_distance=2.0), dict()])
+def test_align_parity_scan_pair(gorio, synth, params):
+    for seed in (1000, 1001, 1002):
+        src, tgt, _ = synth.scan_pair(seed, 1000)
+        g, o = make(gorio, src, tgt, **params, maha_fp64=1)
+        _check_align(g, o)
+
+
+def test_align_parity_submap(gorio, c2):
+    src, tgt, _ = c2
+    g, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+    _check_align(g, o)
+    g, o = make(gorio, src, tgt, max_correspondence_distance=2.0, maha_fp64=1)
+    _check_align(g, o)
+
+
+def test_align_fp32_mahalanobis_within_north_star_tolerance(gorio, synth, c2):
+    src, tgt, _ = c2
+    g, o = make(gorio, src, tgt, max_correspondence_distance=2.0, maha_fp64=0)
+    rg, ro = g.align(), o.align()
+    dt, dr = pose_err(rg["T64"], ro["T64"])
+    assert dt < 1e-6 and dr < 1e-6
+    assert rel(rg["H"], ro["H"]) < 1e-5
+
+
+def test_align_gauss_newton(gorio, c2_small):
+    src, tgt, _ = c2_small
+    g, o = make(gorio, src, tgt, max_correspondence_distance=2.0, optimizer=0, max_iterations=8, maha_fp64=1)
+    _check_align(g, o)
+
+
+def test_align_with_guess_and_aligned_output(gorio, synth, c2_small):
+    src, tgt, Tgt = c2_small
+    g, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+    guess = (Tgt @ synth.make_pose([0.1, 0.05, 0.0], [0, 0, 0.01])).astype(np.float32)
+    _check_align(g, o, guess)
+    rg = g.align(guess, want_aligned=True)
+    ro = o.align(guess, want_aligned=True)
+    assert np.array_equal(rg["aligned"], ro["aligned"]) or np.abs(rg["aligned"] - ro["aligned"]).max() < 1e-4
+
+
+def test_recovers_known_transform(gorio, synth, c2_small):
+    """reference gicp_test.cpp:148-166 bar: < 0.05 m, < 1 deg, converged"""
+    _, tgt, _ = c2_small
+    D = synth.make_pose([0.3, -0.2, 0.05], np.deg2rad([0.3, -0.4, 2.0]))
+    src = moved_copy(synth, tgt, D)[::3].copy()
+    g = gorio.FastAPDGICP(0)
+    g.set_params(max_correspondence_distance=2.0)
+    g.set_input_target(tgt); g.set_input_source(src)
+    r = g.align()
+    dt, dr = pose_err(r["T64"], D)
+    assert r["converged"] and dt < 0.05 and dr < np.deg2rad(1.0)
+    score, n_in, n_inl = g.fitness()
+    assert score < 1e-3 and n_in == src.shape[0] and n_inl == src.shape[0]
+    # identity on identical clouds: zero motion, ~zero error
+    g.set_input_source(tgt[::3].copy())
+    r = g.align()
+    dt, dr = pose_err(r["T64"], np.eye(4))
+    assert r["converged"] and dt < 1e-6 and dr < 1e-6
+
+
+def test_swap_source_and_target(gorio, synth, c2_small):
+    """gicp_test.cpp:157-200: swap then align gives the inverse transform, covariances travel with the clouds"""
+    src, tgt, _ = c2_small
+    g, o = make(gorio, src, tgt, max_correspondence_distance=2.0, maha_fp64=1)
+    _check_align(g, o)
+    cs = g.get_source_covariances()
+    g.swap_source_and_target(); o.swap_source_and_target()
+    assert np.array_equal(g.get_target_covariances(), cs)
+    with pytest.raises(gorio.ApdError):
+        g.compute_error(np.eye(4))  # correspondences_ were cleared by the swap (:96)
+    _check_align(g, o)
+    # swap, then set a new source / a new target
+    g.swap_source_and_target(); o.swap_source_and_target()
+    s2 = src[::2].copy()
+    g.set_input_source(s2); o.set_input_source(s2)
+    _check_align(g, o)
+
+
+def test_clear_and_cache_key(gorio, c1):
+    src, tgt, _ = c1
+    g, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+    g.set_input_target(tgt, key=42)
+    l0 = g.launch_count()
+    g.set_input_target(tgt[:500], key=42)  # same key: early-out (:128), cloud unchanged
+    assert g.launch_count() == l0
+    g.n_target = tgt.shape[0]
+    _check_align(g, o)
+    g.clear_source()
+    with pytest.raises(gorio.ApdError) as e:
+        g.align()
+    assert e.value.code == 1
+    g.set_input_source(src)
+    _check_align(g, o)
+
+
+def test_pcl_xyzinormal_layout(gorio, synth, c1):
+    src, tgt, _ = c1
+    g = gorio.FastAPDGICP(0)
+    g.set_params(**DEPLOYED, maha_fp64=1)
+    g.set_input_target(synth.to_pcl_xyzinormal(tgt)); g.set_input_source(synth.to_pcl_xyzinormal(src))
+    g2, _ = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+    assert np.array_equal(g.align()["T64"], g2.align()["T64"])
+
+
+def test_error_codes(gorio, c1):
+    src, tgt, _ = c1
+    g = gorio.FastAPDGICP(0)
+    g.set_input_target(tgt); g.set_input_source(src[:10])  # fewer than k points
+    with pytest.raises(gorio.ApdError) as e:
+        g.align()
+    assert e.value.code == 3
+    g.set_params(k_correspondences=33)
+    g.set_input_source(src)
+    with pytest.raises(gorio.ApdError) as e:
+        g.align()
+    assert e.value.code == 4
+    g2 = gorio.FastAPDGICP(0)
+    with pytest.raises(gorio.ApdError):
+        g2.align()  # no clouds
+    g2.set_input_source(np.zeros((0, 4), np.float32))
+    g2.set_input_target(tgt)
+    with pytest.raises(gorio.ApdError):
+        g2.align()  # empty source
+
+
+# --------------------------------------------------------------- fitness ----
+def test_fitness_parity(gorio, synth, c2_small):
+    src, tgt, Tgt = c2_small
+    g, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+    for T in (None, Tgt.astype(np.float32)):
+        if T is None:
+            g.align(); o.align()
+        for max_range in (np.finfo(np.float64).max, 1.0):
+            sg, ng, ig = g.fitness(T, max_range)
+            so, no, io = o.fitness(T, max_range)
+            assert (ng, ig) == (no, io)
+            assert abs(sg - so) / so < 1e-12
+    s, n, _ = g.fitness(Tgt.astype(np.float32), 0.0)
+    assert n == 0 and s == np.finfo(np.float64).max  # DBL_MAX when nothing is in range
+
+
+# ------------------------------------------------------- batch and sizes ----
+def test_align_batch_matches_sequential(gorio, synth):
+    pairs = []
+    for seed in range(3000, 3006):
+        s, t, _ = synth.submap_pair(seed, n_source=600, n_frames=4, n_per_frame=1000)
+        pairs.append((s, t, None))
+    p = gorio.ApdParams()
+    gorio.load().apd_default_params(ctypes.byref(p))
+    p.max_correspondence_distance = 2.0
+    p.transformation_epsilon = 0.1
+    res = gorio.align_batch(pairs, p, n_streams=3)
+    for (s, t, _), r in zip(pairs, res):
+        g = gorio.FastAPDGICP(0)
+        g.set_params(max_correspondence_distance=2.0, transformation_epsilon=0.1)
+        g.set_input_target(t); g.set_input_source(s)
+        ra = g.align()
+        assert r["status"] == 0
+        assert np.array_equal(r["T"], ra["T"]) and r["converged"] == ra["converged"] and r["iterations"] == ra["iterations"]
+        assert abs(r["fitness"] - g.fitness()[0]) < 1e-12
+
+
+def test_large_cloud_properties(gorio, synth):
+    """2 M points (size-independent properties; the oracle would take minutes here):
+    identical clouds -> zero cost; moved copy -> align recovers the motion;
+    H from a subset + H from the rest == H from all (linearity of the reduction)."""
+    src, tgt, Tgt = synth.tiled_cloud_pair(4000, 2_000_000)
+    g = gorio.FastAPDGICP(0)
+    g.set_params(max_correspondence_distance=2.0)
+    g.set_input_target(tgt); g.set_input_source(tgt)
+    e, H, b = g.linearize(np.eye(4))
+    assert e == 0.0 and np.abs(b).max() == 0.0
+    c, sq = g.get_correspondences()
+    assert np.array_equal(c, np.arange(tgt.shape[0])) and sq.max() == 0.0
+    g.set_input_source(src)
+    e_all, H_all, b_all = g.linearize(Tgt)
+    cs = g.get_source_covariances()
+    half = src.shape[0] // 2
+    parts = []
+    for sl in (slice(0, half), slice(half, None)):
+        g.set_input_source(src[sl].copy())
+        g.set_source_covariances(cs[sl])  # a point's covariance depends on its cloud: keep the full cloud's
+        parts.append(g.linearize(Tgt))
+    # cl_weight = 1/N differs between the runs; compare H and b (unweighted, :289-290)
+    assert rel(parts[0][1] + parts[1][1], H_all) < 1e-9
+    assert rel(parts[0][2] + parts[1][2], b_all) < 1e-7
+    g.set_input_source(src[::10].copy())
+    r = g.align()
+    dt, dr = pose_err(r["T64"], Tgt)
+    assert r["converged"] and dt < 0.02 and dr < 1e-3
