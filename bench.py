@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — FastAPDGICP registrations/s (scan-to-submap) and linearize GB/s.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic scan/submap
+pairs: for every pair {clearTarget; clearSource; setInputTarget; setInputSource;
+align} (the reference benchmark protocol, fast_apdgicp/src/align.cpp:57-83) with
+the deployed parameters (4DRadarSLAM/launch/ntu_loop2.launch:88-99).
+
+  value     registrations/s, clouds already resident in HBM (apd_set_*_device)
+  e2e       the same through the C-ABI with HOST buffers (apd_set_source/target
+            stage + copy the clouds, apd_align copies the pose back)
+  roofline  the linearize kernel on a cloud larger than L2 (CUDA events on the
+            handle's stream, live in this run) against the measured HBM peak
+  cpu_baseline  the reference-structure CPU restatement (oracle/_ref: OpenMP +
+            the reference tree's nanoflann; else the oracle port) on a bounded
+            sample of the same pairs, all host threads
+
+N > 1: the pairs are sharded across ranks (one process per GPU, no data-path
+collective — pairs are independent, reference loop_detector.cpp:222-236), weak
+scaling; value = all pairs / max-over-ranks time.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+DEPLOYED = dict(max_correspondence_distance=2.0, transformation_epsilon=0.1)
+METRIC = "APDGICP registrations/sec (scan-to-submap)"
+UNIT = "registrations/s"
+BYTES_PER_POINT_LINEARIZE = 64  # src 16 + corr 4 + tgt 16 + maha 24 + geo 4
+BYTES_PER_POINT_KNNCOV = 68     # read point 16, write cov 48 + geo 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=32, help="scan/submap pairs per step and per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="concurrent handles (CUDA streams) per GPU")
+    ap.add_argument("--roofline-points", type=int, default=20_000_000)
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--roofline-reps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-pairs", type=int, default=8, help="pairs per step of the reference arm")
+    return ap.parse_args()
+
+
+def make_pairs(synth, rank, n_pairs, distinct=8):
+    """C2-shaped pairs: 2000-point scan vs 60k-point submap. `distinct` scenes are
+    generated (numpy generation costs ~1 s each) and cycled to n_pairs."""
+    base = []
+    for i in range(min(distinct, n_pairs)):
+        s, t, _ = synth.submap_pair(2000 + rank * 1000 + i)
+        base.append((np.ascontiguousarray(s), np.ascontiguousarray(t)))
+    return [base[i % len(base)] for i in range(n_pairs)]
+
+
+# ------------------------------------------------------------ reference arm ----
+def load_cpu_impl():
+    from oracle_binding import ORACLE_REF_SO, oracle_lib  # tests/oracle_binding.py (checker side)
+    if os.path.exists(ORACLE_REF_SO):
+        return oracle_lib(ref=True), "port", 2, "oracle/_ref (reference loop structure + the reference tree's nanoflann kd-tree, OpenMP)"
+    return oracle_lib(ref=False), "port", 1, "oracle port (own exact kd-tree, OpenMP)"
+
+
+def cpu_registrations(lib, search, pairs, reps):
+    """Runs the CPU restatement on `pairs` x reps with all host threads; returns (seconds, n)."""
+    h = ctypes.c_void_p()
+    lib.apdo_create(ctypes.byref(h))
+    gorio = importlib.import_module("go-rio_b200")
+    p = gorio.ApdParams()
+    lib.apdo_get_params(h, ctypes.byref(p))
+    p.max_correspondence_distance = DEPLOYED["max_correspondence_distance"]
+    p.transformation_epsilon = DEPLOYED["transformation_epsilon"]
+    lib.apdo_set_params(h, ctypes.byref(p))
+    lib.apdo_set_search(h, ctypes.c_int(search))
+    lib.apdo_set_num_threads(h, ctypes.c_int(0))  # setNumThreads(0) = all cores (registrations.cpp:41)
+    ms = (ctypes.c_double * reps)()
+    total = 0.0
+    for s, t in pairs:
+        rc = lib.apdo_bench_align(h, s.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(s.shape[0]), t.ctypes.data_as(ctypes.c_void_p),
+                                  ctypes.c_int32(t.shape[0]), ctypes.c_int32(16), ctypes.c_int32(0), ctypes.c_int32(12), None,
+                                  ctypes.c_int32(reps), ms)
+        assert rc == 0
+        total += sum(ms) / 1e3
+    lib.apdo_destroy(h)
+    return total, len(pairs) * reps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    synth = importlib.import_module("go-rio_b200.synth")
+    lib, kind, search, what = load_cpu_impl()
+    lib.apdo_max_threads.restype = ctypes.c_int
+    cores = lib.apdo_max_threads()
+    pairs = make_pairs(synth, 0, args.ref_pairs, distinct=min(8, args.ref_pairs))
+    for _ in range(args.warmup):
+        cpu_registrations(lib, search, pairs[:1], 1)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        t, n = cpu_registrations(lib, search, pairs, 1)
+        t_total += t
+        n_total += n
+    value = n_total / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 scan-to-submap: 2000-pt radar scan vs 60000-pt keyframe submap, k=20, deployed params",
+                   "pairs_per_step": len(pairs), "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{len(pairs)} pairs per step x {args.steps} steps; {what}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------- clocks ----
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = max(float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples if len(s) > 3 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------ our arm ----
+def run_step(handles, pairs, mode, results):
+    """Registers every pair once, sharing the work over len(handles) threads (one
+    CUDA stream each; ctypes releases the GIL inside the C-ABI calls).
+    mode 'device': pairs = [(d_src_ptr, n_src, d_tgt_ptr, n_tgt)];
+    mode 'host':   pairs = [(src ndarray, tgt ndarray)]."""
+    nxt = [0]
+    lock = threading.Lock()
+
+    def work(g):
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= len(pairs):
+                return
+            g.clear_target()
+            g.clear_source()
+            if mode == "device":
+                ds, ns, dt, nt = pairs[i]
+                g.set_input_target_device(dt, nt)
+                g.set_input_source_device(ds, ns)
+            else:
+                s, t = pairs[i]
+                g.set_input_target(t)
+                g.set_input_source(s)
+            results[i] = g.align()
+
+    ths = [threading.Thread(target=work, args=(g,)) for g in handles]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the registration path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    gorio = importlib.import_module("go-rio_b200")
+    synth = importlib.import_module("go-rio_b200.synth")
+    dev = torch.device("cuda", local_rank)
+
+    host_pairs = make_pairs(synth, rank, args.pairs)
+    # HBM-resident copies of the clouds for `value`
+    dev_tensors, dev_pairs = [], []
+    cache = {}
+    for s, t in host_pairs:
+        key = (s.ctypes.data, t.ctypes.data)
+        if key not in cache:
+            ds, dt = torch.from_numpy(s).to(dev), torch.from_numpy(t).to(dev)
+            dev_tensors += [ds, dt]
+            cache[key] = (ds.data_ptr(), s.shape[0], dt.data_ptr(), t.shape[0])
+        dev_pairs.append(cache[key])
+    pinned_pairs = host_pairs  # the C-ABI stages host clouds through its own pinned buffers
+
+    handles = []
+    for _ in range(args.streams):
+        g = gorio.FastAPDGICP(local_rank)
+        g.set_params(**DEPLOYED)
+        handles.append(g)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(mode, pairs, steps, warmup):
+        results = [None] * len(pairs)
+        for _ in range(warmup):
+            run_step(handles, pairs, mode, results)
+        ms_total = 0.0
+        l0 = sum(g.launch_count() for g in handles)
+        for _ in range(steps):
+            flush.zero_()  # L2 flush between timed iterations (untimed)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run_step(handles, pairs, mode, results)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            ms_total += float(ms.item())
+        launches = sum(g.launch_count() for g in handles) - l0
+        return ms_total, launches, results
+
+    with ClockSampler(local_rank) as clocks:
+        ms_dev, launches, results = timed("device", dev_pairs, args.steps, args.warmup)
+    ms_e2e, _, results_h = timed("host", pinned_pairs, args.steps, args.warmup)
+    total_pairs = args.pairs * world
+    value = total_pairs * args.steps / (ms_dev / 1e3)
+    e2e_value = total_pairs * args.steps / (ms_e2e / 1e3)
+    same = all(np.array_equal(a["T"], b["T"]) for a, b in zip(results, results_h))
+    h2d = sum(s.nbytes + t.nbytes for s, t in host_pairs)
+    d2h = args.pairs * (16 * 4 + 16 * 8 + 36 * 8 + 8)
+
+    # per-kernel-class device time of one step (profiling events on the handle streams; separate, untimed pass)
+    for g in handles:
+        g.set_profiling(True)
+    run_step(handles, dev_pairs, "device", [None] * len(dev_pairs))
+    kms = {}
+    for g in handles:
+        for k, (ms, cnt) in g.kernel_ms().items():
+            a = kms.setdefault(k, [0.0, 0])
+            a[0] += ms
+            a[1] += cnt
+        g.set_profiling(False)
+    tot = sum(v[0] for v in kms.values()) or 1.0
+    kernels = {k: {"ms_per_step": round(v[0], 4), "launches_per_step": v[1], "share": round(v[0] / tot, 4)} for k, v in kms.items()}
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        n_tgt_pts = sum(t.shape[0] for _, t in host_pairs[:1])
+        knn_ms = kms.get("knn_cov", [0.0, 0])[0]
+        knn_pts = sum(s.shape[0] + t.shape[0] for s, t in host_pairs)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2 scan-to-submap: 2000-pt radar scan vs 60000-pt keyframe submap, k=20, deployed params "
+                                   "(max_corr_dist 2.0, trans_eps 0.1, LM, PLANE)",
+                       "pairs_per_step_per_gpu": args.pairs, "streams_per_gpu": args.streams,
+                       "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align",
+                       "l2": "flushed (256 MiB write) between timed steps", "sharding": "pairs across ranks, no collective",
+                       "target_points": n_tgt_pts},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "same_result_as_device_resident": bool(same)},
+            "gpu_launches": int(launches),
+            "kernels": kernels,
+            "knn_cov_roofline": {"bound": "hbm", "achieved": (BYTES_PER_POINT_KNNCOV * knn_pts / 1e9) / (knn_ms / 1e3) if knn_ms > 0 else None,
+                                 "peak": peak, "unit": "GB/s", "note": "search-bound (L2-resident candidates), reported for the step's dominant kernel"},
+            "clocks": clocks.summary(),
+        }
+
+    # ---- roofline of the linearize kernel on a cloud larger than L2 (rank 0, N = 1 only) ----
+    if rank == 0 and world == 1 and not args.no_roofline:
+        for g in handles:
+            g.close()
+        del dev_tensors
+        torch.cuda.empty_cache()
+        n = args.roofline_points
+        src, tgt, Tgt = synth.tiled_cloud_pair(4000, n)
+        ds, dt = torch.from_numpy(src).to(dev), torch.from_numpy(tgt).to(dev)
+        g = gorio.FastAPDGICP(local_rank)
+        g.set_params(max_correspondence_distance=2.0)
+        g.set_input_target_device(dt.data_ptr(), n)
+        g.set_input_source_device(ds.data_ptr(), n)
+        T = Tgt.copy()
+        g.linearize(T)  # builds grids, covariances, correspondences
+        for _ in range(3):
+            g.linearize(T)
+            g.compute_error(T)
+        g.set_profiling(True)
+        reps = max(1, args.roofline_reps)
+        for _ in range(reps):
+            g.linearize(T)
+            g.compute_error(T)
+        k = g.kernel_ms()
+        lin_ms = k["linearize"][0] / reps
+        err_ms = k["error"][0] / reps
+        corr_ms = k["corr"][0] / reps
+        achieved = BYTES_PER_POINT_LINEARIZE * n / 1e9 / (lin_ms / 1e3)
+        n_valid = int((g.get_correspondences()[0] >= 0).sum())
+        line["roofline"] = {
+            "bound": "hbm", "kernel": "linearize_kernel<fp32 maha, H+b+err>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "points": n, "matched_points": n_valid,
+            "bytes_per_point": BYTES_PER_POINT_LINEARIZE, "ms_per_launch": lin_ms,
+            "compute_error": {"ms_per_launch": err_ms, "achieved": BYTES_PER_POINT_LINEARIZE * n / 1e9 / (err_ms / 1e3)},
+            "update_correspondences": {"ms_per_launch": corr_ms, "achieved": 148 * n / 1e9 / (corr_ms / 1e3), "bytes_per_point": 148},
+            "timing": "CUDA events on the handle's stream around each launch; working set 1.28 GB > L2",
+        }
+        g.close()
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        lib, kind, search, what = load_cpu_impl()
+        lib.apdo_max_threads.restype = ctypes.c_int
+        sample = host_pairs[:8]
+        seen, uniq = set(), []
+        for s, t in sample:
+            if s.ctypes.data not in seen:
+                seen.add(s.ctypes.data)
+                uniq.append((s, t))
+        cpu_registrations(lib, search, uniq[:1], 1)
+        t_cpu, n_cpu = cpu_registrations(lib, search, uniq, 3)
+        line["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": UNIT, "cores": lib.apdo_max_threads(), "kind": kind,
+                                "sample": f"{len(uniq)} of the step's pairs x 3 repetitions ({t_cpu:.1f} s wall); {what}"}
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -392,7 +392,9 @@ def test_large_cloud_properties(gorio, synth):
     # cl_weight = 1/N differs between the runs; compare H and b (unweighted, :289-290)
     assert rel(parts[0][1] + parts[1][1], H_all) < 1e-9
     assert rel(parts[0][2] + parts[1][2], b_all) < 1e-7
-    g.set_input_source(src[::10].copy())
+    # an exact moved copy of a subset is registered back onto the cloud
+    sub = moved_copy(synth, tgt[::10].copy(), Tgt)
+    g.set_input_source(sub)
     r = g.align()
     dt, dr = pose_err(r["T64"], Tgt)
-    assert r["converged"] and dt < 0.02 and dr < 1e-3
+    assert r["converged"] and dt < 5e-3 and dr < 1e-4, (r["converged"], r["iterations"], dt, dr)
