@@ -466,7 +466,7 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
   ReduceWork w;
   w.partials = h->partials.as<double>();
   w.ticket = reinterpret_cast<unsigned int*>(d_out + 40);
-  w.max_blocks = h->max_reduce_blocks;
+  w.max_blocks = h->max_reduce_blocks / 2;  // persistent CTAs: 2 resident per SM
   const double n_total = h->comm ? (double)h->n_source_total : (double)h->src.n;
   {
     ProfScope ps(h, want_hb ? APD_K_LINEARIZE : APD_K_ERROR);

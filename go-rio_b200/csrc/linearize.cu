@@ -8,10 +8,18 @@
 // correspondence 4 B + gathered target float4 16 B + Mahalanobis 24 B +
 // geometric weight 4 B = 64 B; output 28 doubles per launch.
 //
-// Reduction: fp64 per-thread accumulators over a grid-stride loop -> fixed
-// warp-shuffle tree -> fixed per-block order -> per-block partials -> the last
-// block (atomic ticket) adds the partials in block order. For a given n the
-// launch shape is fixed, so the result is bit-reproducible run to run.
+// Memory pipeline (sm_100a): persistent CTAs walk 256-point tiles. The five
+// coalesced per-source streams of a tile are brought into shared memory by
+// bulk asynchronous copies (cp.async.bulk ... mbarrier::complete_tx, the TMA
+// engine's 1-D path; SASS UBLKCP) issued by one elected thread into a 4-stage
+// ring, so the bytes in flight do not depend on registers or occupancy. The
+// matched target point of tile j+1 is gathered with a 16-byte cp.async (LDGSTS)
+// per thread while tile j is being computed.
+//
+// Reduction: fp64 per-thread accumulators -> fixed warp-shuffle tree -> fixed
+// per-block order -> per-block partials -> the last block (atomic ticket) adds
+// the partials in block order. The tile->CTA mapping is static, so for a given n
+// the result is bit-reproducible run to run.
 #include "kernels.cuh"
 
 namespace apd {
@@ -20,61 +28,181 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+constexpr int kTile = kThreads;   // points per tile
+constexpr int kStages = 4;
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// shared-memory layout of one stage
 template <bool kFp64>
-__device__ __forceinline__ void load_maha(const void* __restrict__ mahaA, const void* __restrict__ mahaB, int i, int n, double m[6]) {
-  if (kFp64) {
-    const double2 a = __ldg(reinterpret_cast<const double2*>(mahaA) + i);
-    const double2 b = __ldg(reinterpret_cast<const double2*>(mahaB) + i);
-    const double2 d = __ldg(reinterpret_cast<const double2*>(mahaB) + (size_t)n + i);
-    m[0] = a.x; m[1] = a.y; m[2] = b.x; m[3] = b.y; m[4] = d.x; m[5] = d.y;
-  } else {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(mahaA) + i);
-    const float2 b = __ldg(reinterpret_cast<const float2*>(mahaB) + i);
-    m[0] = (double)a.x; m[1] = (double)a.y; m[2] = (double)a.z; m[3] = (double)a.w; m[4] = (double)b.x; m[5] = (double)b.y;
-  }
+struct StageLayout {
+  static constexpr int kSpts = 0;                                        // float4[256]
+  static constexpr int kMahaA = kSpts + kTile * 16;                      // float4[256] | double2[256]
+  static constexpr int kMahaB = kMahaA + kTile * 16;                     // float2[256] | double2[256] x 2 planes
+  static constexpr int kCorr = kMahaB + (kFp64 ? kTile * 32 : kTile * 8);  // int[256]
+  static constexpr int kGeo = kCorr + kTile * 4;                         // float[256] | double[256]
+  static constexpr int kBytes = kGeo + (kFp64 ? kTile * 8 : kTile * 4);
+};
+template <bool kFp64>
+constexpr int smem_bytes() {
+  return kStages * StageLayout<kFp64>::kBytes + 2 * kTile * 16;
 }
 
 template <bool kFp64, bool kHB>
 __global__ void __launch_bounds__(kThreads, 2)
 linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_geo, const double* __restrict__ s_geo64,
-                 const int* __restrict__ corr,
-                 const void* __restrict__ mahaA, const void* __restrict__ mahaB, const float4* __restrict__ t_spts, PoseD T,
-                 double cl_w, int n, double* __restrict__ partials, double* __restrict__ out28, unsigned int* __restrict__ ticket) {
+                 const int* __restrict__ corr, const void* __restrict__ mahaA, const void* __restrict__ mahaB,
+                 const float4* __restrict__ t_spts, PoseD T, double cl_w, int n, double* __restrict__ partials,
+                 double* __restrict__ out28, unsigned int* __restrict__ ticket) {
+  using L = StageLayout<kFp64>;
   constexpr int NV = kHB ? kReduceVals : 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  unsigned char* gat = smem + kStages * L::kBytes;  // float4[2][256] gathered target points
+
+  const int tid = threadIdx.x;
+  const int ntiles = (n + kTile - 1) / kTile;
+  const int my = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; s++) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // one elected thread feeds the ring: tile j of this CTA -> stage j % kStages
+  auto issue_tile = [&](int j) {
+    const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+    const size_t base = (size_t)tile * kTile;
+    const int cnt = min(kTile, n - (int)base);
+    const uint32_t c4 = (uint32_t)((cnt + 3) & ~3);  // element count rounded so every copy is a multiple of 16 B
+    unsigned char* st = smem + (j % kStages) * L::kBytes;
+    uint64_t* bar = &full_bar[j % kStages];
+    const uint32_t b_spts = c4 * 16, b_corr = c4 * 4;
+    const uint32_t b_mA = c4 * 16, b_mB = kFp64 ? c4 * 16 : c4 * 8, b_geo = kFp64 ? c4 * 8 : c4 * 4;
+    mbar_expect_tx(bar, b_spts + b_corr + b_mA + (kFp64 ? 2 * b_mB : b_mB) + b_geo);
+    bulk_g2s(st + L::kSpts, s_spts + base, b_spts, bar);
+    bulk_g2s(st + L::kCorr, corr + base, b_corr, bar);
+    if (kFp64) {
+      bulk_g2s(st + L::kMahaA, reinterpret_cast<const double2*>(mahaA) + base, b_mA, bar);
+      bulk_g2s(st + L::kMahaB, reinterpret_cast<const double2*>(mahaB) + base, b_mB, bar);
+      bulk_g2s(st + L::kMahaB + kTile * 16, reinterpret_cast<const double2*>(mahaB) + (size_t)n + base, b_mB, bar);
+      bulk_g2s(st + L::kGeo, s_geo64 + base, b_geo, bar);
+    } else {
+      bulk_g2s(st + L::kMahaA, reinterpret_cast<const float4*>(mahaA) + base, b_mA, bar);
+      bulk_g2s(st + L::kMahaB, reinterpret_cast<const float2*>(mahaB) + base, b_mB, bar);
+      bulk_g2s(st + L::kGeo, s_geo + base, b_geo, bar);
+    }
+  };
+  if (tid == 0) {
+    const int pre = min(kStages, my);
+    for (int j = 0; j < pre; j++) issue_tile(j);
+  }
+
+  // per-thread gather of the matched target point of tile j into gat[j & 1]
+  auto issue_gather = [&](int j) {
+    const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+    const int i = tile * kTile + tid;
+    const unsigned char* st = smem + (j % kStages) * L::kBytes;
+    const int c = reinterpret_cast<const int*>(st + L::kCorr)[tid];
+    const int pos = (i < n && c >= 0) ? (c & kCorrIndexMask) : 0;
+    cp_async16(gat + ((j & 1) * kTile + tid) * 16, t_spts + pos);
+  };
+
   double acc[NV];
 #pragma unroll
   for (int j = 0; j < NV; j++) acc[j] = 0.0;
 
-#pragma unroll 2
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-    const int c = __ldg(&corr[i]);
-    const bool valid = c >= 0;
-    const int pos = valid ? (c & kCorrIndexMask) : 0;
-    const float4 a = __ldg(&s_spts[i]);
-    const float4 b = __ldg(&t_spts[pos]);
-    const double geo = kFp64 ? __ldg(&s_geo64[i]) : (double)__ldg(&s_geo[i]);
-    double m[6];
-    load_maha<kFp64>(mahaA, mahaB, i, n, m);
+  if (my > 0) {
+    mbar_wait(&full_bar[0], 0);
+    issue_gather(0);
+  }
+  cp_async_commit();
+
+  for (int j = 0; j < my; j++) {
+    if (j + 1 < my) {
+      mbar_wait(&full_bar[(j + 1) % kStages], (uint32_t)(((j + 1) / kStages) & 1));
+      issue_gather(j + 1);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();  // everything but the newest group: tile j's gather has landed
+
+    const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+    const int i = tile * kTile + tid;
+    const unsigned char* st = smem + (j % kStages) * L::kBytes;
+    const int c = reinterpret_cast<const int*>(st + L::kCorr)[tid];
+    const bool valid = (i < n) && (c >= 0);
+    const float4 a = reinterpret_cast<const float4*>(st + L::kSpts)[tid];
+    const float4 b = reinterpret_cast<const float4*>(gat)[(j & 1) * kTile + tid];
+    double m[6], geo;
+    if (kFp64) {
+      const double2 ma = reinterpret_cast<const double2*>(st + L::kMahaA)[tid];
+      const double2 mb = reinterpret_cast<const double2*>(st + L::kMahaB)[tid];
+      const double2 mc = reinterpret_cast<const double2*>(st + L::kMahaB + kTile * 16)[tid];
+      m[0] = ma.x; m[1] = ma.y; m[2] = mb.x; m[3] = mb.y; m[4] = mc.x; m[5] = mc.y;
+      geo = reinterpret_cast<const double*>(st + L::kGeo)[tid];
+    } else {
+      const float4 ma = reinterpret_cast<const float4*>(st + L::kMahaA)[tid];
+      const float2 mb = reinterpret_cast<const float2*>(st + L::kMahaB)[tid];
+      m[0] = (double)ma.x; m[1] = (double)ma.y; m[2] = (double)ma.z; m[3] = (double)ma.w; m[4] = (double)mb.x; m[5] = (double)mb.y;
+      geo = (double)reinterpret_cast<const float*>(st + L::kGeo)[tid];
+    }
 #pragma unroll
     for (int e = 0; e < 6; e++) m[e] = valid ? m[e] : 0.0;
 
-    const double ax = (double)a.x, ay = (double)a.y, az = (double)a.z;
+    // (points past n in the last tile hold padding bytes: zero them so 0 * garbage cannot make a NaN)
+    const double ax = valid ? (double)a.x : 0.0, ay = valid ? (double)a.y : 0.0, az = valid ? (double)a.z : 0.0;
+    const double bx = valid ? (double)b.x : 0.0, by = valid ? (double)b.y : 0.0, bz = valid ? (double)b.z : 0.0;
     // transed_mean_A = T * mean_A ; error = mean_B - transed_mean_A (:262-263)
     const double x = ((T.r[0] * ax + T.r[1] * ay) + T.r[2] * az) + T.t[0];
     const double y = ((T.r[3] * ax + T.r[4] * ay) + T.r[5] * az) + T.t[1];
     const double z = ((T.r[6] * ax + T.r[7] * ay) + T.r[8] * az) + T.t[2];
-    const double e0 = (double)b.x - x, e1 = (double)b.y - y, e2 = (double)b.z - z;
+    const double e0 = bx - x, e1 = by - y, e2 = bz - z;
     // M e and the weighted cost (:276)
     const double me0 = (m[0] * e0 + m[1] * e1) + m[2] * e2;
     const double me1 = (m[1] * e0 + m[3] * e1) + m[4] * e2;
     const double me2 = (m[2] * e0 + m[4] * e1) + m[5] * e2;
     const double q = (e0 * me0 + e1 * me1) + e2 * me2;
-    const double w = (1.0 + geo) + ((c & kCorrLabelBit) ? cl_w : 0.0);
+    const double w = (1.0 + (valid ? geo : 0.0)) + ((c & kCorrLabelBit) ? cl_w : 0.0);
     if (!kHB) {
-      acc[0] += w * q;
+      acc[0] += valid ? w * q : 0.0;
     } else {
-      acc[27] += w * q;
+      acc[27] += valid ? w * q : 0.0;
       // N = M * skew(t), t = (x,y,z): N[:,0] = M[:,1] z - M[:,2] y, N[:,1] = M[:,2] x - M[:,0] z, N[:,2] = M[:,0] y - M[:,1] x
       const double n00 = m[1] * z - m[2] * y, n01 = m[2] * x - m[0] * z, n02 = m[0] * y - m[1] * x;
       const double n10 = m[3] * z - m[4] * y, n11 = m[4] * x - m[1] * z, n12 = m[1] * y - m[3] * x;
@@ -100,11 +228,15 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
       acc[23] += y * me0 - x * me1;
       acc[24] -= me0; acc[25] -= me1; acc[26] -= me2;
     }
+
+    __syncthreads();  // every thread is done with stage j % kStages
+    if (tid == 0 && j + kStages < my) issue_tile(j + kStages);
   }
+  cp_async_wait<0>();
 
   // warp tree -> block -> partials -> last block
   __shared__ double sh[kWarps][NV];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int j = 0; j < NV; j++) {
     double v = acc[j];
@@ -113,27 +245,42 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
     if (lane == 0) sh[warp][j] = v;
   }
   __syncthreads();
-  if (threadIdx.x < NV) {
+  if (tid < NV) {
     double v = 0.0;
 #pragma unroll
-    for (int w2 = 0; w2 < kWarps; w2++) v += sh[w2][threadIdx.x];
-    partials[(size_t)blockIdx.x * NV + threadIdx.x] = v;
+    for (int w2 = 0; w2 < kWarps; w2++) v += sh[w2][tid];
+    partials[(size_t)blockIdx.x * NV + tid] = v;
   }
   __shared__ bool last;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (tid == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
   __syncthreads();
   if (last) {
     __threadfence();
-    if (threadIdx.x < NV) {
+    if (tid < NV) {
       double v = 0.0;
-      for (unsigned int k = 0; k < gridDim.x; k++) v += __ldcg(&partials[(size_t)k * NV + threadIdx.x]);
-      if (kHB) out28[threadIdx.x] = v;
+      for (unsigned int k = 0; k < gridDim.x; k++) v += __ldcg(&partials[(size_t)k * NV + tid]);
+      if (kHB) out28[tid] = v;
       else out28[27] = v;
     }
-    if (threadIdx.x == 0) *ticket = 0;
+    if (tid == 0) *ticket = 0;
   }
+}
+
+template <bool kFp64, bool kHB>
+void launch_one(int blocks, cudaStream_t s, const CloudDev& src, const CloudDev& tgt, const PoseD& T, const CorrOut& c, double cl_w,
+                const ReduceWork& w, double* d_out28) {
+  static bool configured[64] = {false};  // per template instance and device: the attribute is per (function, device)
+  constexpr int bytes = smem_bytes<kFp64>();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaFuncSetAttribute(linearize_kernel<kFp64, kHB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  linearize_kernel<kFp64, kHB><<<blocks, kThreads, bytes, s>>>(src.spts, src.geo, src.geo64, c.corr, c.mahaA, c.mahaB, tgt.spts, T, cl_w,
+                                                                src.n, w.partials, d_out28, w.ticket);
 }
 
 }  // namespace
@@ -141,20 +288,16 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
 void launch_linearize(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const CorrOut& c, double n_total, bool want_hb,
                       const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches) {
   const int n = src.n;
-  int blocks = (n + kThreads - 1) / kThreads;
+  int blocks = (n + kTile - 1) / kTile;
   blocks = max(1, min(blocks, w.max_blocks));
   const double cl_w = 1.0 / n_total;  // 1.0 / correspondences_.size() (:273)
-#define APD_LAUNCH(FP64, HB)                                                                                                      \
-  linearize_kernel<FP64, HB><<<blocks, kThreads, 0, s>>>(src.spts, src.geo, src.geo64, c.corr, c.mahaA, c.mahaB, tgt.spts, T, cl_w, n, \
-                                                         w.partials, d_out28, w.ticket)
   if (c.maha_fp64) {
-    if (want_hb) APD_LAUNCH(true, true);
-    else APD_LAUNCH(true, false);
+    if (want_hb) launch_one<true, true>(blocks, s, src, tgt, T, c, cl_w, w, d_out28);
+    else launch_one<true, false>(blocks, s, src, tgt, T, c, cl_w, w, d_out28);
   } else {
-    if (want_hb) APD_LAUNCH(false, true);
-    else APD_LAUNCH(false, false);
+    if (want_hb) launch_one<false, true>(blocks, s, src, tgt, T, c, cl_w, w, d_out28);
+    else launch_one<false, false>(blocks, s, src, tgt, T, c, cl_w, w, d_out28);
   }
-#undef APD_LAUNCH
   (*launches)++;
 }
 

@@ -56,11 +56,11 @@ def make_pose(t, rpy):
     return T
 
 
-def random_motion(rng, scale=1.0):
+def random_motion(rng, scale=1.0, rot_scale=1.0):
     """Relative motion of SURVEY.md §8(d): t_xy ~ U(-.5,.5) m, t_z ~ U(-.05,.05),
     yaw ~ U(-3,3) deg, roll/pitch ~ U(-.5,.5) deg."""
     t = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(-0.05, 0.05)]) * scale
-    rpy = np.deg2rad([rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(-3, 3)]) * scale
+    rpy = np.deg2rad([rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(-3, 3)]) * scale * rot_scale
     return make_pose(t, rpy)
 
 
@@ -270,7 +270,9 @@ def tiled_cloud_pair(seed, n, base_n=78125, pitch=125.0):
     side = int(np.ceil(np.sqrt(tiles)))
     tgt = np.empty((tiles * base_n, 4), dtype=np.float32)
     src = np.empty((tiles * base_n, 4), dtype=np.float32)
-    delta = random_motion(rng)
+    # keep the rotation small enough that the far edge of the tiled area moves by < ~0.5 m
+    # (a scan-sized yaw would displace points a kilometre away by tens of metres)
+    delta = random_motion(rng, rot_scale=min(1.0, 10.0 / (side * pitch)))
     Dinv = np.linalg.inv(delta)
     for ti in range(tiles):
         off = np.array([(ti % side) * pitch, (ti // side) * pitch, 0.0])
