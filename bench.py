@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--roofline-points", type=int, default=20_000_000)
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-reps", type=int, default=10)
+    ap.add_argument("--roofline-only", action="store_true", help="profiling aid: skip the registrations/s part")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-pairs", type=int, default=8, help="pairs per step of the reference arm")
     return ap.parse_args()
@@ -229,113 +230,118 @@ def main():
     synth = importlib.import_module("go-rio_b200.synth")
     dev = torch.device("cuda", local_rank)
 
-    host_pairs = make_pairs(synth, rank, args.pairs)
-    # HBM-resident copies of the clouds for `value`
-    dev_tensors, dev_pairs = [], []
-    cache = {}
-    for s, t in host_pairs:
-        key = (s.ctypes.data, t.ctypes.data)
-        if key not in cache:
-            ds, dt = torch.from_numpy(s).to(dev), torch.from_numpy(t).to(dev)
-            dev_tensors += [ds, dt]
-            cache[key] = (ds.data_ptr(), s.shape[0], dt.data_ptr(), t.shape[0])
-        dev_pairs.append(cache[key])
-    pinned_pairs = host_pairs  # the C-ABI stages host clouds through its own pinned buffers
-
-    handles = []
-    for _ in range(args.streams):
-        g = gorio.FastAPDGICP(local_rank)
-        g.set_params(**DEPLOYED)
-        handles.append(g)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(mode, pairs, steps, warmup):
-        results = [None] * len(pairs)
-        for _ in range(warmup):
-            run_step(handles, pairs, mode, results)
-        ms_total = 0.0
-        l0 = sum(g.launch_count() for g in handles)
-        for _ in range(steps):
-            flush.zero_()  # L2 flush between timed iterations (untimed)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            run_step(handles, pairs, mode, results)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            ms_total += float(ms.item())
-        launches = sum(g.launch_count() for g in handles) - l0
-        return ms_total, launches, results
-
-    with ClockSampler(local_rank) as clocks:
-        ms_dev, launches, results = timed("device", dev_pairs, args.steps, args.warmup)
-    ms_e2e, _, results_h = timed("host", pinned_pairs, args.steps, args.warmup)
-    total_pairs = args.pairs * world
-    value = total_pairs * args.steps / (ms_dev / 1e3)
-    e2e_value = total_pairs * args.steps / (ms_e2e / 1e3)
-    same = all(np.array_equal(a["T"], b["T"]) for a, b in zip(results, results_h))
-    h2d = sum(s.nbytes + t.nbytes for s, t in host_pairs)
-    d2h = args.pairs * (16 * 4 + 16 * 8 + 36 * 8 + 8)
-
-    # per-kernel-class device time of one step (profiling events on the handle streams; separate, untimed pass)
-    for g in handles:
-        g.set_profiling(True)
-    run_step(handles, dev_pairs, "device", [None] * len(dev_pairs))
-    kms = {}
-    for g in handles:
-        for k, (ms, cnt) in g.kernel_ms().items():
-            a = kms.setdefault(k, [0.0, 0])
-            a[0] += ms
-            a[1] += cnt
-        g.set_profiling(False)
-    tot = sum(v[0] for v in kms.values()) or 1.0
-    kernels = {k: {"ms_per_step": round(v[0], 4), "launches_per_step": v[1], "share": round(v[0] / tot, 4)} for k, v in kms.items()}
-
     line = None
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        n_tgt_pts = sum(t.shape[0] for _, t in host_pairs[:1])
-        knn_ms = kms.get("knn_cov", [0.0, 0])[0]
-        knn_pts = sum(s.shape[0] + t.shape[0] for s, t in host_pairs)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 scan-to-submap: 2000-pt radar scan vs 60000-pt keyframe submap, k=20, deployed params "
-                                   "(max_corr_dist 2.0, trans_eps 0.1, LM, PLANE)",
-                       "pairs_per_step_per_gpu": args.pairs, "streams_per_gpu": args.streams,
-                       "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align",
-                       "l2": "flushed (256 MiB write) between timed steps", "sharding": "pairs across ranks, no collective",
-                       "target_points": n_tgt_pts},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "same_result_as_device_resident": bool(same)},
-            "gpu_launches": int(launches),
-            "kernels": kernels,
-            "knn_cov_roofline": {"bound": "hbm", "achieved": (BYTES_PER_POINT_KNNCOV * knn_pts / 1e9) / (knn_ms / 1e3) if knn_ms > 0 else None,
-                                 "peak": peak, "unit": "GB/s", "note": "search-bound (L2-resident candidates), reported for the step's dominant kernel"},
-            "clocks": clocks.summary(),
-        }
+    handles = []
+    host_pairs = []
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    if args.roofline_only:
+        line = {"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "note": "roofline-only profiling run"}
+    else:
+        host_pairs = make_pairs(synth, rank, args.pairs)
+        # HBM-resident copies of the clouds for `value`
+        dev_tensors, dev_pairs = [], []
+        cache = {}
+        for s, t in host_pairs:
+            key = (s.ctypes.data, t.ctypes.data)
+            if key not in cache:
+                ds, dt = torch.from_numpy(s).to(dev), torch.from_numpy(t).to(dev)
+                dev_tensors += [ds, dt]
+                cache[key] = (ds.data_ptr(), s.shape[0], dt.data_ptr(), t.shape[0])
+            dev_pairs.append(cache[key])
+        pinned_pairs = host_pairs  # the C-ABI stages host clouds through its own pinned buffers
+
+        handles = []
+        for _ in range(args.streams):
+            g = gorio.FastAPDGICP(local_rank)
+            g.set_params(**DEPLOYED)
+            handles.append(g)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(mode, pairs, steps, warmup):
+            results = [None] * len(pairs)
+            for _ in range(warmup):
+                run_step(handles, pairs, mode, results)
+            ms_total = 0.0
+            l0 = sum(g.launch_count() for g in handles)
+            for _ in range(steps):
+                flush.zero_()  # L2 flush between timed iterations (untimed)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run_step(handles, pairs, mode, results)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                ms_total += float(ms.item())
+            launches = sum(g.launch_count() for g in handles) - l0
+            return ms_total, launches, results
+
+        with ClockSampler(local_rank) as clocks:
+            ms_dev, launches, results = timed("device", dev_pairs, args.steps, args.warmup)
+        ms_e2e, _, results_h = timed("host", pinned_pairs, args.steps, args.warmup)
+        total_pairs = args.pairs * world
+        value = total_pairs * args.steps / (ms_dev / 1e3)
+        e2e_value = total_pairs * args.steps / (ms_e2e / 1e3)
+        same = all(np.array_equal(a["T"], b["T"]) for a, b in zip(results, results_h))
+        h2d = sum(s.nbytes + t.nbytes for s, t in host_pairs)
+        d2h = args.pairs * (16 * 4 + 16 * 8 + 36 * 8 + 8)
+
+        # per-kernel-class device time of one step (profiling events on the handle streams; separate, untimed pass)
+        for g in handles:
+            g.set_profiling(True)
+        run_step(handles, dev_pairs, "device", [None] * len(dev_pairs))
+        kms = {}
+        for g in handles:
+            for k, (ms, cnt) in g.kernel_ms().items():
+                a = kms.setdefault(k, [0.0, 0])
+                a[0] += ms
+                a[1] += cnt
+            g.set_profiling(False)
+        tot = sum(v[0] for v in kms.values()) or 1.0
+        kernels = {k: {"ms_per_step": round(v[0], 4), "launches_per_step": v[1], "share": round(v[0] / tot, 4)} for k, v in kms.items()}
+
+        if rank == 0:
+            n_tgt_pts = sum(t.shape[0] for _, t in host_pairs[:1])
+            knn_ms = kms.get("knn_cov", [0.0, 0])[0]
+            knn_pts = sum(s.shape[0] + t.shape[0] for s, t in host_pairs)
+            line = {
+                "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C2 scan-to-submap: 2000-pt radar scan vs 60000-pt keyframe submap, k=20, deployed params "
+                                       "(max_corr_dist 2.0, trans_eps 0.1, LM, PLANE)",
+                           "pairs_per_step_per_gpu": args.pairs, "streams_per_gpu": args.streams,
+                           "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align",
+                           "l2": "flushed (256 MiB write) between timed steps", "sharding": "pairs across ranks, no collective",
+                           "target_points": n_tgt_pts},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "same_result_as_device_resident": bool(same)},
+                "gpu_launches": int(launches),
+                "kernels": kernels,
+                "knn_cov_roofline": {"bound": "hbm", "achieved": (BYTES_PER_POINT_KNNCOV * knn_pts / 1e9) / (knn_ms / 1e3) if knn_ms > 0 else None,
+                                     "peak": peak, "unit": "GB/s", "note": "search-bound (L2-resident candidates), reported for the step's dominant kernel"},
+                "clocks": clocks.summary(),
+            }
 
     # ---- roofline of the linearize kernel on a cloud larger than L2 (rank 0, N = 1 only) ----
     if rank == 0 and world == 1 and not args.no_roofline:
         for g in handles:
             g.close()
-        del dev_tensors
+        dev_tensors = None
         torch.cuda.empty_cache()
         n = args.roofline_points
         src, tgt, Tgt = synth.tiled_cloud_pair(4000, n)
@@ -345,7 +351,10 @@ def main():
         g.set_input_target_device(dt.data_ptr(), n)
         g.set_input_source_device(ds.data_ptr(), n)
         T = Tgt.copy()
+        g.set_profiling(True)
         g.linearize(T)  # builds grids, covariances, correspondences
+        k0 = g.kernel_ms()
+        g.set_profiling(False)
         for _ in range(3):
             g.linearize(T)
             g.compute_error(T)
@@ -366,11 +375,14 @@ def main():
             "bytes_per_point": BYTES_PER_POINT_LINEARIZE, "ms_per_launch": lin_ms,
             "compute_error": {"ms_per_launch": err_ms, "achieved": BYTES_PER_POINT_LINEARIZE * n / 1e9 / (err_ms / 1e3)},
             "update_correspondences": {"ms_per_launch": corr_ms, "achieved": 148 * n / 1e9 / (corr_ms / 1e3), "bytes_per_point": 148},
+            "grid_build": {"ms_per_cloud": k0["grid"][0] / 2, "launches_per_cloud": k0["grid"][1] // 2},
+            "knn_covariance": {"ms_per_cloud": k0["knn_cov"][0] / 2, "achieved": BYTES_PER_POINT_KNNCOV * n / 1e9 / (k0["knn_cov"][0] / 2 / 1e3),
+                               "bytes_per_point": BYTES_PER_POINT_KNNCOV, "mqueries_per_s": n / 1e6 / (k0["knn_cov"][0] / 2 / 1e3)},
             "timing": "CUDA events on the handle's stream around each launch; working set 1.28 GB > L2",
         }
         g.close()
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.roofline_only:
         lib, kind, search, what = load_cpu_impl()
         lib.apdo_max_threads.restype = ctypes.c_int
         sample = host_pairs[:8]

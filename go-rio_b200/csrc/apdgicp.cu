@@ -188,6 +188,13 @@ struct apd_handle {
   int64_t k_launches[APD_K_COUNT] = {0};
   int max_reduce_blocks = 148 * 4;
   double cells_per_point = 8.0;
+  // kNN kernel choice: 0 auto (warp-per-point below knn_thread_min_n points and k <= 32, thread-per-point
+  // above: the warp kernel has the shorter critical path, the thread kernel the higher throughput),
+  // 1 warp, 2 thread. Override with APD_KNN_MODE=warp|thread.
+  int knn_mode = 0;
+  int knn_thread_min_n = 500000;
+  int knn_max_k() const { return knn_mode == 1 ? 32 : 128; }
+  bool knn_use_warp(int n, int k) const { return knn_mode == 1 || (knn_mode == 0 && k <= 32 && n < knn_thread_min_n); }
 };
 
 namespace {
@@ -344,6 +351,8 @@ void size_grid(const float bbox[6], int n, double cells_per_point, GridDesc& g, 
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+int ensure_small(apd_handle* h);
+
 int ensure_grid(apd_handle* h, Cloud& c) {
   if (c.grid_valid) return APD_OK;
   if (!c.present || c.n <= 0) return fail(h, APD_ERR_INVALID, "cloud not set");
@@ -370,6 +379,11 @@ int ensure_grid(apd_handle* h, Cloud& c) {
   w.scan_tmp = (uint32_t*)p;
   w.scan_tmp_elems = scan_elems;
   {
+    int rc = ensure_small(h);
+    if (rc != APD_OK) return rc;
+    w.ticket = reinterpret_cast<unsigned int*>(h->small.as<double>() + 42);
+  }
+  {
     ProfScope ps(h, APD_K_GRID);
     launch_grid_build(c.view(), w, h->stream, &h->launches);
   }
@@ -388,11 +402,15 @@ int ensure_covariances_of(apd_handle* h, Cloud& c) {
   APD_CUDA(h, c.geo64.ensure((size_t)c.n * sizeof(double)));
   if (!c.cov_valid) {
     const int k = h->params.k_correspondences;
-    if (k < 1 || k > 32) return fail(h, APD_ERR_UNSUPPORTED, "k_correspondences must be in [1, 32]");
+    if (k < 1 || k > h->knn_max_k()) return fail(h, APD_ERR_UNSUPPORTED, "k_correspondences out of range (1..128; 1..32 in warp mode)");
     if (c.n < k) return fail(h, APD_ERR_TOO_FEW, "cloud has fewer points than k_correspondences");
     ProfScope ps(h, APD_K_KNN_COV);
-    launch_knn_cov(c.view(), k, nullptr, h->stream, &h->launches);
-    launch_regularize(c.view(), h->params.regularization, h->stream, &h->launches);
+    if (h->knn_use_warp(c.n, k)) {
+      launch_knn_cov(c.view(), k, nullptr, h->stream, &h->launches);
+      launch_regularize(c.view(), h->params.regularization, h->stream, &h->launches);
+    } else {
+      launch_knn_cov_fused(c.view(), k, h->params.regularization, nullptr, h->stream, &h->launches);
+    }
     c.cov_valid = true;
     c.geo_valid = true;
   } else if (!c.geo_valid) {
@@ -754,6 +772,7 @@ int apd_create(int device, apd_handle** out) {
     const double v = std::atof(e);
     if (v > 0.01 && v < 1000.0) h->cells_per_point = v;
   }
+  if (const char* e = std::getenv("APD_KNN_MODE")) h->knn_mode = std::strcmp(e, "warp") == 0 ? 1 : (std::strcmp(e, "thread") == 0 ? 2 : 0);
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   for (int i = 0; i < 36; i++) h->final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity()
   *out = h;
@@ -837,7 +856,7 @@ int apd_get_neighbors(apd_handle* h, int32_t which, int32_t* out, int32_t n, int
   if (!h || !out) return APD_ERR_INVALID;
   Cloud& c = which == 0 ? h->src : h->tgt;
   if (!c.present || n != c.n || k != h->params.k_correspondences) return fail(h, APD_ERR_INVALID, "neighbour query does not match the cloud / k");
-  if (k < 1 || k > 32) return fail(h, APD_ERR_UNSUPPORTED, "k_correspondences must be in [1, 32]");
+  if (k < 1 || k > h->knn_max_k()) return fail(h, APD_ERR_UNSUPPORTED, "k_correspondences out of range (1..128; 1..32 in warp mode)");
   if (c.n < k) return fail(h, APD_ERR_TOO_FEW, "cloud has fewer points than k_correspondences");
   DeviceGuard dg(h->device);
   int rc = ensure_grid(h, c);
@@ -845,8 +864,13 @@ int apd_get_neighbors(apd_handle* h, int32_t which, int32_t* out, int32_t n, int
   const size_t nb_bytes = align_up((size_t)n * k * sizeof(int32_t), 256);
   APD_CUDA(h, h->scratch.ensure(nb_bytes + (size_t)n * 6 * sizeof(double)));
   CloudDev v = c.view();
-  v.cov = reinterpret_cast<double*>(h->scratch.as<char>() + nb_bytes);  // raw covariances go to scratch
-  launch_knn_cov(v, k, h->scratch.as<int32_t>(), h->stream, &h->launches);
+  if (h->knn_use_warp(c.n, k)) {
+    v.cov = reinterpret_cast<double*>(h->scratch.as<char>() + nb_bytes);  // raw covariances go to scratch
+    launch_knn_cov(v, k, h->scratch.as<int32_t>(), h->stream, &h->launches);
+  } else {
+    v.cov = nullptr;  // neighbours only
+    launch_knn_cov_fused(v, k, h->params.regularization, h->scratch.as<int32_t>(), h->stream, &h->launches);
+  }
   APD_CUDA(h, cudaGetLastError());
   APD_CUDA(h, cudaMemcpyAsync(out, h->scratch.p, (size_t)n * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   APD_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -29,22 +29,47 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ spts, int 
 // Exact nearest neighbour by (d2, original index). Expands Chebyshev shells of
 // cells until the best distance is provably final, or until every unscanned
 // point is farther than `limit` (then the caller rejects the match anyway).
+// G consecutive lanes share one query (G = 1, 2, 4, 8, 16, 32): the x-rows of a
+// shell are dealt round-robin to the G lanes and the group's best key is
+// min-reduced with shuffles after every shell, so the critical path of a query is
+// ~1/G of the single-thread scan (small source clouds are latency-bound).
+// All G lanes return the same result.
+template <int G>
 __device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
                                           float qx, float qy, float qz, double limit_sq, unsigned long long& best, int& best_pos) {
+  const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
   const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
   const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
   const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
   best = kInfKey;
   best_pos = -1;
+  // groups of one warp leave the shell loop at different times: shuffle within the group's own lanes only
+  const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+  auto group_min = [&]() {
+    if (G > 1) {
+#pragma unroll
+      for (int o = G >> 1; o > 0; o >>= 1) {
+        const unsigned long long ob = __shfl_xor_sync(gmask, best, o);
+        const int op = __shfl_xor_sync(gmask, best_pos, o);
+        if (ob < best) {
+          best = ob;
+          best_pos = op;
+        }
+      }
+    }
+  };
   // ring 0+1: 3x3x3 cube as 9 x-rows
   {
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); z++)
-      for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); y++) {
-        const int row = (z * g.ny + y) * g.nx;
-        scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
-      }
+    for (int ri = sub; ri < 9; ri += G) {
+      const int y = cy + (ri % 3) - 1, z = cz + (ri / 3) - 1;
+      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      const int row = (z * g.ny + y) * g.nx;
+      scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
+    }
+    group_min();
   }
+  const float mg = 0.002f * g.cell;
   for (int r = 1;; r++) {
     const float lb = ((float)r - 0.002f) * g.cell;
     const float lb2 = lb * lb;
@@ -52,20 +77,29 @@ __device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const
     if ((double)lb2 >= limit_sq) break;
     if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
     const int rr = r + 1;
+    const int side = 2 * rr + 1;
     const int xa = cx - rr, xb = cx + rr;
     const int x0 = max(xa, 0), x1 = min(xb, g.nx - 1);
-    for (int z = max(cz - rr, 0); z <= min(cz + rr, g.nz - 1); z++) {
-      const bool zb = (z == cz - rr) || (z == cz + rr);
-      for (int y = max(cy - rr, 0); y <= min(cy + rr, g.ny - 1); y++) {
-        const int row = (z * g.ny + y) * g.nx;
-        if (zb || y == cy - rr || y == cy + rr) {
-          scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
-        } else {
-          if (xa >= 0) scan_range(spts, (int)__ldg(&cell_start[row + xa]), (int)__ldg(&cell_start[row + xa + 1]), qx, qy, qz, best, best_pos);
-          if (xb < g.nx) scan_range(spts, (int)__ldg(&cell_start[row + xb]), (int)__ldg(&cell_start[row + xb + 1]), qx, qy, qz, best, best_pos);
-        }
+    for (int ri = sub; ri < side * side; ri += G) {
+      const int dy = ri % side - rr, dz = ri / side - rr;
+      const int y = cy + dy, z = cz + dz;
+      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      // skip the row if even its nearest point cannot beat the current best / the limit
+      const float loy = g.oy + (float)y * g.cell - mg, hiy = g.oy + (float)(y + 1) * g.cell + mg;
+      const float loz = g.oz + (float)z * g.cell - mg, hiz = g.oz + (float)(z + 1) * g.cell + mg;
+      const float ddy = fmaxf(0.f, fmaxf(loy - qy, qy - hiy)), ddz = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
+      const float dyz2 = (ddy * ddy + ddz * ddz) * 0.9999f;
+      if ((double)dyz2 >= limit_sq) continue;
+      if (best != kInfKey && dyz2 > __uint_as_float((unsigned)(best >> 32))) continue;
+      const int row = (z * g.ny + y) * g.nx;
+      if (dy == rr || dy == -rr || dz == rr || dz == -rr) {
+        scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
+      } else {
+        if (xa >= 0) scan_range(spts, (int)__ldg(&cell_start[row + xa]), (int)__ldg(&cell_start[row + xa + 1]), qx, qy, qz, best, best_pos);
+        if (xb < g.nx) scan_range(spts, (int)__ldg(&cell_start[row + xb]), (int)__ldg(&cell_start[row + xb + 1]), qx, qy, qz, best, best_pos);
       }
     }
+    group_min();
   }
 }
 
@@ -78,15 +112,17 @@ __device__ __forceinline__ PoseF pose_to_f32(const PoseD& T) {
   return f;
 }
 
-template <bool kFp64>
+template <bool kFp64, int G>
 __global__ void __launch_bounds__(kThreads) update_corr_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_label,
                                                                const double* __restrict__ s_cov, int n_src,
                                                                const float4* __restrict__ t_spts, const float* __restrict__ t_label,
                                                                const double* __restrict__ t_cov, const uint32_t* __restrict__ t_cell_start,
                                                                GridDesc tg, PoseD T, NoiseParams np, int* __restrict__ corr,
                                                                float* __restrict__ sqd, void* __restrict__ mahaA, void* __restrict__ mahaB) {
-  const int i = blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n_src) return;
+  // G lanes per source point (kThreads and the warp size are multiples of G, so a group never straddles a warp;
+  // the grid is sized so that whole warps are either in range or carry clamped duplicates of the last point)
+  const int gi = (blockIdx.x * kThreads + threadIdx.x) / G;
+  const int i = min(gi, n_src - 1);
   const PoseF Tf = pose_to_f32(T);
   const float4 a = s_spts[i];
   float px, py, pz;
@@ -94,7 +130,8 @@ __global__ void __launch_bounds__(kThreads) update_corr_kernel(const float4* __r
 
   unsigned long long best;
   int pos;
-  nn_search(t_spts, t_cell_start, tg, px, py, pz, np.thr_sq, best, pos);  // :178
+  nn_search<G>(t_spts, t_cell_start, tg, px, py, pz, np.thr_sq, best, pos);  // :178
+  if (gi >= n_src || (G > 1 && (threadIdx.x & (G - 1)) != 0)) return;  // one lane per point finishes the job
   const float d2 = (best == kInfKey) ? 3.402823466e38f : __uint_as_float((unsigned)(best >> 32));
   sqd[i] = d2;  // :180
   const bool ok = (best != kInfKey) && ((double)d2 < np.thr_sq);  // :183
@@ -189,7 +226,7 @@ __global__ void __launch_bounds__(kFitThreads) fitness_kernel(const float4* __re
     transform_rn(Tf, a.x, a.y, a.z, px, py, pz);
     unsigned long long best;
     int pos;
-    nn_search(t_spts, t_cell_start, tg, px, py, pz, 1e300, best, pos);
+    nn_search<1>(t_spts, t_cell_start, tg, px, py, pz, 1e300, best, pos);
     if (best != kInfKey) {
       const double d2 = (double)__uint_as_float((unsigned)(best >> 32));
       if (d2 <= max_range) { sum += d2; nr += 1.0; }
@@ -272,13 +309,20 @@ __global__ void __launch_bounds__(256) transform_cloud_kernel(const float4* __re
 void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const NoiseParams& np,
                                    const CorrOut& out, cudaStream_t s, int64_t* launches) {
   if (src.n <= 0) return;
-  const int blocks = (src.n + kThreads - 1) / kThreads;
-  if (out.maha_fp64)
-    update_corr_kernel<true><<<blocks, kThreads, 0, s>>>(src.spts, src.label, src.cov, src.n, tgt.spts, tgt.label, tgt.cov, tgt.cell_start,
-                                                         tgt.g, T, np, out.corr, out.sqd, out.mahaA, out.mahaB);
-  else
-    update_corr_kernel<false><<<blocks, kThreads, 0, s>>>(src.spts, src.label, src.cov, src.n, tgt.spts, tgt.label, tgt.cov, tgt.cell_start,
-                                                          tgt.g, T, np, out.corr, out.sqd, out.mahaA, out.mahaB);
+#define APD_CORR(FP64, GG)                                                                                                              \
+  update_corr_kernel<FP64, GG><<<(unsigned)(((size_t)src.n * GG + kThreads - 1) / kThreads), kThreads, 0, s>>>(                           \
+      src.spts, src.label, src.cov, src.n, tgt.spts, tgt.label, tgt.cov, tgt.cell_start, tgt.g, T, np, out.corr, out.sqd, out.mahaA, \
+      out.mahaB)
+  // small source clouds are latency-bound: 8 lanes share a query; large ones are throughput-bound: one lane per query
+  const bool wide = src.n < 65536;
+  if (out.maha_fp64) {
+    if (wide) APD_CORR(true, 8);
+    else APD_CORR(true, 1);
+  } else {
+    if (wide) APD_CORR(false, 8);
+    else APD_CORR(false, 1);
+  }
+#undef APD_CORR
   (*launches)++;
 }
 

@@ -201,6 +201,124 @@ __global__ void __launch_bounds__(kThreads) reorder_kernel(const float4* __restr
   inv_perm[idx] = s;
 }
 
+// ------------------------------------------------- small-cloud path ----
+// For clouds of at most kSmallCloud points the stable sort is done without radix
+// passes (5 launches instead of ~20): atomic per-cell ranks place the points of a
+// cell in arbitrary order, then every point counts the points of its cell with a
+// smaller original index to find its deterministic slot.
+__global__ void __launch_bounds__(kThreads) cell_keys_rank_kernel(const float4* __restrict__ pts, int n, GridDesc g,
+                                                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ nd_rank,
+                                                                  uint32_t* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  const int cx = cell_coord(p.x, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(p.y, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(p.z, g.oz, g.inv_cell, g.nz);
+  const uint32_t key = (uint32_t)((cz * g.ny + cy) * g.nx + cx);
+  keys[i] = key;
+  nd_rank[i] = atomicAdd(&counts[key], 1u);
+}
+
+// tile-wise exclusive scan (in place); the last block to finish scans the tile totals
+__global__ void __launch_bounds__(kThreads) scan_tiles_last_kernel(uint32_t* data, size_t n, uint32_t* __restrict__ tile_sums,
+                                                                   unsigned int* __restrict__ ticket) {
+  __shared__ uint32_t warp_tot[kThreads / 32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * 8;
+    uint32_t v[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      v[j] = (base + j < n) ? data[base + j] : 0u;
+      sum += v[j];
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint32_t warp_off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) {
+      const uint32_t t = warp_tot[w];
+      if (w < warp) warp_off += t;
+      total += t;
+    }
+    uint32_t run = warp_off + inc - sum;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (base + j < n) data[base + j] = run;
+      run += v[j];
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // exclusive scan of up to 2048 tile totals by this block
+  const int nt = (int)gridDim.x;
+  uint32_t v[8], sum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int t = threadIdx.x * 8 + j;
+    v[j] = t < nt ? __ldcg(&tile_sums[t]) : 0u;
+    sum += v[j];
+  }
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  uint32_t warp_off = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; w++)
+    if (w < warp) warp_off += warp_tot[w];
+  uint32_t run = warp_off + inc - sum;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int t = threadIdx.x * 8 + j;
+    if (t < nt) tile_sums[t] = run;
+    run += v[j];
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+}
+
+__global__ void __launch_bounds__(kThreads) scatter_nd_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ nd_rank, int n,
+                                                              const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ tmp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  tmp[cell_start[keys[i]] + nd_rank[i]] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(kThreads) rank_fix_reorder_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ keys,
+                                                                    const uint32_t* __restrict__ tmp, int n,
+                                                                    const uint32_t* __restrict__ cell_start, float4* __restrict__ spts,
+                                                                    float* __restrict__ label, int* __restrict__ inv_perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t key = keys[i];
+  const uint32_t b = cell_start[key], e = cell_start[key + 1];
+  uint32_t r = 0;
+  for (uint32_t j = b; j < e; j++) r += (tmp[j] < (uint32_t)i) ? 1u : 0u;
+  const int s = (int)(b + r);
+  const float4 p = pts[i];
+  spts[s] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  label[s] = p.w;
+  inv_perm[i] = s;
+}
+
 }  // namespace
 
 size_t scan_tmp_elems_for(size_t n) {
@@ -226,6 +344,20 @@ void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int
   if (n <= 0) return;
   cudaMemsetAsync(c.cell_start, 0, sizeof(uint32_t) * ((size_t)c.ncells + 1), s);
   const int pblocks = (n + kThreads - 1) / kThreads;
+  const size_t ncs = (size_t)c.ncells + 1;
+  const size_t tiles = (ncs + kScanTile - 1) / kScanTile;
+  if (n <= kSmallCloud && tiles <= (size_t)kScanTile && w.ticket != nullptr) {
+    cell_keys_rank_kernel<<<pblocks, kThreads, 0, s>>>(c.pts, n, c.g, w.keys[0], w.vals[0], c.cell_start);
+    scan_tiles_last_kernel<<<(unsigned)tiles, kThreads, 0, s>>>(c.cell_start, ncs, w.scan_tmp, w.ticket);
+    if (tiles > 1) {
+      scan_add_kernel<<<(unsigned)tiles, kThreads, 0, s>>>(c.cell_start, ncs, w.scan_tmp);
+      (*launches)++;
+    }
+    scatter_nd_kernel<<<pblocks, kThreads, 0, s>>>(w.keys[0], w.vals[0], n, c.cell_start, w.vals[1]);
+    rank_fix_reorder_kernel<<<pblocks, kThreads, 0, s>>>(c.pts, w.keys[0], w.vals[1], n, c.cell_start, c.spts, c.label, c.inv_perm);
+    (*launches) += 4;
+    return;
+  }
   cell_keys_kernel<<<pblocks, kThreads, 0, s>>>(c.pts, n, c.g, w.keys[0], w.vals[0], c.cell_start);
   (*launches)++;
   exclusive_scan(c.cell_start, (size_t)c.ncells + 1, w.scan_tmp, s, launches);

@@ -27,7 +27,9 @@ struct GridWork {
   uint32_t* hist;       // [256 * sort_blocks]
   uint32_t* scan_tmp;   // block sums for the multi-level scan
   size_t scan_tmp_elems;
+  unsigned int* ticket; // zero-initialised counter for the small-cloud scan (reset by the kernel)
 };
+constexpr int kSmallCloud = 65536;  // at most this many points: rank-by-counting path (see grid.cu)
 constexpr int kSortTile = 2048;  // keys per block in the radix sort
 constexpr int kScanTile = 2048;  // elements per block in the scan
 size_t scan_tmp_elems_for(size_t n);
@@ -44,6 +46,9 @@ void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int
 // regularisation (:374-405) and the geometric weight (:266-269), one thread per
 // point. neighbors: optional int32[n*k] in ORIGINAL point order / original ids.
 void launch_knn_cov(const CloudDev& c, int k, int32_t* neighbors, cudaStream_t s, int64_t* launches);
+// thread-per-point variant with the regularisation and geometric weight fused in (k <= 128);
+// c.cov == nullptr: neighbours only.
+void launch_knn_cov_fused(const CloudDev& c, int k, int regularization, int32_t* neighbors, cudaStream_t s, int64_t* launches);
 void launch_regularize(const CloudDev& c, int regularization, cudaStream_t s, int64_t* launches);
 // geo weight only (after set*Covariances)
 void launch_geo_weight(const CloudDev& c, cudaStream_t s, int64_t* launches);

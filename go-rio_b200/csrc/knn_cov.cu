@@ -22,12 +22,61 @@ __device__ __forceinline__ unsigned long long shfl_up64(unsigned long long v, in
   return __shfl_up_sync(kFull, v, d);
 }
 
+__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
+
+// ascending bitonic sort of one 64-bit key per lane
+__device__ __forceinline__ unsigned long long bitonic_sort32(unsigned long long key, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(kFull, key, stride);
+      const bool up = (lane & size) == 0;        // this block sorts ascending
+      const bool lower = (lane & stride) == 0;   // this lane is the lower one of the pair
+      key = (lower == up) ? umin64(key, other) : umax64(key, other);
+    }
+  }
+  return key;
+}
+// list (ascending, one key per lane) <- the 32 smallest of list U batch (batch ascending)
+__device__ __forceinline__ unsigned long long merge_keep32(unsigned long long list, unsigned long long batch, int lane) {
+  const unsigned long long rb = shfl64(batch, 31 - lane);
+  unsigned long long c = umin64(list, rb);  // bitonic sequence holding the 32 smallest
+#pragma unroll
+  for (int stride = 16; stride > 0; stride >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(kFull, c, stride);
+    c = ((lane & stride) == 0) ? umin64(c, other) : umax64(c, other);
+  }
+  return c;
+}
+
+// Per-warp state of the k-best search: `list` holds the 32 smallest keys seen so far
+// (ascending over the lanes; the answer is lanes 0..k-1), `kth` the k-th of them, and
+// `buf` (shared memory, 32 keys) collects candidates below `kth` until they are merged
+// in one bitonic sort + merge — ~6 instructions per candidate instead of ~22 for
+// inserting them one by one.
+struct KBest {
+  unsigned long long list, kth;
+  unsigned long long* buf;
+  int buf_n;
+};
+__device__ __forceinline__ void kbest_flush(KBest& s, int lane, int k) {
+  if (s.buf_n == 0) return;  // warp-uniform
+  __syncwarp();
+  unsigned long long b = lane < s.buf_n ? s.buf[lane] : kInfKey;
+  __syncwarp();
+  b = bitonic_sort32(b, lane);
+  s.list = merge_keep32(s.list, b, lane);
+  s.kth = shfl64(s.list, k - 1);
+  s.buf_n = 0;
+}
+
 // Warp-wide candidate scan. Every lane passes one segment [b, b+cnt) of the
 // cell-sorted point array (cnt may be 0). The segments are flattened so that
 // all 32 lanes test candidates even when segments are short (sparse cells).
-// The warp keeps the k best (d2, idx) keys sorted ascending, one per lane.
 __device__ __forceinline__ void scan_segments(const float4* __restrict__ spts, float qx, float qy, float qz, int lane, int k,
-                                              int b, int cnt, unsigned long long& mykey, unsigned long long& kth) {
+                                              int b, int cnt, KBest& s) {
   int incl = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -36,6 +85,7 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ spts, f
   }
   const int total = __shfl_sync(kFull, incl, 31);
   const int excl = incl - cnt;
+  const unsigned lt = (1u << lane) - 1u;
   for (int base = 0; base < total; base += 32) {
     const int t = base + lane;
     const bool valid = t < total;
@@ -52,21 +102,18 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ spts, f
     const float4 p = spts[bj + (tt - ej)];
     const float d2 = sqdist_rn(qx, qy, qz, p.x, p.y, p.z);
     const unsigned long long key = pack_key(d2, __float_as_int(p.w));
-    unsigned mask = __ballot_sync(kFull, valid && key < kth);
-    while (mask) {
-      const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const unsigned long long ck = shfl64(key, src);
-      if (ck < kth) {  // warp-uniform
-        const int pos = __popc(__ballot_sync(kFull, mykey < ck));
-        const unsigned long long up = shfl_up64(mykey, 1);
-        if (lane < k) {
-          if (lane > pos) mykey = up;
-          else if (lane == pos) mykey = ck;
-        }
-        kth = shfl64(mykey, k - 1);
-      }
+    bool pass = valid && key < s.kth;
+    unsigned mask = __ballot_sync(kFull, pass);
+    int m = __popc(mask);
+    if (m == 0) continue;
+    if (s.buf_n + m > 32) {
+      kbest_flush(s, lane, k);
+      pass = pass && key < s.kth;  // the threshold just dropped
+      mask = __ballot_sync(kFull, pass);
+      m = __popc(mask);
     }
+    if (pass) s.buf[s.buf_n + __popc(mask & lt)] = key;
+    s.buf_n += m;
   }
 }
 
@@ -82,7 +129,12 @@ __global__ void __launch_bounds__(kThreads) knn_cov_kernel(const float4* __restr
   const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
   const int cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz);
 
-  unsigned long long mykey = kInfKey, kth = kInfKey;
+  __shared__ unsigned long long kbuf[kThreads / 32][32];
+  KBest st;
+  st.list = kInfKey;
+  st.kth = kInfKey;
+  st.buf = kbuf[threadIdx.x >> 5];
+  st.buf_n = 0;
 
   // ring 0+1: the 3x3x3 cube as 9 x-rows
   {
@@ -96,20 +148,22 @@ __global__ void __launch_bounds__(kThreads) knn_cov_kernel(const float4* __restr
         cnt = (int)cell_start[row + x1 + 1] - b;
       }
     }
-    scan_segments(spts, q.x, q.y, q.z, lane, k, b, cnt, mykey, kth);
+    scan_segments(spts, q.x, q.y, q.z, lane, k, b, cnt, st);
+    kbest_flush(st, lane, k);
   }
   // shells r = 2, 3, ... until the k-th distance is provably final:
   // every unscanned point is at least (r - 0.002) cells away.
   for (int r = 1;; r++) {
     const float lb = ((float)r - 0.002f) * g.cell;
-    const float kd2 = __uint_as_float((unsigned)(kth >> 32));
-    if (kth != kInfKey && kd2 < lb * lb) break;
+    const float kd2 = __uint_as_float((unsigned)(st.kth >> 32));
+    if (st.kth != kInfKey && kd2 < lb * lb) break;
     if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
     const int rr = r + 1;  // shell to scan now
     const int side = 2 * rr + 1;
     const int nslots = 2 * side * side;
     for (int sbase = 0; sbase < nslots; sbase += 32) {
       const int slot = sbase + lane;
+      const float kd2cur = __uint_as_float((unsigned)(st.kth >> 32));  // shrinks as the shell is scanned
       int b = 0, cnt = 0;
       if (slot < nslots) {
         const int rowid = slot >> 1, which = slot & 1;
@@ -126,14 +180,27 @@ __global__ void __launch_bounds__(kThreads) knn_cov_kernel(const float4* __restr
             if (x >= 0 && x < g.nx) { x0 = x; x1 = x; }
           }
           if (x0 <= x1) {
-            b = (int)cell_start[row + x0];
-            cnt = (int)cell_start[row + x1 + 1] - b;
+            // prune the segment if its (slightly grown) box is farther than the current k-th distance
+            const float m = 0.002f * g.cell;
+            const float lox = g.ox + (float)x0 * g.cell - m, hix = g.ox + (float)(x1 + 1) * g.cell + m;
+            const float loy = g.oy + (float)y * g.cell - m, hiy = g.oy + (float)(y + 1) * g.cell + m;
+            const float loz = g.oz + (float)z * g.cell - m, hiz = g.oz + (float)(z + 1) * g.cell + m;
+            const float ddx = fmaxf(0.f, fmaxf(lox - q.x, q.x - hix));
+            const float ddy = fmaxf(0.f, fmaxf(loy - q.y, q.y - hiy));
+            const float ddz = fmaxf(0.f, fmaxf(loz - q.z, q.z - hiz));
+            const float mind2 = (ddx * ddx + ddy * ddy + ddz * ddz) * 0.9999f;
+            if (st.kth == kInfKey || !(mind2 > kd2cur)) {
+              b = (int)cell_start[row + x0];
+              cnt = (int)cell_start[row + x1 + 1] - b;
+            }
           }
         }
       }
-      if (__ballot_sync(kFull, cnt > 0)) scan_segments(spts, q.x, q.y, q.z, lane, k, b, cnt, mykey, kth);
+      if (__ballot_sync(kFull, cnt > 0)) scan_segments(spts, q.x, q.y, q.z, lane, k, b, cnt, st);
     }
+    kbest_flush(st, lane, k);
   }
+  const unsigned long long mykey = st.list;
 
   // covariance of the k neighbours (reference :366-372): fp64, centred, / k
   const int nidx = (lane < k) ? (int)(unsigned)(mykey & 0xffffffffull) : 0;
@@ -166,12 +233,8 @@ __device__ __forceinline__ double geo_weight_of(const Sym3& C) {
   return fabs(l[2]) / fabs(l[0]);  // sigma3 / sigma1 (reference :268-269)
 }
 
-__global__ void __launch_bounds__(kThreads) regularize_kernel(double* __restrict__ cov, float* __restrict__ geo, double* __restrict__ geo64, int n, int reg) {
-  const int i = blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n) return;
-  Sym3 C;
-#pragma unroll
-  for (int e = 0; e < 6; e++) C.v[e] = cov[(size_t)i * 6 + e];
+// regularisation of one covariance (reference :374-405), symmetric storage
+__device__ __forceinline__ Sym3 regularize_sym3(const Sym3& C, int reg) {
   Sym3 out = C;
   if (reg == 0) {  // NONE (:374-376)
   } else if (reg == 4) {  // FROBENIUS (:377-383)
@@ -203,11 +266,179 @@ __global__ void __launch_bounds__(kThreads) regularize_kernel(double* __restrict
       out.v[e] = s;
     }
   }
+  return out;
+}
+
+__global__ void __launch_bounds__(kThreads) regularize_kernel(double* __restrict__ cov, float* __restrict__ geo, double* __restrict__ geo64, int n, int reg) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  Sym3 C;
+#pragma unroll
+  for (int e = 0; e < 6; e++) C.v[e] = cov[(size_t)i * 6 + e];
+  const Sym3 out = regularize_sym3(C, reg);
 #pragma unroll
   for (int e = 0; e < 6; e++) cov[(size_t)i * 6 + e] = out.v[e];
   const double gw = geo_weight_of(out);
   geo[i] = (float)gw;
   geo64[i] = gw;
+}
+
+// ---------------------------------------------------------------------------
+// Thread-per-point exact kNN + covariance + regularisation, fused.
+// Each thread keeps its k best (d2, idx) keys in a max-heap in shared memory
+// (column tid of two [k][128] uint32 arrays: conflict-free), so one warp serves
+// 32 queries at once; neighbouring threads are neighbouring points of the
+// cell-sorted cloud and walk nearly the same cells (L1 hits, little divergence).
+// ---------------------------------------------------------------------------
+constexpr int kKnnT = 128;
+
+__device__ __forceinline__ unsigned long long heap_get(const uint32_t* hd, const uint32_t* hi, int slot, int tid) {
+  return ((unsigned long long)hd[slot * kKnnT + tid] << 32) | hi[slot * kKnnT + tid];
+}
+__device__ __forceinline__ void heap_set(uint32_t* hd, uint32_t* hi, int slot, int tid, unsigned long long key) {
+  hd[slot * kKnnT + tid] = (uint32_t)(key >> 32);
+  hi[slot * kKnnT + tid] = (uint32_t)key;
+}
+// put `key` at the root of a max-heap of `size` slots and sift it down
+__device__ __forceinline__ void heap_sift_root(uint32_t* hd, uint32_t* hi, int size, int tid, unsigned long long key) {
+  int pos = 0;
+  for (;;) {
+    int c = 2 * pos + 1;
+    if (c >= size) break;
+    unsigned long long kc = heap_get(hd, hi, c, tid);
+    if (c + 1 < size) {
+      const unsigned long long k2 = heap_get(hd, hi, c + 1, tid);
+      if (k2 > kc) { kc = k2; c = c + 1; }
+    }
+    if (kc <= key) break;
+    heap_set(hd, hi, pos, tid, kc);
+    pos = c;
+  }
+  heap_set(hd, hi, pos, tid, key);
+}
+
+__device__ __forceinline__ void knn_scan_range(const float4* __restrict__ spts, int b, int e, float qx, float qy, float qz,
+                                               uint32_t* hd, uint32_t* hi, int k, int tid, unsigned long long& top) {
+  for (int j = b; j < e; j++) {
+    const float4 p = __ldg(&spts[j]);
+    const unsigned long long key = pack_key(sqdist_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+    if (key < top) {
+      heap_sift_root(hd, hi, k, tid, key);
+      top = heap_get(hd, hi, 0, tid);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kKnnT) knn_cov_thread_kernel(const float4* __restrict__ spts, const float4* __restrict__ pts,
+                                                               const uint32_t* __restrict__ cell_start, GridDesc g, int n, int k, int reg,
+                                                               double* __restrict__ cov, float* __restrict__ geo, double* __restrict__ geo64,
+                                                               int32_t* __restrict__ neighbors) {
+  extern __shared__ uint32_t heap_smem[];
+  uint32_t* hd = heap_smem;               // [k][128] d2 bits
+  uint32_t* hi = heap_smem + k * kKnnT;   // [k][128] original index
+  const int tid = threadIdx.x;
+  const int w = blockIdx.x * kKnnT + tid;
+  if (w >= n) return;
+  for (int j = 0; j < k; j++) heap_set(hd, hi, j, tid, kInfKey);
+  unsigned long long top = kInfKey;
+
+  const float4 q = spts[w];
+  const int qi = __float_as_int(q.w);
+  const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz);
+
+  // ring 0+1: the 3x3x3 cube as up to 9 x-rows
+  {
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); z++)
+      for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); y++) {
+        const int row = (z * g.ny + y) * g.nx;
+        knn_scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), q.x, q.y, q.z, hd, hi, k, tid, top);
+      }
+  }
+  // shells r = 2, 3, ...: every unscanned point is at least (r - 0.002) cells away
+  const float mg = 0.002f * g.cell;
+  for (int r = 1;; r++) {
+    const float lb = ((float)r - 0.002f) * g.cell;
+    if (top != kInfKey && __uint_as_float((unsigned)(top >> 32)) < lb * lb) break;
+    if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
+    const int rr = r + 1;
+    const int xa = cx - rr, xb = cx + rr;
+    const int x0 = max(xa, 0), x1 = min(xb, g.nx - 1);
+    for (int z = max(cz - rr, 0); z <= min(cz + rr, g.nz - 1); z++) {
+      const bool zb = (z == cz - rr) || (z == cz + rr);
+      const float loz = g.oz + (float)z * g.cell - mg, hiz = g.oz + (float)(z + 1) * g.cell + mg;
+      const float ddz = fmaxf(0.f, fmaxf(loz - q.z, q.z - hiz));
+      for (int y = max(cy - rr, 0); y <= min(cy + rr, g.ny - 1); y++) {
+        const float loy = g.oy + (float)y * g.cell - mg, hiy = g.oy + (float)(y + 1) * g.cell + mg;
+        const float ddy = fmaxf(0.f, fmaxf(loy - q.y, q.y - hiy));
+        const float dyz2 = ddy * ddy + ddz * ddz;
+        const float kd2 = __uint_as_float((unsigned)(top >> 32));
+        // prune the whole row if even its nearest point is farther than the current k-th distance
+        if (top != kInfKey && dyz2 * 0.9999f > kd2) continue;
+        const int row = (z * g.ny + y) * g.nx;
+        if (zb || y == cy - rr || y == cy + rr) {
+          knn_scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), q.x, q.y, q.z, hd, hi, k, tid, top);
+        } else {
+          if (xa >= 0) {
+            const float hix = g.ox + (float)(xa + 1) * g.cell + mg;
+            const float ddx = fmaxf(0.f, q.x - hix);
+            if (top == kInfKey || !((dyz2 + ddx * ddx) * 0.9999f > __uint_as_float((unsigned)(top >> 32))))
+              knn_scan_range(spts, (int)__ldg(&cell_start[row + xa]), (int)__ldg(&cell_start[row + xa + 1]), q.x, q.y, q.z, hd, hi, k, tid, top);
+          }
+          if (xb < g.nx) {
+            const float lox = g.ox + (float)xb * g.cell - mg;
+            const float ddx = fmaxf(0.f, lox - q.x);
+            if (top == kInfKey || !((dyz2 + ddx * ddx) * 0.9999f > __uint_as_float((unsigned)(top >> 32))))
+              knn_scan_range(spts, (int)__ldg(&cell_start[row + xb]), (int)__ldg(&cell_start[row + xb + 1]), q.x, q.y, q.z, hd, hi, k, tid, top);
+          }
+        }
+      }
+    }
+  }
+
+  // heap-sort in place -> ascending (d2, idx)
+  for (int m = k - 1; m >= 1; m--) {
+    const unsigned long long last = heap_get(hd, hi, m, tid);
+    heap_set(hd, hi, m, tid, heap_get(hd, hi, 0, tid));
+    heap_sift_root(hd, hi, m, tid, last);
+  }
+  if (neighbors)
+    for (int j = 0; j < k; j++) neighbors[(size_t)qi * k + j] = (int)hi[j * kKnnT + tid];
+  if (!cov) return;
+
+  // covariance of the k neighbours (reference :366-372): fp64, sums in neighbour order with
+  // one rounding per operation (the CPU path's operation order), centred, divided by k
+  double mx = 0.0, my = 0.0, mz = 0.0;
+  for (int j = 0; j < k; j++) {
+    const float4 p = __ldg(&pts[hi[j * kKnnT + tid]]);
+    mx = __dadd_rn(mx, (double)p.x);
+    my = __dadd_rn(my, (double)p.y);
+    mz = __dadd_rn(mz, (double)p.z);
+  }
+  mx /= (double)k; my /= (double)k; mz /= (double)k;
+  Sym3 C;
+#pragma unroll
+  for (int e = 0; e < 6; e++) C.v[e] = 0.0;
+  for (int j = 0; j < k; j++) {
+    const float4 p = __ldg(&pts[hi[j * kKnnT + tid]]);
+    const double dx = __dsub_rn((double)p.x, mx), dy = __dsub_rn((double)p.y, my), dz = __dsub_rn((double)p.z, mz);
+    C.v[0] = __dadd_rn(C.v[0], __dmul_rn(dx, dx));
+    C.v[1] = __dadd_rn(C.v[1], __dmul_rn(dx, dy));
+    C.v[2] = __dadd_rn(C.v[2], __dmul_rn(dx, dz));
+    C.v[3] = __dadd_rn(C.v[3], __dmul_rn(dy, dy));
+    C.v[4] = __dadd_rn(C.v[4], __dmul_rn(dy, dz));
+    C.v[5] = __dadd_rn(C.v[5], __dmul_rn(dz, dz));
+  }
+#pragma unroll
+  for (int e = 0; e < 6; e++) C.v[e] /= (double)k;
+  const Sym3 out = regularize_sym3(C, reg);
+#pragma unroll
+  for (int e = 0; e < 6; e++) cov[(size_t)w * 6 + e] = out.v[e];
+  const double gw = geo_weight_of(out);
+  geo[w] = (float)gw;
+  geo64[w] = gw;
 }
 
 __global__ void __launch_bounds__(kThreads) geo_weight_kernel(const double* __restrict__ cov, float* __restrict__ geo, double* __restrict__ geo64, int n) {
@@ -253,6 +484,14 @@ __global__ void __launch_bounds__(kThreads) cov_import_kernel(const double* __re
 
 }  // namespace
 
+void launch_knn_cov_fused(const CloudDev& c, int k, int regularization, int32_t* neighbors, cudaStream_t s, int64_t* launches) {
+  if (c.n <= 0) return;
+  const size_t smem = (size_t)2 * k * kKnnT * sizeof(uint32_t);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(knn_cov_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  knn_cov_thread_kernel<<<(c.n + kKnnT - 1) / kKnnT, kKnnT, smem, s>>>(c.spts, c.pts, c.cell_start, c.g, c.n, k, regularization, c.cov, c.geo,
+                                                                        c.geo64, neighbors);
+  (*launches)++;
+}
 void launch_knn_cov(const CloudDev& c, int k, int32_t* neighbors, cudaStream_t s, int64_t* launches) {
   if (c.n <= 0) return;
   const long long threads = (long long)c.n * 32;

@@ -44,7 +44,7 @@ def c2_small(synth):
 
 
 # ---------------------------------------------------------------- kNN ----
-@pytest.mark.parametrize("k", [1, 5, 20, 32])
+@pytest.mark.parametrize("k", [1, 5, 20, 32, 50])
 def test_knn_indices_bit_exact(gorio, c1, k):
     src, tgt, _ = c1
     g, o = make(gorio, src, tgt, k_correspondences=k)
@@ -58,6 +58,29 @@ def test_knn_indices_bit_exact_submap(gorio, c2):
     g, o = make(gorio, src, tgt)
     o.get_target_covariances()
     assert np.array_equal(g.get_neighbors(1), o.get_neighbors(1))
+
+
+def test_knn_warp_and_thread_kernels_match(gorio, c2_small, monkeypatch):
+    """APD_KNN_MODE selects the warp-per-point or the thread-per-point kNN kernel (auto: by cloud
+    size): same neighbours, same covariances"""
+    src, tgt, _ = c2_small
+    monkeypatch.setenv("APD_KNN_MODE", "thread")
+    g = gorio.FastAPDGICP(0)
+    monkeypatch.setenv("APD_KNN_MODE", "warp")
+    gw = gorio.FastAPDGICP(0)
+    monkeypatch.delenv("APD_KNN_MODE")
+    for r in (g, gw):
+        r.set_input_target(tgt); r.set_input_source(src)
+    assert np.array_equal(g.get_neighbors(1), gw.get_neighbors(1))
+    assert np.abs(g.get_target_covariances() - gw.get_target_covariances()).max() < 1e-12
+
+
+def test_raw_covariance_bit_exact(gorio, c2_small, monkeypatch):
+    """NONE regularisation: the thread-per-point kernel sums in the oracle's order with one rounding per operation"""
+    src, tgt, _ = c2_small
+    monkeypatch.setenv("APD_KNN_MODE", "thread")
+    g, o = make(gorio, src, tgt, regularization=0)
+    assert np.array_equal(g.get_target_covariances(), o.get_target_covariances())
 
 
 def test_knn_clustered_and_degenerate_geometry(gorio):
@@ -317,7 +340,7 @@ def test_error_codes(gorio, c1):
     with pytest.raises(gorio.ApdError) as e:
         g.align()
     assert e.value.code == 3
-    g.set_params(k_correspondences=33)
+    g.set_params(k_correspondences=129)
     g.set_input_source(src)
     with pytest.raises(gorio.ApdError) as e:
         g.align()
