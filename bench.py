@@ -47,7 +47,7 @@ BYTES_PER_POINT_KNNCOV = 68     # read point 16, write cov 48 + geo 4
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=32, help="scan/submap pairs per step and per GPU")
@@ -71,6 +71,13 @@ def make_pairs(synth, rank, n_pairs, distinct=8):
     return [base[i % len(base)] for i in range(n_pairs)]
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 # ------------------------------------------------------------ reference arm ----
 def load_cpu_impl():
     from oracle_binding import ORACLE_REF_SO, oracle_lib  # tests/oracle_binding.py (checker side)
@@ -90,7 +97,8 @@ def cpu_registrations(lib, search, pairs, reps):
     p.transformation_epsilon = DEPLOYED["transformation_epsilon"]
     lib.apdo_set_params(h, ctypes.byref(p))
     lib.apdo_set_search(h, ctypes.c_int(search))
-    lib.apdo_set_num_threads(h, ctypes.c_int(0))  # setNumThreads(0) = all cores (registrations.cpp:41)
+    # setNumThreads(0) = all cores (registrations.cpp:41); torchrun exports OMP_NUM_THREADS=1, so ask for the cores explicitly
+    lib.apdo_set_num_threads(h, ctypes.c_int(host_cores()))
     ms = (ctypes.c_double * reps)()
     total = 0.0
     for s, t in pairs:
@@ -109,8 +117,7 @@ def run_reference(args):
         return
     synth = importlib.import_module("go-rio_b200.synth")
     lib, kind, search, what = load_cpu_impl()
-    lib.apdo_max_threads.restype = ctypes.c_int
-    cores = lib.apdo_max_threads()
+    cores = host_cores()
     pairs = make_pairs(synth, 0, args.ref_pairs, distinct=min(8, args.ref_pairs))
     for _ in range(args.warmup):
         cpu_registrations(lib, search, pairs[:1], 1)
@@ -154,7 +161,7 @@ class ClockSampler:
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -393,7 +400,7 @@ def main():
                 uniq.append((s, t))
         cpu_registrations(lib, search, uniq[:1], 1)
         t_cpu, n_cpu = cpu_registrations(lib, search, uniq, 3)
-        line["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": UNIT, "cores": lib.apdo_max_threads(), "kind": kind,
+        line["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": UNIT, "cores": host_cores(), "kind": kind,
                                 "sample": f"{len(uniq)} of the step's pairs x 3 repetitions ({t_cpu:.1f} s wall); {what}"}
 
     if rank == 0:

@@ -1,0 +1,56 @@
+"""The C++ drop-in class (go-rio_b200/include/fast_gicp/gicp/fast_apdgicp.hpp):
+compiles against a stub of the pcl::Registration interface (no PCL/Eigen in this
+image), and — on a GPU — gives the same result as the C-ABI driven from ctypes
+when used the way 4DRadarSLAM's factory and nodelets use it."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM_DIR = os.path.join(REPO, "go-rio_b200", "shim_test")
+
+
+def test_shim_compiles_against_the_registration_interface(gorio):
+    if not os.path.exists(gorio.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    subprocess.check_call(["bash", os.path.join(SHIM_DIR, "build.sh")], env={**os.environ, "MAKEFLAGS": ""})
+    assert os.path.exists(os.path.join(SHIM_DIR, "test_shim"))
+
+
+def test_shim_keeps_the_reference_surface():
+    """every public/protected member function of the reference class is declared by the shim"""
+    text = open(os.path.join(REPO, "go-rio_b200", "include", "fast_gicp", "gicp", "fast_apdgicp.hpp")).read()
+    text += open(os.path.join(REPO, "go-rio_b200", "include", "fast_gicp", "gicp", "lsq_registration.hpp")).read()
+    for name in ["setNumThreads", "setCorrespondenceRandomness", "setRegularizationMethod", "setAzimuthVar", "setElevationVar",
+                 "setDistVar", "swapSourceAndTarget", "clearSource", "clearTarget", "setInputSource", "setSourceCovariances",
+                 "setInputTarget", "setTargetCovariances", "getSourceCovariances", "getTargetCovariances", "computeTransformation",
+                 "update_correspondences", "linearize", "compute_error", "setRotationEpsilon", "setInitialLambdaFactor",
+                 "setDebugPrint", "getFinalHessian", "evaluateCost"]:
+        assert name in text, name
+
+
+@pytest.mark.gpu
+def test_shim_matches_the_c_abi(gorio, synth, tmp_path):
+    exe = os.path.join(SHIM_DIR, "test_shim")
+    if not os.path.exists(exe):
+        subprocess.check_call(["bash", os.path.join(SHIM_DIR, "build.sh")])
+    src, tgt, _ = synth.submap_pair(2002, n_source=1000, n_frames=5, n_per_frame=1500)
+    fs, ft = str(tmp_path / "s.f32"), str(tmp_path / "t.f32")
+    src.tofile(fs); tgt.tofile(ft)
+    out = subprocess.run([exe, fs, str(src.shape[0]), ft, str(tgt.shape[0])], capture_output=True, text=True, check=True)
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    g = gorio.FastAPDGICP(0)
+    g.set_params(max_correspondence_distance=2.0, transformation_epsilon=0.1)
+    g.set_input_target(synth.to_pcl_xyzinormal(tgt)); g.set_input_source(synth.to_pcl_xyzinormal(src))
+    ra = g.align(want_aligned=True)
+    assert bool(r["converged"]) == ra["converged"]
+    assert np.array_equal(np.array(r["T"], dtype=np.float32).reshape(4, 4), ra["T"])
+    assert abs(r["fitness_gpu"] - g.fitness()[0]) < 1e-12
+    assert np.allclose(r["aligned0"], ra["aligned"][0], atol=0)
+    assert r["n_aligned"] == src.shape[0] and r["n_cov"] == tgt.shape[0]
+    assert abs(r["cost"] - g.linearize(ra["T"].astype(np.float64), want_hb=False)) / r["cost"] < 1e-12
+    assert "swapped: converged=" in out.stderr
