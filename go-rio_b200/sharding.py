@@ -1,0 +1,42 @@
+"""Host-side helpers of the two ways the registration path shards across GPUs
+(SURVEY.md §8e). One process per GPU; torch.distributed is only the plumbing.
+
+1. batches of independent scan/submap pairs -> `shard_pairs` (no collective);
+2. one very large cloud split by source points -> `shard_range` + `init_comm`:
+   every rank holds the full target and source points [begin, end); linearize /
+   compute_error all-reduce their 28 / 1 doubles over NCCL inside the library
+   (apd_comm_init), and cl_weight uses the total source count.
+"""
+import ctypes
+
+
+def shard_range(n, rank, world):
+    """contiguous split of n items: ranks [0, n % world) get one extra"""
+    base, extra = divmod(n, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_pairs(n_pairs, rank, world):
+    """pair i -> rank i % world (round-robin keeps per-rank work even when pair sizes vary)"""
+    return list(range(rank, n_pairs, world))
+
+
+def broadcast_unique_id(lib, rank, dist, device=None):
+    """rank 0 creates an ncclUniqueId through the library, everybody receives it"""
+    import torch
+
+    buf = (ctypes.c_char * 128)()
+    if rank == 0:
+        rc = lib.apd_comm_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"apd_comm_unique_id failed ({rc})")
+    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=device)
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().tolist())
+
+
+def init_comm(reg, lib, rank, world, n_source_total, dist, device=None):
+    """attach an NCCL communicator to the registration handle `reg`"""
+    uid = broadcast_unique_id(lib, rank, dist, device)
+    reg.comm_init(uid, rank, world, n_source_total)
