@@ -446,9 +446,18 @@ def main():
         corr_ms = k["corr"][0] / reps
         achieved = BYTES_PER_POINT_LINEARIZE * n / 1e9 / (lin_ms / 1e3)
         n_valid = int((g.get_correspondences()[0] >= 0).sum())
+        traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of the same kernel at the same size
+        try:
+            cap = json.load(open(os.path.join(REPO, "profiles", "r01_ncu_linearize.json")))
+            if cap.get("points") == n:
+                kk = cap["linearize_kernel<fp32 maha, H+b+err>"]
+                traffic = kk["dram_bytes_read"] + kk["dram_bytes_write"]
+        except Exception:
+            pass
         line["roofline"] = {
             "bound": "hbm", "kernel": "linearize_kernel<fp32 maha, H+b+err>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "points": n, "matched_points": n_valid,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_ncu_linearize.json (ncu capture, bytes per launch)" if traffic else None,
+            "algorithmic_bytes": BYTES_PER_POINT_LINEARIZE * n, "peak_source": peak_src, "points": n, "matched_points": n_valid,
             "bytes_per_point": BYTES_PER_POINT_LINEARIZE, "ms_per_launch": lin_ms,
             "compute_error": {"ms_per_launch": err_ms, "achieved": BYTES_PER_POINT_LINEARIZE * n / 1e9 / (err_ms / 1e3)},
             "update_correspondences": {"ms_per_launch": corr_ms, "achieved": 148 * n / 1e9 / (corr_ms / 1e3), "bytes_per_point": 148},
