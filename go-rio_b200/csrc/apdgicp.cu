@@ -187,7 +187,7 @@ struct apd_handle {
   double k_ms[APD_K_COUNT] = {0};
   int64_t k_launches[APD_K_COUNT] = {0};
   int max_reduce_blocks = 148 * 4;
-  double cells_per_point = 8.0;
+  double cells_per_point = 0.0;  // 0: by size (4 below 500 k points: fewer kNN shells; 8 above: cheaper 1-NN per LM iteration)
   // kNN kernel choice: 0 auto (warp-per-point below knn_thread_min_n points and k <= 32, thread-per-point
   // above: the warp kernel has the shorter critical path, the thread kernel the higher throughput),
   // 1 warp, 2 thread. Override with APD_KNN_MODE=warp|thread.
@@ -308,7 +308,7 @@ void stage_cloud(const void* pts, int n, int stride, int xyz_off, int label_off,
   }
 }
 
-// Grid sizing: cell edge so that the bounding box holds ~cells_per_point * n
+// Grid sizing: cell edge so that the bounding box holds ~cells_per_point (4) * n
 // cells (radar clouds live on surfaces, so occupied cells hold several points),
 // at most 2048 cells per axis (bounds the fp32 cell-coordinate error the search
 // margin covers) and 2^28 cells in total.
@@ -356,7 +356,7 @@ int ensure_small(apd_handle* h);
 int ensure_grid(apd_handle* h, Cloud& c) {
   if (c.grid_valid) return APD_OK;
   if (!c.present || c.n <= 0) return fail(h, APD_ERR_INVALID, "cloud not set");
-  size_grid(c.bbox, c.n, h->cells_per_point, c.g, c.ncells);
+  size_grid(c.bbox, c.n, h->cells_per_point > 0.0 ? h->cells_per_point : (c.n < 500000 ? 4.0 : 8.0), c.g, c.ncells);
   const size_t n = (size_t)c.n;
   APD_CUDA(h, c.spts.ensure(n * sizeof(float4)));
   APD_CUDA(h, c.label.ensure(n * sizeof(float)));

@@ -70,16 +70,16 @@ __device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const
     group_min();
   }
   const float mg = 0.002f * g.cell;
-  for (int r = 1;; r++) {
+  // thick shells (r, rr]: one cell at a time near the query, then growing ~1.5x (see knn_cov.cu)
+  for (int r = 1;;) {
     const float lb = ((float)r - 0.002f) * g.cell;
     const float lb2 = lb * lb;
     if (best != kInfKey && __uint_as_float((unsigned)(best >> 32)) < lb2) break;
     if ((double)lb2 >= limit_sq) break;
     if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
-    const int rr = r + 1;
+    const int rr = r < 3 ? r + 1 : r + (r >> 1) + 1;
     const int side = 2 * rr + 1;
-    const int xa = cx - rr, xb = cx + rr;
-    const int x0 = max(xa, 0), x1 = min(xb, g.nx - 1);
+    const int x0 = max(cx - rr, 0), x1 = min(cx + rr, g.nx - 1);
     for (int ri = sub; ri < side * side; ri += G) {
       const int dy = ri % side - rr, dz = ri / side - rr;
       const int y = cy + dy, z = cz + dz;
@@ -92,14 +92,16 @@ __device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const
       if ((double)dyz2 >= limit_sq) continue;
       if (best != kInfKey && dyz2 > __uint_as_float((unsigned)(best >> 32))) continue;
       const int row = (z * g.ny + y) * g.nx;
-      if (dy == rr || dy == -rr || dz == rr || dz == -rr) {
+      if (dy > r || dy < -r || dz > r || dz < -r) {  // row outside the scanned cube: its whole x-range
         scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
-      } else {
-        if (xa >= 0) scan_range(spts, (int)__ldg(&cell_start[row + xa]), (int)__ldg(&cell_start[row + xa + 1]), qx, qy, qz, best, best_pos);
-        if (xb < g.nx) scan_range(spts, (int)__ldg(&cell_start[row + xb]), (int)__ldg(&cell_start[row + xb + 1]), qx, qy, qz, best, best_pos);
+      } else {  // row crosses the scanned cube: the two end pieces
+        const int xl = min(cx - r - 1, g.nx - 1), xr = max(cx + r + 1, 0);
+        if (x0 <= xl) scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + xl + 1]), qx, qy, qz, best, best_pos);
+        if (xr <= x1) scan_range(spts, (int)__ldg(&cell_start[row + xr]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
       }
     }
     group_min();
+    r = rr;
   }
 }
 

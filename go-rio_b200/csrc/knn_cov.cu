@@ -12,6 +12,7 @@ namespace apd {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kWarpKnnThreads = 64;  // warp-per-point kernel: small CTAs, so a long search never holds back seven finished warps
 constexpr unsigned kFull = 0xffffffffu;
 constexpr unsigned long long kInfKey = 0xffffffffffffffffull;
 
@@ -60,6 +61,7 @@ struct KBest {
   unsigned long long list, kth;
   unsigned long long* buf;
   int buf_n;
+  bool empty;  // list holds no key yet
 };
 __device__ __forceinline__ void kbest_flush(KBest& s, int lane, int k) {
   if (s.buf_n == 0) return;  // warp-uniform
@@ -67,7 +69,8 @@ __device__ __forceinline__ void kbest_flush(KBest& s, int lane, int k) {
   unsigned long long b = lane < s.buf_n ? s.buf[lane] : kInfKey;
   __syncwarp();
   b = bitonic_sort32(b, lane);
-  s.list = merge_keep32(s.list, b, lane);
+  s.list = s.empty ? b : merge_keep32(s.list, b, lane);  // nothing to merge with on the first flush
+  s.empty = false;
   s.kth = shfl64(s.list, k - 1);
   s.buf_n = 0;
 }
@@ -117,10 +120,10 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ spts, f
   }
 }
 
-__global__ void __launch_bounds__(kThreads) knn_cov_kernel(const float4* __restrict__ spts, const float4* __restrict__ pts,
+__global__ void __launch_bounds__(kWarpKnnThreads) knn_cov_kernel(const float4* __restrict__ spts, const float4* __restrict__ pts,
                                                            const uint32_t* __restrict__ cell_start, GridDesc g, int n, int k,
                                                            double* __restrict__ cov, int32_t* __restrict__ neighbors) {
-  const int w = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const int w = (blockIdx.x * kWarpKnnThreads + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n) return;
   const float4 q = spts[w];
@@ -129,18 +132,22 @@ __global__ void __launch_bounds__(kThreads) knn_cov_kernel(const float4* __restr
   const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
   const int cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz);
 
-  __shared__ unsigned long long kbuf[kThreads / 32][32];
+  __shared__ unsigned long long kbuf[kWarpKnnThreads / 32][32];
   KBest st;
   st.list = kInfKey;
   st.kth = kInfKey;
   st.buf = kbuf[threadIdx.x >> 5];
   st.buf_n = 0;
+  st.empty = true;
 
   // ring 0+1: the 3x3x3 cube as 9 x-rows
   {
     int b = 0, cnt = 0;
     if (lane < 9) {
-      const int y = cy + (lane % 3) - 1, z = cz + (lane / 3) - 1;
+      // rows nearest first (centre, the 4 face rows, the 4 corner rows) so that the first
+      // 32 candidates already give a tight k-th distance: packed 2-bit (dy+1, dz+1) codes
+      // dy = {0,-1,1,0,0,-1,1,-1,1}[lane], dz = {0,0,0,-1,1,-1,-1,1,1}[lane]
+      const int y = cy + (int)((0x22161u >> (2 * lane)) & 3u) - 1, z = cz + (int)((0x28215u >> (2 * lane)) & 3u) - 1;
       if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
         const int row = (z * g.ny + y) * g.nx;
@@ -153,31 +160,37 @@ __global__ void __launch_bounds__(kThreads) knn_cov_kernel(const float4* __restr
   }
   // shells r = 2, 3, ... until the k-th distance is provably final:
   // every unscanned point is at least (r - 0.002) cells away.
-  for (int r = 1;; r++) {
+  // Thick shells: after the cube of radius r has been scanned, the next step scans radius (r, rr]. One cell at a
+  // time near the query (where most searches end), then growing by ~1.5x: an x-row segment costs the same however
+  // many cells it spans, so a search that must reach R cells costs O(R^2) segments instead of O(R^3).
+  for (int r = 1;;) {
     const float lb = ((float)r - 0.002f) * g.cell;
     const float kd2 = __uint_as_float((unsigned)(st.kth >> 32));
     if (st.kth != kInfKey && kd2 < lb * lb) break;
     if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
-    const int rr = r + 1;  // shell to scan now
+    const int rr = r < 3 ? r + 1 : r + (r >> 1) + 1;  // outer radius of the shell to scan now
     const int side = 2 * rr + 1;
     const int nslots = 2 * side * side;
+    const float inv_side = 1.0f / (float)side;
     for (int sbase = 0; sbase < nslots; sbase += 32) {
       const int slot = sbase + lane;
       const float kd2cur = __uint_as_float((unsigned)(st.kth >> 32));  // shrinks as the shell is scanned
       int b = 0, cnt = 0;
       if (slot < nslots) {
         const int rowid = slot >> 1, which = slot & 1;
-        const int dy = rowid % side - rr, dz = rowid / side - rr;
+        const int qz = __float2int_rd(((float)rowid + 0.5f) * inv_side);  // rowid / side (exact for these small integers)
+        const int dy = rowid - qz * side - rr, dz = qz - rr;
         const int y = cy + dy, z = cz + dz;
         if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
-          const bool border = (dy == rr) || (dy == -rr) || (dz == rr) || (dz == -rr);
+          const bool outer = (dy > r) || (dy < -r) || (dz > r) || (dz < -r);  // row lies outside the scanned cube
           const int row = (z * g.ny + y) * g.nx;
           int x0 = 1, x1 = 0;
-          if (border) {
+          if (outer) {
             if (which == 0) { x0 = max(cx - rr, 0); x1 = min(cx + rr, g.nx - 1); }
+          } else if (which == 0) {
+            x0 = max(cx - rr, 0); x1 = min(cx - r - 1, g.nx - 1);
           } else {
-            const int x = which == 0 ? cx - rr : cx + rr;
-            if (x >= 0 && x < g.nx) { x0 = x; x1 = x; }
+            x0 = max(cx + r + 1, 0); x1 = min(cx + rr, g.nx - 1);
           }
           if (x0 <= x1) {
             // prune the segment if its (slightly grown) box is farther than the current k-th distance
@@ -199,32 +212,39 @@ __global__ void __launch_bounds__(kThreads) knn_cov_kernel(const float4* __restr
       if (__ballot_sync(kFull, cnt > 0)) scan_segments(spts, q.x, q.y, q.z, lane, k, b, cnt, st);
     }
     kbest_flush(st, lane, k);
+    r = rr;
   }
   const unsigned long long mykey = st.list;
 
   // covariance of the k neighbours (reference :366-372): fp64, centred, / k
   const int nidx = (lane < k) ? (int)(unsigned)(mykey & 0xffffffffull) : 0;
   if (neighbors && lane < k) neighbors[(size_t)qi * k + lane] = nidx;
-  double x = 0.0, y = 0.0, z = 0.0;
+  // The k neighbour coordinates go through shared memory; lanes 0-2 sum the means and lanes 0-5 the six
+  // centred products serially in neighbour order with one rounding per operation — the CPU path's order, so
+  // the raw covariance is bit-identical to the oracle's (and ~2x cheaper than nine butterfly reductions).
+  __shared__ double kcoord[kWarpKnnThreads / 32][3][32];
+  double (*kc)[32] = kcoord[threadIdx.x >> 5];
   if (lane < k) {
     const float4 p = pts[nidx];
-    x = (double)p.x; y = (double)p.y; z = (double)p.z;
+    kc[0][lane] = (double)p.x;
+    kc[1][lane] = (double)p.y;
+    kc[2][lane] = (double)p.z;
   }
-  const double inv_k = 1.0 / (double)k;
-  const double mx = warp_sum(x) / (double)k, my = warp_sum(y) / (double)k, mz = warp_sum(z) / (double)k;
-  (void)inv_k;
-  double dx = 0.0, dy = 0.0, dz = 0.0;
-  if (lane < k) { dx = x - mx; dy = y - my; dz = z - mz; }
-  const double cxx = warp_sum(dx * dx) / (double)k;
-  const double cxy = warp_sum(dx * dy) / (double)k;
-  const double cxz = warp_sum(dx * dz) / (double)k;
-  const double cyy = warp_sum(dy * dy) / (double)k;
-  const double cyz = warp_sum(dy * dz) / (double)k;
-  const double czz = warp_sum(dz * dz) / (double)k;
-  if (lane < 6) {
-    const double v = lane == 0 ? cxx : lane == 1 ? cxy : lane == 2 ? cxz : lane == 3 ? cyy : lane == 4 ? cyz : czz;
-    cov[(size_t)w * 6 + lane] = v;
+  __syncwarp();
+  double mean = 0.0;
+  if (lane < 3) {
+    for (int j = 0; j < k; j++) mean = __dadd_rn(mean, kc[lane][j]);
+    mean /= (double)k;
   }
+  const double mx = __shfl_sync(kFull, mean, 0), my = __shfl_sync(kFull, mean, 1), mz = __shfl_sync(kFull, mean, 2);
+  if (cov && lane < 6) {
+    const int a = lane < 3 ? 0 : (lane < 5 ? 1 : 2), bq = lane < 3 ? lane : (lane < 5 ? lane - 2 : 2);  // xx xy xz yy yz zz
+    const double ma = a == 0 ? mx : (a == 1 ? my : mz), mb = bq == 0 ? mx : (bq == 1 ? my : mz);
+    double acc = 0.0;
+    for (int j = 0; j < k; j++) acc = __dadd_rn(acc, __dmul_rn(__dsub_rn(kc[a][j], ma), __dsub_rn(kc[bq][j], mb)));
+    cov[(size_t)w * 6 + lane] = acc / (double)k;
+  }
+  __syncwarp();
 }
 
 __device__ __forceinline__ double geo_weight_of(const Sym3& C) {
@@ -359,43 +379,43 @@ __global__ void __launch_bounds__(kKnnT) knn_cov_thread_kernel(const float4* __r
   }
   // shells r = 2, 3, ...: every unscanned point is at least (r - 0.002) cells away
   const float mg = 0.002f * g.cell;
-  for (int r = 1;; r++) {
+  for (int r = 1;;) {  // thick shells (r, rr], as in the warp kernel
     const float lb = ((float)r - 0.002f) * g.cell;
     if (top != kInfKey && __uint_as_float((unsigned)(top >> 32)) < lb * lb) break;
     if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
-    const int rr = r + 1;
-    const int xa = cx - rr, xb = cx + rr;
-    const int x0 = max(xa, 0), x1 = min(xb, g.nx - 1);
+    const int rr = r < 3 ? r + 1 : r + (r >> 1) + 1;
+    const int x0 = max(cx - rr, 0), x1 = min(cx + rr, g.nx - 1);
     for (int z = max(cz - rr, 0); z <= min(cz + rr, g.nz - 1); z++) {
-      const bool zb = (z == cz - rr) || (z == cz + rr);
+      const bool zo = (z < cz - r) || (z > cz + r);
       const float loz = g.oz + (float)z * g.cell - mg, hiz = g.oz + (float)(z + 1) * g.cell + mg;
       const float ddz = fmaxf(0.f, fmaxf(loz - q.z, q.z - hiz));
       for (int y = max(cy - rr, 0); y <= min(cy + rr, g.ny - 1); y++) {
         const float loy = g.oy + (float)y * g.cell - mg, hiy = g.oy + (float)(y + 1) * g.cell + mg;
         const float ddy = fmaxf(0.f, fmaxf(loy - q.y, q.y - hiy));
         const float dyz2 = ddy * ddy + ddz * ddz;
-        const float kd2 = __uint_as_float((unsigned)(top >> 32));
         // prune the whole row if even its nearest point is farther than the current k-th distance
-        if (top != kInfKey && dyz2 * 0.9999f > kd2) continue;
+        if (top != kInfKey && dyz2 * 0.9999f > __uint_as_float((unsigned)(top >> 32))) continue;
         const int row = (z * g.ny + y) * g.nx;
-        if (zb || y == cy - rr || y == cy + rr) {
+        if (zo || y < cy - r || y > cy + r) {
           knn_scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), q.x, q.y, q.z, hd, hi, k, tid, top);
         } else {
-          if (xa >= 0) {
-            const float hix = g.ox + (float)(xa + 1) * g.cell + mg;
+          const int xl = min(cx - r - 1, g.nx - 1), xr = max(cx + r + 1, 0);
+          if (x0 <= xl) {
+            const float hix = g.ox + (float)(xl + 1) * g.cell + mg;
             const float ddx = fmaxf(0.f, q.x - hix);
             if (top == kInfKey || !((dyz2 + ddx * ddx) * 0.9999f > __uint_as_float((unsigned)(top >> 32))))
-              knn_scan_range(spts, (int)__ldg(&cell_start[row + xa]), (int)__ldg(&cell_start[row + xa + 1]), q.x, q.y, q.z, hd, hi, k, tid, top);
+              knn_scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + xl + 1]), q.x, q.y, q.z, hd, hi, k, tid, top);
           }
-          if (xb < g.nx) {
-            const float lox = g.ox + (float)xb * g.cell - mg;
+          if (xr <= x1) {
+            const float lox = g.ox + (float)xr * g.cell - mg;
             const float ddx = fmaxf(0.f, lox - q.x);
             if (top == kInfKey || !((dyz2 + ddx * ddx) * 0.9999f > __uint_as_float((unsigned)(top >> 32))))
-              knn_scan_range(spts, (int)__ldg(&cell_start[row + xb]), (int)__ldg(&cell_start[row + xb + 1]), q.x, q.y, q.z, hd, hi, k, tid, top);
+              knn_scan_range(spts, (int)__ldg(&cell_start[row + xr]), (int)__ldg(&cell_start[row + x1 + 1]), q.x, q.y, q.z, hd, hi, k, tid, top);
           }
         }
       }
     }
+    r = rr;
   }
 
   // heap-sort in place -> ascending (d2, idx)
@@ -495,8 +515,8 @@ void launch_knn_cov_fused(const CloudDev& c, int k, int regularization, int32_t*
 void launch_knn_cov(const CloudDev& c, int k, int32_t* neighbors, cudaStream_t s, int64_t* launches) {
   if (c.n <= 0) return;
   const long long threads = (long long)c.n * 32;
-  const int blocks = (int)((threads + kThreads - 1) / kThreads);
-  knn_cov_kernel<<<blocks, kThreads, 0, s>>>(c.spts, c.pts, c.cell_start, c.g, c.n, k, c.cov, neighbors);
+  const int blocks = (int)((threads + kWarpKnnThreads - 1) / kWarpKnnThreads);
+  knn_cov_kernel<<<blocks, kWarpKnnThreads, 0, s>>>(c.spts, c.pts, c.cell_start, c.g, c.n, k, c.cov, neighbors);
   (*launches)++;
 }
 void launch_regularize(const CloudDev& c, int regularization, cudaStream_t s, int64_t* launches) {

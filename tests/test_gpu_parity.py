@@ -75,12 +75,14 @@ def test_knn_warp_and_thread_kernels_match(gorio, c2_small, monkeypatch):
     assert np.abs(g.get_target_covariances() - gw.get_target_covariances()).max() < 1e-12
 
 
-def test_raw_covariance_bit_exact(gorio, c2_small, monkeypatch):
-    """NONE regularisation: the thread-per-point kernel sums in the oracle's order with one rounding per operation"""
+@pytest.mark.parametrize("mode", ["thread", "warp"])
+def test_raw_covariance_bit_exact(gorio, c2_small, monkeypatch, mode):
+    """NONE regularisation: both kNN kernels sum in the oracle's order with one rounding per operation"""
     src, tgt, _ = c2_small
-    monkeypatch.setenv("APD_KNN_MODE", "thread")
+    monkeypatch.setenv("APD_KNN_MODE", mode)
     g, o = make(gorio, src, tgt, regularization=0)
     assert np.array_equal(g.get_target_covariances(), o.get_target_covariances())
+    assert np.array_equal(g.get_source_covariances(), o.get_source_covariances())
 
 
 def test_knn_clustered_and_degenerate_geometry(gorio):
