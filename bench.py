@@ -185,38 +185,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ our arm ----
-def run_step(handles, pairs, mode, results):
-    """Registers every pair once, sharing the work over len(handles) threads (one
-    CUDA stream each; ctypes releases the GIL inside the C-ABI calls).
-    mode 'device': pairs = [(d_src_ptr, n_src, d_tgt_ptr, n_tgt)];
-    mode 'host':   pairs = [(src ndarray, tgt ndarray)]."""
-    nxt = [0]
-    lock = threading.Lock()
-
-    def work(g):
-        while True:
-            with lock:
-                i = nxt[0]
-                nxt[0] += 1
-            if i >= len(pairs):
-                return
-            g.clear_target()
-            g.clear_source()
-            if mode == "device":
-                ds, ns, dt, nt = pairs[i]
-                g.set_input_target_device(dt, nt)
-                g.set_input_source_device(ds, ns)
-            else:
-                s, t = pairs[i]
-                g.set_input_target(t)
-                g.set_input_source(s)
-            results[i] = g.align()
-
-    ths = [threading.Thread(target=work, args=(g,)) for g in handles]
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
+LM_RESULT_HEAD_BYTES = 1976  # apdgicp.cu kLmHeadBytes: pose, final hessian, flags and the first LM trace rows, per registration
 
 
 def run_c4(args):
@@ -308,7 +277,6 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     line = None
-    handles = []
     host_pairs = []
     peaks = {}
     try:
@@ -331,13 +299,10 @@ def main():
                 dev_tensors += [ds, dt]
                 cache[key] = (ds.data_ptr(), s.shape[0], dt.data_ptr(), t.shape[0])
             dev_pairs.append(cache[key])
-        pinned_pairs = host_pairs  # the C-ABI stages host clouds through its own pinned buffers
-
-        handles = []
-        for _ in range(args.streams):
-            g = gorio.FastAPDGICP(local_rank)
-            g.set_params(**DEPLOYED)
-            handles.append(g)
+        # the batch context of the C-ABI (apd_batch_*): `--streams` workers, one handle / CUDA stream / host thread each
+        batch = gorio.Batch(local_rank, n_workers=args.streams, **DEPLOYED)
+        prep_dev = batch.prepare([((ds, ns), (dt, nt), None) for ds, ns, dt, nt in dev_pairs])
+        prep_host = batch.prepare([(s, t, None) for s, t in host_pairs])
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
         def barrier():
@@ -346,48 +311,42 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize()
 
-        def timed(mode, pairs, steps, warmup):
-            results = [None] * len(pairs)
+        def timed(prepared, steps, warmup):
             for _ in range(warmup):
-                run_step(handles, pairs, mode, results)
+                batch.align(prepared, with_fitness=False, parse=False)
             ms_total = 0.0
-            l0 = sum(g.launch_count() for g in handles)
+            l0 = batch.launch_count()
             for _ in range(steps):
                 flush.zero_()  # L2 flush between timed iterations (untimed)
                 barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                run_step(handles, pairs, mode, results)
+                batch.align(prepared, with_fitness=False, parse=False)  # returns when every pair's result is on the host
                 e1.record()
                 torch.cuda.synchronize()
                 ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
                 if world > 1:
                     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
                 ms_total += float(ms.item())
-            launches = sum(g.launch_count() for g in handles) - l0
-            return ms_total, launches, results
+            launches = batch.launch_count() - l0
+            return ms_total, launches, batch.align(prepared, with_fitness=False)
 
         with ClockSampler(local_rank) as clocks:
-            ms_dev, launches, results = timed("device", dev_pairs, args.steps, args.warmup)
-        ms_e2e, _, results_h = timed("host", pinned_pairs, args.steps, args.warmup)
+            ms_dev, launches, results = timed(prep_dev, args.steps, args.warmup)
+        ms_e2e, _, results_h = timed(prep_host, args.steps, args.warmup)
         total_pairs = args.pairs * world
         value = total_pairs * args.steps / (ms_dev / 1e3)
         e2e_value = total_pairs * args.steps / (ms_e2e / 1e3)
         same = all(np.array_equal(a["T"], b["T"]) for a, b in zip(results, results_h))
+        ok = all(r["status"] == 0 for r in results + results_h)
         h2d = sum(s.nbytes + t.nbytes for s, t in host_pairs)
-        d2h = args.pairs * (16 * 4 + 16 * 8 + 36 * 8 + 8)
+        d2h = args.pairs * LM_RESULT_HEAD_BYTES
 
-        # per-kernel-class device time of one step (profiling events on the handle streams; separate, untimed pass)
-        for g in handles:
-            g.set_profiling(True)
-        run_step(handles, dev_pairs, "device", [None] * len(dev_pairs))
-        kms = {}
-        for g in handles:
-            for k, (ms, cnt) in g.kernel_ms().items():
-                a = kms.setdefault(k, [0.0, 0])
-                a[0] += ms
-                a[1] += cnt
-            g.set_profiling(False)
+        # per-kernel-class device time of one step (profiling events on the worker streams; separate, untimed pass)
+        batch.set_profiling(True)
+        batch.align(prep_dev, with_fitness=False, parse=False)
+        kms = {k: [ms, cnt] for k, (ms, cnt) in batch.kernel_ms().items()}
+        batch.set_profiling(False)
         tot = sum(v[0] for v in kms.values()) or 1.0
         kernels = {k: {"ms_per_step": round(v[0], 4), "launches_per_step": v[1], "share": round(v[0] / tot, 4)} for k, v in kms.items()}
 
@@ -402,11 +361,13 @@ def main():
                 "config": {"workload": "C2 scan-to-submap: 2000-pt radar scan vs 60000-pt keyframe submap, k=20, deployed params "
                                        "(max_corr_dist 2.0, trans_eps 0.1, LM, PLANE)",
                            "pairs_per_step_per_gpu": args.pairs, "streams_per_gpu": args.streams,
+                           "api": "apd_batch_align_device (value) / apd_batch_align (e2e)", "optimizer_loop": "device-resident (lm.cu), one launch per registration",
                            "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align",
                            "l2": "flushed (256 MiB write) between timed steps", "sharding": "pairs across ranks, no collective",
                            "target_points": n_tgt_pts},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "same_result_as_device_resident": bool(same)},
+                        "same_result_as_device_resident": bool(same), "all_pairs_ok": bool(ok),
+                        "api": "apd_batch_align (host AoS clouds in, poses out)"},
                 "gpu_launches": int(launches),
                 "kernels": kernels,
                 "knn_cov_roofline": {"bound": "hbm", "achieved": (BYTES_PER_POINT_KNNCOV * knn_pts / 1e9) / (knn_ms / 1e3) if knn_ms > 0 else None,
@@ -416,8 +377,8 @@ def main():
 
     # ---- roofline of the linearize kernel on a cloud larger than L2 (rank 0, N = 1 only) ----
     if rank == 0 and world == 1 and not args.no_roofline:
-        for g in handles:
-            g.close()
+        if not args.roofline_only:
+            batch.close()
         dev_tensors = None
         torch.cuda.empty_cache()
         n = args.roofline_points

@@ -43,31 +43,114 @@ def FastAPDGICP(device=0):
     return Registration(load(), "apd_", device)
 
 
-def align_batch(pairs, params=None, device=0, n_streams=4, with_fitness=True):
-    """apd_align_batch over a list of (source[n,4] f32, target[m,4] f32, guess 4x4 or None)."""
+def _pair_array(pairs, keep):
     import numpy as np
 
-    lib = load()
-    if params is None:
-        params = ApdParams()
-        lib.apd_default_params(ctypes.byref(params))
     n = len(pairs)
     arr = (ApdPair * n)()
-    keep = []
     for i, (s, t, g) in enumerate(pairs):
-        s = np.ascontiguousarray(s, dtype=np.float32)
-        t = np.ascontiguousarray(t, dtype=np.float32)
-        keep += [s, t]
-        arr[i].source = s.ctypes.data
-        arr[i].n_source = s.shape[0]
-        arr[i].target = t.ctypes.data
-        arr[i].n_target = t.shape[0]
+        if isinstance(s, tuple):  # (device pointer, count): cloud already on the GPU as float4 {x,y,z,label}
+            arr[i].source, arr[i].n_source = s
+            arr[i].target, arr[i].n_target = t
+        else:
+            s = np.ascontiguousarray(s, dtype=np.float32)
+            t = np.ascontiguousarray(t, dtype=np.float32)
+            keep += [s, t]
+            arr[i].source = s.ctypes.data
+            arr[i].n_source = s.shape[0]
+            arr[i].target = t.ctypes.data
+            arr[i].n_target = t.shape[0]
         if g is not None:
             gg = np.ascontiguousarray(np.asarray(g, dtype=np.float32).T).reshape(-1)
             keep.append(gg)
             arr[i].guess = gg.ctypes.data
         else:
             arr[i].guess = None
+    return arr
+
+
+def _results(res):
+    import numpy as np
+
+    return [dict(T=np.array(r.T, dtype=np.float32).reshape(4, 4).T.copy(), fitness=r.fitness, converged=bool(r.converged),
+                 iterations=r.iterations, status=r.status, n_inliers=r.n_inliers) for r in res]
+
+
+class Batch:
+    """apd_batch_*: a persistent pool of `n_workers` handles / streams / host threads for independent pairs."""
+
+    def __init__(self, device=0, n_workers=8, params=None, **kw):
+        self._lib = load()
+        self._b = ctypes.c_void_p()
+        self._lib.apd_batch_create.restype = ctypes.c_int
+        rc = self._lib.apd_batch_create(ctypes.c_int(device), ctypes.c_int32(n_workers), ctypes.byref(self._b))
+        if rc != 0:
+            raise ApdError(rc, "apd_batch_create")
+        if params is None:
+            params = ApdParams()
+            self._lib.apd_default_params(ctypes.byref(params))
+        for k, v in kw.items():
+            setattr(params, k, v)
+        rc = self._lib.apd_batch_set_params(self._b, ctypes.byref(params))
+        if rc != 0:
+            raise ApdError(rc, "apd_batch_set_params")
+
+    def prepare(self, pairs):
+        """list of (source, target, guess) -> a reusable C array; source/target are [n,4] f32 arrays
+        (host clouds) or (device_ptr, n) tuples (clouds resident in HBM)."""
+        keep = []
+        arr = _pair_array(pairs, keep)
+        device = len(pairs) > 0 and isinstance(pairs[0][0], tuple)
+        return dict(arr=arr, keep=keep, n=len(pairs), device=device, res=(ApdResult * len(pairs))())
+
+    def align(self, prepared, with_fitness=True, parse=True):
+        if not isinstance(prepared, dict):
+            prepared = self.prepare(prepared)
+        n, arr, res = prepared["n"], prepared["arr"], prepared["res"]
+        wf = ctypes.c_int32(1 if with_fitness else 0)
+        if prepared["device"]:
+            rc = self._lib.apd_batch_align_device(self._b, arr, ctypes.c_int32(n), wf, res)
+        else:
+            rc = self._lib.apd_batch_align(self._b, arr, ctypes.c_int32(n), ctypes.c_int32(16), ctypes.c_int32(0), ctypes.c_int32(12), wf, res)
+        if rc != 0:
+            raise ApdError(rc, "apd_batch_align")
+        return _results(res) if parse else res
+
+    def launch_count(self):
+        self._lib.apd_batch_launch_count.restype = ctypes.c_int64
+        return self._lib.apd_batch_launch_count(self._b)
+
+    def set_profiling(self, on):
+        self._lib.apd_batch_set_profiling(self._b, ctypes.c_int32(1 if on else 0))
+
+    def kernel_ms(self):
+        n = len(_binding.KERNEL_CLASSES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        self._lib.apd_batch_get_kernel_ms(self._b, ms, cnt)
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(_binding.KERNEL_CLASSES)}
+
+    def close(self):
+        if self._b:
+            self._lib.apd_batch_destroy(self._b)
+            self._b = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def align_batch(pairs, params=None, device=0, n_streams=4, with_fitness=True):
+    """apd_align_batch over a list of (source[n,4] f32, target[m,4] f32, guess 4x4 or None)."""
+    lib = load()
+    if params is None:
+        params = ApdParams()
+        lib.apd_default_params(ctypes.byref(params))
+    n = len(pairs)
+    keep = []
+    arr = _pair_array(pairs, keep)
     res = (ApdResult * n)()
     lib.apd_align_batch.restype = ctypes.c_int
     rc = lib.apd_align_batch(ctypes.c_int(device), ctypes.byref(params), arr, ctypes.c_int32(n), ctypes.c_int32(16),
@@ -75,8 +158,4 @@ def align_batch(pairs, params=None, device=0, n_streams=4, with_fitness=True):
                              ctypes.c_int32(1 if with_fitness else 0), res)
     if rc != 0:
         raise ApdError(rc, "apd_align_batch")
-    out = []
-    for r in res:
-        out.append(dict(T=np.array(r.T, dtype=np.float32).reshape(4, 4).T.copy(), fitness=r.fitness,
-                        converged=bool(r.converged), iterations=r.iterations, status=r.status, n_inliers=r.n_inliers))
-    return out
+    return _results(res)

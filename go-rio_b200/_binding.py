@@ -14,7 +14,7 @@ import numpy as np
 APD_OK, APD_ERR_INVALID, APD_ERR_CUDA, APD_ERR_TOO_FEW, APD_ERR_UNSUPPORTED, APD_ERR_COMM = range(6)
 REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = range(5)
 OPT_GN, OPT_LM = 0, 1
-KERNEL_CLASSES = ["grid", "knn_cov", "corr", "linearize", "error", "fitness"]
+KERNEL_CLASSES = ["grid", "knn_cov", "corr", "linearize", "error", "fitness", "lm"]
 
 
 class ApdParams(C.Structure):
@@ -33,7 +33,7 @@ class ApdParams(C.Structure):
         ("lm_debug_print", C.c_int32),
         ("lm_init_lambda_factor", C.c_double),
         ("maha_fp64", C.c_int32),
-        ("reserved", C.c_int32),
+        ("host_loop", C.c_int32),
     ]
 
 
@@ -74,7 +74,9 @@ CORE_SYMBOLS = [
 ]
 # symbols only the CUDA library exports
 PRODUCT_SYMBOLS = CORE_SYMBOLS + [
-    "abi_version", "set_source_device", "set_target_device", "align_batch", "comm_unique_id",
+    "abi_version", "set_source_device", "set_target_device", "align_batch", "batch_create", "batch_destroy",
+    "batch_set_params", "batch_align", "batch_align_device", "batch_launch_count", "batch_set_profiling",
+    "batch_get_kernel_ms", "comm_unique_id",
     "comm_init", "comm_destroy", "stream", "launch_count", "set_profiling", "get_kernel_ms",
 ]
 

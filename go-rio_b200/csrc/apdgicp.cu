@@ -6,10 +6,13 @@
 #include <dlfcn.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -167,6 +170,15 @@ struct apd_handle {
   // scratch
   DevBuf work, scratch, partials, small;  // small: out28 + ticket + fitness
   PinnedBuf h_small;
+  DevBuf lm_result;   // LmResult of the device-resident optimizer loop
+  PinnedBuf h_lm;     // its header + first trace rows on the host
+  int lm_cluster = 4; // CTAs per registration in the device loop (APD_LM_CLUSTER=1|2|4|8)
+  bool lm_failed = false;
+  // batch workers ask the device loop to append the getFitnessScore pass (saves a launch and a round trip per pair)
+  bool fuse_fitness = false;
+  double fuse_inlier_sq_thr = 0.25;
+  bool fit_valid = false;  // fit[] describes the last align's final pose
+  double fit[3] = {0, 0, 0};
   // results of the last align
   hm::Pose final_pose = hm::Pose::identity();
   float final_T[16];        // column-major
@@ -352,6 +364,8 @@ void size_grid(const float bbox[6], int n, double cells_per_point, GridDesc& g, 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int ensure_small(apd_handle* h);
+NoiseParams noise_params(const apd_params& p);
+int ensure_corr_buffers(apd_handle* h);
 
 int ensure_grid(apd_handle* h, Cloud& c) {
   if (c.grid_valid) return APD_OK;
@@ -452,20 +466,9 @@ CorrOut corr_view(apd_handle* h) {
 
 // FastAPDGICP::update_correspondences (:160-220)
 int do_update_correspondences(apd_handle* h, const hm::Pose& T) {
-  const size_t n = (size_t)h->src.n;
-  const int fp64 = h->params.maha_fp64 ? 1 : 0;
-  APD_CUDA(h, h->corr.ensure(n * sizeof(int)));
-  APD_CUDA(h, h->sqd.ensure(n * sizeof(float)));
-  APD_CUDA(h, h->mahaA.ensure(n * (fp64 ? sizeof(double2) : sizeof(float4))));
-  APD_CUDA(h, h->mahaB.ensure(n * (fp64 ? 2 * sizeof(double2) : sizeof(float2))));
-  h->corr_fp64 = fp64;
-  NoiseParams np;
-  np.dist_var = h->params.dist_var;
-  np.sin_az = std::sin(h->params.azimuth_var / 180 * M_PI);    // :196
-  np.sin_el = std::sin(h->params.elevation_var / 180 * M_PI);  // :197
-  const double thr = h->params.max_correspondence_distance;
-  np.thr_sq = thr * thr;  // :183 (double product)
-  np.search_limit = (float)thr;
+  int rc0 = ensure_corr_buffers(h);
+  if (rc0 != APD_OK) return rc0;
+  const NoiseParams np = noise_params(h->params);
   {
     ProfScope ps(h, APD_K_CORR);
     launch_update_correspondences(h->src.view(), h->tgt.view(), to_pose_d(T), np, corr_view(h), h->stream, &h->launches);
@@ -683,11 +686,136 @@ void default_params(apd_params* p) {
   p->lm_debug_print = 0;
   p->lm_init_lambda_factor = 1e-9;
   p->maha_fp64 = 0;
+  p->host_loop = 0;
+}
+
+NoiseParams noise_params(const apd_params& p) {
+  NoiseParams np;
+  np.dist_var = p.dist_var;
+  np.sin_az = std::sin(p.azimuth_var / 180 * M_PI);    // :196
+  np.sin_el = std::sin(p.elevation_var / 180 * M_PI);  // :197
+  const double thr = p.max_correspondence_distance;
+  np.thr_sq = thr * thr;  // :183 (double product)
+  np.search_limit = (float)thr;
+  return np;
+}
+
+int ensure_corr_buffers(apd_handle* h) {
+  const size_t n = (size_t)h->src.n;
+  const int fp64 = h->params.maha_fp64 ? 1 : 0;
+  APD_CUDA(h, h->corr.ensure(n * sizeof(int)));
+  APD_CUDA(h, h->sqd.ensure(n * sizeof(float)));
+  APD_CUDA(h, h->mahaA.ensure(n * (fp64 ? sizeof(double2) : sizeof(float4))));
+  APD_CUDA(h, h->mahaB.ensure(n * (fp64 ? 2 * sizeof(double2) : sizeof(float2))));
+  h->corr_fp64 = fp64;
+  return APD_OK;
+}
+
+LmConfig lm_config(const apd_params& p) {
+  LmConfig c{};
+  c.max_iterations = p.max_iterations;
+  c.optimizer = p.optimizer == APD_OPT_GAUSS_NEWTON ? 0 : 1;
+  c.lm_max_iterations = p.lm_max_iterations;
+  c.maha_fp64 = p.maha_fp64 ? 1 : 0;
+  c.want_fitness = 0;
+  c.rotation_epsilon = p.rotation_epsilon;
+  c.transformation_epsilon = p.transformation_epsilon;
+  c.lm_init_lambda_factor = p.lm_init_lambda_factor;
+  c.fitness_max_range = std::numeric_limits<double>::max();
+  c.inlier_sq_thr = 0.0;
+  c.np = noise_params(p);
+  return c;
+}
+
+bool use_device_loop(const apd_handle* h) {
+  return !h->params.host_loop && !h->comm && !h->params.lm_debug_print && h->src.n <= kLmMaxSource;
+}
+
+LmJob lm_job(apd_handle* h, const hm::Pose& x0) {
+  const CloudDev s = h->src.view(), t = h->tgt.view();
+  LmJob j{};
+  j.s_spts = s.spts; j.s_label = s.label; j.s_cov = s.cov; j.s_geo = s.geo; j.s_geo64 = s.geo64;
+  j.t_spts = t.spts; j.t_label = t.label; j.t_cov = t.cov; j.t_cell_start = t.cell_start;
+  j.tg = t.g;
+  j.n_src = s.n;
+  j.corr = h->corr.as<int>(); j.sqd = h->sqd.as<float>(); j.mahaA = h->mahaA.p; j.mahaB = h->mahaB.p;
+  j.cl_w = 1.0 / (double)s.n;  // 1.0 / correspondences_.size() (:273)
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) j.guess[r * 3 + c] = x0(r, c);
+    j.guess[9 + r] = x0(r, 3);
+  }
+  j.result = h->lm_result.as<LmResult>();
+  return j;
+}
+
+constexpr size_t kLmHeadBytes = offsetof(LmResult, trace) + (size_t)kLmTraceHead * 8 * sizeof(double);
+
+// unpack a finished LmResult header (host copy) into the handle
+int finish_device_align(apd_handle* h, const LmResult* r) {
+  hm::Pose x0 = hm::Pose::identity();
+  for (int a = 0; a < 3; a++) {
+    for (int c = 0; c < 3; c++) x0(a, c) = r->pose[a * 3 + c];
+    x0(a, 3) = r->pose[9 + a];
+  }
+  h->converged = r->converged != 0;
+  h->nr_iterations = r->nr_iterations;
+  h->lm_lambda = r->lm_lambda;
+  h->lm_failed = r->lm_failed != 0;
+  if (r->hessian_set) std::memcpy(h->final_H, r->H, sizeof(h->final_H));  // final_hessian_ changes only when a step was accepted
+  const int rows = std::min(r->n_trace, kLmTraceRows);
+  h->trace.resize((size_t)rows * 8);
+  const int head = std::min(rows, kLmTraceHead);
+  std::memcpy(h->trace.data(), r->trace, (size_t)head * 8 * sizeof(double));
+  if (rows > head) {  // rare: long LM runs — fetch the remaining rows
+    APD_CUDA(h, cudaMemcpyAsync(h->trace.data() + (size_t)head * 8, h->lm_result.as<LmResult>()->trace + (size_t)head * 8,
+                                (size_t)(rows - head) * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  if (h->lm_failed) std::fprintf(stderr, "lm not converged!!\n");  // lsq :72
+  h->final_pose = x0;
+  for (int a = 0; a < 4; a++)
+    for (int c = 0; c < 4; c++) h->final_T[c * 4 + a] = (float)x0(a, c);  // lsq :78
+  h->corr_n = h->src.n;
+  return APD_OK;
+}
+
+// LsqRegistration::computeTransformation (lsq :55-80) in one launch (lm.cu)
+int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg) {
+  int rc = ensure_corr_buffers(h);
+  if (rc != APD_OK) return rc;
+  if (!h->lm_result.p) APD_CUDA(h, h->lm_result.ensure(sizeof(LmResult)));
+  APD_CUDA(h, h->h_lm.ensure(kLmHeadBytes));
+  const hm::Pose x0 = guess ? hm::from_colmajor_f32(guess) : hm::Pose::identity();  // lsq :56
+  const LmJob job = lm_job(h, x0);
+  {
+    ProfScope ps(h, APD_K_LM);
+    launch_lm(&job, nullptr, 1, cfg, h->lm_cluster, h->stream, &h->launches);
+  }
+  APD_CUDA(h, cudaGetLastError());
+  APD_CUDA(h, cudaMemcpyAsync(h->h_lm.p, h->lm_result.p, kLmHeadBytes, cudaMemcpyDeviceToHost, h->stream));
+  return APD_OK;
 }
 
 int do_align(apd_handle* h, const float* guess) {
   int rc = ensure_covariances(h);  // FastAPDGICP::computeTransformation (:148-157)
   if (rc != APD_OK) return rc;
+  h->fit_valid = false;
+  if (use_device_loop(h)) {
+    LmConfig cfg = lm_config(h->params);
+    if (h->fuse_fitness) {
+      cfg.want_fitness = 1;
+      cfg.inlier_sq_thr = h->fuse_inlier_sq_thr;
+    }
+    rc = enqueue_device_align(h, guess, cfg);
+    if (rc != APD_OK) return rc;
+    APD_CUDA(h, cudaStreamSynchronize(h->stream));
+    const LmResult* r = reinterpret_cast<const LmResult*>(h->h_lm.p);
+    if (cfg.want_fitness) {
+      h->fit_valid = true;
+      for (int i = 0; i < 3; i++) h->fit[i] = r->fitness[i];
+    }
+    return finish_device_align(h, r);
+  }
   hm::Pose x0 = guess ? hm::from_colmajor_f32(guess) : hm::Pose::identity();  // lsq :56
   h->lm_lambda = -1.0;   // :58
   h->converged = false;  // :59
@@ -772,6 +900,10 @@ int apd_create(int device, apd_handle** out) {
     const double v = std::atof(e);
     if (v > 0.01 && v < 1000.0) h->cells_per_point = v;
   }
+  if (const char* e = std::getenv("APD_LM_CLUSTER")) {
+    const int v = std::atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) h->lm_cluster = v;
+  }
   if (const char* e = std::getenv("APD_KNN_MODE")) h->knn_mode = std::strcmp(e, "warp") == 0 ? 1 : (std::strcmp(e, "thread") == 0 ? 2 : 0);
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   for (int i = 0; i < 36; i++) h->final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity()
@@ -790,6 +922,8 @@ int apd_destroy(apd_handle* h) {
   h->corr.release(); h->sqd.release(); h->mahaA.release(); h->mahaB.release();
   h->work.release(); h->scratch.release(); h->partials.release(); h->small.release();
   h->h_small.release();
+  h->lm_result.release();
+  h->h_lm.release();
   cudaStreamDestroy(h->stream);
   delete h;
   return APD_OK;
@@ -977,50 +1111,211 @@ int apd_get_lm_trace(apd_handle* h, double* rows, int32_t max_rows, int32_t* n_r
 }
 
 // ---- batched registrations ---------------------------------------------------
+}  // extern "C"
+
+// A pool of workers, one handle (CUDA stream) and one host thread each. Pairs are independent (reference
+// loop_detector.cpp:222-236 runs them serially), so a worker takes the next pair, stages and copies its clouds,
+// enqueues grid build + covariances + the device-resident optimizer loop (+ the fitness pass) and waits for
+// the one result copy; the other workers' kernels and copies fill the GPU meanwhile.
+struct apd_batch {
+  int device = 0;
+  std::vector<apd_handle*> handles;
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  uint64_t generation = 0;
+  int pending = 0;
+  bool stop = false;
+  // the current call
+  const apd_pair* pairs = nullptr;
+  apd_result* results = nullptr;
+  int n_pairs = 0, stride = 0, xyz_off = 0, label_off = 0, with_fitness = 0;
+  bool device_clouds = false;
+  std::atomic<int> next{0};
+};
+
+namespace {
+
+void batch_one(apd_batch* b, apd_handle* h, int i) {
+  const apd_pair& pr = b->pairs[i];
+  apd_result& r = b->results[i];
+  std::memset(&r, 0, sizeof(r));
+  // the reference benchmark protocol: clearTarget; clearSource; setInputTarget; setInputSource; align (align.cpp:57-83)
+  apd_clear_target(h);
+  apd_clear_source(h);
+  int rc;
+  if (b->device_clouds) {
+    rc = apd_set_target_device(h, pr.target, pr.n_target);
+    if (rc == APD_OK) rc = apd_set_source_device(h, pr.source, pr.n_source);
+  } else {
+    rc = apd_set_target(h, pr.target, pr.n_target, b->stride, b->xyz_off, b->label_off, 0);
+    if (rc == APD_OK) rc = apd_set_source(h, pr.source, pr.n_source, b->stride, b->xyz_off, b->label_off, 0);
+  }
+  int32_t conv = 0, it = 0;
+  h->fuse_fitness = b->with_fitness != 0;
+  if (rc == APD_OK) rc = apd_align(h, pr.guess, r.T, nullptr, nullptr, &conv, &it, nullptr);
+  r.converged = conv;
+  r.iterations = it;
+  r.fitness = 0.0;
+  if (rc == APD_OK && b->with_fitness) {
+    if (h->fit_valid) {  // the device loop already ran the pass on the final pose
+      const int nr = (int)h->fit[1];
+      r.fitness = nr > 0 ? h->fit[0] / nr : std::numeric_limits<double>::max();
+      r.n_inliers = (int)h->fit[2];
+    } else {
+      rc = apd_fitness(h, nullptr, DBL_MAX, &r.fitness, nullptr, 0.25, &r.n_inliers);
+    }
+  }
+  r.status = rc;
+}
+
+void batch_worker(apd_batch* b, int wi) {
+  cudaSetDevice(b->device);
+  apd_handle* h = b->handles[wi];
+  uint64_t seen = 0;
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(b->mu);
+      b->cv_work.wait(lk, [&] { return b->stop || b->generation != seen; });
+      if (b->stop) return;
+      seen = b->generation;
+    }
+    for (;;) {
+      const int i = b->next.fetch_add(1);
+      if (i >= b->n_pairs) break;
+      batch_one(b, h, i);
+    }
+    {
+      std::lock_guard<std::mutex> lk(b->mu);
+      if (--b->pending == 0) b->cv_done.notify_all();
+    }
+  }
+}
+
+int batch_run(apd_batch* b, const apd_pair* pairs, int32_t n_pairs, int32_t stride, int32_t xyz_off, int32_t label_off, bool device_clouds,
+              int32_t with_fitness, apd_result* results) {
+  if (!b || !pairs || !results || n_pairs < 0) return APD_ERR_INVALID;
+  if (n_pairs == 0) return APD_OK;
+  {
+    std::lock_guard<std::mutex> lk(b->mu);
+    b->pairs = pairs;
+    b->results = results;
+    b->n_pairs = n_pairs;
+    b->stride = stride;
+    b->xyz_off = xyz_off;
+    b->label_off = label_off;
+    b->with_fitness = with_fitness;
+    b->device_clouds = device_clouds;
+    b->next.store(0);
+    b->pending = (int)b->threads.size();
+    b->generation++;
+  }
+  b->cv_work.notify_all();
+  std::unique_lock<std::mutex> lk(b->mu);
+  b->cv_done.wait(lk, [&] { return b->pending == 0; });
+  return APD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int apd_batch_create(int device, int32_t n_workers, apd_batch** out) {
+  if (!out) return APD_ERR_INVALID;
+  *out = nullptr;
+  if (n_workers < 1) n_workers = 1;
+  if (n_workers > 64) n_workers = 64;
+  apd_batch* b = new apd_batch();
+  b->device = device;
+  for (int s = 0; s < n_workers; s++) {
+    apd_handle* h = nullptr;
+    const int rc = apd_create(device, &h);
+    if (rc != APD_OK) {
+      for (auto* hh : b->handles) apd_destroy(hh);
+      delete b;
+      return rc;
+    }
+    b->handles.push_back(h);
+  }
+  for (int s = 0; s < n_workers; s++) b->threads.emplace_back(batch_worker, b, s);
+  *out = b;
+  return APD_OK;
+}
+
+int apd_batch_destroy(apd_batch* b) {
+  if (!b) return APD_OK;
+  {
+    std::lock_guard<std::mutex> lk(b->mu);
+    b->stop = true;
+  }
+  b->cv_work.notify_all();
+  for (auto& t : b->threads) t.join();
+  for (auto* h : b->handles) apd_destroy(h);
+  delete b;
+  return APD_OK;
+}
+
+int apd_batch_set_params(apd_batch* b, const apd_params* p) {
+  if (!b || !p) return APD_ERR_INVALID;
+  for (auto* h : b->handles) {
+    const int rc = apd_set_params(h, p);
+    if (rc != APD_OK) return rc;
+  }
+  return APD_OK;
+}
+
+int apd_batch_align(apd_batch* b, const apd_pair* pairs, int32_t n_pairs, int32_t stride, int32_t xyz_off, int32_t label_off,
+                    int32_t with_fitness, apd_result* results) {
+  return batch_run(b, pairs, n_pairs, stride, xyz_off, label_off, false, with_fitness, results);
+}
+
+int apd_batch_align_device(apd_batch* b, const apd_pair* pairs, int32_t n_pairs, int32_t with_fitness, apd_result* results) {
+  return batch_run(b, pairs, n_pairs, 16, 0, 12, true, with_fitness, results);
+}
+
+int64_t apd_batch_launch_count(const apd_batch* b) {
+  int64_t n = 0;
+  if (b)
+    for (auto* h : b->handles) n += h->launches;
+  return n;
+}
+
+int apd_batch_set_profiling(apd_batch* b, int32_t enabled) {
+  if (!b) return APD_ERR_INVALID;
+  for (auto* h : b->handles) apd_set_profiling(h, enabled);
+  return APD_OK;
+}
+
+int apd_batch_get_kernel_ms(apd_batch* b, double* ms, int64_t* launches) {
+  if (!b) return APD_ERR_INVALID;
+  for (int i = 0; i < APD_K_COUNT; i++) {
+    if (ms) ms[i] = 0.0;
+    if (launches) launches[i] = 0;
+  }
+  for (auto* h : b->handles) {
+    double m[APD_K_COUNT];
+    int64_t l[APD_K_COUNT];
+    apd_get_kernel_ms(h, m, l);
+    for (int i = 0; i < APD_K_COUNT; i++) {
+      if (ms) ms[i] += m[i];
+      if (launches) launches[i] += l[i];
+    }
+  }
+  return APD_OK;
+}
+
 int apd_align_batch(int device, const apd_params* p, const apd_pair* pairs, int32_t n_pairs, int32_t stride, int32_t xyz_off,
                     int32_t label_off, int32_t n_streams, int32_t with_fitness, apd_result* results) {
   if (!pairs || !results || n_pairs < 0) return APD_ERR_INVALID;
   if (n_streams < 1) n_streams = 1;
-  if (n_streams > 32) n_streams = 32;
   if (n_streams > n_pairs) n_streams = std::max(1, n_pairs);
-  std::vector<apd_handle*> hs(n_streams, nullptr);
-  for (int s = 0; s < n_streams; s++) {
-    int rc = apd_create(device, &hs[s]);
-    if (rc != APD_OK) {
-      for (auto* h : hs) apd_destroy(h);
-      return rc;
-    }
-    if (p) apd_set_params(hs[s], p);
-  }
-  std::atomic<int> next(0);
-  auto worker = [&](int s) {
-    cudaSetDevice(device);
-    apd_handle* h = hs[s];
-    for (;;) {
-      const int i = next.fetch_add(1);
-      if (i >= n_pairs) break;
-      const apd_pair& pr = pairs[i];
-      apd_result& r = results[i];
-      std::memset(&r, 0, sizeof(r));
-      // the reference benchmark protocol: clearTarget; clearSource; setInputTarget; setInputSource; align (align.cpp:57-83)
-      apd_clear_target(h);
-      apd_clear_source(h);
-      int rc = apd_set_target(h, pr.target, pr.n_target, stride, xyz_off, label_off, 0);
-      if (rc == APD_OK) rc = apd_set_source(h, pr.source, pr.n_source, stride, xyz_off, label_off, 0);
-      int32_t conv = 0, it = 0;
-      if (rc == APD_OK) rc = apd_align(h, pr.guess, r.T, nullptr, nullptr, &conv, &it, nullptr);
-      r.converged = conv;
-      r.iterations = it;
-      r.fitness = 0.0;
-      if (rc == APD_OK && with_fitness) rc = apd_fitness(h, nullptr, DBL_MAX, &r.fitness, nullptr, 0.25, &r.n_inliers);
-      r.status = rc;
-    }
-  };
-  std::vector<std::thread> th;
-  for (int s = 0; s < n_streams; s++) th.emplace_back(worker, s);
-  for (auto& t : th) t.join();
-  for (auto* h : hs) apd_destroy(h);
-  return APD_OK;
+  apd_batch* b = nullptr;
+  int rc = apd_batch_create(device, n_streams, &b);
+  if (rc != APD_OK) return rc;
+  if (p) rc = apd_batch_set_params(b, p);
+  if (rc == APD_OK) rc = apd_batch_align(b, pairs, n_pairs, stride, xyz_off, label_off, with_fitness, results);
+  apd_batch_destroy(b);
+  return rc;
 }
 
 // ---- source-sharded registration ------------------------------------------------

@@ -10,7 +10,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17
 if [[ "${APD_PTXAS_V:-0}" == "1" ]]; then FLAGS+=(-Xptxas -v); fi
 mkdir -p "${HERE}/_obj"
 pids=()
-for f in grid knn_cov corr linearize apdgicp; do
+for f in grid knn_cov corr linearize lm apdgicp; do
   "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${HERE}/_obj/${f}.o" &
   pids+=($!)
 done

@@ -4,116 +4,13 @@
 // matrix). Replaces FastAPDGICP::update_correspondences (reference
 // fast_apdgicp_impl.hpp:160-220). Also the fitness pass (pcl getFitnessScore)
 // and the export hooks.
-#include "kernels.cuh"
+#include "point_math.cuh"
 
 namespace apd {
 
 namespace {
 
 constexpr int kThreads = 128;
-constexpr unsigned long long kInfKey = 0xffffffffffffffffull;
-
-// scan one contiguous range of the cell-sorted target points
-__device__ __forceinline__ void scan_range(const float4* __restrict__ spts, int b, int e, float qx, float qy, float qz,
-                                           unsigned long long& best, int& best_pos) {
-  for (int j = b; j < e; j++) {
-    const float4 p = __ldg(&spts[j]);
-    const unsigned long long key = pack_key(sqdist_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
-    if (key < best) {
-      best = key;
-      best_pos = j;
-    }
-  }
-}
-
-// Exact nearest neighbour by (d2, original index). Expands Chebyshev shells of
-// cells until the best distance is provably final, or until every unscanned
-// point is farther than `limit` (then the caller rejects the match anyway).
-// G consecutive lanes share one query (G = 1, 2, 4, 8, 16, 32): the x-rows of a
-// shell are dealt round-robin to the G lanes and the group's best key is
-// min-reduced with shuffles after every shell, so the critical path of a query is
-// ~1/G of the single-thread scan (small source clouds are latency-bound).
-// All G lanes return the same result.
-template <int G>
-__device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
-                                          float qx, float qy, float qz, double limit_sq, unsigned long long& best, int& best_pos) {
-  const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
-  const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
-  const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
-  const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
-  best = kInfKey;
-  best_pos = -1;
-  // groups of one warp leave the shell loop at different times: shuffle within the group's own lanes only
-  const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-  auto group_min = [&]() {
-    if (G > 1) {
-#pragma unroll
-      for (int o = G >> 1; o > 0; o >>= 1) {
-        const unsigned long long ob = __shfl_xor_sync(gmask, best, o);
-        const int op = __shfl_xor_sync(gmask, best_pos, o);
-        if (ob < best) {
-          best = ob;
-          best_pos = op;
-        }
-      }
-    }
-  };
-  // ring 0+1: 3x3x3 cube as 9 x-rows
-  {
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-    for (int ri = sub; ri < 9; ri += G) {
-      const int y = cy + (ri % 3) - 1, z = cz + (ri / 3) - 1;
-      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
-      const int row = (z * g.ny + y) * g.nx;
-      scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
-    }
-    group_min();
-  }
-  const float mg = 0.002f * g.cell;
-  // thick shells (r, rr]: one cell at a time near the query, then growing ~1.5x (see knn_cov.cu)
-  for (int r = 1;;) {
-    const float lb = ((float)r - 0.002f) * g.cell;
-    const float lb2 = lb * lb;
-    if (best != kInfKey && __uint_as_float((unsigned)(best >> 32)) < lb2) break;
-    if ((double)lb2 >= limit_sq) break;
-    if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
-    const int rr = r < 3 ? r + 1 : r + (r >> 1) + 1;
-    const int side = 2 * rr + 1;
-    const int x0 = max(cx - rr, 0), x1 = min(cx + rr, g.nx - 1);
-    for (int ri = sub; ri < side * side; ri += G) {
-      const int dy = ri % side - rr, dz = ri / side - rr;
-      const int y = cy + dy, z = cz + dz;
-      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
-      // skip the row if even its nearest point cannot beat the current best / the limit
-      const float loy = g.oy + (float)y * g.cell - mg, hiy = g.oy + (float)(y + 1) * g.cell + mg;
-      const float loz = g.oz + (float)z * g.cell - mg, hiz = g.oz + (float)(z + 1) * g.cell + mg;
-      const float ddy = fmaxf(0.f, fmaxf(loy - qy, qy - hiy)), ddz = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
-      const float dyz2 = (ddy * ddy + ddz * ddz) * 0.9999f;
-      if ((double)dyz2 >= limit_sq) continue;
-      if (best != kInfKey && dyz2 > __uint_as_float((unsigned)(best >> 32))) continue;
-      const int row = (z * g.ny + y) * g.nx;
-      if (dy > r || dy < -r || dz > r || dz < -r) {  // row outside the scanned cube: its whole x-range
-        scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
-      } else {  // row crosses the scanned cube: the two end pieces
-        const int xl = min(cx - r - 1, g.nx - 1), xr = max(cx + r + 1, 0);
-        if (x0 <= xl) scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + xl + 1]), qx, qy, qz, best, best_pos);
-        if (xr <= x1) scan_range(spts, (int)__ldg(&cell_start[row + xr]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
-      }
-    }
-    group_min();
-    r = rr;
-  }
-}
-
-__device__ __forceinline__ PoseF pose_to_f32(const PoseD& T) {
-  PoseF f;
-#pragma unroll
-  for (int i = 0; i < 9; i++) f.r[i] = (float)T.r[i];  // Isometry3d::cast<float>() (:164)
-#pragma unroll
-  for (int i = 0; i < 3; i++) f.t[i] = (float)T.t[i];
-  return f;
-}
-
 template <bool kFp64, int G>
 __global__ void __launch_bounds__(kThreads) update_corr_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_label,
                                                                const double* __restrict__ s_cov, int n_src,
@@ -143,66 +40,8 @@ __global__ void __launch_bounds__(kThreads) update_corr_kernel(const float4* __r
   }
   corr[i] = pos | ((t_label[pos] == s_label[i]) ? kCorrLabelBit : 0);  // label test of :271-273, hoisted
 
-  // radar noise covariance at the transformed point (:194-210)
-  const double dpx = (double)px, dpy = (double)py, dpz = (double)pz;
-  const double dist = sqrt(dpx * dpx + dpy * dpy + dpz * dpz);
-  const double s_x = dist * np.dist_var / 400;
-  const double s_y = dist * np.sin_az;
-  const double s_z = dist * np.sin_el;
-  const float rho_xy = __fsqrt_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)));
-  // float-valued angles as in the reference (atan2f); evaluated in double and rounded to float
-  const double elevation = (double)(float)atan2((double)rho_xy, dpz);
-  const double azimuth = (double)(float)atan2(dpy, dpx);
-  double sz_, cz_, sy_, cy_;
-  sincos(azimuth * 0.5, &sz_, &cz_);
-  sincos(elevation * 0.5, &sy_, &cy_);
-  // quaternion of AngleAxis(az, Z) * AngleAxis(el, Y) -> rotation matrix (Eigen toRotationMatrix)
-  const double qw = cz_ * cy_, qx = -(sz_ * sy_), qy = cz_ * sy_, qz = sz_ * cy_;
-  const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
-  const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
-  const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
-  const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
-  double R[9];
-  R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
-  R[3] = txy + twz; R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
-  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.0 - (txx + tyy);
-  const double sc[3] = {s_x, s_y, s_z};
-  double A[9];
-#pragma unroll
-  for (int r = 0; r < 3; r++)
-#pragma unroll
-    for (int c = 0; c < 3; c++) A[r * 3 + c] = R[r * 3 + c] * sc[c];
-  Sym3 cr;  // cov_r = A A^T
-  cr.v[0] = A[0] * A[0] + A[1] * A[1] + A[2] * A[2];
-  cr.v[1] = A[0] * A[3] + A[1] * A[4] + A[2] * A[5];
-  cr.v[2] = A[0] * A[6] + A[1] * A[7] + A[2] * A[8];
-  cr.v[3] = A[3] * A[3] + A[4] * A[4] + A[5] * A[5];
-  cr.v[4] = A[3] * A[6] + A[4] * A[7] + A[5] * A[8];
-  cr.v[5] = A[6] * A[6] + A[7] * A[7] + A[8] * A[8];
-
-  // RCR = (cov_B + cov_r) + T (cov_A + cov_r) T^T (:213-215), 3x3 block
-  Sym3 ca, cb;
-#pragma unroll
-  for (int e = 0; e < 6; e++) {
-    ca.v[e] = s_cov[(size_t)i * 6 + e] + cr.v[e];
-    cb.v[e] = t_cov[(size_t)pos * 6 + e] + cr.v[e];
-  }
-  // X = Rt * ca (3x3 full), then RCR = cb + X * Rt^T
-  const double* Rt = T.r;
-  const double cam[9] = {ca.v[0], ca.v[1], ca.v[2], ca.v[1], ca.v[3], ca.v[4], ca.v[2], ca.v[4], ca.v[5]};
-  double X[9];
-#pragma unroll
-  for (int r = 0; r < 3; r++)
-#pragma unroll
-    for (int c = 0; c < 3; c++) X[r * 3 + c] = Rt[r * 3 + 0] * cam[0 * 3 + c] + Rt[r * 3 + 1] * cam[1 * 3 + c] + Rt[r * 3 + 2] * cam[2 * 3 + c];
-  Sym3 rcr;
-  const int RR[6] = {0, 0, 0, 1, 1, 2}, CC[6] = {0, 1, 2, 1, 2, 2};
-#pragma unroll
-  for (int e = 0; e < 6; e++) {
-    const int r = RR[e], c = CC[e];
-    rcr.v[e] = cb.v[e] + (X[r * 3 + 0] * Rt[c * 3 + 0] + X[r * 3 + 1] * Rt[c * 3 + 1] + X[r * 3 + 2] * Rt[c * 3 + 2]);
-  }
-  const Sym3 M = sym_inverse(rcr);  // :217-218
+  // radar noise covariance, combined covariance and its inverse (:194-218)
+  const Sym3 M = mahalanobis_of(px, py, pz, s_cov + (size_t)i * 6, t_cov + (size_t)pos * 6, T, np);
   if (kFp64) {
     double2* mA = reinterpret_cast<double2*>(mahaA);
     double2* mB = reinterpret_cast<double2*>(mahaB);

@@ -97,4 +97,39 @@ struct ReduceWork {
 void launch_linearize(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const CorrOut& c, double n_total,
                       bool want_hb, const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches);
 
+// ---- lm.cu ---------------------------------------------------------------------
+// The device-resident optimizer loop (LsqRegistration::computeTransformation,
+// reference lsq_registration_impl.hpp:55-173) of one registration per cluster.
+constexpr int kLmTraceRows = 640;  // max_iterations (64) x lm_max_iterations (10) rows of 8 doubles
+constexpr int kLmTraceHead = 24;   // rows copied back together with the result header
+struct LmResult {
+  double pose[12];     // r[9] row-major, t[3]: the fp64 x0 after the last accepted step
+  double H[36];        // final_hessian_
+  double lm_lambda;
+  double fitness[3];   // sum d2, n in range, n inliers (only with want_fitness)
+  int converged, nr_iterations, lm_failed, n_trace;
+  int hessian_set, pad_;  // hessian_set: H holds a final_hessian_ (some step was accepted)
+  double trace[kLmTraceRows * 8];
+};
+struct LmJob {
+  const float4* s_spts; const float* s_label; const double* s_cov; const float* s_geo; const double* s_geo64;
+  const float4* t_spts; const float* t_label; const double* t_cov; const uint32_t* t_cell_start;
+  GridDesc tg;
+  int n_src;
+  int* corr; float* sqd; void* mahaA; void* mahaB;
+  double cl_w;         // 1 / correspondences_.size() (:273)
+  double guess[12];    // r[9] row-major, t[3]
+  LmResult* result;    // device memory
+};
+struct LmConfig {
+  int max_iterations, optimizer, lm_max_iterations, maha_fp64, want_fitness;
+  double rotation_epsilon, transformation_epsilon, lm_init_lambda_factor;
+  double fitness_max_range, inlier_sq_thr;
+  NoiseParams np;
+};
+constexpr int kLmMaxSource = 32768;  // larger source clouds use the streaming kernels + host loop
+// one: job passed by value (d_jobs == nullptr, n_jobs == 1); d_jobs: device array of n_jobs jobs.
+// cluster: CTAs per registration (1, 2, 4 or 8).
+void launch_lm(const LmJob* one, const LmJob* d_jobs, int n_jobs, const LmConfig& cfg, int cluster, cudaStream_t s, int64_t* launches);
+
 }  // namespace apd

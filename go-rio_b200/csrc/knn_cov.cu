@@ -219,16 +219,18 @@ __global__ void __launch_bounds__(kWarpKnnThreads) knn_cov_kernel(const float4* 
   // covariance of the k neighbours (reference :366-372): fp64, centred, / k
   const int nidx = (lane < k) ? (int)(unsigned)(mykey & 0xffffffffull) : 0;
   if (neighbors && lane < k) neighbors[(size_t)qi * k + lane] = nidx;
-  // The k neighbour coordinates go through shared memory; lanes 0-2 sum the means and lanes 0-5 the six
-  // centred products serially in neighbour order with one rounding per operation — the CPU path's order, so
-  // the raw covariance is bit-identical to the oracle's (and ~2x cheaper than nine butterfly reductions).
-  __shared__ double kcoord[kWarpKnnThreads / 32][3][32];
+  // Serial, in-neighbour-order sums with one rounding per operation — the CPU path's order, so the raw covariance
+  // is bit-identical to the oracle's — but only the ADDITIONS are serial: lane j rounds its own centred coordinates
+  // and their six products in parallel, then lanes 0-5 each add one column of k products.
+  __shared__ double kcoord[kWarpKnnThreads / 32][6][32];
   double (*kc)[32] = kcoord[threadIdx.x >> 5];
+  double px = 0.0, py = 0.0, pz = 0.0;
   if (lane < k) {
     const float4 p = pts[nidx];
-    kc[0][lane] = (double)p.x;
-    kc[1][lane] = (double)p.y;
-    kc[2][lane] = (double)p.z;
+    px = (double)p.x; py = (double)p.y; pz = (double)p.z;
+    kc[0][lane] = px;
+    kc[1][lane] = py;
+    kc[2][lane] = pz;
   }
   __syncwarp();
   double mean = 0.0;
@@ -237,11 +239,16 @@ __global__ void __launch_bounds__(kWarpKnnThreads) knn_cov_kernel(const float4* 
     mean /= (double)k;
   }
   const double mx = __shfl_sync(kFull, mean, 0), my = __shfl_sync(kFull, mean, 1), mz = __shfl_sync(kFull, mean, 2);
+  __syncwarp();
+  if (lane < k) {
+    const double dx = __dsub_rn(px, mx), dy = __dsub_rn(py, my), dz = __dsub_rn(pz, mz);
+    kc[0][lane] = __dmul_rn(dx, dx); kc[1][lane] = __dmul_rn(dx, dy); kc[2][lane] = __dmul_rn(dx, dz);
+    kc[3][lane] = __dmul_rn(dy, dy); kc[4][lane] = __dmul_rn(dy, dz); kc[5][lane] = __dmul_rn(dz, dz);
+  }
+  __syncwarp();
   if (cov && lane < 6) {
-    const int a = lane < 3 ? 0 : (lane < 5 ? 1 : 2), bq = lane < 3 ? lane : (lane < 5 ? lane - 2 : 2);  // xx xy xz yy yz zz
-    const double ma = a == 0 ? mx : (a == 1 ? my : mz), mb = bq == 0 ? mx : (bq == 1 ? my : mz);
     double acc = 0.0;
-    for (int j = 0; j < k; j++) acc = __dadd_rn(acc, __dmul_rn(__dsub_rn(kc[a][j], ma), __dsub_rn(kc[bq][j], mb)));
+    for (int j = 0; j < k; j++) acc = __dadd_rn(acc, kc[lane][j]);
     cov[(size_t)w * 6 + lane] = acc / (double)k;
   }
   __syncwarp();

@@ -20,7 +20,7 @@
 // per-block order -> per-block partials -> the last block (atomic ticket) adds
 // the partials in block order. The tile->CTA mapping is static, so for a given n
 // the result is bit-reproducible run to run.
-#include "kernels.cuh"
+#include "point_math.cuh"
 
 namespace apd {
 
@@ -182,52 +182,7 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
       m[0] = (double)ma.x; m[1] = (double)ma.y; m[2] = (double)ma.z; m[3] = (double)ma.w; m[4] = (double)mb.x; m[5] = (double)mb.y;
       geo = (double)reinterpret_cast<const float*>(st + L::kGeo)[tid];
     }
-#pragma unroll
-    for (int e = 0; e < 6; e++) m[e] = valid ? m[e] : 0.0;
-
-    // (points past n in the last tile hold padding bytes: zero them so 0 * garbage cannot make a NaN)
-    const double ax = valid ? (double)a.x : 0.0, ay = valid ? (double)a.y : 0.0, az = valid ? (double)a.z : 0.0;
-    const double bx = valid ? (double)b.x : 0.0, by = valid ? (double)b.y : 0.0, bz = valid ? (double)b.z : 0.0;
-    // transed_mean_A = T * mean_A ; error = mean_B - transed_mean_A (:262-263)
-    const double x = ((T.r[0] * ax + T.r[1] * ay) + T.r[2] * az) + T.t[0];
-    const double y = ((T.r[3] * ax + T.r[4] * ay) + T.r[5] * az) + T.t[1];
-    const double z = ((T.r[6] * ax + T.r[7] * ay) + T.r[8] * az) + T.t[2];
-    const double e0 = bx - x, e1 = by - y, e2 = bz - z;
-    // M e and the weighted cost (:276)
-    const double me0 = (m[0] * e0 + m[1] * e1) + m[2] * e2;
-    const double me1 = (m[1] * e0 + m[3] * e1) + m[4] * e2;
-    const double me2 = (m[2] * e0 + m[4] * e1) + m[5] * e2;
-    const double q = (e0 * me0 + e1 * me1) + e2 * me2;
-    const double w = (1.0 + (valid ? geo : 0.0)) + ((c & kCorrLabelBit) ? cl_w : 0.0);
-    if (!kHB) {
-      acc[0] += valid ? w * q : 0.0;
-    } else {
-      acc[27] += valid ? w * q : 0.0;
-      // N = M * skew(t), t = (x,y,z): N[:,0] = M[:,1] z - M[:,2] y, N[:,1] = M[:,2] x - M[:,0] z, N[:,2] = M[:,0] y - M[:,1] x
-      const double n00 = m[1] * z - m[2] * y, n01 = m[2] * x - m[0] * z, n02 = m[0] * y - m[1] * x;
-      const double n10 = m[3] * z - m[4] * y, n11 = m[4] * x - m[1] * z, n12 = m[1] * y - m[3] * x;
-      const double n20 = m[4] * z - m[5] * y, n21 = m[5] * x - m[2] * z, n22 = m[2] * y - m[4] * x;
-      // top-left S^T M S (symmetric): TL[r][c] = sum_k S[k][r] N[k][c]
-      acc[0] += z * n10 - y * n20;    // (0,0)
-      acc[1] += z * n11 - y * n21;    // (0,1)
-      acc[2] += z * n12 - y * n22;    // (0,2)
-      acc[6] += x * n21 - z * n01;    // (1,1)
-      acc[7] += x * n22 - z * n02;    // (1,2)
-      acc[11] += y * n02 - x * n12;   // (2,2)
-      // top-right -S^T M = -N^T: H(r, 3+c) = -N[c][r]
-      acc[3] -= n00;  acc[4] -= n10;  acc[5] -= n20;    // row 0
-      acc[8] -= n01;  acc[9] -= n11;  acc[10] -= n21;   // row 1
-      acc[12] -= n02; acc[13] -= n12; acc[14] -= n22;   // row 2
-      // bottom-right M
-      acc[15] += m[0]; acc[16] += m[1]; acc[17] += m[2];
-      acc[18] += m[3]; acc[19] += m[4];
-      acc[20] += m[5];
-      // b = J^T M e = [S^T (M e); -(M e)]
-      acc[21] += z * me1 - y * me2;
-      acc[22] += x * me2 - z * me0;
-      acc[23] += y * me0 - x * me1;
-      acc[24] -= me0; acc[25] -= me1; acc[26] -= me2;
-    }
+    accumulate_point<kHB>(acc, valid, a, b, m, geo, c, T, cl_w);
 
     __syncthreads();  // every thread is done with stage j % kStages
     if (tid == 0 && j + kStages < my) issue_tile(j + kStages);

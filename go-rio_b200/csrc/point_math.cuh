@@ -1,0 +1,238 @@
+// Per-point device functions shared by the streaming kernels (corr.cu,
+// linearize.cu: one launch per stage, large clouds) and the device-resident LM
+// kernel (lm.cu: the whole optimizer loop of one registration in one launch).
+// Both paths run the SAME arithmetic in the SAME order per point.
+#pragma once
+#include "kernels.cuh"
+
+namespace apd {
+
+constexpr unsigned long long kInfKey = 0xffffffffffffffffull;
+
+// scan one contiguous range of the cell-sorted target points
+__device__ __forceinline__ void scan_range(const float4* __restrict__ spts, int b, int e, float qx, float qy, float qz,
+                                           unsigned long long& best, int& best_pos) {
+  for (int j = b; j < e; j++) {
+    const float4 p = __ldg(&spts[j]);
+    const unsigned long long key = pack_key(sqdist_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+    if (key < best) {
+      best = key;
+      best_pos = j;
+    }
+  }
+}
+
+// Exact nearest neighbour by (d2, original index). Expands Chebyshev shells of
+// cells until the best distance is provably final, or until every unscanned
+// point is farther than `limit` (then the caller rejects the match anyway).
+// G consecutive lanes share one query (G = 1, 2, 4, 8, 16, 32): the x-rows of a
+// shell are dealt round-robin to the G lanes and the group's best key is
+// min-reduced with shuffles after every shell, so the critical path of a query is
+// ~1/G of the single-thread scan (small source clouds are latency-bound).
+// All G lanes return the same result.
+template <int G>
+__device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
+                                          float qx, float qy, float qz, double limit_sq, unsigned long long& best, int& best_pos) {
+  const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
+  const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
+  best = kInfKey;
+  best_pos = -1;
+  // groups of one warp leave the shell loop at different times: shuffle within the group's own lanes only
+  const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+  auto group_min = [&]() {
+    if (G > 1) {
+#pragma unroll
+      for (int o = G >> 1; o > 0; o >>= 1) {
+        const unsigned long long ob = __shfl_xor_sync(gmask, best, o);
+        const int op = __shfl_xor_sync(gmask, best_pos, o);
+        if (ob < best) {
+          best = ob;
+          best_pos = op;
+        }
+      }
+    }
+  };
+  // ring 0+1: 3x3x3 cube as 9 x-rows
+  {
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    for (int ri = sub; ri < 9; ri += G) {
+      const int y = cy + (ri % 3) - 1, z = cz + (ri / 3) - 1;
+      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      const int row = (z * g.ny + y) * g.nx;
+      scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
+    }
+    group_min();
+  }
+  const float mg = 0.002f * g.cell;
+  // thick shells (r, rr]: one cell at a time near the query, then growing ~1.5x (see knn_cov.cu)
+  for (int r = 1;;) {
+    const float lb = ((float)r - 0.002f) * g.cell;
+    const float lb2 = lb * lb;
+    if (best != kInfKey && __uint_as_float((unsigned)(best >> 32)) < lb2) break;
+    if ((double)lb2 >= limit_sq) break;
+    if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
+    const int rr = r < 3 ? r + 1 : r + (r >> 1) + 1;
+    const int side = 2 * rr + 1;
+    const int x0 = max(cx - rr, 0), x1 = min(cx + rr, g.nx - 1);
+    for (int ri = sub; ri < side * side; ri += G) {
+      const int dy = ri % side - rr, dz = ri / side - rr;
+      const int y = cy + dy, z = cz + dz;
+      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      // skip the row if even its nearest point cannot beat the current best / the limit
+      const float loy = g.oy + (float)y * g.cell - mg, hiy = g.oy + (float)(y + 1) * g.cell + mg;
+      const float loz = g.oz + (float)z * g.cell - mg, hiz = g.oz + (float)(z + 1) * g.cell + mg;
+      const float ddy = fmaxf(0.f, fmaxf(loy - qy, qy - hiy)), ddz = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
+      const float dyz2 = (ddy * ddy + ddz * ddz) * 0.9999f;
+      if ((double)dyz2 >= limit_sq) continue;
+      if (best != kInfKey && dyz2 > __uint_as_float((unsigned)(best >> 32))) continue;
+      const int row = (z * g.ny + y) * g.nx;
+      if (dy > r || dy < -r || dz > r || dz < -r) {  // row outside the scanned cube: its whole x-range
+        scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
+      } else {  // row crosses the scanned cube: the two end pieces
+        const int xl = min(cx - r - 1, g.nx - 1), xr = max(cx + r + 1, 0);
+        if (x0 <= xl) scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + xl + 1]), qx, qy, qz, best, best_pos);
+        if (xr <= x1) scan_range(spts, (int)__ldg(&cell_start[row + xr]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
+      }
+    }
+    group_min();
+    r = rr;
+  }
+}
+
+__device__ __forceinline__ PoseF pose_to_f32(const PoseD& T) {
+  PoseF f;
+#pragma unroll
+  for (int i = 0; i < 9; i++) f.r[i] = (float)T.r[i];  // Isometry3d::cast<float>() (:164)
+#pragma unroll
+  for (int i = 0; i < 3; i++) f.t[i] = (float)T.t[i];
+  return f;
+}
+
+
+// Radar noise covariance at the transformed source point (px,py,pz) (reference
+// fast_apdgicp_impl.hpp:194-210), combined covariance
+// RCR = (C_B + C_r) + R (C_A + C_r) R^T (:213-215) and its inverse, the per-point
+// Mahalanobis matrix (:217-218). ca_in / cb_in: the regularised covariances of the
+// source point and of its matched target point (symmetric-6).
+__device__ __forceinline__ Sym3 mahalanobis_of(float px, float py, float pz, const double* __restrict__ ca_in,
+                                               const double* __restrict__ cb_in, const PoseD& T, const NoiseParams& np) {
+  // radar noise covariance at the transformed point (:194-210)
+  const double dpx = (double)px, dpy = (double)py, dpz = (double)pz;
+  const double dist = sqrt(dpx * dpx + dpy * dpy + dpz * dpz);
+  const double s_x = dist * np.dist_var / 400;
+  const double s_y = dist * np.sin_az;
+  const double s_z = dist * np.sin_el;
+  const float rho_xy = __fsqrt_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)));
+  // float-valued angles as in the reference (atan2f); evaluated in double and rounded to float
+  const double elevation = (double)(float)atan2((double)rho_xy, dpz);
+  const double azimuth = (double)(float)atan2(dpy, dpx);
+  double sz_, cz_, sy_, cy_;
+  sincos(azimuth * 0.5, &sz_, &cz_);
+  sincos(elevation * 0.5, &sy_, &cy_);
+  // quaternion of AngleAxis(az, Z) * AngleAxis(el, Y) -> rotation matrix (Eigen toRotationMatrix)
+  const double qw = cz_ * cy_, qx = -(sz_ * sy_), qy = cz_ * sy_, qz = sz_ * cy_;
+  const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
+  const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  double R[9];
+  R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.0 - (txx + tyy);
+  const double sc[3] = {s_x, s_y, s_z};
+  double A[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) A[r * 3 + c] = R[r * 3 + c] * sc[c];
+  Sym3 cr;  // cov_r = A A^T
+  cr.v[0] = A[0] * A[0] + A[1] * A[1] + A[2] * A[2];
+  cr.v[1] = A[0] * A[3] + A[1] * A[4] + A[2] * A[5];
+  cr.v[2] = A[0] * A[6] + A[1] * A[7] + A[2] * A[8];
+  cr.v[3] = A[3] * A[3] + A[4] * A[4] + A[5] * A[5];
+  cr.v[4] = A[3] * A[6] + A[4] * A[7] + A[5] * A[8];
+  cr.v[5] = A[6] * A[6] + A[7] * A[7] + A[8] * A[8];
+
+  // RCR = (cov_B + cov_r) + T (cov_A + cov_r) T^T (:213-215), 3x3 block
+  Sym3 ca, cb;
+#pragma unroll
+  for (int e = 0; e < 6; e++) {
+    ca.v[e] = ca_in[e] + cr.v[e];
+    cb.v[e] = cb_in[e] + cr.v[e];
+  }
+  // X = Rt * ca (3x3 full), then RCR = cb + X * Rt^T
+  const double* Rt = T.r;
+  const double cam[9] = {ca.v[0], ca.v[1], ca.v[2], ca.v[1], ca.v[3], ca.v[4], ca.v[2], ca.v[4], ca.v[5]};
+  double X[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) X[r * 3 + c] = Rt[r * 3 + 0] * cam[0 * 3 + c] + Rt[r * 3 + 1] * cam[1 * 3 + c] + Rt[r * 3 + 2] * cam[2 * 3 + c];
+  Sym3 rcr;
+  const int RR[6] = {0, 0, 0, 1, 1, 2}, CC[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+  for (int e = 0; e < 6; e++) {
+    const int r = RR[e], c = CC[e];
+    rcr.v[e] = cb.v[e] + (X[r * 3 + 0] * Rt[c * 3 + 0] + X[r * 3 + 1] * Rt[c * 3 + 1] + X[r * 3 + 2] * Rt[c * 3 + 2]);
+  }
+  return sym_inverse(rcr);  // :217-218
+}
+
+// One term of the linearize / compute_error sums (reference :255-293, :318-341):
+// e = b - T a, weighted Mahalanobis cost, H_i = J^T M J and b_i = J^T M e with
+// J = [skew(T a), -I]. acc: 28 values (21 upper-triangular H, 6 b, err at [27])
+// when kHB, else 1 value (err at [0]). `valid` = the point has a correspondence.
+template <bool kHB>
+__device__ __forceinline__ void accumulate_point(double* acc, bool valid, const float4& a, const float4& b, const double* m_in, double geo_in,
+                                                 int c, const PoseD& T, double cl_w) {
+  double m[6];
+#pragma unroll
+  for (int e = 0; e < 6; e++) m[e] = valid ? m_in[e] : 0.0;
+  // (invalid points may hold padding bytes: zero them so 0 * garbage cannot make a NaN)
+  const double ax = valid ? (double)a.x : 0.0, ay = valid ? (double)a.y : 0.0, az = valid ? (double)a.z : 0.0;
+  const double bx = valid ? (double)b.x : 0.0, by = valid ? (double)b.y : 0.0, bz = valid ? (double)b.z : 0.0;
+  // transed_mean_A = T * mean_A ; error = mean_B - transed_mean_A (:262-263)
+  const double x = ((T.r[0] * ax + T.r[1] * ay) + T.r[2] * az) + T.t[0];
+  const double y = ((T.r[3] * ax + T.r[4] * ay) + T.r[5] * az) + T.t[1];
+  const double z = ((T.r[6] * ax + T.r[7] * ay) + T.r[8] * az) + T.t[2];
+  const double e0 = bx - x, e1 = by - y, e2 = bz - z;
+  // M e and the weighted cost (:276)
+  const double me0 = (m[0] * e0 + m[1] * e1) + m[2] * e2;
+  const double me1 = (m[1] * e0 + m[3] * e1) + m[4] * e2;
+  const double me2 = (m[2] * e0 + m[4] * e1) + m[5] * e2;
+  const double q = (e0 * me0 + e1 * me1) + e2 * me2;
+  const double w = (1.0 + (valid ? geo_in : 0.0)) + ((c & kCorrLabelBit) ? cl_w : 0.0);
+  if (!kHB) {
+    acc[0] += valid ? w * q : 0.0;
+  } else {
+    acc[27] += valid ? w * q : 0.0;
+    // N = M * skew(t), t = (x,y,z): N[:,0] = M[:,1] z - M[:,2] y, N[:,1] = M[:,2] x - M[:,0] z, N[:,2] = M[:,0] y - M[:,1] x
+    const double n00 = m[1] * z - m[2] * y, n01 = m[2] * x - m[0] * z, n02 = m[0] * y - m[1] * x;
+    const double n10 = m[3] * z - m[4] * y, n11 = m[4] * x - m[1] * z, n12 = m[1] * y - m[3] * x;
+    const double n20 = m[4] * z - m[5] * y, n21 = m[5] * x - m[2] * z, n22 = m[2] * y - m[4] * x;
+    // top-left S^T M S (symmetric): TL[r][c] = sum_k S[k][r] N[k][c]
+    acc[0] += z * n10 - y * n20;    // (0,0)
+    acc[1] += z * n11 - y * n21;    // (0,1)
+    acc[2] += z * n12 - y * n22;    // (0,2)
+    acc[6] += x * n21 - z * n01;    // (1,1)
+    acc[7] += x * n22 - z * n02;    // (1,2)
+    acc[11] += y * n02 - x * n12;   // (2,2)
+    // top-right -S^T M = -N^T: H(r, 3+c) = -N[c][r]
+    acc[3] -= n00;  acc[4] -= n10;  acc[5] -= n20;    // row 0
+    acc[8] -= n01;  acc[9] -= n11;  acc[10] -= n21;   // row 1
+    acc[12] -= n02; acc[13] -= n12; acc[14] -= n22;   // row 2
+    // bottom-right M
+    acc[15] += m[0]; acc[16] += m[1]; acc[17] += m[2];
+    acc[18] += m[3]; acc[19] += m[4];
+    acc[20] += m[5];
+    // b = J^T M e = [S^T (M e); -(M e)]
+    acc[21] += z * me1 - y * me2;
+    acc[22] += x * me2 - z * me0;
+    acc[23] += y * me0 - x * me1;
+    acc[24] -= me0; acc[25] -= me1; acc[26] -= me2;
+  }
+}
+
+}  // namespace apd

@@ -87,7 +87,13 @@ typedef struct apd_params {
                                           matrix as 6 x fp32 (24 B, default),
                                           1: as 6 x fp64 (48 B). Arithmetic is
                                           fp64 either way.                    */
-  int32_t reserved;
+  int32_t host_loop;                   /* 0 (default): the optimizer loop of
+                                          apd_align runs ON THE DEVICE in one
+                                          kernel launch when the source cloud has
+                                          at most 32768 points and the handle is
+                                          not sharded; 1: always drive it from the
+                                          host, one launch per stage (what large
+                                          or sharded clouds use anyway).         */
 } apd_params;
 
 typedef struct apd_handle apd_handle;
@@ -201,12 +207,35 @@ typedef struct apd_result {
   int32_t converged;
   int32_t iterations;
   int32_t status;      /* APD_OK or an error code for this pair              */
-  int32_t n_inliers;   /* correspondences != -1 at the last linearize        */
+  int32_t n_inliers;   /* source points with 1-NN d2 < 0.25 m^2 (with_fitness) */
 } apd_result;
 
-/* Runs n_pairs independent clear/set/align sequences on `device`, pipelined
- * over `n_streams` internal handles (H2D of pair i+1 overlaps the kernels of
- * pair i). */
+/* A batch context: `n_workers` internal handles (one CUDA stream and one host
+ * thread each) that persist across calls, so device buffers, pinned staging
+ * and streams are allocated once. apd_batch_align runs n_pairs independent
+ * {clearTarget; clearSource; setInputTarget; setInputSource; align
+ * [; getFitnessScore]} sequences over them: the staging and H2D copy of one
+ * pair overlap the kernels of the others. With with_fitness != 0 the result
+ * carries getFitnessScore(DBL_MAX) of the final pose and the number of source
+ * points whose nearest target point is closer than 0.5 m (the inlier test of
+ * scan_matching_odometry_nodelet.cpp:677-689). Results do not depend on
+ * n_workers or on the order the pairs are taken. One call at a time per
+ * context. */
+typedef struct apd_batch apd_batch;
+APD_API int apd_batch_create(int device, int32_t n_workers, apd_batch** out);
+APD_API int apd_batch_destroy(apd_batch* b);
+APD_API int apd_batch_set_params(apd_batch* b, const apd_params* p);
+APD_API int apd_batch_align(apd_batch* b, const apd_pair* pairs, int32_t n_pairs, int32_t stride_bytes,
+                    int32_t xyz_off, int32_t label_off, int32_t with_fitness, apd_result* results);
+/* same, the clouds of every pair already on the device as float4 {x,y,z,label}
+ * (apd_pair.source / .target are device pointers) */
+APD_API int apd_batch_align_device(apd_batch* b, const apd_pair* pairs, int32_t n_pairs, int32_t with_fitness,
+                           apd_result* results);
+APD_API int64_t apd_batch_launch_count(const apd_batch* b);
+APD_API int apd_batch_set_profiling(apd_batch* b, int32_t enabled);
+APD_API int apd_batch_get_kernel_ms(apd_batch* b, double* ms /* [APD_K_COUNT] */, int64_t* launches);
+
+/* One-shot convenience: create a context of n_streams workers, run, destroy. */
 APD_API int apd_align_batch(int device, const apd_params* p, const apd_pair* pairs, int32_t n_pairs,
                     int32_t stride_bytes, int32_t xyz_off, int32_t label_off,
                     int32_t n_streams, int32_t with_fitness, apd_result* results);
@@ -236,7 +265,9 @@ enum {
   APD_K_LINEARIZE = 3, /* linearize H/b/err reduction                        */
   APD_K_ERROR = 4,     /* compute_error reduction                            */
   APD_K_FITNESS = 5,
-  APD_K_COUNT = 6
+  APD_K_LM = 6,        /* device-resident optimizer loop (corr + linearize +
+                          error trials + solve of ALL iterations, one launch)  */
+  APD_K_COUNT = 7
 };
 APD_API int apd_set_profiling(apd_handle* h, int32_t enabled);
 APD_API int apd_get_kernel_ms(apd_handle* h, double* ms /* [APD_K_COUNT] */, int64_t* launches /* [APD_K_COUNT] */);

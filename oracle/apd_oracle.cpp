@@ -86,7 +86,7 @@ FastAPDGICP::FastAPDGICP() {
   params.lm_debug_print = 0;
   params.lm_init_lambda_factor = 1e-9;
   params.maha_fp64 = 1;
-  params.reserved = 0;
+  params.host_loop = 0;
   final_pose_f64 = M4::identity();
   for (int i = 0; i < 16; i++) final_transformation[i] = (i % 5 == 0) ? 1.f : 0.f;
   for (int i = 0; i < 36; i++) final_hessian[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity() (:23)

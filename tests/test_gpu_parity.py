@@ -255,6 +255,57 @@ def test_align_fp32_mahalanobis_within_north_star_tolerance(gorio, synth, c2):
     assert rel(rg["H"], ro["H"]) < 1e-5
 
 
+@pytest.mark.parametrize("optimizer", [1, 0])
+def test_host_loop_matches_oracle_and_device_loop(gorio, c2_small, optimizer):
+    """apd_align has two drivers of the same kernels' arithmetic: the device-resident loop (lm.cu, default for
+    sources <= 32768 points) and the host loop (host_loop=1; large / sharded clouds). Both must match the oracle,
+    and each other far below the pose tolerance (they differ only in summation order and libm vs CUDA sin/cos)."""
+    src, tgt, _ = c2_small
+    kw = dict(max_correspondence_distance=2.0, optimizer=optimizer, max_iterations=8 if optimizer == 0 else 64, maha_fp64=1)
+    gh, o = make(gorio, src, tgt, **kw, host_loop=1)
+    rh, _ = _check_align(gh, o)
+    gd, o = make(gorio, src, tgt, **kw, host_loop=0)
+    rd, _ = _check_align(gd, o)
+    assert gd.kernel_ms()["lm"][1] == 1 and gh.kernel_ms()["lm"][1] == 0
+    dt, dr = pose_err(rh["T64"], rd["T64"])
+    assert dt < 1e-7 and dr < 1e-7, (dt, dr)
+    assert np.array_equal(gh.get_correspondences()[0], gd.get_correspondences()[0])
+    assert rel(gh.get_mahalanobis(), gd.get_mahalanobis()) < 1e-12
+    # compute_error after a device-loop align reads the correspondences the loop left behind
+    assert abs(gd.compute_error(rd["T64"]) - gh.compute_error(rd["T64"])) / gh.compute_error(rd["T64"]) < 1e-9
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 8])
+def test_device_loop_cluster_sizes(gorio, c2_small, monkeypatch, cluster):
+    """the number of CTAs per registration only changes the summation order"""
+    src, tgt, _ = c2_small
+    g4, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+    r4, _ = _check_align(g4, o)
+    monkeypatch.setenv("APD_LM_CLUSTER", str(cluster))
+    g, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+    r, _ = _check_align(g, o)
+    dt, dr = pose_err(r["T64"], r4["T64"])
+    assert dt < 1e-7 and dr < 1e-7, (dt, dr)
+
+
+def test_device_loop_tiny_and_ragged_sources(gorio, synth, c2_small):
+    """fewer source points than CTAs x lanes, and counts that do not divide by the cluster size"""
+    src, tgt, _ = c2_small
+    for n in (21, 63, 257, 799):
+        s = src[:n].copy()
+        g, o = make(gorio, s, tgt, max_correspondence_distance=2.0, maha_fp64=1)
+        _check_align(g, o)
+
+
+def test_lm_failure_is_reported(gorio, c2_small):
+    """lm_max_iterations exhausted -> converged stays false (lsq_registration_impl.hpp:71-74), same as the oracle"""
+    src, tgt, _ = c2_small
+    for host_loop in (0, 1):
+        g, o = make(gorio, src, tgt, max_correspondence_distance=2.0, lm_max_iterations=1, lm_init_lambda_factor=1e-30,
+                    max_iterations=3, maha_fp64=1, host_loop=host_loop)
+        _check_align(g, o)
+
+
 def test_align_gauss_newton(gorio, c2_small):
     src, tgt, _ = c2_small
     g, o = make(gorio, src, tgt, max_correspondence_distance=2.0, optimizer=0, max_iterations=8, maha_fp64=1)
@@ -391,6 +442,20 @@ def test_align_batch_matches_sequential(gorio, synth):
         assert r["status"] == 0
         assert np.array_equal(r["T"], ra["T"]) and r["converged"] == ra["converged"] and r["iterations"] == ra["iterations"]
         assert abs(r["fitness"] - g.fitness()[0]) < 1e-12
+        assert r["n_inliers"] == g.fitness(None, np.finfo(np.float64).max, 0.25)[2]
+    # a persistent context gives the same answers, call after call, for host and for HBM-resident clouds
+    import torch
+    b = gorio.Batch(0, n_workers=4, max_correspondence_distance=2.0, transformation_epsilon=0.1)
+    dev = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for s, t, _ in pairs for x in (s, t)]
+    dpairs = [((dev[2 * i].data_ptr(), pairs[i][0].shape[0]), (dev[2 * i + 1].data_ptr(), pairs[i][1].shape[0]), None) for i in range(len(pairs))]
+    for prepared in (b.prepare(pairs), b.prepare(dpairs)):
+        for _ in range(2):
+            res2 = b.align(prepared)
+            for r, r2 in zip(res, res2):
+                assert r2["status"] == 0 and np.array_equal(r["T"], r2["T"]) and r["fitness"] == r2["fitness"]
+                assert (r["converged"], r["iterations"], r["n_inliers"]) == (r2["converged"], r2["iterations"], r2["n_inliers"])
+    assert b.kernel_ms()["lm"][1] == 4 * len(pairs)
+    b.close()
 
 
 def test_large_cloud_properties(gorio, synth):
