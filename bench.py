@@ -47,11 +47,11 @@ BYTES_PER_POINT_KNNCOV = 68     # read point 16, write cov 48 + geo 4
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=32, help="scan/submap pairs per step and per GPU")
-    ap.add_argument("--streams", type=int, default=8, help="concurrent handles (CUDA streams) per GPU")
+    ap.add_argument("--pairs", type=int, default=128, help="scan/submap pairs per step and per GPU")
+    ap.add_argument("--streams", type=int, default=16, help="workers of the batch context (handle + CUDA stream + host thread each) per GPU")
     ap.add_argument("--roofline-points", type=int, default=20_000_000)
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-reps", type=int, default=10)

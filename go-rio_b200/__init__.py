@@ -20,7 +20,7 @@ from ._binding import (  # noqa: F401
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "libapdgicp.so")
+LIB_PATH = os.environ.get("APD_LIB") or os.path.join(PKG_DIR, "libapdgicp.so")  # APD_LIB: experiment builds
 
 _lib = None
 

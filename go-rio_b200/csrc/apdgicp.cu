@@ -169,11 +169,16 @@ struct apd_handle {
   int corr_fp64 = 0;
   // scratch
   DevBuf work, scratch, partials, small;  // small: out28 + ticket + fitness
+  DevBuf nbuf;  // neighbour lists (n x k original ids) between the kNN search and the covariance kernel
   PinnedBuf h_small;
   DevBuf lm_result;   // LmResult of the device-resident optimizer loop
   PinnedBuf h_lm;     // its header + first trace rows on the host
   int lm_cluster = 4; // CTAs per registration in the device loop (APD_LM_CLUSTER=1|2|4|8)
   bool lm_failed = false;
+  // wait for the result of the device loop on a blocking-sync event instead of spinning on the stream: the batch
+  // context runs more host threads than it needs cores for (set by apd_batch_create; APD_BLOCKING_SYNC=0|1 overrides)
+  bool blocking_wait = false;
+  cudaEvent_t done_ev = nullptr;
   // batch workers ask the device loop to append the getFitnessScore pass (saves a launch and a round trip per pair)
   bool fuse_fitness = false;
   double fuse_inlier_sq_thr = 0.25;
@@ -420,8 +425,9 @@ int ensure_covariances_of(apd_handle* h, Cloud& c) {
     if (c.n < k) return fail(h, APD_ERR_TOO_FEW, "cloud has fewer points than k_correspondences");
     ProfScope ps(h, APD_K_KNN_COV);
     if (h->knn_use_warp(c.n, k)) {
-      launch_knn_cov(c.view(), k, nullptr, h->stream, &h->launches);
-      launch_regularize(c.view(), h->params.regularization, h->stream, &h->launches);
+      APD_CUDA(h, h->nbuf.ensure((size_t)c.n * k * sizeof(int32_t)));
+      launch_knn_cov(c.view(), k, h->nbuf.as<int32_t>(), nullptr, h->stream, &h->launches);
+      launch_cov_regularize(c.view(), k, h->params.regularization, h->nbuf.as<int32_t>(), h->stream, &h->launches);
     } else {
       launch_knn_cov_fused(c.view(), k, h->params.regularization, nullptr, h->stream, &h->launches);
     }
@@ -808,7 +814,13 @@ int do_align(apd_handle* h, const float* guess) {
     }
     rc = enqueue_device_align(h, guess, cfg);
     if (rc != APD_OK) return rc;
-    APD_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->blocking_wait) {
+      if (!h->done_ev) APD_CUDA(h, cudaEventCreateWithFlags(&h->done_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+      APD_CUDA(h, cudaEventRecord(h->done_ev, h->stream));
+      APD_CUDA(h, cudaEventSynchronize(h->done_ev));
+    } else {
+      APD_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
     const LmResult* r = reinterpret_cast<const LmResult*>(h->h_lm.p);
     if (cfg.want_fitness) {
       h->fit_valid = true;
@@ -904,6 +916,7 @@ int apd_create(int device, apd_handle** out) {
     const int v = std::atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8) h->lm_cluster = v;
   }
+  if (const char* e = std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = std::atoi(e) != 0;
   if (const char* e = std::getenv("APD_KNN_MODE")) h->knn_mode = std::strcmp(e, "warp") == 0 ? 1 : (std::strcmp(e, "thread") == 0 ? 2 : 0);
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   for (int i = 0; i < 36; i++) h->final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity()
@@ -918,11 +931,13 @@ int apd_destroy(apd_handle* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  if (h->done_ev) cudaEventDestroy(h->done_ev);
   h->src.release(); h->tgt.release();
   h->corr.release(); h->sqd.release(); h->mahaA.release(); h->mahaB.release();
   h->work.release(); h->scratch.release(); h->partials.release(); h->small.release();
   h->h_small.release();
   h->lm_result.release();
+  h->nbuf.release();
   h->h_lm.release();
   cudaStreamDestroy(h->stream);
   delete h;
@@ -995,12 +1010,11 @@ int apd_get_neighbors(apd_handle* h, int32_t which, int32_t* out, int32_t n, int
   DeviceGuard dg(h->device);
   int rc = ensure_grid(h, c);
   if (rc != APD_OK) return rc;
-  const size_t nb_bytes = align_up((size_t)n * k * sizeof(int32_t), 256);
-  APD_CUDA(h, h->scratch.ensure(nb_bytes + (size_t)n * 6 * sizeof(double)));
+  APD_CUDA(h, h->scratch.ensure((size_t)n * k * sizeof(int32_t)));
   CloudDev v = c.view();
   if (h->knn_use_warp(c.n, k)) {
-    v.cov = reinterpret_cast<double*>(h->scratch.as<char>() + nb_bytes);  // raw covariances go to scratch
-    launch_knn_cov(v, k, h->scratch.as<int32_t>(), h->stream, &h->launches);
+    APD_CUDA(h, h->nbuf.ensure((size_t)c.n * k * sizeof(int32_t)));
+    launch_knn_cov(v, k, h->nbuf.as<int32_t>(), h->scratch.as<int32_t>(), h->stream, &h->launches);
   } else {
     v.cov = nullptr;  // neighbours only
     launch_knn_cov_fused(v, k, h->params.regularization, h->scratch.as<int32_t>(), h->stream, &h->launches);
@@ -1235,6 +1249,8 @@ int apd_batch_create(int device, int32_t n_workers, apd_batch** out) {
       delete b;
       return rc;
     }
+    // more workers than cores: waiting threads must sleep, not spin
+    if (!std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = (unsigned)n_workers > std::thread::hardware_concurrency();
     b->handles.push_back(h);
   }
   for (int s = 0; s < n_workers; s++) b->threads.emplace_back(batch_worker, b, s);

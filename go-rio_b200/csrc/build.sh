@@ -8,6 +8,8 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17
        -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xcompiler -Wall -ccbin /usr/bin/g++
        --expt-relaxed-constexpr)
 if [[ "${APD_PTXAS_V:-0}" == "1" ]]; then FLAGS+=(-Xptxas -v); fi
+if [[ -n "${APD_EXTRA_FLAGS:-}" ]]; then FLAGS+=(${APD_EXTRA_FLAGS}); fi
+OUT="${APD_OUT:-${OUT}}"
 mkdir -p "${HERE}/_obj"
 pids=()
 for f in grid knn_cov corr linearize lm apdgicp; do

@@ -41,11 +41,13 @@ void launch_bounds(const float4* pts, int n, float* d_out6, cudaStream_t s, int6
 void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int64_t* launches);
 
 // ---- knn_cov.cu --------------------------------------------------------------
-// exact kNN (k <= 32, ties by (d2, index)) + covariance of the k neighbours
-// (reference fast_apdgicp_impl.hpp:361-372), one warp per point; then the
-// regularisation (:374-405) and the geometric weight (:266-269), one thread per
-// point. neighbors: optional int32[n*k] in ORIGINAL point order / original ids.
-void launch_knn_cov(const CloudDev& c, int k, int32_t* neighbors, cudaStream_t s, int64_t* launches);
+// Exact kNN (ties by (d2, index)), in two steps: the search kernels write the neighbour lists d_nb[w*k + j]
+// (original ids, ascending) of the sorted points, then launch_cov_regularize computes the covariance of the k
+// neighbours (reference fast_apdgicp_impl.hpp:361-372), the regularisation (:374-405) and the geometric weight
+// (:266-269), one thread per point. neighbors: optional int32[n*k] in ORIGINAL point order (parity hook).
+// warp-per-point search (k <= 32):
+void launch_knn_cov(const CloudDev& c, int k, int32_t* d_nb, int32_t* neighbors, cudaStream_t s, int64_t* launches);
+void launch_cov_regularize(const CloudDev& c, int k, int regularization, const int32_t* d_nb, cudaStream_t s, int64_t* launches);
 // thread-per-point variant with the regularisation and geometric weight fused in (k <= 128);
 // c.cov == nullptr: neighbours only.
 void launch_knn_cov_fused(const CloudDev& c, int k, int regularization, int32_t* neighbors, cudaStream_t s, int64_t* launches);

@@ -120,19 +120,34 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ spts, f
   }
 }
 
-__global__ void __launch_bounds__(kWarpKnnThreads) knn_cov_kernel(const float4* __restrict__ spts, const float4* __restrict__ pts,
+// The k neighbours of sorted point w (one (d2, index) key per lane, ascending) -> nb[w*k + j] (original point ids,
+// read by cov_regularize_kernel) and, for the parity hook, neighbors[qi*k + j] at the point's ORIGINAL index qi.
+__device__ __forceinline__ void emit_point(unsigned long long mykey, int lane, int k, int w, int qi, int32_t* __restrict__ nb,
+                                           int32_t* __restrict__ neighbors) {
+  if (lane < k) {
+    const int nidx = (int)(unsigned)(mykey & 0xffffffffull);
+    nb[(size_t)w * k + lane] = nidx;
+    if (neighbors) neighbors[(size_t)qi * k + lane] = nidx;
+  }
+}
+
+__global__ void __launch_bounds__(kWarpKnnThreads) knn_cov_kernel(const float4* __restrict__ spts,
                                                            const uint32_t* __restrict__ cell_start, GridDesc g, int n, int k,
-                                                           double* __restrict__ cov, int32_t* __restrict__ neighbors) {
-  const int w = (blockIdx.x * kWarpKnnThreads + threadIdx.x) >> 5;
+                                                           int32_t* __restrict__ nb, int32_t* __restrict__ neighbors,
+                                                           const int* __restrict__ list, const int* __restrict__ list_n) {
+  // list == nullptr: warp i serves sorted point i (+ stride); else: the sorted positions in list[0 .. *list_n)
   const int lane = threadIdx.x & 31;
-  if (w >= n) return;
+  const int count = list ? min(*list_n, n) : n;
+  const int nwarps = (int)((gridDim.x * kWarpKnnThreads) >> 5);
+  __shared__ unsigned long long kbuf[kWarpKnnThreads / 32][32];
+  for (int li = (blockIdx.x * kWarpKnnThreads + threadIdx.x) >> 5; li < count; li += nwarps) {
+  const int w = list ? list[li] : li;
   const float4 q = spts[w];
   const int qi = __float_as_int(q.w);
   const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
   const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
   const int cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz);
 
-  __shared__ unsigned long long kbuf[kWarpKnnThreads / 32][32];
   KBest st;
   st.list = kInfKey;
   st.kth = kInfKey;
@@ -216,42 +231,9 @@ __global__ void __launch_bounds__(kWarpKnnThreads) knn_cov_kernel(const float4* 
   }
   const unsigned long long mykey = st.list;
 
-  // covariance of the k neighbours (reference :366-372): fp64, centred, / k
-  const int nidx = (lane < k) ? (int)(unsigned)(mykey & 0xffffffffull) : 0;
-  if (neighbors && lane < k) neighbors[(size_t)qi * k + lane] = nidx;
-  // Serial, in-neighbour-order sums with one rounding per operation — the CPU path's order, so the raw covariance
-  // is bit-identical to the oracle's — but only the ADDITIONS are serial: lane j rounds its own centred coordinates
-  // and their six products in parallel, then lanes 0-5 each add one column of k products.
-  __shared__ double kcoord[kWarpKnnThreads / 32][6][32];
-  double (*kc)[32] = kcoord[threadIdx.x >> 5];
-  double px = 0.0, py = 0.0, pz = 0.0;
-  if (lane < k) {
-    const float4 p = pts[nidx];
-    px = (double)p.x; py = (double)p.y; pz = (double)p.z;
-    kc[0][lane] = px;
-    kc[1][lane] = py;
-    kc[2][lane] = pz;
-  }
+  emit_point(mykey, lane, k, w, qi, nb, neighbors);
   __syncwarp();
-  double mean = 0.0;
-  if (lane < 3) {
-    for (int j = 0; j < k; j++) mean = __dadd_rn(mean, kc[lane][j]);
-    mean /= (double)k;
-  }
-  const double mx = __shfl_sync(kFull, mean, 0), my = __shfl_sync(kFull, mean, 1), mz = __shfl_sync(kFull, mean, 2);
-  __syncwarp();
-  if (lane < k) {
-    const double dx = __dsub_rn(px, mx), dy = __dsub_rn(py, my), dz = __dsub_rn(pz, mz);
-    kc[0][lane] = __dmul_rn(dx, dx); kc[1][lane] = __dmul_rn(dx, dy); kc[2][lane] = __dmul_rn(dx, dz);
-    kc[3][lane] = __dmul_rn(dy, dy); kc[4][lane] = __dmul_rn(dy, dz); kc[5][lane] = __dmul_rn(dz, dz);
-  }
-  __syncwarp();
-  if (cov && lane < 6) {
-    double acc = 0.0;
-    for (int j = 0; j < k; j++) acc = __dadd_rn(acc, kc[lane][j]);
-    cov[(size_t)w * 6 + lane] = acc / (double)k;
-  }
-  __syncwarp();
+  }  // list / stride loop
 }
 
 __device__ __forceinline__ double geo_weight_of(const Sym3& C) {
@@ -308,6 +290,47 @@ __global__ void __launch_bounds__(kThreads) regularize_kernel(double* __restrict
   const double gw = geo_weight_of(out);
   geo[i] = (float)gw;
   geo64[i] = gw;
+}
+
+// Covariance of the k neighbours of every point (reference :366-372: fp64, centred, divided by k; sums in neighbour
+// order with one rounding per operation — the CPU path's operation order, so the raw covariance is bit-identical to
+// the oracle's) + regularisation (:374-405) + geometric weight (:266-269), one thread per point of the sorted cloud.
+// nb[w*k + j]: original ids of the neighbours of sorted point w, ascending by (d2, index).
+__global__ void __launch_bounds__(kThreads) cov_regularize_kernel(const float4* __restrict__ pts, const int32_t* __restrict__ nb, int n, int k,
+                                                                  int reg, double* __restrict__ cov, float* __restrict__ geo,
+                                                                  double* __restrict__ geo64) {
+  const int w = blockIdx.x * kThreads + threadIdx.x;
+  if (w >= n) return;
+  const int32_t* my = nb + (size_t)w * k;
+  double mx = 0.0, my_ = 0.0, mz = 0.0;
+  for (int j = 0; j < k; j++) {
+    const float4 p = __ldg(&pts[my[j]]);
+    mx = __dadd_rn(mx, (double)p.x);
+    my_ = __dadd_rn(my_, (double)p.y);
+    mz = __dadd_rn(mz, (double)p.z);
+  }
+  mx /= (double)k; my_ /= (double)k; mz /= (double)k;
+  Sym3 C;
+#pragma unroll
+  for (int e = 0; e < 6; e++) C.v[e] = 0.0;
+  for (int j = 0; j < k; j++) {
+    const float4 p = __ldg(&pts[my[j]]);
+    const double dx = __dsub_rn((double)p.x, mx), dy = __dsub_rn((double)p.y, my_), dz = __dsub_rn((double)p.z, mz);
+    C.v[0] = __dadd_rn(C.v[0], __dmul_rn(dx, dx));
+    C.v[1] = __dadd_rn(C.v[1], __dmul_rn(dx, dy));
+    C.v[2] = __dadd_rn(C.v[2], __dmul_rn(dx, dz));
+    C.v[3] = __dadd_rn(C.v[3], __dmul_rn(dy, dy));
+    C.v[4] = __dadd_rn(C.v[4], __dmul_rn(dy, dz));
+    C.v[5] = __dadd_rn(C.v[5], __dmul_rn(dz, dz));
+  }
+#pragma unroll
+  for (int e = 0; e < 6; e++) C.v[e] /= (double)k;
+  const Sym3 out = regularize_sym3(C, reg);
+#pragma unroll
+  for (int e = 0; e < 6; e++) cov[(size_t)w * 6 + e] = out.v[e];
+  const double gw = geo_weight_of(out);
+  geo[w] = (float)gw;
+  geo64[w] = gw;
 }
 
 // ---------------------------------------------------------------------------
@@ -519,11 +542,16 @@ void launch_knn_cov_fused(const CloudDev& c, int k, int regularization, int32_t*
                                                                         c.geo64, neighbors);
   (*launches)++;
 }
-void launch_knn_cov(const CloudDev& c, int k, int32_t* neighbors, cudaStream_t s, int64_t* launches) {
+void launch_knn_cov(const CloudDev& c, int k, int32_t* d_nb, int32_t* neighbors, cudaStream_t s, int64_t* launches) {
   if (c.n <= 0) return;
   const long long threads = (long long)c.n * 32;
   const int blocks = (int)((threads + kWarpKnnThreads - 1) / kWarpKnnThreads);
-  knn_cov_kernel<<<blocks, kWarpKnnThreads, 0, s>>>(c.spts, c.pts, c.cell_start, c.g, c.n, k, c.cov, neighbors);
+  knn_cov_kernel<<<blocks, kWarpKnnThreads, 0, s>>>(c.spts, c.cell_start, c.g, c.n, k, d_nb, neighbors, nullptr, nullptr);
+  (*launches)++;
+}
+void launch_cov_regularize(const CloudDev& c, int k, int regularization, const int32_t* d_nb, cudaStream_t s, int64_t* launches) {
+  if (c.n <= 0) return;
+  cov_regularize_kernel<<<(c.n + kThreads - 1) / kThreads, kThreads, 0, s>>>(c.pts, d_nb, c.n, k, regularization, c.cov, c.geo, c.geo64);
   (*launches)++;
 }
 void launch_regularize(const CloudDev& c, int regularization, cudaStream_t s, int64_t* launches) {

@@ -60,19 +60,33 @@ def test_knn_indices_bit_exact_submap(gorio, c2):
     assert np.array_equal(g.get_neighbors(1), o.get_neighbors(1))
 
 
-def test_knn_warp_and_thread_kernels_match(gorio, c2_small, monkeypatch):
-    """APD_KNN_MODE selects the warp-per-point or the thread-per-point kNN kernel (auto: by cloud
-    size): same neighbours, same covariances"""
+def test_knn_kernels_match(gorio, c2_small, monkeypatch):
+    """APD_KNN_MODE selects the warp-per-point or the thread-per-point kNN kernel (auto: by cloud size and k):
+    same neighbours, same covariances"""
     src, tgt, _ = c2_small
-    monkeypatch.setenv("APD_KNN_MODE", "thread")
-    g = gorio.FastAPDGICP(0)
-    monkeypatch.setenv("APD_KNN_MODE", "warp")
-    gw = gorio.FastAPDGICP(0)
+    hs = []
+    for mode in ("thread", "warp"):
+        monkeypatch.setenv("APD_KNN_MODE", mode)
+        hs.append(gorio.FastAPDGICP(0))
     monkeypatch.delenv("APD_KNN_MODE")
-    for r in (g, gw):
+    for r in hs:
         r.set_input_target(tgt); r.set_input_source(src)
-    assert np.array_equal(g.get_neighbors(1), gw.get_neighbors(1))
-    assert np.abs(g.get_target_covariances() - gw.get_target_covariances()).max() < 1e-12
+    for r in hs[1:]:
+        for which in (0, 1):
+            assert np.array_equal(hs[0].get_neighbors(which), r.get_neighbors(which))
+        assert np.array_equal(hs[0].get_target_covariances(), r.get_target_covariances())
+
+
+@pytest.mark.parametrize("cpp", ["0.5", "2", "16"])
+def test_knn_any_cell_size(gorio, c2_small, monkeypatch, cpp):
+    """the grid resolution only changes how many shells a search walks, never the result"""
+    src, tgt, _ = c2_small
+    monkeypatch.setenv("APD_CELLS_PER_POINT", cpp)
+    g, o = make(gorio, src, tgt, regularization=0)
+    o.get_target_covariances(); o.get_source_covariances()
+    for which in (0, 1):
+        assert np.array_equal(g.get_neighbors(which), o.get_neighbors(which))
+    assert np.array_equal(g.get_target_covariances(), o.get_target_covariances())
 
 
 @pytest.mark.parametrize("mode", ["thread", "warp"])
