@@ -438,10 +438,11 @@ def main():
             if s.ctypes.data not in seen:
                 seen.add(s.ctypes.data)
                 uniq.append((s, t))
-        cpu_registrations(lib, search, uniq[:1], 1)
-        t_cpu, n_cpu = cpu_registrations(lib, search, uniq, 3)
+        t1, n1 = cpu_registrations(lib, search, uniq[:1], 1)
+        reps = max(3, min(200, int(round(12.0 / max(t1 * len(uniq), 1e-3)))))  # ~12 s of CPU work
+        t_cpu, n_cpu = cpu_registrations(lib, search, uniq, reps)
         line["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": UNIT, "cores": host_cores(), "kind": kind,
-                                "sample": f"{len(uniq)} of the step's pairs x 3 repetitions ({t_cpu:.1f} s wall); {what}"}
+                                "sample": f"{len(uniq)} of the step's pairs x {reps} repetitions ({t_cpu:.1f} s wall); {what}"}
 
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -4,6 +4,8 @@
 // matrix). Replaces FastAPDGICP::update_correspondences (reference
 // fast_apdgicp_impl.hpp:160-220). Also the fitness pass (pcl getFitnessScore)
 // and the export hooks.
+#include <cstdlib>
+
 #include "point_math.cuh"
 
 namespace apd {
@@ -154,13 +156,18 @@ void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, con
   update_corr_kernel<FP64, GG><<<(unsigned)(((size_t)src.n * GG + kThreads - 1) / kThreads), kThreads, 0, s>>>(                           \
       src.spts, src.label, src.cov, src.n, tgt.spts, tgt.label, tgt.cov, tgt.cell_start, tgt.g, T, np, out.corr, out.sqd, out.mahaA, \
       out.mahaB)
-  // small source clouds are latency-bound: 8 lanes share a query; large ones are throughput-bound: one lane per query
-  const bool wide = src.n < 65536;
+  // small source clouds are latency-bound: 8 lanes share a query; large ones are throughput-bound: one lane per query.
+  // APD_CORR_MODE = wide | lane forces one variant (tests, profiling); both give identical results.
+  // (Tried and dropped, 20 M points on B200: staging the union box of a warp's 32 query cubes in shared memory with bulk
+  // copies and scanning it densely — 5.7 ms against 4.1 ms: in x-fastest cell order a warp's queries form a strip ~200 cells
+  // long, so the box holds ~100x the 4-5 candidates a query needs.)
+  const char* e = getenv("APD_CORR_MODE");
+  const char mode = e ? e[0] : (src.n < 65536 ? 'w' : 'l');
   if (out.maha_fp64) {
-    if (wide) APD_CORR(true, 8);
+    if (mode == 'w') APD_CORR(true, 8);
     else APD_CORR(true, 1);
   } else {
-    if (wide) APD_CORR(false, 8);
+    if (mode == 'w') APD_CORR(false, 8);
     else APD_CORR(false, 1);
   }
 #undef APD_CORR

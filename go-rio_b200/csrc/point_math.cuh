@@ -30,41 +30,31 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ spts, int 
 // min-reduced with shuffles after every shell, so the critical path of a query is
 // ~1/G of the single-thread scan (small source clouds are latency-bound).
 // All G lanes return the same result.
+// min-reduce (best, best_pos) over the G lanes that share a query
 template <int G>
-__device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
-                                          float qx, float qy, float qz, double limit_sq, unsigned long long& best, int& best_pos) {
-  const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
-  const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
-  const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
-  const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
-  best = kInfKey;
-  best_pos = -1;
-  // groups of one warp leave the shell loop at different times: shuffle within the group's own lanes only
-  const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-  auto group_min = [&]() {
-    if (G > 1) {
+__device__ __forceinline__ void nn_group_min(unsigned long long& best, int& best_pos) {
+  if (G > 1) {
+    // groups of one warp leave the shell loop at different times: shuffle within the group's own lanes only
+    const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
 #pragma unroll
-      for (int o = G >> 1; o > 0; o >>= 1) {
-        const unsigned long long ob = __shfl_xor_sync(gmask, best, o);
-        const int op = __shfl_xor_sync(gmask, best_pos, o);
-        if (ob < best) {
-          best = ob;
-          best_pos = op;
-        }
+    for (int o = G >> 1; o > 0; o >>= 1) {
+      const unsigned long long ob = __shfl_xor_sync(gmask, best, o);
+      const int op = __shfl_xor_sync(gmask, best_pos, o);
+      if (ob < best) {
+        best = ob;
+        best_pos = op;
       }
     }
-  };
-  // ring 0+1: 3x3x3 cube as 9 x-rows
-  {
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-    for (int ri = sub; ri < 9; ri += G) {
-      const int y = cy + (ri % 3) - 1, z = cz + (ri / 3) - 1;
-      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
-      const int row = (z * g.ny + y) * g.nx;
-      scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
-    }
-    group_min();
   }
+}
+
+// Shells r = 2, 3, ... around the query's cell (cx,cy,cz), given the best key over the radius-1 cube: continues until
+// the best distance is provably final or every unscanned point is farther than the limit.
+template <int G>
+__device__ __forceinline__ void nn_shells(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
+                                          float qx, float qy, float qz, int cx, int cy, int cz, double limit_sq, unsigned long long& best,
+                                          int& best_pos) {
+  const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
   const float mg = 0.002f * g.cell;
   // thick shells (r, rr]: one cell at a time near the query, then growing ~1.5x (see knn_cov.cu)
   for (int r = 1;;) {
@@ -96,9 +86,32 @@ __device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const
         if (xr <= x1) scan_range(spts, (int)__ldg(&cell_start[row + xr]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
       }
     }
-    group_min();
+    nn_group_min<G>(best, best_pos);
     r = rr;
   }
+}
+
+template <int G>
+__device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
+                                          float qx, float qy, float qz, double limit_sq, unsigned long long& best, int& best_pos) {
+  const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
+  const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
+  best = kInfKey;
+  best_pos = -1;
+  // ring 0+1: 3x3x3 cube as 9 x-rows
+  {
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    for (int ri = sub; ri < 9; ri += G) {
+      const int y = cy + (ri % 3) - 1, z = cz + (ri / 3) - 1;
+      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      const int row = (z * g.ny + y) * g.nx;
+      scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
+    }
+    nn_group_min<G>(best, best_pos);
+  }
+  nn_shells<G>(spts, cell_start, g, qx, qy, qz, cx, cy, cz, limit_sq, best, best_pos);
 }
 
 __device__ __forceinline__ PoseF pose_to_f32(const PoseD& T) {

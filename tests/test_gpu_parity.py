@@ -205,6 +205,27 @@ def test_linearize_parity_submap(gorio, synth, c2):
         assert abs(eg - eo) / eo < 1e-10 and rel(Hg, Ho) < 1e-10 and rel(bg, bo) < 1e-9
 
 
+@pytest.mark.parametrize("mode", ["lane", "wide"])
+def test_update_correspondences_variants(gorio, synth, c2, monkeypatch, mode):
+    """the two search variants of update_correspondences (8 lanes per query: small sources; one lane per query: large
+    sources) against the oracle: bit-exact correspondences and squared distances, Mahalanobis within 1e-10, at poses
+    near and far from the answer"""
+    src, tgt, Tgt = c2
+    monkeypatch.setenv("APD_CORR_MODE", mode)
+    for thr in (2.0, None):
+        kw = dict(maha_fp64=1, host_loop=1)
+        if thr is not None:
+            kw["max_correspondence_distance"] = thr
+        g, o = make(gorio, src, tgt, **kw)
+        for T in (np.eye(4), Tgt, Tgt @ synth.make_pose([3.0, -2.0, 0.5], [0.02, -0.01, 0.3])):
+            g.update_correspondences(T); o.update_correspondences(T)
+            cg, sg = g.get_correspondences()
+            co, so = o.get_correspondences()
+            assert np.array_equal(cg, co)
+            assert np.array_equal(sg[cg >= 0], so[co >= 0])  # (sq_distances_ of rejected points is write-only scratch, :180)
+            assert rel(g.get_mahalanobis(), o.get_mahalanobis()) < 1e-10
+
+
 def test_cluster_label_weight(gorio, synth, c1):
     """cl_weight = 1/N when source.normal_x == target.normal_x (:271-273)"""
     src, tgt, _ = c1
