@@ -26,7 +26,13 @@ namespace apd {
 
 namespace {
 
-constexpr int kLmThreads = 512;
+#ifndef APD_LM_THREADS
+#define APD_LM_THREADS 512
+#endif
+#ifndef APD_LM_MINB
+#define APD_LM_MINB 1
+#endif
+constexpr int kLmThreads = APD_LM_THREADS;
 constexpr int kLmWarps = kLmThreads / 32;
 constexpr int kLmG = 8;  // lanes per 1-NN query (the search is latency-bound at these sizes)
 
@@ -276,7 +282,7 @@ __device__ __noinline__ void serial_lm_end(LmShared& s, const LmConfig& cfg, boo
 }
 
 template <bool kFp64>
-__global__ void __launch_bounds__(kLmThreads, 1) lm_kernel(LmJob one, const LmJob* __restrict__ jobs, LmConfig cfg) {
+__global__ void __launch_bounds__(kLmThreads, APD_LM_MINB) lm_kernel(LmJob one, const LmJob* __restrict__ jobs, LmConfig cfg) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned C = cluster.num_blocks();
   const unsigned rank = cluster.block_rank();
