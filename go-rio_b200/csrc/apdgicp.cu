@@ -39,6 +39,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load(std::string& err) {
     if (lib) return true;
@@ -55,8 +56,9 @@ struct NcclApi {
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) {
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !AllGather) {
       err = "libnccl is missing required symbols";
       return false;
     }
@@ -65,6 +67,7 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclFloat32 = 7;  // ncclFloat
 constexpr int kNcclSum = 0;      // ncclSum
 
 // -------------------------------------------------------------- buffers ----
@@ -195,7 +198,6 @@ struct apd_handle {
   // sharding
   ncclComm_t comm = nullptr;
   int comm_rank = 0, comm_size = 1;
-  int64_t n_source_total = 0;
   // instrumentation
   int64_t launches = 0;
   bool profiling = false;
@@ -212,6 +214,31 @@ struct apd_handle {
   int knn_thread_min_n = 500000;
   int knn_max_k() const { return knn_mode == 1 ? 32 : 128; }
   bool knn_use_warp(int n, int k) const { return knn_mode == 1 || (knn_mode == 0 && k <= 32 && n < knn_thread_min_n); }
+  // Sharded handle (apd_comm_init): every rank holds both FULL clouds and grids. The cell-sorted points of a cloud are
+  // cut into nranks * kShardSub equal chunks; rank r owns chunks r, r + nranks, r + 2 nranks, ... — interleaved, because
+  // the cost of a 1-NN / kNN query varies across the scene (contiguous halves of one 20 M-point scene differed by 1.5x).
+  // Chunk j of every rank forms one contiguous group, so the covariance all-gather runs in place, group by group.
+  static constexpr int kShardSub = 4;
+  int shard_subs() const { return comm ? kShardSub : 1; }
+  int shard_chunk(int n) const { return comm ? (n + comm_size * kShardSub - 1) / (comm_size * kShardSub) : n; }
+  int sub_begin(int n, int j) const { return comm ? (int)std::min<long long>(n, (long long)(j * comm_size + comm_rank) * shard_chunk(n)) : 0; }
+  int sub_count(int n, int j) const {
+    return comm ? (int)(std::min<long long>(n, (long long)(j * comm_size + comm_rank + 1) * shard_chunk(n)) - sub_begin(n, j)) : n;
+  }
+  size_t sub_local(int n, int j) const { return (size_t)j * shard_chunk(n); }  // offset of chunk j in the rank-local arrays
+  size_t local_n(int n) const { return comm ? (size_t)shard_chunk(n) * kShardSub : (size_t)n; }
+  size_t padded_n(int n) const { return comm ? (size_t)shard_chunk(n) * comm_size * kShardSub : (size_t)n; }
+  // chunk j of the source points this rank linearizes (pointers shifted, n = chunk length); unsharded: the whole cloud
+  CloudDev src_slice(int j) const {
+    CloudDev v = src.view();
+    if (comm) {
+      const int b = sub_begin(src.n, j);
+      v.n = sub_count(src.n, j);
+      v.spts += b; v.label += b; v.cov += (size_t)b * 6; v.geo += b; v.geo64 += b;
+      v.inv_perm = nullptr;  // (indexed by original id: not a per-slice array)
+    }
+    return v;
+  }
 };
 
 namespace {
@@ -411,29 +438,52 @@ int ensure_grid(apd_handle* h, Cloud& c) {
   return APD_OK;
 }
 
+// in-place all-gather of a per-point array whose chunks (see apd_handle::shard_chunk) this rank has just written:
+// group j = chunks [j * nranks, (j + 1) * nranks) is contiguous and holds one chunk of every rank
+int allgather_chunks(apd_handle* h, void* base, int n, size_t elems_per_point, int nccl_type, size_t elem_bytes) {
+  const size_t chunk = (size_t)h->shard_chunk(n) * elems_per_point;
+  for (int j = 0; j < h->shard_subs(); j++) {
+    char* grp = reinterpret_cast<char*>(base) + (size_t)j * h->comm_size * chunk * elem_bytes;
+    ncclResult_t r = g_nccl.AllGather(grp + (size_t)h->comm_rank * chunk * elem_bytes, grp, chunk, nccl_type, h->comm, h->stream);
+    if (r != 0) return fail(h, APD_ERR_COMM, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclAllGather failed");
+  }
+  return APD_OK;
+}
+
 // FastAPDGICP::calculate_covariances (:351-411)
 int ensure_covariances_of(apd_handle* h, Cloud& c) {
   int rc = ensure_grid(h, c);
   if (rc != APD_OK) return rc;
   if (c.cov_valid && c.geo_valid) return APD_OK;
-  APD_CUDA(h, c.cov.ensure((size_t)c.n * 6 * sizeof(double)));
-  APD_CUDA(h, c.geo.ensure((size_t)c.n * sizeof(float)));
-  APD_CUDA(h, c.geo64.ensure((size_t)c.n * sizeof(double)));
+  const size_t np = h->padded_n(c.n);
+  APD_CUDA(h, c.cov.ensure(np * 6 * sizeof(double)));
+  APD_CUDA(h, c.geo.ensure(np * sizeof(float)));
+  APD_CUDA(h, c.geo64.ensure(np * sizeof(double)));
+  // Sharded: this rank searches the full grid for its slice of the points only; the covariance slices are then
+  // all-gathered (the target's are gathered through arbitrary correspondences, and a swap can make either cloud the
+  // target). The geometric weight is only ever read for the rank's own slice of the source, so it stays local.
   if (!c.cov_valid) {
     const int k = h->params.k_correspondences;
     if (k < 1 || k > h->knn_max_k()) return fail(h, APD_ERR_UNSUPPORTED, "k_correspondences out of range (1..128; 1..32 in warp mode)");
     if (c.n < k) return fail(h, APD_ERR_TOO_FEW, "cloud has fewer points than k_correspondences");
     ProfScope ps(h, APD_K_KNN_COV);
-    if (h->knn_use_warp(c.n, k)) {
-      APD_CUDA(h, h->nbuf.ensure((size_t)c.n * k * sizeof(int32_t)));
-      launch_knn_cov(c.view(), k, h->nbuf.as<int32_t>(), nullptr, h->stream, &h->launches);
-      launch_cov_regularize(c.view(), k, h->params.regularization, h->nbuf.as<int32_t>(), h->stream, &h->launches);
-    } else {
-      launch_knn_cov_fused(c.view(), k, h->params.regularization, nullptr, h->stream, &h->launches);
+    if (h->knn_use_warp(c.n, k)) APD_CUDA(h, h->nbuf.ensure((size_t)c.n * k * sizeof(int32_t)));
+    for (int j = 0; j < h->shard_subs(); j++) {
+      const int w0 = h->sub_begin(c.n, j), wn = h->sub_count(c.n, j);
+      if (h->knn_use_warp(c.n, k)) {
+        launch_knn_cov(c.view(), k, h->nbuf.as<int32_t>(), nullptr, h->stream, &h->launches, w0, wn);
+        launch_cov_regularize(c.view(), k, h->params.regularization, h->nbuf.as<int32_t>(), h->stream, &h->launches, w0, wn);
+      } else {
+        launch_knn_cov_fused(c.view(), k, h->params.regularization, nullptr, h->stream, &h->launches, w0, wn);
+      }
+    }
+    if (h->comm) {
+      rc = allgather_chunks(h, c.cov.p, c.n, 6, kNcclFloat64, sizeof(double));
+      if (rc != APD_OK) return rc;
     }
     c.cov_valid = true;
     c.geo_valid = true;
-  } else if (!c.geo_valid) {
+  } else if (!c.geo_valid) {  // after set*Covariances: every rank holds all covariances, the weight is a local map
     ProfScope ps(h, APD_K_KNN_COV);
     launch_geo_weight(c.view(), h->stream, &h->launches);
     c.geo_valid = true;
@@ -460,13 +510,16 @@ int ensure_small(apd_handle* h) {
   return APD_OK;
 }
 
-CorrOut corr_view(apd_handle* h) {
+// per-linearisation arrays of chunk j of this rank's source points (unsharded: j = 0, the whole cloud)
+CorrOut corr_view(apd_handle* h, int j = 0) {
+  const size_t off = h->comm ? h->sub_local(h->src.n, j) : 0;
   CorrOut c;
-  c.corr = h->corr.as<int>();
-  c.sqd = h->sqd.as<float>();
-  c.mahaA = h->mahaA.p;
-  c.mahaB = h->mahaB.p;
+  c.corr = h->corr.as<int>() + off;
+  c.sqd = h->sqd.as<float>() + off;
   c.maha_fp64 = h->corr_fp64;
+  // fp64 storage keeps two planes of `chunk length` double2 in mahaB: every chunk owns [2 off, 2 off + 2 len)
+  c.mahaA = h->corr_fp64 ? (void*)(h->mahaA.as<double2>() + off) : (void*)(h->mahaA.as<float4>() + off);
+  c.mahaB = h->corr_fp64 ? (void*)(h->mahaB.as<double2>() + 2 * off) : (void*)(h->mahaB.as<float2>() + off);
   return c;
 }
 
@@ -477,7 +530,8 @@ int do_update_correspondences(apd_handle* h, const hm::Pose& T) {
   const NoiseParams np = noise_params(h->params);
   {
     ProfScope ps(h, APD_K_CORR);
-    launch_update_correspondences(h->src.view(), h->tgt.view(), to_pose_d(T), np, corr_view(h), h->stream, &h->launches);
+    for (int j = 0; j < h->shard_subs(); j++)
+      launch_update_correspondences(h->src_slice(j), h->tgt.view(), to_pose_d(T), np, corr_view(h, j), h->stream, &h->launches);
   }
   APD_CUDA(h, cudaGetLastError());
   h->corr_n = h->src.n;
@@ -494,10 +548,12 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
   w.partials = h->partials.as<double>();
   w.ticket = reinterpret_cast<unsigned int*>(d_out + 40);
   w.max_blocks = h->max_reduce_blocks / 2;  // persistent CTAs: 2 resident per SM
-  const double n_total = h->comm ? (double)h->n_source_total : (double)h->src.n;
+  const double n_total = (double)h->src.n;  // correspondences_.size() (:273): the whole source cloud, sharded or not
   {
     ProfScope ps(h, want_hb ? APD_K_LINEARIZE : APD_K_ERROR);
-    launch_linearize(h->src.view(), h->tgt.view(), to_pose_d(T), corr_view(h), n_total, want_hb, w, d_out, h->stream, &h->launches);
+    for (int j = 0; j < h->shard_subs(); j++)  // chunks after the first add onto the 28 (1) sums of the previous ones
+      launch_linearize(h->src_slice(j), h->tgt.view(), to_pose_d(T), corr_view(h, j), n_total, want_hb, j > 0, w, d_out, h->stream,
+                       &h->launches);
   }
   APD_CUDA(h, cudaGetLastError());
   if (h->comm) {
@@ -651,9 +707,9 @@ int set_covs(apd_handle* h, Cloud& c, const double* covs, int32_t n) {
   DeviceGuard dg(h->device);
   int rc = ensure_grid(h, c);
   if (rc != APD_OK) return rc;
-  APD_CUDA(h, c.cov.ensure((size_t)n * 6 * sizeof(double)));
-  APD_CUDA(h, c.geo.ensure((size_t)n * sizeof(float)));
-  APD_CUDA(h, c.geo64.ensure((size_t)n * sizeof(double)));
+  APD_CUDA(h, c.cov.ensure(h->padded_n(n) * 6 * sizeof(double)));
+  APD_CUDA(h, c.geo.ensure(h->padded_n(n) * sizeof(float)));
+  APD_CUDA(h, c.geo64.ensure(h->padded_n(n) * sizeof(double)));
   APD_CUDA(h, h->scratch.ensure((size_t)n * 16 * sizeof(double)));
   APD_CUDA(h, cudaMemcpyAsync(h->scratch.p, covs, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   launch_cov_import(c.view(), h->scratch.as<double>(), h->stream, &h->launches);
@@ -707,7 +763,7 @@ NoiseParams noise_params(const apd_params& p) {
 }
 
 int ensure_corr_buffers(apd_handle* h) {
-  const size_t n = (size_t)h->src.n;
+  const size_t n = std::max<size_t>(1, h->local_n(h->src.n));
   const int fp64 = h->params.maha_fp64 ? 1 : 0;
   APD_CUDA(h, h->corr.ensure(n * sizeof(int)));
   APD_CUDA(h, h->sqd.ensure(n * sizeof(float)));
@@ -1090,7 +1146,12 @@ int apd_get_correspondences(apd_handle* h, int32_t* idx, float* sq_dist, int32_t
   APD_CUDA(h, h->scratch.ensure(2 * ib));
   int32_t* d_idx = h->scratch.as<int32_t>();
   float* d_sq = reinterpret_cast<float*>(h->scratch.as<char>() + ib);
-  launch_corr_export(h->src.view(), h->tgt.view(), corr_view(h), d_idx, d_sq, nullptr, h->stream, &h->launches);
+  if (h->comm) {  // a sharded handle reports its own slice of the source; the other points read -1 / 0
+    APD_CUDA(h, cudaMemsetAsync(d_idx, 0xff, (size_t)n * sizeof(int32_t), h->stream));
+    APD_CUDA(h, cudaMemsetAsync(d_sq, 0, (size_t)n * sizeof(float), h->stream));
+  }
+  for (int j = 0; j < h->shard_subs(); j++)
+    launch_corr_export(h->src_slice(j), h->tgt.view(), corr_view(h, j), d_idx, d_sq, nullptr, h->stream, &h->launches);
   if (idx) APD_CUDA(h, cudaMemcpyAsync(idx, d_idx, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   if (sq_dist) APD_CUDA(h, cudaMemcpyAsync(sq_dist, d_sq, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   APD_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1102,7 +1163,9 @@ int apd_get_mahalanobis(apd_handle* h, double* maha, int32_t n) {
   if (h->corr_n != n || n != h->src.n) return fail(h, APD_ERR_INVALID, "no correspondences for this source cloud");
   DeviceGuard dg(h->device);
   APD_CUDA(h, h->scratch.ensure((size_t)n * 16 * sizeof(double)));
-  launch_corr_export(h->src.view(), h->tgt.view(), corr_view(h), nullptr, nullptr, h->scratch.as<double>(), h->stream, &h->launches);
+  if (h->comm) APD_CUDA(h, cudaMemsetAsync(h->scratch.p, 0, (size_t)n * 16 * sizeof(double), h->stream));
+  for (int j = 0; j < h->shard_subs(); j++)
+    launch_corr_export(h->src_slice(j), h->tgt.view(), corr_view(h, j), nullptr, nullptr, h->scratch.as<double>(), h->stream, &h->launches);
   APD_CUDA(h, cudaMemcpyAsync(maha, h->scratch.p, (size_t)n * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   APD_CUDA(h, cudaStreamSynchronize(h->stream));
   return APD_OK;
@@ -1354,7 +1417,15 @@ int apd_comm_init(apd_handle* h, const void* id128, int32_t rank, int32_t nranks
   if (r != 0) return fail(h, APD_ERR_COMM, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclCommInitRank failed");
   h->comm_rank = rank;
   h->comm_size = nranks;
-  h->n_source_total = n_source_total;
+  (void)n_source_total;  // (ABI v1 argument; the handle holds the full source, so the total is src.n)
+  {  // NCCL connects lazily on the first collective (~0.2 s): pay for it here, not inside the first registration
+    int rc = ensure_small(h);
+    if (rc != APD_OK) return rc;
+    double* d = h->small.as<double>() + 56;
+    if (g_nccl.AllReduce(d, d, 1, kNcclFloat64, kNcclSum, h->comm, h->stream) != 0) return fail(h, APD_ERR_COMM, "ncclAllReduce (warm-up) failed");
+    APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  h->corr_n = -1;        // correspondences of the unsharded layout are no longer addressable
   return APD_OK;
 }
 int apd_comm_destroy(apd_handle* h) {
@@ -1364,6 +1435,7 @@ int apd_comm_destroy(apd_handle* h) {
     cudaStreamSynchronize(h->stream);
     g_nccl.CommDestroy(h->comm);
     h->comm = nullptr;
+    h->corr_n = -1;
   }
   h->comm_size = 1;
   h->comm_rank = 0;

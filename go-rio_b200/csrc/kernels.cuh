@@ -46,11 +46,14 @@ void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int
 // neighbours (reference fast_apdgicp_impl.hpp:361-372), the regularisation (:374-405) and the geometric weight
 // (:266-269), one thread per point. neighbors: optional int32[n*k] in ORIGINAL point order (parity hook).
 // warp-per-point search (k <= 32):
-void launch_knn_cov(const CloudDev& c, int k, int32_t* d_nb, int32_t* neighbors, cudaStream_t s, int64_t* launches);
-void launch_cov_regularize(const CloudDev& c, int k, int regularization, const int32_t* d_nb, cudaStream_t s, int64_t* launches);
+// [w0, w0 + wn): the sorted positions to serve (wn < 0: to the end) — a rank of a sharded handle computes its slice only
+void launch_knn_cov(const CloudDev& c, int k, int32_t* d_nb, int32_t* neighbors, cudaStream_t s, int64_t* launches, int w0 = 0, int wn = -1);
+void launch_cov_regularize(const CloudDev& c, int k, int regularization, const int32_t* d_nb, cudaStream_t s, int64_t* launches, int w0 = 0,
+                           int wn = -1);
 // thread-per-point variant with the regularisation and geometric weight fused in (k <= 128);
 // c.cov == nullptr: neighbours only.
-void launch_knn_cov_fused(const CloudDev& c, int k, int regularization, int32_t* neighbors, cudaStream_t s, int64_t* launches);
+void launch_knn_cov_fused(const CloudDev& c, int k, int regularization, int32_t* neighbors, cudaStream_t s, int64_t* launches, int w0 = 0,
+                          int wn = -1);
 void launch_regularize(const CloudDev& c, int regularization, cudaStream_t s, int64_t* launches);
 // geo weight only (after set*Covariances)
 void launch_geo_weight(const CloudDev& c, cudaStream_t s, int64_t* launches);
@@ -95,9 +98,10 @@ struct ReduceWork {
 };
 // reference linearize (:247-304) / compute_error (:313-343) given the stored
 // correspondences and Mahalanobis matrices. out28 = 21 upper-triangular H
-// entries (row-major, r<=c), 6 b, 1 err. cl_weight = 1 / n_total.
+// entries (row-major, r<=c), 6 b, 1 err. cl_weight = 1 / n_total. accumulate: add to out28 instead of overwriting it
+// (the chunks of a sharded source are launched one after the other).
 void launch_linearize(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const CorrOut& c, double n_total,
-                      bool want_hb, const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches);
+                      bool want_hb, bool accumulate, const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches);
 
 // ---- lm.cu ---------------------------------------------------------------------
 // The device-resident optimizer loop (LsqRegistration::computeTransformation,

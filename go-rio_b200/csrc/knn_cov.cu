@@ -134,14 +134,14 @@ __device__ __forceinline__ void emit_point(unsigned long long mykey, int lane, i
 __global__ void __launch_bounds__(kWarpKnnThreads) knn_cov_kernel(const float4* __restrict__ spts,
                                                            const uint32_t* __restrict__ cell_start, GridDesc g, int n, int k,
                                                            int32_t* __restrict__ nb, int32_t* __restrict__ neighbors,
-                                                           const int* __restrict__ list, const int* __restrict__ list_n) {
-  // list == nullptr: warp i serves sorted point i (+ stride); else: the sorted positions in list[0 .. *list_n)
+                                                           const int* __restrict__ list, const int* __restrict__ list_n, int w0, int wn) {
+  // list == nullptr: warp i serves sorted point w0 + i (+ stride), i < wn; else: the sorted positions in list[0 .. *list_n)
   const int lane = threadIdx.x & 31;
-  const int count = list ? min(*list_n, n) : n;
+  const int count = list ? min(*list_n, n) : wn;
   const int nwarps = (int)((gridDim.x * kWarpKnnThreads) >> 5);
   __shared__ unsigned long long kbuf[kWarpKnnThreads / 32][32];
   for (int li = (blockIdx.x * kWarpKnnThreads + threadIdx.x) >> 5; li < count; li += nwarps) {
-  const int w = list ? list[li] : li;
+  const int w = list ? list[li] : w0 + li;
   const float4 q = spts[w];
   const int qi = __float_as_int(q.w);
   const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
@@ -298,9 +298,9 @@ __global__ void __launch_bounds__(kThreads) regularize_kernel(double* __restrict
 // nb[w*k + j]: original ids of the neighbours of sorted point w, ascending by (d2, index).
 __global__ void __launch_bounds__(kThreads) cov_regularize_kernel(const float4* __restrict__ pts, const int32_t* __restrict__ nb, int n, int k,
                                                                   int reg, double* __restrict__ cov, float* __restrict__ geo,
-                                                                  double* __restrict__ geo64) {
-  const int w = blockIdx.x * kThreads + threadIdx.x;
-  if (w >= n) return;
+                                                                  double* __restrict__ geo64, int w0, int wn) {
+  if (blockIdx.x * kThreads + threadIdx.x >= wn) return;
+  const int w = w0 + blockIdx.x * kThreads + threadIdx.x;
   const int32_t* my = nb + (size_t)w * k;
   double mx = 0.0, my_ = 0.0, mz = 0.0;
   for (int j = 0; j < k; j++) {
@@ -382,13 +382,13 @@ __device__ __forceinline__ void knn_scan_range(const float4* __restrict__ spts, 
 __global__ void __launch_bounds__(kKnnT) knn_cov_thread_kernel(const float4* __restrict__ spts, const float4* __restrict__ pts,
                                                                const uint32_t* __restrict__ cell_start, GridDesc g, int n, int k, int reg,
                                                                double* __restrict__ cov, float* __restrict__ geo, double* __restrict__ geo64,
-                                                               int32_t* __restrict__ neighbors) {
+                                                               int32_t* __restrict__ neighbors, int w0, int wn) {
   extern __shared__ uint32_t heap_smem[];
   uint32_t* hd = heap_smem;               // [k][128] d2 bits
   uint32_t* hi = heap_smem + k * kKnnT;   // [k][128] original index
   const int tid = threadIdx.x;
-  const int w = blockIdx.x * kKnnT + tid;
-  if (w >= n) return;
+  if (blockIdx.x * kKnnT + tid >= wn) return;
+  const int w = w0 + blockIdx.x * kKnnT + tid;
   for (int j = 0; j < k; j++) heap_set(hd, hi, j, tid, kInfKey);
   unsigned long long top = kInfKey;
 
@@ -534,24 +534,28 @@ __global__ void __launch_bounds__(kThreads) cov_import_kernel(const double* __re
 
 }  // namespace
 
-void launch_knn_cov_fused(const CloudDev& c, int k, int regularization, int32_t* neighbors, cudaStream_t s, int64_t* launches) {
-  if (c.n <= 0) return;
+void launch_knn_cov_fused(const CloudDev& c, int k, int regularization, int32_t* neighbors, cudaStream_t s, int64_t* launches, int w0,
+                          int wn) {
+  if (wn < 0) wn = c.n - w0;
+  if (c.n <= 0 || wn <= 0) return;
   const size_t smem = (size_t)2 * k * kKnnT * sizeof(uint32_t);
   if (smem > 48 * 1024) cudaFuncSetAttribute(knn_cov_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  knn_cov_thread_kernel<<<(c.n + kKnnT - 1) / kKnnT, kKnnT, smem, s>>>(c.spts, c.pts, c.cell_start, c.g, c.n, k, regularization, c.cov, c.geo,
-                                                                        c.geo64, neighbors);
+  knn_cov_thread_kernel<<<(wn + kKnnT - 1) / kKnnT, kKnnT, smem, s>>>(c.spts, c.pts, c.cell_start, c.g, c.n, k, regularization, c.cov, c.geo,
+                                                                       c.geo64, neighbors, w0, wn);
   (*launches)++;
 }
-void launch_knn_cov(const CloudDev& c, int k, int32_t* d_nb, int32_t* neighbors, cudaStream_t s, int64_t* launches) {
-  if (c.n <= 0) return;
-  const long long threads = (long long)c.n * 32;
+void launch_knn_cov(const CloudDev& c, int k, int32_t* d_nb, int32_t* neighbors, cudaStream_t s, int64_t* launches, int w0, int wn) {
+  if (wn < 0) wn = c.n - w0;
+  if (c.n <= 0 || wn <= 0) return;
+  const long long threads = (long long)wn * 32;
   const int blocks = (int)((threads + kWarpKnnThreads - 1) / kWarpKnnThreads);
-  knn_cov_kernel<<<blocks, kWarpKnnThreads, 0, s>>>(c.spts, c.cell_start, c.g, c.n, k, d_nb, neighbors, nullptr, nullptr);
+  knn_cov_kernel<<<blocks, kWarpKnnThreads, 0, s>>>(c.spts, c.cell_start, c.g, c.n, k, d_nb, neighbors, nullptr, nullptr, w0, wn);
   (*launches)++;
 }
-void launch_cov_regularize(const CloudDev& c, int k, int regularization, const int32_t* d_nb, cudaStream_t s, int64_t* launches) {
-  if (c.n <= 0) return;
-  cov_regularize_kernel<<<(c.n + kThreads - 1) / kThreads, kThreads, 0, s>>>(c.pts, d_nb, c.n, k, regularization, c.cov, c.geo, c.geo64);
+void launch_cov_regularize(const CloudDev& c, int k, int regularization, const int32_t* d_nb, cudaStream_t s, int64_t* launches, int w0, int wn) {
+  if (wn < 0) wn = c.n - w0;
+  if (c.n <= 0 || wn <= 0) return;
+  cov_regularize_kernel<<<(wn + kThreads - 1) / kThreads, kThreads, 0, s>>>(c.pts, d_nb, c.n, k, regularization, c.cov, c.geo, c.geo64, w0, wn);
   (*launches)++;
 }
 void launch_regularize(const CloudDev& c, int regularization, cudaStream_t s, int64_t* launches) {

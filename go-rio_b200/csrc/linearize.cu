@@ -86,7 +86,7 @@ template <bool kFp64, bool kHB>
 __global__ void __launch_bounds__(kThreads, 2)
 linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_geo, const double* __restrict__ s_geo64,
                  const int* __restrict__ corr, const void* __restrict__ mahaA, const void* __restrict__ mahaB,
-                 const float4* __restrict__ t_spts, PoseD T, double cl_w, int n, double* __restrict__ partials,
+                 const float4* __restrict__ t_spts, PoseD T, double cl_w, int n, int accumulate, double* __restrict__ partials,
                  double* __restrict__ out28, unsigned int* __restrict__ ticket) {
   using L = StageLayout<kFp64>;
   constexpr int NV = kHB ? kReduceVals : 1;
@@ -216,8 +216,9 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
     if (tid < NV) {
       double v = 0.0;
       for (unsigned int k = 0; k < gridDim.x; k++) v += __ldcg(&partials[(size_t)k * NV + tid]);
-      if (kHB) out28[tid] = v;
-      else out28[27] = v;
+      // accumulate: this launch covers one chunk of a sharded source; the sums continue those of the previous chunks
+      double* o = kHB ? &out28[tid] : &out28[27];
+      *o = accumulate ? *o + v : v;
     }
     if (tid == 0) *ticket = 0;
   }
@@ -225,7 +226,7 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
 
 template <bool kFp64, bool kHB>
 void launch_one(int blocks, cudaStream_t s, const CloudDev& src, const CloudDev& tgt, const PoseD& T, const CorrOut& c, double cl_w,
-                const ReduceWork& w, double* d_out28) {
+                bool accumulate, const ReduceWork& w, double* d_out28) {
   static bool configured[64] = {false};  // per template instance and device: the attribute is per (function, device)
   constexpr int bytes = smem_bytes<kFp64>();
   int dev = 0;
@@ -235,23 +236,24 @@ void launch_one(int blocks, cudaStream_t s, const CloudDev& src, const CloudDev&
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   linearize_kernel<kFp64, kHB><<<blocks, kThreads, bytes, s>>>(src.spts, src.geo, src.geo64, c.corr, c.mahaA, c.mahaB, tgt.spts, T, cl_w,
-                                                                src.n, w.partials, d_out28, w.ticket);
+                                                                src.n, accumulate ? 1 : 0, w.partials, d_out28, w.ticket);
 }
 
 }  // namespace
 
 void launch_linearize(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const CorrOut& c, double n_total, bool want_hb,
-                      const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches) {
+                      bool accumulate, const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches) {
   const int n = src.n;
+  if (n <= 0 && accumulate) return;  // an empty chunk adds nothing
   int blocks = (n + kTile - 1) / kTile;
   blocks = max(1, min(blocks, w.max_blocks));
   const double cl_w = 1.0 / n_total;  // 1.0 / correspondences_.size() (:273)
   if (c.maha_fp64) {
-    if (want_hb) launch_one<true, true>(blocks, s, src, tgt, T, c, cl_w, w, d_out28);
-    else launch_one<true, false>(blocks, s, src, tgt, T, c, cl_w, w, d_out28);
+    if (want_hb) launch_one<true, true>(blocks, s, src, tgt, T, c, cl_w, accumulate, w, d_out28);
+    else launch_one<true, false>(blocks, s, src, tgt, T, c, cl_w, accumulate, w, d_out28);
   } else {
-    if (want_hb) launch_one<false, true>(blocks, s, src, tgt, T, c, cl_w, w, d_out28);
-    else launch_one<false, false>(blocks, s, src, tgt, T, c, cl_w, w, d_out28);
+    if (want_hb) launch_one<false, true>(blocks, s, src, tgt, T, c, cl_w, accumulate, w, d_out28);
+    else launch_one<false, false>(blocks, s, src, tgt, T, c, cl_w, accumulate, w, d_out28);
   }
   (*launches)++;
 }

@@ -2,10 +2,11 @@
 (SURVEY.md §8e). One process per GPU; torch.distributed is only the plumbing.
 
 1. batches of independent scan/submap pairs -> `shard_pairs` (no collective);
-2. one very large cloud split by source points -> `shard_range` + `init_comm`:
-   every rank holds the full target and source points [begin, end); linearize /
-   compute_error all-reduce their 28 / 1 doubles over NCCL inside the library
-   (apd_comm_init), and cl_weight uses the total source count.
+2. one very large registration split over the GPUs -> `init_comm`: every rank sets
+   the same full clouds; inside the library (apd_comm_init) each rank computes its
+   slice of the covariances (all-gathered) and linearizes its slice of the source
+   (28 / 1 doubles all-reduced over NCCL). `shard_range` is the partition arithmetic
+   for callers that split their own data (pairs, frames).
 """
 import ctypes
 

@@ -240,12 +240,20 @@ APD_API int apd_align_batch(int device, const apd_params* p, const apd_pair* pai
                     int32_t stride_bytes, int32_t xyz_off, int32_t label_off,
                     int32_t n_streams, int32_t with_fitness, apd_result* results);
 
-/* ---- source-sharded registration (config C4; no reference equivalent) --- */
-/* The handle holds source points [shard_begin, shard_begin+n_source) of a
- * cloud of n_source_total points and the FULL target. After apd_comm_init,
- * linearize / compute_error all-reduce their 28 / 1 doubles over NCCL, and
- * cl_weight uses n_source_total (reference: 1/correspondences_.size(),
- * fast_apdgicp_impl.hpp:273). id128 is an ncclUniqueId (128 bytes). */
+/* ---- one registration sharded over several GPUs (config C4; no reference
+ * equivalent) -------------------------------------------------------------- */
+/* One process and one handle per GPU; EVERY rank makes the same calls with the
+ * same FULL source and target clouds. After apd_comm_init the handle splits the
+ * work by contiguous ranges of the cell-sorted points: each rank searches the
+ * full grids for its slice of the covariances (then ncclAllGather), and runs
+ * update_correspondences / linearize / compute_error over its slice of the
+ * source (then ncclAllReduce of 28 / 1 doubles on the handle's stream). The LM
+ * loop runs redundantly on every rank from the identical reduced values, so all
+ * ranks return the same pose; it equals the single-GPU result up to summation
+ * order. cl_weight = 1 / (size of the whole source), as in the reference
+ * (fast_apdgicp_impl.hpp:273). apd_get_correspondences / apd_get_mahalanobis
+ * report the rank's own slice (-1 / 0 elsewhere). id128 is an ncclUniqueId
+ * (128 bytes); n_source_total is ignored (kept for ABI v1). */
 APD_API int apd_comm_unique_id(void* id128);
 APD_API int apd_comm_init(apd_handle* h, const void* id128, int32_t rank, int32_t nranks,
                   int64_t n_source_total);

@@ -94,19 +94,24 @@ kw = dict(max_correspondence_distance=2.0, maha_fp64=1)
 full = gorio.FastAPDGICP(local); full.set_params(**kw)
 full.set_input_target(tgt); full.set_input_source(src)
 e_full, H_full, b_full = full.linearize(T)
-cs = full.get_source_covariances()
-b, e = sharding.shard_range(src.shape[0], rank, world)
 part = gorio.FastAPDGICP(local); part.set_params(**kw)
-part.set_input_target(tgt); part.set_input_source(src[b:e].copy()); part.set_source_covariances(cs[b:e])
 sharding.init_comm(part, gorio.load(), rank, world, src.shape[0], dist, torch.device("cuda", local))
-e_p, H_p, b_p = part.linearize(T)           # all-reduced inside the library
+part.set_input_target(tgt); part.set_input_source(src)   # the same full clouds on every rank
+e_p, H_p, b_p = part.linearize(T)           # covariance slices all-gathered, H/b/err all-reduced inside the library
+cov_ok = bool(np.array_equal(part.get_target_covariances(), full.get_target_covariances()) and
+              np.array_equal(part.get_source_covariances(), full.get_source_covariances()))
+c_full, _ = full.get_correspondences(); c_part, _ = part.get_correspondences()
+mine = c_part >= 0
+counts = torch.tensor([int(mine.sum()), int((c_full >= 0).sum())], device="cuda")
+dist.all_reduce(counts[:1])
+corr_ok = bool(np.array_equal(c_part[mine], c_full[mine]) and int(counts[0]) == int(counts[1]))
 e2_full, e2_p = full.compute_error(T), part.compute_error(T)
 r_full = full.align()
 r_part = part.align()                        # every rank runs the same LM decisions on the reduced values
 rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
 res = {"H": rel(H_p, H_full), "b": rel(b_p, b_full), "err": abs(e_p - e_full) / e_full, "err2": abs(e2_p - e2_full) / e2_full,
        "pose": float(np.abs(r_part["T64"] - r_full["T64"]).max()), "iters": [r_part["iterations"], r_full["iterations"]],
-       "conv": [r_part["converged"], r_full["converged"]]}
+       "conv": [r_part["converged"], r_full["converged"]], "cov_ok": cov_ok, "corr_ok": corr_ok}
 poses = [None] * world
 dist.all_gather_object(poses, r_part["T64"].tolist())
 res["same_pose_on_all_ranks"] = all(p == poses[0] for p in poses)
@@ -125,4 +130,4 @@ def test_source_sharded_linearize_nccl(tmp_path):
     r = _torchrun(_GPU_WORKER, tmp_path, 2)
     assert r["H"] < 1e-11 and r["b"] < 1e-9 and r["err"] < 1e-11 and r["err2"] < 1e-11, r
     assert r["pose"] < 1e-9 and r["iters"][0] == r["iters"][1] and r["conv"][0] == r["conv"][1], r
-    assert r["same_pose_on_all_ranks"], r
+    assert r["same_pose_on_all_ranks"] and r["cov_ok"] and r["corr_ok"], r
