@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--roofline-only", action="store_true", help="profiling aid: skip the registrations/s part")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-pairs", type=int, default=8, help="pairs per step of the reference arm")
+    ap.add_argument("--no-fused", action="store_true", help="c4: ncclAllReduce after the reduction kernels instead of the peer-memory exchange inside them")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2 (default): scan-to-submap pairs, sharded by pair; c4: one large cloud, source-sharded with an NCCL all-reduce")
     return ap.parse_args()
@@ -211,7 +212,7 @@ def run_c4(args):
     g = gorio.FastAPDGICP(local_rank)
     g.set_params(max_correspondence_distance=2.0)
     if world > 1:
-        sharding.init_comm(g, gorio.load(), rank, world, n, dist, dev)
+        sharding.init_comm(g, gorio.load(), rank, world, n, dist, dev, fused=not args.no_fused)
     # every rank sets the same full clouds; the library slices the work (covariances all-gathered, H/b/err all-reduced)
     torch.cuda.synchronize()
     if world > 1:
@@ -253,8 +254,10 @@ def run_c4(args):
             "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C4: {n} source vs {n} target points over {world} GPU(s): covariances computed by slices and "
-                                   "all-gathered, source sliced for update_correspondences/linearize/compute_error, NCCL all-reduce "
-                                   "of 28 doubles per linearize and 1 per compute_error", "l2": "inputs larger than L2"},
+                                   "all-gathered, source sliced for update_correspondences/linearize/compute_error, all-reduce of 28 "
+                                   "doubles per linearize and 1 per compute_error "
+                                   + ("by ncclAllReduce" if (args.no_fused or world == 1) else "inside the reduction kernels over NVLink peer memory"),
+                       "l2": "inputs larger than L2"},
             "setup_ms": 1e3 * float(t_setup.item()), "setup": "grid builds + kNN covariances of both clouds (+ all-gather) + first linearize, wall clock, max over ranks",
             "gpu_launches": int(launches), "err": err, "err_trial": err2,
             "kernels_rank0_ms": {c: v[0] for c, v in k.items()},

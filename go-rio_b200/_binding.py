@@ -77,7 +77,7 @@ PRODUCT_SYMBOLS = CORE_SYMBOLS + [
     "abi_version", "set_source_device", "set_target_device", "align_batch", "batch_create", "batch_destroy",
     "batch_set_params", "batch_align", "batch_align_device", "batch_launch_count", "batch_set_profiling",
     "batch_get_kernel_ms", "comm_unique_id",
-    "comm_init", "comm_destroy", "stream", "launch_count", "set_profiling", "get_kernel_ms",
+    "comm_init", "comm_peer_handle", "comm_peer_attach", "comm_destroy", "stream", "launch_count", "set_profiling", "get_kernel_ms",
 ]
 
 
@@ -311,6 +311,16 @@ class Registration:
     def comm_init(self, id128, rank, nranks, n_source_total):
         buf = (C.c_char * 128).from_buffer_copy(bytes(id128))
         self._call("comm_init", buf, C.c_int32(rank), C.c_int32(nranks), C.c_int64(n_source_total))
+
+    def comm_peer_handle(self):
+        buf = (C.c_char * 64)()
+        self._call("comm_peer_handle", buf)
+        return bytes(buf)
+
+    def comm_peer_attach(self, handles):
+        blob = b"".join(handles)
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        self._call("comm_peer_attach", buf)
 
     def comm_destroy(self):
         self._call("comm_destroy")

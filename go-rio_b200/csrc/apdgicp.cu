@@ -198,6 +198,11 @@ struct apd_handle {
   // sharding
   ncclComm_t comm = nullptr;
   int comm_rank = 0, comm_size = 1;
+  // fused all-reduce over NVLink peer memory (apd_comm_peer_*): this rank's mailbox + the peers' mailboxes as mapped here
+  PeerMailbox* mailbox = nullptr;
+  PeerMailbox* peer_box[kPeerMaxRanks] = {nullptr};
+  bool peers_attached = false;
+  unsigned int xchg_seq = 0;
   // instrumentation
   int64_t launches = 0;
   bool profiling = false;
@@ -551,12 +556,20 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
   const double n_total = (double)h->src.n;  // correspondences_.size() (:273): the whole source cloud, sharded or not
   {
     ProfScope ps(h, want_hb ? APD_K_LINEARIZE : APD_K_ERROR);
-    for (int j = 0; j < h->shard_subs(); j++)  // chunks after the first add onto the 28 (1) sums of the previous ones
+    for (int j = 0; j < h->shard_subs(); j++) {  // chunks after the first add onto the 28 (1) sums of the previous ones
+      if (h->peers_attached && j == h->shard_subs() - 1) {  // the last chunk's kernel also exchanges the totals with the peers
+        for (int r = 0; r < h->comm_size; r++) w.xchg.box[r] = h->peer_box[r];
+        w.xchg.rank = h->comm_rank;
+        w.xchg.nranks = h->comm_size;
+        w.xchg.seq = ++h->xchg_seq;
+        if (w.xchg.seq == 0) w.xchg.seq = h->xchg_seq = 2;  // (wrap-around: 0 means "no exchange"; keep the parity alternating)
+      }
       launch_linearize(h->src_slice(j), h->tgt.view(), to_pose_d(T), corr_view(h, j), n_total, want_hb, j > 0, w, d_out, h->stream,
                        &h->launches);
+    }
   }
   APD_CUDA(h, cudaGetLastError());
-  if (h->comm) {
+  if (h->comm && !h->peers_attached) {
     ncclResult_t r = want_hb ? g_nccl.AllReduce(d_out, d_out, kReduceVals, kNcclFloat64, kNcclSum, h->comm, h->stream)
                              : g_nccl.AllReduce(d_out + 27, d_out + 27, 1, kNcclFloat64, kNcclSum, h->comm, h->stream);
     if (r != 0) return fail(h, APD_ERR_COMM, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclAllReduce failed");
@@ -985,6 +998,9 @@ int apd_destroy(apd_handle* h) {
   DeviceGuard dg(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (int r = 0; r < kPeerMaxRanks; r++)
+    if (h->peer_box[r] && h->peer_box[r] != h->mailbox) cudaIpcCloseMemHandle(h->peer_box[r]);
+  if (h->mailbox) cudaFree(h->mailbox);
   for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
   if (h->done_ev) cudaEventDestroy(h->done_ev);
@@ -1428,11 +1444,58 @@ int apd_comm_init(apd_handle* h, const void* id128, int32_t rank, int32_t nranks
   h->corr_n = -1;        // correspondences of the unsharded layout are no longer addressable
   return APD_OK;
 }
+int apd_comm_peer_handle(apd_handle* h, void* handle64) {
+  if (!h || !handle64) return APD_ERR_INVALID;
+  if (!h->comm) return fail(h, APD_ERR_INVALID, "apd_comm_peer_handle needs apd_comm_init first");
+  if (h->comm_size > kPeerMaxRanks) return fail(h, APD_ERR_UNSUPPORTED, "too many ranks for the peer-memory exchange");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  DeviceGuard dg(h->device);
+  if (!h->mailbox) {
+    APD_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->mailbox), sizeof(PeerMailbox)));  // (IPC needs a plain cudaMalloc allocation)
+    APD_CUDA(h, cudaMemset(h->mailbox, 0, sizeof(PeerMailbox)));
+  }
+  cudaIpcMemHandle_t ipc;
+  APD_CUDA(h, cudaIpcGetMemHandle(&ipc, h->mailbox));
+  std::memcpy(handle64, &ipc, sizeof(ipc));
+  return APD_OK;
+}
+
+int apd_comm_peer_attach(apd_handle* h, const void* handles) {
+  if (!h || !handles) return APD_ERR_INVALID;
+  if (!h->comm || !h->mailbox) return fail(h, APD_ERR_INVALID, "apd_comm_peer_attach needs apd_comm_init and apd_comm_peer_handle first");
+  DeviceGuard dg(h->device);
+  for (int r = 0; r < h->comm_size; r++) {
+    if (r == h->comm_rank) {
+      h->peer_box[r] = h->mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t ipc;
+    std::memcpy(&ipc, reinterpret_cast<const char*>(handles) + (size_t)r * sizeof(ipc), sizeof(ipc));
+    void* p = nullptr;
+    APD_CUDA(h, cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_box[r] = reinterpret_cast<PeerMailbox*>(p);
+  }
+  h->xchg_seq = 0;
+  h->peers_attached = true;
+  return APD_OK;
+}
+
+static void release_peers(apd_handle* h) {
+  for (int r = 0; r < kPeerMaxRanks; r++) {
+    if (h->peer_box[r] && h->peer_box[r] != h->mailbox) cudaIpcCloseMemHandle(h->peer_box[r]);
+    h->peer_box[r] = nullptr;
+  }
+  if (h->mailbox) cudaFree(h->mailbox);
+  h->mailbox = nullptr;
+  h->peers_attached = false;
+}
+
 int apd_comm_destroy(apd_handle* h) {
   if (!h) return APD_ERR_INVALID;
   if (h->comm) {
     DeviceGuard dg(h->device);
     cudaStreamSynchronize(h->stream);
+    release_peers(h);
     g_nccl.CommDestroy(h->comm);
     h->comm = nullptr;
     h->corr_n = -1;

@@ -91,10 +91,27 @@ void launch_transform_cloud(const float4* pts, int n, const PoseF& T, float* d_x
 
 // ---- linearize.cu --------------------------------------------------------------
 constexpr int kReduceVals = 28;  // 21 (upper H) + 6 (b) + 1 (err)
+// Fused all-reduce of the 28 (1) sums across the ranks of a sharded registration, inside the reduction kernel's last
+// block: every rank PUSHES its sums into a mailbox in every peer's memory (plain stores over NVLink peer mappings),
+// publishes a sequence number with release semantics at system scope, waits for the numbers of all ranks in its own
+// mailbox and adds the contributions in rank order — so all ranks hold bit-identical totals without a separate
+// collective launch. Two buffers alternate by sequence parity: a rank can run at most one exchange ahead of a peer.
+constexpr int kPeerMaxRanks = 16;
+struct PeerMailbox {
+  double val[2][kPeerMaxRanks][32];
+  unsigned int flag[2][kPeerMaxRanks];
+  unsigned int timed_out;  // set if a peer did not show up within the time limit (the sums are then NaN)
+};
+struct PeerExchange {
+  PeerMailbox* box[kPeerMaxRanks];  // box[r]: rank r's mailbox as mapped into this process (box[rank] = the local one)
+  int rank = 0, nranks = 1;
+  unsigned int seq = 0;             // sequence number of this exchange (0: no exchange in this launch)
+};
 struct ReduceWork {
   double* partials;     // [max_blocks * 28]
   unsigned int* ticket; // last-block-done counter (zeroed once; the kernel resets it)
   int max_blocks;
+  PeerExchange xchg;    // seq != 0: exchange the totals with the peers in the kernel's tail
 };
 // reference linearize (:247-304) / compute_error (:313-343) given the stored
 // correspondences and Mahalanobis matrices. out28 = 21 upper-triangular H

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_geo, const double* __restrict__ s_geo64,
                  const int* __restrict__ corr, const void* __restrict__ mahaA, const void* __restrict__ mahaB,
                  const float4* __restrict__ t_spts, PoseD T, double cl_w, int n, int accumulate, double* __restrict__ partials,
-                 double* __restrict__ out28, unsigned int* __restrict__ ticket) {
+                 double* __restrict__ out28, unsigned int* __restrict__ ticket, PeerExchange xchg) {
   using L = StageLayout<kFp64>;
   constexpr int NV = kHB ? kReduceVals : 1;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -213,13 +213,46 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
   __syncthreads();
   if (last) {
     __threadfence();
+    double v = 0.0;
+    double* o = kHB ? &out28[tid < NV ? tid : 0] : &out28[27];
     if (tid < NV) {
-      double v = 0.0;
       for (unsigned int k = 0; k < gridDim.x; k++) v += __ldcg(&partials[(size_t)k * NV + tid]);
       // accumulate: this launch covers one chunk of a sharded source; the sums continue those of the previous chunks
-      double* o = kHB ? &out28[tid] : &out28[27];
-      *o = accumulate ? *o + v : v;
+      if (accumulate) v = *o + v;
     }
+    if (xchg.seq != 0) {
+      // ---- fused all-reduce over peer memory (see PeerExchange) ----
+      const int buf = (int)(xchg.seq & 1u);
+      if (tid < NV)
+        for (int r = 0; r < xchg.nranks; r++) xchg.box[r]->val[buf][xchg.rank][tid] = v;  // push to every mailbox, mine included
+      __threadfence_system();
+      __syncthreads();
+      if (tid < xchg.nranks)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&xchg.box[tid]->flag[buf][xchg.rank]), "r"(xchg.seq) : "memory");
+      PeerMailbox* mine = xchg.box[xchg.rank];
+      if (tid < xchg.nranks) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+          unsigned int f;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&mine->flag[buf][tid]) : "memory");
+          if (f == xchg.seq) break;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > 5000000000ull) {  // 5 s: a peer is gone; do not hang the GPU
+            mine->timed_out = 1u;
+            break;
+          }
+          __nanosleep(64);
+        }
+      }
+      __syncthreads();
+      if (tid < NV) {
+        v = 0.0;
+        for (int r = 0; r < xchg.nranks; r++) v += *((volatile double*)&mine->val[buf][r][tid]);  // rank order: same bits everywhere
+        if (*((volatile unsigned int*)&mine->timed_out)) v = __longlong_as_double(0x7ff8000000000000ll);
+      }
+    }
+    if (tid < NV) *o = v;
     if (tid == 0) *ticket = 0;
   }
 }
@@ -236,7 +269,7 @@ void launch_one(int blocks, cudaStream_t s, const CloudDev& src, const CloudDev&
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   linearize_kernel<kFp64, kHB><<<blocks, kThreads, bytes, s>>>(src.spts, src.geo, src.geo64, c.corr, c.mahaA, c.mahaB, tgt.spts, T, cl_w,
-                                                                src.n, accumulate ? 1 : 0, w.partials, d_out28, w.ticket);
+                                                                src.n, accumulate ? 1 : 0, w.partials, d_out28, w.ticket, w.xchg);
 }
 
 }  // namespace
@@ -244,7 +277,7 @@ void launch_one(int blocks, cudaStream_t s, const CloudDev& src, const CloudDev&
 void launch_linearize(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const CorrOut& c, double n_total, bool want_hb,
                       bool accumulate, const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches) {
   const int n = src.n;
-  if (n <= 0 && accumulate) return;  // an empty chunk adds nothing
+  if (n <= 0 && accumulate && w.xchg.seq == 0) return;  // an empty chunk adds nothing (unless it carries the exchange)
   int blocks = (n + kTile - 1) / kTile;
   blocks = max(1, min(blocks, w.max_blocks));
   const double cl_w = 1.0 / n_total;  // 1.0 / correspondences_.size() (:273)

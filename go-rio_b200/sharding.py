@@ -37,7 +37,15 @@ def broadcast_unique_id(lib, rank, dist, device=None):
     return bytes(t.cpu().tolist())
 
 
-def init_comm(reg, lib, rank, world, n_source_total, dist, device=None):
-    """attach an NCCL communicator to the registration handle `reg`"""
+def init_comm(reg, lib, rank, world, n_source_total, dist, device=None, fused=True):
+    """attach an NCCL communicator to the registration handle `reg`; fused: also exchange the peer-memory mailboxes
+    (cudaIpc handles, all-gathered here) so that the H/b/err all-reduce runs inside the reduction kernels"""
+    import torch
+
     uid = broadcast_unique_id(lib, rank, dist, device)
     reg.comm_init(uid, rank, world, n_source_total)
+    if fused and world > 1:
+        mine = torch.tensor(list(reg.comm_peer_handle()), dtype=torch.uint8, device=device)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        reg.comm_peer_attach([bytes(t.cpu().tolist()) for t in every])

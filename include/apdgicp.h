@@ -257,6 +257,17 @@ APD_API int apd_align_batch(int device, const apd_params* p, const apd_pair* pai
 APD_API int apd_comm_unique_id(void* id128);
 APD_API int apd_comm_init(apd_handle* h, const void* id128, int32_t rank, int32_t nranks,
                   int64_t n_source_total);
+/* Optional, after apd_comm_init on every rank: fuse the all-reduce of H/b/err into
+ * the reduction kernels. Each rank exports a small mailbox in its device memory
+ * (handle64: a cudaIpcMemHandle_t, 64 bytes); the caller exchanges the handles
+ * between the processes (any transport) and passes all of them, in rank order
+ * (nranks x 64 bytes), to apd_comm_peer_attach. From then on the last block of
+ * linearize / compute_error pushes its sums into every peer's mailbox over
+ * NVLink, waits for the peers' and adds them in rank order: no separate
+ * collective launch, bit-identical totals on all ranks. All ranks must attach
+ * (or none). At most 16 ranks; GPUs must be peer-accessible (one NVSwitch node). */
+APD_API int apd_comm_peer_handle(apd_handle* h, void* handle64);
+APD_API int apd_comm_peer_attach(apd_handle* h, const void* handles);
 APD_API int apd_comm_destroy(apd_handle* h);
 
 /* ---- instrumentation --------------------------------------------------- */

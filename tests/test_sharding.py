@@ -95,7 +95,7 @@ full = gorio.FastAPDGICP(local); full.set_params(**kw)
 full.set_input_target(tgt); full.set_input_source(src)
 e_full, H_full, b_full = full.linearize(T)
 part = gorio.FastAPDGICP(local); part.set_params(**kw)
-sharding.init_comm(part, gorio.load(), rank, world, src.shape[0], dist, torch.device("cuda", local))
+sharding.init_comm(part, gorio.load(), rank, world, src.shape[0], dist, torch.device("cuda", local), fused=os.environ["APD_FUSED"] == "1")
 part.set_input_target(tgt); part.set_input_source(src)   # the same full clouds on every rank
 e_p, H_p, b_p = part.linearize(T)           # covariance slices all-gathered, H/b/err all-reduced inside the library
 cov_ok = bool(np.array_equal(part.get_target_covariances(), full.get_target_covariances()) and
@@ -123,11 +123,13 @@ dist.barrier(); dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-def test_source_sharded_linearize_nccl(tmp_path):
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_sharded_registration_two_gpus(tmp_path, fused):
+    """fused = 0: ncclAllReduce after the reduction kernels; 1: the exchange over NVLink peer memory inside them"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(_GPU_WORKER, tmp_path, 2)
+    r = _torchrun(_GPU_WORKER, tmp_path, 2, extra_env={"APD_FUSED": fused})
     assert r["H"] < 1e-11 and r["b"] < 1e-9 and r["err"] < 1e-11 and r["err2"] < 1e-11, r
     assert r["pose"] < 1e-9 and r["iters"][0] == r["iters"][1] and r["conv"][0] == r["conv"][1], r
     assert r["same_pose_on_all_ranks"] and r["cov_ok"] and r["corr_ok"], r
