@@ -335,6 +335,7 @@ def main():
                 batch.align(prepared, with_fitness=False, parse=False)
             ms_total = 0.0
             l0 = batch.launch_count()
+            cpu0 = time.process_time()
             for _ in range(steps):
                 flush.zero_()  # L2 flush between timed iterations (untimed)
                 barrier()
@@ -348,11 +349,12 @@ def main():
                     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
                 ms_total += float(ms.item())
             launches = batch.launch_count() - l0
-            return ms_total, launches, batch.align(prepared, with_fitness=False)
+            cpu_ms_per_pair = 1e3 * (time.process_time() - cpu0) / (steps * prepared["n"])  # all threads of this process
+            return ms_total, launches, batch.align(prepared, with_fitness=False), cpu_ms_per_pair
 
         with ClockSampler(local_rank) as clocks:
-            ms_dev, launches, results = timed(prep_dev, args.steps, args.warmup)
-        ms_e2e, _, results_h = timed(prep_host, args.steps, args.warmup)
+            ms_dev, launches, results, cpu_dev = timed(prep_dev, args.steps, args.warmup)
+        ms_e2e, _, results_h, cpu_e2e = timed(prep_host, args.steps, args.warmup)
         total_pairs = args.pairs * world
         value = total_pairs * args.steps / (ms_dev / 1e3)
         e2e_value = total_pairs * args.steps / (ms_e2e / 1e3)
@@ -388,6 +390,8 @@ def main():
                         "same_result_as_device_resident": bool(same), "all_pairs_ok": bool(ok),
                         "api": "apd_batch_align (host AoS clouds in, poses out)"},
                 "gpu_launches": int(launches),
+                "host_cpu_ms_per_registration": {"device_resident": round(cpu_dev, 4), "e2e": round(cpu_e2e, 4), "host_cores": host_cores(),
+                                                 "note": "process CPU time of rank 0 (all worker threads, incl. the L2 flush / barrier between steps) per registration"},
                 "kernels": kernels,
                 "knn_cov_roofline": {"bound": "hbm", "achieved": (BYTES_PER_POINT_KNNCOV * knn_pts / 1e9) / (knn_ms / 1e3) if knn_ms > 0 else None,
                                      "peak": peak, "unit": "GB/s", "note": "search-bound (L2-resident candidates), reported for the step's dominant kernel"},

@@ -4,8 +4,10 @@
 // batched and the source-sharded (NCCL) variants.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <emmintrin.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <cfloat>
@@ -181,6 +183,7 @@ struct apd_handle {
   // wait for the result of the device loop on a blocking-sync event instead of spinning on the stream: the batch
   // context runs more host threads than it needs cores for (set by apd_batch_create; APD_BLOCKING_SYNC=0|1 overrides)
   bool blocking_wait = false;
+  int poll_wait_us = 0;
   cudaEvent_t done_ev = nullptr;
   // batch workers ask the device loop to append the getFitnessScore pass (saves a launch and a round trip per pair)
   bool fuse_fitness = false;
@@ -256,6 +259,28 @@ namespace {
       return APD_ERR_CUDA;                                                                \
     }                                                                                     \
   } while (0)
+
+// Wait for everything enqueued on the handle's stream. A lone handle spins (lowest latency). Handles of a large batch
+// pool — many more host threads than cores — sleep and poll the stream every poll_wait_us: their per-pair latency (ms) hides
+// a 0.2 ms poll, and unlike blocking-sync events it costs no interrupt per wait (measured on 8 x B200, 32 host cores, 256
+// worker threads: 46.1 k registrations/s with polling against 22.6 k with blocking-sync events; 1 GPU: 6.3 k either way).
+cudaError_t wait_stream(apd_handle* h) {
+  if (!h->blocking_wait) return cudaStreamSynchronize(h->stream);
+  if (h->poll_wait_us > 0) {  // sleep-and-poll: no interrupt per wait (APD_POLL_WAIT_US)
+    for (;;) {
+      const cudaError_t e = cudaStreamQuery(h->stream);
+      if (e != cudaErrorNotReady) return e;
+      std::this_thread::sleep_for(std::chrono::microseconds(h->poll_wait_us));
+    }
+  }
+  if (!h->done_ev) {
+    cudaError_t e = cudaEventCreateWithFlags(&h->done_ev, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaEventRecord(h->done_ev, h->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(h->done_ev);
+}
 
 int fail(apd_handle* h, int code, const char* msg) {
   h->error = msg;
@@ -336,24 +361,37 @@ PoseF colmajor_f32_to_pose_f(const float* T) {
   return f;
 }
 
-// host AoS -> pinned float4 staging + bounding box
+// host AoS -> pinned float4 staging + bounding box. Branch-free min / max over a contiguous float4 array (the compiler
+// vectorises it); the common layouts (packed float4 {x,y,z,label}; pcl::PointXYZINormal: xyz at 0, label at 16, stride 48)
+// take fixed-offset loads.
 void stage_cloud(const void* pts, int n, int stride, int xyz_off, int label_off, float4* dst, float bbox[6]) {
-  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   const char* base = reinterpret_cast<const char*>(pts);
-  for (int i = 0; i < n; i++) {
-    const char* p = base + (size_t)i * stride;
-    float xyz[3], l = 0.f;
-    std::memcpy(xyz, p + xyz_off, 12);
-    if (label_off >= 0) std::memcpy(&l, p + label_off, 4);
-    dst[i] = make_float4(xyz[0], xyz[1], xyz[2], l);
-    for (int a = 0; a < 3; a++) {
-      if (xyz[a] < mn[a]) mn[a] = xyz[a];
-      if (xyz[a] > mx[a]) mx[a] = xyz[a];
+  __m128 mn = _mm_set1_ps(FLT_MAX), mx = _mm_set1_ps(-FLT_MAX);
+  if (stride == 16 && xyz_off == 0 && label_off == 12) {  // packed float4: one pass, copy + min / max
+    for (int i = 0; i < n; i++) {
+      const __m128 v = _mm_loadu_ps(reinterpret_cast<const float*>(base + (size_t)i * 16));
+      _mm_store_ps(reinterpret_cast<float*>(&dst[i]), v);
+      mn = _mm_min_ps(v, mn);  // (a NaN coordinate leaves the bound unchanged: the second operand wins)
+      mx = _mm_max_ps(v, mx);
+    }
+  } else {
+    for (int i = 0; i < n; i++) {
+      const char* p = base + (size_t)i * stride;
+      alignas(16) float f[4] = {0.f, 0.f, 0.f, 0.f};
+      std::memcpy(f, p + xyz_off, 12);
+      if (label_off >= 0) std::memcpy(&f[3], p + label_off, 4);
+      const __m128 v = _mm_load_ps(f);
+      _mm_store_ps(reinterpret_cast<float*>(&dst[i]), v);
+      mn = _mm_min_ps(v, mn);  // (a NaN coordinate leaves the bound unchanged: the second operand wins)
+      mx = _mm_max_ps(v, mx);
     }
   }
-  for (int a = 0; a < 3; a++) {
-    bbox[a] = mn[a];
-    bbox[3 + a] = mx[a];
+  alignas(16) float lo[4], hi[4];
+  _mm_store_ps(lo, mn);
+  _mm_store_ps(hi, mx);
+  for (int a = 0; a < 3; a++) {  // (lane 3 is the label: ignored)
+    bbox[a] = lo[a];
+    bbox[3 + a] = hi[a];
   }
 }
 
@@ -576,7 +614,7 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
   }
   double* hs = reinterpret_cast<double*>(h->h_small.p);
   APD_CUDA(h, cudaMemcpyAsync(hs, d_out, kReduceVals * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  APD_CUDA(h, wait_stream(h));
   if (want_hb) {
     if (H36) hm::unpack_upper(hs, H36);
     if (b6) std::memcpy(b6, hs + 21, 6 * sizeof(double));
@@ -673,8 +711,16 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
   if (c.present && key != 0 && key == c.key) return APD_OK;  // pointer-identity early-out (:116,:128)
   DeviceGuard dg(h->device);
   // the previous H2D out of this staging buffer must have completed before it is overwritten
-  if (c.staged) APD_CUDA(h, cudaEventSynchronize(c.staged));
-  else APD_CUDA(h, cudaEventCreateWithFlags(&c.staged, cudaEventDisableTiming));
+  if (c.staged) {
+    if (h->blocking_wait && h->poll_wait_us > 0) {
+      cudaError_t e;
+      while ((e = cudaEventQuery(c.staged)) == cudaErrorNotReady) std::this_thread::sleep_for(std::chrono::microseconds(h->poll_wait_us));
+      APD_CUDA(h, e);
+    } else {
+      APD_CUDA(h, cudaEventSynchronize(c.staged));
+    }
+  }
+  else APD_CUDA(h, cudaEventCreateWithFlags(&c.staged, cudaEventDisableTiming | (h->blocking_wait ? cudaEventBlockingSync : 0)));
   APD_CUDA(h, c.stage.ensure((size_t)std::max(n, 1) * sizeof(float4)));
   stage_cloud(pts, n, stride, xyz_off, label_off, reinterpret_cast<float4*>(c.stage.p), c.bbox);
   APD_CUDA(h, c.pts.ensure((size_t)std::max(n, 1) * sizeof(float4)));
@@ -697,9 +743,9 @@ int set_cloud_device(apd_handle* h, Cloud& c, const void* d_xyzl, int32_t n) {
   if (rc != APD_OK) return rc;
   float* d_b = reinterpret_cast<float*>(h->small.as<double>() + 48);
   launch_bounds(reinterpret_cast<const float4*>(d_xyzl), n, d_b, h->stream, &h->launches);
-  unsigned int enc[6];
-  APD_CUDA(h, cudaMemcpyAsync(enc, d_b, sizeof(enc), cudaMemcpyDeviceToHost, h->stream));
-  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  unsigned int* enc = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(h->h_small.p) + 48);  // pinned: a truly asynchronous copy
+  APD_CUDA(h, cudaMemcpyAsync(enc, d_b, 6 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
   for (int a = 0; a < 6; a++) {
     unsigned int u = enc[a];
     u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
@@ -726,7 +772,7 @@ int set_covs(apd_handle* h, Cloud& c, const double* covs, int32_t n) {
   APD_CUDA(h, h->scratch.ensure((size_t)n * 16 * sizeof(double)));
   APD_CUDA(h, cudaMemcpyAsync(h->scratch.p, covs, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   launch_cov_import(c.view(), h->scratch.as<double>(), h->stream, &h->launches);
-  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  APD_CUDA(h, wait_stream(h));
   c.cov_valid = true;
   c.geo_valid = false;
   return APD_OK;
@@ -740,7 +786,7 @@ int get_covs(apd_handle* h, Cloud& c, double* covs, int32_t n) {
   APD_CUDA(h, h->scratch.ensure((size_t)n * 16 * sizeof(double)));
   launch_cov_export(c.view(), h->scratch.as<double>(), h->stream, &h->launches);
   APD_CUDA(h, cudaMemcpyAsync(covs, h->scratch.p, (size_t)n * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  APD_CUDA(h, wait_stream(h));
   flush_prof(h);
   return APD_OK;
 }
@@ -844,7 +890,7 @@ int finish_device_align(apd_handle* h, const LmResult* r) {
   if (rows > head) {  // rare: long LM runs — fetch the remaining rows
     APD_CUDA(h, cudaMemcpyAsync(h->trace.data() + (size_t)head * 8, h->lm_result.as<LmResult>()->trace + (size_t)head * 8,
                                 (size_t)(rows - head) * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    APD_CUDA(h, cudaStreamSynchronize(h->stream));
+    APD_CUDA(h, wait_stream(h));
   }
   if (h->lm_failed) std::fprintf(stderr, "lm not converged!!\n");  // lsq :72
   h->final_pose = x0;
@@ -883,13 +929,7 @@ int do_align(apd_handle* h, const float* guess) {
     }
     rc = enqueue_device_align(h, guess, cfg);
     if (rc != APD_OK) return rc;
-    if (h->blocking_wait) {
-      if (!h->done_ev) APD_CUDA(h, cudaEventCreateWithFlags(&h->done_ev, cudaEventBlockingSync | cudaEventDisableTiming));
-      APD_CUDA(h, cudaEventRecord(h->done_ev, h->stream));
-      APD_CUDA(h, cudaEventSynchronize(h->done_ev));
-    } else {
-      APD_CUDA(h, cudaStreamSynchronize(h->stream));
-    }
+    APD_CUDA(h, wait_stream(h));
     const LmResult* r = reinterpret_cast<const LmResult*>(h->h_lm.p);
     if (cfg.want_fitness) {
       h->fit_valid = true;
@@ -939,7 +979,7 @@ int do_fitness(apd_handle* h, const float* T, double max_range, double* score, i
   APD_CUDA(h, cudaGetLastError());
   double* hs = reinterpret_cast<double*>(h->h_small.p) + 32;
   APD_CUDA(h, cudaMemcpyAsync(hs, d_small + 32, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  APD_CUDA(h, wait_stream(h));
   const int nr = (int)hs[1];
   if (score) *score = nr > 0 ? hs[0] / nr : std::numeric_limits<double>::max();
   if (n_in_range) *n_in_range = nr;
@@ -986,6 +1026,7 @@ int apd_create(int device, apd_handle** out) {
     if (v == 1 || v == 2 || v == 4 || v == 8) h->lm_cluster = v;
   }
   if (const char* e = std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = std::atoi(e) != 0;
+  if (const char* e = std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = std::atoi(e);
   if (const char* e = std::getenv("APD_KNN_MODE")) h->knn_mode = std::strcmp(e, "warp") == 0 ? 1 : (std::strcmp(e, "thread") == 0 ? 2 : 0);
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   for (int i = 0; i < 36; i++) h->final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity()
@@ -1093,7 +1134,7 @@ int apd_get_neighbors(apd_handle* h, int32_t which, int32_t* out, int32_t n, int
   }
   APD_CUDA(h, cudaGetLastError());
   APD_CUDA(h, cudaMemcpyAsync(out, h->scratch.p, (size_t)n * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  APD_CUDA(h, wait_stream(h));
   return APD_OK;
 }
 
@@ -1115,7 +1156,7 @@ int apd_align(apd_handle* h, const float* guess, float* T_out, double* T_out_f64
     APD_CUDA(h, h->scratch.ensure(bytes));
     launch_transform_cloud(h->src.view().pts, h->src.n, colmajor_f32_to_pose_f(h->final_T), h->scratch.as<float>(), h->stream, &h->launches);
     APD_CUDA(h, cudaMemcpyAsync(aligned_xyz, h->scratch.p, bytes, cudaMemcpyDeviceToHost, h->stream));
-    APD_CUDA(h, cudaStreamSynchronize(h->stream));
+    APD_CUDA(h, wait_stream(h));
   }
   flush_prof(h);
   return APD_OK;
@@ -1149,7 +1190,7 @@ int apd_update_correspondences(apd_handle* h, const double* T) {
   if (rc != APD_OK) return rc;
   rc = do_update_correspondences(h, hm::from_colmajor_f64(T));
   if (rc != APD_OK) return rc;
-  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  APD_CUDA(h, wait_stream(h));
   flush_prof(h);
   return APD_OK;
 }
@@ -1170,7 +1211,7 @@ int apd_get_correspondences(apd_handle* h, int32_t* idx, float* sq_dist, int32_t
     launch_corr_export(h->src_slice(j), h->tgt.view(), corr_view(h, j), d_idx, d_sq, nullptr, h->stream, &h->launches);
   if (idx) APD_CUDA(h, cudaMemcpyAsync(idx, d_idx, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   if (sq_dist) APD_CUDA(h, cudaMemcpyAsync(sq_dist, d_sq, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  APD_CUDA(h, wait_stream(h));
   return APD_OK;
 }
 
@@ -1183,7 +1224,7 @@ int apd_get_mahalanobis(apd_handle* h, double* maha, int32_t n) {
   for (int j = 0; j < h->shard_subs(); j++)
     launch_corr_export(h->src_slice(j), h->tgt.view(), corr_view(h, j), nullptr, nullptr, h->scratch.as<double>(), h->stream, &h->launches);
   APD_CUDA(h, cudaMemcpyAsync(maha, h->scratch.p, (size_t)n * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  APD_CUDA(h, wait_stream(h));
   return APD_OK;
 }
 
@@ -1328,9 +1369,10 @@ int apd_batch_create(int device, int32_t n_workers, apd_batch** out) {
       delete b;
       return rc;
     }
-    // a pool this large keeps the GPU busy by itself: its waiting threads sleep (blocking-sync event) instead of
-    // spinning, so that several ranks' pools can share the host cores (measured: +5 % at 1 GPU, +10 % at 2 GPUs)
+    // a pool this large keeps the GPU busy by itself: its waiting threads sleep instead of spinning, so that several
+    // ranks' pools can share the host cores (see wait_stream)
     if (!std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = n_workers > 8;
+    if (!std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = 200;
     b->handles.push_back(h);
   }
   for (int s = 0; s < n_workers; s++) b->threads.emplace_back(batch_worker, b, s);
@@ -1439,7 +1481,7 @@ int apd_comm_init(apd_handle* h, const void* id128, int32_t rank, int32_t nranks
     if (rc != APD_OK) return rc;
     double* d = h->small.as<double>() + 56;
     if (g_nccl.AllReduce(d, d, 1, kNcclFloat64, kNcclSum, h->comm, h->stream) != 0) return fail(h, APD_ERR_COMM, "ncclAllReduce (warm-up) failed");
-    APD_CUDA(h, cudaStreamSynchronize(h->stream));
+    APD_CUDA(h, wait_stream(h));
   }
   h->corr_n = -1;        // correspondences of the unsharded layout are no longer addressable
   return APD_OK;

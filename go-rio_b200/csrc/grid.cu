@@ -332,8 +332,9 @@ size_t scan_tmp_elems_for(size_t n) {
 
 void launch_bounds(const float4* pts, int n, float* d_out6, cudaStream_t s, int64_t* launches) {
   // d_out6 is used as 6 ordered-uint32 slots; the caller decodes them
-  static const unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
-  cudaMemcpyAsync(d_out6, init, sizeof(init), cudaMemcpyHostToDevice, s);
+  // {0xffffffff x 3, 0 x 3}: two memsets (a copy from pageable host memory would stall the calling thread)
+  cudaMemsetAsync(d_out6, 0xff, 3 * sizeof(unsigned int), s);
+  cudaMemsetAsync(reinterpret_cast<unsigned int*>(d_out6) + 3, 0, 3 * sizeof(unsigned int), s);
   const int blocks = min(148 * 8, (n + kThreads - 1) / kThreads);
   bounds_kernel<<<max(1, blocks), kThreads, 0, s>>>(pts, n, reinterpret_cast<unsigned int*>(d_out6));
   (*launches)++;
