@@ -706,10 +706,58 @@ int step_lm(apd_handle* h, int outer, hm::Pose& x0, hm::Pose& delta, bool* ok) {
   return APD_OK;
 }
 
+// The cloud being set is the one the OTHER slot already holds (same cache key, same size): a frame promoted to keyframe
+// (scan_matching_odometry_nodelet.cpp:587-588 sets the just-registered source as the new target). Its grid and
+// covariances are pure functions of the cloud, so they are copied device-to-device instead of rebuilt (the reference
+// recomputes them).
+int adopt_cloud(apd_handle* h, Cloud& dst, const Cloud& src) {
+  const size_t n = (size_t)src.n;
+  auto copy = [&](DevBuf& d, const DevBuf& s_, size_t bytes) -> cudaError_t {
+    if (!s_.p || bytes == 0) return cudaSuccess;
+    cudaError_t e = d.ensure(bytes);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(d.p, s_.p, bytes, cudaMemcpyDeviceToDevice, h->stream);
+  };
+  if (src.ext_pts) {
+    dst.ext_pts = src.ext_pts;
+  } else {
+    dst.ext_pts = nullptr;
+    APD_CUDA(h, copy(dst.pts, src.pts, n * sizeof(float4)));
+  }
+  if (src.grid_valid) {
+    APD_CUDA(h, copy(dst.spts, src.spts, n * sizeof(float4)));
+    APD_CUDA(h, copy(dst.label, src.label, n * sizeof(float)));
+    APD_CUDA(h, copy(dst.inv_perm, src.inv_perm, n * sizeof(int)));
+    APD_CUDA(h, copy(dst.cell_start, src.cell_start, ((size_t)src.ncells + 1) * sizeof(uint32_t)));
+  }
+  if (src.grid_valid && src.cov_valid) APD_CUDA(h, copy(dst.cov, src.cov, h->padded_n(src.n) * 6 * sizeof(double)));
+  if (src.grid_valid && src.cov_valid && src.geo_valid) {
+    APD_CUDA(h, copy(dst.geo, src.geo, n * sizeof(float)));
+    APD_CUDA(h, copy(dst.geo64, src.geo64, n * sizeof(double)));
+  }
+  dst.n = src.n;
+  dst.present = true;
+  dst.key = src.key;
+  std::memcpy(dst.bbox, src.bbox, sizeof(dst.bbox));
+  dst.g = src.g;
+  dst.ncells = src.ncells;
+  dst.grid_valid = src.grid_valid;
+  dst.cov_valid = src.grid_valid && src.cov_valid;
+  dst.geo_valid = dst.cov_valid && src.geo_valid;
+  return APD_OK;
+}
+
 int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t stride, int32_t xyz_off, int32_t label_off, uint64_t key) {
   if (!pts || n < 0 || stride < 12 || xyz_off < 0) return fail(h, APD_ERR_INVALID, "bad cloud arguments");
   if (c.present && key != 0 && key == c.key) return APD_OK;  // pointer-identity early-out (:116,:128)
   DeviceGuard dg(h->device);
+  {
+    Cloud& other = (&c == &h->src) ? h->tgt : h->src;
+    if (key != 0 && other.present && other.key == key && other.n == n) {
+      h->corr_n = -1;
+      return adopt_cloud(h, c, other);
+    }
+  }
   // the previous H2D out of this staging buffer must have completed before it is overwritten
   if (c.staged) {
     if (h->blocking_wait && h->poll_wait_us > 0) {

@@ -67,9 +67,11 @@ class ScanMatchingOdometry:
             self.prev_trans = np.eye(4)
             self.keyframe_pose = np.eye(4)
             self.keyframe_cloud = cloud
-            self.reg.set_input_target(cloud)
+            self.reg.set_input_target(cloud, key=cloud.ctypes.data)
             return np.eye(4)
-        self.reg.set_input_source(cloud)  # :442
+        # the cloud's address is the cache key, as the shared_ptr is in the reference (fast_apdgicp_impl.hpp:116,:128): a frame
+        # promoted to keyframe below is then recognised and its grid / covariances are reused, not rebuilt
+        self.reg.set_input_source(cloud, key=cloud.ctypes.data)  # :442
         guess = self.prev_trans.astype(np.float32)  # :461 (use_ego_vel = false, msf_delta = I)
         r = self.reg.align(guess)  # :465
         self.iterations.append(r["iterations"])
@@ -92,7 +94,7 @@ class ScanMatchingOdometry:
             self.prev_trans = trans
         if self.updater.decide(odom):  # :583-600
             self.keyframe_cloud = cloud
-            self.reg.set_input_target(cloud)
+            self.reg.set_input_target(cloud, key=cloud.ctypes.data)
             self.keyframe_pose = odom
             self.prev_trans = np.eye(4)
             self.n_keyframes += 1

@@ -412,6 +412,26 @@ def test_clear_and_cache_key(gorio, c1):
     _check_align(g, o)
 
 
+def test_promotion_of_the_source_to_target_reuses_its_covariances(gorio, synth, c2_small):
+    """scan_matching_odometry_nodelet.cpp:587-588: the registered frame becomes the keyframe. Same cache key as the
+    source -> grid and covariances are copied, not rebuilt; results are those of a fresh handle."""
+    src, tgt, _ = c2_small
+    nxt = src[::2].copy()
+    g, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+    g.set_input_source(src, key=7)
+    _check_align(g, o)
+    k0 = g.kernel_ms()["knn_cov"][1]
+    g.set_input_target(src, key=7); o.set_input_target(src)  # promotion
+    assert g.kernel_ms()["knn_cov"][1] == k0
+    assert np.array_equal(g.get_target_covariances(), g.get_source_covariances())
+    g.set_input_source(nxt, key=8); o.set_input_source(nxt)
+    _check_align(g, o)
+    k1 = g.kernel_ms()["knn_cov"][1]
+    fresh, _ = make(gorio, nxt, src, **DEPLOYED, maha_fp64=1)
+    assert np.array_equal(fresh.align()["T64"], g.align()["T64"])
+    assert k1 - k0 == (fresh.kernel_ms()["knn_cov"][1]) // 2  # only the new source needed a kNN pass
+
+
 def test_pcl_xyzinormal_layout(gorio, synth, c1):
     src, tgt, _ = c1
     g = gorio.FastAPDGICP(0)
