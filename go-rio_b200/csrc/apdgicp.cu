@@ -171,6 +171,10 @@ struct apd_handle {
   // per-linearisation state (sorted order of the source)
   DevBuf corr, sqd, mahaA, mahaB;
   int corr_n = -1;          // number of source points the buffers describe (-1: none yet)
+  // warm start of update_correspondences: the buffers hold a pass over the CURRENT clouds at corr_pose with corr_thr
+  bool corr_warm = false;
+  PoseD corr_pose{};
+  double corr_thr = 0.0;
   int corr_fp64 = 0;
   // scratch
   DevBuf work, scratch, partials, small;  // small: out28 + ticket + fitness
@@ -573,11 +577,16 @@ int do_update_correspondences(apd_handle* h, const hm::Pose& T) {
   const NoiseParams np = noise_params(h->params);
   {
     ProfScope ps(h, APD_K_CORR);
+    const bool warm = h->corr_warm && h->corr_n == h->src.n && h->corr_thr == h->params.max_correspondence_distance;
     for (int j = 0; j < h->shard_subs(); j++)
-      launch_update_correspondences(h->src_slice(j), h->tgt.view(), to_pose_d(T), np, corr_view(h, j), h->stream, &h->launches);
+      launch_update_correspondences(h->src_slice(j), h->tgt.view(), to_pose_d(T), np, corr_view(h, j), warm ? &h->corr_pose : nullptr,
+                                    h->stream, &h->launches);
   }
   APD_CUDA(h, cudaGetLastError());
   h->corr_n = h->src.n;
+  h->corr_warm = true;
+  h->corr_pose = to_pose_d(T);
+  h->corr_thr = h->params.max_correspondence_distance;
   return APD_OK;
 }
 
@@ -755,6 +764,7 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
     Cloud& other = (&c == &h->src) ? h->tgt : h->src;
     if (key != 0 && other.present && other.key == key && other.n == n) {
       h->corr_n = -1;
+      h->corr_warm = false;
       return adopt_cloud(h, c, other);
     }
   }
@@ -781,6 +791,7 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
   c.grid_valid = false;
   c.cov_valid = false;  // source_covs_.clear() (:122,:133)
   c.geo_valid = false;
+  h->corr_warm = false;
   return APD_OK;
 }
 
@@ -800,6 +811,7 @@ int set_cloud_device(apd_handle* h, Cloud& c, const void* d_xyzl, int32_t n) {
     std::memcpy(&c.bbox[a], &u, 4);
   }
   c.ext_pts = reinterpret_cast<const float4*>(d_xyzl);
+  h->corr_warm = false;
   c.n = n;
   c.present = true;
   c.key = 0;
@@ -945,6 +957,7 @@ int finish_device_align(apd_handle* h, const LmResult* r) {
   for (int a = 0; a < 4; a++)
     for (int c = 0; c < 4; c++) h->final_T[c * 4 + a] = (float)x0(a, c);  // lsq :78
   h->corr_n = h->src.n;
+  h->corr_warm = false;  // (the buffers hold the loop's last linearisation pose, which the host does not track)
   return APD_OK;
 }
 
@@ -1142,16 +1155,19 @@ int apd_swap_source_and_target(apd_handle* h) {  // :89-98
   if (!h) return APD_ERR_INVALID;
   std::swap(h->src, h->tgt);
   h->corr_n = -1;  // correspondences_.clear()
+  h->corr_warm = false;
   return APD_OK;
 }
 int apd_clear_source(apd_handle* h) {  // :101-105
   if (!h) return APD_ERR_INVALID;
+  h->corr_warm = false;
   h->src.present = false; h->src.n = 0; h->src.key = 0; h->src.ext_pts = nullptr;
   h->src.grid_valid = h->src.cov_valid = h->src.geo_valid = false;
   return APD_OK;
 }
 int apd_clear_target(apd_handle* h) {  // :108-112
   if (!h) return APD_ERR_INVALID;
+  h->corr_warm = false;
   h->tgt.present = false; h->tgt.n = 0; h->tgt.key = 0; h->tgt.ext_pts = nullptr;
   h->tgt.grid_valid = h->tgt.cov_valid = h->tgt.geo_valid = false;
   return APD_OK;
@@ -1532,6 +1548,7 @@ int apd_comm_init(apd_handle* h, const void* id128, int32_t rank, int32_t nranks
     APD_CUDA(h, wait_stream(h));
   }
   h->corr_n = -1;        // correspondences of the unsharded layout are no longer addressable
+  h->corr_warm = false;
   return APD_OK;
 }
 int apd_comm_peer_handle(apd_handle* h, void* handle64) {
@@ -1589,6 +1606,7 @@ int apd_comm_destroy(apd_handle* h) {
     g_nccl.CommDestroy(h->comm);
     h->comm = nullptr;
     h->corr_n = -1;
+    h->corr_warm = false;
   }
   h->comm_size = 1;
   h->comm_rank = 0;

@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(kThreads) update_corr_kernel(const float4* __r
                                                                const float4* __restrict__ t_spts, const float* __restrict__ t_label,
                                                                const double* __restrict__ t_cov, const uint32_t* __restrict__ t_cell_start,
                                                                GridDesc tg, PoseD T, NoiseParams np, int* __restrict__ corr,
-                                                               float* __restrict__ sqd, void* __restrict__ mahaA, void* __restrict__ mahaB) {
+                                                               float* __restrict__ sqd, void* __restrict__ mahaA, void* __restrict__ mahaB,
+                                                               int warm, PoseD T_prev) {
   // G lanes per source point (kThreads and the warp size are multiples of G, so a group never straddles a warp;
   // the grid is sized so that whole warps are either in range or carry clamped duplicates of the last point)
   const int gi = (blockIdx.x * kThreads + threadIdx.x) / G;
@@ -29,17 +30,30 @@ __global__ void __launch_bounds__(kThreads) update_corr_kernel(const float4* __r
   float px, py, pz;
   transform_rn(Tf, a.x, a.y, a.z, px, py, pz);  // :176
 
+  // warm: corr / sqd still hold the previous pass over the same clouds (pose T_prev) — see warm_start
+  int seed = -1;
+  if (warm) {
+    float kept;
+    if (!warm_start(pose_to_f32(T_prev), a, px, py, pz, corr[i], sqd[i], np.thr_sq, seed, kept)) {  // (uniform over the G lanes of a query)
+      nn_group_sync<G>();
+      if (gi < n_src && (G == 1 || (threadIdx.x & (G - 1)) == 0)) sqd[i] = kept;  // still unmatched; corr[i] stays -1
+      return;
+    }
+  }
   unsigned long long best;
   int pos;
-  nn_search<G>(t_spts, t_cell_start, tg, px, py, pz, np.thr_sq, best, pos);  // :178
+  float proven2;
+  nn_search<G>(t_spts, t_cell_start, tg, px, py, pz, np.thr_sq, best, pos, seed, proven2);  // :178
   if (gi >= n_src || (G > 1 && (threadIdx.x & (G - 1)) != 0)) return;  // one lane per point finishes the job
   const float d2 = (best == kInfKey) ? 3.402823466e38f : __uint_as_float((unsigned)(best >> 32));
-  sqd[i] = d2;  // :180
   const bool ok = (best != kInfKey) && ((double)d2 < np.thr_sq);  // :183
   if (!ok) {
     corr[i] = -1;
+    sqd[i] = fminf(d2, proven2);  // (:180 stores the found distance; for a rejected point this slot is write-only scratch in the
+                                  // reference — here it keeps the proven lower bound of its distance for the next warm start)
     return;
   }
+  sqd[i] = d2;  // :180
   corr[i] = pos | ((t_label[pos] == s_label[i]) ? kCorrLabelBit : 0);  // label test of :271-273, hoisted
 
   // radar noise covariance, combined covariance and its inverse (:194-218)
@@ -150,12 +164,12 @@ __global__ void __launch_bounds__(256) transform_cloud_kernel(const float4* __re
 }  // namespace
 
 void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const NoiseParams& np,
-                                   const CorrOut& out, cudaStream_t s, int64_t* launches) {
+                                   const CorrOut& out, const PoseD* T_prev, cudaStream_t s, int64_t* launches) {
   if (src.n <= 0) return;
 #define APD_CORR(FP64, GG)                                                                                                              \
   update_corr_kernel<FP64, GG><<<(unsigned)(((size_t)src.n * GG + kThreads - 1) / kThreads), kThreads, 0, s>>>(                           \
       src.spts, src.label, src.cov, src.n, tgt.spts, tgt.label, tgt.cov, tgt.cell_start, tgt.g, T, np, out.corr, out.sqd, out.mahaA, \
-      out.mahaB)
+      out.mahaB, T_prev ? 1 : 0, T_prev ? *T_prev : T)
   // small source clouds are latency-bound: 8 lanes share a query; large ones are throughput-bound: one lane per query.
   // APD_CORR_MODE = wide | lane forces one variant (tests, profiling); both give identical results.
   // (Tried and dropped, 20 M points on B200: staging the union box of a warp's 32 query cubes in shared memory with bulk

@@ -76,9 +76,10 @@ struct CorrOut {
   void* mahaB;    // float2[n] or double2[2n]
   int maha_fp64;
 };
-// reference update_correspondences (fast_apdgicp_impl.hpp:160-220)
+// reference update_correspondences (fast_apdgicp_impl.hpp:160-220). T_prev != nullptr: `out` still holds the result of
+// the previous pass over the same clouds at pose T_prev, which warm-starts the searches (identical results).
 void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const NoiseParams& np,
-                                   const CorrOut& out, cudaStream_t s, int64_t* launches);
+                                   const CorrOut& out, const PoseD* T_prev, cudaStream_t s, int64_t* launches);
 // getFitnessScore + inlier count: d_out = {sum d2 (double), n_in_range (as double), n_inliers (as double)}
 void launch_fitness(const CloudDev& src, const CloudDev& tgt, const PoseF& T, double max_range, double inlier_sq_thr,
                     double* d_partials, int max_blocks, double* d_out3, unsigned int* d_ticket, cudaStream_t s,

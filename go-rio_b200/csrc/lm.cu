@@ -70,6 +70,7 @@ struct LmShared {
   double part[2][kReduceVals];  // this CTA's partial sums, double-buffered across reductions
   double out[kReduceVals];      // cluster-wide sums (identical in every CTA)
   PoseD T;                      // pose the next phase evaluates
+  PoseD T_corr;                 // pose of the last update_correspondences pass (warm start of the next one)
   int flag_in, flag_out;        // LM trial decision / outer-loop decision (separate words: each is re-read across one barrier only)
   LmSerial ser;
 };
@@ -121,10 +122,12 @@ __device__ __forceinline__ void load_maha(const LmJob& job, int i, double m[6], 
 }
 
 // FastAPDGICP::update_correspondences (:160-220) for this CTA's points [base, base+cnt)
+// warm: job.corr / job.sqd hold the previous outer iteration's pass (pose T_prev), which bounds the searches
 template <bool kFp64>
-__device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg, const PoseD& T, int base, int cnt) {
-  if (cnt <= 0) return;
+__device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg, const PoseD& T, int base, int cnt, bool warm,
+                                           const PoseD& T_prev) {
   const PoseF Tf = pose_to_f32(T);
+  const PoseF Tpf = pose_to_f32(T_prev);
   const int tid = threadIdx.x;
   constexpr int kQ = kLmThreads / kLmG;  // queries per pass
   for (int p0 = 0; p0 < cnt; p0 += kQ) {
@@ -133,18 +136,41 @@ __device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg
     const float4 a = job.s_spts[i];
     float px, py, pz;
     transform_rn(Tf, a.x, a.y, a.z, px, py, pz);  // :176
+    int seed = -1;
+    if (warm) {
+      float kept;
+      if (!warm_start(Tpf, a, px, py, pz, job.corr[i], job.sqd[i], cfg.np.thr_sq, seed, kept)) {  // (uniform over the lanes of a query)
+        nn_group_sync<kLmG>();
+        if (q < cnt && (tid & (kLmG - 1)) == 0) job.sqd[i] = kept;  // provably still unmatched; corr[i] stays -1
+        continue;
+      }
+    }
     unsigned long long best;
     int pos;
-    nn_search<kLmG>(job.t_spts, job.t_cell_start, job.tg, px, py, pz, cfg.np.thr_sq, best, pos);  // :178
+    float proven2;
+    nn_search<kLmG>(job.t_spts, job.t_cell_start, job.tg, px, py, pz, cfg.np.thr_sq, best, pos, seed, proven2);  // :178
     if (q >= cnt || (tid & (kLmG - 1)) != 0) continue;
     const float d2 = (best == kInfKey) ? 3.402823466e38f : __uint_as_float((unsigned)(best >> 32));
-    job.sqd[i] = d2;  // :180
     const bool ok = (best != kInfKey) && ((double)d2 < cfg.np.thr_sq);  // :183
     if (!ok) {
       job.corr[i] = -1;
+      job.sqd[i] = fminf(d2, proven2);  // rejected: the proven lower bound of its distance (see corr.cu)
       continue;
     }
+    job.sqd[i] = d2;  // :180
     job.corr[i] = pos | ((job.t_label[pos] == job.s_label[i]) ? kCorrLabelBit : 0);
+  }
+  __syncthreads();
+  // second pass, one THREAD per point: the fp64 noise model and Mahalanobis matrix of the matched points (:194-218). In the
+  // search pass only one lane in kLmG holds a result; here all lanes work.
+  for (int q = tid; q < cnt; q += kLmThreads) {
+    const int i = base + q;
+    const int c = job.corr[i];
+    if (c < 0) continue;
+    const int pos = c & kCorrIndexMask;
+    const float4 a = job.s_spts[i];
+    float px, py, pz;
+    transform_rn(Tf, a.x, a.y, a.z, px, py, pz);
     const Sym3 M = mahalanobis_of(px, py, pz, job.s_cov + (size_t)i * 6, job.t_cov + (size_t)pos * 6, T, cfg.np);
     if (kFp64) {
       double2* mA = reinterpret_cast<double2*>(job.mahaA);
@@ -318,8 +344,9 @@ __global__ void __launch_bounds__(kLmThreads, APD_LM_MINB) lm_kernel(LmJob one, 
     // ---- linearize(x0) (:224-307) ----
     {
       const PoseD Tx0 = s.T;
-      corr_phase<kFp64>(job, cfg, Tx0, base, cnt);
-      __syncthreads();  // the correspondences of this CTA's points are visible to all of its threads
+      corr_phase<kFp64>(job, cfg, Tx0, base, cnt, it > 0, s.T_corr);
+      __syncthreads();  // the correspondences of this CTA's points are visible to all of its threads; T_corr has been read
+      if (tid == 0) s.T_corr = Tx0;
       sum_phase<kFp64, true>(job, Tx0, base, cnt, acc);
     }
     cluster_reduce<kReduceVals>(cluster, s, acc, phase);

@@ -30,6 +30,12 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ spts, int 
 // min-reduced with shuffles after every shell, so the critical path of a query is
 // ~1/G of the single-thread scan (small source clouds are latency-bound).
 // All G lanes return the same result.
+// barrier over the G lanes that share a query (all of them have finished reading what one of them is about to overwrite)
+template <int G>
+__device__ __forceinline__ void nn_group_sync() {
+  if (G > 1) __syncwarp((G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1))));
+}
+
 // min-reduce (best, best_pos) over the G lanes that share a query
 template <int G>
 __device__ __forceinline__ void nn_group_min(unsigned long long& best, int& best_pos) {
@@ -50,19 +56,28 @@ __device__ __forceinline__ void nn_group_min(unsigned long long& best, int& best
 
 // Shells r = 2, 3, ... around the query's cell (cx,cy,cz), given the best key over the radius-1 cube: continues until
 // the best distance is provably final or every unscanned point is farther than the limit.
+// proven2: on return every point that was NOT scanned is at least sqrt(min(proven2, best d2)) away.
 template <int G>
 __device__ __forceinline__ void nn_shells(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
                                           float qx, float qy, float qz, int cx, int cy, int cz, double limit_sq, unsigned long long& best,
-                                          int& best_pos) {
+                                          int& best_pos, float& proven2) {
   const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
   const float mg = 0.002f * g.cell;
+  // Rows inside a shell are skipped when they lie beyond 1.25 x the correspondence distance (not 1 x): the slack is what
+  // lets the next pass prove "still unmatched" after a small motion without searching again (warm_start).
+  const double prune_sq = limit_sq * 1.5625;
+  const float prune2 = prune_sq < 3.0e38 ? (float)prune_sq : 3.4e38f;
   // thick shells (r, rr]: one cell at a time near the query, then growing ~1.5x (see knn_cov.cu)
   for (int r = 1;;) {
     const float lb = ((float)r - 0.002f) * g.cell;
     const float lb2 = lb * lb;
+    proven2 = fminf(lb2, prune2);
     if (best != kInfKey && __uint_as_float((unsigned)(best >> 32)) < lb2) break;
     if ((double)lb2 >= limit_sq) break;
-    if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
+    if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) {
+      proven2 = prune2;  // the cube covers the grid; only rows skipped for their distance were left out
+      break;
+    }
     const int rr = r < 3 ? r + 1 : r + (r >> 1) + 1;
     const int side = 2 * rr + 1;
     const int x0 = max(cx - rr, 0), x1 = min(cx + rr, g.nx - 1);
@@ -75,7 +90,7 @@ __device__ __forceinline__ void nn_shells(const float4* __restrict__ spts, const
       const float loz = g.oz + (float)z * g.cell - mg, hiz = g.oz + (float)(z + 1) * g.cell + mg;
       const float ddy = fmaxf(0.f, fmaxf(loy - qy, qy - hiy)), ddz = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
       const float dyz2 = (ddy * ddy + ddz * ddz) * 0.9999f;
-      if ((double)dyz2 >= limit_sq) continue;
+      if ((double)dyz2 >= prune_sq) continue;
       if (best != kInfKey && dyz2 > __uint_as_float((unsigned)(best >> 32))) continue;
       const int row = (z * g.ny + y) * g.nx;
       if (dy > r || dy < -r || dz > r || dz < -r) {  // row outside the scanned cube: its whole x-range
@@ -91,27 +106,68 @@ __device__ __forceinline__ void nn_shells(const float4* __restrict__ spts, const
   }
 }
 
+// seed_pos >= 0: a target point (sorted position) to start from — the previous iteration's match. Its distance
+// bounds the search: rows of the cube whose box is farther are skipped, and the shells usually end at once.
+// The result is the same exact nearest neighbour by (d2, original index) with or without the seed.
 template <int G>
 __device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
-                                          float qx, float qy, float qz, double limit_sq, unsigned long long& best, int& best_pos) {
+                                          float qx, float qy, float qz, double limit_sq, unsigned long long& best, int& best_pos,
+                                          int seed_pos, float& proven2) {
   const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
   const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
   const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
   const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
   best = kInfKey;
   best_pos = -1;
+  if (seed_pos >= 0) {
+    const float4 p = __ldg(&spts[seed_pos]);
+    best = pack_key(sqdist_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+    best_pos = seed_pos;
+  }
   // ring 0+1: 3x3x3 cube as 9 x-rows
   {
+    const float mg = 0.002f * g.cell;
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
     for (int ri = sub; ri < 9; ri += G) {
       const int y = cy + (ri % 3) - 1, z = cz + (ri / 3) - 1;
       if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      if (best != kInfKey && ri != 4) {  // skip the row if even its nearest point cannot beat the current best (row 4 is the query's own)
+        const float loy = g.oy + (float)y * g.cell - mg, hiy = g.oy + (float)(y + 1) * g.cell + mg;
+        const float loz = g.oz + (float)z * g.cell - mg, hiz = g.oz + (float)(z + 1) * g.cell + mg;
+        const float ddy = fmaxf(0.f, fmaxf(loy - qy, qy - hiy)), ddz = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
+        if ((ddy * ddy + ddz * ddz) * 0.9999f > __uint_as_float((unsigned)(best >> 32))) continue;
+      }
       const int row = (z * g.ny + y) * g.nx;
       scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
     }
     nn_group_min<G>(best, best_pos);
   }
-  nn_shells<G>(spts, cell_start, g, qx, qy, qz, cx, cy, cz, limit_sq, best, best_pos);
+  nn_shells<G>(spts, cell_start, g, qx, qy, qz, cx, cy, cz, limit_sq, best, best_pos, proven2);
+}
+template <int G>
+__device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
+                                          float qx, float qy, float qz, double limit_sq, unsigned long long& best, int& best_pos) {
+  float proven2;
+  nn_search<G>(spts, cell_start, g, qx, qy, qz, limit_sq, best, best_pos, -1, proven2);
+}
+
+// Warm start of update_correspondences from the previous pass over the same clouds (pose T_prev): decides what the
+// search of source point `a` needs. Returns false when the point is PROVABLY still unmatched (no search needed):
+// it was unmatched with every target point at least sqrt(prev_sqd) away, it has moved by delta since, and
+// sqrt(prev_sqd) - delta still exceeds the correspondence distance (with a 1e-3 margin over the fp32 rounding of d2).
+// Otherwise seed_pos is the previous match (or -1) for nn_search.
+__device__ __forceinline__ bool warm_start(const PoseF& T_prev, const float4& a, float px, float py, float pz, int prev_corr, float prev_sqd,
+                                           double thr_sq, int& seed_pos, float& kept_sqd) {
+  seed_pos = prev_corr >= 0 ? (prev_corr & kCorrIndexMask) : -1;
+  if (prev_corr >= 0) return true;
+  float ox, oy, oz;
+  transform_rn(T_prev, a.x, a.y, a.z, ox, oy, oz);
+  const float delta = sqrtf(sqdist_rn(px, py, pz, ox, oy, oz)) * 1.0001f;
+  const float lb = sqrtf(prev_sqd) * 0.9999f - delta;  // every target point is at least this far from the moved point
+  const float thr = (float)sqrt(thr_sq) * 1.001f;
+  if (!(prev_sqd < 3.0e38f) || !(lb > thr)) return true;  // no usable bound, or too close to call: search
+  kept_sqd = lb * lb;
+  return false;
 }
 
 __device__ __forceinline__ PoseF pose_to_f32(const PoseD& T) {

@@ -217,7 +217,10 @@ def test_update_correspondences_variants(gorio, synth, c2, monkeypatch, mode):
         if thr is not None:
             kw["max_correspondence_distance"] = thr
         g, o = make(gorio, src, tgt, **kw)
-        for T in (np.eye(4), Tgt, Tgt @ synth.make_pose([3.0, -2.0, 0.5], [0.02, -0.01, 0.3])):
+        # consecutive passes on one handle warm-start from the previous one (seeded searches, provably-unmatched points
+        # skipped): small LM-like steps, a return to an earlier pose, and a jump far away must all stay exact
+        steps = [Tgt @ synth.make_pose([0.02 * i, -0.01 * i, 0.005], [0.0, 0.001 * i, -0.002 * i]) for i in range(1, 5)]
+        for T in [np.eye(4), Tgt] + steps + [Tgt, Tgt @ synth.make_pose([3.0, -2.0, 0.5], [0.02, -0.01, 0.3]), steps[0]]:
             g.update_correspondences(T); o.update_correspondences(T)
             cg, sg = g.get_correspondences()
             co, so = o.get_correspondences()
