@@ -131,6 +131,13 @@ struct Cloud {
   bool grid_valid = false;
   bool cov_valid = false;
   bool geo_valid = false;
+  // Covariances on demand (target of the device-resident loop): cov[w] is valid where cov_flag[w] == 1; computed with
+  // lazy_k / lazy_reg, the parameters in force when the cloud's first covariance was asked for (the reference computes
+  // all target covariances at that moment and keeps them across later parameter changes)
+  DevBuf cov_flag;
+  bool cov_lazy = false;
+  int lazy_k = 0, lazy_reg = 0;
+  void drop_derived() { grid_valid = cov_valid = geo_valid = cov_lazy = false; }
   CloudDev view() const {
     CloudDev c;
     c.n = n;
@@ -148,6 +155,7 @@ struct Cloud {
   }
   void release() {
     pts.release(); spts.release(); label.release(); inv_perm.release(); cov.release(); geo.release(); geo64.release(); cell_start.release();
+    cov_flag.release();
     stage.release();
     if (staged) cudaEventDestroy(staged);
     staged = nullptr;
@@ -224,6 +232,11 @@ struct apd_handle {
   // 1 warp, 2 thread. Override with APD_KNN_MODE=warp|thread.
   int knn_mode = 0;
   int knn_thread_min_n = 500000;
+  // Target covariances on demand inside the device-resident loop (see Cloud::cov_lazy): 0 never, 1 whenever the loop
+  // runs, -1 auto: when the target has at least lazy_min_ratio x the source's points (a scan against a submap matches a
+  // few percent of the submap). APD_LAZY_TARGET_COV=0|1|auto.
+  int lazy_mode = -1;
+  int lazy_min_ratio = 4;
   int knn_max_k() const { return knn_mode == 1 ? 32 : 128; }
   bool knn_use_warp(int n, int k) const { return knn_mode == 1 || (knn_mode == 0 && k <= 32 && n < knn_thread_min_n); }
   // Sharded handle (apd_comm_init): every rank holds both FULL clouds and grids. The cell-sorted points of a cloud are
@@ -510,7 +523,9 @@ int ensure_covariances_of(apd_handle* h, Cloud& c) {
   // all-gathered (the target's are gathered through arbitrary correspondences, and a swap can make either cloud the
   // target). The geometric weight is only ever read for the rank's own slice of the source, so it stays local.
   if (!c.cov_valid) {
-    const int k = h->params.k_correspondences;
+    // a cloud whose covariances were started on demand is completed with the parameters they were started with
+    const int k = c.cov_lazy ? c.lazy_k : h->params.k_correspondences;
+    const int reg = c.cov_lazy ? c.lazy_reg : h->params.regularization;
     if (k < 1 || k > h->knn_max_k()) return fail(h, APD_ERR_UNSUPPORTED, "k_correspondences out of range (1..128; 1..32 in warp mode)");
     if (c.n < k) return fail(h, APD_ERR_TOO_FEW, "cloud has fewer points than k_correspondences");
     ProfScope ps(h, APD_K_KNN_COV);
@@ -519,9 +534,9 @@ int ensure_covariances_of(apd_handle* h, Cloud& c) {
       const int w0 = h->sub_begin(c.n, j), wn = h->sub_count(c.n, j);
       if (h->knn_use_warp(c.n, k)) {
         launch_knn_cov(c.view(), k, h->nbuf.as<int32_t>(), nullptr, h->stream, &h->launches, w0, wn);
-        launch_cov_regularize(c.view(), k, h->params.regularization, h->nbuf.as<int32_t>(), h->stream, &h->launches, w0, wn);
+        launch_cov_regularize(c.view(), k, reg, h->nbuf.as<int32_t>(), h->stream, &h->launches, w0, wn);
       } else {
-        launch_knn_cov_fused(c.view(), k, h->params.regularization, nullptr, h->stream, &h->launches, w0, wn);
+        launch_knn_cov_fused(c.view(), k, reg, nullptr, h->stream, &h->launches, w0, wn);
       }
     }
     if (h->comm) {
@@ -530,6 +545,7 @@ int ensure_covariances_of(apd_handle* h, Cloud& c) {
     }
     c.cov_valid = true;
     c.geo_valid = true;
+    c.cov_lazy = false;
   } else if (!c.geo_valid) {  // after set*Covariances: every rank holds all covariances, the weight is a local map
     ProfScope ps(h, APD_K_KNN_COV);
     launch_geo_weight(c.view(), h->stream, &h->launches);
@@ -544,6 +560,34 @@ int ensure_covariances(apd_handle* h) {
   int rc = ensure_covariances_of(h, h->src);  // :149-151
   if (rc != APD_OK) return rc;
   return ensure_covariances_of(h, h->tgt);    // :152-154
+}
+
+bool use_device_loop(const apd_handle* h);
+
+// computeTransformation's covariance step (:148-157) for the device-resident loop: the source's covariances now, the
+// target's on demand inside the loop when that pays (lm.cu: corr_phase). Same values either way.
+int ensure_covariances_for_loop(apd_handle* h) {
+  if (!h->src.present || !h->tgt.present) return fail(h, APD_ERR_INVALID, "source or target cloud not set");
+  Cloud& t = h->tgt;
+  const int k = t.cov_lazy ? t.lazy_k : h->params.k_correspondences;
+  const bool lazy = !t.cov_valid && t.n > 0 && k >= 1 && k <= 32 && t.n >= k &&
+                    (t.cov_lazy || h->lazy_mode == 1 || (h->lazy_mode < 0 && (long long)t.n >= (long long)h->lazy_min_ratio * h->src.n));
+  if (!lazy) return ensure_covariances(h);
+  int rc = ensure_covariances_of(h, h->src);
+  if (rc != APD_OK) return rc;
+  rc = ensure_grid(h, t);
+  if (rc != APD_OK) return rc;
+  APD_CUDA(h, t.cov.ensure((size_t)t.n * 6 * sizeof(double)));
+  APD_CUDA(h, t.cov_flag.ensure((size_t)t.n));
+  APD_CUDA(h, h->nbuf.ensure((size_t)std::max(h->src.n, 1) * k * sizeof(int32_t)));
+  if (!t.cov_lazy) {
+    APD_CUDA(h, cudaMemsetAsync(t.cov_flag.p, 0, (size_t)t.n, h->stream));
+    t.cov_lazy = true;
+    t.lazy_k = k;
+    t.lazy_reg = h->params.regularization;
+    t.geo_valid = false;
+  }
+  return APD_OK;
 }
 
 int ensure_small(apd_handle* h) {
@@ -753,6 +797,7 @@ int adopt_cloud(apd_handle* h, Cloud& dst, const Cloud& src) {
   dst.grid_valid = src.grid_valid;
   dst.cov_valid = src.grid_valid && src.cov_valid;
   dst.geo_valid = dst.cov_valid && src.geo_valid;
+  dst.cov_lazy = false;  // (a partly computed target is not adopted: the new owner computes what it needs)
   return APD_OK;
 }
 
@@ -791,6 +836,7 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
   c.grid_valid = false;
   c.cov_valid = false;  // source_covs_.clear() (:122,:133)
   c.geo_valid = false;
+  c.cov_lazy = false;
   h->corr_warm = false;
   return APD_OK;
 }
@@ -818,6 +864,7 @@ int set_cloud_device(apd_handle* h, Cloud& c, const void* d_xyzl, int32_t n) {
   c.grid_valid = false;
   c.cov_valid = false;
   c.geo_valid = false;
+  c.cov_lazy = false;
   return APD_OK;
 }
 
@@ -835,6 +882,7 @@ int set_covs(apd_handle* h, Cloud& c, const double* covs, int32_t n) {
   APD_CUDA(h, wait_stream(h));
   c.cov_valid = true;
   c.geo_valid = false;
+  c.cov_lazy = false;
   return APD_OK;
 }
 
@@ -926,6 +974,14 @@ LmJob lm_job(apd_handle* h, const hm::Pose& x0) {
     j.guess[9 + r] = x0(r, 3);
   }
   j.result = h->lm_result.as<LmResult>();
+  if (h->tgt.cov_lazy && !h->tgt.cov_valid) {  // target covariances on demand
+    j.t_cov_flag = h->tgt.cov_flag.as<unsigned char>();
+    j.t_cov_rw = t.cov;
+    j.t_pts = t.pts;
+    j.nb = h->nbuf.as<int32_t>();
+    j.k = h->tgt.lazy_k;
+    j.reg = h->tgt.lazy_reg;
+  }
   return j;
 }
 
@@ -979,7 +1035,7 @@ int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg)
 }
 
 int do_align(apd_handle* h, const float* guess) {
-  int rc = ensure_covariances(h);  // FastAPDGICP::computeTransformation (:148-157)
+  int rc = use_device_loop(h) ? ensure_covariances_for_loop(h) : ensure_covariances(h);  // FastAPDGICP::computeTransformation (:148-157)
   if (rc != APD_OK) return rc;
   h->fit_valid = false;
   if (use_device_loop(h)) {
@@ -1088,6 +1144,7 @@ int apd_create(int device, apd_handle** out) {
   }
   if (const char* e = std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = std::atoi(e) != 0;
   if (const char* e = std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = std::atoi(e);
+  if (const char* e = std::getenv("APD_LAZY_TARGET_COV")) h->lazy_mode = std::strcmp(e, "auto") == 0 ? -1 : (std::atoi(e) != 0 ? 1 : 0);
   if (const char* e = std::getenv("APD_KNN_MODE")) h->knn_mode = std::strcmp(e, "warp") == 0 ? 1 : (std::strcmp(e, "thread") == 0 ? 2 : 0);
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   for (int i = 0; i < 36; i++) h->final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity()
@@ -1162,14 +1219,14 @@ int apd_clear_source(apd_handle* h) {  // :101-105
   if (!h) return APD_ERR_INVALID;
   h->corr_warm = false;
   h->src.present = false; h->src.n = 0; h->src.key = 0; h->src.ext_pts = nullptr;
-  h->src.grid_valid = h->src.cov_valid = h->src.geo_valid = false;
+  h->src.drop_derived();
   return APD_OK;
 }
 int apd_clear_target(apd_handle* h) {  // :108-112
   if (!h) return APD_ERR_INVALID;
   h->corr_warm = false;
   h->tgt.present = false; h->tgt.n = 0; h->tgt.key = 0; h->tgt.ext_pts = nullptr;
-  h->tgt.grid_valid = h->tgt.cov_valid = h->tgt.geo_valid = false;
+  h->tgt.drop_derived();
   return APD_OK;
 }
 

@@ -144,6 +144,14 @@ struct LmJob {
   double cl_w;         // 1 / correspondences_.size() (:273)
   double guess[12];    // r[9] row-major, t[3]
   LmResult* result;    // device memory
+  // Target covariances on demand (t_cov_flag != nullptr): only the target points that become correspondences ever need
+  // one (a scan matches ~2 k of a 60 k-point submap), so the loop computes the covariance of a matched target point the
+  // first time it meets it — same kNN search, same arithmetic, same bits as the per-cloud kernels (knn_warp.cuh).
+  unsigned char* t_cov_flag;  // [n_tgt] 1: t_cov_rw[pos] is valid. nullptr: all target covariances are (eager)
+  double* t_cov_rw;           // = t_cov, writable
+  const float4* t_pts;        // target in ORIGINAL order (the covariance gathers its neighbours there)
+  int32_t* nb;                // [n_src][k] scratch: neighbour ids between the search pass and the covariance pass
+  int k, reg;                 // k_correspondences_, regularization_method_
 };
 struct LmConfig {
   int max_iterations, optimizer, lm_max_iterations, maha_fp64, want_fitness;

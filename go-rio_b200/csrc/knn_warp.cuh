@@ -1,0 +1,286 @@
+// Warp-cooperative exact kNN of ONE point of a cell-sorted cloud, and the covariance / regularisation of a point given
+// its neighbour list — shared by the per-cloud kernels (knn_cov.cu) and by the device-resident optimizer loop (lm.cu),
+// which computes target covariances on demand. One definition, so a covariance has the same bits whoever computes it.
+#pragma once
+#include "kernels.cuh"
+
+namespace apd {
+namespace knnw {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned long long kInfKey = 0xffffffffffffffffull;  // (same value as apd::kInfKey in point_math.cuh)
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+  return __shfl_sync(kFull, v, src);
+}
+__device__ __forceinline__ unsigned long long shfl_up64(unsigned long long v, int d) {
+  return __shfl_up_sync(kFull, v, d);
+}
+
+__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
+
+// ascending bitonic sort of one 64-bit key per lane
+__device__ __forceinline__ unsigned long long bitonic_sort32(unsigned long long key, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(kFull, key, stride);
+      const bool up = (lane & size) == 0;        // this block sorts ascending
+      const bool lower = (lane & stride) == 0;   // this lane is the lower one of the pair
+      key = (lower == up) ? umin64(key, other) : umax64(key, other);
+    }
+  }
+  return key;
+}
+// list (ascending, one key per lane) <- the 32 smallest of list U batch (batch ascending)
+__device__ __forceinline__ unsigned long long merge_keep32(unsigned long long list, unsigned long long batch, int lane) {
+  const unsigned long long rb = shfl64(batch, 31 - lane);
+  unsigned long long c = umin64(list, rb);  // bitonic sequence holding the 32 smallest
+#pragma unroll
+  for (int stride = 16; stride > 0; stride >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(kFull, c, stride);
+    c = ((lane & stride) == 0) ? umin64(c, other) : umax64(c, other);
+  }
+  return c;
+}
+
+// Per-warp state of the k-best search: `list` holds the 32 smallest keys seen so far
+// (ascending over the lanes; the answer is lanes 0..k-1), `kth` the k-th of them, and
+// `buf` (shared memory, 32 keys) collects candidates below `kth` until they are merged
+// in one bitonic sort + merge — ~6 instructions per candidate instead of ~22 for
+// inserting them one by one.
+struct KBest {
+  unsigned long long list, kth;
+  unsigned long long* buf;
+  int buf_n;
+  bool empty;  // list holds no key yet
+};
+__device__ __forceinline__ void kbest_flush(KBest& s, int lane, int k) {
+  if (s.buf_n == 0) return;  // warp-uniform
+  __syncwarp();
+  unsigned long long b = lane < s.buf_n ? s.buf[lane] : kInfKey;
+  __syncwarp();
+  b = bitonic_sort32(b, lane);
+  s.list = s.empty ? b : merge_keep32(s.list, b, lane);  // nothing to merge with on the first flush
+  s.empty = false;
+  s.kth = shfl64(s.list, k - 1);
+  s.buf_n = 0;
+}
+
+// Warp-wide candidate scan. Every lane passes one segment [b, b+cnt) of the
+// cell-sorted point array (cnt may be 0). The segments are flattened so that
+// all 32 lanes test candidates even when segments are short (sparse cells).
+__device__ __forceinline__ void scan_segments(const float4* __restrict__ spts, float qx, float qy, float qz, int lane, int k,
+                                              int b, int cnt, KBest& s) {
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(kFull, incl, 31);
+  const int excl = incl - cnt;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < total; base += 32) {
+    const int t = base + lane;
+    const bool valid = t < total;
+    const int tt = valid ? t : total - 1;
+    // segment containing flat index tt: first lane whose inclusive prefix > tt
+    int j = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(kFull, incl, j + step - 1);
+      if (v <= tt) j += step;
+    }
+    const int bj = __shfl_sync(kFull, b, j);
+    const int ej = __shfl_sync(kFull, excl, j);
+    const float4 p = spts[bj + (tt - ej)];
+    const float d2 = sqdist_rn(qx, qy, qz, p.x, p.y, p.z);
+    const unsigned long long key = pack_key(d2, __float_as_int(p.w));
+    bool pass = valid && key < s.kth;
+    unsigned mask = __ballot_sync(kFull, pass);
+    int m = __popc(mask);
+    if (m == 0) continue;
+    if (s.buf_n + m > 32) {
+      kbest_flush(s, lane, k);
+      pass = pass && key < s.kth;  // the threshold just dropped
+      mask = __ballot_sync(kFull, pass);
+      m = __popc(mask);
+    }
+    if (pass) s.buf[s.buf_n + __popc(mask & lt)] = key;
+    s.buf_n += m;
+  }
+}
+
+// Exact k nearest neighbours (ties by (d2, index)) of sorted point w, by the 32 lanes of one warp. Returns one
+// (d2, original index) key per lane, ascending: lanes 0..k-1 hold the answer. kbuf: 32 keys of shared memory owned by
+// this warp. Replaces the nearestKSearch of reference fast_apdgicp_impl.hpp:364.
+__device__ __forceinline__ unsigned long long knn_warp_query(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start,
+                                                             const GridDesc& g, int k, int w, int lane, unsigned long long* kbuf) {
+  const float4 q = spts[w];
+  const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz);
+
+  KBest st;
+  st.list = kInfKey;
+  st.kth = kInfKey;
+  st.buf = kbuf;
+  st.buf_n = 0;
+  st.empty = true;
+
+  // ring 0+1: the 3x3x3 cube as 9 x-rows
+  {
+    int b = 0, cnt = 0;
+    if (lane < 9) {
+      // rows nearest first (centre, the 4 face rows, the 4 corner rows) so that the first
+      // 32 candidates already give a tight k-th distance: packed 2-bit (dy+1, dz+1) codes
+      // dy = {0,-1,1,0,0,-1,1,-1,1}[lane], dz = {0,0,0,-1,1,-1,-1,1,1}[lane]
+      const int y = cy + (int)((0x22161u >> (2 * lane)) & 3u) - 1, z = cz + (int)((0x28215u >> (2 * lane)) & 3u) - 1;
+      if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+        const int row = (z * g.ny + y) * g.nx;
+        b = (int)cell_start[row + x0];
+        cnt = (int)cell_start[row + x1 + 1] - b;
+      }
+    }
+    scan_segments(spts, q.x, q.y, q.z, lane, k, b, cnt, st);
+    kbest_flush(st, lane, k);
+  }
+  // shells r = 2, 3, ... until the k-th distance is provably final:
+  // every unscanned point is at least (r - 0.002) cells away.
+  // Thick shells: after the cube of radius r has been scanned, the next step scans radius (r, rr]. One cell at a
+  // time near the query (where most searches end), then growing by ~1.5x: an x-row segment costs the same however
+  // many cells it spans, so a search that must reach R cells costs O(R^2) segments instead of O(R^3).
+  for (int r = 1;;) {
+    const float lb = ((float)r - 0.002f) * g.cell;
+    const float kd2 = __uint_as_float((unsigned)(st.kth >> 32));
+    if (st.kth != kInfKey && kd2 < lb * lb) break;
+    if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
+    const int rr = r < 3 ? r + 1 : r + (r >> 1) + 1;  // outer radius of the shell to scan now
+    const int side = 2 * rr + 1;
+    const int nslots = 2 * side * side;
+    const float inv_side = 1.0f / (float)side;
+    for (int sbase = 0; sbase < nslots; sbase += 32) {
+      const int slot = sbase + lane;
+      const float kd2cur = __uint_as_float((unsigned)(st.kth >> 32));  // shrinks as the shell is scanned
+      int b = 0, cnt = 0;
+      if (slot < nslots) {
+        const int rowid = slot >> 1, which = slot & 1;
+        const int qz = __float2int_rd(((float)rowid + 0.5f) * inv_side);  // rowid / side (exact for these small integers)
+        const int dy = rowid - qz * side - rr, dz = qz - rr;
+        const int y = cy + dy, z = cz + dz;
+        if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+          const bool outer = (dy > r) || (dy < -r) || (dz > r) || (dz < -r);  // row lies outside the scanned cube
+          const int row = (z * g.ny + y) * g.nx;
+          int x0 = 1, x1 = 0;
+          if (outer) {
+            if (which == 0) { x0 = max(cx - rr, 0); x1 = min(cx + rr, g.nx - 1); }
+          } else if (which == 0) {
+            x0 = max(cx - rr, 0); x1 = min(cx - r - 1, g.nx - 1);
+          } else {
+            x0 = max(cx + r + 1, 0); x1 = min(cx + rr, g.nx - 1);
+          }
+          if (x0 <= x1) {
+            // prune the segment if its (slightly grown) box is farther than the current k-th distance
+            const float m = 0.002f * g.cell;
+            const float lox = g.ox + (float)x0 * g.cell - m, hix = g.ox + (float)(x1 + 1) * g.cell + m;
+            const float loy = g.oy + (float)y * g.cell - m, hiy = g.oy + (float)(y + 1) * g.cell + m;
+            const float loz = g.oz + (float)z * g.cell - m, hiz = g.oz + (float)(z + 1) * g.cell + m;
+            const float ddx = fmaxf(0.f, fmaxf(lox - q.x, q.x - hix));
+            const float ddy = fmaxf(0.f, fmaxf(loy - q.y, q.y - hiy));
+            const float ddz = fmaxf(0.f, fmaxf(loz - q.z, q.z - hiz));
+            const float mind2 = (ddx * ddx + ddy * ddy + ddz * ddz) * 0.9999f;
+            if (st.kth == kInfKey || !(mind2 > kd2cur)) {
+              b = (int)cell_start[row + x0];
+              cnt = (int)cell_start[row + x1 + 1] - b;
+            }
+          }
+        }
+      }
+      if (__ballot_sync(kFull, cnt > 0)) scan_segments(spts, q.x, q.y, q.z, lane, k, b, cnt, st);
+    }
+    kbest_flush(st, lane, k);
+    r = rr;
+  }
+  return st.list;
+}
+
+__device__ __forceinline__ double geo_weight_of(const Sym3& C) {
+  double l[3], V[9];
+  jacobi_eig3(C, l, V);
+  return fabs(l[2]) / fabs(l[0]);  // sigma3 / sigma1 (reference :268-269)
+}
+
+// regularisation of one covariance (reference :374-405), symmetric storage
+__device__ __forceinline__ Sym3 regularize_sym3(const Sym3& C, int reg) {
+  Sym3 out = C;
+  if (reg == 0) {  // NONE (:374-376)
+  } else if (reg == 4) {  // FROBENIUS (:377-383)
+    Sym3 Cl = C;
+    Cl.v[0] += 1e-3; Cl.v[3] += 1e-3; Cl.v[5] += 1e-3;
+    Sym3 Ci = sym_inverse(Cl);
+    const double nrm = sqrt(Ci.v[0] * Ci.v[0] + Ci.v[3] * Ci.v[3] + Ci.v[5] * Ci.v[5] +
+                            2.0 * (Ci.v[1] * Ci.v[1] + Ci.v[2] * Ci.v[2] + Ci.v[4] * Ci.v[4]));
+#pragma unroll
+    for (int e = 0; e < 6; e++) Ci.v[e] /= nrm;
+    out = sym_inverse(Ci);
+  } else {  // SVD-based (:384-407); symmetric PSD input, so U = V up to the sign of negative eigenvalues
+    double l[3], V[9];
+    jacobi_eig3(C, l, V);
+    double val[3], sg[3];
+#pragma unroll
+    for (int e = 0; e < 3; e++) sg[e] = l[e] < 0.0 ? -1.0 : 1.0;
+    const double s0 = fabs(l[0]);
+    if (reg == 3) { val[0] = 1.0; val[1] = 1.0; val[2] = 1e-3; }                                   // PLANE
+    else if (reg == 1) { for (int e = 0; e < 3; e++) val[e] = fmax(fabs(l[e]), 1e-3); }              // MIN_EIG
+    else { for (int e = 0; e < 3; e++) val[e] = fmax(fabs(l[e]) / s0, 1e-3); }                       // NORMALIZED_MIN_EIG
+    // U diag(val) V^T with U = V * diag(sg); stored symmetric (upper triangle)
+    const int R[6] = {0, 0, 0, 1, 1, 2}, Cc[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+    for (int e = 0; e < 6; e++) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < 3; j++) s += sg[j] * V[R[e] * 3 + j] * val[j] * V[Cc[e] * 3 + j];
+      out.v[e] = s;
+    }
+  }
+  return out;
+}
+
+// Covariance of the k neighbours `ids` (original point ids, ascending by (d2, index)) of one point (reference :366-372:
+// fp64, centred, divided by k; sums in neighbour order with one rounding per operation — the CPU path's operation order,
+// so the raw covariance is bit-identical to the oracle's), then the regularisation (:374-405).
+// pts: the cloud in ORIGINAL order. IdT: any indexable list of k ints.
+template <typename IdT>
+__device__ __forceinline__ Sym3 covariance_of_neighbors(const float4* __restrict__ pts, const IdT& ids, int k, int reg) {
+  double mx = 0.0, my_ = 0.0, mz = 0.0;
+  for (int j = 0; j < k; j++) {
+    const float4 p = __ldg(&pts[ids[j]]);
+    mx = __dadd_rn(mx, (double)p.x);
+    my_ = __dadd_rn(my_, (double)p.y);
+    mz = __dadd_rn(mz, (double)p.z);
+  }
+  mx /= (double)k; my_ /= (double)k; mz /= (double)k;
+  Sym3 C;
+#pragma unroll
+  for (int e = 0; e < 6; e++) C.v[e] = 0.0;
+  for (int j = 0; j < k; j++) {
+    const float4 p = __ldg(&pts[ids[j]]);
+    const double dx = __dsub_rn((double)p.x, mx), dy = __dsub_rn((double)p.y, my_), dz = __dsub_rn((double)p.z, mz);
+    C.v[0] = __dadd_rn(C.v[0], __dmul_rn(dx, dx));
+    C.v[1] = __dadd_rn(C.v[1], __dmul_rn(dx, dy));
+    C.v[2] = __dadd_rn(C.v[2], __dmul_rn(dx, dz));
+    C.v[3] = __dadd_rn(C.v[3], __dmul_rn(dy, dy));
+    C.v[4] = __dadd_rn(C.v[4], __dmul_rn(dy, dz));
+    C.v[5] = __dadd_rn(C.v[5], __dmul_rn(dz, dz));
+  }
+#pragma unroll
+  for (int e = 0; e < 6; e++) C.v[e] /= (double)k;
+  return regularize_sym3(C, reg);
+}
+
+}  // namespace knnw
+}  // namespace apd

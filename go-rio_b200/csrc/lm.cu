@@ -18,6 +18,7 @@
 #include <cooperative_groups.h>
 
 #include "host_math.hpp"
+#include "knn_warp.cuh"
 #include "point_math.cuh"
 
 namespace cg = cooperative_groups;
@@ -71,6 +72,7 @@ struct LmShared {
   double out[kReduceVals];      // cluster-wide sums (identical in every CTA)
   PoseD T;                      // pose the next phase evaluates
   PoseD T_corr;                 // pose of the last update_correspondences pass (warm start of the next one)
+  unsigned long long kbuf[kLmWarps][32];  // on-demand target covariances: the kNN search's candidate buffer, per warp
   int flag_in, flag_out;        // LM trial decision / outer-loop decision (separate words: each is re-read across one barrier only)
   LmSerial ser;
 };
@@ -121,10 +123,20 @@ __device__ __forceinline__ void load_maha(const LmJob& job, int i, double m[6], 
   }
 }
 
+// covariance + regularisation of target point `pos` from its neighbour ids (the per-cloud kernels' code: same bits);
+// __noinline__ keeps the Jacobi sweep's registers out of the optimizer loop
+__device__ __noinline__ void lazy_target_covariance(const LmJob& job, const int32_t* nbq, int pos) {
+  const Sym3 C = knnw::covariance_of_neighbors(job.t_pts, nbq, job.k, job.reg);
+#pragma unroll
+  for (int e = 0; e < 6; e++) __stcg(job.t_cov_rw + (size_t)pos * 6 + e, C.v[e]);
+  __threadfence();
+  *((volatile unsigned char*)&job.t_cov_flag[pos]) = 1;
+}
+
 // FastAPDGICP::update_correspondences (:160-220) for this CTA's points [base, base+cnt)
 // warm: job.corr / job.sqd hold the previous outer iteration's pass (pose T_prev), which bounds the searches
 template <bool kFp64>
-__device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg, const PoseD& T, int base, int cnt, bool warm,
+__device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg, LmShared& smem, const PoseD& T, int base, int cnt, bool warm,
                                            const PoseD& T_prev) {
   const PoseF Tf = pose_to_f32(T);
   const PoseF Tpf = pose_to_f32(T_prev);
@@ -161,6 +173,39 @@ __device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg
     job.corr[i] = pos | ((job.t_label[pos] == job.s_label[i]) ? kCorrLabelBit : 0);
   }
   __syncthreads();
+  // Target covariances on demand (calculate_covariances(target), :351-411, restricted to the points that are used).
+  // Pass A, one WARP per matched point whose target has no covariance yet: the exact kNN search of the per-cloud kernel
+  // (knn_warp.cuh), neighbour ids to job.nb. Pass B, one THREAD per such point: covariance + regularisation. Two threads
+  // (or two registrations sharing a target) may compute the same point; they write the same bits, so the race is benign;
+  // the flag is published after the values, and readers take the values from L2 (__ldcg), never from a stale L1 line.
+  if (job.t_cov_flag) {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int q = warp; q < cnt; q += kLmWarps) {
+      const int c = job.corr[base + q];
+      int32_t* nbq = job.nb + (size_t)(base + q) * job.k;
+      bool need = false;
+      if (c >= 0) {
+        const int pos = c & kCorrIndexMask;
+        need = *((volatile unsigned char*)&job.t_cov_flag[pos]) == 0;
+        if (need) {
+          const unsigned long long key = knnw::knn_warp_query(job.t_spts, job.t_cell_start, job.tg, job.k, pos, lane, smem.kbuf[warp]);
+          if (lane < job.k) nbq[lane] = (int)(unsigned)(key & 0xffffffffull);
+        }
+      }
+      if (!need && lane == 0) nbq[0] = -1;
+      __syncwarp();
+    }
+    __threadfence();
+    __syncthreads();
+    for (int q = tid; q < cnt; q += kLmThreads) {
+      const int32_t* nbq = job.nb + (size_t)(base + q) * job.k;
+      if (nbq[0] < 0) continue;
+      const int pos = job.corr[base + q] & kCorrIndexMask;
+      lazy_target_covariance(job, nbq, pos);
+    }
+    __threadfence();
+    __syncthreads();
+  }
   // second pass, one THREAD per point: the fp64 noise model and Mahalanobis matrix of the matched points (:194-218). In the
   // search pass only one lane in kLmG holds a result; here all lanes work.
   for (int q = tid; q < cnt; q += kLmThreads) {
@@ -171,7 +216,15 @@ __device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg
     const float4 a = job.s_spts[i];
     float px, py, pz;
     transform_rn(Tf, a.x, a.y, a.z, px, py, pz);
-    const Sym3 M = mahalanobis_of(px, py, pz, job.s_cov + (size_t)i * 6, job.t_cov + (size_t)pos * 6, T, cfg.np);
+    double cb[6];
+    if (job.t_cov_flag) {
+#pragma unroll
+      for (int e = 0; e < 6; e++) cb[e] = __ldcg(job.t_cov + (size_t)pos * 6 + e);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 6; e++) cb[e] = job.t_cov[(size_t)pos * 6 + e];
+    }
+    const Sym3 M = mahalanobis_of(px, py, pz, job.s_cov + (size_t)i * 6, cb, T, cfg.np);
     if (kFp64) {
       double2* mA = reinterpret_cast<double2*>(job.mahaA);
       double2* mB = reinterpret_cast<double2*>(job.mahaB);
@@ -344,7 +397,7 @@ __global__ void __launch_bounds__(kLmThreads, APD_LM_MINB) lm_kernel(LmJob one, 
     // ---- linearize(x0) (:224-307) ----
     {
       const PoseD Tx0 = s.T;
-      corr_phase<kFp64>(job, cfg, Tx0, base, cnt, it > 0, s.T_corr);
+      corr_phase<kFp64>(job, cfg, s, Tx0, base, cnt, it > 0, s.T_corr);
       __syncthreads();  // the correspondences of this CTA's points are visible to all of its threads; T_corr has been read
       if (tid == 0) s.T_corr = Tx0;
       sum_phase<kFp64, true>(job, Tx0, base, cnt, acc);

@@ -326,6 +326,78 @@ def test_device_loop_cluster_sizes(gorio, c2_small, monkeypatch, cluster):
     assert dt < 1e-7 and dr < 1e-7, (dt, dr)
 
 
+def _handle(gorio, monkeypatch, lazy, src, tgt, **kw):
+    monkeypatch.setenv("APD_LAZY_TARGET_COV", lazy)
+    g = gorio.FastAPDGICP(0)
+    g.set_params(**kw)
+    g.set_input_target(tgt)
+    g.set_input_source(src)
+    return g
+
+
+@pytest.mark.parametrize("reg", ["PLANE", "MIN_EIG", "FROBENIUS"])
+def test_target_covariances_on_demand_are_the_eager_ones(gorio, c2, monkeypatch, reg):
+    """The device loop computes the covariance of a target point the first time a source point matches it
+    (APD_LAZY_TARGET_COV, default for scan-vs-submap sizes) instead of all 60 k up front: same kNN search, same
+    arithmetic -> the SAME BITS in every output, and one kNN launch less."""
+    src, tgt, _ = c2
+    kw = dict(**DEPLOYED, maha_fp64=1, regularization=REGS[reg])
+    ge = _handle(gorio, monkeypatch, "0", src, tgt, **kw)
+    gl = _handle(gorio, monkeypatch, "1", src, tgt, **kw)
+    re_, rl = ge.align(), gl.align()
+    assert np.array_equal(re_["T64"], rl["T64"]) and np.array_equal(re_["H"], rl["H"])
+    assert re_["iterations"] == rl["iterations"] and re_["converged"] == rl["converged"]
+    assert np.array_equal(ge.lm_trace(), gl.lm_trace())
+    assert np.array_equal(ge.get_correspondences()[0], gl.get_correspondences()[0])
+    assert np.array_equal(ge.get_mahalanobis(), gl.get_mahalanobis())
+    assert gl.kernel_ms()["knn_cov"][1] == ge.kernel_ms()["knn_cov"][1] // 2  # the source's pass only
+    # asking for all of them completes the cloud; the ones the loop made are not distinguishable
+    assert np.array_equal(ge.get_target_covariances(), gl.get_target_covariances())
+    if reg == "PLANE":
+        o = Oracle(search=1)
+        o.set_params(**kw)
+        o.set_input_target(tgt)
+        o.set_input_source(src)
+        _check_align(gl, o)
+
+
+def test_target_covariances_on_demand_persist_across_sources(gorio, synth, c2_small, monkeypatch):
+    """a keyframe target serves many scans: what one align computed the next one finds; a parameter change in between
+    does not touch covariances that exist (reference :152-154: target_covs_ is only computed when empty) and the rest
+    of the cloud is completed with the parameters the first align saw"""
+    src, tgt, _ = c2_small
+    kw = dict(max_correspondence_distance=2.0, maha_fp64=1)
+    ge = _handle(gorio, monkeypatch, "0", src, tgt, **kw)
+    gl = _handle(gorio, monkeypatch, "1", src, tgt, **kw)
+    o = Oracle(search=1)
+    o.set_params(**kw)
+    o.set_input_target(tgt)
+    o.set_input_source(src)
+    T = np.eye(4)
+    T[:3, 3] = [0.3, -0.2, 0.05]
+    sources = [src, src[::2].copy(), moved_copy(synth, src, T), src[1::3].copy()]
+    for i, s in enumerate(sources):
+        if i == 2:
+            for r in (ge, gl, o):
+                r.set_params(**kw, k_correspondences=10, regularization=REGS["MIN_EIG"])
+        for r in (ge, gl, o):
+            r.set_input_source(s)
+        re_, rl = ge.align(), gl.align()
+        assert np.array_equal(re_["T64"], rl["T64"]), i
+        assert np.array_equal(ge.get_mahalanobis(), gl.get_mahalanobis()), i
+        ro = o.align()
+        dt, dr = pose_err(rl["T64"], ro["T64"])
+        assert dt < 1e-6 and dr < 1e-6 and rl["iterations"] == ro["iterations"], (i, dt, dr)
+    assert np.array_equal(ge.get_target_covariances(), gl.get_target_covariances())
+    # swap: the partly covered target becomes the source and is completed
+    gl2 = _handle(gorio, monkeypatch, "1", src, tgt, **kw)
+    ge2 = _handle(gorio, monkeypatch, "0", src, tgt, **kw)
+    for g in (gl2, ge2):
+        g.align()
+        g.swap_source_and_target()
+    assert np.array_equal(ge2.align()["T64"], gl2.align()["T64"])
+
+
 def test_device_loop_tiny_and_ragged_sources(gorio, synth, c2_small):
     """fewer source points than CTAs x lanes, and counts that do not divide by the cluster size"""
     src, tgt, _ = c2_small
