@@ -33,6 +33,10 @@ import time
 
 import numpy as np
 
+# one hardware work queue per worker stream of the batch pool (read when the CUDA context is created, i.e. before torch
+# touches the GPU; libapdgicp.so sets the same default when it is loaded — see apdgicp.cu: apd_default_connections)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
@@ -47,11 +51,11 @@ BYTES_PER_POINT_KNNCOV = 68     # read point 16, write cov 48 + geo 4
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=256, help="scan/submap pairs per step and per GPU")
-    ap.add_argument("--streams", type=int, default=32, help="workers of the batch context (handle + CUDA stream + host thread each) per GPU")
+    ap.add_argument("--pairs", type=int, default=512, help="scan/submap pairs per step and per GPU (config C3: 4096 pairs over 8 GPUs)")
+    ap.add_argument("--streams", type=int, default=64, help="registrations in flight per GPU: handles (CUDA stream each) of the batch context, driven by a few host threads")
     ap.add_argument("--roofline-points", type=int, default=20_000_000)
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-reps", type=int, default=10)
@@ -152,28 +156,31 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.samples = []
-        self._stop = threading.Event()
-        self._t = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.05)
+        self._p = None
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        # ONE nvidia-smi process in loop mode (the recipe's clocks line): starting a process per sample re-initialises
+        # NVML every 50 ms and measurably slows kernel launches of the 32-64 worker threads being timed
+        try:
+            self._p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                        "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self._p = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self._p is None:
+            return
+        self._p.terminate()
+        try:
+            out, _ = self._p.communicate(timeout=6)
+        except Exception:
+            self._p.kill()
+            out = ""
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) >= 7:
+                self.samples.append(f)
 
     def summary(self):
         if not self.samples:
@@ -186,7 +193,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ our arm ----
-LM_RESULT_HEAD_BYTES = 1976  # apdgicp.cu kLmHeadBytes: pose, final hessian, flags and the first LM trace rows, per registration
+LM_RESULT_HEAD_BYTES = 1984  # apdgicp.cu kLmHeadBytes: pose, final hessian, flags and the first LM trace rows, per registration
 
 
 def run_c4(args):
@@ -354,7 +361,7 @@ def main():
 
         with ClockSampler(local_rank) as clocks:
             ms_dev, launches, results, cpu_dev = timed(prep_dev, args.steps, args.warmup)
-        ms_e2e, _, results_h, cpu_e2e = timed(prep_host, args.steps, args.warmup)
+            ms_e2e, _, results_h, cpu_e2e = timed(prep_host, args.steps, args.warmup)
         total_pairs = args.pairs * world
         value = total_pairs * args.steps / (ms_dev / 1e3)
         e2e_value = total_pairs * args.steps / (ms_e2e / 1e3)

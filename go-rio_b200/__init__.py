@@ -18,6 +18,9 @@ from ._binding import (  # noqa: F401
     OPT_GN, OPT_LM, REG_FROBENIUS, REG_MIN_EIG, REG_NONE, REG_NORMALIZED_MIN_EIG, REG_PLANE,
 )
 
+# see csrc/apdgicp.cu (apd_default_connections): one hardware work queue per worker stream; must precede the CUDA context
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.environ.get("APD_LIB") or os.path.join(PKG_DIR, "libapdgicp.so")  # APD_LIB: experiment builds

@@ -125,7 +125,11 @@ struct Cloud {
   DevBuf pts, spts, label, inv_perm, cov, geo, geo64, cell_start;
   PinnedBuf stage;                  // host AoS -> float4 staging for the H2D copy
   cudaEvent_t staged = nullptr;     // completion of the last H2D out of `stage`
+  unsigned long long staged_seq = 0;  // ... or: any kernel of the handle with a LATER sequence number has been seen to finish
+  bool staged_by_seq = false;
   const float4* ext_pts = nullptr;  // user-owned device cloud (apd_set_*_device)
+  bool bbox_pending = false;        // ... whose bounding box is still on its way back from the device (see finish_bboxes)
+  unsigned long long bbox_seq = 0;  // ... and the sequence number that announces it
   GridDesc g{};
   int ncells = 0;
   bool grid_valid = false;
@@ -136,8 +140,9 @@ struct Cloud {
   // all target covariances at that moment and keeps them across later parameter changes)
   DevBuf cov_flag;
   bool cov_lazy = false;
+  bool flags_fresh = false;  // the grid build that just ran cleared cov_flag
   int lazy_k = 0, lazy_reg = 0;
-  void drop_derived() { grid_valid = cov_valid = geo_valid = cov_lazy = false; }
+  void drop_derived() { grid_valid = cov_valid = geo_valid = cov_lazy = bbox_pending = false; }
   CloudDev view() const {
     CloudDev c;
     c.n = n;
@@ -190,17 +195,36 @@ struct apd_handle {
   PinnedBuf h_small;
   DevBuf lm_result;   // LmResult of the device-resident optimizer loop
   PinnedBuf h_lm;     // its header + first trace rows on the host
-  int lm_cluster = 4; // CTAs per registration in the device loop (APD_LM_CLUSTER=1|2|4|8)
+  // Zero-copy results: kernels publish small results (the loop's result header, a device cloud's bounding box) straight
+  // into pinned host memory followed by a sequence number; the host polls that word instead of the stream. Per
+  // registration this saves the D2H copies, the memsets of the box reduction and every cudaStreamQuery of the wait: a
+  // batch pool of 32-64 host threads is bound by the rate of driver calls. APD_ZERO_COPY=0: copies + stream waits.
+  bool zero_copy = true;
+  LmResult* h_lm_dev = nullptr;         // h_lm as the device sees it
+  unsigned int* h_small_dev = nullptr;  // h_small as the device sees it
+  unsigned long long seq = 0;           // last sequence number handed to a kernel
+  unsigned long long seq_seen = 0;      // highest sequence number the host has seen published (stream order: everything
+                                        // enqueued before that kernel has completed too)
+  // APD_BATCH_TRACE=1: host wall time per phase of a pooled registration, summed (printed by apd_batch_destroy):
+  // 0 set clouds (staging / H2D enqueue), 1 wait for the bounding boxes, 2 enqueue grids + covariances, 3 enqueue the loop,
+  // 4 wait for the result
+  double phase_s[5] = {0, 0, 0, 0, 0};
+  int64_t phase_n = 0;
+  // CTAs per registration in the device loop (APD_LM_CLUSTER=1|2|4|8|16). A lone registration is latency-bound: 8 CTAs
+  // (C2 on B200: lm_kernel 0.42 ms with 4, 0.29 ms with 8); the workers of a batch pool share the SMs: 4.
+  int lm_cluster = 8;
   bool lm_failed = false;
   // wait for the result of the device loop on a blocking-sync event instead of spinning on the stream: the batch
   // context runs more host threads than it needs cores for (set by apd_batch_create; APD_BLOCKING_SYNC=0|1 overrides)
   bool blocking_wait = false;
+  bool pooled = false;  // a worker of a batch pool: throughput matters, not the latency of one registration
   int poll_wait_us = 0;
   cudaEvent_t done_ev = nullptr;
   // batch workers ask the device loop to append the getFitnessScore pass (saves a launch and a round trip per pair)
   bool fuse_fitness = false;
   double fuse_inlier_sq_thr = 0.25;
   bool fit_valid = false;  // fit[] describes the last align's final pose
+  bool pending_fitness = false;  // the loop in flight carries the fitness pass
   double fit[3] = {0, 0, 0};
   // results of the last align
   hm::Pose final_pose = hm::Pose::identity();
@@ -233,8 +257,10 @@ struct apd_handle {
   int knn_mode = 0;
   int knn_thread_min_n = 500000;
   // Target covariances on demand inside the device-resident loop (see Cloud::cov_lazy): 0 never, 1 whenever the loop
-  // runs, -1 auto: when the target has at least lazy_min_ratio x the source's points (a scan against a submap matches a
-  // few percent of the submap). APD_LAZY_TARGET_COV=0|1|auto.
+  // runs, -1 auto: in the workers of a batch pool when the target has at least lazy_min_ratio x the source's points (a
+  // scan against a submap matches a few percent of the submap: 11.2 k against 7.0 k registrations/s). A lone handle
+  // computes all target covariances in one GPU-wide pass: the on-demand searches run on the loop's few SMs and lengthen
+  // a single registration (C2: 0.67 ms against 0.64 ms). APD_LAZY_TARGET_COV=0|1|auto.
   int lazy_mode = -1;
   int lazy_min_ratio = 4;
   int knn_max_k() const { return knn_mode == 1 ? 32 : 128; }
@@ -297,6 +323,31 @@ cudaError_t wait_stream(apd_handle* h) {
   cudaError_t e = cudaEventRecord(h->done_ev, h->stream);
   if (e != cudaSuccess) return e;
   return cudaEventSynchronize(h->done_ev);
+}
+
+// Wait until a kernel has published `expect` at *word (pinned host memory, see apd_handle::zero_copy). A lone handle
+// spins; pool workers sleep between looks. The stream is queried now and then so that a failed launch / faulting kernel
+// ends the wait with its error instead of hanging.
+cudaError_t wait_host_seq(apd_handle* h, const volatile unsigned long long* word, unsigned long long expect) {
+  const bool sleepy = h->blocking_wait && h->poll_wait_us > 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto next_check = t0 + std::chrono::milliseconds(20);
+  for (unsigned spins = 0;; spins++) {
+    if (*word == expect) break;
+    if (sleepy) std::this_thread::sleep_for(std::chrono::microseconds(h->poll_wait_us));
+    else if ((spins & 63) == 63) std::this_thread::yield();
+    if (sleepy || (spins & 1023) == 1023) {
+      const auto now = std::chrono::steady_clock::now();
+      if (now >= next_check) {
+        const cudaError_t e = cudaStreamQuery(h->stream);
+        if (e != cudaErrorNotReady && e != cudaSuccess) return e;
+        if (e == cudaSuccess && *word != expect) return cudaErrorUnknown;  // the stream is idle and nothing was published
+        next_check = now + std::chrono::milliseconds(20);
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return cudaSuccess;
 }
 
 int fail(apd_handle* h, int code, const char* msg) {
@@ -459,9 +510,41 @@ int ensure_small(apd_handle* h);
 NoiseParams noise_params(const apd_params& p);
 int ensure_corr_buffers(apd_handle* h);
 
-int ensure_grid(apd_handle* h, Cloud& c) {
+// The bounding boxes of device clouds are reduced on the device (set_cloud_device) and read back here, the first time a
+// grid needs one: ONE wait serves both clouds of a {setInputTarget; setInputSource; align} sequence.
+int finish_bboxes(apd_handle* h) {
+  if (!h->src.bbox_pending && !h->tgt.bbox_pending) return APD_OK;
+  const auto t_wait0 = std::chrono::steady_clock::now();
+  struct Acc {
+    apd_handle* h;
+    std::chrono::steady_clock::time_point t0;
+    ~Acc() { h->phase_s[1] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+  } acc{h, t_wait0};
+  if (!h->zero_copy) APD_CUDA(h, wait_stream(h));
+  for (Cloud* c : {&h->src, &h->tgt}) {
+    if (!c->bbox_pending) continue;
+    const unsigned int* enc = reinterpret_cast<const unsigned int*>(reinterpret_cast<double*>(h->h_small.p) + (c == &h->src ? 48 : 52));
+    if (h->zero_copy) {
+      APD_CUDA(h, wait_host_seq(h, reinterpret_cast<const volatile unsigned long long*>(enc + 6), c->bbox_seq));
+      h->seq_seen = std::max(h->seq_seen, c->bbox_seq);
+    }
+    for (int a = 0; a < 6; a++) {
+      unsigned int u = enc[a];
+      u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+      std::memcpy(&c->bbox[a], &u, 4);
+    }
+    c->bbox_pending = false;
+  }
+  return APD_OK;
+}
+
+int ensure_grid(apd_handle* h, Cloud& c, bool clear_flags = false) {
   if (c.grid_valid) return APD_OK;
   if (!c.present || c.n <= 0) return fail(h, APD_ERR_INVALID, "cloud not set");
+  {
+    int rc = finish_bboxes(h);
+    if (rc != APD_OK) return rc;
+  }
   size_grid(c.bbox, c.n, h->cells_per_point > 0.0 ? h->cells_per_point : (c.n < 500000 ? 4.0 : 8.0), c.g, c.ncells);
   const size_t n = (size_t)c.n;
   APD_CUDA(h, c.spts.ensure(n * sizeof(float4)));
@@ -489,6 +572,8 @@ int ensure_grid(apd_handle* h, Cloud& c) {
     if (rc != APD_OK) return rc;
     w.ticket = reinterpret_cast<unsigned int*>(h->small.as<double>() + 42);
   }
+  w.zero_flags = clear_flags ? c.cov_flag.as<unsigned char>() : nullptr;  // (allocated by the caller)
+  c.flags_fresh = clear_flags;
   {
     ProfScope ps(h, APD_K_GRID);
     launch_grid_build(c.view(), w, h->stream, &h->launches);
@@ -571,17 +656,18 @@ int ensure_covariances_for_loop(apd_handle* h) {
   Cloud& t = h->tgt;
   const int k = t.cov_lazy ? t.lazy_k : h->params.k_correspondences;
   const bool lazy = !t.cov_valid && t.n > 0 && k >= 1 && k <= 32 && t.n >= k &&
-                    (t.cov_lazy || h->lazy_mode == 1 || (h->lazy_mode < 0 && (long long)t.n >= (long long)h->lazy_min_ratio * h->src.n));
+                    (t.cov_lazy || h->lazy_mode == 1 || (h->lazy_mode < 0 && h->pooled && (long long)t.n >= (long long)h->lazy_min_ratio * h->src.n));
   if (!lazy) return ensure_covariances(h);
   int rc = ensure_covariances_of(h, h->src);
   if (rc != APD_OK) return rc;
-  rc = ensure_grid(h, t);
-  if (rc != APD_OK) return rc;
   APD_CUDA(h, t.cov.ensure((size_t)t.n * 6 * sizeof(double)));
   APD_CUDA(h, t.cov_flag.ensure((size_t)t.n));
-  APD_CUDA(h, h->nbuf.ensure((size_t)std::max(h->src.n, 1) * k * sizeof(int32_t)));
+  APD_CUDA(h, h->nbuf.ensure((size_t)std::max(h->src.n, 1) * (k + 1) * sizeof(int32_t)));
+  t.flags_fresh = false;
+  rc = ensure_grid(h, t, !t.cov_lazy);  // a grid built now clears the flags on its way (saves the memset call)
+  if (rc != APD_OK) return rc;
   if (!t.cov_lazy) {
-    APD_CUDA(h, cudaMemsetAsync(t.cov_flag.p, 0, (size_t)t.n, h->stream));
+    if (!t.flags_fresh) APD_CUDA(h, cudaMemsetAsync(t.cov_flag.p, 0, (size_t)t.n, h->stream));
     t.cov_lazy = true;
     t.lazy_k = k;
     t.lazy_reg = h->params.regularization;
@@ -592,12 +678,23 @@ int ensure_covariances_for_loop(apd_handle* h) {
 
 int ensure_small(apd_handle* h) {
   // [0..27] out28, [32..34] fitness out3, then tickets (uint) at double index 40, 41
+  // device: [0..27] out28, [32..34] fitness out3, tickets (uint) at double index 40-42, the state of the bounding-box
+  // reduction at 48 (source) / 52 (target), 56: its output when zero-copy is off. host: the same indices; a box is
+  // 6 uints + its 64-bit sequence number (48..51 / 52..55)
   if (!h->small.p) {
     APD_CUDA(h, h->small.ensure(64 * sizeof(double)));
     APD_CUDA(h, cudaMemsetAsync(h->small.p, 0, 64 * sizeof(double), h->stream));
+    init_bounds_state(reinterpret_cast<unsigned int*>(h->small.as<double>() + 48), h->stream);
+    init_bounds_state(reinterpret_cast<unsigned int*>(h->small.as<double>() + 52), h->stream);
   }
   if (!h->partials.p) APD_CUDA(h, h->partials.ensure((size_t)h->max_reduce_blocks * kReduceVals * sizeof(double)));
-  APD_CUDA(h, h->h_small.ensure(64 * sizeof(double)));
+  if (!h->h_small.p) {
+    APD_CUDA(h, h->h_small.ensure(64 * sizeof(double)));
+    std::memset(h->h_small.p, 0, 64 * sizeof(double));
+    void* d = nullptr;
+    if (h->zero_copy && cudaHostGetDevicePointer(&d, h->h_small.p, 0) == cudaSuccess) h->h_small_dev = reinterpret_cast<unsigned int*>(d);
+    else h->zero_copy = false;
+  }
   return APD_OK;
 }
 
@@ -764,6 +861,11 @@ int step_lm(apd_handle* h, int outer, hm::Pose& x0, hm::Pose& delta, bool* ok) {
 // covariances are pure functions of the cloud, so they are copied device-to-device instead of rebuilt (the reference
 // recomputes them).
 int adopt_cloud(apd_handle* h, Cloud& dst, const Cloud& src) {
+  {
+    const int rc = finish_bboxes(h);
+    if (rc != APD_OK) return rc;
+  }
+  dst.bbox_pending = false;
   const size_t n = (size_t)src.n;
   auto copy = [&](DevBuf& d, const DevBuf& s_, size_t bytes) -> cudaError_t {
     if (!s_.p || bytes == 0) return cudaSuccess;
@@ -814,7 +916,11 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
     }
   }
   // the previous H2D out of this staging buffer must have completed before it is overwritten
-  if (c.staged) {
+  if (c.staged_by_seq) {
+    // (zero-copy handles: no event per copy — a later kernel of this stream was seen to finish, which is the normal case
+    // of a pool worker reusing its handle; otherwise wait for the stream)
+    if (h->seq_seen <= c.staged_seq) APD_CUDA(h, wait_stream(h));
+  } else if (c.staged) {
     if (h->blocking_wait && h->poll_wait_us > 0) {
       cudaError_t e;
       while ((e = cudaEventQuery(c.staged)) == cudaErrorNotReady) std::this_thread::sleep_for(std::chrono::microseconds(h->poll_wait_us));
@@ -823,13 +929,20 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
       APD_CUDA(h, cudaEventSynchronize(c.staged));
     }
   }
-  else APD_CUDA(h, cudaEventCreateWithFlags(&c.staged, cudaEventDisableTiming | (h->blocking_wait ? cudaEventBlockingSync : 0)));
   APD_CUDA(h, c.stage.ensure((size_t)std::max(n, 1) * sizeof(float4)));
   stage_cloud(pts, n, stride, xyz_off, label_off, reinterpret_cast<float4*>(c.stage.p), c.bbox);
   APD_CUDA(h, c.pts.ensure((size_t)std::max(n, 1) * sizeof(float4)));
   APD_CUDA(h, cudaMemcpyAsync(c.pts.p, c.stage.p, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-  APD_CUDA(h, cudaEventRecord(c.staged, h->stream));
+  if (h->zero_copy) {
+    c.staged_by_seq = true;
+    c.staged_seq = h->seq;  // kernels enqueued from now on carry larger numbers
+  } else {
+    c.staged_by_seq = false;
+    if (!c.staged) APD_CUDA(h, cudaEventCreateWithFlags(&c.staged, cudaEventDisableTiming | (h->blocking_wait ? cudaEventBlockingSync : 0)));
+    APD_CUDA(h, cudaEventRecord(c.staged, h->stream));
+  }
   c.ext_pts = nullptr;
+  c.bbox_pending = false;
   c.n = n;
   c.present = true;
   c.key = key;
@@ -846,16 +959,19 @@ int set_cloud_device(apd_handle* h, Cloud& c, const void* d_xyzl, int32_t n) {
   DeviceGuard dg(h->device);
   int rc = ensure_small(h);
   if (rc != APD_OK) return rc;
-  float* d_b = reinterpret_cast<float*>(h->small.as<double>() + 48);
-  launch_bounds(reinterpret_cast<const float4*>(d_xyzl), n, d_b, h->stream, &h->launches);
-  unsigned int* enc = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(h->h_small.p) + 48);  // pinned: a truly asynchronous copy
-  APD_CUDA(h, cudaMemcpyAsync(enc, d_b, 6 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
-  APD_CUDA(h, wait_stream(h));
-  for (int a = 0; a < 6; a++) {
-    unsigned int u = enc[a];
-    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-    std::memcpy(&c.bbox[a], &u, 4);
+  const int slot = (&c == &h->src) ? 48 : 52;  // per-cloud slots: both boxes may be in flight at once
+  unsigned int* d_state = reinterpret_cast<unsigned int*>(h->small.as<double>() + slot);  // prepared by ensure_small
+  unsigned int* enc = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(h->h_small.p) + slot);
+  c.bbox_seq = ++h->seq;
+  if (h->zero_copy) {
+    launch_bounds(reinterpret_cast<const float4*>(d_xyzl), n, d_state, h->h_small_dev + 2 * slot, c.bbox_seq, h->stream, &h->launches);
+  } else {  // the kernel publishes into device scratch (small[56..59]), copied back in stream order
+    unsigned int* d_out = reinterpret_cast<unsigned int*>(h->small.as<double>() + 56);
+    launch_bounds(reinterpret_cast<const float4*>(d_xyzl), n, d_state, d_out, c.bbox_seq, h->stream, &h->launches);
+    APD_CUDA(h, cudaMemcpyAsync(enc, d_out, 6 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
   }
+  APD_CUDA(h, cudaGetLastError());
+  c.bbox_pending = true;
   c.ext_pts = reinterpret_cast<const float4*>(d_xyzl);
   h->corr_warm = false;
   c.n = n;
@@ -1022,38 +1138,75 @@ int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg)
   int rc = ensure_corr_buffers(h);
   if (rc != APD_OK) return rc;
   if (!h->lm_result.p) APD_CUDA(h, h->lm_result.ensure(sizeof(LmResult)));
-  APD_CUDA(h, h->h_lm.ensure(kLmHeadBytes));
+  if (!h->h_lm.p) {
+    APD_CUDA(h, h->h_lm.ensure(kLmHeadBytes));
+    std::memset(h->h_lm.p, 0, kLmHeadBytes);
+    void* d = nullptr;
+    if (h->zero_copy && cudaHostGetDevicePointer(&d, h->h_lm.p, 0) == cudaSuccess) h->h_lm_dev = reinterpret_cast<LmResult*>(d);
+    else h->zero_copy = false;
+  }
   const hm::Pose x0 = guess ? hm::from_colmajor_f32(guess) : hm::Pose::identity();  // lsq :56
-  const LmJob job = lm_job(h, x0);
+  LmJob job = lm_job(h, x0);
+  job.seq = ++h->seq;
+  job.host_result = h->zero_copy ? h->h_lm_dev : nullptr;
   {
     ProfScope ps(h, APD_K_LM);
     launch_lm(&job, nullptr, 1, cfg, h->lm_cluster, h->stream, &h->launches);
   }
   APD_CUDA(h, cudaGetLastError());
-  APD_CUDA(h, cudaMemcpyAsync(h->h_lm.p, h->lm_result.p, kLmHeadBytes, cudaMemcpyDeviceToHost, h->stream));
+  if (!h->zero_copy) APD_CUDA(h, cudaMemcpyAsync(h->h_lm.p, h->lm_result.p, kLmHeadBytes, cudaMemcpyDeviceToHost, h->stream));
   return APD_OK;
 }
 
+// The device-resident loop in two halves, so that a pool worker can keep several registrations in flight:
+// begin_device_align enqueues covariances + the loop and returns; result_arrived polls; end_device_align unpacks.
+int begin_device_align(apd_handle* h, const float* guess) {
+  const auto t_a = std::chrono::steady_clock::now();
+  const double bbox_before = h->phase_s[1];
+  int rc = ensure_covariances_for_loop(h);  // FastAPDGICP::computeTransformation (:148-157)
+  if (rc != APD_OK) return rc;
+  const auto t_b = std::chrono::steady_clock::now();
+  h->phase_s[2] += std::chrono::duration<double>(t_b - t_a).count() - (h->phase_s[1] - bbox_before);
+  h->fit_valid = false;
+  LmConfig cfg = lm_config(h->params);
+  if (h->fuse_fitness) {
+    cfg.want_fitness = 1;
+    cfg.inlier_sq_thr = h->fuse_inlier_sq_thr;
+  }
+  h->pending_fitness = cfg.want_fitness != 0;
+  rc = enqueue_device_align(h, guess, cfg);
+  h->phase_s[3] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_b).count();
+  return rc;
+}
+bool result_arrived(const apd_handle* h) {
+  return *reinterpret_cast<const volatile unsigned long long*>(&reinterpret_cast<const LmResult*>(h->h_lm.p)->seq) == h->seq;
+}
+int end_device_align(apd_handle* h) {
+  const LmResult* r = reinterpret_cast<const LmResult*>(h->h_lm.p);
+  const auto t_c = std::chrono::steady_clock::now();
+  if (h->zero_copy && !h->profiling) {
+    APD_CUDA(h, wait_host_seq(h, &r->seq, h->seq));
+    h->seq_seen = std::max(h->seq_seen, h->seq);
+  } else {
+    APD_CUDA(h, wait_stream(h));
+  }
+  h->phase_s[4] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_c).count();
+  h->phase_n++;
+  if (h->pending_fitness) {
+    h->fit_valid = true;
+    for (int i = 0; i < 3; i++) h->fit[i] = r->fitness[i];
+  }
+  return finish_device_align(h, r);
+}
+
 int do_align(apd_handle* h, const float* guess) {
-  int rc = use_device_loop(h) ? ensure_covariances_for_loop(h) : ensure_covariances(h);  // FastAPDGICP::computeTransformation (:148-157)
+  if (use_device_loop(h)) {
+    const int rc = begin_device_align(h, guess);
+    return rc != APD_OK ? rc : end_device_align(h);
+  }
+  int rc = ensure_covariances(h);  // FastAPDGICP::computeTransformation (:148-157)
   if (rc != APD_OK) return rc;
   h->fit_valid = false;
-  if (use_device_loop(h)) {
-    LmConfig cfg = lm_config(h->params);
-    if (h->fuse_fitness) {
-      cfg.want_fitness = 1;
-      cfg.inlier_sq_thr = h->fuse_inlier_sq_thr;
-    }
-    rc = enqueue_device_align(h, guess, cfg);
-    if (rc != APD_OK) return rc;
-    APD_CUDA(h, wait_stream(h));
-    const LmResult* r = reinterpret_cast<const LmResult*>(h->h_lm.p);
-    if (cfg.want_fitness) {
-      h->fit_valid = true;
-      for (int i = 0; i < 3; i++) h->fit[i] = r->fitness[i];
-    }
-    return finish_device_align(h, r);
-  }
   hm::Pose x0 = guess ? hm::from_colmajor_f32(guess) : hm::Pose::identity();  // lsq :56
   h->lm_lambda = -1.0;   // :58
   h->converged = false;  // :59
@@ -1106,6 +1259,12 @@ int do_fitness(apd_handle* h, const float* T, double max_range, double* score, i
 
 }  // namespace
 
+// A batch pool drives one CUDA stream per worker (32-64). With the driver's default of 8 hardware work queues the
+// streams share queues, and a short kernel of one worker waits behind the 1 ms optimizer kernel of another (measured on
+// B200, C2, 32 workers: 6.3 k registrations/s with 8 queues, 15.1 k with 32). The variable is read when the CUDA context
+// is created, so it is set when the library is loaded; a value the user exported wins.
+__attribute__((constructor)) static void apd_default_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 // =============================================================== C-ABI =====
 extern "C" {
 
@@ -1140,11 +1299,12 @@ int apd_create(int device, apd_handle** out) {
   }
   if (const char* e = std::getenv("APD_LM_CLUSTER")) {
     const int v = std::atoi(e);
-    if (v == 1 || v == 2 || v == 4 || v == 8) h->lm_cluster = v;
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->lm_cluster = v;
   }
   if (const char* e = std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = std::atoi(e) != 0;
   if (const char* e = std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = std::atoi(e);
   if (const char* e = std::getenv("APD_LAZY_TARGET_COV")) h->lazy_mode = std::strcmp(e, "auto") == 0 ? -1 : (std::atoi(e) != 0 ? 1 : 0);
+  if (const char* e = std::getenv("APD_ZERO_COPY")) h->zero_copy = std::atoi(e) != 0;
   if (const char* e = std::getenv("APD_KNN_MODE")) h->knn_mode = std::strcmp(e, "warp") == 0 ? 1 : (std::strcmp(e, "thread") == 0 ? 2 : 0);
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   for (int i = 0; i < 36; i++) h->final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity()
@@ -1210,6 +1370,11 @@ int apd_set_target_device(apd_handle* h, const void* d, int32_t n) {
 
 int apd_swap_source_and_target(apd_handle* h) {  // :89-98
   if (!h) return APD_ERR_INVALID;
+  {
+    DeviceGuard dg(h->device);
+    const int rc = finish_bboxes(h);  // (the read-back slots belong to the roles, not to the clouds)
+    if (rc != APD_OK) return rc;
+  }
   std::swap(h->src, h->tgt);
   h->corr_n = -1;  // correspondences_.clear()
   h->corr_warm = false;
@@ -1376,6 +1541,7 @@ struct apd_batch {
   int device = 0;
   std::vector<apd_handle*> handles;
   std::vector<std::thread> threads;
+  int n_threads = 0;
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
   uint64_t generation = 0;
@@ -1391,10 +1557,68 @@ struct apd_batch {
 
 namespace {
 
-void batch_one(apd_batch* b, apd_handle* h, int i) {
-  const apd_pair& pr = b->pairs[i];
+// result of pair i from the handle that has just finished it (rc: the status so far)
+void batch_fill_result(apd_batch* b, apd_handle* h, int i, int rc) {
   apd_result& r = b->results[i];
-  std::memset(&r, 0, sizeof(r));
+  if (rc == APD_OK) {
+    std::memcpy(r.T, h->final_T, sizeof(h->final_T));
+    r.converged = h->converged ? 1 : 0;
+    r.iterations = h->nr_iterations;
+    if (b->with_fitness) {
+      if (h->fit_valid) {  // the device loop already ran the pass on the final pose
+        const int nr = (int)h->fit[1];
+        r.fitness = nr > 0 ? h->fit[0] / nr : std::numeric_limits<double>::max();
+        r.n_inliers = (int)h->fit[2];
+      } else {
+        rc = apd_fitness(h, nullptr, DBL_MAX, &r.fitness, nullptr, 0.25, &r.n_inliers);
+      }
+    }
+  }
+  r.status = rc;
+}
+
+// A pool worker drives several handles ("slots") and never blocks on one of them: a registration is a short state
+// machine — set the clouds (device clouds: launch the bounding-box kernels), wait for the boxes, enqueue grids +
+// covariances + the device-resident loop, wait for the result — and the waits are looks at sequence numbers the kernels
+// publish into pinned host memory (apd_handle::zero_copy). Few threads issue all the driver calls: with one thread per
+// registration in flight (32-64 threads) the calls contend for the driver's context lock and cost ~50 us each.
+enum { kSlotIdle = 0, kSlotBbox, kSlotResult, kSlotDone };
+struct PoolSlot {
+  apd_handle* h = nullptr;
+  int pair = -1;
+  int state = kSlotIdle;
+  std::chrono::steady_clock::time_point since;
+};
+
+bool bboxes_arrived(const apd_handle* h) {
+  for (const Cloud* c : {&h->src, &h->tgt}) {
+    if (!c->bbox_pending) continue;
+    const unsigned int* enc = reinterpret_cast<const unsigned int*>(reinterpret_cast<const double*>(h->h_small.p) + (c == &h->src ? 48 : 52));
+    if (*reinterpret_cast<const volatile unsigned long long*>(enc + 6) != c->bbox_seq) return false;
+  }
+  return true;
+}
+
+// enqueue the registration of the slot's pair (the clouds are set, their boxes have arrived)
+void slot_enqueue(apd_batch* b, PoolSlot& sl) {
+  apd_handle* h = sl.h;
+  int rc = begin_device_align(h, b->pairs[sl.pair].guess);
+  if (rc == APD_OK && !h->zero_copy) rc = end_device_align(h);  // (no zero-copy mapping after all: finish it here)
+  else if (rc == APD_OK) {
+    sl.state = kSlotResult;
+    sl.since = std::chrono::steady_clock::now();
+    return;
+  }
+  batch_fill_result(b, h, sl.pair, rc);
+  sl.state = kSlotIdle;
+}
+
+void slot_begin(apd_batch* b, PoolSlot& sl, int i) {
+  apd_handle* h = sl.h;
+  sl.pair = i;
+  const apd_pair& pr = b->pairs[i];
+  std::memset(&b->results[i], 0, sizeof(apd_result));
+  const auto t_set = std::chrono::steady_clock::now();
   // the reference benchmark protocol: clearTarget; clearSource; setInputTarget; setInputSource; align (align.cpp:57-83)
   apd_clear_target(h);
   apd_clear_source(h);
@@ -1406,27 +1630,49 @@ void batch_one(apd_batch* b, apd_handle* h, int i) {
     rc = apd_set_target(h, pr.target, pr.n_target, b->stride, b->xyz_off, b->label_off, 0);
     if (rc == APD_OK) rc = apd_set_source(h, pr.source, pr.n_source, b->stride, b->xyz_off, b->label_off, 0);
   }
-  int32_t conv = 0, it = 0;
+  h->phase_s[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_set).count();
   h->fuse_fitness = b->with_fitness != 0;
-  if (rc == APD_OK) rc = apd_align(h, pr.guess, r.T, nullptr, nullptr, &conv, &it, nullptr);
-  r.converged = conv;
-  r.iterations = it;
-  r.fitness = 0.0;
-  if (rc == APD_OK && b->with_fitness) {
-    if (h->fit_valid) {  // the device loop already ran the pass on the final pose
-      const int nr = (int)h->fit[1];
-      r.fitness = nr > 0 ? h->fit[0] / nr : std::numeric_limits<double>::max();
-      r.n_inliers = (int)h->fit[2];
-    } else {
-      rc = apd_fitness(h, nullptr, DBL_MAX, &r.fitness, nullptr, 0.25, &r.n_inliers);
-    }
+  if (rc != APD_OK) {
+    batch_fill_result(b, h, i, rc);
+    sl.state = kSlotIdle;
+    return;
   }
-  r.status = rc;
+  if (!use_device_loop(h) || !h->zero_copy || h->profiling) {  // host-driven loop / copies + stream waits / timing events: blocking
+    rc = apd_align(h, pr.guess, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    batch_fill_result(b, h, i, rc);
+    sl.state = kSlotIdle;
+    return;
+  }
+  DeviceGuard dg(h->device);
+  if (h->src.bbox_pending || h->tgt.bbox_pending) {
+    sl.state = kSlotBbox;
+    sl.since = std::chrono::steady_clock::now();
+    return;
+  }
+  slot_enqueue(b, sl);
+}
+
+// a slot has been waiting for 20 ms: make sure its stream is still alive (a failed launch or a faulting kernel publishes nothing)
+bool slot_stalled(PoolSlot& sl, bool arrived_now) {
+  const auto now = std::chrono::steady_clock::now();
+  if (now - sl.since < std::chrono::milliseconds(20)) return false;
+  sl.since = now;
+  const cudaError_t e = cudaStreamQuery(sl.h->stream);
+  if (e == cudaErrorNotReady) return false;
+  if (e == cudaSuccess && arrived_now) return false;
+  sl.h->error = e == cudaSuccess ? "kernel finished without publishing its result" : cudaGetErrorString(e);
+  return true;
 }
 
 void batch_worker(apd_batch* b, int wi) {
   cudaSetDevice(b->device);
-  apd_handle* h = b->handles[wi];
+  std::vector<PoolSlot> slots;
+  for (size_t s = (size_t)wi; s < b->handles.size(); s += (size_t)b->n_threads) {
+    PoolSlot sl;
+    sl.h = b->handles[s];
+    slots.push_back(sl);
+  }
+  const int nap_us = std::max(1, slots[0].h->poll_wait_us);
   uint64_t seen = 0;
   for (;;) {
     {
@@ -1435,10 +1681,51 @@ void batch_worker(apd_batch* b, int wi) {
       if (b->stop) return;
       seen = b->generation;
     }
-    for (;;) {
-      const int i = b->next.fetch_add(1);
-      if (i >= b->n_pairs) break;
-      batch_one(b, h, i);
+    for (auto& sl : slots) sl.state = kSlotIdle;
+    for (size_t done = 0; done < slots.size();) {
+      bool progressed = false;
+      done = 0;
+      for (auto& sl : slots) {
+        apd_handle* h = sl.h;
+        switch (sl.state) {
+          case kSlotIdle: {
+            const int i = b->next.fetch_add(1);
+            if (i >= b->n_pairs) {
+              sl.state = kSlotDone;
+            } else {
+              slot_begin(b, sl, i);
+              progressed = true;
+            }
+            break;
+          }
+          case kSlotBbox:
+            if (bboxes_arrived(h)) {
+              DeviceGuard dg(h->device);
+              slot_enqueue(b, sl);
+              progressed = true;
+            } else if (slot_stalled(sl, bboxes_arrived(h))) {
+              batch_fill_result(b, h, sl.pair, APD_ERR_CUDA);
+              sl.state = kSlotIdle;
+            }
+            break;
+          case kSlotResult:
+            if (result_arrived(h)) {
+              DeviceGuard dg(h->device);
+              const int rc = end_device_align(h);
+              batch_fill_result(b, h, sl.pair, rc);
+              sl.state = kSlotIdle;
+              progressed = true;
+            } else if (slot_stalled(sl, result_arrived(h))) {
+              batch_fill_result(b, h, sl.pair, APD_ERR_CUDA);
+              sl.state = kSlotIdle;
+            }
+            break;
+          default:
+            done++;
+            break;
+        }
+      }
+      if (!progressed && done < slots.size()) std::this_thread::sleep_for(std::chrono::microseconds(nap_us));
     }
     {
       std::lock_guard<std::mutex> lk(b->mu);
@@ -1492,11 +1779,18 @@ int apd_batch_create(int device, int32_t n_workers, apd_batch** out) {
     }
     // a pool this large keeps the GPU busy by itself: its waiting threads sleep instead of spinning, so that several
     // ranks' pools can share the host cores (see wait_stream)
+    h->pooled = true;
+    if (!std::getenv("APD_LM_CLUSTER")) h->lm_cluster = 4;
     if (!std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = n_workers > 8;
-    if (!std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = 200;
+    if (!std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = 50;  // (a look at pinned host memory: cheap)
     b->handles.push_back(h);
   }
-  for (int s = 0; s < n_workers; s++) b->threads.emplace_back(batch_worker, b, s);
+  // host threads: each drives n_workers / n_threads registrations at a time (APD_BATCH_THREADS)
+  int n_threads = 8;
+  if (const char* e = std::getenv("APD_BATCH_THREADS")) n_threads = std::atoi(e);
+  n_threads = std::max(1, std::min(n_threads, n_workers));
+  b->n_threads = n_threads;
+  for (int s = 0; s < n_threads; s++) b->threads.emplace_back(batch_worker, b, s);
   *out = b;
   return APD_OK;
 }
@@ -1509,6 +1803,20 @@ int apd_batch_destroy(apd_batch* b) {
   }
   b->cv_work.notify_all();
   for (auto& t : b->threads) t.join();
+  if (const char* e = std::getenv("APD_BATCH_TRACE")) {
+    if (std::atoi(e) != 0) {
+      double ph[5] = {0, 0, 0, 0, 0};
+      int64_t n = 0;
+      for (auto* h : b->handles) {
+        for (int i = 0; i < 5; i++) ph[i] += h->phase_s[i];
+        n += h->phase_n;
+      }
+      if (n > 0)
+        std::fprintf(stderr, "apd_batch trace: %lld registrations, host ms per registration: set %.3f, bbox wait %.3f, enqueue grids+cov %.3f, "
+                     "enqueue loop %.3f, result wait %.3f\n", (long long)n, 1e3 * ph[0] / n, 1e3 * ph[1] / n, 1e3 * ph[2] / n, 1e3 * ph[3] / n,
+                     1e3 * ph[4] / n);
+    }
+  }
   for (auto* h : b->handles) apd_destroy(h);
   delete b;
   return APD_OK;

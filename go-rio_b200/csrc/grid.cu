@@ -4,6 +4,8 @@
 // setInputSource / setInputTarget (fast_apdgicp_impl.hpp:121,132).
 // The sort is stable (ties keep original-index order) so the sorted layout — and
 // with it every later reduction order — is bit-deterministic.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace apd {
@@ -18,7 +20,12 @@ __device__ __forceinline__ unsigned int f2ord(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__global__ void __launch_bounds__(kThreads) bounds_kernel(const float4* __restrict__ pts, int n, unsigned int* __restrict__ out6) {
+// state: 6 ordered-uint slots {min x,y,z = 0xffffffff; max x,y,z = 0} + a ticket, in device memory, initialised ONCE
+// (init_bounds_state) — the last block to finish publishes the box and restores the initial state for the next launch.
+// host_out: 6 uints + a 64-bit sequence number in pinned host memory, written by the kernel itself (zero-copy): the host
+// polls the number — no memset, no copy, no stream query per cloud (a batch pool is bound by the driver's call rate).
+__global__ void __launch_bounds__(kThreads) bounds_kernel(const float4* __restrict__ pts, int n, unsigned int* state, unsigned int* host_out,
+                                                          unsigned long long seq) {
   float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = pts[i];
@@ -37,10 +44,26 @@ __global__ void __launch_bounds__(kThreads) bounds_kernel(const float4* __restri
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-      atomicMin(&out6[a], f2ord(mn[a]));
-      atomicMax(&out6[3 + a], f2ord(mx[a]));
+      atomicMin(&state[a], f2ord(mn[a]));
+      atomicMax(&state[3 + a], f2ord(mx[a]));
     }
+    __threadfence();
   }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  if (atomicAdd(&state[6], 1u) != gridDim.x - 1) return;
+  __threadfence();
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+    host_out[a] = atomicExch(&state[a], a < 3 ? 0xffffffffu : 0u);  // read the result, restore the initial state
+  }
+  state[6] = 0u;
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long*>(host_out + 6) = seq;
+}
+
+__global__ void init_bounds_state_kernel(unsigned int* state) {
+  if (threadIdx.x < 7) state[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u;
 }
 
 // ------------------------------------------------------------ keys/counts ----
@@ -191,9 +214,11 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
 
 // ---------------------------------------------------------------- reorder ----
 __global__ void __launch_bounds__(kThreads) reorder_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ vals, int n,
-                                                           float4* __restrict__ spts, float* __restrict__ label, int* __restrict__ inv_perm) {
+                                                           float4* __restrict__ spts, float* __restrict__ label, int* __restrict__ inv_perm,
+                                                           unsigned char* __restrict__ zero_flags) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
+  if (zero_flags) zero_flags[s] = 0;
   const int idx = (int)vals[s];
   const float4 p = pts[idx];
   spts[s] = make_float4(p.x, p.y, p.z, __int_as_float(idx));
@@ -305,9 +330,11 @@ __global__ void __launch_bounds__(kThreads) scatter_nd_kernel(const uint32_t* __
 __global__ void __launch_bounds__(kThreads) rank_fix_reorder_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ keys,
                                                                     const uint32_t* __restrict__ tmp, int n,
                                                                     const uint32_t* __restrict__ cell_start, float4* __restrict__ spts,
-                                                                    float* __restrict__ label, int* __restrict__ inv_perm) {
+                                                                    float* __restrict__ label, int* __restrict__ inv_perm,
+                                                                    unsigned char* __restrict__ zero_flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (zero_flags) zero_flags[i] = 0;
   const uint32_t key = keys[i];
   const uint32_t b = cell_start[key], e = cell_start[key + 1];
   uint32_t r = 0;
@@ -317,6 +344,71 @@ __global__ void __launch_bounds__(kThreads) rank_fix_reorder_kernel(const float4
   spts[s] = make_float4(p.x, p.y, p.z, __int_as_float(i));
   label[s] = p.w;
   inv_perm[i] = s;
+}
+
+// ------------------------------------------------- tiny-cloud path ----
+// A radar scan (1-4 k points, <= 32 k cells) is built by ONE CTA in ONE launch: zero the counters, atomic per-cell
+// ranks, block-wide exclusive scan, scatter, deterministic slot by counting (the small-cloud path's steps with CTA
+// barriers instead of kernel boundaries — same sorted layout). A batch pool is bound by the driver's launch rate, and
+// a lone scan-to-scan registration by launch latency: 1 call instead of 6.
+constexpr int kTinyThreads = 1024;
+constexpr int kTinyCloud = 4096;
+constexpr int kTinyCellsPerThread = 32;
+// (no __restrict__ / const on the arrays written here: later phases must not read them through the non-coherent path)
+__global__ void __launch_bounds__(kTinyThreads) grid_tiny_kernel(const float4* __restrict__ pts, int n, GridDesc g, int ncs, uint32_t* cell_start,
+                                                                 uint32_t* keys, uint32_t* nd_rank, uint32_t* tmp, float4* __restrict__ spts,
+                                                                 float* __restrict__ label, int* __restrict__ inv_perm,
+                                                                 unsigned char* __restrict__ zero_flags) {
+  __shared__ uint32_t warp_tot[kTinyThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = tid; j < ncs; j += kTinyThreads) cell_start[j] = 0u;
+  __syncthreads();
+  for (int i = tid; i < n; i += kTinyThreads) {
+    const float4 p = pts[i];
+    const int cx = cell_coord(p.x, g.ox, g.inv_cell, g.nx);
+    const int cy = cell_coord(p.y, g.oy, g.inv_cell, g.ny);
+    const int cz = cell_coord(p.z, g.oz, g.inv_cell, g.nz);
+    const uint32_t key = (uint32_t)((cz * g.ny + cy) * g.nx + cx);
+    keys[i] = key;
+    nd_rank[i] = atomicAdd(&cell_start[key], 1u);
+  }
+  __syncthreads();
+  {  // exclusive scan of cell_start[0 .. ncs): thread t owns `per` consecutive counters
+    const int per = (ncs + kTinyThreads - 1) / kTinyThreads;
+    const int b = min(tid * per, ncs), e = min(b + per, ncs);
+    uint32_t sum = 0;
+    for (int j = b; j < e; j++) sum += cell_start[j];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint32_t run = inc - sum;
+    for (int w = 0; w < warp; w++) run += warp_tot[w];
+    for (int j = b; j < e; j++) {
+      const uint32_t v = cell_start[j];
+      cell_start[j] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kTinyThreads) tmp[cell_start[keys[i]] + nd_rank[i]] = (uint32_t)i;
+  __syncthreads();
+  for (int i = tid; i < n; i += kTinyThreads) {
+    const uint32_t key = keys[i];
+    const uint32_t b = cell_start[key], e = cell_start[key + 1];
+    uint32_t r = 0;
+    for (uint32_t j = b; j < e; j++) r += (tmp[j] < (uint32_t)i) ? 1u : 0u;
+    const int sp = (int)(b + r);
+    const float4 p = pts[i];
+    spts[sp] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    label[sp] = p.w;
+    inv_perm[i] = sp;
+    if (zero_flags) zero_flags[i] = 0;
+  }
 }
 
 }  // namespace
@@ -330,22 +422,27 @@ size_t scan_tmp_elems_for(size_t n) {
   return total + 8;
 }
 
-void launch_bounds(const float4* pts, int n, float* d_out6, cudaStream_t s, int64_t* launches) {
-  // d_out6 is used as 6 ordered-uint32 slots; the caller decodes them
-  // {0xffffffff x 3, 0 x 3}: two memsets (a copy from pageable host memory would stall the calling thread)
-  cudaMemsetAsync(d_out6, 0xff, 3 * sizeof(unsigned int), s);
-  cudaMemsetAsync(reinterpret_cast<unsigned int*>(d_out6) + 3, 0, 3 * sizeof(unsigned int), s);
+void init_bounds_state(unsigned int* d_state, cudaStream_t s) { init_bounds_state_kernel<<<1, 32, 0, s>>>(d_state); }
+void launch_bounds(const float4* pts, int n, unsigned int* d_state, unsigned int* h_out, unsigned long long seq, cudaStream_t s,
+                   int64_t* launches) {
   const int blocks = min(148 * 8, (n + kThreads - 1) / kThreads);
-  bounds_kernel<<<max(1, blocks), kThreads, 0, s>>>(pts, n, reinterpret_cast<unsigned int*>(d_out6));
+  bounds_kernel<<<max(1, blocks), kThreads, 0, s>>>(pts, n, d_state, h_out, seq);
   (*launches)++;
 }
 
 void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int64_t* launches) {
   const int n = c.n;
   if (n <= 0) return;
-  cudaMemsetAsync(c.cell_start, 0, sizeof(uint32_t) * ((size_t)c.ncells + 1), s);
   const int pblocks = (n + kThreads - 1) / kThreads;
   const size_t ncs = (size_t)c.ncells + 1;
+  static const bool tiny_ok = [] { const char* e = getenv("APD_GRID_TINY"); return !e || atoi(e) != 0; }();
+  if (tiny_ok && n <= kTinyCloud && ncs <= (size_t)kTinyThreads * kTinyCellsPerThread) {
+    grid_tiny_kernel<<<1, kTinyThreads, 0, s>>>(c.pts, n, c.g, (int)ncs, c.cell_start, w.keys[0], w.vals[0], w.vals[1], c.spts, c.label,
+                                                c.inv_perm, w.zero_flags);
+    (*launches)++;
+    return;
+  }
+  cudaMemsetAsync(c.cell_start, 0, sizeof(uint32_t) * ((size_t)c.ncells + 1), s);
   const size_t tiles = (ncs + kScanTile - 1) / kScanTile;
   if (n <= kSmallCloud && tiles <= (size_t)kScanTile && w.ticket != nullptr) {
     cell_keys_rank_kernel<<<pblocks, kThreads, 0, s>>>(c.pts, n, c.g, w.keys[0], w.vals[0], c.cell_start);
@@ -355,7 +452,7 @@ void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int
       (*launches)++;
     }
     scatter_nd_kernel<<<pblocks, kThreads, 0, s>>>(w.keys[0], w.vals[0], n, c.cell_start, w.vals[1]);
-    rank_fix_reorder_kernel<<<pblocks, kThreads, 0, s>>>(c.pts, w.keys[0], w.vals[1], n, c.cell_start, c.spts, c.label, c.inv_perm);
+    rank_fix_reorder_kernel<<<pblocks, kThreads, 0, s>>>(c.pts, w.keys[0], w.vals[1], n, c.cell_start, c.spts, c.label, c.inv_perm, w.zero_flags);
     (*launches) += 4;
     return;
   }
@@ -376,7 +473,7 @@ void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int
     (*launches)++;
     cur ^= 1;
   }
-  reorder_kernel<<<pblocks, kThreads, 0, s>>>(c.pts, w.vals[cur], n, c.spts, c.label, c.inv_perm);
+  reorder_kernel<<<pblocks, kThreads, 0, s>>>(c.pts, w.vals[cur], n, c.spts, c.label, c.inv_perm, w.zero_flags);
   (*launches)++;
 }
 

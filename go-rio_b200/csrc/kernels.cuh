@@ -28,14 +28,20 @@ struct GridWork {
   uint32_t* scan_tmp;   // block sums for the multi-level scan
   size_t scan_tmp_elems;
   unsigned int* ticket; // zero-initialised counter for the small-cloud scan (reset by the kernel)
+  unsigned char* zero_flags = nullptr;  // optional [n]: cleared by the reorder step (Cloud::cov_flag of a target whose
+                                        // covariances will be computed on demand — saves the memset call)
 };
 constexpr int kSmallCloud = 65536;  // at most this many points: rank-by-counting path (see grid.cu)
 constexpr int kSortTile = 2048;  // keys per block in the radix sort
 constexpr int kScanTile = 2048;  // elements per block in the scan
 size_t scan_tmp_elems_for(size_t n);
 
-// bounding box of a device-resident cloud: out6 = {minx,miny,minz,maxx,maxy,maxz}
-void launch_bounds(const float4* pts, int n, float* d_out6, cudaStream_t s, int64_t* launches);
+// bounding box of a device-resident cloud, published by the kernel itself into pinned host memory: h_out = 6 ordered
+// uints {minx,miny,minz,maxx,maxy,maxz} (the caller decodes them) followed by a 64-bit sequence number that becomes
+// `seq` when the box is complete. d_state: 7 uints of device memory, prepared once by init_bounds_state.
+void init_bounds_state(unsigned int* d_state, cudaStream_t s);
+void launch_bounds(const float4* pts, int n, unsigned int* d_state, unsigned int* h_out, unsigned long long seq, cudaStream_t s,
+                   int64_t* launches);
 // keys/counts -> scan -> stable radix sort by cell -> reorder. Fills cell_start,
 // spts, label, inv_perm of `c` (c.pts, c.n, c.g, c.ncells must be set).
 void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int64_t* launches);
@@ -133,6 +139,7 @@ struct LmResult {
   double fitness[3];   // sum d2, n in range, n inliers (only with want_fitness)
   int converged, nr_iterations, lm_failed, n_trace;
   int hessian_set, pad_;  // hessian_set: H holds a final_hessian_ (some step was accepted)
+  unsigned long long seq; // host copy only: LmJob::seq once the header + first trace rows have arrived (written last)
   double trace[kLmTraceRows * 8];
 };
 struct LmJob {
@@ -144,13 +151,17 @@ struct LmJob {
   double cl_w;         // 1 / correspondences_.size() (:273)
   double guess[12];    // r[9] row-major, t[3]
   LmResult* result;    // device memory
+  // Zero-copy publication: the kernel's tail writes the result header + the first kLmTraceHead trace rows into pinned
+  // host memory and then host_result->seq = seq; the host polls that word — no D2H copy, no stream query per registration
+  LmResult* host_result;  // pinned host memory as seen from the device (nullptr: the host copies `result` itself)
+  unsigned long long seq;
   // Target covariances on demand (t_cov_flag != nullptr): only the target points that become correspondences ever need
   // one (a scan matches ~2 k of a 60 k-point submap), so the loop computes the covariance of a matched target point the
   // first time it meets it — same kNN search, same arithmetic, same bits as the per-cloud kernels (knn_warp.cuh).
   unsigned char* t_cov_flag;  // [n_tgt] 1: t_cov_rw[pos] is valid. nullptr: all target covariances are (eager)
   double* t_cov_rw;           // = t_cov, writable
   const float4* t_pts;        // target in ORIGINAL order (the covariance gathers its neighbours there)
-  int32_t* nb;                // [n_src][k] scratch: neighbour ids between the search pass and the covariance pass
+  int32_t* nb;                // [n_src][k] + [n_src] scratch: neighbour ids between the search pass and the covariance pass, work list
   int k, reg;                 // k_correspondences_, regularization_method_
 };
 struct LmConfig {

@@ -17,6 +17,8 @@
 // The per-point arithmetic is the code the streaming kernels use (point_math.cuh).
 #include <cooperative_groups.h>
 
+#include <cstddef>
+
 #include "host_math.hpp"
 #include "knn_warp.cuh"
 #include "point_math.cuh"
@@ -73,6 +75,7 @@ struct LmShared {
   PoseD T;                      // pose the next phase evaluates
   PoseD T_corr;                 // pose of the last update_correspondences pass (warm start of the next one)
   unsigned long long kbuf[kLmWarps][32];  // on-demand target covariances: the kNN search's candidate buffer, per warp
+  int n_need;                   // ... and the number of target points this CTA serves in the current pass
   int flag_in, flag_out;        // LM trial decision / outer-loop decision (separate words: each is re-read across one barrier only)
   LmSerial ser;
 };
@@ -141,6 +144,7 @@ __device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg
   const PoseF Tf = pose_to_f32(T);
   const PoseF Tpf = pose_to_f32(T_prev);
   const int tid = threadIdx.x;
+  if (tid == 0) smem.n_need = 0;
   constexpr int kQ = kLmThreads / kLmG;  // queries per pass
   for (int p0 = 0; p0 < cnt; p0 += kQ) {
     const int q = p0 + tid / kLmG;
@@ -174,35 +178,28 @@ __device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg
   }
   __syncthreads();
   // Target covariances on demand (calculate_covariances(target), :351-411, restricted to the points that are used).
-  // Pass A, one WARP per matched point whose target has no covariance yet: the exact kNN search of the per-cloud kernel
-  // (knn_warp.cuh), neighbour ids to job.nb. Pass B, one THREAD per such point: covariance + regularisation. Two threads
+  // The matched target points without a covariance are listed (this CTA's slice of job.nb); pass A, one WARP per listed
+  // point: the exact kNN search of the per-cloud kernel (knn_warp.cuh); pass B, one THREAD per listed point: covariance
+  // + regularisation. Two threads
   // (or two registrations sharing a target) may compute the same point; they write the same bits, so the race is benign;
   // the flag is published after the values, and readers take the values from L2 (__ldcg), never from a stale L1 line.
   if (job.t_cov_flag) {
     const int lane = tid & 31, warp = tid >> 5;
-    for (int q = warp; q < cnt; q += kLmWarps) {
-      const int c = job.corr[base + q];
-      int32_t* nbq = job.nb + (size_t)(base + q) * job.k;
-      bool need = false;
-      if (c >= 0) {
-        const int pos = c & kCorrIndexMask;
-        need = *((volatile unsigned char*)&job.t_cov_flag[pos]) == 0;
-        if (need) {
-          const unsigned long long key = knnw::knn_warp_query(job.t_spts, job.t_cell_start, job.tg, job.k, pos, lane, smem.kbuf[warp]);
-          if (lane < job.k) nbq[lane] = (int)(unsigned)(key & 0xffffffffull);
-        }
-      }
-      if (!need && lane == 0) nbq[0] = -1;
-      __syncwarp();
-    }
-    __threadfence();
-    __syncthreads();
+    int32_t* list = job.nb + (size_t)job.n_src * job.k;  // [n_src] sorted positions of the target points to serve, per CTA slice
     for (int q = tid; q < cnt; q += kLmThreads) {
-      const int32_t* nbq = job.nb + (size_t)(base + q) * job.k;
-      if (nbq[0] < 0) continue;
-      const int pos = job.corr[base + q] & kCorrIndexMask;
-      lazy_target_covariance(job, nbq, pos);
+      const int c = job.corr[base + q];
+      if (c < 0) continue;
+      const int pos = c & kCorrIndexMask;
+      if (*((volatile unsigned char*)&job.t_cov_flag[pos]) == 0) list[base + atomicAdd(&smem.n_need, 1)] = pos;
     }
+    __syncthreads();
+    const int n_need = smem.n_need;
+    for (int li = warp; li < n_need; li += kLmWarps) {
+      const unsigned long long key = knnw::knn_warp_query(job.t_spts, job.t_cell_start, job.tg, job.k, list[base + li], lane, smem.kbuf[warp]);
+      if (lane < job.k) job.nb[(size_t)(base + li) * job.k + lane] = (int)(unsigned)(key & 0xffffffffull);
+    }
+    __syncthreads();
+    for (int li = tid; li < n_need; li += kLmThreads) lazy_target_covariance(job, job.nb + (size_t)(base + li) * job.k, list[base + li]);
     __threadfence();
     __syncthreads();
   }
@@ -476,6 +473,19 @@ __global__ void __launch_bounds__(kLmThreads, APD_LM_MINB) lm_kernel(LmJob one, 
     res->n_trace = z.n_rows;
     res->hessian_set = z.h_set;
   }
+  if (job.host_result && rank == 0) {
+    // publish: header and first trace rows to the host (one 8-byte word per thread), then the sequence number
+    __syncthreads();
+    constexpr int kWords = (int)((offsetof(LmResult, trace) + (size_t)kLmTraceHead * 8 * sizeof(double)) / 8);
+    constexpr int kSeqWord = (int)(offsetof(LmResult, seq) / 8);
+    const unsigned long long* srcw = reinterpret_cast<const unsigned long long*>(job.result);
+    unsigned long long* dstw = reinterpret_cast<unsigned long long*>(job.host_result);
+    for (int w = tid; w < kWords; w += kLmThreads)
+      if (w != kSeqWord) dstw[w] = srcw[w];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(&job.host_result->seq) = job.seq;
+  }
   cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
@@ -497,6 +507,14 @@ void launch_lm(const LmJob* one, const LmJob* d_jobs, int n_jobs, const LmConfig
   lc.numAttrs = 1;
   LmJob byval{};
   if (one) byval = *one;
+  if (cluster > 8) {  // beyond the portable cluster size: opt in once per kernel
+    static bool allowed = [] {
+      cudaFuncSetAttribute(lm_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      return true;
+    }();
+    (void)allowed;
+  }
   if (cfg.maha_fp64) cudaLaunchKernelEx(&lc, lm_kernel<true>, byval, d_jobs, cfg);
   else cudaLaunchKernelEx(&lc, lm_kernel<false>, byval, d_jobs, cfg);
   (*launches)++;
