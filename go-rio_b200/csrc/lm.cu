@@ -37,7 +37,10 @@ namespace {
 #endif
 constexpr int kLmThreads = APD_LM_THREADS;
 constexpr int kLmWarps = kLmThreads / 32;
-constexpr int kLmG = 8;  // lanes per 1-NN query (the search is latency-bound at these sizes)
+#ifndef APD_LM_G
+#define APD_LM_G 8
+#endif
+constexpr int kLmG = APD_LM_G;  // lanes per 1-NN query (the search is latency-bound at these sizes)
 
 __device__ __forceinline__ hm::Pose pose_from(const PoseD& T) {
   hm::Pose p = hm::Pose::identity();
