@@ -34,6 +34,8 @@ class ApdParams(C.Structure):
         ("lm_init_lambda_factor", C.c_double),
         ("maha_fp64", C.c_int32),
         ("host_loop", C.c_int32),
+        ("variant", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

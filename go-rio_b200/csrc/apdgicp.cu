@@ -135,6 +135,7 @@ struct Cloud {
   bool grid_valid = false;
   bool cov_valid = false;
   bool geo_valid = false;
+  int geo_variant = APD_VARIANT_APDGICP;  // what geo / geo64 hold: sigma3/sigma1 (APDGICP) or zeros (GICP: unit weights)
   // Covariances on demand (target of the device-resident loop): cov[w] is valid where cov_flag[w] == 1; computed with
   // lazy_k / lazy_reg, the parameters in force when the cloud's first covariance was asked for (the reference computes
   // all target covariances at that moment and keeps them across later parameter changes)
@@ -599,7 +600,7 @@ int allgather_chunks(apd_handle* h, void* base, int n, size_t elems_per_point, i
 int ensure_covariances_of(apd_handle* h, Cloud& c) {
   int rc = ensure_grid(h, c);
   if (rc != APD_OK) return rc;
-  if (c.cov_valid && c.geo_valid) return APD_OK;
+  if (c.cov_valid && c.geo_valid && c.geo_variant == h->params.variant) return APD_OK;
   const size_t np = h->padded_n(c.n);
   APD_CUDA(h, c.cov.ensure(np * 6 * sizeof(double)));
   APD_CUDA(h, c.geo.ensure(np * sizeof(float)));
@@ -630,11 +631,20 @@ int ensure_covariances_of(apd_handle* h, Cloud& c) {
     }
     c.cov_valid = true;
     c.geo_valid = true;
+    c.geo_variant = APD_VARIANT_APDGICP;
     c.cov_lazy = false;
-  } else if (!c.geo_valid) {  // after set*Covariances: every rank holds all covariances, the weight is a local map
+  } else if (!c.geo_valid || (c.geo_variant != h->params.variant && h->params.variant == APD_VARIANT_APDGICP)) {
+    // after set*Covariances (every rank holds all covariances, the weight is a local map), or back from GICP
     ProfScope ps(h, APD_K_KNN_COV);
     launch_geo_weight(c.view(), h->stream, &h->launches);
     c.geo_valid = true;
+    c.geo_variant = APD_VARIANT_APDGICP;
+  }
+  if (h->params.variant == APD_VARIANT_GICP && c.geo_variant != APD_VARIANT_GICP) {
+    // FastGICP weighs every term by 1 (fast_gicp_impl.hpp:205): 1 + geo + cl with geo = 0 and cl = 0 is exactly 1
+    APD_CUDA(h, cudaMemsetAsync(c.geo.p, 0, np * sizeof(float), h->stream));
+    APD_CUDA(h, cudaMemsetAsync(c.geo64.p, 0, np * sizeof(double), h->stream));
+    c.geo_variant = APD_VARIANT_GICP;
   }
   APD_CUDA(h, cudaGetLastError());
   return APD_OK;
@@ -741,7 +751,8 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
   w.partials = h->partials.as<double>();
   w.ticket = reinterpret_cast<unsigned int*>(d_out + 40);
   w.max_blocks = h->max_reduce_blocks / 2;  // persistent CTAs: 2 resident per SM
-  const double n_total = (double)h->src.n;  // correspondences_.size() (:273): the whole source cloud, sharded or not
+  // correspondences_.size() (:273): the whole source cloud, sharded or not; GICP has no label weight (1 / inf = 0)
+  const double n_total = h->params.variant == APD_VARIANT_GICP ? std::numeric_limits<double>::infinity() : (double)h->src.n;
   {
     ProfScope ps(h, want_hb ? APD_K_LINEARIZE : APD_K_ERROR);
     for (int j = 0; j < h->shard_subs(); j++) {  // chunks after the first add onto the 28 (1) sums of the previous ones
@@ -899,6 +910,7 @@ int adopt_cloud(apd_handle* h, Cloud& dst, const Cloud& src) {
   dst.grid_valid = src.grid_valid;
   dst.cov_valid = src.grid_valid && src.cov_valid;
   dst.geo_valid = dst.cov_valid && src.geo_valid;
+  dst.geo_variant = src.geo_variant;
   dst.cov_lazy = false;  // (a partly computed target is not adopted: the new owner computes what it needs)
   return APD_OK;
 }
@@ -1041,6 +1053,7 @@ NoiseParams noise_params(const apd_params& p) {
   np.sin_el = std::sin(p.elevation_var / 180 * M_PI);  // :197
   const double thr = p.max_correspondence_distance;
   np.thr_sq = thr * thr;  // :183 (double product)
+  np.gicp = p.variant == APD_VARIANT_GICP ? 1 : 0;
   np.search_limit = (float)thr;
   return np;
 }
@@ -1084,7 +1097,7 @@ LmJob lm_job(apd_handle* h, const hm::Pose& x0) {
   j.tg = t.g;
   j.n_src = s.n;
   j.corr = h->corr.as<int>(); j.sqd = h->sqd.as<float>(); j.mahaA = h->mahaA.p; j.mahaB = h->mahaB.p;
-  j.cl_w = 1.0 / (double)s.n;  // 1.0 / correspondences_.size() (:273)
+  j.cl_w = h->params.variant == APD_VARIANT_GICP ? 0.0 : 1.0 / (double)s.n;  // 1.0 / correspondences_.size() (:273); GICP: unit weights
   for (int r = 0; r < 3; r++) {
     for (int c = 0; c < 3; c++) j.guess[r * 3 + c] = x0(r, c);
     j.guess[9 + r] = x0(r, 3);
@@ -1341,6 +1354,8 @@ int apd_set_params(apd_handle* h, const apd_params* p) {
   if (!h || !p) return APD_ERR_INVALID;
   const bool cov_dep = p->k_correspondences != h->params.k_correspondences || p->regularization != h->params.regularization;
   if (p->regularization < APD_REG_NONE || p->regularization > APD_REG_FROBENIUS) return fail(h, APD_ERR_INVALID, "bad regularization");
+  if (p->variant != APD_VARIANT_APDGICP && p->variant != APD_VARIANT_GICP) return fail(h, APD_ERR_INVALID, "bad variant");
+  if (p->variant != h->params.variant) h->corr_warm = false;  // (the stored Mahalanobis matrices are the other variant's)
   h->params = *p;
   (void)cov_dep;  // reference: changing k / regularisation does NOT drop cached covariances either
   return APD_OK;

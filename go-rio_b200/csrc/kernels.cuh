@@ -74,6 +74,7 @@ struct NoiseParams {
   double sin_el;        // sin(elevation_variance_ / 180 * pi)
   double thr_sq;        // corr_dist_threshold_^2 (double product)
   float search_limit;   // radius (m) beyond which no correspondence can pass the threshold; inf if none
+  int gicp;             // 1: FastGICP's combined covariance C_B + T C_A T^T (fast_gicp_impl.hpp:157) — no noise term
 };
 struct CorrOut {
   int* corr;      // [n_src] sorted order of the source

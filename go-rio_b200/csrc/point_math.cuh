@@ -187,42 +187,47 @@ __device__ __forceinline__ PoseF pose_to_f32(const PoseD& T) {
 // source point and of its matched target point (symmetric-6).
 __device__ __forceinline__ Sym3 mahalanobis_of(float px, float py, float pz, const double* __restrict__ ca_in,
                                                const double* __restrict__ cb_in, const PoseD& T, const NoiseParams& np) {
-  // radar noise covariance at the transformed point (:194-210)
-  const double dpx = (double)px, dpy = (double)py, dpz = (double)pz;
-  const double dist = sqrt(dpx * dpx + dpy * dpy + dpz * dpz);
-  const double s_x = dist * np.dist_var / 400;
-  const double s_y = dist * np.sin_az;
-  const double s_z = dist * np.sin_el;
-  const float rho_xy = __fsqrt_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)));
-  // float-valued angles as in the reference (atan2f); evaluated in double and rounded to float
-  const double elevation = (double)(float)atan2((double)rho_xy, dpz);
-  const double azimuth = (double)(float)atan2(dpy, dpx);
-  double sz_, cz_, sy_, cy_;
-  sincos(azimuth * 0.5, &sz_, &cz_);
-  sincos(elevation * 0.5, &sy_, &cy_);
-  // quaternion of AngleAxis(az, Z) * AngleAxis(el, Y) -> rotation matrix (Eigen toRotationMatrix)
-  const double qw = cz_ * cy_, qx = -(sz_ * sy_), qy = cz_ * sy_, qz = sz_ * cy_;
-  const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
-  const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
-  const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
-  const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
-  double R[9];
-  R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
-  R[3] = txy + twz; R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
-  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.0 - (txx + tyy);
-  const double sc[3] = {s_x, s_y, s_z};
-  double A[9];
+  Sym3 cr;  // cov_r (:204-210); FastGICP has none: adding exact zeros below leaves C_A and C_B as they are
 #pragma unroll
-  for (int r = 0; r < 3; r++)
+  for (int e = 0; e < 6; e++) cr.v[e] = 0.0;
+  if (!np.gicp) {
+    // radar noise covariance at the transformed point (:194-210)
+    const double dpx = (double)px, dpy = (double)py, dpz = (double)pz;
+    const double dist = sqrt(dpx * dpx + dpy * dpy + dpz * dpz);
+    const double s_x = dist * np.dist_var / 400;
+    const double s_y = dist * np.sin_az;
+    const double s_z = dist * np.sin_el;
+    const float rho_xy = __fsqrt_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)));
+    // float-valued angles as in the reference (atan2f); evaluated in double and rounded to float
+    const double elevation = (double)(float)atan2((double)rho_xy, dpz);
+    const double azimuth = (double)(float)atan2(dpy, dpx);
+    double sz_, cz_, sy_, cy_;
+    sincos(azimuth * 0.5, &sz_, &cz_);
+    sincos(elevation * 0.5, &sy_, &cy_);
+    // quaternion of AngleAxis(az, Z) * AngleAxis(el, Y) -> rotation matrix (Eigen toRotationMatrix)
+    const double qw = cz_ * cy_, qx = -(sz_ * sy_), qy = cz_ * sy_, qz = sz_ * cy_;
+    const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
+    const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+    const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+    const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    double R[9];
+    R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.0 - (txx + tyy);
+    const double sc[3] = {s_x, s_y, s_z};
+    double A[9];
 #pragma unroll
-    for (int c = 0; c < 3; c++) A[r * 3 + c] = R[r * 3 + c] * sc[c];
-  Sym3 cr;  // cov_r = A A^T
-  cr.v[0] = A[0] * A[0] + A[1] * A[1] + A[2] * A[2];
-  cr.v[1] = A[0] * A[3] + A[1] * A[4] + A[2] * A[5];
-  cr.v[2] = A[0] * A[6] + A[1] * A[7] + A[2] * A[8];
-  cr.v[3] = A[3] * A[3] + A[4] * A[4] + A[5] * A[5];
-  cr.v[4] = A[3] * A[6] + A[4] * A[7] + A[5] * A[8];
-  cr.v[5] = A[6] * A[6] + A[7] * A[7] + A[8] * A[8];
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) A[r * 3 + c] = R[r * 3 + c] * sc[c];
+    // cov_r = A A^T
+    cr.v[0] = A[0] * A[0] + A[1] * A[1] + A[2] * A[2];
+    cr.v[1] = A[0] * A[3] + A[1] * A[4] + A[2] * A[5];
+    cr.v[2] = A[0] * A[6] + A[1] * A[7] + A[2] * A[8];
+    cr.v[3] = A[3] * A[3] + A[4] * A[4] + A[5] * A[5];
+    cr.v[4] = A[3] * A[6] + A[4] * A[7] + A[5] * A[8];
+    cr.v[5] = A[6] * A[6] + A[7] * A[7] + A[8] * A[8];
+  }
 
   // RCR = (cov_B + cov_r) + T (cov_A + cov_r) T^T (:213-215), 3x3 block
   Sym3 ca, cb;

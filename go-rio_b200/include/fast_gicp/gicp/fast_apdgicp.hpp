@@ -223,6 +223,7 @@ private:
     p.lm_debug_print = lm_debug_print_ ? 1 : 0;
     p.lm_init_lambda_factor = lm_init_lambda_factor_;
     p.maha_fp64 = maha_fp64_ ? 1 : 0;
+    p.variant = variant_;
     apd_set_params(handle_, &p);
   }
 
@@ -235,6 +236,7 @@ protected:
   double distance_variance_ = 0.86;
   mutable CovarianceVector source_covs_, target_covs_;
   mutable bool source_covs_valid_ = false, target_covs_valid_ = false;
+  int variant_ = APD_VARIANT_APDGICP;  // fast_gicp.hpp's FastGICP sets APD_VARIANT_GICP
 
 private:
   apd_handle* handle_ = nullptr;

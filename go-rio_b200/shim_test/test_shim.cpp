@@ -2,12 +2,16 @@
 // select_registration_method (registrations.cpp:38-51) constructs and configures
 // it, then the nodelets use it through pcl::Registration::Ptr
 // (scan_matching_odometry_nodelet.cpp:430-490, loop_detector.cpp:222-236).
-// usage: test_shim source.f32 n_source target.f32 n_target   (float32 [n,4] = x,y,z,label)
+// usage: test_shim source.f32 n_source target.f32 n_target [gicp]   (float32 [n,4] = x,y,z,label)
+// "gicp": the factory's FAST_GICP branch (registrations.cpp:28-37) instead of FAST_APDGICP
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 
+#include <cstring>
+
 #include <fast_gicp/gicp/fast_apdgicp.hpp>
+#include <fast_gicp/gicp/fast_gicp.hpp>
 
 using PointT = pcl::PointXYZINormal;
 
@@ -26,7 +30,16 @@ static pcl::PointCloud<PointT>::Ptr load(const char* path, int n) {
 }
 
 // the reference factory, registrations.cpp:38-51, with the deployed rosparam values (launch/ntu_loop2.launch:88-99)
-static pcl::Registration<PointT, PointT>::Ptr select_registration_method() {
+static pcl::Registration<PointT, PointT>::Ptr select_registration_method(bool fast_gicp_branch) {
+  if (fast_gicp_branch) {  // registrations.cpp:28-37
+    fast_gicp::FastGICP<PointT, PointT>::Ptr gicp(new fast_gicp::FastGICP<PointT, PointT>());
+    gicp->setNumThreads(0);
+    gicp->setTransformationEpsilon(0.1);
+    gicp->setMaximumIterations(64);
+    gicp->setMaxCorrespondenceDistance(2.0);
+    gicp->setCorrespondenceRandomness(20);
+    return gicp;
+  }
   fast_gicp::FastAPDGICP<PointT, PointT>::Ptr apdgicp(new fast_gicp::FastAPDGICP<PointT, PointT>());
   apdgicp->setNumThreads(0);
   apdgicp->setTransformationEpsilon(0.1);
@@ -43,7 +56,7 @@ int main(int argc, char** argv) {
   if (argc < 5) return 2;
   auto source = load(argv[1], std::atoi(argv[2]));
   auto target = load(argv[3], std::atoi(argv[4]));
-  pcl::Registration<PointT, PointT>::Ptr registration = select_registration_method();
+  pcl::Registration<PointT, PointT>::Ptr registration = select_registration_method(argc > 5 && std::strcmp(argv[5], "gicp") == 0);
   registration->setInputTarget(target);
   registration->setInputSource(source);
   pcl::PointCloud<PointT>::Ptr aligned(new pcl::PointCloud<PointT>());

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define APD_ABI_VERSION 1
+#define APD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define APD_API __attribute__((visibility("default")))
@@ -61,6 +61,12 @@ enum {
   APD_REG_PLANE = 3,
   APD_REG_FROBENIUS = 4
 };
+
+/* Which cost the registration minimises. APDGICP: fast_apdgicp_impl.hpp (radar noise model in the combined
+ * covariance, :194-215; per-point weight 1 + geometric + label weight, :266-276). GICP: the reference's FastGICP
+ * (fast_gicp_impl.hpp:124-258, selected by registrations.cpp:28-37): the same covariances, correspondences and
+ * optimizer, RCR = C_B + T C_A T^T (:157) and unit weights (:205) — dist/azimuth/elevation_var are not read. */
+enum { APD_VARIANT_APDGICP = 0, APD_VARIANT_GICP = 1 };
 
 /* reference lsq_registration.hpp:13 — same order */
 enum { APD_OPT_GAUSS_NEWTON = 0, APD_OPT_LEVENBERG_MARQUARDT = 1 };
@@ -94,6 +100,8 @@ typedef struct apd_params {
                                           not sharded; 1: always drive it from the
                                           host, one launch per stage (what large
                                           or sharded clouds use anyway).         */
+  int32_t variant;                     /* APD_VARIANT_APDGICP (default) / _GICP  */
+  int32_t reserved_;                   /* 0                                      */
 } apd_params;
 
 typedef struct apd_handle apd_handle;

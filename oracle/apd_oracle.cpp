@@ -87,6 +87,8 @@ FastAPDGICP::FastAPDGICP() {
   params.lm_init_lambda_factor = 1e-9;
   params.maha_fp64 = 1;
   params.host_loop = 0;
+  params.variant = APD_VARIANT_APDGICP;
+  params.reserved_ = 0;
   final_pose_f64 = M4::identity();
   for (int i = 0; i < 16; i++) final_transformation[i] = (i % 5 == 0) ? 1.f : 0.f;
   for (int i = 0; i < 36; i++) final_hessian[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity() (:23)
@@ -296,6 +298,11 @@ void FastAPDGICP::update_correspondences(const M4& trans) {
     const int target_index = correspondences[i];
     const M3& cov_A = source_covs[i];
     const M3& cov_B = target_covs[target_index];
+    if (params.variant == APD_VARIANT_GICP) {
+      // FastGICP (fast_gicp_impl.hpp:157-161): RCR = cov_B + T cov_A T^T, no noise term
+      mahalanobis[i] = inverse3(add3(cov_B, mul3(mul3(R3, cov_A), R3t)));
+      continue;
+    }
 
     // :194-199 radar noise at the transformed source point
     const double dist = std::sqrt((double)px * (double)px + (double)py * (double)py + (double)pz * (double)pz);
@@ -356,14 +363,15 @@ inline bool point_terms(const FastAPDGICP& g, const M4& trans, int i, bool want_
     tA[r] = ((trans(r, 0) * mean_A[0] + trans(r, 1) * mean_A[1]) + trans(r, 2) * mean_A[2]) + trans(r, 3);
     e[r] = mean_B[r] - tA[r];
   }
-  const double geo_weight = geo_weight_of(g.source_covs[i]);  // :266-269 (recomputed per call, as the reference does)
+  const bool gicp = g.params.variant == APD_VARIANT_GICP;  // FastGICP: sum_errors += e^T M e (fast_gicp_impl.hpp:205,:255)
+  const double geo_weight = gicp ? 0.0 : geo_weight_of(g.source_covs[i]);  // :266-269 (recomputed per call, as the reference does)
   double cl_weight = 0.0;
-  if (bpt.label == a.label) cl_weight = 1.0 / (double)g.correspondences.size();  // :271-273
+  if (!gicp && bpt.label == a.label) cl_weight = 1.0 / (double)g.correspondences.size();  // :271-273
   const M3& M = g.mahalanobis[i];
   double Me[3];
   for (int r = 0; r < 3; r++) Me[r] = (M(r, 0) * e[0] + M(r, 1) * e[1]) + M(r, 2) * e[2];
   const double q = (e[0] * Me[0] + e[1] * Me[1]) + e[2] * Me[2];
-  out.err = (1.0 + geo_weight + cl_weight) * q;  // :276
+  out.err = gicp ? q : (1.0 + geo_weight + cl_weight) * q;  // :276
   if (!want_hb) return true;
   // :284-287 J = [skew(T a), -I] (3x6; the 4th row is zero)
   double J[3][6] = {{0}};

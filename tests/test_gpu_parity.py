@@ -326,6 +326,65 @@ def test_device_loop_cluster_sizes(gorio, c2_small, monkeypatch, cluster):
     assert dt < 1e-7 and dr < 1e-7, (dt, dr)
 
 
+# ------------------------------------------------- FastGICP behind the same kernels ----
+GICP = dict(variant=1)  # APD_VARIANT_GICP: reference fast_gicp_impl.hpp (registrations.cpp:28-37 "FAST_GICP")
+
+
+@pytest.mark.parametrize("host_loop", [0, 1])
+@pytest.mark.parametrize("thr", [2.0, None])
+def test_gicp_variant_align_parity(gorio, synth, c1, c2_small, host_loop, thr):
+    """FastGICP = the combined covariance without the radar noise term (fast_gicp_impl.hpp:157) and unit weights
+    (:205); everything else is the APDGICP path. Same bars as APDGICP against the oracle's FastGICP."""
+    kw = dict(**GICP, maha_fp64=1, host_loop=host_loop)
+    if thr is not None:
+        kw["max_correspondence_distance"] = thr
+    for src, tgt, _ in (c1, c2_small):
+        g, o = make(gorio, src, tgt, **kw)
+        rg, ro = _check_align(g, o)
+        assert np.array_equal(g.get_correspondences()[0], o.get_correspondences()[0])
+        assert rel(g.get_mahalanobis(), o.get_mahalanobis()) < 1e-9
+        # and it is a different cost from APDGICP's
+        ga, _ = make(gorio, src, tgt, **{**kw, "variant": 0})
+        assert not np.array_equal(ga.align()["T64"], rg["T64"])
+
+
+def test_gicp_variant_linearize_and_switching(gorio, synth, c1):
+    src, tgt, _ = c1
+    g, o = make(gorio, src, tgt, **GICP, max_correspondence_distance=2.0, maha_fp64=1)
+    t, rpy = POSES[1]
+    T = synth.make_pose(t, np.deg2rad(rpy))
+    eg, Hg, bg = g.linearize(T)
+    eo, Ho, bo = o.linearize(T)
+    assert rel(Hg, Ho) < 1e-10 and rel(bg, bo) < 1e-9 and abs(eg - eo) / eo < 1e-10
+    assert abs(g.compute_error(T) - o.compute_error(T)) / eo < 1e-10
+    # the radar noise parameters are not read
+    g.set_params(dist_var=5.0, azimuth_var=3.0, elevation_var=4.0)
+    assert g.linearize(T)[0] == eg
+    # switching the variant on a live handle: the weights and the stored Mahalanobis matrices follow
+    for r in (g, o):
+        r.set_params(variant=0, dist_var=0.86, azimuth_var=0.5, elevation_var=1.0)
+    ea, eoa = g.linearize(T)[0], o.linearize(T)[0]
+    assert abs(ea - eoa) / eoa < 1e-10 and ea != eg
+    for r in (g, o):
+        r.set_params(variant=1)
+    assert g.linearize(T)[0] == eg
+    with pytest.raises(gorio.ApdError):
+        g.set_params(variant=7)
+
+
+def test_gicp_variant_in_a_pool(gorio, synth, monkeypatch):
+    monkeypatch.setenv("APD_LM_CLUSTER", "4")
+    pairs = [synth.submap_pair(3100 + i, n_source=600, n_frames=4, n_per_frame=1000)[:2] + (None,) for i in range(4)]
+    b = gorio.Batch(0, n_workers=4, max_correspondence_distance=2.0, transformation_epsilon=0.1, variant=1)
+    res = b.align(b.prepare(pairs))
+    b.close()
+    for (s, t, _), r in zip(pairs, res):
+        g = gorio.FastAPDGICP(0)
+        g.set_params(max_correspondence_distance=2.0, transformation_epsilon=0.1, variant=1)
+        g.set_input_target(t); g.set_input_source(s)
+        assert r["status"] == 0 and np.array_equal(r["T"], g.align()["T"])
+
+
 def _handle(gorio, monkeypatch, lazy, src, tgt, **kw):
     monkeypatch.setenv("APD_LAZY_TARGET_COV", lazy)
     g = gorio.FastAPDGICP(0)
@@ -539,6 +598,9 @@ def test_error_codes(gorio, c1):
 
 # --------------------------------------------------------------- fitness ----
 def test_fitness_parity(gorio, synth, c2_small):
+    """pcl getFitnessScore(max_range) of the final pose, and — with an explicit pose and a finite max_range —
+    InformationMatrixCalculator::calc_fitness_score(cloud1 = target, cloud2 = source, relpose, max_range)
+    (information_matrix_calculator.cpp:55-86): the same mean of 1-NN squared distances within max_range."""
     src, tgt, Tgt = c2_small
     g, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
     for T in (None, Tgt.astype(np.float32)):

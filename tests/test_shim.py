@@ -34,17 +34,18 @@ def test_shim_keeps_the_reference_surface():
 
 
 @pytest.mark.gpu
-def test_shim_matches_the_c_abi(gorio, synth, tmp_path):
+@pytest.mark.parametrize("variant", ["apdgicp", "gicp"])
+def test_shim_matches_the_c_abi(gorio, synth, tmp_path, variant):
     exe = os.path.join(SHIM_DIR, "test_shim")
     if not os.path.exists(exe):
         subprocess.check_call(["bash", os.path.join(SHIM_DIR, "build.sh")])
     src, tgt, _ = synth.submap_pair(2002, n_source=1000, n_frames=5, n_per_frame=1500)
     fs, ft = str(tmp_path / "s.f32"), str(tmp_path / "t.f32")
     src.tofile(fs); tgt.tofile(ft)
-    out = subprocess.run([exe, fs, str(src.shape[0]), ft, str(tgt.shape[0])], capture_output=True, text=True, check=True)
+    out = subprocess.run([exe, fs, str(src.shape[0]), ft, str(tgt.shape[0]), variant], capture_output=True, text=True, check=True)
     r = json.loads(out.stdout.strip().splitlines()[-1])
     g = gorio.FastAPDGICP(0)
-    g.set_params(max_correspondence_distance=2.0, transformation_epsilon=0.1)
+    g.set_params(max_correspondence_distance=2.0, transformation_epsilon=0.1, variant=1 if variant == "gicp" else 0)
     g.set_input_target(synth.to_pcl_xyzinormal(tgt)); g.set_input_source(synth.to_pcl_xyzinormal(src))
     ra = g.align(want_aligned=True)
     assert bool(r["converged"]) == ra["converged"]
