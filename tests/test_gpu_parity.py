@@ -641,13 +641,16 @@ def test_align_batch_matches_sequential(gorio, synth, monkeypatch):
     b = gorio.Batch(0, n_workers=4, max_correspondence_distance=2.0, transformation_epsilon=0.1)
     dev = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for s, t, _ in pairs for x in (s, t)]
     dpairs = [((dev[2 * i].data_ptr(), pairs[i][0].shape[0]), (dev[2 * i + 1].data_ptr(), pairs[i][1].shape[0]), None) for i in range(len(pairs))]
-    for prepared in (b.prepare(pairs), b.prepare(dpairs)):
+    # ... and for host clouds in page-locked memory, which the pool copies from directly (no staging pass)
+    pin = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for s, t, _ in pairs for x in (s, t)]
+    ppairs = [(pin[2 * i].numpy(), pin[2 * i + 1].numpy(), None) for i in range(len(pairs))]
+    for prepared in (b.prepare(pairs), b.prepare(dpairs), b.prepare(ppairs)):
         for _ in range(2):
             res2 = b.align(prepared)
             for r, r2 in zip(res, res2):
                 assert r2["status"] == 0 and np.array_equal(r["T"], r2["T"]) and r["fitness"] == r2["fitness"]
                 assert (r["converged"], r["iterations"], r["n_inliers"]) == (r2["converged"], r2["iterations"], r2["n_inliers"])
-    assert b.kernel_ms()["lm"][1] == 4 * len(pairs)
+    assert b.kernel_ms()["lm"][1] == 6 * len(pairs)
     b.close()
 
 
