@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Generates tests/golden/apdgicp_c1_small.npz — known-answer vectors for the FastAPDGICP path.
+"""Generates tests/golden/apdgicp_c1_small.npz — known-answer vectors for the FastAPDGICP path — and
+tests/golden/fastgicp_c1_small.npz — the same for the FastGICP variant (apd_params.variant = 1) on the same clouds.
 
 The reference holds no golden vector, test or fixture for FastAPDGICP and cannot be built in
 this image (no Eigen / PCL / FLANN), so these vectors come from the CPU oracle (oracle/, a line-by-line
@@ -7,7 +8,8 @@ restatement of fast_apdgicp_impl.hpp / lsq_registration_impl.hpp), AFTER this sc
 against the independent NumPy/SciPy restatement (tests/numpy_restatement.py) on the same inputs. The input
 clouds are stored in the file, so the fixture does not depend on the synthetic generator staying unchanged.
 
-    python tests/golden/make_golden.py        # rewrites the .npz (run from the repo root)
+    python tests/golden/make_golden.py        # rewrites both .npz (run from the repo root)
+    python tests/golden/make_golden.py gicp   # only the FastGICP one
 """
 import importlib
 import os
@@ -25,6 +27,7 @@ import numpy_restatement as nr  # noqa: E402
 from oracle_binding import Oracle  # noqa: E402
 
 OUT = os.path.join(HERE, "apdgicp_c1_small.npz")
+OUT_GICP = os.path.join(HERE, "fastgicp_c1_small.npz")
 DEPLOYED = dict(max_correspondence_distance=2.0, transformation_epsilon=0.1)
 
 
@@ -32,7 +35,8 @@ def sym6(c4):  # n x 4 x 4 -> n x 6 (xx xy xz yy yz zz)
     return np.stack([c4[:, 0, 0], c4[:, 0, 1], c4[:, 0, 2], c4[:, 1, 1], c4[:, 1, 2], c4[:, 2, 2]], axis=1)
 
 
-def main():
+def main(variant=0, path=OUT):
+    gicp = variant == 1
     synth = importlib.import_module("go-rio_b200.synth")
     src, tgt, T_true = synth.scan_pair(4242, 400)
     src, tgt = np.ascontiguousarray(src), np.ascontiguousarray(tgt)
@@ -41,7 +45,7 @@ def main():
 
     def fresh(**kw):
         o = Oracle(search=0)  # brute force: the definitional search
-        o.set_params(maha_fp64=1, **kw)
+        o.set_params(maha_fp64=1, variant=variant, **kw)
         o.set_input_target(tgt)
         o.set_input_source(src)
         return o
@@ -60,8 +64,8 @@ def main():
     for name, T in (("I", np.eye(4)), ("P2", pose2)):
         err, H, b = o.linearize(T)
         c, sq = o.get_correspondences()
-        Mn = nr.mahalanobis(T, src, tgt, cov_s[:, :3, :3], cov_t[:, :3, :3], c)
-        en, Hn, bn = nr.linearize(T, src, tgt, cov_s[:, :3, :3], c, Mn)
+        Mn = nr.mahalanobis(T, src, tgt, cov_s[:, :3, :3], cov_t[:, :3, :3], c, gicp=gicp)
+        en, Hn, bn = nr.linearize(T, src, tgt, cov_s[:, :3, :3], c, Mn, gicp=gicp)
         assert abs(err - en) / en < 1e-10 and np.abs(H - Hn).max() / np.abs(Hn).max() < 1e-10 and np.abs(b - bn).max() / np.abs(bn).max() < 1e-9
         out[f"corr_{name}"], out[f"sqd_{name}"] = c, sq
         out[f"maha_{name}"] = sym6(o.get_mahalanobis())
@@ -76,9 +80,11 @@ def main():
         out[f"{name}_trace"] = o2.lm_trace()
         s, n_in, n_inl = o2.fitness()
         out[f"{name}_fitness"] = np.array([s, n_in, n_inl], np.float64)
-    np.savez_compressed(OUT, **out)
-    print("wrote", OUT, os.path.getsize(OUT), "bytes;", "LM deployed:", out["lm_deployed_flags"], "GN:", out["gn_flags"])
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", "LM deployed:", out["lm_deployed_flags"], "GN:", out["gn_flags"])
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] != "gicp":
+        main(0, OUT)
+    main(1, OUT_GICP)

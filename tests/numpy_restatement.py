@@ -63,10 +63,10 @@ def transform_f32(T, xyz32):
     return out
 
 
-def mahalanobis(T, src, tgt, cov_src, cov_tgt, corr, dist_var=0.86, az_var=0.5, el_var=1.0):
-    """fast_apdgicp_impl.hpp:193-218 given the correspondences."""
+def mahalanobis(T, src, tgt, cov_src, cov_tgt, corr, dist_var=0.86, az_var=0.5, el_var=1.0, gicp=False):
+    """fast_apdgicp_impl.hpp:193-218 given the correspondences; gicp: fast_gicp_impl.hpp:157-161 (no noise term)."""
     pt = transform_f32(T, src[:, :3])
-    cov_r = noise_cov(pt, dist_var, az_var, el_var)
+    cov_r = np.zeros((src.shape[0], 3, 3)) if gicp else noise_cov(pt, dist_var, az_var, el_var)
     R = T[:3, :3]
     valid = corr >= 0
     M = np.zeros((src.shape[0], 3, 3))
@@ -76,8 +76,8 @@ def mahalanobis(T, src, tgt, cov_src, cov_tgt, corr, dist_var=0.86, az_var=0.5, 
     return M
 
 
-def linearize(T, src, tgt, cov_src, corr, M):
-    """fast_apdgicp_impl.hpp:247-304 given correspondences and Mahalanobis."""
+def linearize(T, src, tgt, cov_src, corr, M, gicp=False):
+    """fast_apdgicp_impl.hpp:247-304 given correspondences and Mahalanobis; gicp: fast_gicp_impl.hpp:168-237 (unit weights)."""
     n = src.shape[0]
     valid = corr >= 0
     a = src[:, :3].astype(np.float64)
@@ -88,7 +88,7 @@ def linearize(T, src, tgt, cov_src, corr, M):
     geo = sv[:, 2] / sv[:, 0]
     cl = np.where(tgt[np.where(valid, corr, 0), 3] == src[:, 3], 1.0 / n, 0.0)
     q = np.einsum("ni,nij,nj->n", e, M, e)
-    err = ((1.0 + geo + cl) * q)[valid].sum()
+    err = (q if gicp else (1.0 + geo + cl) * q)[valid].sum()
     J = np.zeros((n, 3, 6))
     J[:, 0, 1] = -tA[:, 2]; J[:, 0, 2] = tA[:, 1]
     J[:, 1, 0] = tA[:, 2];  J[:, 1, 2] = -tA[:, 0]

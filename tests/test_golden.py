@@ -13,14 +13,18 @@ from helpers import pose_err, rel
 from oracle_binding import Oracle
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "apdgicp_c1_small.npz")
+GOLD_GICP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fastgicp_c1_small.npz")  # variant = 1
 DEPLOYED = dict(max_correspondence_distance=2.0, transformation_epsilon=0.1)
 ALIGNS = {"lm_deployed": DEPLOYED, "lm_default": dict(max_correspondence_distance=2.0),
           "gn": dict(max_correspondence_distance=2.0, optimizer=0, max_iterations=6)}
 
 
-@pytest.fixture(scope="module")
-def gold():
-    return dict(np.load(GOLD))
+@pytest.fixture(scope="module", params=[0, 1], ids=["apdgicp", "fastgicp"])
+def gold(request):
+    """the fixture of one variant; gold["variant"] is passed on to set_params"""
+    g = dict(np.load(GOLD_GICP if request.param else GOLD))
+    g["variant"] = request.param
+    return g
 
 
 def sym6(c4):
@@ -66,12 +70,12 @@ def check_align(r, gold, name):
 def test_oracle_reproduces_the_fixture(gold, synth):
     for search in (0, 1):  # brute force (what made the fixture) and the oracle's kd-tree
         o = Oracle(search=search)
-        o.set_params(maha_fp64=1, **DEPLOYED)
+        o.set_params(maha_fp64=1, variant=gold["variant"], **DEPLOYED)
         o.set_input_target(gold["target"]); o.set_input_source(gold["source"])
         check(o, gold, synth, 1e-13, 1e-12, 1e-11)
     for name, kw in ALIGNS.items():
         o = Oracle(search=1)
-        o.set_params(maha_fp64=1, **kw)
+        o.set_params(maha_fp64=1, variant=gold["variant"], **kw)
         o.set_input_target(gold["target"]); o.set_input_source(gold["source"])
         check_align(o, gold, name)
 
@@ -89,7 +93,7 @@ def test_fixture_is_a_registration_problem(gold):
 @pytest.mark.parametrize("fp64", [1, 0])
 def test_cuda_matches_the_fixture(gorio, gold, synth, fp64):
     g = gorio.FastAPDGICP(0)
-    g.set_params(maha_fp64=fp64, **DEPLOYED)
+    g.set_params(maha_fp64=fp64, variant=gold["variant"], **DEPLOYED)
     g.set_input_target(gold["target"]); g.set_input_source(gold["source"])
     # fp64 Mahalanobis storage: only summation order differs (1e-10); fp32 storage (default): 1e-6 (north_star: 1e-5 on H)
     check(g, gold, synth, 1e-9, 1e-10 if fp64 else 1e-6, 1e-9 if fp64 else 1e-5)
@@ -100,6 +104,6 @@ def test_cuda_matches_the_fixture(gorio, gold, synth, fp64):
 @pytest.mark.parametrize("host_loop", [0, 1])
 def test_cuda_align_matches_the_fixture(gorio, gold, name, host_loop):
     g = gorio.FastAPDGICP(0)
-    g.set_params(maha_fp64=1, host_loop=host_loop, **ALIGNS[name])
+    g.set_params(maha_fp64=1, host_loop=host_loop, variant=gold["variant"], **ALIGNS[name])
     g.set_input_target(gold["target"]); g.set_input_source(gold["source"])
     check_align(g, gold, name)
