@@ -70,7 +70,6 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 constexpr int kNcclFloat64 = 8;  // ncclDouble
-constexpr int kNcclFloat32 = 7;  // ncclFloat
 constexpr int kNcclSum = 0;      // ncclSum
 
 // -------------------------------------------------------------- buffers ----
@@ -305,10 +304,10 @@ namespace {
     }                                                                                     \
   } while (0)
 
-// Wait for everything enqueued on the handle's stream. A lone handle spins (lowest latency). Handles of a large batch
-// pool — many more host threads than cores — sleep and poll the stream every poll_wait_us: their per-pair latency (ms) hides
-// a 0.2 ms poll, and unlike blocking-sync events it costs no interrupt per wait (measured on 8 x B200, 32 host cores, 256
-// worker threads: 46.1 k registrations/s with polling against 22.6 k with blocking-sync events; 1 GPU: 6.3 k either way).
+// Wait for everything enqueued on the handle's stream (the paths that do not publish into pinned memory: host-driven
+// loop, parity hooks, APD_ZERO_COPY=0). A lone handle spins (lowest latency); handles of a batch pool sleep and poll the
+// stream every poll_wait_us — unlike blocking-sync events that costs no interrupt per wait (8 x B200, 256 waiting
+// threads: 46.1 k registrations/s with polling against 22.6 k with blocking-sync events).
 cudaError_t wait_stream(apd_handle* h) {
   if (!h->blocking_wait) return cudaStreamSynchronize(h->stream);
   if (h->poll_wait_us > 0) {  // sleep-and-poll: no interrupt per wait (APD_POLL_WAIT_US)

@@ -227,7 +227,9 @@ typedef struct apd_result {
  * already set — it must be loaded before the process creates its CUDA context.) apd_batch_align runs n_pairs independent
  * {clearTarget; clearSource; setInputTarget; setInputSource; align
  * [; getFitnessScore]} sequences over them: the staging and H2D copy of one
- * pair overlap the kernels of the others. With with_fitness != 0 the result
+ * pair overlap the kernels of the others. Packed float4 {x,y,z,label} clouds
+ * (stride 16, xyz_off 0, label_off 12) in page-locked host memory are copied
+ * without a staging pass. With with_fitness != 0 the result
  * carries getFitnessScore(DBL_MAX) of the final pose and the number of source
  * points whose nearest target point is closer than 0.5 m (the inlier test of
  * scan_matching_odometry_nodelet.cpp:677-689). Results do not depend on

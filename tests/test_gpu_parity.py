@@ -654,6 +654,21 @@ def test_align_batch_matches_sequential(gorio, synth, monkeypatch):
     b.close()
 
 
+def test_pool_reports_errors_per_pair(gorio, synth):
+    """a pair that cannot be registered (fewer source points than k: APD_ERR_TOO_FEW, where the reference reads
+    uninitialised memory) fails alone; the pool carries on with the others, call after call"""
+    good = synth.submap_pair(3200, n_source=600, n_frames=4, n_per_frame=1000)
+    bad_src = good[0][:7].copy()
+    pairs = [(good[0], good[1], None), (bad_src, good[1], None), (good[0], good[1], None), (good[0][:300].copy(), good[1], None)]
+    b = gorio.Batch(0, n_workers=3, max_correspondence_distance=2.0, transformation_epsilon=0.1)
+    prepared = b.prepare(pairs)
+    for _ in range(2):
+        res = b.align(prepared)
+        assert [r["status"] for r in res] == [0, 3, 0, 0]
+        assert np.array_equal(res[0]["T"], res[2]["T"]) and res[0]["converged"]
+    b.close()
+
+
 def test_large_cloud_properties(gorio, synth):
     """2 M points (size-independent properties; the oracle would take minutes here):
     identical clouds -> zero cost; moved copy -> align recovers the motion;
