@@ -214,6 +214,9 @@ struct apd_handle {
   // CTAs per registration in the device loop (APD_LM_CLUSTER=1|2|4|8|16). A lone registration is latency-bound: 8 CTAs
   // (C2 on B200: lm_kernel 0.42 ms with 4, 0.29 ms with 8); the workers of a batch pool share the SMs: 4.
   int lm_cluster = 8;
+  // which build of the loop kernel: 1 = 128 registers, one CTA per SM (shortest lone registration); 2 = 64 registers, two
+  // CTAs per SM (a batch pool: +27 % registrations/s). Same arithmetic either way. APD_LM_MINB=1|2.
+  int lm_min_blocks = 1;
   bool lm_failed = false;
   // wait for the result of the device loop on a blocking-sync event instead of spinning on the stream: the batch
   // context runs more host threads than it needs cores for (set by apd_batch_create; APD_BLOCKING_SYNC=0|1 overrides)
@@ -1205,7 +1208,7 @@ int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg)
   job.host_result = h->zero_copy ? h->h_lm_dev : nullptr;
   {
     ProfScope ps(h, APD_K_LM);
-    launch_lm(&job, nullptr, 1, cfg, h->lm_cluster, h->stream, &h->launches);
+    launch_lm(&job, nullptr, 1, cfg, h->lm_cluster, h->lm_min_blocks, h->stream, &h->launches);
   }
   APD_CUDA(h, cudaGetLastError());
   if (!h->zero_copy) APD_CUDA(h, cudaMemcpyAsync(h->h_lm.p, h->lm_result.p, kLmHeadBytes, cudaMemcpyDeviceToHost, h->stream));
@@ -1355,6 +1358,7 @@ int apd_create(int device, apd_handle** out) {
     const int v = std::atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->lm_cluster = v;
   }
+  if (const char* e = std::getenv("APD_LM_MINB")) h->lm_min_blocks = std::atoi(e) >= 2 ? 2 : 1;
   if (const char* e = std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = std::atoi(e) != 0;
   if (const char* e = std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = std::atoi(e);
   if (const char* e = std::getenv("APD_LAZY_TARGET_COV")) h->lazy_mode = std::strcmp(e, "auto") == 0 ? -1 : (std::atoi(e) != 0 ? 1 : 0);
@@ -1837,6 +1841,7 @@ int apd_batch_create(int device, int32_t n_workers, apd_batch** out) {
     // ranks' pools can share the host cores (see wait_stream)
     h->pooled = true;
     if (!std::getenv("APD_LM_CLUSTER")) h->lm_cluster = 4;
+    if (!std::getenv("APD_LM_MINB")) h->lm_min_blocks = 2;
     if (!std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = n_workers > 8;
     if (!std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = 50;  // (a look at pinned host memory: cheap)
     b->handles.push_back(h);

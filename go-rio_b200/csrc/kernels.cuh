@@ -174,6 +174,9 @@ struct LmConfig {
 constexpr int kLmMaxSource = 32768;  // larger source clouds use the streaming kernels + host loop
 // one: job passed by value (d_jobs == nullptr, n_jobs == 1); d_jobs: device array of n_jobs jobs.
 // cluster: CTAs per registration (1, 2, 4 or 8).
-void launch_lm(const LmJob* one, const LmJob* d_jobs, int n_jobs, const LmConfig& cfg, int cluster, cudaStream_t s, int64_t* launches);
+// min_blocks: 1 = the 128-register build of the kernel (one CTA per SM: a lone registration), 2 = the 64-register build
+// (two CTAs per SM: the workers of a batch pool)
+void launch_lm(const LmJob* one, const LmJob* d_jobs, int n_jobs, const LmConfig& cfg, int cluster, int min_blocks, cudaStream_t s,
+               int64_t* launches);
 
 }  // namespace apd

@@ -32,9 +32,6 @@ namespace {
 #ifndef APD_LM_THREADS
 #define APD_LM_THREADS 512
 #endif
-#ifndef APD_LM_MINB
-#define APD_LM_MINB 1
-#endif
 constexpr int kLmThreads = APD_LM_THREADS;
 constexpr int kLmWarps = kLmThreads / 32;
 #ifndef APD_LM_G
@@ -360,8 +357,12 @@ __device__ __noinline__ void serial_lm_end(LmShared& s, const LmConfig& cfg, boo
   }
 }
 
-template <bool kFp64>
-__global__ void __launch_bounds__(kLmThreads, APD_LM_MINB) lm_kernel(LmJob one, const LmJob* __restrict__ jobs, LmConfig cfg) {
+// kMinB = CTAs per SM the register allocation allows for. 1: 128 registers per thread — the shortest single registration
+// (a lone handle). 2: 64 registers (some fp64 state spills to L1-backed local memory) and twice the warps per SM — a batch
+// pool is bound by the loop kernel's latency-limited SMs (35 % issue utilisation at 16 warps), and two resident CTAs of
+// different registrations hide each other's stalls: 20.7 k -> 26.3 k registrations/s on C2.
+template <bool kFp64, int kMinB>
+__global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const LmJob* __restrict__ jobs, LmConfig cfg) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned C = cluster.num_blocks();
   const unsigned rank = cluster.block_rank();
@@ -494,7 +495,8 @@ __global__ void __launch_bounds__(kLmThreads, APD_LM_MINB) lm_kernel(LmJob one, 
 
 }  // namespace
 
-void launch_lm(const LmJob* one, const LmJob* d_jobs, int n_jobs, const LmConfig& cfg, int cluster, cudaStream_t s, int64_t* launches) {
+void launch_lm(const LmJob* one, const LmJob* d_jobs, int n_jobs, const LmConfig& cfg, int cluster, int min_blocks, cudaStream_t s,
+               int64_t* launches) {
   if (n_jobs <= 0) return;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)(n_jobs * cluster), 1, 1);
@@ -512,14 +514,21 @@ void launch_lm(const LmJob* one, const LmJob* d_jobs, int n_jobs, const LmConfig
   if (one) byval = *one;
   if (cluster > 8) {  // beyond the portable cluster size: opt in once per kernel
     static bool allowed = [] {
-      cudaFuncSetAttribute(lm_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(lm_kernel<true, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(lm_kernel<false, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(lm_kernel<true, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(lm_kernel<false, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       return true;
     }();
     (void)allowed;
   }
-  if (cfg.maha_fp64) cudaLaunchKernelEx(&lc, lm_kernel<true>, byval, d_jobs, cfg);
-  else cudaLaunchKernelEx(&lc, lm_kernel<false>, byval, d_jobs, cfg);
+  if (min_blocks >= 2) {
+    if (cfg.maha_fp64) cudaLaunchKernelEx(&lc, lm_kernel<true, 2>, byval, d_jobs, cfg);
+    else cudaLaunchKernelEx(&lc, lm_kernel<false, 2>, byval, d_jobs, cfg);
+  } else {
+    if (cfg.maha_fp64) cudaLaunchKernelEx(&lc, lm_kernel<true, 1>, byval, d_jobs, cfg);
+    else cudaLaunchKernelEx(&lc, lm_kernel<false, 1>, byval, d_jobs, cfg);
+  }
   (*launches)++;
 }
 

@@ -374,6 +374,7 @@ def test_gicp_variant_linearize_and_switching(gorio, synth, c1):
 
 def test_gicp_variant_in_a_pool(gorio, synth, monkeypatch):
     monkeypatch.setenv("APD_LM_CLUSTER", "4")
+    monkeypatch.setenv("APD_LM_MINB", "2")
     pairs = [synth.submap_pair(3100 + i, n_source=600, n_frames=4, n_per_frame=1000)[:2] + (None,) for i in range(4)]
     b = gorio.Batch(0, n_workers=4, max_correspondence_distance=2.0, transformation_epsilon=0.1, variant=1)
     res = b.align(b.prepare(pairs))
@@ -455,6 +456,21 @@ def test_target_covariances_on_demand_persist_across_sources(gorio, synth, c2_sm
         g.align()
         g.swap_source_and_target()
     assert np.array_equal(ge2.align()["T64"], gl2.align()["T64"])
+
+
+def test_loop_kernel_register_builds_agree(gorio, c2_small, monkeypatch):
+    """lm_kernel exists in two register allocations (128 registers: lone handles; 64 registers, two CTAs per SM: pool
+    workers). Same source, same arithmetic: same LM path, poses equal far below the tolerance."""
+    src, tgt, _ = c2_small
+    res = []
+    for minb in ("1", "2"):
+        monkeypatch.setenv("APD_LM_MINB", minb)
+        g, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
+        r, _ = _check_align(g, o)
+        res.append((r, g.lm_trace()))
+    assert np.array_equal(res[0][1][:, [0, 1, 7]], res[1][1][:, [0, 1, 7]])
+    dt, dr = pose_err(res[0][0]["T64"], res[1][0]["T64"])
+    assert dt < 1e-10 and dr < 1e-10, (dt, dr)
 
 
 def test_device_loop_tiny_and_ragged_sources(gorio, synth, c2_small):
@@ -618,6 +634,7 @@ def test_fitness_parity(gorio, synth, c2_small):
 # ------------------------------------------------------- batch and sizes ----
 def test_align_batch_matches_sequential(gorio, synth, monkeypatch):
     monkeypatch.setenv("APD_LM_CLUSTER", "4")  # pool workers default to 4 CTAs per registration, lone handles to 8: same summation order for the bit comparison
+    monkeypatch.setenv("APD_LM_MINB", "2")     # ... and to the 64-register build of the loop kernel, lone handles to the 128-register one
     pairs = []
     for seed in range(3000, 3006):
         s, t, _ = synth.submap_pair(seed, n_source=600, n_frames=4, n_per_frame=1000)
