@@ -1826,7 +1826,7 @@ int apd_batch_create(int device, int32_t n_workers, apd_batch** out) {
   if (!out) return APD_ERR_INVALID;
   *out = nullptr;
   if (n_workers < 1) n_workers = 1;
-  if (n_workers > 64) n_workers = 64;
+  if (n_workers > 128) n_workers = 128;
   apd_batch* b = new apd_batch();
   b->device = device;
   for (int s = 0; s < n_workers; s++) {
