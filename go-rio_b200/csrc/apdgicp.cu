@@ -1635,6 +1635,8 @@ void batch_fill_result(apd_batch* b, apd_handle* h, int i, int rc) {
     }
   }
   r.status = rc;
+  // a failed pair may leave copies out of the caller's buffers in flight: they must not outlive apd_batch_align
+  if (rc != APD_OK) cudaStreamSynchronize(h->stream);
 }
 
 // A pool worker drives several handles ("slots") and never blocks on one of them: a registration is a short state
