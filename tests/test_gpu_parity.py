@@ -589,6 +589,17 @@ def test_pcl_xyzinormal_layout(gorio, synth, c1):
     g.set_input_target(synth.to_pcl_xyzinormal(tgt)); g.set_input_source(synth.to_pcl_xyzinormal(src))
     g2, _ = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
     assert np.array_equal(g.align()["T64"], g2.align()["T64"])
+    # odd point counts (the staging loop handles two points per turn) and a layout that takes the general gather
+    s3, t3 = src[:777].copy(), tgt[:999].copy()
+    g.set_input_target(synth.to_pcl_xyzinormal(t3)); g.set_input_source(synth.to_pcl_xyzinormal(s3))
+    g2.set_input_target(t3); g2.set_input_source(s3)
+    r3 = g2.align()["T64"]
+    assert np.array_equal(g.align()["T64"], r3)
+    wide = np.zeros((999, 6), np.float32); wide[:, 1:5] = t3  # stride 24, xyz at 4, label at 16
+    g._call("set_target", wide.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(999), ctypes.c_int32(24), ctypes.c_int32(4),
+            ctypes.c_int32(16), ctypes.c_uint64(0))
+    g.n_target = 999
+    assert np.array_equal(g.align()["T64"], r3)
 
 
 def test_error_codes(gorio, c1):
