@@ -44,6 +44,8 @@ sys.path.insert(0, os.path.join(REPO, "tests"))
 DEPLOYED = dict(max_correspondence_distance=2.0, transformation_epsilon=0.1)
 METRIC = "APDGICP registrations/sec (scan-to-submap)"
 UNIT = "registrations/s"
+WORKLOAD = ("C2 scan-to-submap: 2000-pt radar scan vs 60000-pt keyframe submap, k=20, deployed params "
+            "(max_corr_dist 2.0, trans_eps 0.1, LM, PLANE)")  # the same string in both arms
 BYTES_PER_POINT_LINEARIZE = 64  # src 16 + corr 4 + tgt 16 + maha 24 + geo 4
 BYTES_PER_POINT_KNNCOV = 68     # read point 16, write cov 48 + geo 4
 
@@ -142,7 +144,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 scan-to-submap: 2000-pt radar scan vs 60000-pt keyframe submap, k=20, deployed params",
+        "config": {"workload": WORKLOAD,
                    "pairs_per_step": len(pairs), "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{len(pairs)} pairs per step x {args.steps} steps; {what}"},
@@ -399,8 +401,7 @@ def main():
                 "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "C2 scan-to-submap: 2000-pt radar scan vs 60000-pt keyframe submap, k=20, deployed params "
-                                       "(max_corr_dist 2.0, trans_eps 0.1, LM, PLANE)",
+                "config": {"workload": WORKLOAD,
                            "pairs_per_step_per_gpu": args.pairs, "streams_per_gpu": args.streams,
                            "api": "apd_batch_align_device (value) / apd_batch_align (e2e)", "optimizer_loop": "device-resident (lm.cu), one launch per registration",
                            "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align",
