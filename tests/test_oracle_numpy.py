@@ -69,11 +69,14 @@ def test_covariances(pair, reg):
     assert np.abs(o.get_target_covariances()[:, 3, :]).max() == 0.0
 
 
-def test_update_correspondences_and_linearize(pair, synth):
+@pytest.mark.parametrize("variant", [0, 1], ids=["apdgicp", "fastgicp"])
+def test_update_correspondences_and_linearize(pair, synth, variant):
+    """variant 1: the oracle's FastGICP switch (fast_gicp_impl.hpp:157 no noise term, :205 unit weights) against NumPy"""
+    gicp = variant == 1
     src, tgt, Tgt = pair
     T = Tgt @ synth.make_pose([0.05, -0.03, 0.01], np.deg2rad([0.1, -0.2, 0.4]))
     o = Oracle(search=1)
-    o.set_params(max_correspondence_distance=2.0)
+    o.set_params(max_correspondence_distance=2.0, variant=variant)
     o.set_input_source(src); o.set_input_target(tgt)
     err, H, b = o.linearize(T)
     corr, sq = o.get_correspondences()
@@ -90,17 +93,17 @@ def test_update_correspondences_and_linearize(pair, synth):
     # Mahalanobis, H, b, err against numpy
     cs = o.get_source_covariances()[:, :3, :3]
     ct = o.get_target_covariances()[:, :3, :3]
-    M = nr.mahalanobis(T, src, tgt, cs, ct, corr)
+    M = nr.mahalanobis(T, src, tgt, cs, ct, corr, gicp=gicp)
     Mo = o.get_mahalanobis()[:, :3, :3]
     assert _rel(Mo, M) < 1e-9
-    e2, H2, b2 = nr.linearize(T, src, tgt, cs, corr, M)
+    e2, H2, b2 = nr.linearize(T, src, tgt, cs, corr, M, gicp=gicp)
     assert abs(err - e2) / e2 < 1e-10
     assert _rel(H, H2) < 1e-10
     assert _rel(b, b2) < 1e-9
     # compute_error at a trial pose uses the stale correspondences / Mahalanobis (:310-346)
     T2 = synth.make_pose([0.01, 0.0, 0.0], [0, 0, 0.001]) @ T
     e3 = o.compute_error(T2)
-    e4, _, _ = nr.linearize(T2, src, tgt, cs, corr, M)
+    e4, _, _ = nr.linearize(T2, src, tgt, cs, corr, M, gicp=gicp)
     assert abs(e3 - e4) / e4 < 1e-10
 
 
