@@ -24,6 +24,7 @@
 
 #include "../../include/apdgicp.h"
 #include "host_math.hpp"
+#include "host_stage.hpp"
 #include "kernels.cuh"
 
 using namespace apd;
@@ -431,136 +432,6 @@ PoseF colmajor_f32_to_pose_f(const float* T) {
     f.t[r] = T[3 * 4 + r];
   }
   return f;
-}
-
-// host AoS -> pinned float4 staging + bounding box. Branch-free min / max over a contiguous float4 array (the compiler
-// vectorises it); the common layouts (packed float4 {x,y,z,label}; pcl::PointXYZINormal: xyz at 0, label at 16, stride 48)
-// take fixed-offset loads.
-// pcl::PointXYZINormal: {x, y, z, data[3]} at 0, normal_x at 16 -> {x, y, z, normal_x} with two shuffles (SSE2)
-static inline __m128 pcl_xyz_label(const char* p) {
-  const __m128 xyzw = _mm_loadu_ps(reinterpret_cast<const float*>(p));
-  const __m128 l = _mm_load_ss(reinterpret_cast<const float*>(p + 16));
-  const __m128 zl = _mm_shuffle_ps(xyzw, l, _MM_SHUFFLE(0, 0, 3, 2));  // (z, w, l, l)
-  return _mm_shuffle_ps(xyzw, zl, _MM_SHUFFLE(2, 0, 1, 0));            // (x, y, z, l)
-}
-
-void stage_cloud(const void* pts, int n, int stride, int xyz_off, int label_off, float4* dst, float bbox[6]) {
-  const char* base = reinterpret_cast<const char*>(pts);
-  __m128 mn = _mm_set1_ps(FLT_MAX), mx = _mm_set1_ps(-FLT_MAX);
-  if (stride == 16 && xyz_off == 0 && label_off == 12) {  // packed float4: one pass, copy + min / max
-    for (int i = 0; i < n; i++) {
-      const __m128 v = _mm_loadu_ps(reinterpret_cast<const float*>(base + (size_t)i * 16));
-      _mm_store_ps(reinterpret_cast<float*>(&dst[i]), v);
-      mn = _mm_min_ps(v, mn);  // (a NaN coordinate leaves the bound unchanged: the second operand wins)
-      mx = _mm_max_ps(v, mx);
-    }
-  } else if (stride == 48 && xyz_off == 0 && label_off == 16) {  // PCL's AoS: 3.5x faster than the general gather below
-    __m128 mn1 = mn, mx1 = mx;
-    int i = 0;
-    for (; i + 2 <= n; i += 2) {
-      const __m128 v0 = pcl_xyz_label(base + (size_t)i * 48), v1 = pcl_xyz_label(base + (size_t)i * 48 + 48);
-      _mm_store_ps(reinterpret_cast<float*>(&dst[i]), v0);
-      _mm_store_ps(reinterpret_cast<float*>(&dst[i + 1]), v1);
-      mn = _mm_min_ps(v0, mn); mx = _mm_max_ps(v0, mx);
-      mn1 = _mm_min_ps(v1, mn1); mx1 = _mm_max_ps(v1, mx1);
-    }
-    for (; i < n; i++) {
-      const __m128 v = pcl_xyz_label(base + (size_t)i * 48);
-      _mm_store_ps(reinterpret_cast<float*>(&dst[i]), v);
-      mn = _mm_min_ps(v, mn); mx = _mm_max_ps(v, mx);
-    }
-    mn = _mm_min_ps(mn, mn1);
-    mx = _mm_max_ps(mx, mx1);
-  } else {
-    for (int i = 0; i < n; i++) {
-      const char* p = base + (size_t)i * stride;
-      alignas(16) float f[4] = {0.f, 0.f, 0.f, 0.f};
-      std::memcpy(f, p + xyz_off, 12);
-      if (label_off >= 0) std::memcpy(&f[3], p + label_off, 4);
-      const __m128 v = _mm_load_ps(f);
-      _mm_store_ps(reinterpret_cast<float*>(&dst[i]), v);
-      mn = _mm_min_ps(v, mn);  // (a NaN coordinate leaves the bound unchanged: the second operand wins)
-      mx = _mm_max_ps(v, mx);
-    }
-  }
-  alignas(16) float lo[4], hi[4];
-  _mm_store_ps(lo, mn);
-  _mm_store_ps(hi, mx);
-  for (int a = 0; a < 3; a++) {  // (lane 3 is the label: ignored)
-    bbox[a] = lo[a];
-    bbox[3 + a] = hi[a];
-  }
-}
-
-// bounding box of a packed float4 {x,y,z,label} array (read-only pass). Four independent min / max chains: with one, the
-// loop runs at the latency of minps / maxps (4 cycles per point), not at the speed the cache delivers the points.
-void bounds_of_packed(const void* pts, int n, float bbox[6]) {
-  const char* base = reinterpret_cast<const char*>(pts);
-  const __m128 hi0 = _mm_set1_ps(FLT_MAX), lo0 = _mm_set1_ps(-FLT_MAX);
-  __m128 mn0 = hi0, mn1 = hi0, mn2 = hi0, mn3 = hi0, mx0 = lo0, mx1 = lo0, mx2 = lo0, mx3 = lo0;
-  int i = 0;
-  for (; i + 4 <= n; i += 4) {
-    const float* p = reinterpret_cast<const float*>(base + (size_t)i * 16);
-    const __m128 v0 = _mm_loadu_ps(p), v1 = _mm_loadu_ps(p + 4), v2 = _mm_loadu_ps(p + 8), v3 = _mm_loadu_ps(p + 12);
-    mn0 = _mm_min_ps(v0, mn0); mx0 = _mm_max_ps(v0, mx0);  // (a NaN coordinate leaves the bound unchanged: the second operand wins)
-    mn1 = _mm_min_ps(v1, mn1); mx1 = _mm_max_ps(v1, mx1);
-    mn2 = _mm_min_ps(v2, mn2); mx2 = _mm_max_ps(v2, mx2);
-    mn3 = _mm_min_ps(v3, mn3); mx3 = _mm_max_ps(v3, mx3);
-  }
-  for (; i < n; i++) {
-    const __m128 v = _mm_loadu_ps(reinterpret_cast<const float*>(base + (size_t)i * 16));
-    mn0 = _mm_min_ps(v, mn0);
-    mx0 = _mm_max_ps(v, mx0);
-  }
-  const __m128 mn = _mm_min_ps(_mm_min_ps(mn0, mn1), _mm_min_ps(mn2, mn3)), mx = _mm_max_ps(_mm_max_ps(mx0, mx1), _mm_max_ps(mx2, mx3));
-  alignas(16) float lo[4], hi[4];
-  _mm_store_ps(lo, mn);
-  _mm_store_ps(hi, mx);
-  for (int a = 0; a < 3; a++) {
-    bbox[a] = lo[a];
-    bbox[3 + a] = hi[a];
-  }
-}
-
-// Grid sizing: cell edge so that the bounding box holds ~cells_per_point (4) * n
-// cells (radar clouds live on surfaces, so occupied cells hold several points),
-// at most 2048 cells per axis (bounds the fp32 cell-coordinate error the search
-// margin covers) and 2^28 cells in total.
-void size_grid(const float bbox[6], int n, double cells_per_point, GridDesc& g, int& ncells) {
-  double ext[3];
-  for (int a = 0; a < 3; a++) {
-    ext[a] = (double)bbox[3 + a] - (double)bbox[a];
-    if (!(ext[a] > 0.0) || !std::isfinite(ext[a])) ext[a] = 0.0;
-  }
-  const double emax = std::max(std::max(ext[0], ext[1]), std::max(ext[2], 1e-3));
-  const double target = std::max(64.0, cells_per_point * (double)n);
-  double vol = 1.0;
-  for (int a = 0; a < 3; a++) vol *= std::max(ext[a], emax * 1e-3);
-  double cell = std::cbrt(vol / target);
-  cell = std::max(cell, emax / 2040.0);
-  long long d[3];
-  for (int iter = 0; iter < 200; iter++) {
-    long long tot = 1;
-    bool too_wide = false;
-    for (int a = 0; a < 3; a++) {
-      d[a] = (long long)std::floor(ext[a] / cell) + 1;
-      if (d[a] > 2048) too_wide = true;
-      tot *= d[a];
-    }
-    if (!too_wide && (double)tot <= 2.0 * target && tot <= (1ll << 28)) break;
-    cell *= 1.2599210498948732;  // 2^(1/3)
-  }
-  g.ox = bbox[0];
-  g.oy = bbox[1];
-  g.oz = bbox[2];
-  g.inv_cell = (float)(1.0 / cell);
-  g.cell = (float)(1.0 / (double)g.inv_cell);
-  // dims from the SAME fp32 expression the kernels use, so the max corner maps inside
-  auto dim = [&](float mx, float o) { return (int)std::floor((mx - o) * g.inv_cell) + 1; };
-  g.nx = std::max(1, dim(bbox[3], g.ox));
-  g.ny = std::max(1, dim(bbox[4], g.oy));
-  g.nz = std::max(1, dim(bbox[5], g.oz));
-  ncells = g.nx * g.ny * g.nz;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1023,7 +894,7 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
     }
   }
   APD_CUDA(h, c.stage.ensure((size_t)std::max(n, 1) * sizeof(float4)));
-  stage_cloud(pts, n, stride, xyz_off, label_off, reinterpret_cast<float4*>(c.stage.p), c.bbox);
+  stage_cloud(pts, n, stride, xyz_off, label_off, reinterpret_cast<float*>(c.stage.p), c.bbox);
   APD_CUDA(h, c.pts.ensure((size_t)std::max(n, 1) * sizeof(float4)));
   APD_CUDA(h, cudaMemcpyAsync(c.pts.p, c.stage.p, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
   if (h->zero_copy) {

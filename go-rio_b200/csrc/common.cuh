@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "grid_desc.hpp"
+
 namespace apd {
 
 // ---------------------------------------------------------------------------
@@ -26,12 +28,7 @@ namespace apd {
 //               (24 B/pt) or double2 x 3 planes (48 B/pt)
 // ---------------------------------------------------------------------------
 
-struct GridDesc {
-  float ox, oy, oz;   // origin (min corner)
-  float inv_cell;     // 1 / cell size
-  float cell;         // cell size (metres)
-  int nx, ny, nz;     // dimensions
-};
+// struct GridDesc {ox, oy, oz, inv_cell, cell, nx, ny, nz}: grid_desc.hpp (included below the layout notes)
 
 constexpr int kCorrLabelBit = 1 << 30;
 constexpr int kCorrIndexMask = kCorrLabelBit - 1;
