@@ -32,6 +32,25 @@ def test_shard_pairs_cover_all():
             assert got == list(range(n))
 
 
+def test_bench_gives_every_rank_the_same_work(synth, monkeypatch):
+    """weak scaling = equal work per GPU: every rank of bench.py registers the same scenes, starting at a different one"""
+    import bench
+    calls = []
+
+    def fake_pair(seed, **kw):
+        calls.append(seed)
+        return np.full((2, 4), seed, np.float32), np.full((3, 4), seed, np.float32), None
+
+    monkeypatch.setattr(synth, "submap_pair", fake_pair)
+    per_rank = []
+    for rank in range(8):
+        pairs = bench.make_pairs(synth, rank, 512)
+        per_rank.append(sorted(int(s[0, 0]) for s, _ in pairs))
+        assert int(pairs[0][0][0, 0]) == 2000 + rank  # rotated start
+    assert all(p == per_rank[0] for p in per_rank) and set(per_rank[0]) == set(range(2000, 2008))
+    assert sorted(set(calls)) == list(range(2000, 2008))
+
+
 _WORKER = r'''
 import importlib, json, os, sys
 import numpy as np
