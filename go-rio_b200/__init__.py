@@ -145,6 +145,112 @@ class Batch:
             pass
 
 
+class Group:
+    """apd_group_*: the handles of ONE process as the ranks of one sharded registration (devices[i] = the device of rank i;
+    several ranks may share a device). The calls fan out to all ranks from the library's own threads."""
+
+    def __init__(self, devices, **params):
+        import numpy as np
+
+        self._np = np
+        self._lib = load()
+        self.ranks = [Registration(self._lib, "apd_", d) for d in devices]
+        if params:
+            for r in self.ranks:
+                r.set_params(**params)
+        arr = (ctypes.c_void_p * len(self.ranks))(*[r._h for r in self.ranks])
+        self._g = ctypes.c_void_p()
+        self._lib.apd_group_create.restype = ctypes.c_int
+        rc = self._lib.apd_group_create(arr, ctypes.c_int32(len(self.ranks)), ctypes.byref(self._g))
+        if rc != 0:
+            raise ApdError(rc, "apd_group_create")
+        self._keep = []
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise ApdError(rc, what + ": " + "; ".join(r.last_error() for r in self.ranks))
+
+    def _set(self, name, cloud):
+        a, n, stride, xo, lo = Registration._layout(cloud)
+        self._keep = self._keep[-3:] + [a]
+        fn = getattr(self._lib, name)
+        fn.restype = ctypes.c_int
+        self._check(fn(self._g, a.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(n), ctypes.c_int32(stride), ctypes.c_int32(xo),
+                       ctypes.c_int32(lo)), name)
+        return n
+
+    def set_input_source(self, cloud):
+        n = self._set("apd_group_set_source", cloud)
+        for r in self.ranks:
+            r.n_source = n
+
+    def set_input_target(self, cloud):
+        n = self._set("apd_group_set_target", cloud)
+        for r in self.ranks:
+            r.n_target = n
+
+    def _set_device(self, name, dptrs, n):
+        arr = (ctypes.c_void_p * len(self.ranks))(*dptrs)
+        fn = getattr(self._lib, name)
+        fn.restype = ctypes.c_int
+        self._check(fn(self._g, arr, ctypes.c_int32(n)), name)
+
+    def set_input_source_device(self, dptrs, n):
+        self._set_device("apd_group_set_source_device", dptrs, n)
+        for r in self.ranks:
+            r.n_source = n
+
+    def set_input_target_device(self, dptrs, n):
+        self._set_device("apd_group_set_target_device", dptrs, n)
+        for r in self.ranks:
+            r.n_target = n
+
+    def linearize(self, T, want_hb=True):
+        np = self._np
+        t = _binding._colmajor(T, np.float64)
+        H, b, err = np.empty(36, np.float64), np.empty(6, np.float64), ctypes.c_double()
+        self._lib.apd_group_linearize.restype = ctypes.c_int
+        self._check(self._lib.apd_group_linearize(self._g, t.ctypes.data_as(ctypes.c_void_p), H.ctypes.data_as(ctypes.c_void_p) if want_hb else None,
+                                                  b.ctypes.data_as(ctypes.c_void_p) if want_hb else None, ctypes.byref(err)), "apd_group_linearize")
+        return (err.value, H.reshape(6, 6).T.copy(), b) if want_hb else err.value
+
+    def compute_error(self, T):
+        t = _binding._colmajor(T, self._np.float64)
+        err = ctypes.c_double()
+        self._lib.apd_group_compute_error.restype = ctypes.c_int
+        self._check(self._lib.apd_group_compute_error(self._g, t.ctypes.data_as(ctypes.c_void_p), ctypes.byref(err)), "apd_group_compute_error")
+        return err.value
+
+    def align(self, guess=None):
+        np = self._np
+        g = None if guess is None else _binding._colmajor(guess, np.float32)
+        T, T64, H = np.empty(16, np.float32), np.empty(16, np.float64), np.empty(36, np.float64)
+        conv, it = ctypes.c_int32(), ctypes.c_int32()
+        self._lib.apd_group_align.restype = ctypes.c_int
+        self._check(self._lib.apd_group_align(self._g, g.ctypes.data_as(ctypes.c_void_p) if g is not None else None, T.ctypes.data_as(ctypes.c_void_p),
+                                              T64.ctypes.data_as(ctypes.c_void_p), H.ctypes.data_as(ctypes.c_void_p), ctypes.byref(conv),
+                                              ctypes.byref(it)), "apd_group_align")
+        return dict(T=T.reshape(4, 4).T.copy(), T64=T64.reshape(4, 4).T.copy(), H=H.reshape(6, 6).T.copy(), converged=bool(conv.value),
+                    iterations=it.value)
+
+    def launch_count(self):
+        return sum(r.launch_count() for r in self.ranks)
+
+    def close(self):
+        if self._g:
+            self._lib.apd_group_destroy(self._g)
+            self._g = ctypes.c_void_p()
+        for r in self.ranks:
+            r.close()
+        self.ranks = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def align_batch(pairs, params=None, device=0, n_streams=4, with_fitness=True):
     """apd_align_batch over a list of (source[n,4] f32, target[m,4] f32, guess 4x4 or None)."""
     lib = load()

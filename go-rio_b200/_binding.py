@@ -79,7 +79,9 @@ PRODUCT_SYMBOLS = CORE_SYMBOLS + [
     "abi_version", "set_source_device", "set_target_device", "align_batch", "batch_create", "batch_destroy",
     "batch_set_params", "batch_align", "batch_align_device", "batch_launch_count", "batch_set_profiling",
     "batch_get_kernel_ms", "comm_unique_id",
-    "comm_init", "comm_peer_handle", "comm_peer_attach", "comm_destroy", "stream", "launch_count", "set_profiling", "get_kernel_ms",
+    "comm_init", "comm_peer_handle", "comm_peer_attach", "comm_destroy", "group_create", "group_destroy", "group_size",
+    "group_set_params", "group_set_source", "group_set_target", "group_set_source_device", "group_set_target_device", "group_align",
+    "group_linearize", "group_compute_error", "stream", "launch_count", "set_profiling", "get_kernel_ms",
 ]
 
 

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstddef>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <string>
 #include <thread>
@@ -122,6 +123,7 @@ struct Cloud {
   int n = 0;
   bool present = false;
   uint64_t key = 0;
+  uint64_t print = 0;  // content fingerprint taken when `key` was accepted (see cloud_fingerprint)
   float bbox[6] = {0, 0, 0, 0, 0, 0};
   DevBuf pts, spts, label, inv_perm, cov, geo, geo64, cell_start;
   PinnedBuf stage;                  // host AoS -> float4 staging for the H2D copy
@@ -177,6 +179,8 @@ struct ProfEvent {
 
 }  // namespace
 
+struct apd_group;
+
 struct apd_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -195,6 +199,7 @@ struct apd_handle {
   DevBuf work, scratch, partials, small;  // small: out28 + ticket + fitness
   DevBuf nbuf;  // neighbour lists (n x k original ids) between the kNN search and the covariance kernel
   PinnedBuf h_small;
+  PinnedBuf h_query;  // staging of apd_nearest_k's query points
   DevBuf lm_result;   // LmResult of the device-resident optimizer loop
   PinnedBuf h_lm;     // its header + first trace rows on the host
   // Zero-copy results: kernels publish small results (the loop's result header, a device cloud's bounding box) straight
@@ -270,30 +275,75 @@ struct apd_handle {
   int lazy_min_ratio = 4;
   int knn_max_k() const { return knn_mode == 1 ? 32 : 128; }
   bool knn_use_warp(int n, int k) const { return knn_mode == 1 || (knn_mode == 0 && k <= 32 && n < knn_thread_min_n); }
-  // Sharded handle (apd_comm_init): every rank holds both FULL clouds and grids. The cell-sorted points of a cloud are
-  // cut into nranks * kShardSub equal chunks; rank r owns chunks r, r + nranks, r + 2 nranks, ... — interleaved, because
+  // Sharded handle (apd_comm_init across processes, apd_group_create inside one): every rank holds both FULL clouds and
+  // grids. The cell-sorted points of a cloud are cut into nranks * kShardSub equal chunks (a multiple of 256 points: whole
+  // tiles, 16-byte aligned in every array); rank r owns chunks r, r + nranks, r + 2 nranks, ... — interleaved, because
   // the cost of a 1-NN / kNN query varies across the scene (contiguous halves of one 20 M-point scene differed by 1.5x).
   // Chunk j of every rank forms one contiguous group, so the covariance all-gather runs in place, group by group.
-  static constexpr int kShardSub = 4;
-  int shard_subs() const { return comm ? kShardSub : 1; }
-  int shard_chunk(int n) const { return comm ? (n + comm_size * kShardSub - 1) / (comm_size * kShardSub) : n; }
-  int sub_begin(int n, int j) const { return comm ? (int)std::min<long long>(n, (long long)(j * comm_size + comm_rank) * shard_chunk(n)) : 0; }
-  int sub_count(int n, int j) const {
-    return comm ? (int)(std::min<long long>(n, (long long)(j * comm_size + comm_rank + 1) * shard_chunk(n)) - sub_begin(n, j)) : n;
+  static constexpr int kShardSub = kShardSubMax;
+  apd_group* group = nullptr;  // in-process ranks (apd_group_create): peers are plain pointers, no NCCL
+  unsigned int bar_seq = 0;    // last peer barrier this rank has entered
+  bool sharded() const { return comm != nullptr || group != nullptr; }
+  int shard_subs() const { return sharded() ? kShardSub : 1; }
+  int shard_chunk(int n) const {
+    if (!sharded()) return n;
+    const int c = (n + comm_size * kShardSub - 1) / (comm_size * kShardSub);
+    return (c + 255) / 256 * 256;
   }
-  size_t sub_local(int n, int j) const { return (size_t)j * shard_chunk(n); }  // offset of chunk j in the rank-local arrays
-  size_t local_n(int n) const { return comm ? (size_t)shard_chunk(n) * kShardSub : (size_t)n; }
-  size_t padded_n(int n) const { return comm ? (size_t)shard_chunk(n) * comm_size * kShardSub : (size_t)n; }
-  // chunk j of the source points this rank linearizes (pointers shifted, n = chunk length); unsharded: the whole cloud
-  CloudDev src_slice(int j) const {
-    CloudDev v = src.view();
-    if (comm) {
-      const int b = sub_begin(src.n, j);
-      v.n = sub_count(src.n, j);
-      v.spts += b; v.label += b; v.cov += (size_t)b * 6; v.geo += b; v.geo64 += b;
-      v.inv_perm = nullptr;  // (indexed by original id: not a per-slice array)
+  int sub_begin(int n, int j) const { return sharded() ? (int)std::min<long long>(n, (long long)(j * comm_size + comm_rank) * shard_chunk(n)) : 0; }
+  int sub_count(int n, int j) const {
+    return sharded() ? (int)(std::min<long long>(n, (long long)(j * comm_size + comm_rank + 1) * shard_chunk(n)) - sub_begin(n, j)) : n;
+  }
+  size_t local_n(int n) const { return sharded() ? (size_t)shard_chunk(n) * kShardSub : (size_t)n; }
+  size_t padded_n(int n) const { return sharded() ? (size_t)shard_chunk(n) * comm_size * kShardSub : (size_t)n; }
+  // the chunks of a cloud of n points this rank serves (unsharded: the whole cloud)
+  ShardTable shard_table(int n) const {
+    if (!sharded()) return whole_cloud(n);
+    ShardTable t;
+    t.nsub = kShardSub;
+    t.chunk = shard_chunk(n);
+    for (int j = 0; j < kShardSub; j++) {
+      t.begin[j] = sub_begin(n, j);
+      t.count[j] = sub_count(n, j);
     }
-    return v;
+    t.plane = (int)local_n(n);
+    return t;
+  }
+  // lanes per 1-NN query of update_correspondences (0: by cloud size). APD_CORR_LANES=1|2|4|8; APD_CORR_MODE=wide|lane (8 | 1)
+  int corr_lanes = 0;
+};
+
+// In-process ranks of one sharded registration (apd_group_create): the handles of ONE process, on one device or on
+// several, each driven by its own host thread (the group's, for the apd_group_* calls). Peers are plain pointers:
+// mailboxes for the in-kernel exchange of the H/b/err sums and for the stream barrier, and the peers' covariance
+// arrays, which a rank PULLS its missing chunks from (peer-to-peer copies over NVLink when the devices differ).
+struct apd_group {
+  std::vector<apd_handle*> ranks;
+  // barrier of the rank threads on the host (the all-gather publishes buffer pointers across it)
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  uint64_t gen = 0;
+  void* gather_ptr[apd::kPeerMaxRanks] = {nullptr};
+  // the group's own threads (one per rank) for the fan-out calls
+  std::vector<std::thread> threads;
+  std::condition_variable cv_job, cv_done;
+  uint64_t job_gen = 0;
+  int job_pending = 0;
+  bool stop = false;
+  std::function<int(apd_handle*, int)> job;
+  std::vector<int> job_rc;
+  // waits until every rank thread has arrived; false after 60 s (a rank failed before the meeting point)
+  bool host_barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    const uint64_t my = gen;
+    if (++arrived == (int)ranks.size()) {
+      arrived = 0;
+      gen++;
+      cv.notify_all();
+      return true;
+    }
+    return cv.wait_for(lk, std::chrono::seconds(60), [&] { return gen != my; });
   }
 };
 
@@ -525,6 +575,37 @@ int allgather_chunks(apd_handle* h, void* base, int n, size_t elems_per_point, i
   return APD_OK;
 }
 
+PeerExchange barrier_ticket(apd_handle* h) {
+  PeerExchange x;
+  for (int r = 0; r < h->comm_size; r++) x.box[r] = h->peer_box[r];
+  x.rank = h->comm_rank;
+  x.nranks = h->comm_size;
+  x.seq = ++h->bar_seq;
+  return x;
+}
+
+// the same all-gather between the in-process ranks of a group: publish the array's address, meet the other rank threads,
+// order the streams with a barrier kernel (every rank's chunks are complete), then PULL the peers' chunks
+int group_allgather_chunks(apd_handle* h, void* base, int n, size_t bytes_per_point) {
+  apd_group* g = h->group;
+  g->gather_ptr[h->comm_rank] = base;
+  if (!g->host_barrier()) return fail(h, APD_ERR_COMM, "a rank of the group did not reach the all-gather");
+  launch_peer_barrier(barrier_ticket(h), h->stream, &h->launches);
+  const size_t chunk = (size_t)h->shard_chunk(n) * bytes_per_point;
+  for (int j = 0; j < h->shard_subs(); j++)
+    for (int r = 0; r < h->comm_size; r++) {
+      if (r == h->comm_rank) continue;
+      const size_t off = ((size_t)j * h->comm_size + r) * chunk;
+      APD_CUDA(h, cudaMemcpyAsync(reinterpret_cast<char*>(base) + off, reinterpret_cast<const char*>(g->gather_ptr[r]) + off, chunk,
+                                  cudaMemcpyDefault, h->stream));
+    }
+  // nobody may rewrite its array (the next cloud) while a peer still pulls from it: every stream passes a second barrier
+  // behind its own pulls
+  launch_peer_barrier(barrier_ticket(h), h->stream, &h->launches);
+  APD_CUDA(h, cudaGetLastError());
+  return APD_OK;
+}
+
 // FastAPDGICP::calculate_covariances (:351-411)
 int ensure_covariances_of(apd_handle* h, Cloud& c) {
   int rc = ensure_grid(h, c);
@@ -554,10 +635,9 @@ int ensure_covariances_of(apd_handle* h, Cloud& c) {
         launch_knn_cov_fused(c.view(), k, reg, nullptr, h->stream, &h->launches, w0, wn);
       }
     }
-    if (h->comm) {
-      rc = allgather_chunks(h, c.cov.p, c.n, 6, kNcclFloat64, sizeof(double));
-      if (rc != APD_OK) return rc;
-    }
+    if (h->group) rc = group_allgather_chunks(h, c.cov.p, c.n, 6 * sizeof(double));
+    else if (h->comm) rc = allgather_chunks(h, c.cov.p, c.n, 6, kNcclFloat64, sizeof(double));
+    if (rc != APD_OK) return rc;
     c.cov_valid = true;
     c.geo_valid = true;
     c.geo_variant = APD_VARIANT_APDGICP;
@@ -637,16 +717,14 @@ int ensure_small(apd_handle* h) {
   return APD_OK;
 }
 
-// per-linearisation arrays of chunk j of this rank's source points (unsharded: j = 0, the whole cloud)
-CorrOut corr_view(apd_handle* h, int j = 0) {
-  const size_t off = h->comm ? h->sub_local(h->src.n, j) : 0;
+// per-linearisation arrays of this rank's source points (rank-local slots, see ShardTable)
+CorrOut corr_view(apd_handle* h) {
   CorrOut c;
-  c.corr = h->corr.as<int>() + off;
-  c.sqd = h->sqd.as<float>() + off;
+  c.corr = h->corr.as<int>();
+  c.sqd = h->sqd.as<float>();
   c.maha_fp64 = h->corr_fp64;
-  // fp64 storage keeps two planes of `chunk length` double2 in mahaB: every chunk owns [2 off, 2 off + 2 len)
-  c.mahaA = h->corr_fp64 ? (void*)(h->mahaA.as<double2>() + off) : (void*)(h->mahaA.as<float4>() + off);
-  c.mahaB = h->corr_fp64 ? (void*)(h->mahaB.as<double2>() + 2 * off) : (void*)(h->mahaB.as<float2>() + off);
+  c.mahaA = h->mahaA.p;
+  c.mahaB = h->mahaB.p;  // fp64 storage: two planes of local_n double2
   return c;
 }
 
@@ -658,9 +736,8 @@ int do_update_correspondences(apd_handle* h, const hm::Pose& T) {
   {
     ProfScope ps(h, APD_K_CORR);
     const bool warm = h->corr_warm && h->corr_n == h->src.n && h->corr_thr == h->params.max_correspondence_distance;
-    for (int j = 0; j < h->shard_subs(); j++)
-      launch_update_correspondences(h->src_slice(j), h->tgt.view(), to_pose_d(T), np, corr_view(h, j), warm ? &h->corr_pose : nullptr,
-                                    h->stream, &h->launches);
+    launch_update_correspondences(h->src.view(), h->tgt.view(), h->shard_table(h->src.n), to_pose_d(T), np, corr_view(h),
+                                  warm ? &h->corr_pose : nullptr, h->corr_lanes, h->stream, &h->launches);
   }
   APD_CUDA(h, cudaGetLastError());
   h->corr_n = h->src.n;
@@ -684,17 +761,16 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
   const double n_total = h->params.variant == APD_VARIANT_GICP ? std::numeric_limits<double>::infinity() : (double)h->src.n;
   {
     ProfScope ps(h, want_hb ? APD_K_LINEARIZE : APD_K_ERROR);
-    for (int j = 0; j < h->shard_subs(); j++) {  // chunks after the first add onto the 28 (1) sums of the previous ones
-      if (h->peers_attached && j == h->shard_subs() - 1) {  // the last chunk's kernel also exchanges the totals with the peers
-        for (int r = 0; r < h->comm_size; r++) w.xchg.box[r] = h->peer_box[r];
-        w.xchg.rank = h->comm_rank;
-        w.xchg.nranks = h->comm_size;
-        w.xchg.seq = ++h->xchg_seq;
-        if (w.xchg.seq == 0) w.xchg.seq = h->xchg_seq = 2;  // (wrap-around: 0 means "no exchange"; keep the parity alternating)
-      }
-      launch_linearize(h->src_slice(j), h->tgt.view(), to_pose_d(T), corr_view(h, j), n_total, want_hb, j > 0, w, d_out, h->stream,
-                       &h->launches);
+    if (h->peers_attached) {  // the kernel's last block also exchanges the totals with the peers
+      for (int r = 0; r < h->comm_size; r++) w.xchg.box[r] = h->peer_box[r];
+      w.xchg.rank = h->comm_rank;
+      w.xchg.nranks = h->comm_size;
+      w.xchg.seq = ++h->xchg_seq;
+      if (w.xchg.seq == 0) w.xchg.seq = h->xchg_seq = 2;  // (wrap-around: 0 means "no exchange"; keep the parity alternating)
     }
+    // ONE launch serves all the rank's chunks (a chunk table in the kernel; round 1 launched once per chunk)
+    launch_linearize(h->src.view(), h->tgt.view(), h->shard_table(h->src.n), to_pose_d(T), corr_view(h), n_total, want_hb, w, d_out,
+                     h->stream, &h->launches);
   }
   APD_CUDA(h, cudaGetLastError());
   if (h->comm && !h->peers_attached) {
@@ -833,6 +909,7 @@ int adopt_cloud(apd_handle* h, Cloud& dst, const Cloud& src) {
   dst.n = src.n;
   dst.present = true;
   dst.key = src.key;
+  dst.print = src.print;
   std::memcpy(dst.bbox, src.bbox, sizeof(dst.bbox));
   dst.g = src.g;
   dst.ncells = src.ncells;
@@ -844,13 +921,36 @@ int adopt_cloud(apd_handle* h, Cloud& dst, const Cloud& src) {
   return APD_OK;
 }
 
+// The reference early-outs on shared_ptr identity, and the pointer keeps the cloud alive. Here the key is a number the
+// caller chose (usually the cloud's address), which can go stale: a freed cloud's address is reused by the next frame.
+// A key is therefore only honoured together with the point count and a fingerprint of the content (64 points spread
+// over the cloud: xyz + label bits, FNV-1a) taken when the key was accepted — a recycled address with other points in
+// it is a new cloud.
+uint64_t cloud_fingerprint(const void* pts, int32_t n, int32_t stride, int32_t xyz_off, int32_t label_off) {
+  uint64_t hsh = 1469598103934665603ull ^ (uint64_t)(uint32_t)n;
+  const int samples = std::min<int32_t>(n, 64);
+  for (int q = 0; q < samples; q++) {
+    const size_t i = samples > 1 ? (size_t)q * (size_t)(n - 1) / (size_t)(samples - 1) : 0;
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(pts) + i * (size_t)stride;
+    uint32_t w[4] = {0, 0, 0, 0};
+    std::memcpy(w, p + xyz_off, 12);
+    if (label_off >= 0) std::memcpy(w + 3, p + label_off, 4);
+    for (int e = 0; e < 4; e++) {
+      hsh ^= w[e];
+      hsh *= 1099511628211ull;
+    }
+  }
+  return hsh;
+}
+
 int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t stride, int32_t xyz_off, int32_t label_off, uint64_t key) {
   if (!pts || n < 0 || stride < 12 || xyz_off < 0) return fail(h, APD_ERR_INVALID, "bad cloud arguments");
-  if (c.present && key != 0 && key == c.key) return APD_OK;  // pointer-identity early-out (:116,:128)
+  const uint64_t print = key != 0 ? cloud_fingerprint(pts, n, stride, xyz_off, label_off) : 0;
+  if (c.present && key != 0 && key == c.key && n == c.n && print == c.print) return APD_OK;  // pointer-identity early-out (:116,:128)
   DeviceGuard dg(h->device);
   {
     Cloud& other = (&c == &h->src) ? h->tgt : h->src;
-    if (key != 0 && other.present && other.key == key && other.n == n) {
+    if (key != 0 && other.present && other.key == key && other.n == n && other.print == print && !h->sharded()) {
       h->corr_n = -1;
       h->corr_warm = false;
       return adopt_cloud(h, c, other);
@@ -870,6 +970,7 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
       c.n = n;
       c.present = true;
       c.key = key;
+      c.print = print;
       c.grid_valid = false;
       c.cov_valid = false;  // source_covs_.clear() (:122,:133)
       c.geo_valid = false;
@@ -910,6 +1011,7 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
   c.n = n;
   c.present = true;
   c.key = key;
+  c.print = print;
   c.grid_valid = false;
   c.cov_valid = false;  // source_covs_.clear() (:122,:133)
   c.geo_valid = false;
@@ -1038,7 +1140,7 @@ LmConfig lm_config(const apd_params& p) {
 }
 
 bool use_device_loop(const apd_handle* h) {
-  return !h->params.host_loop && !h->comm && !h->params.lm_debug_print && h->src.n <= kLmMaxSource;
+  return !h->params.host_loop && !h->sharded() && !h->params.lm_debug_print && h->src.n <= kLmMaxSource;
 }
 
 LmJob lm_job(apd_handle* h, const hm::Pose& x0) {
@@ -1271,6 +1373,11 @@ int apd_create(int device, apd_handle** out) {
   if (const char* e = std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = std::atoi(e);
   if (const char* e = std::getenv("APD_LAZY_TARGET_COV")) h->lazy_mode = std::strcmp(e, "auto") == 0 ? -1 : (std::atoi(e) != 0 ? 1 : 0);
   if (const char* e = std::getenv("APD_ZERO_COPY")) h->zero_copy = std::atoi(e) != 0;
+  if (const char* e = std::getenv("APD_CORR_MODE")) h->corr_lanes = e[0] == 'w' ? 8 : (e[0] == 'l' ? 1 : 0);
+  if (const char* e = std::getenv("APD_CORR_LANES")) {
+    const int v = std::atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) h->corr_lanes = v;
+  }
   if (const char* e = std::getenv("APD_KNN_MODE")) h->knn_mode = std::strcmp(e, "warp") == 0 ? 1 : (std::strcmp(e, "thread") == 0 ? 2 : 0);
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   for (int i = 0; i < 36; i++) h->final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity()
@@ -1284,7 +1391,7 @@ int apd_destroy(apd_handle* h) {
   cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (int r = 0; r < kPeerMaxRanks; r++)
-    if (h->peer_box[r] && h->peer_box[r] != h->mailbox) cudaIpcCloseMemHandle(h->peer_box[r]);
+    if (!h->group && h->peer_box[r] && h->peer_box[r] != h->mailbox) cudaIpcCloseMemHandle(h->peer_box[r]);
   if (h->mailbox) cudaFree(h->mailbox);
   for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -1293,6 +1400,7 @@ int apd_destroy(apd_handle* h) {
   h->corr.release(); h->sqd.release(); h->mahaA.release(); h->mahaB.release();
   h->work.release(); h->scratch.release(); h->partials.release(); h->small.release();
   h->h_small.release();
+  h->h_query.release();
   h->lm_result.release();
   h->nbuf.release();
   h->h_lm.release();
@@ -1457,12 +1565,11 @@ int apd_get_correspondences(apd_handle* h, int32_t* idx, float* sq_dist, int32_t
   APD_CUDA(h, h->scratch.ensure(2 * ib));
   int32_t* d_idx = h->scratch.as<int32_t>();
   float* d_sq = reinterpret_cast<float*>(h->scratch.as<char>() + ib);
-  if (h->comm) {  // a sharded handle reports its own slice of the source; the other points read -1 / 0
+  if (h->sharded()) {  // a sharded handle reports its own slice of the source; the other points read -1 / 0
     APD_CUDA(h, cudaMemsetAsync(d_idx, 0xff, (size_t)n * sizeof(int32_t), h->stream));
     APD_CUDA(h, cudaMemsetAsync(d_sq, 0, (size_t)n * sizeof(float), h->stream));
   }
-  for (int j = 0; j < h->shard_subs(); j++)
-    launch_corr_export(h->src_slice(j), h->tgt.view(), corr_view(h, j), d_idx, d_sq, nullptr, h->stream, &h->launches);
+  launch_corr_export(h->src.view(), h->tgt.view(), h->shard_table(h->src.n), corr_view(h), d_idx, d_sq, nullptr, h->stream, &h->launches);
   if (idx) APD_CUDA(h, cudaMemcpyAsync(idx, d_idx, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   if (sq_dist) APD_CUDA(h, cudaMemcpyAsync(sq_dist, d_sq, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   APD_CUDA(h, wait_stream(h));
@@ -1474,9 +1581,9 @@ int apd_get_mahalanobis(apd_handle* h, double* maha, int32_t n) {
   if (h->corr_n != n || n != h->src.n) return fail(h, APD_ERR_INVALID, "no correspondences for this source cloud");
   DeviceGuard dg(h->device);
   APD_CUDA(h, h->scratch.ensure((size_t)n * 16 * sizeof(double)));
-  if (h->comm) APD_CUDA(h, cudaMemsetAsync(h->scratch.p, 0, (size_t)n * 16 * sizeof(double), h->stream));
-  for (int j = 0; j < h->shard_subs(); j++)
-    launch_corr_export(h->src_slice(j), h->tgt.view(), corr_view(h, j), nullptr, nullptr, h->scratch.as<double>(), h->stream, &h->launches);
+  if (h->sharded()) APD_CUDA(h, cudaMemsetAsync(h->scratch.p, 0, (size_t)n * 16 * sizeof(double), h->stream));
+  launch_corr_export(h->src.view(), h->tgt.view(), h->shard_table(h->src.n), corr_view(h), nullptr, nullptr, h->scratch.as<double>(), h->stream,
+                     &h->launches);
   APD_CUDA(h, cudaMemcpyAsync(maha, h->scratch.p, (size_t)n * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   APD_CUDA(h, wait_stream(h));
   return APD_OK;
@@ -1488,6 +1595,56 @@ int apd_fitness(apd_handle* h, const float* T, double max_range, double* score, 
   int rc = do_fitness(h, T, max_range, score, n_in_range, inlier_sq_thr, n_inliers);
   flush_prof(h);
   return rc;
+}
+
+int apd_nearest_k(apd_handle* h, int32_t which, const void* queries, int32_t n, int32_t stride, int32_t k, int32_t* idx, float* sq_dist) {
+  if (!h || !queries || n < 0 || stride < 12 || !idx || !sq_dist) return APD_ERR_INVALID;
+  if (k < 1 || k > 32) return fail(h, APD_ERR_UNSUPPORTED, "apd_nearest_k serves 1 <= k <= 32");
+  Cloud& c = which == 0 ? h->src : h->tgt;
+  if (!c.present || c.n <= 0) return fail(h, APD_ERR_INVALID, "cloud not set");
+  if (n == 0) return APD_OK;
+  DeviceGuard dg(h->device);
+  int rc = ensure_grid(h, c);
+  if (rc != APD_OK) return rc;
+  const size_t qb = align_up((size_t)n * sizeof(float4), 256), ib = align_up((size_t)n * k * sizeof(int32_t), 256);
+  APD_CUDA(h, h->scratch.ensure(qb + 2 * ib));
+  APD_CUDA(h, h->h_query.ensure(qb));
+  float* st = reinterpret_cast<float*>(h->h_query.p);
+  for (int32_t i = 0; i < n; i++) {
+    std::memcpy(st + 4 * (size_t)i, reinterpret_cast<const char*>(queries) + (size_t)i * stride, 12);
+    st[4 * (size_t)i + 3] = 0.f;
+  }
+  char* d = h->scratch.as<char>();
+  APD_CUDA(h, cudaMemcpyAsync(d, st, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  launch_knn_query(c.view(), k, reinterpret_cast<const float4*>(d), n, reinterpret_cast<int32_t*>(d + qb), reinterpret_cast<float*>(d + qb + ib),
+                   h->stream, &h->launches);
+  APD_CUDA(h, cudaGetLastError());
+  APD_CUDA(h, cudaMemcpyAsync(idx, d + qb, (size_t)n * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, cudaMemcpyAsync(sq_dist, d + qb + ib, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
+  return APD_OK;
+}
+
+int apd_source_nearest(apd_handle* h, const float* T, int32_t* idx, float* sq_dist, float* xyz, int32_t n) {
+  if (!h || !idx || !sq_dist) return APD_ERR_INVALID;
+  if (!h->src.present || !h->tgt.present || n != h->src.n) return fail(h, APD_ERR_INVALID, "source or target cloud not set, or n is not the source's size");
+  if (n == 0) return APD_OK;
+  DeviceGuard dg(h->device);
+  int rc = ensure_grid(h, h->src);
+  if (rc != APD_OK) return rc;
+  rc = ensure_grid(h, h->tgt);
+  if (rc != APD_OK) return rc;
+  const size_t ib = align_up((size_t)n * sizeof(int32_t), 256);
+  APD_CUDA(h, h->scratch.ensure(2 * ib + (size_t)n * 3 * sizeof(float)));
+  char* d = h->scratch.as<char>();
+  launch_source_nearest(h->src.view(), h->tgt.view(), colmajor_f32_to_pose_f(T ? T : h->final_T), reinterpret_cast<int32_t*>(d),
+                        reinterpret_cast<float*>(d + ib), xyz ? reinterpret_cast<float*>(d + 2 * ib) : nullptr, h->stream, &h->launches);
+  APD_CUDA(h, cudaGetLastError());
+  APD_CUDA(h, cudaMemcpyAsync(idx, d, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, cudaMemcpyAsync(sq_dist, d + ib, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (xyz) APD_CUDA(h, cudaMemcpyAsync(xyz, d + 2 * ib, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
+  return APD_OK;
 }
 
 int apd_get_lm_trace(apd_handle* h, double* rows, int32_t max_rows, int32_t* n_rows) {
@@ -1960,6 +2117,183 @@ int apd_comm_destroy(apd_handle* h) {
   h->comm_size = 1;
   h->comm_rank = 0;
   return APD_OK;
+}
+
+// ---- the same sharding between handles of ONE process ---------------------------------
+}  // extern "C"
+
+namespace {
+
+void group_thread(apd_group* g, int rank) {
+  cudaSetDevice(g->ranks[rank]->device);
+  uint64_t seen = 0;
+  for (;;) {
+    std::function<int(apd_handle*, int)> job;
+    {
+      std::unique_lock<std::mutex> lk(g->mu);
+      g->cv_job.wait(lk, [&] { return g->stop || g->job_gen != seen; });
+      if (g->stop) return;
+      seen = g->job_gen;
+      job = g->job;
+    }
+    const int rc = job(g->ranks[rank], rank);
+    {
+      std::lock_guard<std::mutex> lk(g->mu);
+      g->job_rc[rank] = rc;
+      if (--g->job_pending == 0) g->cv_done.notify_all();
+    }
+  }
+}
+
+// runs `job` on every rank from the group's threads; returns the first non-zero status (rank order)
+int group_run(apd_group* g, std::function<int(apd_handle*, int)> job) {
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->job = std::move(job);
+    g->job_pending = (int)g->ranks.size();
+    g->job_gen++;
+  }
+  g->cv_job.notify_all();
+  std::unique_lock<std::mutex> lk(g->mu);
+  g->cv_done.wait(lk, [&] { return g->job_pending == 0; });
+  for (int rc : g->job_rc)
+    if (rc != APD_OK) return rc;
+  return APD_OK;
+}
+
+void group_detach(apd_handle* h) {
+  for (int r = 0; r < kPeerMaxRanks; r++) h->peer_box[r] = nullptr;
+  if (h->mailbox) {
+    DeviceGuard dg(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->mailbox);
+  }
+  h->mailbox = nullptr;
+  h->peers_attached = false;
+  h->group = nullptr;
+  h->comm_size = 1;
+  h->comm_rank = 0;
+  h->corr_n = -1;
+  h->corr_warm = false;
+  h->src.drop_derived();  // (covariance arrays were sized and gathered for the sharded layout)
+  h->tgt.drop_derived();
+}
+
+}  // namespace
+
+extern "C" {
+
+int apd_group_create(apd_handle* const* handles, int32_t n, apd_group** out) {
+  if (!handles || !out || n < 1 || n > kPeerMaxRanks) return APD_ERR_INVALID;
+  *out = nullptr;
+  for (int r = 0; r < n; r++)
+    if (!handles[r] || handles[r]->sharded()) return APD_ERR_INVALID;
+  apd_group* g = new apd_group();
+  g->ranks.assign(handles, handles + n);
+  g->job_rc.assign((size_t)n, APD_OK);
+  // mailboxes, and peer access between the devices involved (one NVSwitch node: every pair is peer-accessible)
+  for (int r = 0; r < n; r++) {
+    apd_handle* h = handles[r];
+    DeviceGuard dg(h->device);
+    for (int q = 0; q < n; q++) {
+      if (handles[q]->device == h->device) continue;
+      const cudaError_t e = cudaDeviceEnablePeerAccess(handles[q]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        h->error = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+        for (int t = 0; t <= r; t++) group_detach(handles[t]);
+        delete g;
+        return APD_ERR_CUDA;
+      }
+      (void)cudaGetLastError();
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&h->mailbox), sizeof(PeerMailbox)) != cudaSuccess ||
+        cudaMemset(h->mailbox, 0, sizeof(PeerMailbox)) != cudaSuccess) {
+      for (int t = 0; t <= r; t++) group_detach(handles[t]);
+      delete g;
+      return APD_ERR_CUDA;
+    }
+  }
+  for (int r = 0; r < n; r++) {
+    apd_handle* h = handles[r];
+    for (int q = 0; q < n; q++) h->peer_box[q] = handles[q]->mailbox;
+    h->group = g;
+    h->comm_rank = r;
+    h->comm_size = n;
+    h->peers_attached = true;
+    h->xchg_seq = 0;
+    h->bar_seq = 0;
+    h->corr_n = -1;
+    h->corr_warm = false;
+    h->src.drop_derived();
+    h->tgt.drop_derived();
+  }
+  for (int r = 0; r < n; r++) g->threads.emplace_back(group_thread, g, r);
+  *out = g;
+  return APD_OK;
+}
+
+int apd_group_destroy(apd_group* g) {
+  if (!g) return APD_OK;
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->stop = true;
+  }
+  g->cv_job.notify_all();
+  for (auto& t : g->threads) t.join();
+  for (auto* h : g->ranks)
+    if (h) group_detach(h);
+  delete g;
+  return APD_OK;
+}
+
+int apd_group_size(const apd_group* g) { return g ? (int)g->ranks.size() : 0; }
+
+int apd_group_set_params(apd_group* g, const apd_params* p) {
+  if (!g || !p) return APD_ERR_INVALID;
+  for (auto* h : g->ranks) {
+    const int rc = apd_set_params(h, p);
+    if (rc != APD_OK) return rc;
+  }
+  return APD_OK;
+}
+
+int apd_group_set_source(apd_group* g, const void* pts, int32_t n, int32_t stride, int32_t xyz_off, int32_t label_off) {
+  if (!g) return APD_ERR_INVALID;
+  return group_run(g, [=](apd_handle* h, int) { return apd_set_source(h, pts, n, stride, xyz_off, label_off, 0); });
+}
+int apd_group_set_target(apd_group* g, const void* pts, int32_t n, int32_t stride, int32_t xyz_off, int32_t label_off) {
+  if (!g) return APD_ERR_INVALID;
+  return group_run(g, [=](apd_handle* h, int) { return apd_set_target(h, pts, n, stride, xyz_off, label_off, 0); });
+}
+int apd_group_set_source_device(apd_group* g, const void* const* d_xyzl, int32_t n) {
+  if (!g || !d_xyzl) return APD_ERR_INVALID;
+  return group_run(g, [=](apd_handle* h, int r) { return apd_set_source_device(h, d_xyzl[r], n); });
+}
+int apd_group_set_target_device(apd_group* g, const void* const* d_xyzl, int32_t n) {
+  if (!g || !d_xyzl) return APD_ERR_INVALID;
+  return group_run(g, [=](apd_handle* h, int r) { return apd_set_target_device(h, d_xyzl[r], n); });
+}
+
+int apd_group_align(apd_group* g, const float* guess, float* T_out, double* T_out_f64, double* H_out, int32_t* converged, int32_t* iterations) {
+  if (!g) return APD_ERR_INVALID;
+  return group_run(g, [=](apd_handle* h, int r) {  // every rank takes the same LM decisions on the reduced sums; rank 0 reports
+    return r == 0 ? apd_align(h, guess, T_out, T_out_f64, H_out, converged, iterations, nullptr)
+                  : apd_align(h, guess, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  });
+}
+int apd_group_linearize(apd_group* g, const double* T, double* H, double* b, double* err) {
+  if (!g || !T || !err) return APD_ERR_INVALID;
+  return group_run(g, [=](apd_handle* h, int r) {
+    double Hr[36], br[6], er;
+    return r == 0 ? apd_linearize(h, T, H, b, err) : apd_linearize(h, T, (H && b) ? Hr : nullptr, (H && b) ? br : nullptr, &er);
+  });
+}
+int apd_group_compute_error(apd_group* g, const double* T, double* err) {
+  if (!g || !T || !err) return APD_ERR_INVALID;
+  return group_run(g, [=](apd_handle* h, int r) {
+    double er;
+    return apd_compute_error(h, T, r == 0 ? err : &er);
+  });
 }
 
 // ---- instrumentation -------------------------------------------------------------

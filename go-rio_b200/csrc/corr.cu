@@ -4,28 +4,44 @@
 // matrix). Replaces FastAPDGICP::update_correspondences (reference
 // fast_apdgicp_impl.hpp:160-220). Also the fitness pass (pcl getFitnessScore)
 // and the export hooks.
-#include <cstdlib>
-
 #include "point_math.cuh"
 
 namespace apd {
 
 namespace {
 
+constexpr int kCorrLanesLarge = 1;  // lanes per 1-NN query on large source clouds
+
+PoseF pose_to_f32_host(const PoseD& T) {
+  PoseF f;
+  for (int i = 0; i < 9; i++) f.r[i] = (float)T.r[i];  // Isometry3d::cast<float>() (:164)
+  for (int i = 0; i < 3; i++) f.t[i] = (float)T.t[i];
+  return f;
+}
+
 constexpr int kThreads = 128;
-template <bool kFp64, int G>
-__global__ void __launch_bounds__(kThreads) update_corr_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_label,
-                                                               const double* __restrict__ s_cov, int n_src,
-                                                               const float4* __restrict__ t_spts, const float* __restrict__ t_label,
-                                                               const double* __restrict__ t_cov, const uint32_t* __restrict__ t_cell_start,
-                                                               GridDesc tg, PoseD T, NoiseParams np, int* __restrict__ corr,
-                                                               float* __restrict__ sqd, void* __restrict__ mahaA, void* __restrict__ mahaB,
-                                                               int warm, PoseD T_prev) {
-  // G lanes per source point (kThreads and the warp size are multiples of G, so a group never straddles a warp;
-  // the grid is sized so that whole warps are either in range or carry clamped duplicates of the last point)
-  const int gi = (blockIdx.x * kThreads + threadIdx.x) / G;
-  const int i = min(gi, n_src - 1);
-  const PoseF Tf = pose_to_f32(T);
+
+// rank-local slot l -> chunk j and offset o; false if the slot is padding
+__device__ __forceinline__ bool slot_of(const ShardTable& sh, int l, int& j, int& o) {
+  if (sh.nsub == 1) { j = 0; o = l; }
+  else { j = l / sh.chunk; o = l - j * sh.chunk; }
+  return j < sh.nsub && o < sh.count[j];
+}
+
+// ---- pass 1: the search (:176-190). fp32 and index work only: no fp64 state is live, so many warps fit an SM and the
+// divergent candidate loop is all the kernel has to hide. G lanes share a query.
+template <int G>
+__global__ void __launch_bounds__(kThreads) corr_search_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_label,
+                                                               ShardTable sh, const float4* __restrict__ t_spts,
+                                                               const float* __restrict__ t_label, const uint32_t* __restrict__ t_cell_start,
+                                                               GridDesc tg, PoseF Tf, double thr_sq, int* __restrict__ corr,
+                                                               float* __restrict__ sqd, int warm, PoseF Tpf) {
+  // kThreads and the warp size are multiples of G, so a group never straddles a warp; the lanes of a group share the
+  // slot, so a padding slot retires its whole group (every shuffle below is masked to the group's own lanes)
+  const int l = (int)(((size_t)blockIdx.x * kThreads + threadIdx.x) / G);
+  int j, o;
+  if (!slot_of(sh, l, j, o)) return;
+  const int i = sh.begin[j] + o;
   const float4 a = s_spts[i];
   float px, py, pz;
   transform_rn(Tf, a.x, a.y, a.z, px, py, pz);  // :176
@@ -34,39 +50,67 @@ __global__ void __launch_bounds__(kThreads) update_corr_kernel(const float4* __r
   int seed = -1;
   if (warm) {
     float kept;
-    if (!warm_start(pose_to_f32(T_prev), a, px, py, pz, corr[i], sqd[i], np.thr_sq, seed, kept)) {  // (uniform over the G lanes of a query)
+    if (!warm_start(Tpf, a, px, py, pz, corr[l], sqd[l], thr_sq, seed, kept)) {  // (uniform over the G lanes of a query)
       nn_group_sync<G>();
-      if (gi < n_src && (G == 1 || (threadIdx.x & (G - 1)) == 0)) sqd[i] = kept;  // still unmatched; corr[i] stays -1
+      if (G == 1 || (threadIdx.x & (G - 1)) == 0) sqd[l] = kept;  // still unmatched; corr[l] stays -1
       return;
     }
+    nn_group_sync<G>();  // every lane of the group has read corr[l] / sqd[l] before lane 0 rewrites them
   }
   unsigned long long best;
   int pos;
   float proven2;
-  nn_search<G>(t_spts, t_cell_start, tg, px, py, pz, np.thr_sq, best, pos, seed, proven2);  // :178
-  if (gi >= n_src || (G > 1 && (threadIdx.x & (G - 1)) != 0)) return;  // one lane per point finishes the job
+  nn_search<G>(t_spts, t_cell_start, tg, px, py, pz, thr_sq, best, pos, seed, proven2);  // :178
+  if (G > 1 && (threadIdx.x & (G - 1)) != 0) return;  // one lane per point finishes the job
   const float d2 = (best == kInfKey) ? 3.402823466e38f : __uint_as_float((unsigned)(best >> 32));
-  const bool ok = (best != kInfKey) && ((double)d2 < np.thr_sq);  // :183
+  const bool ok = (best != kInfKey) && ((double)d2 < thr_sq);  // :183
   if (!ok) {
-    corr[i] = -1;
-    sqd[i] = fminf(d2, proven2);  // (:180 stores the found distance; for a rejected point this slot is write-only scratch in the
+    corr[l] = -1;
+    sqd[l] = fminf(d2, proven2);  // (:180 stores the found distance; for a rejected point this slot is write-only scratch in the
                                   // reference — here it keeps the proven lower bound of its distance for the next warm start)
     return;
   }
-  sqd[i] = d2;  // :180
-  corr[i] = pos | ((t_label[pos] == s_label[i]) ? kCorrLabelBit : 0);  // label test of :271-273, hoisted
+  sqd[l] = d2;  // :180
+  corr[l] = pos | ((__ldg(&t_label[pos]) == s_label[i]) ? kCorrLabelBit : 0);  // label test of :271-273, hoisted
+}
 
-  // radar noise covariance, combined covariance and its inverse (:194-218)
-  const Sym3 M = mahalanobis_of(px, py, pz, s_cov + (size_t)i * 6, t_cov + (size_t)pos * 6, T, np);
+// ---- pass 2: radar noise covariance, combined covariance and its inverse (:194-218), one thread per matched pair:
+// coalesced streams (point 16 B, correspondence 4 B, source covariance 48 B, Mahalanobis out 24 / 48 B) + one 48-byte
+// gather of the target covariance; fp64 arithmetic.
+template <bool kFp64>
+__global__ void __launch_bounds__(256) maha_kernel(const float4* __restrict__ s_spts, const double* __restrict__ s_cov, ShardTable sh,
+                                                   const double* __restrict__ t_cov, PoseD T, NoiseParams np, const int* __restrict__ corr,
+                                                   void* __restrict__ mahaA, void* __restrict__ mahaB) {
+  const int l = blockIdx.x * 256 + threadIdx.x;
+  int j, o;
+  if (!slot_of(sh, l, j, o)) return;
+  const int c = corr[l];
+  if (c < 0) return;  // (the reductions never read the matrix of an unmatched point)
+  const int i = sh.begin[j] + o;
+  const int pos = c & kCorrIndexMask;
+  const float4 a = s_spts[i];
+  const PoseF Tf = pose_to_f32(T);
+  float px, py, pz;
+  transform_rn(Tf, a.x, a.y, a.z, px, py, pz);
+  double ca[6], cb[6];
+  {
+    const double2* pa = reinterpret_cast<const double2*>(s_cov + (size_t)i * 6);
+    const double2* pb = reinterpret_cast<const double2*>(t_cov + (size_t)pos * 6);
+    const double2 a0 = pa[0], a1 = pa[1], a2 = pa[2];
+    const double2 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+    ca[0] = a0.x; ca[1] = a0.y; ca[2] = a1.x; ca[3] = a1.y; ca[4] = a2.x; ca[5] = a2.y;
+    cb[0] = b0.x; cb[1] = b0.y; cb[2] = b1.x; cb[3] = b1.y; cb[4] = b2.x; cb[5] = b2.y;
+  }
+  const Sym3 M = mahalanobis_of(px, py, pz, ca, cb, T, np);
   if (kFp64) {
     double2* mA = reinterpret_cast<double2*>(mahaA);
     double2* mB = reinterpret_cast<double2*>(mahaB);
-    mA[i] = make_double2(M.v[0], M.v[1]);
-    mB[i] = make_double2(M.v[2], M.v[3]);
-    mB[(size_t)n_src + i] = make_double2(M.v[4], M.v[5]);
+    mA[l] = make_double2(M.v[0], M.v[1]);
+    mB[l] = make_double2(M.v[2], M.v[3]);
+    mB[(size_t)sh.plane + l] = make_double2(M.v[4], M.v[5]);
   } else {
-    reinterpret_cast<float4*>(mahaA)[i] = make_float4((float)M.v[0], (float)M.v[1], (float)M.v[2], (float)M.v[3]);
-    reinterpret_cast<float2*>(mahaB)[i] = make_float2((float)M.v[4], (float)M.v[5]);
+    reinterpret_cast<float4*>(mahaA)[l] = make_float4((float)M.v[0], (float)M.v[1], (float)M.v[2], (float)M.v[3]);
+    reinterpret_cast<float2*>(mahaB)[l] = make_float2((float)M.v[4], (float)M.v[5]);
   }
 }
 
@@ -116,15 +160,38 @@ __global__ void __launch_bounds__(kFitThreads) fitness_kernel(const float4* __re
   }
 }
 
+// ---- per-point nearest neighbour of the transformed source (the search-method adaptor's batch) ----
+__global__ void __launch_bounds__(kFitThreads) source_nearest_kernel(const float4* __restrict__ s_spts, int n_src, const float4* __restrict__ t_spts,
+                                                                     const uint32_t* __restrict__ t_cell_start, GridDesc tg, PoseF Tf,
+                                                                     int32_t* __restrict__ idx, float* __restrict__ d2out, float* __restrict__ xyz) {
+  const int i = blockIdx.x * kFitThreads + threadIdx.x;
+  if (i >= n_src) return;
+  const float4 a = s_spts[i];
+  const int oi = __float_as_int(a.w);
+  float px, py, pz;
+  transform_rn(Tf, a.x, a.y, a.z, px, py, pz);
+  unsigned long long best;
+  int pos;
+  nn_search<1>(t_spts, t_cell_start, tg, px, py, pz, 1e300, best, pos);
+  idx[oi] = best == kInfKey ? -1 : (int)(unsigned)(best & 0xffffffffull);
+  d2out[oi] = best == kInfKey ? 3.402823466e38f : __uint_as_float((unsigned)(best >> 32));
+  if (xyz) {
+    xyz[3 * (size_t)oi + 0] = px;
+    xyz[3 * (size_t)oi + 1] = py;
+    xyz[3 * (size_t)oi + 2] = pz;
+  }
+}
+
 // ---- export hooks ----------------------------------------------------------------
 template <bool kFp64>
-__global__ void __launch_bounds__(256) corr_export_kernel(const float4* __restrict__ s_spts, int n_src, const float4* __restrict__ t_spts,
+__global__ void __launch_bounds__(256) corr_export_kernel(const float4* __restrict__ s_spts, ShardTable sh, const float4* __restrict__ t_spts,
                                                           const int* __restrict__ corr, const float* __restrict__ sqd,
                                                           const void* __restrict__ mahaA, const void* __restrict__ mahaB,
                                                           int32_t* __restrict__ idx_out, float* __restrict__ sqd_out, double* __restrict__ maha_out) {
-  const int s = blockIdx.x * 256 + threadIdx.x;
-  if (s >= n_src) return;
-  const int oi = __float_as_int(s_spts[s].w);
+  const int s = blockIdx.x * 256 + threadIdx.x;  // rank-local slot
+  int j, o;
+  if (!slot_of(sh, s, j, o)) return;
+  const int oi = __float_as_int(s_spts[sh.begin[j] + o].w);
   const int c = corr[s];
   if (idx_out) idx_out[oi] = c < 0 ? -1 : __float_as_int(t_spts[c & kCorrIndexMask].w);
   if (sqd_out) sqd_out[oi] = sqd[s];
@@ -134,7 +201,7 @@ __global__ void __launch_bounds__(256) corr_export_kernel(const float4* __restri
       if (kFp64) {
         const double2 a = reinterpret_cast<const double2*>(mahaA)[s];
         const double2 b = reinterpret_cast<const double2*>(mahaB)[s];
-        const double2 d = reinterpret_cast<const double2*>(mahaB)[(size_t)n_src + s];
+        const double2 d = reinterpret_cast<const double2*>(mahaB)[(size_t)sh.plane + s];
         m[0] = a.x; m[1] = a.y; m[2] = b.x; m[3] = b.y; m[4] = d.x; m[5] = d.y;
       } else {
         const float4 a = reinterpret_cast<const float4*>(mahaA)[s];
@@ -163,28 +230,31 @@ __global__ void __launch_bounds__(256) transform_cloud_kernel(const float4* __re
 
 }  // namespace
 
-void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const NoiseParams& np,
-                                   const CorrOut& out, const PoseD* T_prev, cudaStream_t s, int64_t* launches) {
-  if (src.n <= 0) return;
-#define APD_CORR(FP64, GG)                                                                                                              \
-  update_corr_kernel<FP64, GG><<<(unsigned)(((size_t)src.n * GG + kThreads - 1) / kThreads), kThreads, 0, s>>>(                           \
-      src.spts, src.label, src.cov, src.n, tgt.spts, tgt.label, tgt.cov, tgt.cell_start, tgt.g, T, np, out.corr, out.sqd, out.mahaA, \
-      out.mahaB, T_prev ? 1 : 0, T_prev ? *T_prev : T)
-  // small source clouds are latency-bound: 8 lanes share a query; large ones are throughput-bound: one lane per query.
-  // APD_CORR_MODE = wide | lane forces one variant (tests, profiling); both give identical results.
+void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const PoseD& T, const NoiseParams& np,
+                                   const CorrOut& out, const PoseD* T_prev, int lanes, cudaStream_t s, int64_t* launches) {
+  const int slots = sh.slots();
+  if (slots <= 0) return;
+  // small source clouds are latency-bound: 8 lanes share a query; large ones are throughput-bound (see DESIGN.md §4.3 for
+  // the measured choice). All variants give identical results.
   // (Tried and dropped, 20 M points on B200: staging the union box of a warp's 32 query cubes in shared memory with bulk
   // copies and scanning it densely — 5.7 ms against 4.1 ms: in x-fastest cell order a warp's queries form a strip ~200 cells
   // long, so the box holds ~100x the 4-5 candidates a query needs.)
-  const char* e = getenv("APD_CORR_MODE");
-  const char mode = e ? e[0] : (src.n < 65536 ? 'w' : 'l');
-  if (out.maha_fp64) {
-    if (mode == 'w') APD_CORR(true, 8);
-    else APD_CORR(true, 1);
-  } else {
-    if (mode == 'w') APD_CORR(false, 8);
-    else APD_CORR(false, 1);
+  if (lanes <= 0) lanes = src.n < 65536 ? 8 : kCorrLanesLarge;
+  const PoseF Tf = pose_to_f32_host(T), Tpf = pose_to_f32_host(T_prev ? *T_prev : T);
+#define APD_SEARCH(GG)                                                                                                                 \
+  corr_search_kernel<GG><<<(unsigned)(((size_t)slots * GG + kThreads - 1) / kThreads), kThreads, 0, s>>>(                               \
+      src.spts, src.label, sh, tgt.spts, tgt.label, tgt.cell_start, tgt.g, Tf, np.thr_sq, out.corr, out.sqd, T_prev ? 1 : 0, Tpf)
+  switch (lanes) {
+    case 1: APD_SEARCH(1); break;
+    case 2: APD_SEARCH(2); break;
+    case 4: APD_SEARCH(4); break;
+    default: APD_SEARCH(8); break;
   }
-#undef APD_CORR
+#undef APD_SEARCH
+  (*launches)++;
+  const unsigned mblocks = (unsigned)((slots + 255) / 256);
+  if (out.maha_fp64) maha_kernel<true><<<mblocks, 256, 0, s>>>(src.spts, src.cov, sh, tgt.cov, T, np, out.corr, out.mahaA, out.mahaB);
+  else maha_kernel<false><<<mblocks, 256, 0, s>>>(src.spts, src.cov, sh, tgt.cov, T, np, out.corr, out.mahaA, out.mahaB);
   (*launches)++;
 }
 
@@ -197,14 +267,22 @@ void launch_fitness(const CloudDev& src, const CloudDev& tgt, const PoseF& T, do
   (*launches)++;
 }
 
-void launch_corr_export(const CloudDev& src, const CloudDev& tgt, const CorrOut& c, int32_t* d_idx, float* d_sqd, double* d_maha4x4,
-                        cudaStream_t s, int64_t* launches) {
+void launch_source_nearest(const CloudDev& src, const CloudDev& tgt, const PoseF& T, int32_t* d_idx, float* d_d2, float* d_xyz, cudaStream_t s,
+                           int64_t* launches) {
   if (src.n <= 0) return;
-  const int blocks = (src.n + 255) / 256;
+  source_nearest_kernel<<<(src.n + kFitThreads - 1) / kFitThreads, kFitThreads, 0, s>>>(src.spts, src.n, tgt.spts, tgt.cell_start, tgt.g, T, d_idx,
+                                                                                      d_d2, d_xyz);
+  (*launches)++;
+}
+
+void launch_corr_export(const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const CorrOut& c, int32_t* d_idx, float* d_sqd,
+                        double* d_maha4x4, cudaStream_t s, int64_t* launches) {
+  if (sh.slots() <= 0) return;
+  const int blocks = (sh.slots() + 255) / 256;
   if (c.maha_fp64)
-    corr_export_kernel<true><<<blocks, 256, 0, s>>>(src.spts, src.n, tgt.spts, c.corr, c.sqd, c.mahaA, c.mahaB, d_idx, d_sqd, d_maha4x4);
+    corr_export_kernel<true><<<blocks, 256, 0, s>>>(src.spts, sh, tgt.spts, c.corr, c.sqd, c.mahaA, c.mahaB, d_idx, d_sqd, d_maha4x4);
   else
-    corr_export_kernel<false><<<blocks, 256, 0, s>>>(src.spts, src.n, tgt.spts, c.corr, c.sqd, c.mahaA, c.mahaB, d_idx, d_sqd, d_maha4x4);
+    corr_export_kernel<false><<<blocks, 256, 0, s>>>(src.spts, sh, tgt.spts, c.corr, c.sqd, c.mahaA, c.mahaB, d_idx, d_sqd, d_maha4x4);
   (*launches)++;
 }
 

@@ -61,11 +61,36 @@ void launch_cov_regularize(const CloudDev& c, int k, int regularization, const i
 void launch_knn_cov_fused(const CloudDev& c, int k, int regularization, int32_t* neighbors, cudaStream_t s, int64_t* launches, int w0 = 0,
                           int wn = -1);
 void launch_regularize(const CloudDev& c, int regularization, cudaStream_t s, int64_t* launches);
+// exact kNN (k <= 32) of nq arbitrary query points {x,y,z,-} on the cloud's grid: d_idx / d_d2 [q*k + j] = original ids and
+// fp32 squared distances, ascending by (d2, index)
+void launch_knn_query(const CloudDev& c, int k, const float4* d_queries, int nq, int32_t* d_idx, float* d_d2, cudaStream_t s, int64_t* launches);
 // geo weight only (after set*Covariances)
 void launch_geo_weight(const CloudDev& c, cudaStream_t s, int64_t* launches);
 // covariance layout conversion for the getters/setters: sorted sym6 <-> 4x4 col-major in original order
 void launch_cov_export(const CloudDev& c, double* d_out4x4, cudaStream_t s, int64_t* launches);
 void launch_cov_import(const CloudDev& c, const double* d_in4x4, cudaStream_t s, int64_t* launches);
+
+// ---- sharding of one registration over several GPUs ------------------------------
+// The cell-sorted source points are cut into nranks * kShardSubMax equal chunks of `chunk` points (a multiple of 256, so
+// every chunk starts on a tile and on a 16-byte boundary of every per-point array); rank r owns chunks r, r + nranks, ...
+// (interleaved: the cost of a query varies across a scene). A kernel gets the rank's chunks as a table and serves all of
+// them in ONE launch. Per-cloud arrays (spts, label, cov, geo) are indexed by the global sorted position begin[j] + o,
+// per-linearisation arrays (corr, sqd, Mahalanobis) by the rank-local slot j * chunk + o. Unsharded: one chunk,
+// begin 0, count n, chunk n — both indices are the sorted position.
+constexpr int kShardSubMax = 4;
+struct ShardTable {
+  int nsub = 1;
+  int chunk = 0;
+  int begin[kShardSubMax] = {0, 0, 0, 0};
+  int count[kShardSubMax] = {0, 0, 0, 0};
+  int plane = 0;  // local slots in all (= stride between the planes of the fp64 Mahalanobis storage)
+  __host__ __device__ int slots() const { return nsub * chunk; }
+};
+inline ShardTable whole_cloud(int n) {
+  ShardTable t;
+  t.nsub = 1; t.chunk = n; t.count[0] = n; t.plane = n;
+  return t;
+}
 
 // ---- corr.cu -----------------------------------------------------------------
 struct NoiseParams {
@@ -83,16 +108,25 @@ struct CorrOut {
   void* mahaB;    // float2[n] or double2[2n]
   int maha_fp64;
 };
-// reference update_correspondences (fast_apdgicp_impl.hpp:160-220). T_prev != nullptr: `out` still holds the result of
-// the previous pass over the same clouds at pose T_prev, which warm-starts the searches (identical results).
-void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const NoiseParams& np,
-                                   const CorrOut& out, const PoseD* T_prev, cudaStream_t s, int64_t* launches);
+// reference update_correspondences (fast_apdgicp_impl.hpp:160-220) over the source points `sh` lists, in two launches:
+// the search (:176-190: fp32 transform, exact 1-NN on the target grid, threshold; writes corr + sqd) and the per-point
+// noise model / combined covariance / inverse (:194-218; reads the matched pairs coalesced, writes the Mahalanobis
+// planes). T_prev != nullptr: `out` still holds the result of the previous pass over the same clouds at pose T_prev,
+// which warm-starts the searches (identical results). lanes: lanes per 1-NN query (0: by cloud size).
+void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const PoseD& T, const NoiseParams& np,
+                                   const CorrOut& out, const PoseD* T_prev, int lanes, cudaStream_t s, int64_t* launches);
 // getFitnessScore + inlier count: d_out = {sum d2 (double), n_in_range (as double), n_inliers (as double)}
 void launch_fitness(const CloudDev& src, const CloudDev& tgt, const PoseF& T, double max_range, double inlier_sq_thr,
                     double* d_partials, int max_blocks, double* d_out3, unsigned int* d_ticket, cudaStream_t s,
                     int64_t* launches);
+// the nearest target point of every source point under pose T, in the source's ORIGINAL order: the transformed point
+// (fp32, pcl::transformPointCloud's arithmetic), the target point's original id (-1: empty target) and the fp32 squared
+// distance — what pcl::Registration::getFitnessScore and the nodelet's inlier loop ask the search method for, one
+// point at a time (scan_matching_odometry_nodelet.cpp:674-691)
+void launch_source_nearest(const CloudDev& src, const CloudDev& tgt, const PoseF& T, int32_t* d_idx, float* d_d2, float* d_xyz, cudaStream_t s,
+                           int64_t* launches);
 // hooks: correspondences / mahalanobis back to original order and ids
-void launch_corr_export(const CloudDev& src, const CloudDev& tgt, const CorrOut& c, int32_t* d_idx, float* d_sqd,
+void launch_corr_export(const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const CorrOut& c, int32_t* d_idx, float* d_sqd,
                         double* d_maha4x4, cudaStream_t s, int64_t* launches);
 // transformed source cloud in original order (pcl::transformPointCloud)
 void launch_transform_cloud(const float4* pts, int n, const PoseF& T, float* d_xyz, cudaStream_t s, int64_t* launches);
@@ -108,6 +142,7 @@ constexpr int kPeerMaxRanks = 16;
 struct PeerMailbox {
   double val[2][kPeerMaxRanks][32];
   unsigned int flag[2][kPeerMaxRanks];
+  unsigned int bar[kPeerMaxRanks];  // launch_peer_barrier: bar[r] = the last barrier number rank r has reached
   unsigned int timed_out;  // set if a peer did not show up within the time limit (the sums are then NaN)
 };
 struct PeerExchange {
@@ -123,10 +158,12 @@ struct ReduceWork {
 };
 // reference linearize (:247-304) / compute_error (:313-343) given the stored
 // correspondences and Mahalanobis matrices. out28 = 21 upper-triangular H
-// entries (row-major, r<=c), 6 b, 1 err. cl_weight = 1 / n_total. accumulate: add to out28 instead of overwriting it
-// (the chunks of a sharded source are launched one after the other).
-void launch_linearize(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const CorrOut& c, double n_total,
-                      bool want_hb, bool accumulate, const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches);
+// entries (row-major, r<=c), 6 b, 1 err. cl_weight = 1 / n_total. One launch serves all the chunks `sh` lists.
+void launch_linearize(const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const PoseD& T, const CorrOut& c, double n_total,
+                      bool want_hb, const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches);
+// barrier across the ranks of a sharded registration on their streams (one tiny kernel per rank: publish a sequence
+// number in every peer's mailbox, wait for all of them) — orders the peer-to-peer copies of the covariance all-gather
+void launch_peer_barrier(const PeerExchange& x, cudaStream_t s, int64_t* launches);
 
 // ---- lm.cu ---------------------------------------------------------------------
 // The device-resident optimizer loop (LsqRegistration::computeTransformation,

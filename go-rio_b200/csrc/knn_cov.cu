@@ -40,6 +40,24 @@ __global__ void __launch_bounds__(kWarpKnnThreads) knn_cov_kernel(const float4* 
   emit_point(mykey, lane, k, w, qi, nb, neighbors);
 }
 
+// exact kNN of arbitrary query points on a cloud's grid (apd_nearest_k: the search method PCL callers reach through
+// pcl::Registration::getSearchMethodTarget()): one warp per query, k <= 32; out_idx / out_d2 [q*k + j], ascending by
+// (d2, index); entries beyond the cloud's size read -1 / inf
+__global__ void __launch_bounds__(kWarpKnnThreads) knn_query_kernel(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start,
+                                                                    GridDesc g, int n, int k, const float4* __restrict__ queries, int nq,
+                                                                    int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+  const int lane = threadIdx.x & 31;
+  __shared__ unsigned long long kbuf[kWarpKnnThreads / 32][32];
+  const int qi = (blockIdx.x * kWarpKnnThreads + threadIdx.x) >> 5;
+  if (qi >= nq) return;
+  const unsigned long long key = knn_warp_query_at(spts, cell_start, g, min(k, n), queries[qi], lane, kbuf[threadIdx.x >> 5]);
+  if (lane < k) {
+    const bool have = lane < n && key != kInfKey;
+    out_idx[(size_t)qi * k + lane] = have ? (int)(unsigned)(key & 0xffffffffull) : -1;
+    out_d2[(size_t)qi * k + lane] = have ? __uint_as_float((unsigned)(key >> 32)) : __int_as_float(0x7f800000);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) regularize_kernel(double* __restrict__ cov, float* __restrict__ geo, double* __restrict__ geo64, int n, int reg) {
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
@@ -287,6 +305,13 @@ void launch_knn_cov(const CloudDev& c, int k, int32_t* d_nb, int32_t* neighbors,
   const long long threads = (long long)wn * 32;
   const int blocks = (int)((threads + kWarpKnnThreads - 1) / kWarpKnnThreads);
   knn_cov_kernel<<<blocks, kWarpKnnThreads, 0, s>>>(c.spts, c.cell_start, c.g, c.n, k, d_nb, neighbors, w0, wn);
+  (*launches)++;
+}
+void launch_knn_query(const CloudDev& c, int k, const float4* d_queries, int nq, int32_t* d_idx, float* d_d2, cudaStream_t s, int64_t* launches) {
+  if (c.n <= 0 || nq <= 0) return;
+  const long long threads = (long long)nq * 32;
+  knn_query_kernel<<<(unsigned)((threads + kWarpKnnThreads - 1) / kWarpKnnThreads), kWarpKnnThreads, 0, s>>>(c.spts, c.cell_start, c.g, c.n, k,
+                                                                                                        d_queries, nq, d_idx, d_d2);
   (*launches)++;
 }
 void launch_cov_regularize(const CloudDev& c, int k, int regularization, const int32_t* d_nb, cudaStream_t s, int64_t* launches, int w0, int wn) {

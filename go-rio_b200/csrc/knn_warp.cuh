@@ -117,9 +117,9 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ spts, f
 // Exact k nearest neighbours (ties by (d2, index)) of sorted point w, by the 32 lanes of one warp. Returns one
 // (d2, original index) key per lane, ascending: lanes 0..k-1 hold the answer. kbuf: 32 keys of shared memory owned by
 // this warp. Replaces the nearestKSearch of reference fast_apdgicp_impl.hpp:364.
-__device__ __forceinline__ unsigned long long knn_warp_query(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start,
-                                                             const GridDesc& g, int k, int w, int lane, unsigned long long* kbuf) {
-  const float4 q = spts[w];
+// knn_warp_query_at: the same for an arbitrary query point q (not necessarily a point of the cloud).
+__device__ __forceinline__ unsigned long long knn_warp_query_at(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start,
+                                                                const GridDesc& g, int k, const float4 q, int lane, unsigned long long* kbuf) {
   const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
   const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
   const int cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz);
@@ -206,6 +206,10 @@ __device__ __forceinline__ unsigned long long knn_warp_query(const float4* __res
     r = rr;
   }
   return st.list;
+}
+__device__ __forceinline__ unsigned long long knn_warp_query(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start,
+                                                             const GridDesc& g, int k, int w, int lane, unsigned long long* kbuf) {
+  return knn_warp_query_at(spts, cell_start, g, k, spts[w], lane, kbuf);
 }
 
 __device__ __forceinline__ double geo_weight_of(const Sym3& C) {

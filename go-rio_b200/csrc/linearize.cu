@@ -20,6 +20,8 @@
 // per-block order -> per-block partials -> the last block (atomic ticket) adds
 // the partials in block order. The tile->CTA mapping is static, so for a given n
 // the result is bit-reproducible run to run.
+#include <atomic>
+
 #include "point_math.cuh"
 
 namespace apd {
@@ -86,7 +88,7 @@ template <bool kFp64, bool kHB>
 __global__ void __launch_bounds__(kThreads, 2)
 linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_geo, const double* __restrict__ s_geo64,
                  const int* __restrict__ corr, const void* __restrict__ mahaA, const void* __restrict__ mahaB,
-                 const float4* __restrict__ t_spts, PoseD T, double cl_w, int n, int accumulate, double* __restrict__ partials,
+                 const float4* __restrict__ t_spts, PoseD T, double cl_w, ShardTable sh, double* __restrict__ partials,
                  double* __restrict__ out28, unsigned int* __restrict__ ticket, PeerExchange xchg) {
   using L = StageLayout<kFp64>;
   constexpr int NV = kHB ? kReduceVals : 1;
@@ -95,7 +97,17 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
   unsigned char* gat = smem + kStages * L::kBytes;  // float4[2][256] gathered target points
 
   const int tid = threadIdx.x;
-  const int ntiles = (n + kTile - 1) / kTile;
+  // tiles: chunk j of the rank's source points holds tpc tiles (a chunk is a whole number of tiles when there are several)
+  const int tpc = (sh.chunk + kTile - 1) / kTile;
+  const int ntiles = sh.nsub * tpc;
+  // tile -> (first global sorted position, first rank-local slot, points in the tile; 0 for a padding tile)
+  auto tile_span = [&](int tile, size_t& gbase, size_t& lbase) -> int {
+    const int j = sh.nsub == 1 ? 0 : tile / tpc;
+    const int o = (tile - j * tpc) * kTile;
+    gbase = (size_t)sh.begin[j] + o;
+    lbase = (size_t)j * sh.chunk + o;
+    return max(0, min(kTile, sh.count[j] - o));
+  };
   const int my = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
@@ -107,26 +119,26 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
 
   // one elected thread feeds the ring: tile j of this CTA -> stage j % kStages
   auto issue_tile = [&](int j) {
-    const int tile = (int)blockIdx.x + j * (int)gridDim.x;
-    const size_t base = (size_t)tile * kTile;
-    const int cnt = min(kTile, n - (int)base);
+    size_t gb, base;  // gb: per-cloud arrays (spts, geo); base: per-linearisation arrays (corr, Mahalanobis)
+    const int cnt = tile_span((int)blockIdx.x + j * (int)gridDim.x, gb, base);
     const uint32_t c4 = (uint32_t)((cnt + 3) & ~3);  // element count rounded so every copy is a multiple of 16 B
     unsigned char* st = smem + (j % kStages) * L::kBytes;
     uint64_t* bar = &full_bar[j % kStages];
     const uint32_t b_spts = c4 * 16, b_corr = c4 * 4;
     const uint32_t b_mA = c4 * 16, b_mB = kFp64 ? c4 * 16 : c4 * 8, b_geo = kFp64 ? c4 * 8 : c4 * 4;
     mbar_expect_tx(bar, b_spts + b_corr + b_mA + (kFp64 ? 2 * b_mB : b_mB) + b_geo);
-    bulk_g2s(st + L::kSpts, s_spts + base, b_spts, bar);
+    if (c4 == 0) return;  // (a padding tile: the barrier completes on the arrival alone)
+    bulk_g2s(st + L::kSpts, s_spts + gb, b_spts, bar);
     bulk_g2s(st + L::kCorr, corr + base, b_corr, bar);
     if (kFp64) {
       bulk_g2s(st + L::kMahaA, reinterpret_cast<const double2*>(mahaA) + base, b_mA, bar);
       bulk_g2s(st + L::kMahaB, reinterpret_cast<const double2*>(mahaB) + base, b_mB, bar);
-      bulk_g2s(st + L::kMahaB + kTile * 16, reinterpret_cast<const double2*>(mahaB) + (size_t)n + base, b_mB, bar);
-      bulk_g2s(st + L::kGeo, s_geo64 + base, b_geo, bar);
+      bulk_g2s(st + L::kMahaB + kTile * 16, reinterpret_cast<const double2*>(mahaB) + (size_t)sh.plane + base, b_mB, bar);
+      bulk_g2s(st + L::kGeo, s_geo64 + gb, b_geo, bar);
     } else {
       bulk_g2s(st + L::kMahaA, reinterpret_cast<const float4*>(mahaA) + base, b_mA, bar);
       bulk_g2s(st + L::kMahaB, reinterpret_cast<const float2*>(mahaB) + base, b_mB, bar);
-      bulk_g2s(st + L::kGeo, s_geo + base, b_geo, bar);
+      bulk_g2s(st + L::kGeo, s_geo + gb, b_geo, bar);
     }
   };
   if (tid == 0) {
@@ -136,11 +148,11 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
 
   // per-thread gather of the matched target point of tile j into gat[j & 1]
   auto issue_gather = [&](int j) {
-    const int tile = (int)blockIdx.x + j * (int)gridDim.x;
-    const int i = tile * kTile + tid;
+    size_t gb, lb;
+    const int cnt = tile_span((int)blockIdx.x + j * (int)gridDim.x, gb, lb);
     const unsigned char* st = smem + (j % kStages) * L::kBytes;
-    const int c = reinterpret_cast<const int*>(st + L::kCorr)[tid];
-    const int pos = (i < n && c >= 0) ? (c & kCorrIndexMask) : 0;
+    const int c = tid < cnt ? reinterpret_cast<const int*>(st + L::kCorr)[tid] : -1;
+    const int pos = c >= 0 ? (c & kCorrIndexMask) : 0;
     cp_async16(gat + ((j & 1) * kTile + tid) * 16, t_spts + pos);
   };
 
@@ -162,11 +174,11 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
     cp_async_commit();
     cp_async_wait<1>();  // everything but the newest group: tile j's gather has landed
 
-    const int tile = (int)blockIdx.x + j * (int)gridDim.x;
-    const int i = tile * kTile + tid;
+    size_t gb, lb;
+    const int cnt = tile_span((int)blockIdx.x + j * (int)gridDim.x, gb, lb);
     const unsigned char* st = smem + (j % kStages) * L::kBytes;
-    const int c = reinterpret_cast<const int*>(st + L::kCorr)[tid];
-    const bool valid = (i < n) && (c >= 0);
+    const int c = tid < cnt ? reinterpret_cast<const int*>(st + L::kCorr)[tid] : -1;
+    const bool valid = c >= 0;
     const float4 a = reinterpret_cast<const float4*>(st + L::kSpts)[tid];
     const float4 b = reinterpret_cast<const float4*>(gat)[(j & 1) * kTile + tid];
     double m[6], geo;
@@ -190,20 +202,20 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
   cp_async_wait<0>();
 
   // warp tree -> block -> partials -> last block
-  __shared__ double sh[kWarps][NV];
+  __shared__ double wsum[kWarps][NV];
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int j = 0; j < NV; j++) {
     double v = acc[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) sh[warp][j] = v;
+    if (lane == 0) wsum[warp][j] = v;
   }
   __syncthreads();
   if (tid < NV) {
     double v = 0.0;
 #pragma unroll
-    for (int w2 = 0; w2 < kWarps; w2++) v += sh[w2][tid];
+    for (int w2 = 0; w2 < kWarps; w2++) v += wsum[w2][tid];
     partials[(size_t)blockIdx.x * NV + tid] = v;
   }
   __shared__ bool last;
@@ -217,8 +229,6 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
     double* o = kHB ? &out28[tid < NV ? tid : 0] : &out28[27];
     if (tid < NV) {
       for (unsigned int k = 0; k < gridDim.x; k++) v += __ldcg(&partials[(size_t)k * NV + tid]);
-      // accumulate: this launch covers one chunk of a sharded source; the sums continue those of the previous chunks
-      if (accumulate) v = *o + v;
     }
     if (xchg.seq != 0) {
       // ---- fused all-reduce over peer memory (see PeerExchange) ----
@@ -258,36 +268,63 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
 }
 
 template <bool kFp64, bool kHB>
-void launch_one(int blocks, cudaStream_t s, const CloudDev& src, const CloudDev& tgt, const PoseD& T, const CorrOut& c, double cl_w,
-                bool accumulate, const ReduceWork& w, double* d_out28) {
-  static bool configured[64] = {false};  // per template instance and device: the attribute is per (function, device)
+void launch_one(int blocks, cudaStream_t s, const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const PoseD& T, const CorrOut& c,
+                double cl_w, const ReduceWork& w, double* d_out28) {
+  // the attribute is per (function, device); handles of several devices and pool threads come through here
+  static std::atomic<bool> configured[64];
   constexpr int bytes = smem_bytes<kFp64>();
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     cudaFuncSetAttribute(linearize_kernel<kFp64, kHB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   linearize_kernel<kFp64, kHB><<<blocks, kThreads, bytes, s>>>(src.spts, src.geo, src.geo64, c.corr, c.mahaA, c.mahaB, tgt.spts, T, cl_w,
-                                                                src.n, accumulate ? 1 : 0, w.partials, d_out28, w.ticket, w.xchg);
+                                                                sh, w.partials, d_out28, w.ticket, w.xchg);
+}
+
+// barrier of the ranks of a sharded registration (see launch_peer_barrier)
+__global__ void peer_barrier_kernel(PeerExchange x) {
+  const int tid = threadIdx.x;
+  if (tid >= x.nranks) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&x.box[tid]->bar[x.rank]), "r"(x.seq) : "memory");
+  PeerMailbox* mine = x.box[x.rank];
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned int f;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&mine->bar[tid]) : "memory");
+    if ((int)(f - x.seq) >= 0) break;  // (a peer may already have reached a later barrier)
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull) {  // 20 s (a peer may still be searching its covariances): give up rather than hang the GPU
+      mine->timed_out = 1u;
+      break;
+    }
+    __nanosleep(256);
+  }
 }
 
 }  // namespace
 
-void launch_linearize(const CloudDev& src, const CloudDev& tgt, const PoseD& T, const CorrOut& c, double n_total, bool want_hb,
-                      bool accumulate, const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches) {
-  const int n = src.n;
-  if (n <= 0 && accumulate && w.xchg.seq == 0) return;  // an empty chunk adds nothing (unless it carries the exchange)
-  int blocks = (n + kTile - 1) / kTile;
+void launch_linearize(const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const PoseD& T, const CorrOut& c, double n_total,
+                      bool want_hb, const ReduceWork& w, double* d_out28, cudaStream_t s, int64_t* launches) {
+  const int tpc = (sh.chunk + kTile - 1) / kTile;
+  int blocks = sh.nsub * tpc;
   blocks = max(1, min(blocks, w.max_blocks));
   const double cl_w = 1.0 / n_total;  // 1.0 / correspondences_.size() (:273)
   if (c.maha_fp64) {
-    if (want_hb) launch_one<true, true>(blocks, s, src, tgt, T, c, cl_w, accumulate, w, d_out28);
-    else launch_one<true, false>(blocks, s, src, tgt, T, c, cl_w, accumulate, w, d_out28);
+    if (want_hb) launch_one<true, true>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);
+    else launch_one<true, false>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);
   } else {
-    if (want_hb) launch_one<false, true>(blocks, s, src, tgt, T, c, cl_w, accumulate, w, d_out28);
-    else launch_one<false, false>(blocks, s, src, tgt, T, c, cl_w, accumulate, w, d_out28);
+    if (want_hb) launch_one<false, true>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);
+    else launch_one<false, false>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);
   }
+  (*launches)++;
+}
+
+void launch_peer_barrier(const PeerExchange& x, cudaStream_t s, int64_t* launches) {
+  peer_barrier_kernel<<<1, 32, 0, s>>>(x);
   (*launches)++;
 }
 

@@ -1,6 +1,6 @@
 // MINIMAL STAND-IN for <pcl/point_types.h>: pcl::PointXYZINormal with PCL 1.10's
 // 48-byte layout (x,y,z,pad | normal_x,normal_y,normal_z,pad | intensity,curvature,pad,pad).
-// NOTE: real PCL stores `intensity` at byte 32; only x,y,z and normal_x matter here.
+// (intensity at byte 32, curvature at 36, as PCL_ADD_POINT4D / PCL_ADD_NORMAL4D / the {intensity, curvature} union lay it out)
 #ifndef APD_STUB_PCL_POINT_TYPES
 #define APD_STUB_PCL_POINT_TYPES
 #define PCL_VERSION_CALC(MAJ, MIN, PATCH) ((MAJ)*100000 + (MIN)*100 + (PATCH))

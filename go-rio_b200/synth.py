@@ -28,7 +28,7 @@ PCL_XYZINORMAL = np.dtype(
     {
         "names": ["x", "y", "z", "intensity", "normal_x", "normal_y", "normal_z", "curvature"],
         "formats": ["<f4"] * 8,
-        "offsets": [0, 4, 8, 12, 16, 20, 24, 32],
+        "offsets": [0, 4, 8, 32, 16, 20, 24, 36],  # PCL_ADD_POINT4D | PCL_ADD_NORMAL4D | {intensity, curvature, pad, pad}
         "itemsize": 48,
     }
 )
@@ -203,14 +203,30 @@ def radar_scan(scene, T_ws, n, seed, noise=True):
     return _dedup(cloud, rng)
 
 
+def _duplicate_rows(xyz):
+    """mask of the rows whose xyz equals that of an EARLIER row (what np.unique(axis=0, return_index=True) leaves out),
+    found through a 1-D sort of a 64-bit hash of the coordinate bits — the row-wise unique costs 30x more"""
+    bits = np.ascontiguousarray(xyz + np.float32(0.0)).view(np.uint32).astype(np.uint64)  # (+0.0: -0.0 and 0.0 are one value)
+    h = (bits[:, 0] * np.uint64(0x9E3779B97F4A7C15)) ^ (bits[:, 1] * np.uint64(0xC2B2AE3D27D4EB4F)) ^ (bits[:, 2] * np.uint64(0x165667B19E3779F9))
+    order = np.argsort(h, kind="stable")
+    same = h[order][1:] == h[order][:-1]
+    dup = np.zeros(xyz.shape[0], dtype=bool)
+    if not same.any():
+        return dup
+    # rows that share a hash with a neighbour: settle those few exactly
+    cand = np.unique(np.concatenate([order[1:][same], order[:-1][same]]))
+    _, first = np.unique(xyz[cand], axis=0, return_index=True)
+    dup[cand] = True
+    dup[cand[first]] = False
+    return dup
+
+
 def _dedup(cloud, rng):
     """No duplicate xyz (exact float ties make the kNN tie rule visible)."""
     for _ in range(8):
-        _, first = np.unique(cloud[:, :3], axis=0, return_index=True)
-        if first.size == cloud.shape[0]:
+        dup = _duplicate_rows(cloud[:, :3])
+        if not dup.any():
             return cloud
-        dup = np.ones(cloud.shape[0], dtype=bool)
-        dup[first] = False
         cloud[dup, :3] += rng.normal(0, 1e-3, (int(dup.sum()), 3)).astype(np.float32)
     return cloud
 

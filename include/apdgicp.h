@@ -127,8 +127,13 @@ APD_API int apd_get_params(const apd_handle* h, apd_params* out);
  * label_off < 0 for "all zero". For pcl::PointXYZINormal: stride 48,
  * xyz_off 0, label_off 16.
  * cache_key: the reference early-outs on pointer identity (:116,:128); pass
- * the cloud pointer value (or any id); 0 disables the early-out. Setting a
- * cloud drops its cached covariances. */
+ * the cloud pointer value (or any id); 0 disables the early-out. A key is only
+ * honoured together with the point count and a fingerprint of 64 sampled
+ * points, so a recycled address holding other points is a new cloud. A cloud
+ * set with the key (and content) the OTHER slot holds is adopted device-to-
+ * device with its grid and covariances (a source promoted to target,
+ * scan_matching_odometry_nodelet.cpp:587-588). Setting a cloud drops its
+ * cached covariances. */
 APD_API int apd_set_source(apd_handle* h, const void* pts, int32_t n, int32_t stride_bytes,
                    int32_t xyz_off, int32_t label_off, uint64_t cache_key);
 APD_API int apd_set_target(apd_handle* h, const void* pts, int32_t n, int32_t stride_bytes,
@@ -192,6 +197,19 @@ APD_API int apd_get_mahalanobis(apd_handle* h, double* maha4x4, int32_t n);
  * 1-NN squared distance is < inlier_sq_thr. */
 APD_API int apd_fitness(apd_handle* h, const float* T, double max_range, double* score,
                 int32_t* n_in_range, double inlier_sq_thr, int32_t* n_inliers);
+
+/* The search method behind pcl::Registration::getSearchMethodTarget() (PCL 1.10 registration.h: tree_, a
+ * pcl::search::KdTree the base class rebuilds over every new target in initCompute(), and that getFitnessScore() and
+ * scan_matching_odometry_nodelet.cpp:684 query one point at a time) on the GPU grid this library builds anyway:
+ * exact k nearest neighbours (1 <= k <= 32, ordered by (fp32 d2, index) like every search here) of n host query points
+ * (x,y,z floats at queries + i*stride_bytes) in the cloud `which` (0 source, 1 target). idx / sq_dist: [n*k], original
+ * point indices and fp32 squared distances; -1 / inf where the cloud has fewer than k points. */
+APD_API int apd_nearest_k(apd_handle* h, int32_t which, const void* queries, int32_t n, int32_t stride_bytes, int32_t k, int32_t* idx,
+                  float* sq_dist);
+/* The same for what those callers actually ask: the nearest target point of EVERY source point under the pose T
+ * (float[16] column-major; NULL = final_transformation_), in one pass, in the source's original order. xyz (optional,
+ * float[3n]): the transformed points. The shim's search adaptor answers the per-point queries from this batch. */
+APD_API int apd_source_nearest(apd_handle* h, const float* T, int32_t* idx, float* sq_dist, float* xyz, int32_t n);
 
 /* LM trace of the last apd_align: rows of {outer, inner, y0, yi, rho, lambda,
  * |d|, accepted} as 8 doubles, the columns of the reference's lm_debug_print_
@@ -259,10 +277,12 @@ APD_API int apd_align_batch(int device, const apd_params* p, const apd_pair* pai
  * equivalent) -------------------------------------------------------------- */
 /* One process and one handle per GPU; EVERY rank makes the same calls with the
  * same FULL source and target clouds. After apd_comm_init the handle splits the
- * work by contiguous ranges of the cell-sorted points: each rank searches the
- * full grids for its slice of the covariances (then ncclAllGather), and runs
- * update_correspondences / linearize / compute_error over its slice of the
- * source (then ncclAllReduce of 28 / 1 doubles on the handle's stream). The LM
+ * work by interleaved chunks of the cell-sorted points (nranks x 4 equal chunks
+ * of a multiple of 256 points; rank r owns chunks r, r + nranks, ...): each rank
+ * searches the full grids for its chunks of the covariances (then
+ * ncclAllGather), and runs update_correspondences / linearize / compute_error
+ * over its chunks of the source in ONE launch each (then ncclAllReduce of 28 / 1
+ * doubles on the handle's stream, or the in-kernel exchange below). The LM
  * loop runs redundantly on every rank from the identical reduced values, so all
  * ranks return the same pose; it equals the single-GPU result up to summation
  * order. cl_weight = 1 / (size of the whole source), as in the reference
@@ -284,6 +304,29 @@ APD_API int apd_comm_init(apd_handle* h, const void* id128, int32_t rank, int32_
 APD_API int apd_comm_peer_handle(apd_handle* h, void* handle64);
 APD_API int apd_comm_peer_attach(apd_handle* h, const void* handles);
 APD_API int apd_comm_destroy(apd_handle* h);
+
+/* The same sharding between handles of ONE process (a C++ caller that owns several GPUs, or several handles on one GPU):
+ * no NCCL and no IPC — the n handles (created with apd_create on any devices of one NVSwitch node, 1 <= n <= 16) become
+ * ranks 0..n-1; mailboxes and covariance arrays of the peers are plain pointers (peer access is enabled between the
+ * devices). The exchange of the H/b/err sums runs inside the reduction kernels as with apd_comm_peer_attach; the
+ * covariance chunks are pulled peer-to-peer. Every rank's calls meet inside the library, so each rank must be driven by
+ * its own host thread: either the caller's (make the same apd_* calls on every handle, one thread per handle), or the
+ * group's — the apd_group_* calls below fan one call out to all ranks and return rank 0's outputs (all ranks hold the
+ * same). *_device variants take one device pointer per rank (the cloud as float4 {x,y,z,label} on that rank's device).
+ * Destroy the group before its handles; the handles are plain unsharded handles again afterwards. */
+typedef struct apd_group apd_group;
+APD_API int apd_group_create(apd_handle* const* handles, int32_t n, apd_group** out);
+APD_API int apd_group_destroy(apd_group* g);
+APD_API int apd_group_size(const apd_group* g);
+APD_API int apd_group_set_params(apd_group* g, const apd_params* p);
+APD_API int apd_group_set_source(apd_group* g, const void* pts, int32_t n, int32_t stride_bytes, int32_t xyz_off, int32_t label_off);
+APD_API int apd_group_set_target(apd_group* g, const void* pts, int32_t n, int32_t stride_bytes, int32_t xyz_off, int32_t label_off);
+APD_API int apd_group_set_source_device(apd_group* g, const void* const* d_xyzl, int32_t n);
+APD_API int apd_group_set_target_device(apd_group* g, const void* const* d_xyzl, int32_t n);
+APD_API int apd_group_align(apd_group* g, const float* guess, float* T_out, double* T_out_f64, double* H_out, int32_t* converged,
+                    int32_t* iterations);
+APD_API int apd_group_linearize(apd_group* g, const double* T, double* H, double* b, double* err);
+APD_API int apd_group_compute_error(apd_group* g, const double* T, double* err);
 
 /* ---- instrumentation --------------------------------------------------- */
 /* CUDA stream of the handle (cudaStream_t as void*), for event timing. */

@@ -152,3 +152,106 @@ def test_sharded_registration_two_gpus(tmp_path, fused):
     assert r["H"] < 1e-11 and r["b"] < 1e-9 and r["err"] < 1e-11 and r["err2"] < 1e-11, r
     assert r["pose"] < 1e-9 and r["iters"][0] == r["iters"][1] and r["conv"][0] == r["conv"][1], r
     assert r["same_pose_on_all_ranks"] and r["cov_ok"] and r["corr_ok"], r
+
+
+# ---- the sharded arithmetic on ONE GPU: the ranks are handles of this process (apd_group_*), exchanging through the
+# same PeerMailbox code as the multi-process path (plain pointers instead of cudaIpc mappings) --------------------------
+@pytest.fixture(scope="module")
+def tiled300k(synth):
+    return synth.tiled_cloud_pair(4001, 300_000)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_sharded_group_on_one_gpu(gorio, tiled300k, nranks):
+    """2-4 ranks on device 0 against the unsharded handle: the chunk table of the one-launch kernels, the in-kernel
+    exchange of the 28 / 1 sums, the peer-to-peer all-gather of the covariance chunks, the redundant LM loop"""
+    src, tgt, T = tiled300k
+    kw = dict(max_correspondence_distance=2.0, maha_fp64=1)
+    full = gorio.FastAPDGICP(0)
+    full.set_params(**kw)
+    full.set_input_target(tgt)
+    full.set_input_source(src)
+    e_full, H_full, b_full = full.linearize(T)
+    grp = gorio.Group([0] * nranks, **kw)
+    grp.set_input_target(tgt)
+    grp.set_input_source(src)
+    e_p, H_p, b_p = grp.linearize(T)
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    assert rel(H_p, H_full) < 1e-11 and rel(b_p, b_full) < 1e-9 and abs(e_p - e_full) / e_full < 1e-11
+    c_full, _ = full.get_correspondences()
+    owned = np.zeros(src.shape[0], bool)
+    for r in grp.ranks:  # every rank holds ALL covariances (gathered) and its own chunks of the correspondences
+        assert np.array_equal(r.get_target_covariances(), full.get_target_covariances())
+        assert np.array_equal(r.get_source_covariances(), full.get_source_covariances())
+        c_r, _ = r.get_correspondences()
+        mine = c_r >= 0
+        assert np.array_equal(c_r[mine], c_full[mine]) and not (owned & mine).any()
+        owned |= mine
+    assert np.array_equal(owned, c_full >= 0)
+    assert abs(grp.compute_error(T) - full.compute_error(T)) / e_full < 1e-11
+    # a second pass (warm-started searches) and a different pose
+    T2 = T @ synth_pose()
+    e2_p, H2_p, _ = grp.linearize(T2)
+    e2_f, H2_f, _ = full.linearize(T2)
+    assert abs(e2_p - e2_f) / e2_f < 1e-11 and rel(H2_p, H2_f) < 1e-11
+    r_full, r_part = full.align(), grp.align()
+    assert np.abs(r_part["T64"] - r_full["T64"]).max() < 1e-9
+    assert r_part["iterations"] == r_full["iterations"] and r_part["converged"] == r_full["converged"]
+    traces = [r.lm_trace() for r in grp.ranks]
+    assert all(np.array_equal(t, traces[0]) for t in traces)  # identical LM decisions from bit-identical totals on every rank
+    grp.close()
+    full.close()
+
+
+def synth_pose():
+    synth = importlib.import_module("go-rio_b200.synth")
+    return synth.make_pose([0.03, -0.02, 0.01], [0.001, -0.002, 0.003])
+
+
+@pytest.mark.gpu
+def test_sharded_group_against_the_oracle(gorio, tiled300k):
+    """the sharded sums at 300 k points against the CPU oracle (H, b, err of one linearisation; bit-exact correspondences)"""
+    from oracle_binding import Oracle
+    src, tgt, T = tiled300k
+    kw = dict(max_correspondence_distance=2.0, maha_fp64=1)
+    o = Oracle(search=1)
+    o.set_params(**kw)
+    o.set_input_target(tgt)
+    o.set_input_source(src)
+    e_o, H_o, b_o = o.linearize(T)
+    c_o, _ = o.get_correspondences()
+    grp = gorio.Group([0, 0], **kw)
+    grp.set_input_target(tgt)
+    grp.set_input_source(src)
+    e_p, H_p, b_p = grp.linearize(T)
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    assert abs(e_p - e_o) / e_o < 1e-10 and rel(H_p, H_o) < 1e-10 and rel(b_p, b_o) < 1e-9
+    got = np.full(src.shape[0], -1, np.int32)
+    for r in grp.ranks:
+        c_r, _ = r.get_correspondences()
+        got[c_r >= 0] = c_r[c_r >= 0]
+    assert np.array_equal(got, c_o)
+    grp.close()
+
+
+@pytest.mark.gpu
+def test_group_small_clouds_and_odd_sizes(gorio, synth):
+    """chunks shorter than a tile, empty chunks (n < ranks x 4 x 256) and a rank count that does not divide anything"""
+    for case, nranks in ((0, 2), (1, 3), (2, 4)):
+        src, tgt, T = (synth.scan_pair(1001, 1000), synth.scan_pair(1002, 777), synth.submap_pair(2001, n_source=5000))[case]
+        kw = dict(max_correspondence_distance=2.0, maha_fp64=1, host_loop=1)
+        full = gorio.FastAPDGICP(0)
+        full.set_params(**kw)
+        full.set_input_target(tgt)
+        full.set_input_source(src)
+        grp = gorio.Group([0] * nranks, **kw)
+        grp.set_input_target(tgt)
+        grp.set_input_source(src)
+        e_f, H_f, b_f = full.linearize(np.eye(4))
+        e_p, H_p, b_p = grp.linearize(np.eye(4))
+        assert abs(e_p - e_f) / e_f < 1e-11 and np.abs(H_p - H_f).max() / np.abs(H_f).max() < 1e-11
+        r_f, r_p = full.align(), grp.align()
+        assert np.abs(r_p["T64"] - r_f["T64"]).max() < 1e-9 and r_p["iterations"] == r_f["iterations"]
+        grp.close()
+        full.close()
