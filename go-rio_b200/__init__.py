@@ -46,7 +46,7 @@ def FastAPDGICP(device=0):
     return Registration(load(), "apd_", device)
 
 
-def _pair_array(pairs, keep):
+def _pair_array(pairs, keep, raw=False):
     import numpy as np
 
     n = len(pairs)
@@ -55,6 +55,10 @@ def _pair_array(pairs, keep):
         if isinstance(s, tuple):  # (device pointer, count): cloud already on the GPU as float4 {x,y,z,label}
             arr[i].source, arr[i].n_source = s
             arr[i].target, arr[i].n_target = t
+        elif raw:  # structured AoS (e.g. the 48-byte pcl::PointXYZINormal): passed as it lies
+            keep += [s, t]
+            arr[i].source, arr[i].n_source = s.ctypes.data, s.shape[0]
+            arr[i].target, arr[i].n_target = t.ctypes.data, t.shape[0]
         else:
             s = np.ascontiguousarray(s, dtype=np.float32)
             t = np.ascontiguousarray(t, dtype=np.float32)
@@ -83,10 +87,14 @@ class Batch:
     """apd_batch_*: a persistent pool of `n_workers` handles / streams / host threads for independent pairs."""
 
     def __init__(self, device=0, n_workers=8, params=None, **kw):
+        """device: one device index, or a list of them (apd_batch_create_multi: n_workers registrations in flight per
+        device, one shared queue of pairs)"""
         self._lib = load()
         self._b = ctypes.c_void_p()
-        self._lib.apd_batch_create.restype = ctypes.c_int
-        rc = self._lib.apd_batch_create(ctypes.c_int(device), ctypes.c_int32(n_workers), ctypes.byref(self._b))
+        self.devices = list(device) if isinstance(device, (list, tuple)) else [device]
+        arr = (ctypes.c_int32 * len(self.devices))(*self.devices)
+        self._lib.apd_batch_create_multi.restype = ctypes.c_int
+        rc = self._lib.apd_batch_create_multi(arr, ctypes.c_int32(len(self.devices)), ctypes.c_int32(n_workers), ctypes.byref(self._b))
         if rc != 0:
             raise ApdError(rc, "apd_batch_create")
         if params is None:
@@ -98,13 +106,20 @@ class Batch:
         if rc != 0:
             raise ApdError(rc, "apd_batch_set_params")
 
-    def prepare(self, pairs):
+    def prepare(self, pairs, layout=(16, 0, 12)):
         """list of (source, target, guess) -> a reusable C array; source/target are [n,4] f32 arrays
-        (host clouds) or (device_ptr, n) tuples (clouds resident in HBM)."""
+        (host clouds), structured PCL arrays with layout=(stride, xyz_off, label_off), or (device_ptr, n) tuples
+        (clouds resident in HBM)."""
         keep = []
-        arr = _pair_array(pairs, keep)
+        structured = len(pairs) > 0 and not isinstance(pairs[0][0], tuple) and pairs[0][0].dtype.names is not None
+        arr = _pair_array(pairs, keep, raw=structured)
         device = len(pairs) > 0 and isinstance(pairs[0][0], tuple)
-        return dict(arr=arr, keep=keep, n=len(pairs), device=device, res=(ApdResult * len(pairs))())
+        return dict(arr=arr, keep=keep, n=len(pairs), device=device, res=(ApdResult * len(pairs))(), layout=layout)
+
+    def device_pairs(self):
+        out = (ctypes.c_int64 * len(self.devices))()
+        self._lib.apd_batch_device_pairs(self._b, out, ctypes.c_int32(len(self.devices)))
+        return list(out)
 
     def align(self, prepared, with_fitness=True, parse=True):
         if not isinstance(prepared, dict):
@@ -114,7 +129,8 @@ class Batch:
         if prepared["device"]:
             rc = self._lib.apd_batch_align_device(self._b, arr, ctypes.c_int32(n), wf, res)
         else:
-            rc = self._lib.apd_batch_align(self._b, arr, ctypes.c_int32(n), ctypes.c_int32(16), ctypes.c_int32(0), ctypes.c_int32(12), wf, res)
+            stride, xo, lo = prepared.get("layout", (16, 0, 12))
+            rc = self._lib.apd_batch_align(self._b, arr, ctypes.c_int32(n), ctypes.c_int32(stride), ctypes.c_int32(xo), ctypes.c_int32(lo), wf, res)
         if rc != 0:
             raise ApdError(rc, "apd_batch_align")
         return _results(res) if parse else res

@@ -81,7 +81,8 @@ PRODUCT_SYMBOLS = CORE_SYMBOLS + [
     "batch_get_kernel_ms", "comm_unique_id",
     "comm_init", "comm_peer_handle", "comm_peer_attach", "comm_destroy", "group_create", "group_destroy", "group_size",
     "group_set_params", "group_set_source", "group_set_target", "group_set_source_device", "group_set_target_device", "group_align",
-    "group_linearize", "group_compute_error", "stream", "launch_count", "set_profiling", "get_kernel_ms",
+    "group_linearize", "group_compute_error", "nearest_k", "source_nearest", "batch_create_multi", "batch_device_pairs",
+    "align_batch_multi", "stream", "launch_count", "set_profiling", "get_kernel_ms",
 ]
 
 
@@ -285,6 +286,27 @@ class Registration:
         self._call("fitness", t.ctypes.data_as(C.c_void_p) if t is not None else None, C.c_double(max_range),
                    C.byref(score), C.byref(nr), C.c_double(inlier_sq_thr), C.byref(ni))
         return score.value, nr.value, ni.value
+
+    def nearest_k(self, queries, k, which=1):
+        """exact k nearest neighbours of arbitrary query points [n,3+] in the target (which=1) or source (0) cloud:
+        (indices [n,k] int32, squared distances [n,k] float32), ascending by (d2, index)"""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        n = q.shape[0]
+        idx = np.empty((n, k), np.int32)
+        d2 = np.empty((n, k), np.float32)
+        self._call("nearest_k", C.c_int32(which), q.ctypes.data_as(C.c_void_p), C.c_int32(n), C.c_int32(q.shape[1] * 4), C.c_int32(k),
+                   idx.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p))
+        return idx, d2
+
+    def source_nearest(self, T=None):
+        """nearest target point of every source point under pose T (None: the final transformation):
+        (index [n], squared distance [n], transformed xyz [n,3])"""
+        t = None if T is None else _colmajor(T, np.float32)
+        n = self.n_source
+        idx, d2, xyz = np.empty(n, np.int32), np.empty(n, np.float32), np.empty((n, 3), np.float32)
+        self._call("source_nearest", t.ctypes.data_as(C.c_void_p) if t is not None else None, idx.ctypes.data_as(C.c_void_p),
+                   d2.ctypes.data_as(C.c_void_p), xyz.ctypes.data_as(C.c_void_p), C.c_int32(n))
+        return idx, d2, xyz
 
     def lm_trace(self, max_rows=1024):
         rows = np.zeros((max_rows, 8), np.float64)

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -487,6 +488,7 @@ PoseF colmajor_f32_to_pose_f(const float* T) {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int ensure_small(apd_handle* h);
+void ensure_work_queues();
 NoiseParams noise_params(const apd_params& p);
 int ensure_corr_buffers(apd_handle* h);
 
@@ -1326,11 +1328,48 @@ int do_fitness(apd_handle* h, const float* T, double max_range, double* score, i
 
 }  // namespace
 
+namespace {
+
 // A batch pool drives one CUDA stream per worker (32-64). With the driver's default of 8 hardware work queues the
 // streams share queues, and a short kernel of one worker waits behind the 1 ms optimizer kernel of another (measured on
-// B200, C2, 32 workers: 6.3 k registrations/s with 8 queues, 15.1 k with 32). The variable is read when the CUDA context
-// is created, so it is set when the library is loaded; a value the user exported wins.
-__attribute__((constructor)) static void apd_default_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+// B200, C2, 32 workers: 6.3 k registrations/s with 8 queues, 15.1 k with 32). CUDA_DEVICE_MAX_CONNECTIONS is read when the
+// CUDA context is created and belongs to the whole host process (a nodelet manager has other CUDA users), so the library
+// does not touch it at load time (round 1 did): the first pool / group asks for 32 queues only if the variable is unset
+// AND no primary context is active yet on its device, and says so once when it is too late for that.
+void ensure_work_queues() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (std::getenv("CUDA_DEVICE_MAX_CONNECTIONS")) return;
+    bool active = true;  // unknown -> assume the context exists
+    if (void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_NOLOAD)) {
+      typedef int (*StateFn)(int, unsigned int*, int*);
+      typedef int (*InitFn)(unsigned int);
+      StateFn state = (StateFn)dlsym(cu, "cuDevicePrimaryCtxGetState");
+      InitFn init = (InitFn)dlsym(cu, "cuInit");
+      unsigned int flags = 0;
+      int act = 1;
+      if (state && init && init(0) == 0) {
+        active = false;
+        int count = 0;
+        typedef int (*CountFn)(int*);
+        CountFn cnt = (CountFn)dlsym(cu, "cuDeviceGetCount");
+        if (cnt) cnt(&count);
+        for (int d = 0; d < count; d++)
+          if (state(d, &flags, &act) == 0 && act) active = true;
+      }
+    } else {
+      active = false;  // the driver library is not even loaded: no context can exist
+    }
+    if (!active) {
+      setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    } else {
+      std::fprintf(stderr, "[apdgicp] note: the CUDA context already exists and CUDA_DEVICE_MAX_CONNECTIONS is unset: the batch pool's streams "
+                           "share the default 8 hardware queues (export CUDA_DEVICE_MAX_CONNECTIONS=32 before the process starts for full throughput)\n");
+    }
+  });
+}
+
+}  // namespace
 
 // =============================================================== C-ABI =====
 extern "C" {
@@ -1663,10 +1702,13 @@ int apd_get_lm_trace(apd_handle* h, double* rows, int32_t max_rows, int32_t* n_r
 // enqueues grid build + covariances + the device-resident optimizer loop (+ the fitness pass) and waits for
 // the one result copy; the other workers' kernels and copies fill the GPU meanwhile.
 struct apd_batch {
-  int device = 0;
-  std::vector<apd_handle*> handles;
+  int device = 0;                // the first device
+  std::vector<int> devices;      // one pool of workers per device; ALL of them take pairs from the one counter `next`
+  std::vector<apd_handle*> handles;  // device d owns handles [d * per_device, (d + 1) * per_device)
+  int per_device = 0;
   std::vector<std::thread> threads;
-  int n_threads = 0;
+  int n_threads = 0;             // host threads per device
+  std::vector<int64_t> pairs_by_device;  // how many pairs of the last call each device took (apd_batch_device_pairs)
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
   uint64_t generation = 0;
@@ -1792,13 +1834,16 @@ bool slot_stalled(PoolSlot& sl, bool arrived_now) {
 }
 
 void batch_worker(apd_batch* b, int wi) {
-  cudaSetDevice(b->device);
+  // thread wi serves device wi / n_threads: every n_threads-th handle of that device
+  const int di = wi / b->n_threads, ti = wi % b->n_threads;
+  cudaSetDevice(b->devices[(size_t)di]);
   std::vector<PoolSlot> slots;
-  for (size_t s = (size_t)wi; s < b->handles.size(); s += (size_t)b->n_threads) {
+  for (int s = ti; s < b->per_device; s += b->n_threads) {
     PoolSlot sl;
-    sl.h = b->handles[s];
+    sl.h = b->handles[(size_t)di * b->per_device + s];
     slots.push_back(sl);
   }
+  int64_t taken = 0;
   const int nap_us = std::max(1, slots[0].h->poll_wait_us);
   uint64_t seen = 0;
   for (;;) {
@@ -1816,11 +1861,12 @@ void batch_worker(apd_batch* b, int wi) {
         apd_handle* h = sl.h;
         switch (sl.state) {
           case kSlotIdle: {
-            const int i = b->next.fetch_add(1);
+            const int i = b->next.fetch_add(1);  // ONE queue for all devices: whoever is free takes the next pair
             if (i >= b->n_pairs) {
               sl.state = kSlotDone;
             } else {
               slot_begin(b, sl, i);
+              taken++;
               progressed = true;
             }
             break;
@@ -1856,6 +1902,8 @@ void batch_worker(apd_batch* b, int wi) {
     }
     {
       std::lock_guard<std::mutex> lk(b->mu);
+      b->pairs_by_device[(size_t)di] += taken;
+      taken = 0;
       if (--b->pending == 0) b->cv_done.notify_all();
     }
   }
@@ -1865,8 +1913,10 @@ int batch_run(apd_batch* b, const apd_pair* pairs, int32_t n_pairs, int32_t stri
               int32_t with_fitness, apd_result* results) {
   if (!b || !pairs || !results || n_pairs < 0) return APD_ERR_INVALID;
   if (n_pairs == 0) return APD_OK;
+  if (device_clouds && b->devices.size() > 1) return APD_ERR_UNSUPPORTED;  // (a device pointer names ONE device's memory)
   {
     std::lock_guard<std::mutex> lk(b->mu);
+    std::fill(b->pairs_by_device.begin(), b->pairs_by_device.end(), 0);
     b->pairs = pairs;
     b->results = results;
     b->n_pairs = n_pairs;
@@ -1889,35 +1939,41 @@ int batch_run(apd_batch* b, const apd_pair* pairs, int32_t n_pairs, int32_t stri
 
 extern "C" {
 
-int apd_batch_create(int device, int32_t n_workers, apd_batch** out) {
-  if (!out) return APD_ERR_INVALID;
+int apd_batch_create_multi(const int32_t* devices, int32_t n_devices, int32_t n_workers, apd_batch** out) {
+  if (!out || !devices || n_devices < 1 || n_devices > 64) return APD_ERR_INVALID;
   *out = nullptr;
   if (n_workers < 1) n_workers = 1;
   if (n_workers > 128) n_workers = 128;
+  ensure_work_queues();
   apd_batch* b = new apd_batch();
-  b->device = device;
-  for (int s = 0; s < n_workers; s++) {
-    apd_handle* h = nullptr;
-    const int rc = apd_create(device, &h);
-    if (rc != APD_OK) {
-      for (auto* hh : b->handles) apd_destroy(hh);
-      delete b;
-      return rc;
+  b->device = devices[0];
+  b->devices.assign(devices, devices + n_devices);
+  b->per_device = n_workers;
+  b->pairs_by_device.assign((size_t)n_devices, 0);
+  for (int d = 0; d < n_devices; d++)
+    for (int s = 0; s < n_workers; s++) {
+      apd_handle* h = nullptr;
+      const int rc = apd_create(devices[d], &h);
+      if (rc != APD_OK) {
+        for (auto* hh : b->handles) apd_destroy(hh);
+        delete b;
+        return rc;
+      }
+      // a pool this large keeps the GPU busy by itself: its waiting threads sleep instead of spinning, so that several
+      // ranks' pools can share the host cores (see wait_stream)
+      h->pooled = true;
+      if (!std::getenv("APD_LM_CLUSTER")) h->lm_cluster = 4;
+      if (!std::getenv("APD_LM_MINB")) h->lm_min_blocks = 2;
+      if (!std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = n_workers > 8;
+      if (!std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = 50;  // (a look at pinned host memory: cheap)
+      b->handles.push_back(h);
     }
-    // a pool this large keeps the GPU busy by itself: its waiting threads sleep instead of spinning, so that several
-    // ranks' pools can share the host cores (see wait_stream)
-    h->pooled = true;
-    if (!std::getenv("APD_LM_CLUSTER")) h->lm_cluster = 4;
-    if (!std::getenv("APD_LM_MINB")) h->lm_min_blocks = 2;
-    if (!std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = n_workers > 8;
-    if (!std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = 50;  // (a look at pinned host memory: cheap)
-    b->handles.push_back(h);
-  }
-  // Host threads: each drives n_workers / n_threads registrations at a time. Default: the host cores this process may
-  // use divided by the ranks sharing the node (one process per GPU: LOCAL_WORLD_SIZE as torchrun exports it, else the
-  // number of visible GPUs), between 2 and 8. More threads than cores is what to avoid: a thread that holds the CUDA
-  // driver's lock and loses its core stalls every other thread of the process (8 x B200 on 32 cores, 8 threads per
-  // rank: host CPU per registration 0.08 -> 0.29 ms device-resident, 0.18 -> 0.63 ms end to end). APD_BATCH_THREADS overrides.
+  // Host threads per device: each drives n_workers / n_threads registrations at a time. Default: the host cores this
+  // process may use divided by the GPUs sharing them (the devices of this context x the ranks on the node — one process
+  // per GPU: LOCAL_WORLD_SIZE as torchrun exports it), between 2 and 8. More threads than cores is what to avoid: a
+  // thread that holds the CUDA driver's lock and loses its core stalls every other thread of the process (8 x B200 on 32
+  // cores, 8 threads per rank: host CPU per registration 0.08 -> 0.29 ms device-resident, 0.18 -> 0.63 ms end to end).
+  // APD_BATCH_THREADS overrides.
   int n_threads = 8;
   {
     int cores = (int)std::thread::hardware_concurrency();
@@ -1925,14 +1981,26 @@ int apd_batch_create(int device, int32_t n_workers, apd_batch** out) {
     if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
     int ranks = 0;
     if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::atoi(e);
-    if (ranks < 1 && cudaGetDeviceCount(&ranks) != cudaSuccess) ranks = 1;
+    if (ranks < 1) ranks = 1;
+    ranks *= n_devices;
     if (cores > 0 && ranks > 0) n_threads = std::max(2, std::min(8, cores / ranks));
   }
   if (const char* e = std::getenv("APD_BATCH_THREADS")) n_threads = std::atoi(e);
   n_threads = std::max(1, std::min(n_threads, n_workers));
   b->n_threads = n_threads;
-  for (int s = 0; s < n_threads; s++) b->threads.emplace_back(batch_worker, b, s);
+  for (int s = 0; s < n_threads * n_devices; s++) b->threads.emplace_back(batch_worker, b, s);
   *out = b;
+  return APD_OK;
+}
+
+int apd_batch_create(int device, int32_t n_workers, apd_batch** out) {
+  const int32_t dev = device;
+  return apd_batch_create_multi(&dev, 1, n_workers, out);
+}
+
+int apd_batch_device_pairs(const apd_batch* b, int64_t* pairs, int32_t n_devices) {
+  if (!b || !pairs || n_devices != (int32_t)b->devices.size()) return APD_ERR_INVALID;
+  for (int d = 0; d < n_devices; d++) pairs[d] = b->pairs_by_device[(size_t)d];
   return APD_OK;
 }
 
@@ -2014,11 +2082,17 @@ int apd_batch_get_kernel_ms(apd_batch* b, double* ms, int64_t* launches) {
 
 int apd_align_batch(int device, const apd_params* p, const apd_pair* pairs, int32_t n_pairs, int32_t stride, int32_t xyz_off,
                     int32_t label_off, int32_t n_streams, int32_t with_fitness, apd_result* results) {
-  if (!pairs || !results || n_pairs < 0) return APD_ERR_INVALID;
+  const int32_t dev = device;
+  return apd_align_batch_multi(&dev, 1, p, pairs, n_pairs, stride, xyz_off, label_off, n_streams, with_fitness, results);
+}
+
+int apd_align_batch_multi(const int32_t* devices, int32_t n_devices, const apd_params* p, const apd_pair* pairs, int32_t n_pairs, int32_t stride,
+                          int32_t xyz_off, int32_t label_off, int32_t n_streams, int32_t with_fitness, apd_result* results) {
+  if (!pairs || !results || n_pairs < 0 || !devices || n_devices < 1) return APD_ERR_INVALID;
   if (n_streams < 1) n_streams = 1;
   if (n_streams > n_pairs) n_streams = std::max(1, n_pairs);
   apd_batch* b = nullptr;
-  int rc = apd_batch_create(device, n_streams, &b);
+  int rc = apd_batch_create_multi(devices, n_devices, n_streams, &b);
   if (rc != APD_OK) return rc;
   if (p) rc = apd_batch_set_params(b, p);
   if (rc == APD_OK) rc = apd_batch_align(b, pairs, n_pairs, stride, xyz_off, label_off, with_fitness, results);
@@ -2188,6 +2262,7 @@ int apd_group_create(apd_handle* const* handles, int32_t n, apd_group** out) {
   *out = nullptr;
   for (int r = 0; r < n; r++)
     if (!handles[r] || handles[r]->sharded()) return APD_ERR_INVALID;
+  ensure_work_queues();
   apd_group* g = new apd_group();
   g->ranks.assign(handles, handles + n);
   g->job_rc.assign((size_t)n, APD_OK);

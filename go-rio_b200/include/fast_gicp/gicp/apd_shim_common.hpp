@@ -2,8 +2,10 @@
 #ifndef FAST_GICP_APD_SHIM_COMMON_HPP
 #define FAST_GICP_APD_SHIM_COMMON_HPP
 
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <type_traits>

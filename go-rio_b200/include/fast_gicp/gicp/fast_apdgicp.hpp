@@ -9,21 +9,30 @@
 // header unchanged. Differences a maintainer should know:
 //  - setNumThreads() is accepted and ignored (the work runs on the GPU);
 //    setDevice() picks the GPU (default 0).
-//  - getFitnessScore() is a NON-virtual member of pcl::Registration, so a call
-//    through the base pointer still runs PCL's CPU kd-tree version. Call
-//    getFitnessScoreGPU() (or apd_fitness) to get the same number from the GPU.
+//  - getFitnessScore() is a NON-virtual member of pcl::Registration; through the
+//    base pointer it runs PCL's loop over tree_->nearestKSearch. The shim installs
+//    its own search method there (apd_search.hpp: the GPU grid behind the
+//    pcl::search::KdTree interface, force_no_recompute), so that loop — and
+//    getSearchMethodTarget()->nearestKSearch — is answered from one GPU pass and
+//    align() builds no CPU kd-tree per target. getFitnessScoreGPU() gives the same
+//    number (and the inlier count) in one call.
 //  - The protected members source_kdtree_/target_kdtree_ do not exist: the
 //    neighbour search is the GPU grid.
+//  - setInputSource / setInputTarget pass the cloud's address as the cache key of
+//    the C-ABI (the shim holds the shared_ptr, so the address stays valid): a source
+//    promoted to target (scan_matching_odometry_nodelet.cpp:587-588) keeps its grid
+//    and covariances on the device instead of rebuilding them.
 #ifndef FAST_GICP_FAST_IGICP_HPP
 #define FAST_GICP_FAST_IGICP_HPP
 
 #include <fast_gicp/gicp/gicp_settings.hpp>
 #include <fast_gicp/gicp/lsq_registration.hpp>
+#include <fast_gicp/gicp/apd_search.hpp>
 
 namespace fast_gicp {
 
 template <typename PointSource, typename PointTarget>
-class FastAPDGICP : public LsqRegistration<PointSource, PointTarget> {
+class FastAPDGICP : public LsqRegistration<PointSource, PointTarget>, private ApdSearchOwner<PointTarget> {
 public:
   APD_SHIM_REGISTRATION_ALIASES(FastAPDGICP, PointSource, PointTarget);
   using CovarianceVector = std::vector<Eigen::Matrix4d, Eigen::aligned_allocator<Eigen::Matrix4d>>;
@@ -32,6 +41,9 @@ public:
     this->reg_name_ = "FastAPDGICP";
     this->corr_dist_threshold_ = std::numeric_limits<float>::max();
     open(0);
+    // the base class's target search method: the GPU grid instead of a CPU kd-tree rebuilt per target (apd_search.hpp)
+    search_.reset(new ApdTargetSearch<PointTarget>(this));
+    this->setSearchMethodTarget(search_, /*force_no_recompute=*/true);
   }
   virtual ~FastAPDGICP() override {
     if (handle_) apd_destroy(handle_);
@@ -54,18 +66,21 @@ public:
 
   // ---- cloud management (:89-135) ----
   virtual void swapSourceAndTarget() override {
+    generation_++;
     input_.swap(target_);
     std::swap(source_covs_valid_, target_covs_valid_);
     source_covs_.swap(target_covs_);
     if (handle_) apd_detail::check(handle_, apd_swap_source_and_target(handle_), "swapSourceAndTarget");
   }
   virtual void clearSource() override {
+    generation_++;
     input_.reset();
     source_covs_.clear();
     source_covs_valid_ = false;
     if (handle_) apd_clear_source(handle_);
   }
   virtual void clearTarget() override {
+    generation_++;
     target_.reset();
     target_covs_.clear();
     target_covs_valid_ = false;
@@ -73,6 +88,7 @@ public:
   }
   virtual void setInputSource(const PointCloudSourceConstPtr& cloud) override {
     if (input_ == cloud) return;
+    generation_++;
     PclBase::setInputSource(cloud);
     source_covs_.clear();
     source_covs_valid_ = false;
@@ -80,6 +96,7 @@ public:
   }
   virtual void setInputTarget(const PointCloudTargetConstPtr& cloud) override {
     if (target_ == cloud) return;
+    generation_++;
     PclBase::setInputTarget(cloud);
     target_covs_.clear();
     target_covs_valid_ = false;
@@ -97,14 +114,14 @@ public:
   }
   // The covariances live on the device; they are downloaded on first request.
   const CovarianceVector& getSourceCovariances() const {
-    if (!source_covs_valid_ && handle_ && input_) {
+    if (!source_covs_valid_ && handle_ && input_ && input_->size() > 0) {
       source_covs_.resize(input_->size());
       if (apd_get_source_covariances(handle_, source_covs_[0].data(), (int32_t)source_covs_.size()) == APD_OK) source_covs_valid_ = true;
     }
     return source_covs_;
   }
   const CovarianceVector& getTargetCovariances() const {
-    if (!target_covs_valid_ && handle_ && target_) {
+    if (!target_covs_valid_ && handle_ && target_ && target_->size() > 0) {
       target_covs_.resize(target_->size());
       if (apd_get_target_covariances(handle_, target_covs_[0].data(), (int32_t)target_covs_.size()) == APD_OK) target_covs_valid_ = true;
     }
@@ -122,6 +139,8 @@ public:
     return score;
   }
   apd_handle* handle() { return handle_; }
+  // the search method installed in the base class (instrumentation: how its queries were answered)
+  const ApdTargetSearch<PointTarget>& targetSearch() const { return *search_; }
 
 protected:
   using PclBase::converged_;
@@ -143,17 +162,21 @@ protected:
   // pcl::Registration::align() -> here (:148-157 + lsq_registration_impl.hpp:55-80)
   virtual void computeTransformation(PointCloudSource& output, const Matrix4& guess) override {
     converged_ = false;
+    generation_++;
     if (!handle_ || !input_ || !target_) return;
     push_params();
     Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
     int32_t conv = 0, iters = 0;
-    std::vector<float> xyz(output.size() == input_->size() ? 3 * input_->size() : 0);
+    // (pcl::Registration::align() hands over `output` as a copy of the input; a direct caller may not have)
+    if (output.size() != input_->size()) output.points = input_->points;
+    std::vector<float> xyz(3 * input_->size());
     const int rc = apd_align(handle_, guess.data(), T.data(), nullptr, final_hessian_.data(), &conv, &iters, xyz.empty() ? nullptr : xyz.data());
     apd_detail::check(handle_, rc, "align");
     if (rc != APD_OK) return;
     final_transformation_ = T;
     converged_ = conv != 0;
     nr_iterations_ = iters;
+    generation_++;  // (final_transformation_ changed)
     source_covs_valid_ = source_covs_valid_ && !source_covs_.empty();
     // pcl::transformPointCloud(*input_, output, final_transformation_): align() already copied the
     // input's fields into `output`; only x, y, z change, and the GPU has just computed them.
@@ -202,8 +225,11 @@ private:
     using P = typename CloudT::PointType;
     const void* data = cloud->points.empty() ? static_cast<const void*>(cloud) : static_cast<const void*>(cloud->points.data());
     const int32_t n = (int32_t)cloud->points.size();
-    const int rc = source ? apd_set_source(handle_, data, n, (int32_t)sizeof(P), apd_detail::xyz_offset<P>(), apd_detail::LabelOffset<P>::value(), 0)
-                          : apd_set_target(handle_, data, n, (int32_t)sizeof(P), apd_detail::xyz_offset<P>(), apd_detail::LabelOffset<P>::value(), 0);
+    // cache key = the cloud's address: input_ / target_ keep the cloud alive while the key is in use, so identity is as
+    // good as the reference's shared_ptr comparison (:116,:128); the library also fingerprints the content
+    const uint64_t key = (uint64_t)reinterpret_cast<std::uintptr_t>(cloud);
+    const int rc = source ? apd_set_source(handle_, data, n, (int32_t)sizeof(P), apd_detail::xyz_offset<P>(), apd_detail::LabelOffset<P>::value(), key)
+                          : apd_set_target(handle_, data, n, (int32_t)sizeof(P), apd_detail::xyz_offset<P>(), apd_detail::LabelOffset<P>::value(), key);
     apd_detail::check(handle_, rc, source ? "setInputSource" : "setInputTarget");
   }
   void push_params() {
@@ -239,9 +265,20 @@ protected:
   int variant_ = APD_VARIANT_APDGICP;  // fast_gicp.hpp's FastGICP sets APD_VARIANT_GICP
 
 private:
+  // ApdSearchOwner: what the installed search method asks of this object
+  apd_handle* apdSearchHandle() const override { return (input_ && target_) ? handle_ : nullptr; }
+  unsigned long long apdSearchGeneration() const override { return generation_; }
+  std::size_t apdSearchSourceSize() const override { return input_ ? input_->size() : 0; }
+  const PointTarget* apdSearchTargetPoints(std::size_t* n) const override {
+    *n = target_ ? target_->size() : 0;
+    return *n ? target_->points.data() : nullptr;
+  }
+
   apd_handle* handle_ = nullptr;
   int device_ = 0;
   bool maha_fp64_ = false;
+  unsigned long long generation_ = 0;  // bumps whenever a cloud or final_transformation_ changes (the search batch's validity)
+  typename ApdTargetSearch<PointTarget>::Ptr search_;
 };
 
 }  // namespace fast_gicp

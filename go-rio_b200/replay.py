@@ -60,18 +60,22 @@ class ScanMatchingOdometry:
         self.n_not_converged = 0
         self.n_thresholded = 0
         self.iterations = []
+        self.frame_id = 0
 
     def matching(self, cloud):
         """returns the odometry pose of this frame (:423-632)"""
+        # The cache key stands in for the reference's shared_ptr identity (fast_apdgicp_impl.hpp:116,:128): a frame promoted
+        # to keyframe below is recognised by it and its grid / covariances are reused, not rebuilt. A frame counter, not the
+        # array's address: a streamed sequence frees each frame, and the allocator hands the same address to the next one.
+        self.frame_id += 1
+        key = self.frame_id
         if self.keyframe_cloud is None:  # :424-438
             self.prev_trans = np.eye(4)
             self.keyframe_pose = np.eye(4)
             self.keyframe_cloud = cloud
-            self.reg.set_input_target(cloud, key=cloud.ctypes.data)
+            self.reg.set_input_target(cloud, key=key)
             return np.eye(4)
-        # the cloud's address is the cache key, as the shared_ptr is in the reference (fast_apdgicp_impl.hpp:116,:128): a frame
-        # promoted to keyframe below is then recognised and its grid / covariances are reused, not rebuilt
-        self.reg.set_input_source(cloud, key=cloud.ctypes.data)  # :442
+        self.reg.set_input_source(cloud, key=key)  # :442
         guess = self.prev_trans.astype(np.float32)  # :461 (use_ego_vel = false, msf_delta = I)
         r = self.reg.align(guess)  # :465
         self.iterations.append(r["iterations"])
@@ -94,7 +98,7 @@ class ScanMatchingOdometry:
             self.prev_trans = trans
         if self.updater.decide(odom):  # :583-600
             self.keyframe_cloud = cloud
-            self.reg.set_input_target(cloud, key=cloud.ctypes.data)
+            self.reg.set_input_target(cloud, key=key)
             self.keyframe_pose = odom
             self.prev_trans = np.eye(4)
             self.n_keyframes += 1

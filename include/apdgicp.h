@@ -241,9 +241,12 @@ typedef struct apd_result {
  * state machines, that persist across calls, so device buffers, pinned staging
  * and streams are allocated once. 64 nearly saturate a B200 on scan-to-submap pairs
  * (96: +3.5 %).
- * (Streams only run concurrently if each has a hardware work queue: the library
- * sets CUDA_DEVICE_MAX_CONNECTIONS=32 when it is loaded unless the variable is
- * already set — it must be loaded before the process creates its CUDA context.) apd_batch_align runs n_pairs independent
+ * (Streams only run concurrently if each has a hardware work queue, and the
+ * driver reads CUDA_DEVICE_MAX_CONNECTIONS (default 8) when the CUDA context is
+ * created: export CUDA_DEVICE_MAX_CONNECTIONS=32 for the process. The library
+ * never changes the environment when it is loaded; the first apd_batch_create
+ * sets the variable only if it is unset and no CUDA context exists yet, and
+ * prints a note when it is too late.) apd_batch_align runs n_pairs independent
  * {clearTarget; clearSource; setInputTarget; setInputSource; align
  * [; getFitnessScore]} sequences over them: the staging and H2D copy of one
  * pair overlap the kernels of the others. Packed float4 {x,y,z,label} clouds
@@ -256,6 +259,13 @@ typedef struct apd_result {
  * context. */
 typedef struct apd_batch apd_batch;
 APD_API int apd_batch_create(int device, int32_t n_workers, apd_batch** out);
+/* The same over several GPUs of the node from ONE process (apd_align_batch(..., n_devices)): n_workers
+ * registrations in flight on EACH of the devices, and ONE shared queue of pairs — a worker of any device takes the next
+ * pair when it is free, so pairs that need 3 and pairs that need 30 iterations (loop-closure candidates differ that much)
+ * even out by themselves; a static pair -> device split cannot do that. Host clouds only (apd_batch_align); results
+ * do not depend on which device took a pair. apd_batch_device_pairs: how many pairs of the last call each device took. */
+APD_API int apd_batch_create_multi(const int32_t* devices, int32_t n_devices, int32_t n_workers, apd_batch** out);
+APD_API int apd_batch_device_pairs(const apd_batch* b, int64_t* pairs, int32_t n_devices);
 APD_API int apd_batch_destroy(apd_batch* b);
 APD_API int apd_batch_set_params(apd_batch* b, const apd_params* p);
 APD_API int apd_batch_align(apd_batch* b, const apd_pair* pairs, int32_t n_pairs, int32_t stride_bytes,
@@ -268,7 +278,10 @@ APD_API int64_t apd_batch_launch_count(const apd_batch* b);
 APD_API int apd_batch_set_profiling(apd_batch* b, int32_t enabled);
 APD_API int apd_batch_get_kernel_ms(apd_batch* b, double* ms /* [APD_K_COUNT] */, int64_t* launches);
 
-/* One-shot convenience: create a context of n_streams workers, run, destroy. */
+/* One-shot convenience: create a context of n_streams workers (per device), run, destroy. */
+APD_API int apd_align_batch_multi(const int32_t* devices, int32_t n_devices, const apd_params* p, const apd_pair* pairs, int32_t n_pairs,
+                          int32_t stride_bytes, int32_t xyz_off, int32_t label_off, int32_t n_streams, int32_t with_fitness,
+                          apd_result* results);
 APD_API int apd_align_batch(int device, const apd_params* p, const apd_pair* pairs, int32_t n_pairs,
                     int32_t stride_bytes, int32_t xyz_off, int32_t label_off,
                     int32_t n_streams, int32_t with_fitness, apd_result* results);

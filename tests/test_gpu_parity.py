@@ -549,10 +549,19 @@ def test_clear_and_cache_key(gorio, c1):
     src, tgt, _ = c1
     g, o = make(gorio, src, tgt, **DEPLOYED, maha_fp64=1)
     g.set_input_target(tgt, key=42)
+    g.align()
     l0 = g.launch_count()
-    g.set_input_target(tgt[:500], key=42)  # same key: early-out (:128), cloud unchanged
+    g.set_input_target(tgt.copy(), key=42)  # same key, same content: early-out (:128), nothing is rebuilt
     assert g.launch_count() == l0
-    g.n_target = tgt.shape[0]
+    _check_align(g, o)
+    # a stale key: the same number now names other points — it must not keep the old cloud
+    t2 = tgt[::-1].copy()[: tgt.shape[0] - 7]
+    g.set_input_target(t2, key=42); o.set_input_target(t2)
+    _check_align(g, o)
+    t3 = t2.copy(); t3[:, 0] += 0.25  # same size, same address pattern, other content
+    g.set_input_target(t3, key=42); o.set_input_target(t3)
+    _check_align(g, o)
+    g.set_input_target(tgt, key=43); o.set_input_target(tgt)
     _check_align(g, o)
     g.clear_source()
     with pytest.raises(gorio.ApdError) as e:
@@ -560,6 +569,24 @@ def test_clear_and_cache_key(gorio, c1):
     assert e.value.code == 1
     g.set_input_source(src)
     _check_align(g, o)
+
+
+def test_streamed_frames_with_recycled_addresses(gorio, synth):
+    """a sequence that copies each frame and lets it go reuses host addresses; keys derived from addresses then repeat with
+    different content. The library must register the frames it was given (it silently kept the previous one)."""
+    frames = [synth.scan_pair(1100 + i, 600) for i in range(4)]
+    g = gorio.FastAPDGICP(0)
+    g.set_params(**DEPLOYED, maha_fp64=1)
+    o = Oracle(search=1)
+    o.set_params(**DEPLOYED, maha_fp64=1)
+    buf_s, buf_t = np.empty((600, 4), np.float32), np.empty((600, 4), np.float32)
+    for s, t, _ in frames:
+        n_s, n_t = s.shape[0], t.shape[0]
+        assert n_s <= 600 and n_t <= 600
+        buf_s[:n_s], buf_t[:n_t] = s, t  # the SAME host buffers every frame: address-derived keys collide by construction
+        g.set_input_target(buf_t[:n_t], key=buf_t.ctypes.data); o.set_input_target(t)
+        g.set_input_source(buf_s[:n_s], key=buf_s.ctypes.data); o.set_input_source(s)
+        _check_align(g, o)
 
 
 def test_promotion_of_the_source_to_target_reuses_its_covariances(gorio, synth, c2_small):

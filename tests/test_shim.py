@@ -29,7 +29,7 @@ def test_shim_keeps_the_reference_surface():
                  "setDistVar", "swapSourceAndTarget", "clearSource", "clearTarget", "setInputSource", "setSourceCovariances",
                  "setInputTarget", "setTargetCovariances", "getSourceCovariances", "getTargetCovariances", "computeTransformation",
                  "update_correspondences", "linearize", "compute_error", "setRotationEpsilon", "setInitialLambdaFactor",
-                 "setDebugPrint", "getFinalHessian", "evaluateCost"]:
+                 "setDebugPrint", "getFinalHessian", "evaluateCost", "setSearchMethodTarget"]:
         assert name in text, name
 
 
@@ -55,3 +55,15 @@ def test_shim_matches_the_c_abi(gorio, synth, tmp_path, variant):
     assert r["n_aligned"] == src.shape[0] and r["n_cov"] == tgt.shape[0]
     assert abs(r["cost"] - g.linearize(ra["T"].astype(np.float64), want_hb=False)) / r["cost"] < 1e-12
     assert "swapped: converged=" in out.stderr
+    # --- the base class's search method is the GPU grid (apd_search.hpp) ---
+    # pcl::Registration::align -> initCompute built no CPU kd-tree (the stub counts what real PCL would build per target)
+    assert r["tree_builds"] == 0 and r["tree_builds_end"] == 0
+    # getFitnessScore() through the base pointer (PCL's per-point loop; its own transform rounds differently in the last bit)
+    assert abs(r["fitness_pcl"] - r["fitness_gpu"]) / r["fitness_gpu"] < 1e-6
+    # the nodelet's inlier loop over the aligned cloud (scan_matching_odometry_nodelet.cpp:680-688)
+    assert r["nodelet_inliers"] == r["inliers"] == g.fitness()[2]
+    # 2 n point-at-a-time queries were served by ONE pass over the source, none by a round trip of its own
+    assert r["search_passes"] == 1 and r["search_hits"] == 2 * src.shape[0] and r["search_singles"] == 0
+    assert r["knn_equal"] == 1  # an arbitrary query, k = 5: same indices and distances as brute force
+    # --- keyframe promotion keeps grid + covariances on the device: only the new scan's kNN runs ---
+    assert r["knn_launches_first"] == 2 * r["knn_launches_promoted"] > 0 and r["promoted_same_pose"] == 1
