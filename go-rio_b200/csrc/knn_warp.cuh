@@ -57,9 +57,27 @@ struct KBest {
   int buf_n;
   bool empty;  // list holds no key yet
 };
+// list (ascending, one key per lane) <- list with key c inserted at its rank (the largest key drops out)
+__device__ __forceinline__ unsigned long long insert_keep32(unsigned long long list, unsigned long long c, int lane) {
+  const int pos = __popc(__ballot_sync(kFull, list < c));  // keys are unique, so this is c's rank
+  const unsigned long long up = shfl_up64(list, 1);
+  return lane < pos ? list : (lane == pos ? c : up);
+}
+constexpr int kInsertMax = 10;  // a flush of up to this many candidates inserts them one by one (~12 instructions each)
+                                // instead of the 32-key sort + merge (~180): most flushes at the end of a shell are small
 __device__ __forceinline__ void kbest_flush(KBest& s, int lane, int k) {
   if (s.buf_n == 0) return;  // warp-uniform
   __syncwarp();
+  if (!s.empty && s.buf_n <= kInsertMax) {
+    for (int i = 0; i < s.buf_n; i++) {
+      const unsigned long long c = s.buf[i];  // (broadcast read)
+      if (c < s.kth) s.list = insert_keep32(s.list, c, lane);  // (uniform; kth only shrinks while inserting)
+    }
+    __syncwarp();
+    s.kth = shfl64(s.list, k - 1);
+    s.buf_n = 0;
+    return;
+  }
   unsigned long long b = lane < s.buf_n ? s.buf[lane] : kInfKey;
   __syncwarp();
   b = bitonic_sort32(b, lane);

@@ -76,6 +76,7 @@ struct LmShared {
   PoseD T_corr;                 // pose of the last update_correspondences pass (warm start of the next one)
   unsigned long long kbuf[kLmWarps][32];  // on-demand target covariances: the kNN search's candidate buffer, per warp
   int n_need;                   // ... and the number of target points this CTA serves in the current pass
+  int next_q, next_li;          // work counters of the search passes: groups / warps take the next query when they are free
   int flag_in, flag_out;        // LM trial decision / outer-loop decision (separate words: each is re-read across one barrier only)
   LmSerial ser;
 };
@@ -126,14 +127,26 @@ __device__ __forceinline__ void load_maha(const LmJob& job, int i, double m[6], 
   }
 }
 
+// Publication of an on-demand covariance: the six values, then the flag with RELEASE semantics at device scope; a
+// reader that sees the flag through an ACQUIRE load is guaranteed to see the values (it reads them from L2, __ldcg).
+// Several CTAs — of one registration or of registrations sharing a target — may compute the same point concurrently:
+// they store the same bits, and the flag only ever goes 0 -> 1.
+__device__ __forceinline__ void flag_publish(unsigned char* f) {
+  asm volatile("st.release.gpu.global.u8 [%0], %1;" ::"l"(f), "r"(1u) : "memory");
+}
+__device__ __forceinline__ unsigned flag_acquire(const unsigned char* f) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  return v;
+}
+
 // covariance + regularisation of target point `pos` from its neighbour ids (the per-cloud kernels' code: same bits);
 // __noinline__ keeps the Jacobi sweep's registers out of the optimizer loop
 __device__ __noinline__ void lazy_target_covariance(const LmJob& job, const int32_t* nbq, int pos) {
   const Sym3 C = knnw::covariance_of_neighbors(job.t_pts, nbq, job.k, job.reg);
 #pragma unroll
   for (int e = 0; e < 6; e++) __stcg(job.t_cov_rw + (size_t)pos * 6 + e, C.v[e]);
-  __threadfence();
-  *((volatile unsigned char*)&job.t_cov_flag[pos]) = 1;
+  flag_publish(&job.t_cov_flag[pos]);
 }
 
 // FastAPDGICP::update_correspondences (:160-220) for this CTA's points [base, base+cnt)
@@ -144,37 +157,52 @@ __device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg
   const PoseF Tf = pose_to_f32(T);
   const PoseF Tpf = pose_to_f32(T_prev);
   const int tid = threadIdx.x;
-  if (tid == 0) smem.n_need = 0;
-  constexpr int kQ = kLmThreads / kLmG;  // queries per pass
-  for (int p0 = 0; p0 < cnt; p0 += kQ) {
-    const int q = p0 + tid / kLmG;
-    const int i = base + min(q, cnt - 1);
-    const float4 a = job.s_spts[i];
-    float px, py, pz;
-    transform_rn(Tf, a.x, a.y, a.z, px, py, pz);  // :176
-    int seed = -1;
-    if (warm) {
-      float kept;
-      if (!warm_start(Tpf, a, px, py, pz, job.corr[i], job.sqd[i], cfg.np.thr_sq, seed, kept)) {  // (uniform over the lanes of a query)
-        nn_group_sync<kLmG>();
-        if (q < cnt && (tid & (kLmG - 1)) == 0) job.sqd[i] = kept;  // provably still unmatched; corr[i] stays -1
+  if (tid == 0) {
+    smem.n_need = 0;
+    smem.next_q = 0;
+    smem.next_li = 0;
+  }
+  __syncthreads();
+  // The searches differ in cost (a cold query walks shells, a warm one checks a row, a provably unmatched one returns at
+  // once): the groups of kLmG lanes take queries from a counter instead of a fixed stride, so no warp waits at the
+  // barrier below for the unluckiest one. Who serves a query does not matter: it writes that query's own slots.
+  {
+    const unsigned gmask = nn_group_mask<kLmG>();
+    const int leader = (int)(tid & 31) & ~(kLmG - 1);
+    for (;;) {
+      int q = 0;
+      if ((tid & (kLmG - 1)) == 0) q = atomicAdd(&smem.next_q, 1);
+      q = __shfl_sync(gmask, q, leader);
+      if (q >= cnt) break;
+      const int i = base + q;
+      const float4 a = job.s_spts[i];
+      float px, py, pz;
+      transform_rn(Tf, a.x, a.y, a.z, px, py, pz);  // :176
+      int seed = -1;
+      if (warm) {
+        float kept;
+        const bool search = warm_start(Tpf, a, px, py, pz, job.corr[i], job.sqd[i], cfg.np.thr_sq, seed, kept);  // (uniform over the lanes of a query)
+        nn_group_sync<kLmG>();  // every lane has read corr[i] / sqd[i] before one of them rewrites them
+        if (!search) {
+          if ((tid & (kLmG - 1)) == 0) job.sqd[i] = kept;  // provably still unmatched; corr[i] stays -1
+          continue;
+        }
+      }
+      unsigned long long best;
+      int pos;
+      float proven2;
+      nn_search<kLmG>(job.t_spts, job.t_cell_start, job.tg, px, py, pz, cfg.np.thr_sq, best, pos, seed, proven2);  // :178
+      if ((tid & (kLmG - 1)) != 0) continue;
+      const float d2 = (best == kInfKey) ? 3.402823466e38f : __uint_as_float((unsigned)(best >> 32));
+      const bool ok = (best != kInfKey) && ((double)d2 < cfg.np.thr_sq);  // :183
+      if (!ok) {
+        job.corr[i] = -1;
+        job.sqd[i] = fminf(d2, proven2);  // rejected: the proven lower bound of its distance (see corr.cu)
         continue;
       }
+      job.sqd[i] = d2;  // :180
+      job.corr[i] = pos | ((job.t_label[pos] == job.s_label[i]) ? kCorrLabelBit : 0);
     }
-    unsigned long long best;
-    int pos;
-    float proven2;
-    nn_search<kLmG>(job.t_spts, job.t_cell_start, job.tg, px, py, pz, cfg.np.thr_sq, best, pos, seed, proven2);  // :178
-    if (q >= cnt || (tid & (kLmG - 1)) != 0) continue;
-    const float d2 = (best == kInfKey) ? 3.402823466e38f : __uint_as_float((unsigned)(best >> 32));
-    const bool ok = (best != kInfKey) && ((double)d2 < cfg.np.thr_sq);  // :183
-    if (!ok) {
-      job.corr[i] = -1;
-      job.sqd[i] = fminf(d2, proven2);  // rejected: the proven lower bound of its distance (see corr.cu)
-      continue;
-    }
-    job.sqd[i] = d2;  // :180
-    job.corr[i] = pos | ((job.t_label[pos] == job.s_label[i]) ? kCorrLabelBit : 0);
   }
   __syncthreads();
   // Target covariances on demand (calculate_covariances(target), :351-411, restricted to the points that are used).
@@ -190,11 +218,16 @@ __device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg
       const int c = job.corr[base + q];
       if (c < 0) continue;
       const int pos = c & kCorrIndexMask;
-      if (*((volatile unsigned char*)&job.t_cov_flag[pos]) == 0) list[base + atomicAdd(&smem.n_need, 1)] = pos;
+      // (the thread that sees the flag here is the one that reads this point's covariance in the last pass below)
+      if (flag_acquire(&job.t_cov_flag[pos]) == 0) list[base + atomicAdd(&smem.n_need, 1)] = pos;
     }
     __syncthreads();
     const int n_need = smem.n_need;
-    for (int li = warp; li < n_need; li += kLmWarps) {
+    for (;;) {  // warps take listed points from a counter (a kNN search walks 1 to 4 shells)
+      int li = 0;
+      if (lane == 0) li = atomicAdd(&smem.next_li, 1);
+      li = __shfl_sync(0xffffffffu, li, 0);
+      if (li >= n_need) break;
       const unsigned long long key = knnw::knn_warp_query(job.t_spts, job.t_cell_start, job.tg, job.k, list[base + li], lane, smem.kbuf[warp]);
       if (lane < job.k) job.nb[(size_t)(base + li) * job.k + lane] = (int)(unsigned)(key & 0xffffffffull);
     }
@@ -444,13 +477,14 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
     constexpr int kQ = kLmThreads / kLmG;
     for (int p0 = 0; p0 < cnt; p0 += kQ) {
       const int q = p0 + tid / kLmG;
-      const float4 a = job.s_spts[base + min(q, cnt - 1)];
+      if (q >= cnt) continue;  // (the lanes of a group share q: the whole group sits this round out)
+      const float4 a = job.s_spts[base + q];
       float px, py, pz;
       transform_rn(Tf, a.x, a.y, a.z, px, py, pz);
       unsigned long long best;
       int pos;
       nn_search<kLmG>(job.t_spts, job.t_cell_start, job.tg, px, py, pz, 1e300, best, pos);
-      if (q < cnt && (tid & (kLmG - 1)) == 0 && best != kInfKey) {
+      if ((tid & (kLmG - 1)) == 0 && best != kInfKey) {
         const double d2 = (double)__uint_as_float((unsigned)(best >> 32));
         if (d2 <= cfg.fitness_max_range) { f[0] += d2; f[1] += 1.0; }
         if (d2 < cfg.inlier_sq_thr) f[2] += 1.0;

@@ -54,6 +54,50 @@ __device__ __forceinline__ void nn_group_min(unsigned long long& best, int& best
   }
 }
 
+// The G lanes of a query scan candidate segments TOGETHER: every lane brings one segment [b, b + cnt) of the cell-sorted
+// target points (cnt = 0: nothing — its row was pruned or lies outside the grid); the non-empty segments are taken one
+// after the other (ballot over the group), broadcast, and scanned with the lanes strided over their points. After a
+// warm start one or two rows of a cube survive the pruning: dealing ROWS to lanes (round 1) left ~1 lane in 8 busy in
+// the candidate loop (4.2 active threads per instruction, 27 % of the loop kernel's instructions); dealing POINTS does not.
+template <int G>
+__device__ __forceinline__ unsigned nn_group_mask() {
+  return (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+}
+template <int G>
+__device__ __forceinline__ void scan_segments_group(const float4* __restrict__ spts, int b, int cnt, float qx, float qy, float qz,
+                                                    unsigned long long& best, int& best_pos) {
+  if (G == 1) {
+    scan_range(spts, b, b + cnt, qx, qy, qz, best, best_pos);
+    return;
+  }
+  const unsigned gmask = nn_group_mask<G>();
+  const int gbase = (int)(threadIdx.x & 31) & ~(G - 1), sub = (int)(threadIdx.x & (G - 1));
+  unsigned m = __ballot_sync(gmask, cnt > 0) & gmask;
+  while (m) {  // (uniform over the group)
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int bb = __shfl_sync(gmask, b, src), cc = __shfl_sync(gmask, cnt, src);
+    for (int j = bb + sub; j < bb + cc; j += G) {
+      const float4 p = __ldg(&spts[j]);
+      const unsigned long long key = pack_key(sqdist_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+      if (key < best) {
+        best = key;
+        best_pos = j;
+      }
+    }
+  }
+  (void)gbase;
+}
+
+// squared distance (with the search's safety factor) from the query to the y/z slab of cell row (y, z)
+__device__ __forceinline__ float row_dist2(const GridDesc& g, int y, int z, float qy, float qz) {
+  const float mg = 0.002f * g.cell;
+  const float loy = g.oy + (float)y * g.cell - mg, hiy = g.oy + (float)(y + 1) * g.cell + mg;
+  const float loz = g.oz + (float)z * g.cell - mg, hiz = g.oz + (float)(z + 1) * g.cell + mg;
+  const float ddy = fmaxf(0.f, fmaxf(loy - qy, qy - hiy)), ddz = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
+  return (ddy * ddy + ddz * ddz) * 0.9999f;
+}
+
 // Shells r = 2, 3, ... around the query's cell (cx,cy,cz), given the best key over the radius-1 cube: continues until
 // the best distance is provably final or every unscanned point is farther than the limit.
 // proven2: on return every point that was NOT scanned is at least sqrt(min(proven2, best d2)) away.
@@ -62,7 +106,6 @@ __device__ __forceinline__ void nn_shells(const float4* __restrict__ spts, const
                                           float qx, float qy, float qz, int cx, int cy, int cz, double limit_sq, unsigned long long& best,
                                           int& best_pos, float& proven2) {
   const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
-  const float mg = 0.002f * g.cell;
   // Rows inside a shell are skipped when they lie beyond 1.25 x the correspondence distance (not 1 x): the slack is what
   // lets the next pass prove "still unmatched" after a small motion without searching again (warm_start).
   const double prune_sq = limit_sq * 1.5625;
@@ -81,25 +124,37 @@ __device__ __forceinline__ void nn_shells(const float4* __restrict__ spts, const
     const int rr = r < 3 ? r + 1 : r + (r >> 1) + 1;
     const int side = 2 * rr + 1;
     const int x0 = max(cx - rr, 0), x1 = min(cx + rr, g.nx - 1);
-    for (int ri = sub; ri < side * side; ri += G) {
-      const int dy = ri % side - rr, dz = ri / side - rr;
-      const int y = cy + dy, z = cz + dz;
-      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
-      // skip the row if even its nearest point cannot beat the current best / the limit
-      const float loy = g.oy + (float)y * g.cell - mg, hiy = g.oy + (float)(y + 1) * g.cell + mg;
-      const float loz = g.oz + (float)z * g.cell - mg, hiz = g.oz + (float)(z + 1) * g.cell + mg;
-      const float ddy = fmaxf(0.f, fmaxf(loy - qy, qy - hiy)), ddz = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
-      const float dyz2 = (ddy * ddy + ddz * ddz) * 0.9999f;
-      if ((double)dyz2 >= prune_sq) continue;
-      if (best != kInfKey && dyz2 > __uint_as_float((unsigned)(best >> 32))) continue;
-      const int row = (z * g.ny + y) * g.nx;
-      if (dy > r || dy < -r || dz > r || dz < -r) {  // row outside the scanned cube: its whole x-range
-        scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
-      } else {  // row crosses the scanned cube: the two end pieces
-        const int xl = min(cx - r - 1, g.nx - 1), xr = max(cx + r + 1, 0);
-        if (x0 <= xl) scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + xl + 1]), qx, qy, qz, best, best_pos);
-        if (xr <= x1) scan_range(spts, (int)__ldg(&cell_start[row + xr]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
+    // rounds of G rows: lane `sub` sets up row ri0 + sub (its one or two segments), the group scans what survived
+    for (int ri0 = 0; ri0 < side * side; ri0 += G) {  // (uniform over the group)
+      const int ri = ri0 + sub;
+      int b0 = 0, c0 = 0, b1 = 0, c1 = 0;
+      if (ri < side * side) {
+        const int dy = ri % side - rr, dz = ri / side - rr;
+        const int y = cy + dy, z = cz + dz;
+        if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+          // skip the row if even its nearest point cannot beat the current best / the limit
+          const float dyz2 = row_dist2(g, y, z, qy, qz);
+          if ((double)dyz2 < prune_sq && !(best != kInfKey && dyz2 > __uint_as_float((unsigned)(best >> 32)))) {
+            const int row = (z * g.ny + y) * g.nx;
+            if (dy > r || dy < -r || dz > r || dz < -r) {  // row outside the scanned cube: its whole x-range
+              b0 = (int)__ldg(&cell_start[row + x0]);
+              c0 = (int)__ldg(&cell_start[row + x1 + 1]) - b0;
+            } else {  // row crosses the scanned cube: the two end pieces
+              const int xl = min(cx - r - 1, g.nx - 1), xr = max(cx + r + 1, 0);
+              if (x0 <= xl) {
+                b0 = (int)__ldg(&cell_start[row + x0]);
+                c0 = (int)__ldg(&cell_start[row + xl + 1]) - b0;
+              }
+              if (xr <= x1) {
+                b1 = (int)__ldg(&cell_start[row + xr]);
+                c1 = (int)__ldg(&cell_start[row + x1 + 1]) - b1;
+              }
+            }
+          }
+        }
       }
+      scan_segments_group<G>(spts, b0, c0, qx, qy, qz, best, best_pos);
+      scan_segments_group<G>(spts, b1, c1, qx, qy, qz, best, best_pos);
     }
     nn_group_min<G>(best, best_pos);
     r = rr;
@@ -124,21 +179,30 @@ __device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const
     best = pack_key(sqdist_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
     best_pos = seed_pos;
   }
-  // ring 0+1: 3x3x3 cube as 9 x-rows
+  // ring 0+1: the 3x3x3 cube as 9 x-rows. The query's own row first, by all lanes; its best prunes the other eight,
+  // which are set up one per lane (G = 8; fewer lanes: in rounds) and scanned together.
   {
-    const float mg = 0.002f * g.cell;
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-    for (int ri = sub; ri < 9; ri += G) {
-      const int y = cy + (ri % 3) - 1, z = cz + (ri / 3) - 1;
-      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
-      if (best != kInfKey && ri != 4) {  // skip the row if even its nearest point cannot beat the current best (row 4 is the query's own)
-        const float loy = g.oy + (float)y * g.cell - mg, hiy = g.oy + (float)(y + 1) * g.cell + mg;
-        const float loz = g.oz + (float)z * g.cell - mg, hiz = g.oz + (float)(z + 1) * g.cell + mg;
-        const float ddy = fmaxf(0.f, fmaxf(loy - qy, qy - hiy)), ddz = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
-        if ((ddy * ddy + ddz * ddz) * 0.9999f > __uint_as_float((unsigned)(best >> 32))) continue;
+    {
+      const int row = (cz * g.ny + cy) * g.nx;
+      const int b = (int)__ldg(&cell_start[row + x0]);
+      scan_segments_group<G>(spts, sub == 0 ? b : 0, sub == 0 ? (int)__ldg(&cell_start[row + x1 + 1]) - b : 0, qx, qy, qz, best, best_pos);
+      nn_group_min<G>(best, best_pos);
+    }
+    for (int k0 = 0; k0 < 8; k0 += G) {  // (uniform over the group)
+      const int kk = k0 + sub;          // the eight rows around the centre one
+      int b = 0, cnt = 0;
+      if (kk < 8) {
+        const int ri = kk < 4 ? kk : kk + 1;
+        const int y = cy + (ri % 3) - 1, z = cz + (ri / 3) - 1;
+        if (y >= 0 && y < g.ny && z >= 0 && z < g.nz &&
+            !(best != kInfKey && row_dist2(g, y, z, qy, qz) > __uint_as_float((unsigned)(best >> 32)))) {
+          const int row = (z * g.ny + y) * g.nx;
+          b = (int)__ldg(&cell_start[row + x0]);
+          cnt = (int)__ldg(&cell_start[row + x1 + 1]) - b;
+        }
       }
-      const int row = (z * g.ny + y) * g.nx;
-      scan_range(spts, (int)__ldg(&cell_start[row + x0]), (int)__ldg(&cell_start[row + x1 + 1]), qx, qy, qz, best, best_pos);
+      scan_segments_group<G>(spts, b, cnt, qx, qy, qz, best, best_pos);
     }
     nn_group_min<G>(best, best_pos);
   }
