@@ -8,33 +8,42 @@ pairs: for every pair {clearTarget; clearSource; setInputTarget; setInputSource;
 align} (the reference benchmark protocol, fast_apdgicp/src/align.cpp:57-83) with
 the deployed parameters (4DRadarSLAM/launch/ntu_loop2.launch:88-99).
 
-  value     registrations/s, clouds already resident in HBM (apd_set_*_device)
-  e2e       the same through the C-ABI with HOST buffers (apd_set_source/target
-            stage + copy the clouds, apd_align copies the pose back)
-  roofline  the linearize kernel on a cloud larger than L2 (CUDA events on the
-            handle's stream, live in this run) against the measured HBM peak
-  cpu_baseline  the reference-structure CPU restatement (oracle/_ref: OpenMP +
-            the reference tree's nanoflann; else the oracle port) on a bounded
-            sample of the same pairs, all host threads
+The batch is config C3 of BASELINE.json: 4096 scan/submap pairs, EVERY ONE A DIFFERENT
+SCENE (C2-shaped: 2000-point scan vs 60 000-point keyframe submap, seeds 3000 + i),
+sharded across the N ranks by pair index (pair i -> rank i mod N, no data-path
+collective: pairs are independent, reference loop_detector.cpp:222-236). The total
+work is fixed, so this is strong scaling; at N = 1 the one GPU registers all 4096.
 
-N > 1: the pairs are sharded across ranks (one process per GPU, no data-path
-collective — pairs are independent, reference loop_detector.cpp:222-236), weak
-scaling; value = all pairs / max-over-ranks time.
+  value     registrations/s, clouds already resident in HBM (apd_batch_align_device)
+  e2e       the same through the C-ABI with HOST buffers in the layout the drop-in
+            class receives: pageable 48-byte pcl::PointXYZINormal clouds
+            (apd_batch_align stages, copies, registers, brings the poses back)
+  e2e_packed  the same with packed float4 clouds in page-locked memory (no staging)
+  eager     device-resident rate with ALL target covariances computed up front, as
+            the reference does (the default computes the ~4 100 a registration meets)
+  parity_vs_cpu  max |dT| against the CPU restatement on the first pairs of the batch
+  c4        config C4, one 20 M x 20 M registration source-sharded over the N ranks:
+            ms per LM iteration (linearize + compute_error, all-reduce inside the
+            reduction kernels over NVLink peer memory), err against a committed constant
+  roofline  (N = 1) the linearize kernel on that cloud (> L2), CUDA events on the
+            handle's stream, against the measured HBM peak; + the loop kernel's share
+  cpu_baseline  (N = 1) the reference-structure CPU restatement (oracle/_ref: OpenMP +
+            the reference tree's nanoflann; else the oracle port) on a bounded sample
 """
 import argparse
 import ctypes
 import importlib
 import json
+import multiprocessing
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
 
-# one hardware work queue per worker stream of the batch pool (read when the CUDA context is created, i.e. before torch
-# touches the GPU; libapdgicp.so sets the same default when it is loaded — see apdgicp.cu: apd_default_connections)
+# one hardware work queue per worker stream of the batch pool: read by the driver when the CUDA context is created, i.e.
+# before torch touches the GPU (the library itself no longer changes the environment when it is loaded)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -44,10 +53,14 @@ sys.path.insert(0, os.path.join(REPO, "tests"))
 DEPLOYED = dict(max_correspondence_distance=2.0, transformation_epsilon=0.1)
 METRIC = "APDGICP registrations/sec (scan-to-submap)"
 UNIT = "registrations/s"
-WORKLOAD = ("C2 scan-to-submap: 2000-pt radar scan vs 60000-pt keyframe submap, k=20, deployed params "
-            "(max_corr_dist 2.0, trans_eps 0.1, LM, PLANE)")  # the same string in both arms
+WORKLOAD = ("C3 batch of C2 scan-to-submap pairs: 2000-pt radar scan vs 60000-pt keyframe submap, every pair a different scene "
+            "(seeds 3000+i), k=20, deployed params (max_corr_dist 2.0, trans_eps 0.1, LM, PLANE)")  # the same string in both arms
 BYTES_PER_POINT_LINEARIZE = 64  # src 16 + corr 4 + tgt 16 + maha 24 + geo 4
-BYTES_PER_POINT_KNNCOV = 68     # read point 16, write cov 48 + geo 4
+BYTES_PER_POINT_CORR = 148
+SCENE_SEED0 = 3000              # C3 pair i is scene 3000 + i
+# err of one linearisation of the seed-4000 tiled 20 M-point pair at its ground-truth pose (sum over 20 M points): the
+# value every sharding (N = 1, 2, 4, 8; NCCL or in-kernel exchange) must reproduce to 12 digits (summation order differs)
+C4_ERR_20M = 4856.67264058955
 
 
 def parse():
@@ -56,32 +69,21 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=512, help="scan/submap pairs per step and per GPU (config C3: 4096 pairs over 8 GPUs)")
-    ap.add_argument("--streams", type=int, default=64, help="registrations in flight per GPU: handles (CUDA stream each) of the batch context, driven by a few host threads")
+    ap.add_argument("--pairs", type=int, default=4096, help="scan/submap pairs per step over ALL GPUs (config C3: 4096)")
+    ap.add_argument("--distinct", type=int, default=0, help="distinct scenes among the pairs (0: all; fewer are cycled — profiling aid)")
+    ap.add_argument("--streams", type=int, default=128, help="registrations in flight per GPU: handles (CUDA stream each) of the batch context, driven by a few host threads")
     ap.add_argument("--roofline-points", type=int, default=20_000_000)
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true")
+    ap.add_argument("--no-eager", action="store_true")
     ap.add_argument("--roofline-reps", type=int, default=10)
     ap.add_argument("--roofline-only", action="store_true", help="profiling aid: skip the registrations/s part")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-pairs", type=int, default=8, help="pairs per step of the reference arm")
     ap.add_argument("--no-fused", action="store_true", help="c4: ncclAllReduce after the reduction kernels instead of the peer-memory exchange inside them")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
-                    help="c2 (default): scan-to-submap pairs, sharded by pair; c4: one large cloud, source-sharded with an NCCL all-reduce")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4"],
+                    help="c3 (default): the batch of scan-to-submap pairs (+ the c4 block); c4: only the large source-sharded cloud")
     return ap.parse_args()
-
-
-def make_pairs(synth, rank, n_pairs, distinct=8):
-    """C2-shaped pairs: 2000-point scan vs 60k-point submap. `distinct` scenes are
-    generated (numpy generation costs ~1 s each) and cycled to n_pairs. Weak scaling
-    means the SAME work per GPU: every rank registers the same scenes (seeds 2000..),
-    starting at a different one. (With per-rank seeds the ranks' scenes need 33 to 65
-    outer iterations per 8 scenes, and the max-over-ranks time measures the unluckiest
-    draw: 8 x B200 read 80 % of 8 x the 1-GPU rate for that reason alone.)"""
-    base = []
-    for i in range(min(distinct, n_pairs)):
-        s, t, _ = synth.submap_pair(2000 + i)
-        base.append((np.ascontiguousarray(s), np.ascontiguousarray(t)))
-    return [base[(i + rank) % len(base)] for i in range(n_pairs)]
 
 
 def host_cores():
@@ -89,6 +91,39 @@ def host_cores():
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+def _scene(seed):
+    synth = importlib.import_module("go-rio_b200.synth")
+    s, t, _ = synth.submap_pair(seed)
+    return np.ascontiguousarray(s), np.ascontiguousarray(t)
+
+
+def pair_indices(rank, world, total):
+    """config C3's split: pair i -> rank i mod N"""
+    return list(range(rank, total, world))
+
+
+def make_pairs(synth, rank, world, total, distinct=0, procs=None):
+    """This rank's share of the `total` C2-shaped pairs, pair i being scene SCENE_SEED0 + (i mod distinct): (source, target)
+    float32 [n,4] arrays. Scenes are generated by a pool of forked workers (0.1 s of numpy each) BEFORE the process
+    touches CUDA."""
+    distinct = total if distinct <= 0 else min(distinct, total)
+    mine = pair_indices(rank, world, total)
+    need = sorted({i % distinct for i in mine})
+    seeds = [SCENE_SEED0 + j for j in need]
+    if procs is None:
+        procs = max(1, min(32, host_cores() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    if procs > 1 and len(seeds) > 4:
+        with multiprocessing.get_context("fork").Pool(procs) as pool:
+            scenes = pool.map(_scene, seeds, chunksize=max(1, len(seeds) // (8 * procs)))
+    else:
+        scenes = []
+        for sd in seeds:
+            s, t, _ = synth.submap_pair(sd)
+            scenes.append((np.ascontiguousarray(s), np.ascontiguousarray(t)))
+    by = dict(zip(need, scenes))
+    return [by[i % distinct] for i in mine]
 
 
 # ------------------------------------------------------------ reference arm ----
@@ -99,8 +134,7 @@ def load_cpu_impl():
     return oracle_lib(ref=False), "port", 1, "oracle port (own exact kd-tree, OpenMP)"
 
 
-def cpu_registrations(lib, search, pairs, reps):
-    """Runs the CPU restatement on `pairs` x reps with all host threads; returns (seconds, n)."""
+def cpu_handle(lib, search):
     h = ctypes.c_void_p()
     lib.apdo_create(ctypes.byref(h))
     gorio = importlib.import_module("go-rio_b200")
@@ -112,6 +146,12 @@ def cpu_registrations(lib, search, pairs, reps):
     lib.apdo_set_search(h, ctypes.c_int(search))
     # setNumThreads(0) = all cores (registrations.cpp:41); torchrun exports OMP_NUM_THREADS=1, so ask for the cores explicitly
     lib.apdo_set_num_threads(h, ctypes.c_int(host_cores()))
+    return h
+
+
+def cpu_registrations(lib, search, pairs, reps):
+    """Runs the CPU restatement on `pairs` x reps with all host threads; returns (seconds, n)."""
+    h = cpu_handle(lib, search)
     ms = (ctypes.c_double * reps)()
     total = 0.0
     for s, t in pairs:
@@ -124,6 +164,22 @@ def cpu_registrations(lib, search, pairs, reps):
     return total, len(pairs) * reps
 
 
+def cpu_poses(pairs):
+    """final float poses of the CPU restatement (the checker) for `pairs`, and whether each converged"""
+    from oracle_binding import ORACLE_REF_SO, Oracle
+    ref = os.path.exists(ORACLE_REF_SO)
+    o = Oracle(search=2 if ref else 1, threads=host_cores(), ref=ref)
+    o.set_params(**DEPLOYED)
+    out = []
+    for s, t in pairs:
+        o.clear_target(); o.clear_source()
+        o.set_input_target(t); o.set_input_source(s)
+        r = o.align()
+        out.append((r["T"], r["converged"], r["iterations"]))
+    o.close()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -131,7 +187,7 @@ def run_reference(args):
     synth = importlib.import_module("go-rio_b200.synth")
     lib, kind, search, what = load_cpu_impl()
     cores = host_cores()
-    pairs = make_pairs(synth, 0, args.ref_pairs, distinct=min(8, args.ref_pairs))
+    pairs = make_pairs(synth, 0, 1, args.ref_pairs)  # the first pairs of the batch our arm registers
     for _ in range(args.warmup):
         cpu_registrations(lib, search, pairs[:1], 1)
     t_total, n_total = 0.0, 0
@@ -142,10 +198,11 @@ def run_reference(args):
     value = n_total / t_total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD,
-                   "pairs_per_step": len(pairs), "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align"},
+                   "pairs_per_step": len(pairs), "sample": f"the first {len(pairs)} pairs of the batch per step (a bounded sample: the CPU path "
+                   "needs ~20 ms per pair on all cores)", "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{len(pairs)} pairs per step x {args.steps} steps; {what}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -166,7 +223,7 @@ class ClockSampler:
 
     def __enter__(self):
         # ONE nvidia-smi process in loop mode (the recipe's clocks line): starting a process per sample re-initialises
-        # NVML every 50 ms and measurably slows kernel launches of the 32-64 worker threads being timed
+        # NVML every 50 ms and measurably slows kernel launches of the worker threads being timed
         try:
             self._p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index),
                                         "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -202,43 +259,36 @@ class ClockSampler:
 LM_RESULT_HEAD_BYTES = 1984  # apdgicp.cu kLmHeadBytes: pose, final hessian, flags and the first LM trace rows, per registration
 
 
-def run_c4(args):
-    """Config C4: `--roofline-points` source points vs as many target points, the source split contiguously over the
-    ranks, the target replicated; one step = one LM iteration's device work (linearize = update_correspondences +
-    H/b/err reduction + all-reduce of 28 doubles, then one compute_error + all-reduce of 1 double)."""
-    import torch
-    import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    gorio = importlib.import_module("go-rio_b200")
-    synth = importlib.import_module("go-rio_b200.synth")
+def c4_block(args, torch, dist, gorio, synth, rank, local_rank, world, dev, steps, with_roofline, peak, peak_src):
+    """Config C4 on the N ranks of this run: `--roofline-points` source points vs as many target points; every rank holds
+    both full clouds, the library cuts the cell-sorted source into interleaved chunks (covariances computed by chunks and
+    all-gathered; update_correspondences / linearize / compute_error over the rank's chunks in ONE launch each; the 28 / 1
+    sums exchanged inside the reduction kernels over NVLink peer memory). One step = one LM iteration's device work:
+    linearize (= update_correspondences + H/b/err) + one compute_error. At N = 1 the same handle gives the roofline block."""
     sharding = importlib.import_module("go-rio_b200.sharding")
     n = args.roofline_points
     src, tgt, T = synth.tiled_cloud_pair(4000, n)
     dsrc, dtgt = torch.from_numpy(src).to(dev), torch.from_numpy(tgt).to(dev)
+    del src, tgt
     g = gorio.FastAPDGICP(local_rank)
     g.set_params(max_correspondence_distance=2.0)
     if world > 1:
         sharding.init_comm(g, gorio.load(), rank, world, n, dist, dev, fused=not args.no_fused)
-    # every rank sets the same full clouds; the library slices the work (covariances all-gathered, H/b/err all-reduced)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_setup = time.perf_counter()
     g.set_input_target_device(dtgt.data_ptr(), n)
     g.set_input_source_device(dsrc.data_ptr(), n)
+    g.set_profiling(True)
     g.linearize(T)  # grids + covariances (+ all-gather) + the first linearisation
     torch.cuda.synchronize()
+    k0 = g.kernel_ms()
+    g.set_profiling(False)
     t_setup = torch.tensor([time.perf_counter() - t_setup], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_setup, op=dist.ReduceOp.MAX)
-    for _ in range(max(1, args.warmup)):
+    for _ in range(3):
         g.linearize(T)
         g.compute_error(T)
     l0 = g.launch_count()
@@ -247,7 +297,7 @@ def run_c4(args):
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         err, H, bb = g.linearize(T)
         err2 = g.compute_error(T)
     e1.record()
@@ -258,27 +308,61 @@ def run_c4(args):
     ms = float(ms.item())
     launches = g.launch_count() - l0
     g.set_profiling(True)
-    g.linearize(T)
-    g.compute_error(T)
+    reps = max(1, args.roofline_reps)
+    for _ in range(reps):
+        g.linearize(T)
+        g.compute_error(T)
     k = g.kernel_ms()
-    if rank == 0:
-        print(json.dumps({
-            "metric": "APDGICP LM-iteration throughput on one large cloud (source points/s)", "value": n * args.steps / (ms / 1e3),
-            "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C4: {n} source vs {n} target points over {world} GPU(s): covariances computed by slices and "
-                                   "all-gathered, source sliced for update_correspondences/linearize/compute_error, all-reduce of 28 "
-                                   "doubles per linearize and 1 per compute_error "
-                                   + ("by ncclAllReduce" if (args.no_fused or world == 1) else "inside the reduction kernels over NVLink peer memory"),
-                       "l2": "inputs larger than L2"},
-            "setup_ms": 1e3 * float(t_setup.item()), "setup": "grid builds + kNN covariances of both clouds (+ all-gather) + first linearize, wall clock, max over ranks",
-            "gpu_launches": int(launches), "err": err, "err_trial": err2,
-            "kernels_rank0_ms": {c: v[0] for c, v in k.items()},
-        }), flush=True)
+    g.set_profiling(False)
+    lin_ms, err_ms, corr_ms = k["linearize"][0] / reps, k["error"][0] / reps, k["corr"][0] / reps
+    n_local = -(-n // world)  # source points this rank serves
+    block = {
+        "workload": f"C4: {n} source vs {n} target points, source-sharded over {world} GPU(s) in interleaved chunks; covariances by chunks + "
+                    "all-gather; per LM iteration ONE update_correspondences pass (search + Mahalanobis kernels), ONE linearize and ONE "
+                    "compute_error launch per rank; all-reduce of 28 / 1 doubles "
+                    + ("by ncclAllReduce" if (args.no_fused and world > 1) else ("inside the reduction kernels over NVLink peer memory" if world > 1 else "not needed (1 GPU)")),
+        "ms_per_step": ms / steps, "steps": steps, "points_per_s": n * steps / (ms / 1e3), "scaling": "strong",
+        "launches_per_step": launches / steps,
+        "kernels_rank0_ms": {"update_correspondences": corr_ms, "linearize": lin_ms, "compute_error": err_ms},
+        "setup_ms": 1e3 * float(t_setup.item()),
+        "setup": "grid builds + kNN covariances of both clouds (+ all-gather) + first linearize, wall clock, max over ranks",
+        "err": err, "err_trial": err2,
+        "err_expected": C4_ERR_20M if n == 20_000_000 else None,
+        "err_equal_across_N": (abs(err - C4_ERR_20M) / C4_ERR_20M < 1e-12) if n == 20_000_000 else None,
+        "timing": "CUDA events around the steps, max over ranks (inputs 1.28 GB per pass > L2)",
+    }
+    roof = None
+    if with_roofline:
+        achieved = BYTES_PER_POINT_LINEARIZE * n_local / 1e9 / (lin_ms / 1e3)
+        n_valid = int((g.get_correspondences()[0] >= 0).sum())
+        traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of the same kernel at the same size
+        try:
+            cap = json.load(open(os.path.join(REPO, "profiles", "r02_ncu_linearize.json")))
+            if cap.get("points") == n:
+                kk = cap["linearize_kernel<fp32 maha, H+b+err>"]
+                traffic = kk["dram_bytes_read"] + kk["dram_bytes_write"]
+        except Exception:
+            pass
+        roof = {
+            "bound": "hbm", "kernel": "linearize_kernel<fp32 maha, H+b+err>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r02_ncu_linearize.json (ncu capture, bytes per launch)" if traffic else None,
+            "algorithmic_bytes": BYTES_PER_POINT_LINEARIZE * n, "peak_source": peak_src, "points": n, "matched_points": n_valid,
+            "bytes_per_point": BYTES_PER_POINT_LINEARIZE, "ms_per_launch": lin_ms,
+            "compute_error": {"ms_per_launch": err_ms, "achieved": BYTES_PER_POINT_LINEARIZE * n / 1e9 / (err_ms / 1e3),
+                              "frac": BYTES_PER_POINT_LINEARIZE * n / 1e9 / (err_ms / 1e3) / peak},
+            "update_correspondences": {"ms_per_pass": corr_ms, "launches_per_pass": 2, "achieved": BYTES_PER_POINT_CORR * n / 1e9 / (corr_ms / 1e3),
+                                       "frac": BYTES_PER_POINT_CORR * n / 1e9 / (corr_ms / 1e3) / peak, "bytes_per_point": BYTES_PER_POINT_CORR,
+                                       "note": "search kernel (fp32, index work) + Mahalanobis kernel (fp64, coalesced); warm-started pass"},
+            "grid_build": {"ms_per_cloud": k0["grid"][0] / 2, "launches_per_cloud": k0["grid"][1] // 2},
+            "knn_covariance": {"ms_per_cloud": k0["knn_cov"][0] / 2, "mqueries_per_s": n / 1e6 / (k0["knn_cov"][0] / 2 / 1e3)},
+            "timing": "CUDA events on the handle's stream around each launch; working set 1.28 GB > L2",
+        }
     if world > 1:
         g.comm_destroy()
-        dist.barrier()
-        dist.destroy_process_group()
+    g.close()
+    del dsrc, dtgt
+    torch.cuda.empty_cache()
+    return block, roof
 
 
 def main():
@@ -290,26 +374,29 @@ def main():
     sys.stdout = real_stdout
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload == "c4":
-        return run_c4(args)
-
-    import torch
-    import torch.distributed as dist
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    synth = importlib.import_module("go-rio_b200.synth")
+    only_c4 = args.workload == "c4"
+    host_pairs = []
+    t_gen = time.perf_counter()
+    if not args.roofline_only and not only_c4:
+        host_pairs = make_pairs(synth, rank, world, args.pairs, args.distinct)  # (forks: before CUDA is touched)
+    t_gen = time.perf_counter() - t_gen
+
+    import torch
+    import torch.distributed as dist
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the registration path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    gorio = importlib.import_module("go-rio_b200")
-    synth = importlib.import_module("go-rio_b200.synth")
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    gorio = importlib.import_module("go-rio_b200")
 
-    line = None
-    host_pairs = []
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -317,33 +404,43 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    if args.roofline_only:
-        line = {"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "note": "roofline-only profiling run"}
+
+    line = {"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world}
+    if args.roofline_only or only_c4:
+        line["note"] = "profiling run: only the large-cloud (C4 / roofline) part"
     else:
-        host_pairs = make_pairs(synth, rank, args.pairs)
-        # e2e inputs live in page-locked host memory (the contract's "pinned host memory"): the pool copies packed
-        # float4 clouds straight out of it; pageable clouds would be staged through the handles' own pinned buffers
-        pinned = {}
-        def pin(a):
-            if a.ctypes.data not in pinned:
-                t = torch.from_numpy(a).pin_memory()
-                pinned[a.ctypes.data] = (t, t.numpy())
-            return pinned[a.ctypes.data][1]
-        host_pairs = [(pin(s), pin(t)) for s, t in host_pairs]
-        # HBM-resident copies of the clouds for `value`
-        dev_tensors, dev_pairs = [], []
-        cache = {}
+        n_mine = len(host_pairs)
+        uniq = {}
         for s, t in host_pairs:
-            key = (s.ctypes.data, t.ctypes.data)
-            if key not in cache:
-                ds, dt = torch.from_numpy(s).to(dev), torch.from_numpy(t).to(dev)
-                dev_tensors += [ds, dt]
-                cache[key] = (ds.data_ptr(), s.shape[0], dt.data_ptr(), t.shape[0])
-            dev_pairs.append(cache[key])
-        # the batch context of the C-ABI (apd_batch_*): `--streams` workers, one handle / CUDA stream / host thread each
+            uniq.setdefault(s.ctypes.data, (s, t))
+        uniq = list(uniq.values())
+        # --- e2e_packed inputs: packed float4 clouds in ONE page-locked buffer (the pool copies them without staging) ---
+        total_f = sum(s.size + t.size for s, t in uniq)
+        pinned = torch.empty(total_f, dtype=torch.float32).pin_memory()
+        pinned_np = pinned.numpy()
+        pin_of, off = {}, 0
+        for s, t in uniq:
+            ps = pinned_np[off:off + s.size].reshape(s.shape); off += s.size
+            pt = pinned_np[off:off + t.size].reshape(t.shape); off += t.size
+            ps[...] = s
+            pt[...] = t
+            pin_of[s.ctypes.data] = (ps, pt)
+        pinned_pairs = [pin_of[s.ctypes.data] for s, _ in host_pairs]
+        # --- e2e inputs: pageable 48-byte pcl::PointXYZINormal clouds, what the drop-in class hands over ---
+        pcl_of = {s.ctypes.data: (synth.to_pcl_xyzinormal(s), synth.to_pcl_xyzinormal(t)) for s, t in uniq}
+        pcl_pairs = [pcl_of[s.ctypes.data] for s, _ in host_pairs]
+        # --- HBM-resident copies for `value` ---
+        dev_all = pinned.to(dev, non_blocking=True)
+        torch.cuda.synchronize()
+        base_ptr = dev_all.data_ptr()
+        host_base = pinned_np.ctypes.data
+        dev_pairs = [((base_ptr + (ps.ctypes.data - host_base), ps.shape[0]), (base_ptr + (pt.ctypes.data - host_base), pt.shape[0]), None)
+                     for ps, pt in pinned_pairs]
+        # the batch context of the C-ABI (apd_batch_*): `--streams` registrations in flight, a few host threads
         batch = gorio.Batch(local_rank, n_workers=args.streams, **DEPLOYED)
-        prep_dev = batch.prepare([((ds, ns), (dt, nt), None) for ds, ns, dt, nt in dev_pairs])
-        prep_host = batch.prepare([(s, t, None) for s, t in host_pairs])
+        prep_dev = batch.prepare(dev_pairs)
+        prep_packed = batch.prepare([(s, t, None) for s, t in pinned_pairs])
+        prep_pcl = batch.prepare([(s, t, None) for s, t in pcl_pairs], layout=(48, 0, 16))
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
         def barrier():
@@ -352,38 +449,45 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize()
 
-        def timed(prepared, steps, warmup):
+        def timed(b, prepared, steps, warmup):
             for _ in range(warmup):
-                batch.align(prepared, with_fitness=False, parse=False)
+                b.align(prepared, with_fitness=False, parse=False)
             ms_total = 0.0
-            l0 = batch.launch_count()
+            l0 = b.launch_count()
             cpu0 = time.process_time()
             for _ in range(steps):
                 flush.zero_()  # L2 flush between timed iterations (untimed)
                 barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                batch.align(prepared, with_fitness=False, parse=False)  # returns when every pair's result is on the host
+                b.align(prepared, with_fitness=False, parse=False)  # returns when every pair's result is on the host
                 e1.record()
                 torch.cuda.synchronize()
                 ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
                 if world > 1:
                     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
                 ms_total += float(ms.item())
-            launches = batch.launch_count() - l0
-            cpu_ms_per_pair = 1e3 * (time.process_time() - cpu0) / (steps * prepared["n"])  # all threads of this process
-            return ms_total, launches, batch.align(prepared, with_fitness=False), cpu_ms_per_pair
+            launches = b.launch_count() - l0
+            cpu_ms_per_pair = 1e3 * (time.process_time() - cpu0) / max(1, steps * prepared["n"])  # all threads of this process
+            return ms_total, launches, b.align(prepared, with_fitness=False), cpu_ms_per_pair
 
         with ClockSampler(local_rank) as clocks:
-            ms_dev, launches, results, cpu_dev = timed(prep_dev, args.steps, args.warmup)
-            ms_e2e, _, results_h, cpu_e2e = timed(prep_host, args.steps, args.warmup)
-        total_pairs = args.pairs * world
-        value = total_pairs * args.steps / (ms_dev / 1e3)
-        e2e_value = total_pairs * args.steps / (ms_e2e / 1e3)
-        same = all(np.array_equal(a["T"], b["T"]) for a, b in zip(results, results_h))
-        ok = all(r["status"] == 0 for r in results + results_h)
-        h2d = sum(s.nbytes + t.nbytes for s, t in host_pairs)
-        d2h = args.pairs * LM_RESULT_HEAD_BYTES
+            ms_dev, launches, results, cpu_dev = timed(batch, prep_dev, args.steps, args.warmup)
+            ms_pcl, _, results_pcl, cpu_pcl = timed(batch, prep_pcl, args.steps, args.warmup)
+            ms_packed, _, results_packed, cpu_packed = timed(batch, prep_packed, args.steps, args.warmup)
+        value = args.pairs * args.steps / (ms_dev / 1e3)
+        e2e_value = args.pairs * args.steps / (ms_pcl / 1e3)
+        packed_value = args.pairs * args.steps / (ms_packed / 1e3)
+        same = all(np.array_equal(a["T"], b["T"]) and np.array_equal(a["T"], c["T"]) for a, b, c in zip(results, results_pcl, results_packed))
+        every = results + results_pcl + results_packed
+        counts = torch.tensor([sum(r["status"] == 0 for r in every), sum(bool(r["converged"]) for r in every), len(every),
+                               sum(r["iterations"] for r in results)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(counts)
+        n_ok, n_conv, n_all, n_iter = (int(x) for x in counts.tolist())
+        h2d_pcl = sum(s.nbytes + t.nbytes for s, t in pcl_pairs)
+        h2d_packed = sum(s.nbytes + t.nbytes for s, t in pinned_pairs)
+        d2h = n_mine * LM_RESULT_HEAD_BYTES
 
         # per-kernel-class device time of one step (profiling events on the worker streams; separate, untimed pass)
         batch.set_profiling(True)
@@ -392,101 +496,96 @@ def main():
         batch.set_profiling(False)
         tot = sum(v[0] for v in kms.values()) or 1.0
         kernels = {k: {"ms_per_step": round(v[0], 4), "launches_per_step": v[1], "share": round(v[0] / tot, 4)} for k, v in kms.items()}
+        batch.close()
 
+        # --- the same with every target covariance computed up front, as the reference does (calculate_covariances over
+        # all 60 000 target points per registration): separates the algorithmic part of the speed-up from the hardware part
+        eager = None
+        if not args.no_eager:
+            os.environ["APD_LAZY_TARGET_COV"] = "0"
+            b2 = gorio.Batch(local_rank, n_workers=args.streams, **DEPLOYED)
+            del os.environ["APD_LAZY_TARGET_COV"]
+            sub = batch_sub = b2.prepare(dev_pairs[: max(1, min(n_mine, 1024 // world))])
+            ms_eager, _, res_eager, _ = timed(b2, sub, max(2, args.steps // 4), 1)
+            eager_same = all(np.array_equal(a["T"], b["T"]) for a, b in zip(results, res_eager))
+            eager = {"value": world * batch_sub["n"] * max(2, args.steps // 4) / (ms_eager / 1e3), "unit": UNIT, "pairs_per_step": world * batch_sub["n"],
+                     "same_poses_as_on_demand": bool(eager_same),
+                     "note": "APD_LAZY_TARGET_COV=0: all 60 000 target covariances per registration (the reference's work); the default "
+                             "computes the ones the registration meets (~4 100), bit-identical outputs"}
+            b2.close()
+
+        # --- parity against the CPU restatement on the first pairs of the batch (rank 0; the same pairs the reference arm times) ---
+        parity = None
         if rank == 0:
-            n_tgt_pts = sum(t.shape[0] for _, t in host_pairs[:1])
-            knn_ms = kms.get("knn_cov", [0.0, 0])[0]
-            knn_pts = sum(s.shape[0] + t.shape[0] for s, t in host_pairs)
-            line = {
-                "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD,
-                           "pairs_per_step_per_gpu": args.pairs, "streams_per_gpu": args.streams,
-                           "api": "apd_batch_align_device (value) / apd_batch_align (e2e)", "optimizer_loop": "device-resident (lm.cu), one launch per registration",
-                           "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align",
-                           "l2": "flushed (256 MiB write) between timed steps", "sharding": "pairs across ranks, no collective; every rank registers the same 8 scenes (equal work per GPU)",
-                           "target_points": n_tgt_pts},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "same_result_as_device_resident": bool(same), "all_pairs_ok": bool(ok),
-                        "api": "apd_batch_align (host AoS clouds in, poses out)"},
-                "gpu_launches": int(launches),
-                "host_cpu_ms_per_registration": {"device_resident": round(cpu_dev, 4), "e2e": round(cpu_e2e, 4), "host_cores": host_cores(),
-                                                 "note": "process CPU time of rank 0 (all worker threads, incl. the L2 flush / barrier between steps) per registration"},
-                "kernels": kernels,
-                "knn_cov_roofline": {"bound": "hbm", "achieved": (BYTES_PER_POINT_KNNCOV * knn_pts / 1e9) / (knn_ms / 1e3) if knn_ms > 0 else None,
-                                     "peak": peak, "unit": "GB/s", "note": "search-bound (L2-resident candidates), reported for the step's dominant kernel"},
-                "clocks": clocks.summary(),
-            }
+            try:
+                k = min(8, n_mine)
+                cpu = cpu_poses(host_pairs[:k])
+                dT = max(float(np.abs(results_pcl[i]["T"].astype(np.float64) - cpu[i][0].astype(np.float64)).max()) for i in range(k))
+                parity = {"pairs": k, "max_abs_dT": dT,
+                          "same_converged_and_iterations": all(bool(results_pcl[i]["converged"]) == bool(cpu[i][1]) and results_pcl[i]["iterations"] == cpu[i][2] for i in range(k)),
+                          "against": "the CPU restatement (oracle), the first pairs of the batch — the pairs the reference arm times",
+                          "bar": "float poses; fp32 Mahalanobis storage: within north_star's 1e-5 (the fp64 bar, 1e-6 m / 1e-6 rad, is held in tests/)"}
+            except Exception as e:  # the checker is optional here (tests/ hold the parity bar)
+                parity = {"error": str(e)}
 
-    # ---- roofline of the linearize kernel on a cloud larger than L2 (rank 0, N = 1 only) ----
-    if rank == 0 and world == 1 and not args.no_roofline:
-        if not args.roofline_only:
-            batch.close()
-        dev_tensors = None
+        line.update({
+            "value": value, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step": args.pairs, "pairs_per_step_per_gpu": n_mine,
+                       "distinct_scenes": args.pairs if args.distinct <= 0 else min(args.distinct, args.pairs),
+                       "streams_per_gpu": args.streams, "api": "apd_batch_align_device (value) / apd_batch_align (e2e)",
+                       "optimizer_loop": "device-resident (lm.cu), one launch per registration",
+                       "mahalanobis_storage": "fp32 (6 x 4 B per point; arithmetic fp64; within north_star's 1e-5, tests/test_gpu_parity.py)",
+                       "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align",
+                       "l2": "flushed (256 MiB write) between timed steps",
+                       "sharding": "pair i -> rank i mod N, no collective; every pair is a different scene (heterogeneous iteration counts)",
+                       "scene_generation_s": round(t_gen, 1)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_pcl, "d2h_bytes_per_step": d2h,
+                    "layout": "pageable 48-byte pcl::PointXYZINormal AoS (staged to pinned float4 by the pool, then copied)",
+                    "same_result_as_device_resident": bool(same), "all_pairs_ok": bool(n_ok == n_all), "pairs_converged": n_conv, "pairs_run": n_all,
+                    "api": "apd_batch_align (host AoS clouds in, poses out)"},
+            "e2e_packed": {"value": packed_value, "unit": UNIT, "h2d_bytes_per_step": h2d_packed, "d2h_bytes_per_step": d2h,
+                           "layout": "packed float4 {x,y,z,label} in page-locked memory (no staging pass)"},
+            "eager": eager,
+            "parity_vs_cpu": parity,
+            "mean_outer_iterations": n_iter / max(1, args.pairs),
+            "gpu_launches": int(launches),
+            "host_cpu_ms_per_registration": {"device_resident": round(cpu_dev, 4), "e2e": round(cpu_pcl, 4), "e2e_packed": round(cpu_packed, 4),
+                                             "host_cores": host_cores(),
+                                             "note": "process CPU time of rank 0 (all worker threads, incl. the L2 flush / barrier between steps) per registration"},
+            "kernels": kernels,
+            "clocks": clocks.summary(),
+        })
+        # the step's dominant kernel: the device-resident loop. It is latency / issue bound (0.04 % of DRAM peak), so its
+        # live figure is how full it keeps the GPU; the ncu figures of the same kernel are in profiles/
+        lm_ms = kms.get("lm", [0.0, 0])[0]
+        ctas = 4 if "APD_LM_CLUSTER" not in os.environ else int(os.environ["APD_LM_CLUSTER"])
+        line["loop_kernel"] = {"kernel": "lm_kernel<fp32 maha, 2 CTAs/SM>", "share_of_step_kernel_time": round(lm_ms / tot, 4),
+                               "ms_per_registration": lm_ms / max(1, n_mine), "ctas_per_registration": ctas,
+                               "cta_slot_occupancy": round(lm_ms * ctas / (296.0 * (ms_dev / args.steps)), 4),
+                               "note": "CTA-slot occupancy = sum of loop-kernel time x CTAs / (148 SMs x 2 slots x step time), profiled pass over timed pass; "
+                                       "issue-slot %, L2 GB/s: profiles/r02_ncu_lm_kernel.txt"}
+        del dev_all, flush
         torch.cuda.empty_cache()
-        n = args.roofline_points
-        src, tgt, Tgt = synth.tiled_cloud_pair(4000, n)
-        ds, dt = torch.from_numpy(src).to(dev), torch.from_numpy(tgt).to(dev)
-        g = gorio.FastAPDGICP(local_rank)
-        g.set_params(max_correspondence_distance=2.0)
-        g.set_input_target_device(dt.data_ptr(), n)
-        g.set_input_source_device(ds.data_ptr(), n)
-        T = Tgt.copy()
-        g.set_profiling(True)
-        g.linearize(T)  # builds grids, covariances, correspondences
-        k0 = g.kernel_ms()
-        g.set_profiling(False)
-        for _ in range(3):
-            g.linearize(T)
-            g.compute_error(T)
-        g.set_profiling(True)
-        reps = max(1, args.roofline_reps)
-        for _ in range(reps):
-            g.linearize(T)
-            g.compute_error(T)
-        k = g.kernel_ms()
-        lin_ms = k["linearize"][0] / reps
-        err_ms = k["error"][0] / reps
-        corr_ms = k["corr"][0] / reps
-        achieved = BYTES_PER_POINT_LINEARIZE * n / 1e9 / (lin_ms / 1e3)
-        n_valid = int((g.get_correspondences()[0] >= 0).sum())
-        traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of the same kernel at the same size
-        try:
-            cap = json.load(open(os.path.join(REPO, "profiles", "r01_ncu_linearize.json")))
-            if cap.get("points") == n:
-                kk = cap["linearize_kernel<fp32 maha, H+b+err>"]
-                traffic = kk["dram_bytes_read"] + kk["dram_bytes_write"]
-        except Exception:
-            pass
-        line["roofline"] = {
-            "bound": "hbm", "kernel": "linearize_kernel<fp32 maha, H+b+err>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_ncu_linearize.json (ncu capture, bytes per launch)" if traffic else None,
-            "algorithmic_bytes": BYTES_PER_POINT_LINEARIZE * n, "peak_source": peak_src, "points": n, "matched_points": n_valid,
-            "bytes_per_point": BYTES_PER_POINT_LINEARIZE, "ms_per_launch": lin_ms,
-            "compute_error": {"ms_per_launch": err_ms, "achieved": BYTES_PER_POINT_LINEARIZE * n / 1e9 / (err_ms / 1e3)},
-            "update_correspondences": {"ms_per_launch": corr_ms, "achieved": 148 * n / 1e9 / (corr_ms / 1e3), "bytes_per_point": 148},
-            "grid_build": {"ms_per_cloud": k0["grid"][0] / 2, "launches_per_cloud": k0["grid"][1] // 2},
-            "knn_covariance": {"ms_per_cloud": k0["knn_cov"][0] / 2, "achieved": BYTES_PER_POINT_KNNCOV * n / 1e9 / (k0["knn_cov"][0] / 2 / 1e3),
-                               "bytes_per_point": BYTES_PER_POINT_KNNCOV, "mqueries_per_s": n / 1e6 / (k0["knn_cov"][0] / 2 / 1e3)},
-            "timing": "CUDA events on the handle's stream around each launch; working set 1.28 GB > L2",
-        }
-        g.close()
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.roofline_only:
+    # ---- config C4 on the ranks of this run; at N = 1 also the roofline of the linearize kernel ----
+    if not args.no_c4 and not (args.no_roofline and world == 1 and not only_c4):
+        block, roof = c4_block(args, torch, dist, gorio, synth, rank, local_rank, world, dev, max(5, args.steps), world == 1, peak, peak_src)
+        line["c4"] = block
+        if roof is not None:
+            line["roofline"] = roof
+        if only_c4 or args.roofline_only:
+            line.update({"metric": "APDGICP LM-iteration throughput on one large cloud (source points/s)", "value": block["points_per_s"], "unit": "points/s",
+                         "ms_per_step": block["ms_per_step"], "steps": block["steps"], "scaling": "strong", "higher_is_better": True})
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and host_pairs:
         lib, kind, search, what = load_cpu_impl()
-        lib.apdo_max_threads.restype = ctypes.c_int
         sample = host_pairs[:8]
-        seen, uniq = set(), []
-        for s, t in sample:
-            if s.ctypes.data not in seen:
-                seen.add(s.ctypes.data)
-                uniq.append((s, t))
-        t1, n1 = cpu_registrations(lib, search, uniq[:1], 1)
-        reps = max(3, min(200, int(round(12.0 / max(t1 * len(uniq), 1e-3)))))  # ~12 s of CPU work
-        t_cpu, n_cpu = cpu_registrations(lib, search, uniq, reps)
+        t1, n1 = cpu_registrations(lib, search, sample[:1], 1)
+        reps = max(1, min(50, int(round(12.0 / max(t1 * len(sample), 1e-3)))))  # ~12 s of CPU work
+        t_cpu, n_cpu = cpu_registrations(lib, search, sample, reps)
         line["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": UNIT, "cores": host_cores(), "kind": kind,
-                                "sample": f"{len(uniq)} of the step's pairs x {reps} repetitions ({t_cpu:.1f} s wall); {what}"}
+                                "sample": f"the first {len(sample)} pairs of the batch x {reps} repetitions ({t_cpu:.1f} s wall); {what}"}
 
     if rank == 0:
         print(json.dumps(line), flush=True)

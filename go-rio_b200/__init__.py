@@ -139,6 +139,13 @@ class Batch:
         self._lib.apd_batch_launch_count.restype = ctypes.c_int64
         return self._lib.apd_batch_launch_count(self._b)
 
+    def load_stats(self, reset=True):
+        """see apd_batch_get_load_stats"""
+        st = (ctypes.c_double * 7)()
+        self._lib.apd_batch_get_load_stats(self._b, st, ctypes.c_int32(7), ctypes.c_int32(1 if reset else 0))
+        names = ["registrations", "lm_kernel_ms", "host_set_ms", "host_bbox_wait_ms", "host_enqueue_prep_ms", "host_enqueue_loop_ms", "host_result_wait_ms"]
+        return dict(zip(names, st))
+
     def set_profiling(self, on):
         self._lib.apd_batch_set_profiling(self._b, ctypes.c_int32(1 if on else 0))
 

@@ -218,6 +218,7 @@ struct apd_handle {
   // 4 wait for the result
   double phase_s[5] = {0, 0, 0, 0, 0};
   int64_t phase_n = 0;
+  double lm_kernel_s = 0.0;  // device time of the loop kernels (their own %globaltimer stamps: valid under load, no events needed)
   // CTAs per registration in the device loop (APD_LM_CLUSTER=1|2|4|8|16). A lone registration is latency-bound: 8 CTAs
   // (C2 on B200: lm_kernel 0.42 ms with 4, 0.29 ms with 8); the workers of a batch pool share the SMs: 4.
   int lm_cluster = 8;
@@ -1181,6 +1182,7 @@ int finish_device_align(apd_handle* h, const LmResult* r) {
   }
   h->converged = r->converged != 0;
   h->nr_iterations = r->nr_iterations;
+  if (r->t_end > r->t_begin) h->lm_kernel_s += 1e-9 * (double)(r->t_end - r->t_begin);
   h->lm_lambda = r->lm_lambda;
   h->lm_failed = r->lm_failed != 0;
   if (r->hessian_set) std::memcpy(h->final_H, r->H, sizeof(h->final_H));  // final_hessian_ changes only when a step was accepted
@@ -2054,6 +2056,51 @@ int64_t apd_batch_launch_count(const apd_batch* b) {
   if (b)
     for (auto* h : b->handles) n += h->launches;
   return n;
+}
+
+int apd_batch_get_load_stats(apd_batch* b, double* stats, int32_t n, int32_t reset) {
+  if (!b || !stats || n < 7) return APD_ERR_INVALID;
+  for (int i = 0; i < n; i++) stats[i] = 0.0;
+  for (auto* h : b->handles) {
+    stats[0] += (double)h->phase_n;
+    stats[1] += 1e3 * h->lm_kernel_s;
+    for (int i = 0; i < 5; i++) stats[2 + i] += 1e3 * h->phase_s[i];
+    if (reset) {
+      h->phase_n = 0;
+      h->lm_kernel_s = 0.0;
+      for (int i = 0; i < 5; i++) h->phase_s[i] = 0.0;
+    }
+  }
+  return APD_OK;
+}
+
+// Diagnostic: how many (empty) kernel launches per second this process can issue on `device` from n_threads host threads
+// over n_streams streams. A pool of registrations issues ~11 launches each; this is the ceiling the driver puts on that.
+int apd_debug_launch_rate(int device, int32_t n_streams, int32_t n_threads, int32_t launches_per_thread, double* per_second) {
+  if (!per_second || n_streams < 1 || n_threads < 1 || launches_per_thread < 1) return APD_ERR_INVALID;
+  DeviceGuard dg(device);
+  std::vector<cudaStream_t> st((size_t)n_streams);
+  for (auto& s : st)
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return APD_ERR_CUDA;
+  int64_t dummy = 0;
+  for (auto& s : st) launch_noop(s, &dummy);
+  cudaDeviceSynchronize();
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; t++)
+    th.emplace_back([&, t] {
+      cudaSetDevice(device);
+      int64_t d2 = 0;
+      for (int i = 0; i < launches_per_thread; i++) launch_noop(st[(size_t)((t + (int64_t)i * n_threads) % n_streams)], &d2);
+    });
+  for (auto& t : th) t.join();
+  const double issue_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  cudaDeviceSynchronize();
+  const double total_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (auto& s : st) cudaStreamDestroy(s);
+  per_second[0] = (double)n_threads * launches_per_thread / issue_s;
+  per_second[1] = (double)n_threads * launches_per_thread / total_s;
+  return APD_OK;
 }
 
 int apd_batch_set_profiling(apd_batch* b, int32_t enabled) {

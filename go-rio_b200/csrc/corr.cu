@@ -25,7 +25,7 @@ constexpr int kThreads = 128;
 __device__ __forceinline__ bool slot_of(const ShardTable& sh, int l, int& j, int& o) {
   if (sh.nsub == 1) { j = 0; o = l; }
   else { j = l / sh.chunk; o = l - j * sh.chunk; }
-  return j < sh.nsub && o < sh.count[j];
+  return j < sh.nsub && o < sh.count_of(j);
 }
 
 // ---- pass 1: the search (:176-190). fp32 and index work only: no fp64 state is live, so many warps fit an SM and the
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kThreads) corr_search_kernel(const float4* __r
   const int l = (int)(((size_t)blockIdx.x * kThreads + threadIdx.x) / G);
   int j, o;
   if (!slot_of(sh, l, j, o)) return;
-  const int i = sh.begin[j] + o;
+  const int i = sh.begin_of(j) + o;
   const float4 a = s_spts[i];
   float px, py, pz;
   transform_rn(Tf, a.x, a.y, a.z, px, py, pz);  // :176
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) maha_kernel(const float4* __restrict__ s_
   if (!slot_of(sh, l, j, o)) return;
   const int c = corr[l];
   if (c < 0) return;  // (the reductions never read the matrix of an unmatched point)
-  const int i = sh.begin[j] + o;
+  const int i = sh.begin_of(j) + o;
   const int pos = c & kCorrIndexMask;
   const float4 a = s_spts[i];
   const PoseF Tf = pose_to_f32(T);
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) corr_export_kernel(const float4* __restri
   const int s = blockIdx.x * 256 + threadIdx.x;  // rank-local slot
   int j, o;
   if (!slot_of(sh, s, j, o)) return;
-  const int oi = __float_as_int(s_spts[sh.begin[j] + o].w);
+  const int oi = __float_as_int(s_spts[sh.begin_of(j) + o].w);
   const int c = corr[s];
   if (idx_out) idx_out[oi] = c < 0 ? -1 : __float_as_int(t_spts[c & kCorrIndexMask].w);
   if (sqd_out) sqd_out[oi] = sqd[s];

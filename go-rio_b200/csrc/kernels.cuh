@@ -85,6 +85,10 @@ struct ShardTable {
   int count[kShardSubMax] = {0, 0, 0, 0};
   int plane = 0;  // local slots in all (= stride between the planes of the fp64 Mahalanobis storage)
   __host__ __device__ int slots() const { return nsub * chunk; }
+  // begin / count of chunk j by constant indices: a kernel parameter indexed with a run-time value is copied to local
+  // memory first (the linearize kernel lost 13 % to that)
+  __host__ __device__ __forceinline__ int begin_of(int j) const { return j == 0 ? begin[0] : (j == 1 ? begin[1] : (j == 2 ? begin[2] : begin[3])); }
+  __host__ __device__ __forceinline__ int count_of(int j) const { return j == 0 ? count[0] : (j == 1 ? count[1] : (j == 2 ? count[2] : count[3])); }
 };
 inline ShardTable whole_cloud(int n) {
   ShardTable t;
@@ -165,6 +169,9 @@ void launch_linearize(const CloudDev& src, const CloudDev& tgt, const ShardTable
 // number in every peer's mailbox, wait for all of them) — orders the peer-to-peer copies of the covariance all-gather
 void launch_peer_barrier(const PeerExchange& x, cudaStream_t s, int64_t* launches);
 
+// an empty kernel (launch-rate diagnostic)
+void launch_noop(cudaStream_t s, int64_t* launches);
+
 // ---- lm.cu ---------------------------------------------------------------------
 // The device-resident optimizer loop (LsqRegistration::computeTransformation,
 // reference lsq_registration_impl.hpp:55-173) of one registration per cluster.
@@ -177,6 +184,7 @@ struct LmResult {
   double fitness[3];   // sum d2, n in range, n inliers (only with want_fitness)
   int converged, nr_iterations, lm_failed, n_trace;
   int hessian_set, pad_;  // hessian_set: H holds a final_hessian_ (some step was accepted)
+  unsigned long long t_begin, t_end;  // %globaltimer (ns) when the kernel's first CTA started / just before it published
   unsigned long long seq; // host copy only: LmJob::seq once the header + first trace rows have arrived (written last)
   double trace[kLmTraceRows * 8];
 };

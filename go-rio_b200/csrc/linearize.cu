@@ -104,9 +104,9 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
   auto tile_span = [&](int tile, size_t& gbase, size_t& lbase) -> int {
     const int j = sh.nsub == 1 ? 0 : tile / tpc;
     const int o = (tile - j * tpc) * kTile;
-    gbase = (size_t)sh.begin[j] + o;
+    gbase = (size_t)sh.begin_of(j) + o;
     lbase = (size_t)j * sh.chunk + o;
-    return max(0, min(kTile, sh.count[j] - o));
+    return max(0, min(kTile, sh.count_of(j) - o));
   };
   const int my = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -320,6 +320,12 @@ void launch_linearize(const CloudDev& src, const CloudDev& tgt, const ShardTable
     if (want_hb) launch_one<false, true>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);
     else launch_one<false, false>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);
   }
+  (*launches)++;
+}
+
+__global__ void noop_kernel() {}
+void launch_noop(cudaStream_t s, int64_t* launches) {
+  noop_kernel<<<1, 32, 0, s>>>();
   (*launches)++;
 }
 

@@ -403,6 +403,8 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
   __shared__ LmShared s;
   const int tid = threadIdx.x;
   const bool writer = (rank == 0 && tid == 0);  // the one thread that reports results
+  unsigned long long t_begin = 0;
+  if (writer) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
 
   // this CTA's contiguous slice of the (cell-sorted) source points
   const int per = (job.n_src + (int)C - 1) / (int)C;
@@ -510,6 +512,8 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
     res->lm_failed = z.lm_failed;
     res->n_trace = z.n_rows;
     res->hessian_set = z.h_set;
+    res->t_begin = t_begin;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(res->t_end));
   }
   if (job.host_result && rank == 0) {
     // publish: header and first trace rows to the host (one 8-byte word per thread), then the sequence number

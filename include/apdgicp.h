@@ -275,6 +275,15 @@ APD_API int apd_batch_align(apd_batch* b, const apd_pair* pairs, int32_t n_pairs
 APD_API int apd_batch_align_device(apd_batch* b, const apd_pair* pairs, int32_t n_pairs, int32_t with_fitness,
                            apd_result* results);
 APD_API int64_t apd_batch_launch_count(const apd_batch* b);
+/* What the pool did since the last reset, measured WHILE it runs at full load (no profiling events): stats[0] pooled
+ * registrations, [1] milliseconds of device time summed over their loop kernels (each kernel stamps %globaltimer at its
+ * start and end: x CTAs per registration / (296 CTA slots x wall time) = how full the loop keeps the GPU), [2..6] host
+ * milliseconds spent per phase: set clouds, wait for the bounding boxes, enqueue grids + covariances, enqueue the loop,
+ * wait for the result. n >= 7. */
+APD_API int apd_batch_get_load_stats(apd_batch* b, double* stats, int32_t n, int32_t reset);
+/* diagnostic: empty-kernel launches per second from n_threads host threads over n_streams streams (per_second[0]: issue
+ * rate, [1]: completion rate) — the driver's ceiling on a pool that issues several launches per registration */
+APD_API int apd_debug_launch_rate(int device, int32_t n_streams, int32_t n_threads, int32_t launches_per_thread, double* per_second);
 APD_API int apd_batch_set_profiling(apd_batch* b, int32_t enabled);
 APD_API int apd_batch_get_kernel_ms(apd_batch* b, double* ms /* [APD_K_COUNT] */, int64_t* launches);
 

@@ -32,8 +32,9 @@ def test_shard_pairs_cover_all():
             assert got == list(range(n))
 
 
-def test_bench_gives_every_rank_the_same_work(synth, monkeypatch):
-    """weak scaling = equal work per GPU: every rank of bench.py registers the same scenes, starting at a different one"""
+def test_bench_shards_distinct_scenes_by_pair_index(synth, monkeypatch):
+    """config C3 as bench.py runs it: 4096 pairs, pair i = scene 3000 + i, pair i -> rank i mod N; every scene is generated
+    once, by the rank that registers it"""
     import bench
     calls = []
 
@@ -42,13 +43,17 @@ def test_bench_gives_every_rank_the_same_work(synth, monkeypatch):
         return np.full((2, 4), seed, np.float32), np.full((3, 4), seed, np.float32), None
 
     monkeypatch.setattr(synth, "submap_pair", fake_pair)
-    per_rank = []
-    for rank in range(8):
-        pairs = bench.make_pairs(synth, rank, 512)
-        per_rank.append(sorted(int(s[0, 0]) for s, _ in pairs))
-        assert int(pairs[0][0][0, 0]) == 2000 + rank  # rotated start
-    assert all(p == per_rank[0] for p in per_rank) and set(per_rank[0]) == set(range(2000, 2008))
-    assert sorted(set(calls)) == list(range(2000, 2008))
+    world, total = 8, 64
+    seen = []
+    for rank in range(world):
+        pairs = bench.make_pairs(synth, rank, world, total, procs=1)
+        seeds = [int(s[0, 0]) for s, _ in pairs]
+        assert seeds == [3000 + i for i in range(rank, total, world)]
+        seen += seeds
+    assert sorted(seen) == [3000 + i for i in range(total)] and sorted(calls) == sorted(seen)
+    # fewer distinct scenes (a profiling aid) are cycled
+    pairs = bench.make_pairs(synth, 0, 1, 16, distinct=4, procs=1)
+    assert [int(s[0, 0]) for s, _ in pairs] == [3000 + i % 4 for i in range(16)]
 
 
 _WORKER = r'''
