@@ -132,7 +132,10 @@ struct Cloud {
   unsigned long long staged_seq = 0;  // ... or: any kernel of the handle with a LATER sequence number has been seen to finish
   bool staged_by_seq = false;
   const float4* ext_pts = nullptr;  // user-owned device cloud (apd_set_*_device)
-  bool bbox_pending = false;        // ... whose bounding box is still on its way back from the device (see finish_bboxes)
+  bool bbox_pending = false;        // ... whose bounding box is not known on the host yet (see finish_bboxes)
+  bool bbox_launched = false;       // ... the kernel that reduces it has been launched (it is only launched when a grid is sized on the host:
+                                    // the fused registration kernel sizes its grids itself)
+  const void* host_packed = nullptr;  // packed float4 cloud in the caller's page-locked memory whose box has not been computed (same reason)
   unsigned long long bbox_seq = 0;  // ... and the sequence number that announces it
   GridDesc g{};
   int ncells = 0;
@@ -147,7 +150,7 @@ struct Cloud {
   bool cov_lazy = false;
   bool flags_fresh = false;  // the grid build that just ran cleared cov_flag
   int lazy_k = 0, lazy_reg = 0;
-  void drop_derived() { grid_valid = cov_valid = geo_valid = cov_lazy = bbox_pending = false; }
+  void drop_derived() { grid_valid = cov_valid = geo_valid = cov_lazy = bbox_pending = bbox_launched = false; host_packed = nullptr; }
   CloudDev view() const {
     CloudDev c;
     c.n = n;
@@ -226,6 +229,11 @@ struct apd_handle {
   // CTAs per SM (a batch pool: +27 % registrations/s). Same arithmetic either way. APD_LM_MINB=1|2.
   int lm_min_blocks = 1;
   bool lm_failed = false;
+  // The fused registration kernel (lm.cu + prep.cuh): bounding boxes, grid sizing, both grids and the source covariances
+  // inside the loop kernel's launch — one launch per registration, no wait for the boxes. APD_FUSED=0: the separate kernels.
+  bool fused = true;
+  int fused_inflight = 0;       // prep bits of the loop launch in flight (0: unfused)
+  int fused_max_target = 131072;  // larger targets are built by the GPU-wide kernels (the prologue runs on the loop's few SMs)
   // wait for the result of the device loop on a blocking-sync event instead of spinning on the stream: the batch
   // context runs more host threads than it needs cores for (set by apd_batch_create; APD_BLOCKING_SYNC=0|1 overrides)
   bool blocking_wait = false;
@@ -495,8 +503,19 @@ int ensure_corr_buffers(apd_handle* h);
 
 // The bounding boxes of device clouds are reduced on the device (set_cloud_device) and read back here, the first time a
 // grid needs one: ONE wait serves both clouds of a {setInputTarget; setInputSource; align} sequence.
+int launch_bounds_of(apd_handle* h, Cloud& c);
 int finish_bboxes(apd_handle* h) {
+  for (Cloud* c : {&h->src, &h->tgt})
+    if (c->host_packed) {  // a packed host cloud whose box was left for later (the caller's buffer is still valid: same call)
+      bounds_of_packed(c->host_packed, c->n, c->bbox);
+      c->host_packed = nullptr;
+    }
   if (!h->src.bbox_pending && !h->tgt.bbox_pending) return APD_OK;
+  for (Cloud* c : {&h->src, &h->tgt})
+    if (c->bbox_pending && !c->bbox_launched) {
+      const int rc = launch_bounds_of(h, *c);
+      if (rc != APD_OK) return rc;
+    }
   const auto t_wait0 = std::chrono::steady_clock::now();
   struct Acc {
     apd_handle* h;
@@ -517,6 +536,7 @@ int finish_bboxes(apd_handle* h) {
       std::memcpy(&c->bbox[a], &u, 4);
     }
     c->bbox_pending = false;
+    c->bbox_launched = false;
   }
   return APD_OK;
 }
@@ -695,6 +715,67 @@ int ensure_covariances_for_loop(apd_handle* h) {
     t.lazy_reg = h->params.regularization;
     t.geo_valid = false;
   }
+  return APD_OK;
+}
+
+// Which parts of the preparation the fused registration kernel takes over for the clouds as they are now: bit 0 the
+// source's grid + covariances, bit 1 the target's grid; 0: nothing (everything is ready, or the case is not the fused
+// kernel's: the separate kernels run). The fused kernel needs the target's covariances either valid already or computed
+// on demand inside the loop, i.e. the conditions of ensure_covariances_for_loop.
+int fused_prep_bits(const apd_handle* h) {
+  if (!h->fused || !use_device_loop(h) || !h->src.present || !h->tgt.present) return 0;
+  const Cloud& s = h->src;
+  const Cloud& t = h->tgt;
+  const int k = h->params.k_correspondences;
+  if (k < 1 || k > 32 || s.n < k || t.n < k || t.n > h->fused_max_target || h->knn_mode == 2) return 0;
+  const bool src_ready = s.grid_valid && s.cov_valid && s.geo_valid && s.geo_variant == h->params.variant;
+  if (!src_ready && s.cov_valid) return 0;  // covariances given by the caller (setSourceCovariances): only the weights are missing
+  const int tk = t.cov_lazy ? t.lazy_k : k;
+  const bool lazy_ok = tk >= 1 && tk <= 32 && t.n >= tk &&
+                       (t.cov_lazy || h->lazy_mode == 1 || (h->lazy_mode < 0 && h->pooled && (long long)t.n >= (long long)h->lazy_min_ratio * s.n));
+  if (!t.cov_valid && !lazy_ok) return 0;
+  if (t.cov_valid && !t.grid_valid) return 0;
+  const int bits = (src_ready ? 0 : 1) | (t.grid_valid ? 0 : 2);
+  return bits;
+}
+
+// buffers + cloud state for a fused launch with prep bits `bits` (the counterpart of ensure_covariances_for_loop)
+int prepare_fused(apd_handle* h, int bits) {
+  Cloud& s = h->src;
+  Cloud& t = h->tgt;
+  const int k = h->params.k_correspondences;
+  const double s_cpp = h->cells_per_point > 0.0 ? h->cells_per_point : 4.0, t_cpp = s_cpp;
+  if (bits & 1) {
+    const size_t n = (size_t)s.n;
+    APD_CUDA(h, s.spts.ensure(n * sizeof(float4)));
+    APD_CUDA(h, s.label.ensure(n * sizeof(float)));
+    APD_CUDA(h, s.inv_perm.ensure(n * sizeof(int)));
+    APD_CUDA(h, s.cell_start.ensure((size_t)grid_cell_capacity(s.n, s_cpp) * sizeof(uint32_t)));
+    APD_CUDA(h, s.cov.ensure(n * 6 * sizeof(double)));
+    APD_CUDA(h, s.geo.ensure(n * sizeof(float)));
+    APD_CUDA(h, s.geo64.ensure(n * sizeof(double)));
+  }
+  if (bits & 2) {
+    const size_t n = (size_t)t.n;
+    APD_CUDA(h, t.spts.ensure(n * sizeof(float4)));
+    APD_CUDA(h, t.label.ensure(n * sizeof(float)));
+    APD_CUDA(h, t.inv_perm.ensure(n * sizeof(int)));
+    APD_CUDA(h, t.cell_start.ensure((size_t)grid_cell_capacity(t.n, t_cpp) * sizeof(uint32_t)));
+  }
+  APD_CUDA(h, h->work.ensure(3 * ((size_t)s.n + (size_t)t.n) * sizeof(uint32_t) + 512));
+  if (!t.cov_valid) {  // target covariances on demand
+    APD_CUDA(h, t.cov.ensure((size_t)t.n * 6 * sizeof(double)));
+    APD_CUDA(h, t.cov_flag.ensure((size_t)t.n));
+    if (!(bits & 2) && !t.cov_lazy) APD_CUDA(h, cudaMemsetAsync(t.cov_flag.p, 0, (size_t)t.n, h->stream));  // (a grid built in the kernel clears them on its way)
+    if (!t.cov_lazy) {
+      t.cov_lazy = true;
+      t.lazy_k = k;
+      t.lazy_reg = h->params.regularization;
+      t.geo_valid = false;
+    }
+  }
+  const int kmax = std::max(k, t.cov_lazy ? t.lazy_k : k);
+  APD_CUDA(h, h->nbuf.ensure((size_t)std::max(s.n, 1) * (kmax + 1) * sizeof(int32_t)));
   return APD_OK;
 }
 
@@ -965,11 +1046,12 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
   if (h->pooled && n > 0 && stride == 16 && xyz_off == 0 && label_off == 12) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, pts) == cudaSuccess && at.type == cudaMemoryTypeHost) {
-      bounds_of_packed(pts, n, c.bbox);
+      c.host_packed = pts;  // (its box is computed only if a grid is sized on the host: finish_bboxes)
       APD_CUDA(h, c.pts.ensure((size_t)n * sizeof(float4)));
       APD_CUDA(h, cudaMemcpyAsync(c.pts.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
       c.ext_pts = nullptr;
       c.bbox_pending = false;
+      c.bbox_launched = false;
       c.n = n;
       c.present = true;
       c.key = key;
@@ -1011,6 +1093,8 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
   }
   c.ext_pts = nullptr;
   c.bbox_pending = false;
+  c.bbox_launched = false;
+  c.host_packed = nullptr;
   c.n = n;
   c.present = true;
   c.key = key;
@@ -1023,24 +1107,33 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
   return APD_OK;
 }
 
-int set_cloud_device(apd_handle* h, Cloud& c, const void* d_xyzl, int32_t n) {
-  if (!d_xyzl || n < 0) return fail(h, APD_ERR_INVALID, "bad cloud arguments");
-  DeviceGuard dg(h->device);
+// the bounding box of a device-resident cloud: reduced by a kernel that publishes it into pinned host memory
+int launch_bounds_of(apd_handle* h, Cloud& c) {
   int rc = ensure_small(h);
   if (rc != APD_OK) return rc;
   const int slot = (&c == &h->src) ? 48 : 52;  // per-cloud slots: both boxes may be in flight at once
   unsigned int* d_state = reinterpret_cast<unsigned int*>(h->small.as<double>() + slot);  // prepared by ensure_small
   unsigned int* enc = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(h->h_small.p) + slot);
   c.bbox_seq = ++h->seq;
+  const float4* d_xyzl = c.ext_pts ? c.ext_pts : c.pts.as<const float4>();
   if (h->zero_copy) {
-    launch_bounds(reinterpret_cast<const float4*>(d_xyzl), n, d_state, h->h_small_dev + 2 * slot, c.bbox_seq, h->stream, &h->launches);
+    launch_bounds(d_xyzl, c.n, d_state, h->h_small_dev + 2 * slot, c.bbox_seq, h->stream, &h->launches);
   } else {  // the kernel publishes into device scratch (small[56..59]), copied back in stream order
     unsigned int* d_out = reinterpret_cast<unsigned int*>(h->small.as<double>() + 56);
-    launch_bounds(reinterpret_cast<const float4*>(d_xyzl), n, d_state, d_out, c.bbox_seq, h->stream, &h->launches);
+    launch_bounds(d_xyzl, c.n, d_state, d_out, c.bbox_seq, h->stream, &h->launches);
     APD_CUDA(h, cudaMemcpyAsync(enc, d_out, 6 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
   }
   APD_CUDA(h, cudaGetLastError());
-  c.bbox_pending = true;
+  c.bbox_launched = true;
+  return APD_OK;
+}
+
+int set_cloud_device(apd_handle* h, Cloud& c, const void* d_xyzl, int32_t n) {
+  if (!d_xyzl || n < 0) return fail(h, APD_ERR_INVALID, "bad cloud arguments");
+  DeviceGuard dg(h->device);
+  c.bbox_pending = true;     // (its box is reduced when — and if — a grid is sized on the host: finish_bboxes)
+  c.bbox_launched = false;
+  c.host_packed = nullptr;
   c.ext_pts = reinterpret_cast<const float4*>(d_xyzl);
   h->corr_warm = false;
   c.n = n;
@@ -1146,7 +1239,7 @@ bool use_device_loop(const apd_handle* h) {
   return !h->params.host_loop && !h->sharded() && !h->params.lm_debug_print && h->src.n <= kLmMaxSource;
 }
 
-LmJob lm_job(apd_handle* h, const hm::Pose& x0) {
+LmJob lm_job(apd_handle* h, const hm::Pose& x0, int prep_bits = 0) {
   const CloudDev s = h->src.view(), t = h->tgt.view();
   LmJob j{};
   j.s_spts = s.spts; j.s_label = s.label; j.s_cov = s.cov; j.s_geo = s.geo; j.s_geo64 = s.geo64;
@@ -1160,6 +1253,27 @@ LmJob lm_job(apd_handle* h, const hm::Pose& x0) {
     j.guess[9 + r] = x0(r, 3);
   }
   j.result = h->lm_result.as<LmResult>();
+  j.n_tgt = t.n;
+  j.sg = s.g;
+  j.s_ncells = s.ncells;
+  j.t_ncells = t.ncells;
+  if (prep_bits) {  // the kernel builds (some of) the grids and the source covariances itself
+    j.prep = prep_bits;
+    j.s_pts = s.pts;
+    j.t_pts = t.pts;
+    j.s_inv_perm = s.inv_perm;
+    j.t_inv_perm = t.inv_perm;
+    j.s_cell_start = s.cell_start;
+    j.s_cell_cap = (int)std::min<size_t>(h->src.cell_start.cap / sizeof(uint32_t), 0x7fffffff);
+    j.t_cell_cap = (int)std::min<size_t>(h->tgt.cell_start.cap / sizeof(uint32_t), 0x7fffffff);
+    j.s_scratch = h->work.as<uint32_t>();
+    j.t_scratch = h->work.as<uint32_t>() + 3 * (size_t)s.n;
+    j.s_cells_per_point = j.t_cells_per_point = h->cells_per_point > 0.0 ? h->cells_per_point : 4.0;
+    j.s_k = h->params.k_correspondences;
+    j.s_reg = h->params.regularization;
+    j.gicp = h->params.variant == APD_VARIANT_GICP ? 1 : 0;
+    j.nb = h->nbuf.as<int32_t>();
+  }
   if (h->tgt.cov_lazy && !h->tgt.cov_valid) {  // target covariances on demand
     j.t_cov_flag = h->tgt.cov_flag.as<unsigned char>();
     j.t_cov_rw = t.cov;
@@ -1175,6 +1289,29 @@ constexpr size_t kLmHeadBytes = offsetof(LmResult, trace) + (size_t)kLmTraceHead
 
 // unpack a finished LmResult header (host copy) into the handle
 int finish_device_align(apd_handle* h, const LmResult* r) {
+  if (h->fused_inflight) {
+    const int bits = h->fused_inflight;
+    h->fused_inflight = 0;
+    if (r->prep_status != 0) return APD_ERR_UNSUPPORTED;  // (a grid did not fit: do_align / the pool run the unfused path)
+    // the kernel sized and built the grids: take their descriptors, and what is now valid on the device
+    if (bits & 1) {
+      h->src.g = r->grid[0];
+      h->src.ncells = r->ncells[0];
+      h->src.grid_valid = h->src.cov_valid = h->src.geo_valid = true;
+      h->src.geo_variant = h->params.variant;
+      h->src.cov_lazy = false;
+    }
+    if (bits & 2) {
+      h->tgt.g = r->grid[1];
+      h->tgt.ncells = r->ncells[1];
+      h->tgt.grid_valid = true;
+    }
+    for (Cloud* c : {&h->src, &h->tgt})
+      if (c->grid_valid) {  // (the box was never needed on the host)
+        c->host_packed = nullptr;
+        if (!c->bbox_launched) c->bbox_pending = false;
+      }
+  }
   hm::Pose x0 = hm::Pose::identity();
   for (int a = 0; a < 3; a++) {
     for (int c = 0; c < 3; c++) x0(a, c) = r->pose[a * 3 + c];
@@ -1205,7 +1342,7 @@ int finish_device_align(apd_handle* h, const LmResult* r) {
 }
 
 // LsqRegistration::computeTransformation (lsq :55-80) in one launch (lm.cu)
-int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg) {
+int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg, int prep_bits = 0) {
   int rc = ensure_corr_buffers(h);
   if (rc != APD_OK) return rc;
   if (!h->lm_result.p) APD_CUDA(h, h->lm_result.ensure(sizeof(LmResult)));
@@ -1217,7 +1354,8 @@ int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg)
     else h->zero_copy = false;
   }
   const hm::Pose x0 = guess ? hm::from_colmajor_f32(guess) : hm::Pose::identity();  // lsq :56
-  LmJob job = lm_job(h, x0);
+  LmJob job = lm_job(h, x0, prep_bits);
+  h->fused_inflight = prep_bits;
   job.seq = ++h->seq;
   job.host_result = h->zero_copy ? h->h_lm_dev : nullptr;
   {
@@ -1234,7 +1372,9 @@ int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg)
 int begin_device_align(apd_handle* h, const float* guess) {
   const auto t_a = std::chrono::steady_clock::now();
   const double bbox_before = h->phase_s[1];
-  int rc = ensure_covariances_for_loop(h);  // FastAPDGICP::computeTransformation (:148-157)
+  // FastAPDGICP::computeTransformation (:148-157): the covariances — by the separate kernels, or (prep_bits) inside the loop's launch
+  const int prep_bits = fused_prep_bits(h);
+  int rc = prep_bits ? prepare_fused(h, prep_bits) : ensure_covariances_for_loop(h);
   if (rc != APD_OK) return rc;
   const auto t_b = std::chrono::steady_clock::now();
   h->phase_s[2] += std::chrono::duration<double>(t_b - t_a).count() - (h->phase_s[1] - bbox_before);
@@ -1245,7 +1385,7 @@ int begin_device_align(apd_handle* h, const float* guess) {
     cfg.inlier_sq_thr = h->fuse_inlier_sq_thr;
   }
   h->pending_fitness = cfg.want_fitness != 0;
-  rc = enqueue_device_align(h, guess, cfg);
+  rc = enqueue_device_align(h, guess, cfg, prep_bits);
   h->phase_s[3] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_b).count();
   return rc;
 }
@@ -1272,8 +1412,16 @@ int end_device_align(apd_handle* h) {
 
 int do_align(apd_handle* h, const float* guess) {
   if (use_device_loop(h)) {
-    const int rc = begin_device_align(h, guess);
-    return rc != APD_OK ? rc : end_device_align(h);
+    int rc = begin_device_align(h, guess);
+    if (rc == APD_OK) rc = end_device_align(h);
+    if (rc == APD_ERR_UNSUPPORTED && h->fused) {  // the fused kernel declined (a grid larger than its arrays): the separate kernels
+      h->fused = false;
+      h->tgt.cov_lazy = h->tgt.cov_lazy && h->tgt.grid_valid;
+      rc = begin_device_align(h, guess);
+      if (rc == APD_OK) rc = end_device_align(h);
+      h->fused = true;
+    }
+    return rc;
   }
   int rc = ensure_covariances(h);  // FastAPDGICP::computeTransformation (:148-157)
   if (rc != APD_OK) return rc;
@@ -1414,6 +1562,7 @@ int apd_create(int device, apd_handle** out) {
   if (const char* e = std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = std::atoi(e);
   if (const char* e = std::getenv("APD_LAZY_TARGET_COV")) h->lazy_mode = std::strcmp(e, "auto") == 0 ? -1 : (std::atoi(e) != 0 ? 1 : 0);
   if (const char* e = std::getenv("APD_ZERO_COPY")) h->zero_copy = std::atoi(e) != 0;
+  if (const char* e = std::getenv("APD_FUSED")) h->fused = std::atoi(e) != 0;
   if (const char* e = std::getenv("APD_CORR_MODE")) h->corr_lanes = e[0] == 'w' ? 8 : (e[0] == 'l' ? 1 : 0);
   if (const char* e = std::getenv("APD_CORR_LANES")) {
     const int v = std::atoi(e);
@@ -1489,7 +1638,8 @@ int apd_swap_source_and_target(apd_handle* h) {  // :89-98
   if (!h) return APD_ERR_INVALID;
   {
     DeviceGuard dg(h->device);
-    const int rc = finish_bboxes(h);  // (the read-back slots belong to the roles, not to the clouds)
+    // (the read-back slots belong to the roles, not to the clouds: a box in flight is collected before the roles change)
+    const int rc = (h->src.bbox_launched || h->tgt.bbox_launched) ? finish_bboxes(h) : APD_OK;
     if (rc != APD_OK) return rc;
   }
   std::swap(h->src, h->tgt);
@@ -1815,12 +1965,20 @@ void slot_begin(apd_batch* b, PoolSlot& sl, int i) {
     return;
   }
   DeviceGuard dg(h->device);
-  if (h->src.bbox_pending || h->tgt.bbox_pending) {
+  if (fused_prep_bits(h) == 0 && (h->src.bbox_pending || h->tgt.bbox_pending)) {
+    // the grids are sized on the host: reduce the boxes of the device clouds and come back when they have arrived
+    for (Cloud* c : {&h->src, &h->tgt})
+      if (c->bbox_pending && !c->bbox_launched) rc = rc != APD_OK ? rc : launch_bounds_of(h, *c);
+    if (rc != APD_OK) {
+      batch_fill_result(b, h, i, rc);
+      sl.state = kSlotIdle;
+      return;
+    }
     sl.state = kSlotBbox;
     sl.since = std::chrono::steady_clock::now();
     return;
   }
-  slot_enqueue(b, sl);
+  slot_enqueue(b, sl);  // (the fused kernel sizes its grids itself: one launch, no wait for the boxes)
 }
 
 // a slot has been waiting for 20 ms: make sure its stream is still alive (a failed launch or a faulting kernel publishes nothing)
@@ -1886,7 +2044,12 @@ void batch_worker(apd_batch* b, int wi) {
           case kSlotResult:
             if (result_arrived(h)) {
               DeviceGuard dg(h->device);
-              const int rc = end_device_align(h);
+              int rc = end_device_align(h);
+              if (rc == APD_ERR_UNSUPPORTED && h->fused) {  // the fused kernel declined this pair (a grid larger than its arrays)
+                h->fused = false;
+                rc = apd_align(h, b->pairs[sl.pair].guess, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+                h->fused = true;
+              }
               batch_fill_result(b, h, sl.pair, rc);
               sl.state = kSlotIdle;
               progressed = true;

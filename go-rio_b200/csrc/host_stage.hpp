@@ -102,46 +102,6 @@ inline void bounds_of_packed(const void* pts, int n, float bbox[6]) {
   }
 }
 
-// Grid sizing: cell edge so that the bounding box holds ~cells_per_point (4) * n
-// cells (radar clouds live on surfaces, so occupied cells hold several points),
-// at most 2048 cells per axis (bounds the fp32 cell-coordinate error the search
-// margin covers) and 2^28 cells in total.
-inline void size_grid(const float bbox[6], int n, double cells_per_point, GridDesc& g, int& ncells) {
-  double ext[3];
-  for (int a = 0; a < 3; a++) {
-    ext[a] = (double)bbox[3 + a] - (double)bbox[a];
-    if (!(ext[a] > 0.0) || !std::isfinite(ext[a])) ext[a] = 0.0;
-  }
-  const double emax = std::max(std::max(ext[0], ext[1]), std::max(ext[2], 1e-3));
-  const double target = std::max(64.0, cells_per_point * (double)n);
-  double vol = 1.0;
-  for (int a = 0; a < 3; a++) vol *= std::max(ext[a], emax * 1e-3);
-  double cell = std::cbrt(vol / target);
-  cell = std::max(cell, emax / 2040.0);
-  long long d[3];
-  for (int iter = 0; iter < 200; iter++) {
-    long long tot = 1;
-    bool too_wide = false;
-    for (int a = 0; a < 3; a++) {
-      d[a] = (long long)std::floor(ext[a] / cell) + 1;
-      if (d[a] > 2048) too_wide = true;
-      tot *= d[a];
-    }
-    if (!too_wide && (double)tot <= 2.0 * target && tot <= (1ll << 28)) break;
-    cell *= 1.2599210498948732;  // 2^(1/3)
-  }
-  g.ox = bbox[0];
-  g.oy = bbox[1];
-  g.oz = bbox[2];
-  g.inv_cell = (float)(1.0 / cell);
-  g.cell = (float)(1.0 / (double)g.inv_cell);
-  // dims from the SAME fp32 expression the kernels use, so the max corner maps inside
-  auto dim = [&](float mx, float o) { return (int)std::floor((mx - o) * g.inv_cell) + 1; };
-  g.nx = std::max(1, dim(bbox[3], g.ox));
-  g.ny = std::max(1, dim(bbox[4], g.oy));
-  g.nz = std::max(1, dim(bbox[5], g.oz));
-  ncells = g.nx * g.ny * g.nz;
-}
-
+// (grid sizing: grid_desc.hpp — shared with the device)
 
 }  // namespace apd

@@ -185,6 +185,11 @@ struct LmResult {
   int converged, nr_iterations, lm_failed, n_trace;
   int hessian_set, pad_;  // hessian_set: H holds a final_hessian_ (some step was accepted)
   unsigned long long t_begin, t_end;  // %globaltimer (ns) when the kernel's first CTA started / just before it published
+  // fused prologue (LmJob::prep): the grids the kernel chose, for the host's later calls on the same clouds
+  GridDesc grid[2];    // {source, target}
+  int ncells[2];
+  int prep_status;     // 0 ok; 1 a grid did not fit its arrays: nothing was registered, the host takes the unfused path
+  int pad2_;
   unsigned long long seq; // host copy only: LmJob::seq once the header + first trace rows have arrived (written last)
   double trace[kLmTraceRows * 8];
 };
@@ -209,6 +214,22 @@ struct LmJob {
   const float4* t_pts;        // target in ORIGINAL order (the covariance gathers its neighbours there)
   int32_t* nb;                // [n_src][k] + [n_src] scratch: neighbour ids between the search pass and the covariance pass, work list
   int k, reg;                 // k_correspondences_, regularization_method_
+  // Fused prologue (prep != 0; prep.cuh): the kernel is handed the RAW clouds and builds what the loop needs itself —
+  // bit 0: the source's grid + covariances, bit 1: the target's grid (its covariances come on demand). The arrays above
+  // are then outputs of the prologue as well; tg is an output when bit 1 is set.
+  int prep;
+  int n_tgt;
+  const float4* s_pts;        // source in ORIGINAL order (t_pts: the target)
+  int* s_inv_perm; int* t_inv_perm;
+  uint32_t* s_cell_start;     // [s_cell_cap]; t_cell_start: [t_cell_cap]
+  int s_cell_cap, t_cell_cap;
+  uint32_t* s_scratch;        // [3 n_src]: keys, ranks, tmp of the grid build; t_scratch: [3 n_tgt]
+  uint32_t* t_scratch;
+  double s_cells_per_point, t_cells_per_point;
+  int s_k, s_reg;             // the source's covariance parameters (the target's: k, reg)
+  int gicp;                   // FastGICP: unit weights — the geometric weights are written as zeros
+  GridDesc sg;                // the source's grid when the prologue does not build it (prep bit 0 clear), for the result
+  int s_ncells, t_ncells;     // ... and the cell counts of grids that are not rebuilt
 };
 struct LmConfig {
   int max_iterations, optimizer, lm_max_iterations, maha_fp64, want_fitness;

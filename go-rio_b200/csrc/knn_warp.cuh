@@ -90,7 +90,7 @@ __device__ __forceinline__ void kbest_flush(KBest& s, int lane, int k) {
 // Warp-wide candidate scan. Every lane passes one segment [b, b+cnt) of the
 // cell-sorted point array (cnt may be 0). The segments are flattened so that
 // all 32 lanes test candidates even when segments are short (sparse cells).
-__device__ __forceinline__ void scan_segments(const float4* __restrict__ spts, float qx, float qy, float qz, int lane, int k,
+__device__ __forceinline__ void scan_segments(const float4* spts, float qx, float qy, float qz, int lane, int k,
                                               int b, int cnt, KBest& s) {
   int incl = cnt;
 #pragma unroll
@@ -136,7 +136,7 @@ __device__ __forceinline__ void scan_segments(const float4* __restrict__ spts, f
 // (d2, original index) key per lane, ascending: lanes 0..k-1 hold the answer. kbuf: 32 keys of shared memory owned by
 // this warp. Replaces the nearestKSearch of reference fast_apdgicp_impl.hpp:364.
 // knn_warp_query_at: the same for an arbitrary query point q (not necessarily a point of the cloud).
-__device__ __forceinline__ unsigned long long knn_warp_query_at(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start,
+__device__ __forceinline__ unsigned long long knn_warp_query_at(const float4* spts, const uint32_t* cell_start,
                                                                 const GridDesc& g, int k, const float4 q, int lane, unsigned long long* kbuf) {
   const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
   const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
@@ -225,7 +225,7 @@ __device__ __forceinline__ unsigned long long knn_warp_query_at(const float4* __
   }
   return st.list;
 }
-__device__ __forceinline__ unsigned long long knn_warp_query(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start,
+__device__ __forceinline__ unsigned long long knn_warp_query(const float4* spts, const uint32_t* cell_start,
                                                              const GridDesc& g, int k, int w, int lane, unsigned long long* kbuf) {
   return knn_warp_query_at(spts, cell_start, g, k, spts[w], lane, kbuf);
 }

@@ -22,6 +22,7 @@
 #include "host_math.hpp"
 #include "knn_warp.cuh"
 #include "point_math.cuh"
+#include "prep.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -399,12 +400,62 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned C = cluster.num_blocks();
   const unsigned rank = cluster.block_rank();
-  const LmJob job = jobs ? jobs[blockIdx.x / C] : one;
+  LmJob job = jobs ? jobs[blockIdx.x / C] : one;
   __shared__ LmShared s;
   const int tid = threadIdx.x;
   const bool writer = (rank == 0 && tid == 0);  // the one thread that reports results
   unsigned long long t_begin = 0;
   if (writer) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+
+  // ---- fused prologue: from the raw clouds to grids + source covariances, inside this launch (prep.cuh) ----
+  int s_ncells = job.s_ncells, t_ncells = job.t_ncells;
+  GridDesc s_grid = job.sg;
+  if (job.prep) {
+    __shared__ prep::PrepShared ps;
+    const int gt = (int)rank * kLmThreads + tid, GT = (int)C * kLmThreads;
+    const int first = (job.prep & 1) ? 0 : 1;  // clouds [first, last) are built: 0 source, 1 target
+    const int last = (job.prep & 2) ? 2 : 1;
+    const float4* const pts[2] = {job.s_pts, job.t_pts};
+    const int np[2] = {(job.prep & 1) ? job.n_src : 0, (job.prep & 2) ? job.n_tgt : 0};
+    prep::bounds_phase(cluster, ps, pts, np, gt, GT);
+    if (tid == 0) {
+      ps.status = 0;
+      ps.grid[0] = job.sg; ps.ncells[0] = job.s_ncells;
+      ps.grid[1] = job.tg; ps.ncells[1] = job.t_ncells;
+      for (int c = first; c < last; c++) {
+        float bbox[6];
+        for (int a = 0; a < 6; a++) bbox[a] = prep::ord2f(ps.box[c][a]);
+        size_grid(bbox, c == 0 ? job.n_src : job.n_tgt, c == 0 ? job.s_cells_per_point : job.t_cells_per_point, ps.grid[c], ps.ncells[c]);
+        if (ps.ncells[c] + 1 > (c == 0 ? job.s_cell_cap : job.t_cell_cap)) ps.status = 1;
+      }
+    }
+    __syncthreads();
+    s_grid = ps.grid[0]; s_ncells = ps.ncells[0];
+    job.tg = ps.grid[1]; t_ncells = ps.ncells[1];
+    if (ps.status != 0) {  // (uniform over the cluster: every CTA computed the same grids from the same boxes)
+      if (writer) {
+        job.result->prep_status = 1;
+        if (job.host_result) {
+          job.host_result->prep_status = 1;
+          __threadfence_system();
+          *reinterpret_cast<volatile unsigned long long*>(&job.host_result->seq) = job.seq;
+        }
+      }
+      cluster.sync();
+      return;
+    }
+    prep::GridJob gj[2];
+    gj[0] = prep::GridJob{job.s_pts, job.n_src, job.s_cell_start, job.s_cell_cap, job.s_scratch, job.s_scratch + job.n_src,
+                          job.s_scratch + 2 * (size_t)job.n_src, const_cast<float4*>(job.s_spts), const_cast<float*>(job.s_label), job.s_inv_perm,
+                          nullptr};
+    gj[1] = prep::GridJob{job.t_pts, job.n_tgt, const_cast<uint32_t*>(job.t_cell_start), job.t_cell_cap, job.t_scratch, job.t_scratch + job.n_tgt,
+                          job.t_scratch + 2 * (size_t)job.n_tgt, const_cast<float4*>(job.t_spts), const_cast<float*>(job.t_label), job.t_inv_perm,
+                          job.t_cov_flag};
+    if (first < last) prep::grids_phase(cluster, ps, gj, first, last, gt, GT);
+    if (job.prep & 1)
+      prep::source_cov_phase(cluster, job.s_pts, job.s_spts, job.s_cell_start, s_grid, job.n_src, job.s_k, job.s_reg, job.gicp, job.nb,
+                             const_cast<double*>(job.s_cov), const_cast<float*>(job.s_geo), const_cast<double*>(job.s_geo64), s.kbuf[tid >> 5], gt, GT);
+  }
 
   // this CTA's contiguous slice of the (cell-sorted) source points
   const int per = (job.n_src + (int)C - 1) / (int)C;
@@ -513,6 +564,9 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
     res->n_trace = z.n_rows;
     res->hessian_set = z.h_set;
     res->t_begin = t_begin;
+    res->grid[0] = s_grid; res->grid[1] = job.tg;
+    res->ncells[0] = s_ncells; res->ncells[1] = t_ncells;
+    res->prep_status = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(res->t_end));
   }
   if (job.host_result && rank == 0) {

@@ -10,10 +10,10 @@ namespace apd {
 constexpr unsigned long long kInfKey = 0xffffffffffffffffull;
 
 // scan one contiguous range of the cell-sorted target points
-__device__ __forceinline__ void scan_range(const float4* __restrict__ spts, int b, int e, float qx, float qy, float qz,
+__device__ __forceinline__ void scan_range(const float4* spts, int b, int e, float qx, float qy, float qz,
                                            unsigned long long& best, int& best_pos) {
   for (int j = b; j < e; j++) {
-    const float4 p = __ldg(&spts[j]);
+    const float4 p = spts[j];
     const unsigned long long key = pack_key(sqdist_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
     if (key < best) {
       best = key;
@@ -64,7 +64,7 @@ __device__ __forceinline__ unsigned nn_group_mask() {
   return (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
 }
 template <int G>
-__device__ __forceinline__ void scan_segments_group(const float4* __restrict__ spts, int b, int cnt, float qx, float qy, float qz,
+__device__ __forceinline__ void scan_segments_group(const float4* spts, int b, int cnt, float qx, float qy, float qz,
                                                     unsigned long long& best, int& best_pos) {
   if (G == 1) {
     scan_range(spts, b, b + cnt, qx, qy, qz, best, best_pos);
@@ -78,7 +78,7 @@ __device__ __forceinline__ void scan_segments_group(const float4* __restrict__ s
     m &= m - 1;
     const int bb = __shfl_sync(gmask, b, src), cc = __shfl_sync(gmask, cnt, src);
     for (int j = bb + sub; j < bb + cc; j += G) {
-      const float4 p = __ldg(&spts[j]);
+      const float4 p = spts[j];
       const unsigned long long key = pack_key(sqdist_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
       if (key < best) {
         best = key;
@@ -102,7 +102,7 @@ __device__ __forceinline__ float row_dist2(const GridDesc& g, int y, int z, floa
 // the best distance is provably final or every unscanned point is farther than the limit.
 // proven2: on return every point that was NOT scanned is at least sqrt(min(proven2, best d2)) away.
 template <int G>
-__device__ __forceinline__ void nn_shells(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
+__device__ __forceinline__ void nn_shells(const float4* spts, const uint32_t* cell_start, const GridDesc& g,
                                           float qx, float qy, float qz, int cx, int cy, int cz, double limit_sq, unsigned long long& best,
                                           int& best_pos, float& proven2) {
   const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
@@ -137,17 +137,17 @@ __device__ __forceinline__ void nn_shells(const float4* __restrict__ spts, const
           if ((double)dyz2 < prune_sq && !(best != kInfKey && dyz2 > __uint_as_float((unsigned)(best >> 32)))) {
             const int row = (z * g.ny + y) * g.nx;
             if (dy > r || dy < -r || dz > r || dz < -r) {  // row outside the scanned cube: its whole x-range
-              b0 = (int)__ldg(&cell_start[row + x0]);
-              c0 = (int)__ldg(&cell_start[row + x1 + 1]) - b0;
+              b0 = (int)cell_start[row + x0];
+              c0 = (int)cell_start[row + x1 + 1] - b0;
             } else {  // row crosses the scanned cube: the two end pieces
               const int xl = min(cx - r - 1, g.nx - 1), xr = max(cx + r + 1, 0);
               if (x0 <= xl) {
-                b0 = (int)__ldg(&cell_start[row + x0]);
-                c0 = (int)__ldg(&cell_start[row + xl + 1]) - b0;
+                b0 = (int)cell_start[row + x0];
+                c0 = (int)cell_start[row + xl + 1] - b0;
               }
               if (xr <= x1) {
-                b1 = (int)__ldg(&cell_start[row + xr]);
-                c1 = (int)__ldg(&cell_start[row + x1 + 1]) - b1;
+                b1 = (int)cell_start[row + xr];
+                c1 = (int)cell_start[row + x1 + 1] - b1;
               }
             }
           }
@@ -165,7 +165,7 @@ __device__ __forceinline__ void nn_shells(const float4* __restrict__ spts, const
 // bounds the search: rows of the cube whose box is farther are skipped, and the shells usually end at once.
 // The result is the same exact nearest neighbour by (d2, original index) with or without the seed.
 template <int G>
-__device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
+__device__ __forceinline__ void nn_search(const float4* spts, const uint32_t* cell_start, const GridDesc& g,
                                           float qx, float qy, float qz, double limit_sq, unsigned long long& best, int& best_pos,
                                           int seed_pos, float& proven2) {
   const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
@@ -175,7 +175,7 @@ __device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const
   best = kInfKey;
   best_pos = -1;
   if (seed_pos >= 0) {
-    const float4 p = __ldg(&spts[seed_pos]);
+    const float4 p = spts[seed_pos];
     best = pack_key(sqdist_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
     best_pos = seed_pos;
   }
@@ -185,8 +185,8 @@ __device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
     {
       const int row = (cz * g.ny + cy) * g.nx;
-      const int b = (int)__ldg(&cell_start[row + x0]);
-      scan_segments_group<G>(spts, sub == 0 ? b : 0, sub == 0 ? (int)__ldg(&cell_start[row + x1 + 1]) - b : 0, qx, qy, qz, best, best_pos);
+      const int b = (int)cell_start[row + x0];
+      scan_segments_group<G>(spts, sub == 0 ? b : 0, sub == 0 ? (int)cell_start[row + x1 + 1] - b : 0, qx, qy, qz, best, best_pos);
       nn_group_min<G>(best, best_pos);
     }
     for (int k0 = 0; k0 < 8; k0 += G) {  // (uniform over the group)
@@ -198,8 +198,8 @@ __device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const
         if (y >= 0 && y < g.ny && z >= 0 && z < g.nz &&
             !(best != kInfKey && row_dist2(g, y, z, qy, qz) > __uint_as_float((unsigned)(best >> 32)))) {
           const int row = (z * g.ny + y) * g.nx;
-          b = (int)__ldg(&cell_start[row + x0]);
-          cnt = (int)__ldg(&cell_start[row + x1 + 1]) - b;
+          b = (int)cell_start[row + x0];
+          cnt = (int)cell_start[row + x1 + 1] - b;
         }
       }
       scan_segments_group<G>(spts, b, cnt, qx, qy, qz, best, best_pos);
@@ -209,7 +209,7 @@ __device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const
   nn_shells<G>(spts, cell_start, g, qx, qy, qz, cx, cy, cz, limit_sq, best, best_pos, proven2);
 }
 template <int G>
-__device__ __forceinline__ void nn_search(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, const GridDesc& g,
+__device__ __forceinline__ void nn_search(const float4* spts, const uint32_t* cell_start, const GridDesc& g,
                                           float qx, float qy, float qz, double limit_sq, unsigned long long& best, int& best_pos) {
   float proven2;
   nn_search<G>(spts, cell_start, g, qx, qy, qz, limit_sq, best, best_pos, -1, proven2);
@@ -249,8 +249,8 @@ __device__ __forceinline__ PoseF pose_to_f32(const PoseD& T) {
 // RCR = (C_B + C_r) + R (C_A + C_r) R^T (:213-215) and its inverse, the per-point
 // Mahalanobis matrix (:217-218). ca_in / cb_in: the regularised covariances of the
 // source point and of its matched target point (symmetric-6).
-__device__ __forceinline__ Sym3 mahalanobis_of(float px, float py, float pz, const double* __restrict__ ca_in,
-                                               const double* __restrict__ cb_in, const PoseD& T, const NoiseParams& np) {
+__device__ __forceinline__ Sym3 mahalanobis_of(float px, float py, float pz, const double* ca_in,
+                                               const double* cb_in, const PoseD& T, const NoiseParams& np) {
   Sym3 cr;  // cov_r (:204-210); FastGICP has none: adding exact zeros below leaves C_A and C_B as they are
 #pragma unroll
   for (int e = 0; e < 6; e++) cr.v[e] = 0.0;
