@@ -141,10 +141,13 @@ class Batch:
 
     def load_stats(self, reset=True):
         """see apd_batch_get_load_stats"""
-        st = (ctypes.c_double * 7)()
-        self._lib.apd_batch_get_load_stats(self._b, st, ctypes.c_int32(7), ctypes.c_int32(1 if reset else 0))
+        st = (ctypes.c_double * 17)()
+        self._lib.apd_batch_get_load_stats(self._b, st, ctypes.c_int32(17), ctypes.c_int32(1 if reset else 0))
         names = ["registrations", "lm_kernel_ms", "host_set_ms", "host_bbox_wait_ms", "host_enqueue_prep_ms", "host_enqueue_loop_ms", "host_result_wait_ms"]
-        return dict(zip(names, st))
+        out = dict(zip(names, st))
+        phases = ["boxes_grids", "source_cov", "nn_search", "lazy_knn", "lazy_cov", "mahalanobis", "sums_solve", "lm_trials", "fitness", "spare"]
+        out["lm_phase_ms"] = {k: st[7 + i] for i, k in enumerate(phases)}  # (zeros unless the library was built with -DAPD_LM_PHASE_TIMING)
+        return out
 
     def set_profiling(self, on):
         self._lib.apd_batch_set_profiling(self._b, ctypes.c_int32(1 if on else 0))

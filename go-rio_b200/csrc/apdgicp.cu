@@ -221,6 +221,7 @@ struct apd_handle {
   // 4 wait for the result
   double phase_s[5] = {0, 0, 0, 0, 0};
   int64_t phase_n = 0;
+  double lm_phase_s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ... by phase (LmResult::phase_ns; diagnostic builds only)
   double lm_kernel_s = 0.0;  // device time of the loop kernels (their own %globaltimer stamps: valid under load, no events needed)
   // CTAs per registration in the device loop (APD_LM_CLUSTER=1|2|4|8|16). A lone registration is latency-bound: 8 CTAs
   // (C2 on B200: lm_kernel 0.42 ms with 4, 0.29 ms with 8); the workers of a batch pool share the SMs: 4.
@@ -1320,6 +1321,7 @@ int finish_device_align(apd_handle* h, const LmResult* r) {
   h->converged = r->converged != 0;
   h->nr_iterations = r->nr_iterations;
   if (r->t_end > r->t_begin) h->lm_kernel_s += 1e-9 * (double)(r->t_end - r->t_begin);
+  for (int i = 0; i < 10; i++) h->lm_phase_s[i] += 1e-9 * (double)r->phase_ns[i];
   h->lm_lambda = r->lm_lambda;
   h->lm_failed = r->lm_failed != 0;
   if (r->hessian_set) std::memcpy(h->final_H, r->H, sizeof(h->final_H));  // final_hessian_ changes only when a step was accepted
@@ -1345,7 +1347,10 @@ int finish_device_align(apd_handle* h, const LmResult* r) {
 int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg, int prep_bits = 0) {
   int rc = ensure_corr_buffers(h);
   if (rc != APD_OK) return rc;
-  if (!h->lm_result.p) APD_CUDA(h, h->lm_result.ensure(sizeof(LmResult)));
+  if (!h->lm_result.p) {
+    APD_CUDA(h, h->lm_result.ensure(sizeof(LmResult)));
+    APD_CUDA(h, cudaMemsetAsync(h->lm_result.p, 0, sizeof(LmResult), h->stream));
+  }
   if (!h->h_lm.p) {
     APD_CUDA(h, h->h_lm.ensure(kLmHeadBytes));
     std::memset(h->h_lm.p, 0, kLmHeadBytes);
@@ -2228,7 +2233,9 @@ int apd_batch_get_load_stats(apd_batch* b, double* stats, int32_t n, int32_t res
     stats[0] += (double)h->phase_n;
     stats[1] += 1e3 * h->lm_kernel_s;
     for (int i = 0; i < 5; i++) stats[2 + i] += 1e3 * h->phase_s[i];
+    for (int i = 0; i < 10 && 7 + i < n; i++) stats[7 + i] += 1e3 * h->lm_phase_s[i];
     if (reset) {
+      for (int i = 0; i < 10; i++) h->lm_phase_s[i] = 0.0;
       h->phase_n = 0;
       h->lm_kernel_s = 0.0;
       for (int i = 0; i < 5; i++) h->phase_s[i] = 0.0;

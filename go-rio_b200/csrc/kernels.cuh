@@ -190,6 +190,10 @@ struct LmResult {
   int ncells[2];
   int prep_status;     // 0 ok; 1 a grid did not fit its arrays: nothing was registered, the host takes the unfused path
   int pad2_;
+  // where the kernel's time went, by phase, as CTA 0 saw it (ns; only filled by a library built with -DAPD_LM_PHASE_TIMING):
+  // 0 boxes + grids, 1 source covariances, 2 1-NN searches, 3 on-demand kNN searches, 4 on-demand covariances,
+  // 5 Mahalanobis matrices, 6 H/b/err sums + reduction + solve, 7 LM trials, 8 fitness tail, 9 (spare)
+  unsigned long long phase_ns[10];
   unsigned long long seq; // host copy only: LmJob::seq once the header + first trace rows have arrived (written last)
   double trace[kLmTraceRows * 8];
 };

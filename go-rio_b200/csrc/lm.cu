@@ -82,6 +82,34 @@ struct LmShared {
   LmSerial ser;
 };
 
+// Phase clock (diagnostic build, -DAPD_LM_PHASE_TIMING): thread 0 of CTA 0 adds the time since the last tick to a phase's
+// counter — after the barrier that ends the phase, so waiting for slower warps / CTAs counts towards the phase
+struct PhaseClock {
+#ifdef APD_LM_PHASE_TIMING
+  unsigned long long last = 0, ns[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  bool on = false;
+  __device__ __forceinline__ void start(bool writer) {
+    on = writer;
+    if (on) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(last));
+  }
+  __device__ __forceinline__ void tick(int i) {
+    if (!on) return;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    ns[i] += now - last;
+    last = now;
+  }
+  __device__ __forceinline__ void store(LmResult* r) const {
+    if (on)
+      for (int i = 0; i < 10; i++) r->phase_ns[i] = ns[i];
+  }
+#else
+  __device__ __forceinline__ void start(bool) {}
+  __device__ __forceinline__ void tick(int) {}
+  __device__ __forceinline__ void store(LmResult*) const {}
+#endif
+};
+
 // acc[NV] of every thread -> s.out[0..NV) = the sum over the whole cluster
 template <int NV>
 __device__ __forceinline__ void cluster_reduce(cg::cluster_group& cluster, LmShared& s, const double* acc, int& phase) {
@@ -154,7 +182,7 @@ __device__ __noinline__ void lazy_target_covariance(const LmJob& job, const int3
 // warm: job.corr / job.sqd hold the previous outer iteration's pass (pose T_prev), which bounds the searches
 template <bool kFp64>
 __device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg, LmShared& smem, const PoseD& T, int base, int cnt, bool warm,
-                                           const PoseD& T_prev) {
+                                           const PoseD& T_prev, PhaseClock& clk) {
   const PoseF Tf = pose_to_f32(T);
   const PoseF Tpf = pose_to_f32(T_prev);
   const int tid = threadIdx.x;
@@ -206,6 +234,7 @@ __device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg
     }
   }
   __syncthreads();
+  clk.tick(2);
   // Target covariances on demand (calculate_covariances(target), :351-411, restricted to the points that are used).
   // The matched target points without a covariance are listed (this CTA's slice of job.nb); pass A, one WARP per listed
   // point: the exact kNN search of the per-cloud kernel (knn_warp.cuh); pass B, one THREAD per listed point: covariance
@@ -233,9 +262,11 @@ __device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg
       if (lane < job.k) job.nb[(size_t)(base + li) * job.k + lane] = (int)(unsigned)(key & 0xffffffffull);
     }
     __syncthreads();
+    clk.tick(3);
     for (int li = tid; li < n_need; li += kLmThreads) lazy_target_covariance(job, job.nb + (size_t)(base + li) * job.k, list[base + li]);
     __threadfence();
     __syncthreads();
+    clk.tick(4);
   }
   // second pass, one THREAD per point: the fp64 noise model and Mahalanobis matrix of the matched points (:194-218). In the
   // search pass only one lane in kLmG holds a result; here all lanes work.
@@ -406,6 +437,8 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
   const bool writer = (rank == 0 && tid == 0);  // the one thread that reports results
   unsigned long long t_begin = 0;
   if (writer) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+  PhaseClock clk;
+  clk.start(writer);
 
   // ---- fused prologue: from the raw clouds to grids + source covariances, inside this launch (prep.cuh) ----
   int s_ncells = job.s_ncells, t_ncells = job.t_ncells;
@@ -452,9 +485,11 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
                           job.t_scratch + 2 * (size_t)job.n_tgt, const_cast<float4*>(job.t_spts), const_cast<float*>(job.t_label), job.t_inv_perm,
                           job.t_cov_flag};
     if (first < last) prep::grids_phase(cluster, ps, gj, first, last, gt, GT);
+    clk.tick(0);
     if (job.prep & 1)
       prep::source_cov_phase(cluster, job.s_pts, job.s_spts, job.s_cell_start, s_grid, job.n_src, job.s_k, job.s_reg, job.gicp, job.nb,
                              const_cast<double*>(job.s_cov), const_cast<float*>(job.s_geo), const_cast<double*>(job.s_geo64), s.kbuf[tid >> 5], gt, GT);
+    clk.tick(1);
   }
 
   // this CTA's contiguous slice of the (cell-sorted) source points
@@ -484,13 +519,15 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
     // ---- linearize(x0) (:224-307) ----
     {
       const PoseD Tx0 = s.T;
-      corr_phase<kFp64>(job, cfg, s, Tx0, base, cnt, it > 0, s.T_corr);
+      corr_phase<kFp64>(job, cfg, s, Tx0, base, cnt, it > 0, s.T_corr, clk);
       __syncthreads();  // the correspondences of this CTA's points are visible to all of its threads; T_corr has been read
+      clk.tick(5);
       if (tid == 0) s.T_corr = Tx0;
       sum_phase<kFp64, true>(job, Tx0, base, cnt, acc);
     }
     cluster_reduce<kReduceVals>(cluster, s, acc, phase);
     if (tid == 0) serial_after_linearize(s, cfg);
+    clk.tick(6);
     if (cfg.optimizer == 0) {
       if (tid == 0) serial_step_gn(s, cfg, job.result, writer, it);
       __syncthreads();
@@ -517,6 +554,7 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
     }
     if (tid == 0) serial_lm_end(s, cfg, step_ok);
     __syncthreads();
+    clk.tick(7);
     if (s.flag_out) break;
   }
 
@@ -544,6 +582,7 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
       }
     }
     cluster_reduce<3>(cluster, s, f, phase);
+    clk.tick(8);
   }
 
   if (writer) {
@@ -567,6 +606,7 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
     res->grid[0] = s_grid; res->grid[1] = job.tg;
     res->ncells[0] = s_ncells; res->ncells[1] = t_ncells;
     res->prep_status = 0;
+    clk.store(res);
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(res->t_end));
   }
   if (job.host_result && rank == 0) {

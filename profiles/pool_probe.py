@@ -70,7 +70,8 @@ def main():
                 "lm_kernel_ms_mean_under_load": st["lm_kernel_ms"] / max(1, st["registrations"]),
                 "cta_slot_occupancy": st["lm_kernel_ms"] * ctas / (296.0 * wall * 1e3),
                 "host_cpu_ms_per_registration": 1e3 * cpu / n,
-                "host_ms_per_registration": {k: v / max(1, st["registrations"]) for k, v in st.items() if k.startswith("host_")}})
+                "host_ms_per_registration": {k: v / max(1, st["registrations"]) for k, v in st.items() if k.startswith("host_")},
+                "lm_phase_ms_per_registration": {k: round(v / max(1, st["registrations"]), 4) for k, v in st["lm_phase_ms"].items() if v}})
     print(json.dumps(out))
     b.close()
 

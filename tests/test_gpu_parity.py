@@ -410,7 +410,9 @@ def test_target_covariances_on_demand_are_the_eager_ones(gorio, c2, monkeypatch,
     assert np.array_equal(ge.lm_trace(), gl.lm_trace())
     assert np.array_equal(ge.get_correspondences()[0], gl.get_correspondences()[0])
     assert np.array_equal(ge.get_mahalanobis(), gl.get_mahalanobis())
-    assert gl.kernel_ms()["knn_cov"][1] == ge.kernel_ms()["knn_cov"][1] // 2  # the source's pass only
+    # the on-demand handle took the fused kernel: grids, source covariances and the loop in ONE launch; the eager one ran the
+    # separate kernels (host-sized grids) — and still every output above has the same bits
+    assert gl.kernel_ms()["knn_cov"][1] == 0 and gl.kernel_ms()["grid"][1] == 0 and gl.kernel_ms()["lm"][1] == 1
     # asking for all of them completes the cloud; the ones the loop made are not distinguishable
     assert np.array_equal(ge.get_target_covariances(), gl.get_target_covariances())
     if reg == "PLANE":
@@ -569,6 +571,42 @@ def test_clear_and_cache_key(gorio, c1):
     assert e.value.code == 1
     g.set_input_source(src)
     _check_align(g, o)
+
+
+def test_fused_kernel_equals_the_separate_kernels(gorio, synth, c2_small, monkeypatch):
+    """APD_FUSED=0 builds grids and source covariances with the GPU-wide kernels (boxes reduced on the device, grids sized on
+    the host); the default does all of it inside the loop kernel's launch (device-sized grids: grid_desc.hpp is one function
+    for both). Same bits everywhere, 1 launch against 11; keyframe reuse (target kept) and odd sizes included."""
+    src, tgt, _ = c2_small
+    monkeypatch.setenv("APD_LAZY_TARGET_COV", "1")
+    kw = dict(**DEPLOYED, maha_fp64=1)
+    monkeypatch.setenv("APD_FUSED", "0")
+    gs = gorio.FastAPDGICP(0); gs.set_params(**kw)
+    monkeypatch.setenv("APD_FUSED", "1")
+    gf = gorio.FastAPDGICP(0); gf.set_params(**kw)
+    for cut_s, cut_t in ((0, 0), (7, 13), (301, 999)):
+        s_, t_ = src[cut_s:].copy(), tgt[cut_t:].copy()
+        for g in (gs, gf):
+            g.clear_target(); g.clear_source()
+            g.set_input_target(t_); g.set_input_source(s_)
+        l0 = gf.launch_count()
+        rs, rf = gs.align(), gf.align()
+        assert gf.launch_count() - l0 == 1 and gs.kernel_ms()["grid"][1] > 0
+        assert np.array_equal(rs["T64"], rf["T64"]) and np.array_equal(rs["H"], rf["H"]) and rs["iterations"] == rf["iterations"]
+        assert np.array_equal(gs.lm_trace(), gf.lm_trace())
+        assert np.array_equal(gs.get_correspondences()[0], gf.get_correspondences()[0])
+        assert np.array_equal(gs.get_source_covariances(), gf.get_source_covariances())
+        assert np.array_equal(gs.get_neighbors(0), gf.get_neighbors(0)) and np.array_equal(gs.get_neighbors(1), gf.get_neighbors(1))
+        # the next scan against the SAME target: the fused kernel prepares the source only (the target's grid and the
+        # covariances it has met so far stay)
+        s2 = s_[::2].copy()
+        for g in (gs, gf):
+            g.set_input_source(s2)
+        l0 = gf.launch_count()
+        rs, rf = gs.align(), gf.align()
+        assert gf.launch_count() - l0 == 1 and np.array_equal(rs["T64"], rf["T64"]) and np.array_equal(gs.lm_trace(), gf.lm_trace())
+        assert np.array_equal(gs.get_target_covariances(), gf.get_target_covariances())
+        assert gf.fitness() == gs.fitness()
 
 
 def test_streamed_frames_with_recycled_addresses(gorio, synth):
