@@ -84,7 +84,9 @@ constexpr int smem_bytes() {
   return kStages * StageLayout<kFp64>::kBytes + 2 * kTile * 16;
 }
 
-template <bool kFp64, bool kHB>
+// kSharded: the source is served in several chunks (ShardTable); false: one chunk = the whole cloud, and the tile
+// arithmetic below folds to base = tile * 256
+template <bool kFp64, bool kHB, bool kSharded>
 __global__ void __launch_bounds__(kThreads, 2)
 linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_geo, const double* __restrict__ s_geo64,
                  const int* __restrict__ corr, const void* __restrict__ mahaA, const void* __restrict__ mahaB,
@@ -99,10 +101,14 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
   const int tid = threadIdx.x;
   // tiles: chunk j of the rank's source points holds tpc tiles (a chunk is a whole number of tiles when there are several)
   const int tpc = (sh.chunk + kTile - 1) / kTile;
-  const int ntiles = sh.nsub * tpc;
+  const int ntiles = kSharded ? sh.nsub * tpc : tpc;
   // tile -> (first global sorted position, first rank-local slot, points in the tile; 0 for a padding tile)
   auto tile_span = [&](int tile, size_t& gbase, size_t& lbase) -> int {
-    const int j = sh.nsub == 1 ? 0 : tile / tpc;
+    if (!kSharded) {
+      gbase = lbase = (size_t)tile * kTile;
+      return min(kTile, sh.count[0] - tile * kTile);
+    }
+    const int j = tile / tpc;
     const int o = (tile - j * tpc) * kTile;
     gbase = (size_t)sh.begin_of(j) + o;
     lbase = (size_t)j * sh.chunk + o;
@@ -267,7 +273,7 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
   }
 }
 
-template <bool kFp64, bool kHB>
+template <bool kFp64, bool kHB, bool kSharded>
 void launch_one(int blocks, cudaStream_t s, const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const PoseD& T, const CorrOut& c,
                 double cl_w, const ReduceWork& w, double* d_out28) {
   // the attribute is per (function, device); handles of several devices and pool threads come through here
@@ -276,10 +282,10 @@ void launch_one(int blocks, cudaStream_t s, const CloudDev& src, const CloudDev&
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-    cudaFuncSetAttribute(linearize_kernel<kFp64, kHB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(linearize_kernel<kFp64, kHB, kSharded>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
-  linearize_kernel<kFp64, kHB><<<blocks, kThreads, bytes, s>>>(src.spts, src.geo, src.geo64, c.corr, c.mahaA, c.mahaB, tgt.spts, T, cl_w,
+  linearize_kernel<kFp64, kHB, kSharded><<<blocks, kThreads, bytes, s>>>(src.spts, src.geo, src.geo64, c.corr, c.mahaA, c.mahaB, tgt.spts, T, cl_w,
                                                                 sh, w.partials, d_out28, w.ticket, w.xchg);
 }
 
@@ -313,13 +319,19 @@ void launch_linearize(const CloudDev& src, const CloudDev& tgt, const ShardTable
   int blocks = sh.nsub * tpc;
   blocks = max(1, min(blocks, w.max_blocks));
   const double cl_w = 1.0 / n_total;  // 1.0 / correspondences_.size() (:273)
+#define APD_LIN(F, H)                                                                              \
+  do {                                                                                             \
+    if (sh.nsub > 1) launch_one<F, H, true>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);       \
+    else launch_one<F, H, false>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);                  \
+  } while (0)
   if (c.maha_fp64) {
-    if (want_hb) launch_one<true, true>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);
-    else launch_one<true, false>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);
+    if (want_hb) APD_LIN(true, true);
+    else APD_LIN(true, false);
   } else {
-    if (want_hb) launch_one<false, true>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);
-    else launch_one<false, false>(blocks, s, src, tgt, sh, T, c, cl_w, w, d_out28);
+    if (want_hb) APD_LIN(false, true);
+    else APD_LIN(false, false);
   }
+#undef APD_LIN
   (*launches)++;
 }
 

@@ -644,7 +644,9 @@ def test_promotion_of_the_source_to_target_reuses_its_covariances(gorio, synth, 
     k1 = g.kernel_ms()["knn_cov"][1]
     fresh, _ = make(gorio, nxt, src, **DEPLOYED, maha_fp64=1)
     assert np.array_equal(fresh.align()["T64"], g.align()["T64"])
-    assert k1 - k0 == (fresh.kernel_ms()["knn_cov"][1]) // 2  # only the new source needed a kNN pass
+    # only the new source needed covariances — and with the target's all valid the loop kernel computed them itself (fused
+    # prologue, source only): no separate kNN launch at all
+    assert k1 - k0 == 0 and fresh.kernel_ms()["knn_cov"][1] == 4
 
 
 def test_pcl_xyzinormal_layout(gorio, synth, c1):
