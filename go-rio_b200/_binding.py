@@ -81,7 +81,7 @@ PRODUCT_SYMBOLS = CORE_SYMBOLS + [
     "batch_get_kernel_ms", "comm_unique_id",
     "comm_init", "comm_peer_handle", "comm_peer_attach", "comm_destroy", "group_create", "group_destroy", "group_size",
     "group_set_params", "group_set_source", "group_set_target", "group_set_source_device", "group_set_target_device", "group_align",
-    "group_linearize", "group_compute_error", "nearest_k", "source_nearest", "batch_create_multi", "batch_device_pairs", "batch_get_load_stats", "debug_launch_rate",
+    "group_linearize", "group_compute_error", "nearest_k", "source_nearest", "batch_create_multi", "batch_device_pairs", "batch_get_load_stats", "debug_launch_rate", "radius_search", "voxel_downsample", "submap_assemble",
     "align_batch_multi", "stream", "launch_count", "set_profiling", "get_kernel_ms",
 ]
 
@@ -307,6 +307,51 @@ class Registration:
         self._call("source_nearest", t.ctypes.data_as(C.c_void_p) if t is not None else None, idx.ctypes.data_as(C.c_void_p),
                    d2.ctypes.data_as(C.c_void_p), xyz.ctypes.data_as(C.c_void_p), C.c_int32(n))
         return idx, d2, xyz
+
+    def radius_search(self, radius, which=1, lists=False):
+        """neighbours within `radius` of every point of the cloud (pcl radiusSearch semantics: d2 < r^2, the point itself
+        included): counts [n]; with lists=True also (offsets [n+1], indices) in CSR form"""
+        n = self.n_source if which == 0 else self.n_target
+        counts = np.empty(n, np.int32)
+        if not lists:
+            self._call("radius_search", C.c_int32(which), C.c_double(radius), counts.ctypes.data_as(C.c_void_p), None, None, C.c_int64(0), C.c_int32(n))
+            return counts
+        offsets = np.empty(n + 1, np.int64)
+        self._call("radius_search", C.c_int32(which), C.c_double(radius), counts.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p), None,
+                   C.c_int64(0), C.c_int32(n))
+        indices = np.empty(int(offsets[-1]), np.int32)
+        self._call("radius_search", C.c_int32(which), C.c_double(radius), None, offsets.ctypes.data_as(C.c_void_p), indices.ctypes.data_as(C.c_void_p),
+                   C.c_int64(indices.shape[0]), C.c_int32(n))
+        return counts, offsets, indices
+
+    def voxel_downsample(self, cloud, leaf):
+        """pcl::VoxelGrid with a cubic leaf: float32 [m,4] {x,y,z,label}"""
+        a, n, stride, xo, lo = self._layout(cloud)
+        out = np.empty((max(n, 1), 4), np.float32)
+        m = C.c_int32()
+        self._call("voxel_downsample", a.ctypes.data_as(C.c_void_p), C.c_int32(n), C.c_int32(stride), C.c_int32(xo), C.c_int32(lo), C.c_double(leaf),
+                   out.ctypes.data_as(C.c_void_p), C.c_int32(out.shape[0]), C.byref(m))
+        return out[: m.value].copy()
+
+    def submap_assemble(self, clouds, poses, leaf, set_as_target=False):
+        """scan_matching_odometry_nodelet.cpp:602-618: clouds[c] moved by poses[c] (4x4), concatenated, voxel-downsampled"""
+
+        class Ref(C.Structure):
+            _fields_ = [("pts", C.c_void_p), ("n", C.c_int32)]
+
+        arrs = [_f32(c) for c in clouds]
+        refs = (Ref * len(arrs))()
+        for i, a in enumerate(arrs):
+            refs[i].pts, refs[i].n = a.ctypes.data, a.shape[0]
+        P = np.ascontiguousarray(np.stack([np.asarray(T, np.float64).T for T in poses])).reshape(-1)
+        total = sum(a.shape[0] for a in arrs)
+        out = np.empty((max(total, 1), 4), np.float32)
+        m = C.c_int32()
+        self._call("submap_assemble", refs, P.ctypes.data_as(C.c_void_p), C.c_int32(len(arrs)), C.c_int32(16), C.c_int32(0), C.c_int32(12),
+                   C.c_double(leaf), C.c_int32(1 if set_as_target else 0), out.ctypes.data_as(C.c_void_p), C.c_int32(out.shape[0]), C.byref(m))
+        if set_as_target:
+            self.n_target = m.value
+        return out[: m.value].copy()
 
     def lm_trace(self, max_rows=1024):
         rows = np.zeros((max_rows, 8), np.float64)

@@ -1843,6 +1843,213 @@ int apd_source_nearest(apd_handle* h, const float* T, int32_t* idx, float* sq_di
   return APD_OK;
 }
 
+// ---- the radius searches of the preprocessing stage on the cloud's grid ----
+int apd_radius_search(apd_handle* h, int32_t which, double radius, int32_t* counts, int64_t* offsets, int32_t* indices, int64_t capacity, int32_t n) {
+  if (!h || !(radius > 0.0) || (!counts && !offsets)) return APD_ERR_INVALID;
+  Cloud& c = which == 0 ? h->src : h->tgt;
+  if (!c.present || n != c.n || c.n <= 0) return fail(h, APD_ERR_INVALID, "cloud not set, or n is not its size");
+  DeviceGuard dg(h->device);
+  int rc = ensure_grid(h, c);
+  if (rc != APD_OK) return rc;
+  const size_t cb = align_up((size_t)n * sizeof(int32_t), 256), ob = align_up((size_t)n * sizeof(long long), 256);
+  APD_CUDA(h, h->scratch.ensure(cb + ob));
+  int32_t* d_counts = h->scratch.as<int32_t>();
+  long long* d_off = reinterpret_cast<long long*>(h->scratch.as<char>() + cb);
+  launch_radius_search(c.view(), (float)radius, d_counts, nullptr, nullptr, h->stream, &h->launches);
+  APD_CUDA(h, cudaGetLastError());
+  std::vector<int32_t> hc((size_t)n);
+  APD_CUDA(h, cudaMemcpyAsync(hc.data(), d_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
+  if (counts) std::memcpy(counts, hc.data(), (size_t)n * sizeof(int32_t));
+  if (!offsets) return APD_OK;
+  std::vector<long long> ho((size_t)n + 1);
+  ho[0] = 0;
+  for (int32_t i = 0; i < n; i++) ho[(size_t)i + 1] = ho[(size_t)i] + hc[(size_t)i];
+  for (int32_t i = 0; i <= n; i++) offsets[i] = ho[(size_t)i];
+  if (!indices) return APD_OK;
+  if (capacity < ho[(size_t)n]) return fail(h, APD_ERR_INVALID, "indices: capacity below offsets[n]");
+  if (ho[(size_t)n] == 0) return APD_OK;
+  DevBuf lists;
+  APD_CUDA(h, lists.ensure((size_t)ho[(size_t)n] * sizeof(int32_t)));
+  APD_CUDA(h, cudaMemcpyAsync(d_off, ho.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  launch_radius_search(c.view(), (float)radius, nullptr, d_off, lists.as<int32_t>(), h->stream, &h->launches);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(indices, lists.p, (size_t)ho[(size_t)n] * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = wait_stream(h);
+  lists.release();
+  APD_CUDA(h, e);
+  return APD_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// pcl::VoxelGrid of n device points d_in (float4 {x,y,z,label}) into d_out (capacity n): *n_out voxels in ascending voxel
+// index. status_out: 0 ok, 1 = the leaf is too small for the extent (PCL passes the cloud through unchanged: so does this)
+int voxel_downsample_device(apd_handle* h, const float4* d_in, int n, double leaf, float4* d_out, int* n_out, int* refused) {
+  *n_out = 0;
+  *refused = 0;
+  if (n <= 0) return APD_OK;
+  int rc = ensure_small(h);
+  if (rc != APD_OK) return rc;
+  unsigned int* d_state = reinterpret_cast<unsigned int*>(h->small.as<double>() + 60);  // 6 uints of scratch
+  const unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+  APD_CUDA(h, cudaMemcpyAsync(d_state, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  launch_voxel_bounds(d_in, n, d_state, h->stream, &h->launches);
+  unsigned int enc[6];
+  APD_CUDA(h, cudaMemcpyAsync(enc, d_state, sizeof(enc), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
+  if (enc[0] == 0xffffffffu) return APD_OK;  // no finite point
+  float mn[3], mx[3];
+  for (int a = 0; a < 6; a++) {
+    unsigned int u = enc[a];
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    std::memcpy(a < 3 ? &mn[a] : &mx[a - 3], &u, 4);
+  }
+  const float inv = 1.0f / (float)leaf;
+  const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1, dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+  if (dx * dy * dz > (long long)std::numeric_limits<int32_t>::max()) {  // voxel_grid.hpp: "Leaf size is too small for the input dataset"
+    APD_CUDA(h, cudaMemcpyAsync(d_out, d_in, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+    *n_out = n;
+    *refused = 1;
+    return APD_OK;
+  }
+  int min_b[3], div_b[3];
+  for (int a = 0; a < 3; a++) {
+    min_b[a] = (int)std::floor(mn[a] * inv);
+    div_b[a] = (int)std::floor(mx[a] * inv) - min_b[a] + 1;
+  }
+  const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+  // scratch: keys x2, vals x2, hist, scan tmp, heads
+  const int sblocks = (n + kSortTile - 1) / kSortTile;
+  const size_t hist_elems = (size_t)256 * sblocks;
+  const size_t scan_elems = std::max(scan_tmp_elems_for((size_t)n + 1), scan_tmp_elems_for(hist_elems));
+  const size_t kv = align_up((size_t)n * sizeof(uint32_t), 256);
+  APD_CUDA(h, h->work.ensure(5 * kv + 256 + align_up(hist_elems * 4, 256) + align_up(scan_elems * 4, 256)));
+  char* p = h->work.as<char>();
+  uint32_t* keys[2] = {(uint32_t*)p, (uint32_t*)(p + kv)};
+  uint32_t* vals[2] = {(uint32_t*)(p + 2 * kv), (uint32_t*)(p + 3 * kv)};
+  uint32_t* heads = (uint32_t*)(p + 4 * kv);
+  uint32_t* hist = (uint32_t*)(p + 5 * kv + 256);
+  uint32_t* scan_tmp = (uint32_t*)(p + 5 * kv + 256 + align_up(hist_elems * 4, 256));
+  launch_voxel_keys(d_in, n, inv, min_b, mul, keys[0], vals[0], h->stream, &h->launches);
+  const int cur = launch_sort_pairs_u32(keys, vals, n, 32, hist, scan_tmp, h->stream, &h->launches);
+  launch_voxel_heads(keys[cur], n, heads, h->stream, &h->launches);
+  launch_exclusive_scan_u32(heads, (size_t)n + 1, scan_tmp, h->stream, &h->launches);
+  launch_voxel_centroids(d_in, keys[cur], vals[cur], heads, n, d_out, h->stream, &h->launches);
+  APD_CUDA(h, cudaGetLastError());
+  uint32_t nv = 0;
+  APD_CUDA(h, cudaMemcpyAsync(&nv, heads + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
+  *n_out = (int)nv;
+  return APD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int apd_voxel_downsample(apd_handle* h, const void* pts, int32_t n, int32_t stride, int32_t xyz_off, int32_t label_off, double leaf, float* out_xyzl,
+                         int32_t capacity, int32_t* n_out) {
+  if (!h || !pts || n < 0 || stride < 12 || xyz_off < 0 || !(leaf > 0.0) || !out_xyzl || !n_out || capacity < n) return APD_ERR_INVALID;
+  *n_out = 0;
+  if (n == 0) return APD_OK;
+  DeviceGuard dg(h->device);
+  PinnedBuf stage;
+  DevBuf in, out;
+  int rc = APD_OK, refused = 0, nv = 0;
+  cudaError_t e = stage.ensure((size_t)n * sizeof(float4));
+  if (e == cudaSuccess) e = in.ensure((size_t)n * sizeof(float4));
+  if (e == cudaSuccess) e = out.ensure((size_t)n * sizeof(float4));
+  if (e == cudaSuccess) {
+    float bbox[6];
+    stage_cloud(pts, n, stride, xyz_off, label_off, reinterpret_cast<float*>(stage.p), bbox);
+    e = cudaMemcpyAsync(in.p, stage.p, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream);
+  }
+  if (e == cudaSuccess) {
+    rc = voxel_downsample_device(h, in.as<const float4>(), n, leaf, out.as<float4>(), &nv, &refused);
+    if (rc == APD_OK && nv > 0) e = cudaMemcpyAsync(out_xyzl, out.p, (size_t)nv * sizeof(float4), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = wait_stream(h);
+  }
+  stage.release(); in.release(); out.release();
+  if (e != cudaSuccess) {
+    h->error = cudaGetErrorString(e);
+    return APD_ERR_CUDA;
+  }
+  if (rc == APD_OK) *n_out = nv;
+  return rc;
+}
+
+int apd_submap_assemble(apd_handle* h, const apd_cloud_ref* clouds, const double* poses, int32_t n_clouds, int32_t stride, int32_t xyz_off,
+                        int32_t label_off, double leaf, int32_t set_as_target, float* out_xyzl, int32_t capacity, int32_t* n_out) {
+  if (!h || !clouds || !poses || n_clouds < 1 || stride < 12 || xyz_off < 0 || !n_out) return APD_ERR_INVALID;
+  long long total = 0;
+  for (int c = 0; c < n_clouds; c++) {
+    if (!clouds[c].pts || clouds[c].n < 0) return APD_ERR_INVALID;
+    total += clouds[c].n;
+  }
+  if (total > 0x7fffffffll || (out_xyzl && capacity < total)) return fail(h, APD_ERR_INVALID, "submap: capacity below the sum of the keyframe sizes");
+  *n_out = 0;
+  if (total == 0) return APD_OK;
+  DeviceGuard dg(h->device);
+  const int n = (int)total;
+  PinnedBuf stage;
+  DevBuf raw, moved, vox;
+  cudaError_t e = stage.ensure((size_t)n * sizeof(float4));
+  if (e == cudaSuccess) e = raw.ensure((size_t)n * sizeof(float4));
+  if (e == cudaSuccess) e = moved.ensure((size_t)n * sizeof(float4));
+  int rc = APD_OK, nv = n, refused = 0;
+  if (e == cudaSuccess) {
+    size_t off = 0;
+    for (int c = 0; c < n_clouds; c++) {  // gather every keyframe into one pinned buffer, one copy, then one transform launch per keyframe
+      float bbox[6];
+      stage_cloud(clouds[c].pts, clouds[c].n, stride, xyz_off, label_off, reinterpret_cast<float*>(stage.p) + 4 * off, bbox);
+      off += (size_t)clouds[c].n;
+    }
+    e = cudaMemcpyAsync(raw.p, stage.p, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream);
+    off = 0;
+    for (int c = 0; c < n_clouds && e == cudaSuccess; c++) {
+      launch_transform_cloud_d(raw.as<const float4>() + off, clouds[c].n, poses + 16 * (size_t)c, moved.as<float4>() + off, h->stream, &h->launches);
+      off += (size_t)clouds[c].n;
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  const float4* result = moved.as<const float4>();
+  if (e == cudaSuccess && leaf > 0.0) {
+    e = vox.ensure((size_t)n * sizeof(float4));
+    if (e == cudaSuccess) {
+      rc = voxel_downsample_device(h, moved.as<const float4>(), n, leaf, vox.as<float4>(), &nv, &refused);
+      result = vox.as<const float4>();
+    }
+  }
+  if (e == cudaSuccess && rc == APD_OK && out_xyzl && nv > 0) e = cudaMemcpyAsync(out_xyzl, result, (size_t)nv * sizeof(float4), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && rc == APD_OK && set_as_target && nv > 0) {
+    // registration_s2m->setInputTarget(submap): the submap never leaves the device
+    Cloud& t = h->tgt;
+    e = t.pts.ensure((size_t)nv * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t.pts.p, result, (size_t)nv * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream);
+    if (e == cudaSuccess) {
+      t.ext_pts = nullptr;
+      t.n = nv;
+      t.present = true;
+      t.key = 0;
+      t.print = 0;
+      t.drop_derived();
+      t.bbox_pending = true;  // (its box is reduced on the device when a grid is sized on the host)
+      h->corr_warm = false;
+    }
+  }
+  if (e == cudaSuccess) e = wait_stream(h);
+  stage.release(); raw.release(); moved.release(); vox.release();
+  if (e != cudaSuccess) {
+    h->error = cudaGetErrorString(e);
+    return APD_ERR_CUDA;
+  }
+  if (rc == APD_OK) *n_out = nv;
+  return rc;
+}
+
 int apd_get_lm_trace(apd_handle* h, double* rows, int32_t max_rows, int32_t* n_rows) {
   if (!h || !rows || !n_rows) return APD_ERR_INVALID;
   const int n = std::min<int>(max_rows, (int)(h->trace.size() / 8));

@@ -430,6 +430,24 @@ void launch_bounds(const float4* pts, int n, unsigned int* d_state, unsigned int
   (*launches)++;
 }
 
+void launch_exclusive_scan_u32(uint32_t* data, size_t n, uint32_t* tmp, cudaStream_t s, int64_t* launches) { exclusive_scan(data, n, tmp, s, launches); }
+
+int launch_sort_pairs_u32(uint32_t* const keys[2], uint32_t* const vals[2], int n, int bits, uint32_t* hist, uint32_t* scan_tmp, cudaStream_t s,
+                          int64_t* launches) {
+  const int passes = (bits + 7) / 8;
+  const int sblocks = (n + kSortTile - 1) / kSortTile;
+  int cur = 0;
+  for (int p = 0; p < passes; p++) {
+    radix_hist_kernel<<<sblocks, kThreads, 0, s>>>(keys[cur], n, p * 8, hist, sblocks);
+    (*launches)++;
+    exclusive_scan(hist, (size_t)256 * sblocks, scan_tmp, s, launches);
+    radix_scatter_kernel<<<sblocks, kThreads, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, p * 8, hist, sblocks);
+    (*launches)++;
+    cur ^= 1;
+  }
+  return cur;
+}
+
 void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int64_t* launches) {
   const int n = c.n;
   if (n <= 0) return;

@@ -46,6 +46,28 @@ void launch_bounds(const float4* pts, int n, unsigned int* d_state, unsigned int
 // spts, label, inv_perm of `c` (c.pts, c.n, c.g, c.ncells must be set).
 void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int64_t* launches);
 
+// stable LSD radix sort of (key, value) pairs by the low `bits` bits of the key (8-bit digits); keys / vals: two buffers of
+// n each (input in [0]); hist: 256 * ceil(n / kSortTile) uints; returns the index of the buffer that holds the result
+int launch_sort_pairs_u32(uint32_t* const keys[2], uint32_t* const vals[2], int n, int bits, uint32_t* hist, uint32_t* scan_tmp, cudaStream_t s,
+                          int64_t* launches);
+void launch_exclusive_scan_u32(uint32_t* data, size_t n, uint32_t* tmp, cudaStream_t s, int64_t* launches);
+
+// ---- prep_ops.cu: the stages on either side of the registration that use the same grid ------------
+// radius search of every point of a cloud on its own grid (pcl radiusSearch semantics: fp32 d2 STRICTLY below r^2, the
+// point itself included). counts: [n] at the ORIGINAL index. With offsets != nullptr (CSR, [n] at the original index) the
+// neighbours' original ids are written to indices[offsets[i] ...] (in the grid's scan order).
+void launch_radius_search(const CloudDev& c, float radius, int32_t* d_counts, const long long* d_offsets, int32_t* d_indices, cudaStream_t s,
+                          int64_t* launches);
+// pcl::transformPointCloud(cloud, out, Eigen::Matrix4d): double arithmetic, cast to float; the label is carried over
+void launch_transform_cloud_d(const float4* in, int n, const double* T16_colmajor_host, float4* out, cudaStream_t s, int64_t* launches);
+// voxel grid pieces (pcl::VoxelGrid, see apd_voxel_downsample)
+void launch_voxel_bounds(const float4* pts, int n, unsigned int* d_state6, cudaStream_t s, int64_t* launches);
+void launch_voxel_keys(const float4* pts, int n, float inv_leaf, const int min_b[3], const int mul[3], uint32_t* keys, uint32_t* vals, cudaStream_t s,
+                       int64_t* launches);
+void launch_voxel_heads(const uint32_t* keys, int n, uint32_t* heads, cudaStream_t s, int64_t* launches);
+void launch_voxel_centroids(const float4* pts, const uint32_t* keys, const uint32_t* vals, const uint32_t* voxel_of, int n, float4* out, cudaStream_t s,
+                            int64_t* launches);
+
 // ---- knn_cov.cu --------------------------------------------------------------
 // Exact kNN (ties by (d2, index)), in two steps: the search kernels write the neighbour lists d_nb[w*k + j]
 // (original ids, ascending) of the sorted points, then launch_cov_regularize computes the covariance of the k

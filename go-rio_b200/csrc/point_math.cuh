@@ -161,6 +161,90 @@ __device__ __forceinline__ void nn_shells(const float4* spts, const uint32_t* ce
   }
 }
 
+// ---- one lane per query (the streaming kernels of large clouds, where the searches are bound by instruction issue):
+// the same exact search with the set-up arithmetic taken out of the row loops. The squared distances from the query to
+// the (slightly grown) cell slabs at offsets -1 / 0 / +1 are computed once per axis — they are the terms of row_dist2 —
+// so that a row of the 3x3x3 cube costs one add and one compare, its end cells are dropped when even their corner is
+// farther than the best so far, and in the shells a whole z-slab of rows goes with one test.
+__device__ __forceinline__ float slab_dist2(float q, float o, int c, float cell, float mg) {
+  const float lo = o + (float)c * cell - mg, hi = o + (float)(c + 1) * cell + mg;
+  const float d = fmaxf(0.f, fmaxf(lo - q, q - hi));
+  return d * d;
+}
+__device__ __forceinline__ void nn_search_lane(const float4* spts, const uint32_t* cell_start, const GridDesc& g, float qx, float qy, float qz,
+                                               double limit_sq, unsigned long long& best, int& best_pos, int seed_pos, float& proven2) {
+  const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
+  best = kInfKey;
+  best_pos = -1;
+  if (seed_pos >= 0) {
+    const float4 p = spts[seed_pos];
+    best = pack_key(sqdist_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+    best_pos = seed_pos;
+  }
+  const float mg = 0.002f * g.cell;
+  float dx2[3], dy2[3], dz2[3];
+#pragma unroll
+  for (int o = 0; o < 3; o++) {
+    dx2[o] = slab_dist2(qx, g.ox, cx + o - 1, g.cell, mg);
+    dy2[o] = slab_dist2(qy, g.oy, cy + o - 1, g.cell, mg);
+    dz2[o] = slab_dist2(qz, g.oz, cz + o - 1, g.cell, mg);
+  }
+  // ring 0+1: the query's own row first, then the other eight
+#pragma unroll 1
+  for (int ri = 0; ri < 9; ri++) {
+    const int oy = ri == 0 ? 1 : ((ri - 1 < 4 ? ri - 1 : ri) % 3), oz = ri == 0 ? 1 : ((ri - 1 < 4 ? ri - 1 : ri) / 3);  // offsets + 1; (1,1) first
+    const int y = cy + oy - 1, z = cz + oz - 1;
+    if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+    const float ryz = dy2[oy] + dz2[oz];
+    const bool have = best != kInfKey;
+    const float bd = __uint_as_float((unsigned)(best >> 32));
+    if (have && ri != 0 && ryz * 0.9999f > bd) continue;  // even the row's nearest point cannot beat the current best
+    // the end cells of the row are only read if their corner can
+    const int xa = (cx > 0 && !(have && (ryz + dx2[0]) * 0.9999f > bd)) ? cx - 1 : cx;
+    const int xb = (cx < g.nx - 1 && !(have && (ryz + dx2[2]) * 0.9999f > bd)) ? cx + 1 : cx;
+    const int row = (z * g.ny + y) * g.nx;
+    scan_range(spts, (int)cell_start[row + xa], (int)cell_start[row + xb + 1], qx, qy, qz, best, best_pos);
+  }
+  // shells r = 2, 3, ... (see nn_shells): z-slabs outermost, their distance hoisted
+  const double prune_sq = limit_sq * 1.5625;
+  const float prune2 = prune_sq < 3.0e38 ? (float)prune_sq : 3.4e38f;
+  for (int r = 1;;) {
+    const float lb = ((float)r - 0.002f) * g.cell;
+    const float lb2 = lb * lb;
+    proven2 = fminf(lb2, prune2);
+    if (best != kInfKey && __uint_as_float((unsigned)(best >> 32)) < lb2) break;
+    if ((double)lb2 >= limit_sq) break;
+    if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) {
+      proven2 = prune2;  // the cube covers the grid; only rows skipped for their distance were left out
+      break;
+    }
+    const int rr = r < 3 ? r + 1 : r + (r >> 1) + 1;
+    const int x0 = max(cx - rr, 0), x1 = min(cx + rr, g.nx - 1);
+    const int xl = min(cx - r - 1, g.nx - 1), xr = max(cx + r + 1, 0);
+    for (int z = max(cz - rr, 0); z <= min(cz + rr, g.nz - 1); z++) {
+      const float sz2 = slab_dist2(qz, g.oz, z, g.cell, mg);
+      if ((double)(sz2 * 0.9999f) >= prune_sq) continue;
+      if (best != kInfKey && sz2 * 0.9999f > __uint_as_float((unsigned)(best >> 32))) continue;  // the whole slab of rows
+      const bool z_outer = z > cz + r || z < cz - r;
+      for (int y = max(cy - rr, 0); y <= min(cy + rr, g.ny - 1); y++) {
+        const float dyz2 = (slab_dist2(qy, g.oy, y, g.cell, mg) + sz2) * 0.9999f;
+        if ((double)dyz2 >= prune_sq) continue;
+        if (best != kInfKey && dyz2 > __uint_as_float((unsigned)(best >> 32))) continue;
+        const int row = (z * g.ny + y) * g.nx;
+        if (z_outer || y > cy + r || y < cy - r) {  // row outside the scanned cube: its whole x-range
+          scan_range(spts, (int)cell_start[row + x0], (int)cell_start[row + x1 + 1], qx, qy, qz, best, best_pos);
+        } else {  // row crosses the scanned cube: the two end pieces
+          if (x0 <= xl) scan_range(spts, (int)cell_start[row + x0], (int)cell_start[row + xl + 1], qx, qy, qz, best, best_pos);
+          if (xr <= x1) scan_range(spts, (int)cell_start[row + xr], (int)cell_start[row + x1 + 1], qx, qy, qz, best, best_pos);
+        }
+      }
+    }
+    r = rr;
+  }
+}
+
 // seed_pos >= 0: a target point (sorted position) to start from — the previous iteration's match. Its distance
 // bounds the search: rows of the cube whose box is farther are skipped, and the shells usually end at once.
 // The result is the same exact nearest neighbour by (d2, original index) with or without the seed.
@@ -168,6 +252,10 @@ template <int G>
 __device__ __forceinline__ void nn_search(const float4* spts, const uint32_t* cell_start, const GridDesc& g,
                                           float qx, float qy, float qz, double limit_sq, unsigned long long& best, int& best_pos,
                                           int seed_pos, float& proven2) {
+  if (G == 1) {
+    nn_search_lane(spts, cell_start, g, qx, qy, qz, limit_sq, best, best_pos, seed_pos, proven2);
+    return;
+  }
   const int sub = (G == 1) ? 0 : (int)(threadIdx.x & (G - 1));
   const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
   const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);

@@ -211,6 +211,36 @@ APD_API int apd_nearest_k(apd_handle* h, int32_t which, const void* queries, int
  * float[3n]): the transformed points. The shim's search adaptor answers the per-point queries from this batch. */
 APD_API int apd_source_nearest(apd_handle* h, const float* T, int32_t* idx, float* sq_dist, float* xyz, int32_t n);
 
+/* ---- the stages on either side of the registration that use the same grid ------------------------ */
+/* The radius searches of the preprocessing nodelet — pcl::RadiusOutlierRemoval (preprocessing_nodelet_ntu.cpp:163-172:
+ * a point stays when its radiusSearch finds MORE than min_neighbors points, itself included) and the neighbour queries
+ * of DBSCANKdtreeCluster (:520-532, eps 0.9, core points >= 10) — on the grid of the cloud `which` (0 source, 1 target),
+ * every point of the cloud being a query. pcl / FLANN radiusSearch semantics: a point is a neighbour when its fp32
+ * squared distance is STRICTLY below radius^2; the query point counts. counts: int32[n] (optional). offsets: int64[n+1]
+ * (optional), the CSR row starts; indices: the neighbours' point indices, row by row (unordered within a row), capacity
+ * entries — call once with indices = NULL to learn offsets[n], then again with the array. */
+APD_API int apd_radius_search(apd_handle* h, int32_t which, double radius, int32_t* counts, int64_t* offsets, int32_t* indices,
+                      int64_t capacity, int32_t n);
+/* pcl::VoxelGrid<PointT> with a cubic leaf (PCL 1.10 voxel_grid.hpp, downsample_all_data): one point per occupied voxel,
+ * voxels in ascending voxel index; x, y, z are the float mean of the voxel's points; the cluster label (normal_x) goes
+ * through PCL's normal accumulator — summed and normalised — so it becomes 1 where any member had a positive label, 0
+ * otherwise (normal_y = normal_z = 0 on this pipeline). out_xyzl: float4 {x,y,z,label}[capacity >= n]. When the leaf is
+ * too small for the cloud's extent (voxel index overflow) PCL warns and passes the cloud through: so does this. */
+APD_API int apd_voxel_downsample(apd_handle* h, const void* pts, int32_t n, int32_t stride_bytes, int32_t xyz_off, int32_t label_off,
+                         double leaf, float* out_xyzl, int32_t capacity, int32_t* n_out);
+/* The submap of the scan-to-map branch (scan_matching_odometry_nodelet.cpp:602-618): keyframe cloud c moved by
+ * poses[c] (column-major 4x4 doubles, rel_pose = odom_c^-1 * odom_last; pcl::transformPointCloud with a Matrix4d: double
+ * arithmetic, cast to float), concatenated in order, then voxel-downsampled with `leaf` (<= 0: not downsampled).
+ * out_xyzl (optional): float4[capacity >= sum of the keyframe sizes]. set_as_target != 0: the submap also becomes the
+ * handle's target cloud (registration_s2m->setInputTarget) without leaving the device. */
+typedef struct apd_cloud_ref {
+  const void* pts; /* host AoS, the layout arguments of apd_set_source */
+  int32_t n;
+} apd_cloud_ref;
+APD_API int apd_submap_assemble(apd_handle* h, const apd_cloud_ref* clouds, const double* poses, int32_t n_clouds, int32_t stride_bytes,
+                        int32_t xyz_off, int32_t label_off, double leaf, int32_t set_as_target, float* out_xyzl, int32_t capacity,
+                        int32_t* n_out);
+
 /* LM trace of the last apd_align: rows of {outer, inner, y0, yi, rho, lambda,
  * |d|, accepted} as 8 doubles, the columns of the reference's lm_debug_print_
  * table (lsq_registration_impl.hpp:148-154). Returns the number of rows
