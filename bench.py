@@ -27,6 +27,8 @@ work is fixed, so this is strong scaling; at N = 1 the one GPU registers all 409
             reduction kernels over NVLink peer memory), err against a committed constant
   roofline  (N = 1) the linearize kernel on that cloud (> L2), CUDA events on the
             handle's stream, against the measured HBM peak; + the loop kernel's share
+  replay    (N = 1) config C5: frames/s of the scan-to-scan odometry front end over a synthetic drive, next to
+            the CPU restatement on a prefix of the same drive (same keyframes, same poses)
   cpu_baseline  (N = 1) the reference-structure CPU restatement (oracle/_ref: OpenMP +
             the reference tree's nanoflann; else the oracle port) on a bounded sample
 """
@@ -76,6 +78,8 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-c4", action="store_true")
     ap.add_argument("--no-eager", action="store_true")
+    ap.add_argument("--no-replay", action="store_true")
+    ap.add_argument("--replay-frames", type=int, default=2000, help="frames of the C5 odometry replay block (N = 1; profiles/replay_bench.py runs all 10 000)")
     ap.add_argument("--roofline-reps", type=int, default=10)
     ap.add_argument("--roofline-only", action="store_true", help="profiling aid: skip the registrations/s part")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -577,6 +581,15 @@ def main():
         if only_c4 or args.roofline_only:
             line.update({"metric": "APDGICP LM-iteration throughput on one large cloud (source points/s)", "value": block["points_per_s"], "unit": "points/s",
                          "ms_per_step": block["ms_per_step"], "steps": block["steps"], "scaling": "strong", "higher_is_better": True})
+
+    # ---- config C5: the scan-to-scan odometry front end over a synthetic drive, one handle, frames in sequence (N = 1) ----
+    if rank == 0 and world == 1 and not args.no_replay and host_pairs:
+        try:
+            sys.path.insert(0, os.path.join(REPO, "profiles"))
+            import replay_bench
+            line["replay"] = replay_bench.run(args.replay_frames, min(300, args.replay_frames), 1000, local_rank)
+        except Exception as e:
+            line["replay"] = {"error": str(e)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and host_pairs:
         lib, kind, search, what = load_cpu_impl()

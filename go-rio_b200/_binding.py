@@ -81,7 +81,7 @@ PRODUCT_SYMBOLS = CORE_SYMBOLS + [
     "batch_get_kernel_ms", "comm_unique_id",
     "comm_init", "comm_peer_handle", "comm_peer_attach", "comm_destroy", "group_create", "group_destroy", "group_size",
     "group_set_params", "group_set_source", "group_set_target", "group_set_source_device", "group_set_target_device", "group_align",
-    "group_linearize", "group_compute_error", "nearest_k", "source_nearest", "batch_create_multi", "batch_device_pairs", "batch_get_load_stats", "debug_launch_rate", "radius_search", "voxel_downsample", "submap_assemble",
+    "group_linearize", "group_compute_error", "nearest_k", "source_nearest", "batch_create_multi", "batch_device_pairs", "batch_get_load_stats", "debug_launch_rate", "debug_multi_align", "radius_search", "voxel_downsample", "submap_assemble",
     "align_batch_multi", "stream", "launch_count", "set_profiling", "get_kernel_ms",
 ]
 

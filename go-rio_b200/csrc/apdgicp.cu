@@ -2451,6 +2451,46 @@ int apd_batch_get_load_stats(apd_batch* b, double* stats, int32_t n, int32_t res
   return APD_OK;
 }
 
+// Diagnostic: ONE launch of the loop kernel that registers the pairs set on n handles at once (n x cluster CTAs: with n
+// >= 74 the GPU is as full as a pool keeps it) — so that ncu, which profiles kernels one at a time, sees the kernel under
+// the co-residency it runs with in a pool. The handles' clouds must be set; their results are not unpacked.
+int apd_debug_multi_align(apd_handle* const* hs, int32_t n, int32_t repeat) {
+  if (!hs || n < 1) return APD_ERR_INVALID;
+  apd_handle* h0 = hs[0];
+  DeviceGuard dg(h0->device);
+  std::vector<LmJob> jobs((size_t)n);
+  LmConfig cfg = lm_config(h0->params);
+  for (int rep = 0; rep < std::max(1, repeat); rep++) {
+    for (int i = 0; i < n; i++) {
+      apd_handle* h = hs[i];
+      h->pooled = true;
+      if (rep > 0) {  // the protocol of a pooled registration: the derived state of both clouds is dropped
+        h->src.drop_derived();
+        h->tgt.drop_derived();
+        h->src.bbox_pending = h->src.ext_pts != nullptr;
+        h->tgt.bbox_pending = h->tgt.ext_pts != nullptr;
+      }
+      const int bits = fused_prep_bits(h);
+      int rc = bits ? prepare_fused(h, bits) : ensure_covariances_for_loop(h);
+      if (rc == APD_OK) rc = ensure_corr_buffers(h);
+      if (rc != APD_OK) return rc;
+      if (!h->lm_result.p) APD_CUDA(h, h->lm_result.ensure(sizeof(LmResult)));
+      jobs[(size_t)i] = lm_job(h, hm::Pose::identity(), bits);
+      jobs[(size_t)i].seq = 0;
+      jobs[(size_t)i].host_result = nullptr;
+      APD_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    DevBuf d_jobs;
+    APD_CUDA(h0, d_jobs.ensure(jobs.size() * sizeof(LmJob)));
+    APD_CUDA(h0, cudaMemcpy(d_jobs.p, jobs.data(), jobs.size() * sizeof(LmJob), cudaMemcpyHostToDevice));
+    launch_lm(nullptr, d_jobs.as<LmJob>(), n, cfg, h0->lm_cluster, h0->lm_min_blocks, h0->stream, &h0->launches);
+    const cudaError_t e = cudaStreamSynchronize(h0->stream);
+    d_jobs.release();
+    APD_CUDA(h0, e);
+  }
+  return APD_OK;
+}
+
 // Diagnostic: how many (empty) kernel launches per second this process can issue on `device` from n_threads host threads
 // over n_streams streams. A pool of registrations issues ~11 launches each; this is the ceiling the driver puts on that.
 int apd_debug_launch_rate(int device, int32_t n_streams, int32_t n_threads, int32_t launches_per_thread, double* per_second) {

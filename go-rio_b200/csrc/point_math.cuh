@@ -191,21 +191,40 @@ __device__ __forceinline__ void nn_search_lane(const float4* spts, const uint32_
     dy2[o] = slab_dist2(qy, g.oy, cy + o - 1, g.cell, mg);
     dz2[o] = slab_dist2(qz, g.oz, cz + o - 1, g.cell, mg);
   }
-  // ring 0+1: the query's own row first, then the other eight
-#pragma unroll 1
-  for (int ri = 0; ri < 9; ri++) {
-    const int oy = ri == 0 ? 1 : ((ri - 1 < 4 ? ri - 1 : ri) % 3), oz = ri == 0 ? 1 : ((ri - 1 < 4 ? ri - 1 : ri) / 3);  // offsets + 1; (1,1) first
-    const int y = cy + oy - 1, z = cz + oz - 1;
-    if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
-    const float ryz = dy2[oy] + dz2[oz];
+  // ring 0+1: the query's own row first; then the rows among the other eight that can still hold a closer point. Which
+  // ones is decided for all eight at once (straight-line code), and the lanes of a warp then walk their own survivors
+  // side by side — a lane that keeps two rows and a lane that keeps five share two turns, not nine.
+  auto scan_row = [&](int oy, int oz, float ryz, bool own) {
     const bool have = best != kInfKey;
     const float bd = __uint_as_float((unsigned)(best >> 32));
-    if (have && ri != 0 && ryz * 0.9999f > bd) continue;  // even the row's nearest point cannot beat the current best
+    if (have && !own && ryz * 0.9999f > bd) return;  // even the row's nearest point cannot beat the current best
     // the end cells of the row are only read if their corner can
     const int xa = (cx > 0 && !(have && (ryz + dx2[0]) * 0.9999f > bd)) ? cx - 1 : cx;
     const int xb = (cx < g.nx - 1 && !(have && (ryz + dx2[2]) * 0.9999f > bd)) ? cx + 1 : cx;
-    const int row = (z * g.ny + y) * g.nx;
+    const int row = ((cz + oz - 1) * g.ny + (cy + oy - 1)) * g.nx;
     scan_range(spts, (int)cell_start[row + xa], (int)cell_start[row + xb + 1], qx, qy, qz, best, best_pos);
+  };
+  if (cy >= 0 && cy < g.ny && cz >= 0 && cz < g.nz) scan_row(1, 1, dy2[1] + dz2[1], true);
+  unsigned m = 0;
+  {
+    const bool have = best != kInfKey;
+    const float bd = __uint_as_float((unsigned)(best >> 32));
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int idx = k < 4 ? k : k + 1, oy = idx % 3, oz = idx / 3;  // (compile-time)
+      const int y = cy + oy - 1, z = cz + oz - 1;
+      const bool keep = y >= 0 && y < g.ny && z >= 0 && z < g.nz && !(have && (dy2[oy] + dz2[oz]) * 0.9999f > bd);
+      m |= keep ? (1u << k) : 0u;
+    }
+  }
+  while (m) {
+    const int k = __ffs(m) - 1;
+    m &= m - 1;
+    const int idx = k < 4 ? k : k + 1;
+    const int oz = (idx * 11) >> 5, oy = idx - 3 * oz;  // idx / 3, idx % 3 for idx < 9
+    const float ry = oy == 0 ? dy2[0] : (oy == 1 ? dy2[1] : dy2[2]);
+    const float rz = oz == 0 ? dz2[0] : (oz == 1 ? dz2[1] : dz2[2]);
+    scan_row(oy, oz, ry + rz, false);
   }
   // shells r = 2, 3, ... (see nn_shells): z-slabs outermost, their distance hoisted
   const double prune_sq = limit_sq * 1.5625;

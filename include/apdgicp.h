@@ -311,6 +311,8 @@ APD_API int64_t apd_batch_launch_count(const apd_batch* b);
  * milliseconds spent per phase: set clouds, wait for the bounding boxes, enqueue grids + covariances, enqueue the loop,
  * wait for the result. n >= 7. */
 APD_API int apd_batch_get_load_stats(apd_batch* b, double* stats, int32_t n, int32_t reset);
+/* diagnostic: ONE loop-kernel launch over the pairs set on n handles (profiling the kernel under pool-like co-residency) */
+APD_API int apd_debug_multi_align(apd_handle* const* handles, int32_t n, int32_t repeat);
 /* diagnostic: empty-kernel launches per second from n_threads host threads over n_streams streams (per_second[0]: issue
  * rate, [1]: completion rate) — the driver's ceiling on a pool that issues several launches per registration */
 APD_API int apd_debug_launch_rate(int device, int32_t n_streams, int32_t n_threads, int32_t launches_per_thread, double* per_second);
