@@ -73,7 +73,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="scan/submap pairs per step over ALL GPUs (config C3: 4096)")
     ap.add_argument("--distinct", type=int, default=0, help="distinct scenes among the pairs (0: all; fewer are cycled — profiling aid)")
-    ap.add_argument("--streams", type=int, default=128, help="registrations in flight per GPU: handles (CUDA stream each) of the batch context, driven by a few host threads")
+    ap.add_argument("--streams", type=int, default=192, help="registrations in flight per GPU: handles (CUDA stream each) of the batch context, driven by a few host threads")
     ap.add_argument("--roofline-points", type=int, default=20_000_000)
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-c4", action="store_true")
@@ -563,7 +563,7 @@ def main():
         # the step's dominant kernel: the device-resident loop. It is latency / issue bound (0.04 % of DRAM peak), so its
         # live figure is how full it keeps the GPU; the ncu figures of the same kernel are in profiles/
         lm_ms = kms.get("lm", [0.0, 0])[0]
-        ctas = 4 if "APD_LM_CLUSTER" not in os.environ else int(os.environ["APD_LM_CLUSTER"])
+        ctas = 2 if "APD_LM_CLUSTER" not in os.environ else int(os.environ["APD_LM_CLUSTER"])  # (a pool's default cluster size)
         line["loop_kernel"] = {"kernel": "lm_kernel<fp32 maha, 2 CTAs/SM>", "share_of_step_kernel_time": round(lm_ms / tot, 4),
                                "ms_per_registration": lm_ms / max(1, n_mine), "ctas_per_registration": ctas,
                                "cta_slot_occupancy": round(lm_ms * ctas / (296.0 * (ms_dev / args.steps)), 4),

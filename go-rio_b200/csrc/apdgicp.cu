@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstddef>
+#include <cctype>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -133,6 +134,7 @@ struct Cloud {
   bool staged_by_seq = false;
   const float4* ext_pts = nullptr;  // user-owned device cloud (apd_set_*_device)
   bool bbox_pending = false;        // ... whose bounding box is not known on the host yet (see finish_bboxes)
+  bool bbox_known = false;          // bbox[] holds this cloud's box (staging pass, or a finished device reduction)
   bool bbox_launched = false;       // ... the kernel that reduces it has been launched (it is only launched when a grid is sized on the host:
                                     // the fused registration kernel sizes its grids itself)
   const void* host_packed = nullptr;  // packed float4 cloud in the caller's page-locked memory whose box has not been computed (same reason)
@@ -140,6 +142,8 @@ struct Cloud {
   GridDesc g{};
   int ncells = 0;
   bool grid_valid = false;
+  bool grid_ordered = true;  // points of a cell lie in ascending original index (always, except a target the fused kernel placed
+                             // by atomic ranks: prep.cuh). Only a SOURCE needs it: swapping such a target in rebuilds its grid.
   bool cov_valid = false;
   bool geo_valid = false;
   int geo_variant = APD_VARIANT_APDGICP;  // what geo / geo64 hold: sigma3/sigma1 (APDGICP) or zeros (GICP: unit weights)
@@ -272,6 +276,16 @@ struct apd_handle {
   int64_t k_launches[APD_K_COUNT] = {0};
   int max_reduce_blocks = 148 * 4;
   double cells_per_point = 0.0;  // 0: by size (4 below 500 k points: fewer kNN shells; 8 above: cheaper 1-NN per LM iteration)
+  // Scans (<= small_cloud_n points): what their grid is searched for most is their own k = 20 neighbours, and a 1-2 k-point
+  // radar scan is so sparse that at 4 cells per point the 3x3x3 cube holds ~7 of them: every query walks several shells.
+  // APD_CELLS_PER_POINT_SMALL overrides.
+  double cells_per_point_small = 4.0;
+  int small_cloud_n = 8192;
+  double cells_for(int n) const {
+    if (cells_per_point > 0.0) return cells_per_point;
+    if (n >= 500000) return 8.0;
+    return n <= small_cloud_n ? cells_per_point_small : 4.0;
+  }
   // kNN kernel choice: 0 auto (warp-per-point below knn_thread_min_n points and k <= 32, thread-per-point
   // above: the warp kernel has the shorter critical path, the thread kernel the higher throughput),
   // 1 warp, 2 thread. Override with APD_KNN_MODE=warp|thread.
@@ -510,6 +524,7 @@ int finish_bboxes(apd_handle* h) {
     if (c->host_packed) {  // a packed host cloud whose box was left for later (the caller's buffer is still valid: same call)
       bounds_of_packed(c->host_packed, c->n, c->bbox);
       c->host_packed = nullptr;
+      c->bbox_known = true;
     }
   if (!h->src.bbox_pending && !h->tgt.bbox_pending) return APD_OK;
   for (Cloud* c : {&h->src, &h->tgt})
@@ -538,6 +553,7 @@ int finish_bboxes(apd_handle* h) {
     }
     c->bbox_pending = false;
     c->bbox_launched = false;
+    c->bbox_known = true;
   }
   return APD_OK;
 }
@@ -546,10 +562,11 @@ int ensure_grid(apd_handle* h, Cloud& c, bool clear_flags = false) {
   if (c.grid_valid) return APD_OK;
   if (!c.present || c.n <= 0) return fail(h, APD_ERR_INVALID, "cloud not set");
   {
+    if (!c.bbox_known && !c.host_packed) c.bbox_pending = true;  // (e.g. a cloud whose grid the fused kernel had sized itself)
     int rc = finish_bboxes(h);
     if (rc != APD_OK) return rc;
   }
-  size_grid(c.bbox, c.n, h->cells_per_point > 0.0 ? h->cells_per_point : (c.n < 500000 ? 4.0 : 8.0), c.g, c.ncells);
+  size_grid(c.bbox, c.n, h->cells_for(c.n), c.g, c.ncells);
   const size_t n = (size_t)c.n;
   APD_CUDA(h, c.spts.ensure(n * sizeof(float4)));
   APD_CUDA(h, c.label.ensure(n * sizeof(float)));
@@ -584,6 +601,7 @@ int ensure_grid(apd_handle* h, Cloud& c, bool clear_flags = false) {
   }
   APD_CUDA(h, cudaGetLastError());
   c.grid_valid = true;
+  c.grid_ordered = true;
   return APD_OK;
 }
 
@@ -745,7 +763,7 @@ int prepare_fused(apd_handle* h, int bits) {
   Cloud& s = h->src;
   Cloud& t = h->tgt;
   const int k = h->params.k_correspondences;
-  const double s_cpp = h->cells_per_point > 0.0 ? h->cells_per_point : 4.0, t_cpp = s_cpp;
+  const double s_cpp = h->cells_for(s.n), t_cpp = h->cells_for(t.n);
   if (bits & 1) {
     const size_t n = (size_t)s.n;
     APD_CUDA(h, s.spts.ensure(n * sizeof(float4)));
@@ -962,11 +980,13 @@ int step_lm(apd_handle* h, int outer, hm::Pose& x0, hm::Pose& delta, bool* ok) {
 // covariances are pure functions of the cloud, so they are copied device-to-device instead of rebuilt (the reference
 // recomputes them).
 int adopt_cloud(apd_handle* h, Cloud& dst, const Cloud& src) {
-  {
+  if (h->src.bbox_launched || h->tgt.bbox_launched) {  // (a box in flight is collected first: the read-back slots belong to the roles)
     const int rc = finish_bboxes(h);
     if (rc != APD_OK) return rc;
   }
-  dst.bbox_pending = false;
+  dst.bbox_launched = false;
+  dst.host_packed = nullptr;
+  dst.bbox_pending = !src.bbox_known;  // (reduced on the device if a grid of the copy is ever sized on the host)
   const size_t n = (size_t)src.n;
   auto copy = [&](DevBuf& d, const DevBuf& s_, size_t bytes) -> cudaError_t {
     if (!s_.p || bytes == 0) return cudaSuccess;
@@ -996,9 +1016,11 @@ int adopt_cloud(apd_handle* h, Cloud& dst, const Cloud& src) {
   dst.key = src.key;
   dst.print = src.print;
   std::memcpy(dst.bbox, src.bbox, sizeof(dst.bbox));
+  dst.bbox_known = src.bbox_known && !src.host_packed;
   dst.g = src.g;
   dst.ncells = src.ncells;
   dst.grid_valid = src.grid_valid;
+  dst.grid_ordered = src.grid_ordered;
   dst.cov_valid = src.grid_valid && src.cov_valid;
   dst.geo_valid = dst.cov_valid && src.geo_valid;
   dst.geo_variant = src.geo_variant;
@@ -1053,6 +1075,7 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
       c.ext_pts = nullptr;
       c.bbox_pending = false;
       c.bbox_launched = false;
+      c.bbox_known = false;
       c.n = n;
       c.present = true;
       c.key = key;
@@ -1095,6 +1118,7 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
   c.ext_pts = nullptr;
   c.bbox_pending = false;
   c.bbox_launched = false;
+  c.bbox_known = true;  // (found by the staging pass)
   c.host_packed = nullptr;
   c.n = n;
   c.present = true;
@@ -1134,6 +1158,7 @@ int set_cloud_device(apd_handle* h, Cloud& c, const void* d_xyzl, int32_t n) {
   DeviceGuard dg(h->device);
   c.bbox_pending = true;     // (its box is reduced when — and if — a grid is sized on the host: finish_bboxes)
   c.bbox_launched = false;
+  c.bbox_known = false;
   c.host_packed = nullptr;
   c.ext_pts = reinterpret_cast<const float4*>(d_xyzl);
   h->corr_warm = false;
@@ -1269,7 +1294,8 @@ LmJob lm_job(apd_handle* h, const hm::Pose& x0, int prep_bits = 0) {
     j.t_cell_cap = (int)std::min<size_t>(h->tgt.cell_start.cap / sizeof(uint32_t), 0x7fffffff);
     j.s_scratch = h->work.as<uint32_t>();
     j.t_scratch = h->work.as<uint32_t>() + 3 * (size_t)s.n;
-    j.s_cells_per_point = j.t_cells_per_point = h->cells_per_point > 0.0 ? h->cells_per_point : 4.0;
+    j.s_cells_per_point = h->cells_for(s.n);
+    j.t_cells_per_point = h->cells_for(t.n);
     j.s_k = h->params.k_correspondences;
     j.s_reg = h->params.regularization;
     j.gicp = h->params.variant == APD_VARIANT_GICP ? 1 : 0;
@@ -1306,6 +1332,7 @@ int finish_device_align(apd_handle* h, const LmResult* r) {
       h->tgt.g = r->grid[1];
       h->tgt.ncells = r->ncells[1];
       h->tgt.grid_valid = true;
+      h->tgt.grid_ordered = false;
     }
     for (Cloud* c : {&h->src, &h->tgt})
       if (c->grid_valid) {  // (the box was never needed on the host)
@@ -1558,6 +1585,10 @@ int apd_create(int device, apd_handle** out) {
     const double v = std::atof(e);
     if (v > 0.01 && v < 1000.0) h->cells_per_point = v;
   }
+  if (const char* e = std::getenv("APD_CELLS_PER_POINT_SMALL")) {
+    const double v = std::atof(e);
+    if (v > 0.01 && v < 1000.0) h->cells_per_point_small = v;
+  }
   if (const char* e = std::getenv("APD_LM_CLUSTER")) {
     const int v = std::atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->lm_cluster = v;
@@ -1648,6 +1679,7 @@ int apd_swap_source_and_target(apd_handle* h) {  // :89-98
     if (rc != APD_OK) return rc;
   }
   std::swap(h->src, h->tgt);
+  if (h->src.grid_valid && !h->src.grid_ordered) h->src.drop_derived();  // (sums over source points follow the source's layout: rebuild it in order)
   h->corr_n = -1;  // correspondences_.clear()
   h->corr_warm = false;
   return APD_OK;
@@ -2036,6 +2068,7 @@ int apd_submap_assemble(apd_handle* h, const apd_cloud_ref* clouds, const double
       t.key = 0;
       t.print = 0;
       t.drop_derived();
+      t.bbox_known = false;
       t.bbox_pending = true;  // (its box is reduced on the device when a grid is sized on the host)
       h->corr_warm = false;
     }
@@ -2205,10 +2238,49 @@ bool slot_stalled(PoolSlot& sl, bool arrived_now) {
   return true;
 }
 
+// Host threads that feed a GPU run on the cores of the GPU's NUMA node (staging a 3 MB PCL cloud is a memory-bound loop,
+// and the pinned staging buffers are first touched by these threads): best effort from sysfs, within the process's own
+// affinity mask; APD_NUMA_PIN=0 leaves the threads where the scheduler puts them.
+void pin_to_gpu_node(int device) {
+  if (const char* e = std::getenv("APD_NUMA_PIN"))
+    if (std::atoi(e) == 0) return;
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return;
+  for (char* p = bus; *p; p++) *p = (char)std::tolower(*p);
+  char path[128];
+  std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  int node = -1;
+  if (FILE* f = std::fopen(path, "r")) {
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+  }
+  if (node < 0) return;
+  std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  FILE* f = std::fopen(path, "r");
+  if (!f) return;
+  char list[4096] = {0};
+  const bool ok = std::fgets(list, sizeof(list), f) != nullptr;
+  std::fclose(f);
+  if (!ok) return;
+  cpu_set_t mine, want;
+  if (sched_getaffinity(0, sizeof(mine), &mine) != 0) return;
+  CPU_ZERO(&want);
+  for (char* tok = std::strtok(list, ",\n"); tok; tok = std::strtok(nullptr, ",\n")) {
+    int a = 0, b2 = 0;
+    const int k = std::sscanf(tok, "%d-%d", &a, &b2);
+    if (k == 1) b2 = a;
+    if (k >= 1)
+      for (int c = a; c <= b2 && c < CPU_SETSIZE; c++)
+        if (CPU_ISSET(c, &mine)) CPU_SET(c, &want);
+  }
+  if (CPU_COUNT(&want) > 0) sched_setaffinity(0, sizeof(want), &want);
+}
+
 void batch_worker(apd_batch* b, int wi) {
   // thread wi serves device wi / n_threads: every n_threads-th handle of that device
   const int di = wi / b->n_threads, ti = wi % b->n_threads;
   cudaSetDevice(b->devices[(size_t)di]);
+  pin_to_gpu_node(b->devices[(size_t)di]);
   std::vector<PoolSlot> slots;
   for (int s = ti; s < b->per_device; s += b->n_threads) {
     PoolSlot sl;
@@ -2320,7 +2392,7 @@ int apd_batch_create_multi(const int32_t* devices, int32_t n_devices, int32_t n_
   if (!out || !devices || n_devices < 1 || n_devices > 64) return APD_ERR_INVALID;
   *out = nullptr;
   if (n_workers < 1) n_workers = 1;
-  if (n_workers > 128) n_workers = 128;
+  if (n_workers > 512) n_workers = 512;
   ensure_work_queues();
   apd_batch* b = new apd_batch();
   b->device = devices[0];
@@ -2339,7 +2411,7 @@ int apd_batch_create_multi(const int32_t* devices, int32_t n_devices, int32_t n_
       // a pool this large keeps the GPU busy by itself: its waiting threads sleep instead of spinning, so that several
       // ranks' pools can share the host cores (see wait_stream)
       h->pooled = true;
-      if (!std::getenv("APD_LM_CLUSTER")) h->lm_cluster = 4;
+      if (!std::getenv("APD_LM_CLUSTER")) h->lm_cluster = 2;
       if (!std::getenv("APD_LM_MINB")) h->lm_min_blocks = 2;
       if (!std::getenv("APD_BLOCKING_SYNC")) h->blocking_wait = n_workers > 8;
       if (!std::getenv("APD_POLL_WAIT_US")) h->poll_wait_us = 50;  // (a look at pinned host memory: cheap)
@@ -2347,7 +2419,8 @@ int apd_batch_create_multi(const int32_t* devices, int32_t n_devices, int32_t n_
     }
   // Host threads per device: each drives n_workers / n_threads registrations at a time. Default: the host cores this
   // process may use divided by the GPUs sharing them (the devices of this context x the ranks on the node — one process
-  // per GPU: LOCAL_WORLD_SIZE as torchrun exports it), between 2 and 8. More threads than cores is what to avoid: a
+  // per GPU: LOCAL_WORLD_SIZE as torchrun exports it), between 2 and 16 (staging the 48-byte PCL layout is what the
+  // threads are for: 0.3 ms of a core per 60 k-point target). More threads than cores is what to avoid: a
   // thread that holds the CUDA driver's lock and loses its core stalls every other thread of the process (8 x B200 on 32
   // cores, 8 threads per rank: host CPU per registration 0.08 -> 0.29 ms device-resident, 0.18 -> 0.63 ms end to end).
   // APD_BATCH_THREADS overrides.
@@ -2360,7 +2433,7 @@ int apd_batch_create_multi(const int32_t* devices, int32_t n_devices, int32_t n_
     if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::atoi(e);
     if (ranks < 1) ranks = 1;
     ranks *= n_devices;
-    if (cores > 0 && ranks > 0) n_threads = std::max(2, std::min(8, cores / ranks));
+    if (cores > 0 && ranks > 0) n_threads = std::max(2, std::min(16, cores / ranks));
   }
   if (const char* e = std::getenv("APD_BATCH_THREADS")) n_threads = std::atoi(e);
   n_threads = std::max(1, std::min(n_threads, n_workers));

@@ -480,10 +480,10 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
     prep::GridJob gj[2];
     gj[0] = prep::GridJob{job.s_pts, job.n_src, job.s_cell_start, job.s_cell_cap, job.s_scratch, job.s_scratch + job.n_src,
                           job.s_scratch + 2 * (size_t)job.n_src, const_cast<float4*>(job.s_spts), const_cast<float*>(job.s_label), job.s_inv_perm,
-                          nullptr};
+                          nullptr, true};
     gj[1] = prep::GridJob{job.t_pts, job.n_tgt, const_cast<uint32_t*>(job.t_cell_start), job.t_cell_cap, job.t_scratch, job.t_scratch + job.n_tgt,
                           job.t_scratch + 2 * (size_t)job.n_tgt, const_cast<float4*>(job.t_spts), const_cast<float*>(job.t_label), job.t_inv_perm,
-                          job.t_cov_flag};
+                          job.t_cov_flag, false};
     if (first < last) prep::grids_phase(cluster, ps, gj, first, last, gt, GT);
     clk.tick(0);
     if (job.prep & 1)

@@ -52,6 +52,12 @@ struct GridJob {
   float* label;
   int* inv_perm;
   unsigned char* zero_flags;  // optional [n]
+  // ordered: points of a cell in ascending original index (the deterministic layout of grid.cu). The order of the SOURCE
+  // decides the order of every sum over source points; the order of the TARGET inside a cell decides nothing that leaves
+  // the library (searches select by the key (d2, original index); covariances, correspondences and neighbour lists are
+  // reported by original index) — so the target is placed by its atomic ranks, without the counting pass that costs
+  // O(points per cell) per point (5.5 % of the fused kernel's instructions at 6.6 active lanes).
+  bool ordered;
 };
 
 // ---- bounding boxes of both clouds: every thread strides over the points, warp min/max, CTA atomics in shared memory,
@@ -163,14 +169,19 @@ __device__ __forceinline__ void grids_phase(cg::cluster_group& cluster, PrepShar
   cluster.sync();
   for (int c = first; c < last; c++) scan_phase(cluster, ps, job[c].cell_start, ps.ncells[c] + 1);
   for (int c = first; c < last; c++)
-    for (int i = gt; i < job[c].n; i += GT) __stcg(&job[c].tmp[__ldcg(&job[c].cell_start[job[c].keys[i]]) + job[c].rank[i]], (uint32_t)i);
+    if (job[c].ordered)
+      for (int i = gt; i < job[c].n; i += GT) __stcg(&job[c].tmp[__ldcg(&job[c].cell_start[job[c].keys[i]]) + job[c].rank[i]], (uint32_t)i);
   cluster.sync();
   for (int c = first; c < last; c++)
     for (int i = gt; i < job[c].n; i += GT) {
       const uint32_t key = job[c].keys[i];
-      const uint32_t b = __ldcg(&job[c].cell_start[key]), e = __ldcg(&job[c].cell_start[key + 1]);
-      uint32_t r = 0;
-      for (uint32_t j = b; j < e; j++) r += (__ldcg(&job[c].tmp[j]) < (uint32_t)i) ? 1u : 0u;
+      const uint32_t b = __ldcg(&job[c].cell_start[key]);
+      uint32_t r = job[c].rank[i];
+      if (job[c].ordered) {
+        const uint32_t e = __ldcg(&job[c].cell_start[key + 1]);
+        r = 0;
+        for (uint32_t j = b; j < e; j++) r += (__ldcg(&job[c].tmp[j]) < (uint32_t)i) ? 1u : 0u;
+      }
       const int sp = (int)(b + r);
       const float4 p = job[c].pts[i];
       job[c].spts[sp] = make_float4(p.x, p.y, p.z, __int_as_float(i));

@@ -266,7 +266,7 @@ typedef struct apd_result {
   int32_t n_inliers;   /* source points with 1-NN d2 < 0.25 m^2 (with_fitness) */
 } apd_result;
 
-/* A batch context: `n_workers` registrations in flight (1..128; an internal handle
+/* A batch context: `n_workers` registrations in flight (1..512; an internal handle
  * with its own CUDA stream each), driven by a few host threads as non-blocking
  * state machines, that persist across calls, so device buffers, pinned staging
  * and streams are allocated once. 64 nearly saturate a B200 on scan-to-submap pairs

@@ -24,7 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=2048)
     ap.add_argument("--distinct", type=int, default=64)
-    ap.add_argument("--streams", type=int, default=128)
+    ap.add_argument("--streams", type=int, default=192)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--no-launch-rate", action="store_true")
     args = ap.parse_args()
@@ -63,7 +63,7 @@ def main():
     cpu = time.process_time() - c0
     st = b.load_stats()
     n = args.steps * args.pairs
-    ctas = int(os.environ.get("APD_LM_CLUSTER", "4"))
+    ctas = int(os.environ.get("APD_LM_CLUSTER", "2"))
     out.update({"streams": args.streams, "cluster": ctas, "threads": os.environ.get("APD_BATCH_THREADS", "default"),
                 "registrations_per_s": round(n / wall), "launches_per_s": round((b.launch_count() - l0) / wall),
                 "launches_per_registration": (b.launch_count() - l0) / n,
