@@ -206,6 +206,7 @@ struct apd_handle {
   // scratch
   DevBuf work, scratch, partials, small;  // small: out28 + ticket + fitness
   DevBuf nbuf;  // neighbour lists (n x k original ids) between the kNN search and the covariance kernel
+  DevBuf nbpts; // ... and, in the loop kernel, the neighbours' points (n_src x k float4)
   PinnedBuf h_small;
   PinnedBuf h_query;  // staging of apd_nearest_k's query points
   DevBuf lm_result;   // LmResult of the device-resident optimizer loop
@@ -279,7 +280,7 @@ struct apd_handle {
   // Scans (<= small_cloud_n points): what their grid is searched for most is their own k = 20 neighbours, and a 1-2 k-point
   // radar scan is so sparse that at 4 cells per point the 3x3x3 cube holds ~7 of them: every query walks several shells.
   // APD_CELLS_PER_POINT_SMALL overrides.
-  double cells_per_point_small = 4.0;
+  double cells_per_point_small = 1.0;  // (measured on the C3 pool: 4 -> 29.8 k, 2 -> 30.5 k, 1 -> 31.2 k, 0.5 -> 31.5 k registrations/s)
   int small_cloud_n = 8192;
   double cells_for(int n) const {
     if (cells_per_point > 0.0) return cells_per_point;
@@ -724,6 +725,7 @@ int ensure_covariances_for_loop(apd_handle* h) {
   APD_CUDA(h, t.cov.ensure((size_t)t.n * 6 * sizeof(double)));
   APD_CUDA(h, t.cov_flag.ensure((size_t)t.n));
   APD_CUDA(h, h->nbuf.ensure((size_t)std::max(h->src.n, 1) * (k + 1) * sizeof(int32_t)));
+  APD_CUDA(h, h->nbpts.ensure((size_t)std::max(h->src.n, 1) * k * sizeof(float4)));
   t.flags_fresh = false;
   rc = ensure_grid(h, t, !t.cov_lazy);  // a grid built now clears the flags on its way (saves the memset call)
   if (rc != APD_OK) return rc;
@@ -795,6 +797,7 @@ int prepare_fused(apd_handle* h, int bits) {
   }
   const int kmax = std::max(k, t.cov_lazy ? t.lazy_k : k);
   APD_CUDA(h, h->nbuf.ensure((size_t)std::max(s.n, 1) * (kmax + 1) * sizeof(int32_t)));
+  APD_CUDA(h, h->nbpts.ensure((size_t)std::max(s.n, 1) * kmax * sizeof(float4)));
   return APD_OK;
 }
 
@@ -864,6 +867,9 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
   const double n_total = h->params.variant == APD_VARIANT_GICP ? std::numeric_limits<double>::infinity() : (double)h->src.n;
   {
     ProfScope ps(h, want_hb ? APD_K_LINEARIZE : APD_K_ERROR);
+    // ranks of one process: nothing that synchronises the device (a buffer that grows: cudaFree) may run on one rank's
+    // thread while another rank's kernel already waits for it inside the exchange — meet first, launch after
+    if (h->group && !h->group->host_barrier()) return fail(h, APD_ERR_COMM, "a rank of the group did not reach the reduction");
     if (h->peers_attached) {  // the kernel's last block also exchanges the totals with the peers
       for (int r = 0; r < h->comm_size; r++) w.xchg.box[r] = h->peer_box[r];
       w.xchg.rank = h->comm_rank;
@@ -1300,12 +1306,14 @@ LmJob lm_job(apd_handle* h, const hm::Pose& x0, int prep_bits = 0) {
     j.s_reg = h->params.regularization;
     j.gicp = h->params.variant == APD_VARIANT_GICP ? 1 : 0;
     j.nb = h->nbuf.as<int32_t>();
+    j.nbp = h->nbpts.as<float4>();
   }
   if (h->tgt.cov_lazy && !h->tgt.cov_valid) {  // target covariances on demand
     j.t_cov_flag = h->tgt.cov_flag.as<unsigned char>();
     j.t_cov_rw = t.cov;
     j.t_pts = t.pts;
     j.nb = h->nbuf.as<int32_t>();
+    j.nbp = h->nbpts.as<float4>();
     j.k = h->tgt.lazy_k;
     j.reg = h->tgt.lazy_reg;
   }
@@ -1629,6 +1637,7 @@ int apd_destroy(apd_handle* h) {
   h->h_query.release();
   h->lm_result.release();
   h->nbuf.release();
+  h->nbpts.release();
   h->h_lm.release();
   cudaStreamDestroy(h->stream);
   delete h;
@@ -2106,6 +2115,8 @@ struct apd_batch {
   std::vector<std::thread> threads;
   int n_threads = 0;             // host threads per device
   std::vector<int64_t> pairs_by_device;  // how many pairs of the last call each device took (apd_batch_device_pairs)
+  int reserved_s = 0, reserved_t = 0;    // cloud sizes the workers' buffers have been sized for
+  bool reserved_host = false;            // ... including the pinned staging buffers of host clouds
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
   uint64_t generation = 0;
@@ -2358,11 +2369,62 @@ void batch_worker(apd_batch* b, int wi) {
   }
 }
 
+// Sizes every buffer a pooled registration of an (ns, nt)-point pair will touch. A buffer that grows later does it with
+// cudaFree + cudaMalloc, which synchronise the whole device — i.e. every other registration in flight; with a few pairs
+// per worker and clouds of varying size that was what a short batch spent its time on (bench.py --gpus 2: 9.9 k
+// registrations/s in the first timed arm, 46 k in the third).
+int reserve_pool_buffers(apd_handle* h, int ns, int nt, bool host_clouds) {
+  DeviceGuard dg(h->device);
+  Cloud& s = h->src;
+  Cloud& t = h->tgt;
+  const int k = h->params.k_correspondences;
+  const size_t S = (size_t)std::max(ns, 1), T = (size_t)std::max(nt, 1);
+  APD_CUDA(h, s.pts.ensure(S * sizeof(float4)));
+  APD_CUDA(h, t.pts.ensure(T * sizeof(float4)));
+  if (host_clouds) {
+    APD_CUDA(h, s.stage.ensure(S * sizeof(float4)));
+    APD_CUDA(h, t.stage.ensure(T * sizeof(float4)));
+  }
+  for (int c = 0; c < 2; c++) {
+    Cloud& cl = c == 0 ? s : t;
+    const size_t n = c == 0 ? S : T;
+    APD_CUDA(h, cl.spts.ensure(n * sizeof(float4)));
+    APD_CUDA(h, cl.label.ensure(n * sizeof(float)));
+    APD_CUDA(h, cl.inv_perm.ensure(n * sizeof(int)));
+    APD_CUDA(h, cl.cell_start.ensure((size_t)grid_cell_capacity((int)n, h->cells_for((int)n)) * sizeof(uint32_t)));
+    APD_CUDA(h, cl.cov.ensure(n * 6 * sizeof(double)));
+  }
+  APD_CUDA(h, s.geo.ensure(S * sizeof(float)));
+  APD_CUDA(h, s.geo64.ensure(S * sizeof(double)));
+  APD_CUDA(h, t.cov_flag.ensure(T));
+  APD_CUDA(h, h->work.ensure(3 * (S + T) * sizeof(uint32_t) + 512));
+  APD_CUDA(h, h->nbuf.ensure(S * (size_t)(std::max(k, 1) + 1) * sizeof(int32_t)));
+  APD_CUDA(h, h->nbpts.ensure(S * (size_t)std::max(k, 1) * sizeof(float4)));
+  APD_CUDA(h, h->corr.ensure(S * sizeof(int)));
+  APD_CUDA(h, h->sqd.ensure(S * sizeof(float)));
+  APD_CUDA(h, h->mahaA.ensure(S * sizeof(double2)));
+  APD_CUDA(h, h->mahaB.ensure(S * 2 * sizeof(double2)));
+  return APD_OK;
+}
+
 int batch_run(apd_batch* b, const apd_pair* pairs, int32_t n_pairs, int32_t stride, int32_t xyz_off, int32_t label_off, bool device_clouds,
               int32_t with_fitness, apd_result* results) {
   if (!b || !pairs || !results || n_pairs < 0) return APD_ERR_INVALID;
   if (n_pairs == 0) return APD_OK;
   if (device_clouds && b->devices.size() > 1) return APD_ERR_UNSUPPORTED;  // (a device pointer names ONE device's memory)
+  {
+    int max_s = 0, max_t = 0;
+    for (int i = 0; i < n_pairs; i++) {
+      max_s = std::max(max_s, pairs[i].n_source);
+      max_t = std::max(max_t, pairs[i].n_target);
+    }
+    if (max_s > b->reserved_s || max_t > b->reserved_t || (!device_clouds && !b->reserved_host)) {  // (before any registration is in flight)
+      b->reserved_s = std::max(b->reserved_s, max_s + max_s / 8);
+      b->reserved_t = std::max(b->reserved_t, max_t + max_t / 8);
+      b->reserved_host = b->reserved_host || !device_clouds;
+      for (auto* h : b->handles) (void)reserve_pool_buffers(h, b->reserved_s, b->reserved_t, !device_clouds);  // (best effort: set_cloud reports a real failure)
+    }
+  }
   {
     std::lock_guard<std::mutex> lk(b->mu);
     std::fill(b->pairs_by_device.begin(), b->pairs_by_device.end(), 0);
@@ -2824,6 +2886,11 @@ int apd_group_create(apd_handle* const* handles, int32_t n, apd_group** out) {
       delete g;
       return APD_ERR_CUDA;
     }
+  }
+  for (int r = 0; r < n; r++) {  // no kernel may be loaded lazily once ranks of this process wait for each other inside kernels
+    DeviceGuard dg(handles[r]->device);
+    preload_grid_kernels(); preload_knn_kernels(); preload_corr_kernels(); preload_linearize_kernels(); preload_lm_kernels();
+    preload_prep_kernels();
   }
   for (int r = 0; r < n; r++) {
     apd_handle* h = handles[r];

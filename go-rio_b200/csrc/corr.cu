@@ -292,4 +292,22 @@ void launch_transform_cloud(const float4* pts, int n, const PoseF& T, float* d_x
   (*launches)++;
 }
 
+// Loads this file's kernels into the current context (CUDA loads kernels lazily, at their first launch, and a load may have
+// to synchronise with the context: if it happens while another rank's kernel of the same process is spinning on a peer
+// — the sharded exchange — neither can proceed. apd_group_create loads everything up front.)
+void preload_corr_kernels() {
+  cudaFuncAttributes a;
+  (void)cudaFuncGetAttributes(&a, corr_search_kernel<1>);
+  (void)cudaFuncGetAttributes(&a, corr_search_kernel<2>);
+  (void)cudaFuncGetAttributes(&a, corr_search_kernel<4>);
+  (void)cudaFuncGetAttributes(&a, corr_search_kernel<8>);
+  (void)cudaFuncGetAttributes(&a, maha_kernel<false>);
+  (void)cudaFuncGetAttributes(&a, maha_kernel<true>);
+  (void)cudaFuncGetAttributes(&a, fitness_kernel);
+  (void)cudaFuncGetAttributes(&a, source_nearest_kernel);
+  (void)cudaFuncGetAttributes(&a, corr_export_kernel<false>);
+  (void)cudaFuncGetAttributes(&a, corr_export_kernel<true>);
+  (void)cudaFuncGetAttributes(&a, transform_cloud_kernel);
+}
+
 }  // namespace apd

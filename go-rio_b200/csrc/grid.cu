@@ -495,4 +495,24 @@ void launch_grid_build(const CloudDev& c, const GridWork& w, cudaStream_t s, int
   (*launches)++;
 }
 
+// Loads this file's kernels into the current context (CUDA loads kernels lazily, at their first launch, and a load may have
+// to synchronise with the context: if it happens while another rank's kernel of the same process is spinning on a peer
+// — the sharded exchange — neither can proceed. apd_group_create loads everything up front.)
+void preload_grid_kernels() {
+  cudaFuncAttributes a;
+  (void)cudaFuncGetAttributes(&a, bounds_kernel);
+  (void)cudaFuncGetAttributes(&a, init_bounds_state_kernel);
+  (void)cudaFuncGetAttributes(&a, cell_keys_kernel);
+  (void)cudaFuncGetAttributes(&a, scan_tiles_kernel);
+  (void)cudaFuncGetAttributes(&a, scan_add_kernel);
+  (void)cudaFuncGetAttributes(&a, radix_hist_kernel);
+  (void)cudaFuncGetAttributes(&a, radix_scatter_kernel);
+  (void)cudaFuncGetAttributes(&a, reorder_kernel);
+  (void)cudaFuncGetAttributes(&a, cell_keys_rank_kernel);
+  (void)cudaFuncGetAttributes(&a, scan_tiles_last_kernel);
+  (void)cudaFuncGetAttributes(&a, scatter_nd_kernel);
+  (void)cudaFuncGetAttributes(&a, rank_fix_reorder_kernel);
+  (void)cudaFuncGetAttributes(&a, grid_tiny_kernel);
+}
+
 }  // namespace apd

@@ -191,6 +191,14 @@ void launch_linearize(const CloudDev& src, const CloudDev& tgt, const ShardTable
 // number in every peer's mailbox, wait for all of them) — orders the peer-to-peer copies of the covariance all-gather
 void launch_peer_barrier(const PeerExchange& x, cudaStream_t s, int64_t* launches);
 
+// load every kernel of a translation unit into the current context now instead of at its first launch
+void preload_grid_kernels();
+void preload_knn_kernels();
+void preload_corr_kernels();
+void preload_linearize_kernels();
+void preload_lm_kernels();
+void preload_prep_kernels();
+
 // an empty kernel (launch-rate diagnostic)
 void launch_noop(cudaStream_t s, int64_t* launches);
 
@@ -239,6 +247,7 @@ struct LmJob {
   double* t_cov_rw;           // = t_cov, writable
   const float4* t_pts;        // target in ORIGINAL order (the covariance gathers its neighbours there)
   int32_t* nb;                // [n_src][k] + [n_src] scratch: neighbour ids between the search pass and the covariance pass, work list
+  float4* nbp;                // [n_src][k] scratch: the neighbours' points, gathered by the searching warp for the covariance pass
   int k, reg;                 // k_correspondences_, regularization_method_
   // Fused prologue (prep != 0; prep.cuh): the kernel is handed the RAW clouds and builds what the loop needs itself —
   // bit 0: the source's grid + covariances, bit 1: the target's grid (its covariances come on demand). The arrays above

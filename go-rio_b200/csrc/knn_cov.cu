@@ -341,4 +341,19 @@ void launch_cov_import(const CloudDev& c, const double* d_in4x4, cudaStream_t s,
   (*launches)++;
 }
 
+// Loads this file's kernels into the current context (CUDA loads kernels lazily, at their first launch, and a load may have
+// to synchronise with the context: if it happens while another rank's kernel of the same process is spinning on a peer
+// — the sharded exchange — neither can proceed. apd_group_create loads everything up front.)
+void preload_knn_kernels() {
+  cudaFuncAttributes a;
+  (void)cudaFuncGetAttributes(&a, knn_cov_kernel);
+  (void)cudaFuncGetAttributes(&a, knn_query_kernel);
+  (void)cudaFuncGetAttributes(&a, regularize_kernel);
+  (void)cudaFuncGetAttributes(&a, cov_regularize_kernel);
+  (void)cudaFuncGetAttributes(&a, knn_cov_thread_kernel);
+  (void)cudaFuncGetAttributes(&a, geo_weight_kernel);
+  (void)cudaFuncGetAttributes(&a, cov_export_kernel);
+  (void)cudaFuncGetAttributes(&a, cov_import_kernel);
+}
+
 }  // namespace apd

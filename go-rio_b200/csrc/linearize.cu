@@ -346,4 +346,21 @@ void launch_peer_barrier(const PeerExchange& x, cudaStream_t s, int64_t* launche
   (*launches)++;
 }
 
+// Loads this file's kernels into the current context (CUDA loads kernels lazily, at their first launch, and a load may have
+// to synchronise with the context: if it happens while another rank's kernel of the same process is spinning on a peer
+// — the sharded exchange — neither can proceed. apd_group_create loads everything up front.)
+void preload_linearize_kernels() {
+  cudaFuncAttributes a;
+  (void)cudaFuncGetAttributes(&a, linearize_kernel<false, false, false>);
+  (void)cudaFuncGetAttributes(&a, linearize_kernel<false, false, true>);
+  (void)cudaFuncGetAttributes(&a, linearize_kernel<false, true, false>);
+  (void)cudaFuncGetAttributes(&a, linearize_kernel<false, true, true>);
+  (void)cudaFuncGetAttributes(&a, linearize_kernel<true, false, false>);
+  (void)cudaFuncGetAttributes(&a, linearize_kernel<true, false, true>);
+  (void)cudaFuncGetAttributes(&a, linearize_kernel<true, true, false>);
+  (void)cudaFuncGetAttributes(&a, linearize_kernel<true, true, true>);
+  (void)cudaFuncGetAttributes(&a, peer_barrier_kernel);
+  (void)cudaFuncGetAttributes(&a, noop_kernel);
+}
+
 }  // namespace apd

@@ -180,4 +180,17 @@ void launch_voxel_centroids(const float4* pts, const uint32_t* keys, const uint3
   (*launches)++;
 }
 
+// Loads this file's kernels into the current context (CUDA loads kernels lazily, at their first launch, and a load may have
+// to synchronise with the context: if it happens while another rank's kernel of the same process is spinning on a peer
+// — the sharded exchange — neither can proceed. apd_group_create loads everything up front.)
+void preload_prep_kernels() {
+  cudaFuncAttributes a;
+  (void)cudaFuncGetAttributes(&a, radius_search_kernel);
+  (void)cudaFuncGetAttributes(&a, transform_d_kernel);
+  (void)cudaFuncGetAttributes(&a, voxel_bounds_kernel);
+  (void)cudaFuncGetAttributes(&a, voxel_keys_kernel);
+  (void)cudaFuncGetAttributes(&a, voxel_heads_kernel);
+  (void)cudaFuncGetAttributes(&a, voxel_centroids_kernel);
+}
+
 }  // namespace apd
