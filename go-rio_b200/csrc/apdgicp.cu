@@ -206,7 +206,6 @@ struct apd_handle {
   // scratch
   DevBuf work, scratch, partials, small;  // small: out28 + ticket + fitness
   DevBuf nbuf;  // neighbour lists (n x k original ids) between the kNN search and the covariance kernel
-  DevBuf nbpts; // ... and, in the loop kernel, the neighbours' points (n_src x k float4)
   PinnedBuf h_small;
   PinnedBuf h_query;  // staging of apd_nearest_k's query points
   DevBuf lm_result;   // LmResult of the device-resident optimizer loop
@@ -725,7 +724,6 @@ int ensure_covariances_for_loop(apd_handle* h) {
   APD_CUDA(h, t.cov.ensure((size_t)t.n * 6 * sizeof(double)));
   APD_CUDA(h, t.cov_flag.ensure((size_t)t.n));
   APD_CUDA(h, h->nbuf.ensure((size_t)std::max(h->src.n, 1) * (k + 1) * sizeof(int32_t)));
-  APD_CUDA(h, h->nbpts.ensure((size_t)std::max(h->src.n, 1) * k * sizeof(float4)));
   t.flags_fresh = false;
   rc = ensure_grid(h, t, !t.cov_lazy);  // a grid built now clears the flags on its way (saves the memset call)
   if (rc != APD_OK) return rc;
@@ -797,7 +795,6 @@ int prepare_fused(apd_handle* h, int bits) {
   }
   const int kmax = std::max(k, t.cov_lazy ? t.lazy_k : k);
   APD_CUDA(h, h->nbuf.ensure((size_t)std::max(s.n, 1) * (kmax + 1) * sizeof(int32_t)));
-  APD_CUDA(h, h->nbpts.ensure((size_t)std::max(s.n, 1) * kmax * sizeof(float4)));
   return APD_OK;
 }
 
@@ -1306,14 +1303,12 @@ LmJob lm_job(apd_handle* h, const hm::Pose& x0, int prep_bits = 0) {
     j.s_reg = h->params.regularization;
     j.gicp = h->params.variant == APD_VARIANT_GICP ? 1 : 0;
     j.nb = h->nbuf.as<int32_t>();
-    j.nbp = h->nbpts.as<float4>();
   }
   if (h->tgt.cov_lazy && !h->tgt.cov_valid) {  // target covariances on demand
     j.t_cov_flag = h->tgt.cov_flag.as<unsigned char>();
     j.t_cov_rw = t.cov;
     j.t_pts = t.pts;
     j.nb = h->nbuf.as<int32_t>();
-    j.nbp = h->nbpts.as<float4>();
     j.k = h->tgt.lazy_k;
     j.reg = h->tgt.lazy_reg;
   }
@@ -1637,7 +1632,6 @@ int apd_destroy(apd_handle* h) {
   h->h_query.release();
   h->lm_result.release();
   h->nbuf.release();
-  h->nbpts.release();
   h->h_lm.release();
   cudaStreamDestroy(h->stream);
   delete h;
@@ -2399,7 +2393,6 @@ int reserve_pool_buffers(apd_handle* h, int ns, int nt, bool host_clouds) {
   APD_CUDA(h, t.cov_flag.ensure(T));
   APD_CUDA(h, h->work.ensure(3 * (S + T) * sizeof(uint32_t) + 512));
   APD_CUDA(h, h->nbuf.ensure(S * (size_t)(std::max(k, 1) + 1) * sizeof(int32_t)));
-  APD_CUDA(h, h->nbpts.ensure(S * (size_t)std::max(k, 1) * sizeof(float4)));
   APD_CUDA(h, h->corr.ensure(S * sizeof(int)));
   APD_CUDA(h, h->sqd.ensure(S * sizeof(float)));
   APD_CUDA(h, h->mahaA.ensure(S * sizeof(double2)));

@@ -247,7 +247,6 @@ struct LmJob {
   double* t_cov_rw;           // = t_cov, writable
   const float4* t_pts;        // target in ORIGINAL order (the covariance gathers its neighbours there)
   int32_t* nb;                // [n_src][k] + [n_src] scratch: neighbour ids between the search pass and the covariance pass, work list
-  float4* nbp;                // [n_src][k] scratch: the neighbours' points, gathered by the searching warp for the covariance pass
   int k, reg;                 // k_correspondences_, regularization_method_
   // Fused prologue (prep != 0; prep.cuh): the kernel is handed the RAW clouds and builds what the loop needs itself —
   // bit 0: the source's grid + covariances, bit 1: the target's grid (its covariances come on demand). The arrays above

@@ -171,8 +171,8 @@ __device__ __forceinline__ unsigned flag_acquire(const unsigned char* f) {
 
 // covariance + regularisation of target point `pos` from its neighbour ids (the per-cloud kernels' code: same bits);
 // __noinline__ keeps the Jacobi sweep's registers out of the optimizer loop
-__device__ __noinline__ void lazy_target_covariance(const LmJob& job, const float4* nbp, int pos) {
-  const Sym3 C = knnw::covariance_of_points(nbp, job.k, job.reg);
+__device__ __noinline__ void lazy_target_covariance(const LmJob& job, const int32_t* nbq, int pos) {
+  const Sym3 C = knnw::covariance_of_neighbors(job.t_pts, nbq, job.k, job.reg);
 #pragma unroll
   for (int e = 0; e < 6; e++) __stcg(job.t_cov_rw + (size_t)pos * 6 + e, C.v[e]);
   flag_publish(&job.t_cov_flag[pos]);
@@ -259,11 +259,11 @@ __device__ __forceinline__ void corr_phase(const LmJob& job, const LmConfig& cfg
       li = __shfl_sync(0xffffffffu, li, 0);
       if (li >= n_need) break;
       const unsigned long long key = knnw::knn_warp_query(job.t_spts, job.t_cell_start, job.tg, job.k, list[base + li], lane, smem.kbuf[warp]);
-      if (lane < job.k) job.nbp[(size_t)(base + li) * job.k + lane] = __ldg(&job.t_pts[(int)(unsigned)(key & 0xffffffffull)]);
+      if (lane < job.k) job.nb[(size_t)(base + li) * job.k + lane] = (int)(unsigned)(key & 0xffffffffull);
     }
     __syncthreads();
     clk.tick(3);
-    for (int li = tid; li < n_need; li += kLmThreads) lazy_target_covariance(job, job.nbp + (size_t)(base + li) * job.k, list[base + li]);
+    for (int li = tid; li < n_need; li += kLmThreads) lazy_target_covariance(job, job.nb + (size_t)(base + li) * job.k, list[base + li]);
     __threadfence();
     __syncthreads();
     clk.tick(4);
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
     if (first < last) prep::grids_phase(cluster, ps, gj, first, last, gt, GT);
     clk.tick(0);
     if (job.prep & 1)
-      prep::source_cov_phase(cluster, job.s_pts, job.s_spts, job.s_cell_start, s_grid, job.n_src, job.s_k, job.s_reg, job.gicp, job.nbp,
+      prep::source_cov_phase(cluster, job.s_pts, job.s_spts, job.s_cell_start, s_grid, job.n_src, job.s_k, job.s_reg, job.gicp, job.nb,
                              const_cast<double*>(job.s_cov), const_cast<float*>(job.s_geo), const_cast<double*>(job.s_geo64), s.kbuf[tid >> 5], gt, GT);
     clk.tick(1);
   }

@@ -196,16 +196,16 @@ __device__ __forceinline__ void grids_phase(cg::cluster_group& cluster, PrepShar
 // point for the exact kNN search, then one THREAD per point for covariance + regularisation + geometric weight — the
 // two per-cloud kernels of knn_cov.cu, with a cluster barrier between them
 __device__ __forceinline__ void source_cov_phase(cg::cluster_group& cluster, const float4* pts, const float4* spts, const uint32_t* cell_start,
-                                                 const GridDesc& g, int n, int k, int reg, int gicp, float4* nbp, double* cov, float* geo, double* geo64,
+                                                 const GridDesc& g, int n, int k, int reg, int gicp, int32_t* nb, double* cov, float* geo, double* geo64,
                                                  unsigned long long* kbuf, int gt, int GT) {
   const int lane = threadIdx.x & 31;
   for (int w = gt >> 5; w < n; w += GT >> 5) {
     const unsigned long long key = knnw::knn_warp_query(spts, cell_start, g, k, w, lane, kbuf);
-    if (lane < k) nbp[(size_t)w * k + lane] = __ldg(&pts[(int)(unsigned)(key & 0xffffffffull)]);  // (the raw cloud: read-only input)
+    if (lane < k) nb[(size_t)w * k + lane] = (int)(unsigned)(key & 0xffffffffull);
   }
   cluster.sync();
   for (int w = gt; w < n; w += GT) {
-    const Sym3 out = knnw::covariance_of_points(nbp + (size_t)w * k, k, reg);
+    const Sym3 out = knnw::covariance_of_neighbors(pts, nb + (size_t)w * k, k, reg);
 #pragma unroll
     for (int e = 0; e < 6; e++) cov[(size_t)w * 6 + e] = out.v[e];
     const double gw = gicp ? 0.0 : knnw::geo_weight_of(out);  // FastGICP weighs every term by 1 (fast_gicp_impl.hpp:205)

@@ -33,9 +33,10 @@ elif case == "group":
     grp = gorio.Group([0, 0], max_correspondence_distance=2.0)
     grp.set_input_target(t); grp.set_input_source(s); print("group ok", grp.linearize(T)[0]); grp.close()
 PY
-for tool in memcheck racecheck synccheck; do
-  for case in smoke pool eager group; do
-    timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py $case > $OUT/${tool}_${case}.log 2>&1
-    echo "$tool $case rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $OUT/${tool}_${case}.log | tail -1)"
-  done
-done
+run() {
+  timeout 900 compute-sanitizer --tool $1 --print-limit 20 python /tmp/san_case.py $2 > $OUT/$1_$2.log 2>&1
+  echo "$1 $2 rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $OUT/$1_$2.log | tail -1) | $(grep -E ' ok' $OUT/$1_$2.log | tail -1)"
+}
+for case in smoke pool eager group; do run memcheck $case; done
+for case in pool eager; do run racecheck $case; done
+for case in pool group; do run synccheck $case; done
