@@ -65,7 +65,10 @@ __device__ __forceinline__ unsigned long long insert_keep32(unsigned long long l
 }
 constexpr int kInsertMax = 10;  // a flush of up to this many candidates inserts them one by one (~12 instructions each)
                                 // instead of the 32-key sort + merge (~180): most flushes at the end of a shell are small
-__device__ __forceinline__ void kbest_flush(KBest& s, int lane, int k) {
+// (__noinline__: the flush is the bulk of the search's code and is reached from four places; one copy keeps the loop
+// kernel's hot path inside the instruction cache — under a pool's co-residency 8 % of its stall cycles were
+// instruction fetches)
+static __device__ __noinline__ void kbest_flush(KBest& s, int lane, int k) {
   if (s.buf_n == 0) return;  // warp-uniform
   __syncwarp();
   if (!s.empty && s.buf_n <= kInsertMax) {
@@ -138,7 +141,7 @@ __device__ __forceinline__ void scan_segments(const float4* spts, float qx, floa
 // (d2, original index) key per lane, ascending: lanes 0..k-1 hold the answer. kbuf: 32 keys of shared memory owned by
 // this warp. Replaces the nearestKSearch of reference fast_apdgicp_impl.hpp:364.
 // knn_warp_query_at: the same for an arbitrary query point q (not necessarily a point of the cloud).
-__device__ __forceinline__ unsigned long long knn_warp_query_at(const float4* spts, const uint32_t* cell_start,
+static __device__ __noinline__ unsigned long long knn_warp_query_at(const float4* spts, const uint32_t* cell_start,
                                                                 const GridDesc& g, int k, const float4 q, int lane, unsigned long long* kbuf) {
   const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
   const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
