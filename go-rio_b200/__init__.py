@@ -116,6 +116,25 @@ class Batch:
         device = len(pairs) > 0 and isinstance(pairs[0][0], tuple)
         return dict(arr=arr, keep=keep, n=len(pairs), device=device, res=(ApdResult * len(pairs))(), layout=layout)
 
+    def repeat(self, prepared, k):
+        """the prepared pair list k times over, as ONE list (k passes over a batch without draining the pool in between)"""
+        n = prepared["n"]
+        arr = (ApdPair * (n * k))()
+        size = ctypes.sizeof(ApdPair) * n
+        for j in range(k):
+            ctypes.memmove(ctypes.addressof(arr) + j * size, prepared["arr"], size)
+        return dict(arr=arr, keep=[prepared], n=n * k, device=prepared["device"], res=(ApdResult * (n * k))(), layout=prepared.get("layout", (16, 0, 12)))
+
+    @staticmethod
+    def results_view(res):
+        """the C result array as a NumPy structured array (no copy)"""
+        import numpy as np
+
+        dt = np.dtype([("T", np.float32, (16,)), ("fitness", np.float64), ("converged", np.int32), ("iterations", np.int32),
+                       ("status", np.int32), ("n_inliers", np.int32)])
+        assert dt.itemsize == ctypes.sizeof(ApdResult)
+        return np.frombuffer(res, dtype=dt)
+
     def device_pairs(self):
         out = (ctypes.c_int64 * len(self.devices))()
         self._lib.apd_batch_device_pairs(self._b, out, ctypes.c_int32(len(self.devices)))

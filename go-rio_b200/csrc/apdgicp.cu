@@ -196,7 +196,8 @@ struct apd_handle {
   std::string error;
   Cloud src, tgt;
   // per-linearisation state (sorted order of the source)
-  DevBuf corr, sqd, mahaA, mahaB;
+  DevBuf corr, sqd, second, mahaA, mahaB;
+  bool second_valid = false;  // `second` holds the bounds of the pass the warm start refers to (single-lane search)
   int corr_n = -1;          // number of source points the buffers describe (-1: none yet)
   // warm start of update_correspondences: the buffers hold a pass over the CURRENT clouds at corr_pose with corr_thr
   bool corr_warm = false;
@@ -645,6 +646,13 @@ int group_allgather_chunks(apd_handle* h, void* base, int n, size_t bytes_per_po
   // behind its own pulls
   launch_peer_barrier(barrier_ticket(h), h->stream, &h->launches);
   APD_CUDA(h, cudaGetLastError());
+  // The rank threads share ONE process: whatever one of them does next that synchronises the device (a buffer of the
+  // next cloud that grows: cudaFree; a first allocation) would wait for a barrier kernel that is still spinning for a
+  // peer whose launch in turn waits for the driver's lock. So: every rank drains its stream, then the threads meet —
+  // no barrier kernel of the group is left on the device when any of them goes on. (Seen as a 5 s time-out + NaN sums in
+  // one run of the full test suite, never in the sharding tests alone.)
+  APD_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (!g->host_barrier()) return fail(h, APD_ERR_COMM, "a rank of the group did not finish the all-gather");
   return APD_OK;
 }
 
@@ -825,6 +833,8 @@ CorrOut corr_view(apd_handle* h) {
   CorrOut c;
   c.corr = h->corr.as<int>();
   c.sqd = h->sqd.as<float>();
+  c.second = h->second.as<float>();
+  c.second_valid = h->second_valid ? 1 : 0;
   c.maha_fp64 = h->corr_fp64;
   c.mahaA = h->mahaA.p;
   c.mahaB = h->mahaB.p;  // fp64 storage: two planes of local_n double2
@@ -839,8 +849,10 @@ int do_update_correspondences(apd_handle* h, const hm::Pose& T) {
   {
     ProfScope ps(h, APD_K_CORR);
     const bool warm = h->corr_warm && h->corr_n == h->src.n && h->corr_thr == h->params.max_correspondence_distance;
-    launch_update_correspondences(h->src.view(), h->tgt.view(), h->shard_table(h->src.n), to_pose_d(T), np, corr_view(h),
-                                  warm ? &h->corr_pose : nullptr, h->corr_lanes, h->stream, &h->launches);
+    if (!warm) h->second_valid = false;
+    const int lanes = launch_update_correspondences(h->src.view(), h->tgt.view(), h->shard_table(h->src.n), to_pose_d(T), np, corr_view(h),
+                                                    warm ? &h->corr_pose : nullptr, h->corr_lanes, h->stream, &h->launches);
+    h->second_valid = lanes == 1;
   }
   APD_CUDA(h, cudaGetLastError());
   h->corr_n = h->src.n;
@@ -887,6 +899,9 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
   double* hs = reinterpret_cast<double*>(h->h_small.p);
   APD_CUDA(h, cudaMemcpyAsync(hs, d_out, kReduceVals * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   APD_CUDA(h, wait_stream(h));
+  // (ranks of one process: nobody goes on — possibly to a call that synchronises the device — while a peer's kernel may
+  // still be waiting inside the exchange for a rank whose launch has not gone through yet; see group_allgather_chunks)
+  if (h->group && !h->group->host_barrier()) return fail(h, APD_ERR_COMM, "a rank of the group did not finish the reduction");
   if (want_hb) {
     if (H36) hm::unpack_upper(hs, H36);
     if (b6) std::memcpy(b6, hs + 21, 6 * sizeof(double));
@@ -1242,6 +1257,7 @@ int ensure_corr_buffers(apd_handle* h) {
   const int fp64 = h->params.maha_fp64 ? 1 : 0;
   APD_CUDA(h, h->corr.ensure(n * sizeof(int)));
   APD_CUDA(h, h->sqd.ensure(n * sizeof(float)));
+  APD_CUDA(h, h->second.ensure(n * sizeof(float)));
   APD_CUDA(h, h->mahaA.ensure(n * (fp64 ? sizeof(double2) : sizeof(float4))));
   APD_CUDA(h, h->mahaB.ensure(n * (fp64 ? 2 * sizeof(double2) : sizeof(float2))));
   h->corr_fp64 = fp64;
@@ -1626,7 +1642,7 @@ int apd_destroy(apd_handle* h) {
   for (auto e : h->event_pool) cudaEventDestroy(e);
   if (h->done_ev) cudaEventDestroy(h->done_ev);
   h->src.release(); h->tgt.release();
-  h->corr.release(); h->sqd.release(); h->mahaA.release(); h->mahaB.release();
+  h->corr.release(); h->sqd.release(); h->second.release(); h->mahaA.release(); h->mahaB.release();
   h->work.release(); h->scratch.release(); h->partials.release(); h->small.release();
   h->h_small.release();
   h->h_query.release();
@@ -2395,6 +2411,7 @@ int reserve_pool_buffers(apd_handle* h, int ns, int nt, bool host_clouds) {
   APD_CUDA(h, h->nbuf.ensure(S * (size_t)(std::max(k, 1) + 1) * sizeof(int32_t)));
   APD_CUDA(h, h->corr.ensure(S * sizeof(int)));
   APD_CUDA(h, h->sqd.ensure(S * sizeof(float)));
+  APD_CUDA(h, h->second.ensure(S * sizeof(float)));
   APD_CUDA(h, h->mahaA.ensure(S * sizeof(double2)));
   APD_CUDA(h, h->mahaB.ensure(S * 2 * sizeof(double2)));
   return APD_OK;

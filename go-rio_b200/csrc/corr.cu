@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(kThreads) corr_search_kernel(const float4* __r
                                                                ShardTable sh, const float4* __restrict__ t_spts,
                                                                const float* __restrict__ t_label, const uint32_t* __restrict__ t_cell_start,
                                                                GridDesc tg, PoseF Tf, double thr_sq, int* __restrict__ corr,
-                                                               float* __restrict__ sqd, int warm, PoseF Tpf) {
+                                                               float* __restrict__ sqd, int warm, PoseF Tpf, float* __restrict__ second,
+                                                               int second_valid) {
   // kThreads and the warp size are multiples of G, so a group never straddles a warp; the lanes of a group share the
   // slot, so a padding slot retires its whole group (every shuffle below is masked to the group's own lanes)
   const int l = (int)(((size_t)blockIdx.x * kThreads + threadIdx.x) / G);
@@ -48,6 +49,26 @@ __global__ void __launch_bounds__(kThreads) corr_search_kernel(const float4* __r
 
   // warm: corr / sqd still hold the previous pass over the same clouds (pose T_prev) — see warm_start
   int seed = -1;
+  if (G == 1 && warm && second_valid) {
+    // The previous pass left, next to each match, a lower bound of the squared distance of every OTHER target point
+    // (second[l], nn_search_lane_t). The point has moved by delta since: every other target point is still at least
+    // sqrt(second) - delta away. If the old match, at its new exact distance, is closer than that (with margins far
+    // above the fp32 rounding of the distances), it is still THE nearest neighbour by (d2, index): no search.
+    const int pc = corr[l];
+    if (pc >= 0) {
+      const float4 p = t_spts[pc & kCorrIndexMask];
+      const float d1 = sqdist_rn(px, py, pz, p.x, p.y, p.z);
+      float ox, oy, oz;
+      transform_rn(Tpf, a.x, a.y, a.z, ox, oy, oz);
+      const float delta = sqrtf(sqdist_rn(px, py, pz, ox, oy, oz)) * 1.0001f;
+      const float lb = sqrtf(second[l]) * 0.9999f - delta;
+      if (lb > 0.f && d1 * 1.001f < lb * lb && (double)d1 < thr_sq) {
+        sqd[l] = d1;            // :180, the distance the search would have found
+        second[l] = lb * lb;    // the bound, carried to the new position
+        return;                 // corr[l] (match + label bit) stays
+      }
+    }
+  }
   if (warm) {
     float kept;
     if (!warm_start(Tpf, a, px, py, pz, corr[l], sqd[l], thr_sq, seed, kept)) {  // (uniform over the G lanes of a query)
@@ -59,8 +80,9 @@ __global__ void __launch_bounds__(kThreads) corr_search_kernel(const float4* __r
   }
   unsigned long long best;
   int pos;
-  float proven2;
-  nn_search<G>(t_spts, t_cell_start, tg, px, py, pz, thr_sq, best, pos, seed, proven2);  // :178
+  float proven2, second2 = 0.f;
+  if (G == 1) nn_search_lane_t<true>(t_spts, t_cell_start, tg, px, py, pz, thr_sq, best, pos, seed, proven2, second2);  // :178
+  else nn_search<G>(t_spts, t_cell_start, tg, px, py, pz, thr_sq, best, pos, seed, proven2);
   if (G > 1 && (threadIdx.x & (G - 1)) != 0) return;  // one lane per point finishes the job
   const float d2 = (best == kInfKey) ? 3.402823466e38f : __uint_as_float((unsigned)(best >> 32));
   const bool ok = (best != kInfKey) && ((double)d2 < thr_sq);  // :183
@@ -71,6 +93,7 @@ __global__ void __launch_bounds__(kThreads) corr_search_kernel(const float4* __r
     return;
   }
   sqd[l] = d2;  // :180
+  if (G == 1) second[l] = second2;
   corr[l] = pos | ((__ldg(&t_label[pos]) == s_label[i]) ? kCorrLabelBit : 0);  // label test of :271-273, hoisted
 }
 
@@ -230,10 +253,10 @@ __global__ void __launch_bounds__(256) transform_cloud_kernel(const float4* __re
 
 }  // namespace
 
-void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const PoseD& T, const NoiseParams& np,
-                                   const CorrOut& out, const PoseD* T_prev, int lanes, cudaStream_t s, int64_t* launches) {
+int launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const PoseD& T, const NoiseParams& np,
+                                  const CorrOut& out, const PoseD* T_prev, int lanes, cudaStream_t s, int64_t* launches) {
   const int slots = sh.slots();
-  if (slots <= 0) return;
+  if (slots <= 0) return 0;
   // small source clouds are latency-bound: 8 lanes share a query; large ones are throughput-bound (see DESIGN.md §4.3 for
   // the measured choice). All variants give identical results.
   // (Tried and dropped, 20 M points on B200: staging the union box of a warp's 32 query cubes in shared memory with bulk
@@ -243,7 +266,8 @@ void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, con
   const PoseF Tf = pose_to_f32_host(T), Tpf = pose_to_f32_host(T_prev ? *T_prev : T);
 #define APD_SEARCH(GG)                                                                                                                 \
   corr_search_kernel<GG><<<(unsigned)(((size_t)slots * GG + kThreads - 1) / kThreads), kThreads, 0, s>>>(                               \
-      src.spts, src.label, sh, tgt.spts, tgt.label, tgt.cell_start, tgt.g, Tf, np.thr_sq, out.corr, out.sqd, T_prev ? 1 : 0, Tpf)
+      src.spts, src.label, sh, tgt.spts, tgt.label, tgt.cell_start, tgt.g, Tf, np.thr_sq, out.corr, out.sqd, T_prev ? 1 : 0, Tpf, out.second,  \
+      (T_prev && out.second_valid && GG == 1) ? 1 : 0)
   switch (lanes) {
     case 1: APD_SEARCH(1); break;
     case 2: APD_SEARCH(2); break;
@@ -256,6 +280,7 @@ void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, con
   if (out.maha_fp64) maha_kernel<true><<<mblocks, 256, 0, s>>>(src.spts, src.cov, sh, tgt.cov, T, np, out.corr, out.mahaA, out.mahaB);
   else maha_kernel<false><<<mblocks, 256, 0, s>>>(src.spts, src.cov, sh, tgt.cov, T, np, out.corr, out.mahaA, out.mahaB);
   (*launches)++;
+  return lanes;
 }
 
 void launch_fitness(const CloudDev& src, const CloudDev& tgt, const PoseF& T, double max_range, double inlier_sq_thr,

@@ -130,6 +130,8 @@ struct NoiseParams {
 struct CorrOut {
   int* corr;      // [n_src] sorted order of the source
   float* sqd;     // [n_src]
+  float* second;  // [n_src] lower bound of the squared distance of every target point other than the match (single-lane search)
+  int second_valid;  // `second` was written by the previous pass over the same clouds
   void* mahaA;    // float4[n] or double2[n] {xx,xy | ...} see common.cuh
   void* mahaB;    // float2[n] or double2[2n]
   int maha_fp64;
@@ -139,8 +141,9 @@ struct CorrOut {
 // noise model / combined covariance / inverse (:194-218; reads the matched pairs coalesced, writes the Mahalanobis
 // planes). T_prev != nullptr: `out` still holds the result of the previous pass over the same clouds at pose T_prev,
 // which warm-starts the searches (identical results). lanes: lanes per 1-NN query (0: by cloud size).
-void launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const PoseD& T, const NoiseParams& np,
-                                   const CorrOut& out, const PoseD* T_prev, int lanes, cudaStream_t s, int64_t* launches);
+// Returns the lanes per query it used (1: `out.second` now holds the bounds of this pass).
+int launch_update_correspondences(const CloudDev& src, const CloudDev& tgt, const ShardTable& sh, const PoseD& T, const NoiseParams& np,
+                                  const CorrOut& out, const PoseD* T_prev, int lanes, cudaStream_t s, int64_t* launches);
 // getFitnessScore + inlier count: d_out = {sum d2 (double), n_in_range (as double), n_inliers (as double)}
 void launch_fitness(const CloudDev& src, const CloudDev& tgt, const PoseF& T, double max_range, double inlier_sq_thr,
                     double* d_partials, int max_blocks, double* d_out3, unsigned int* d_ticket, cudaStream_t s,

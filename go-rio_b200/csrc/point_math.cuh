@@ -22,6 +22,29 @@ __device__ __forceinline__ void scan_range(const float4* spts, int b, int e, flo
   }
 }
 
+// The same, also keeping `second2`: a lower bound of the squared distance of every scanned point OTHER than the best one
+// (the seed of a warm-started search is met again at its own position: it is not "another" point).
+template <bool kTrack>
+__device__ __forceinline__ void scan_range_t(const float4* spts, int b, int e, float qx, float qy, float qz,
+                                             unsigned long long& best, int& best_pos, float& second2) {
+  if constexpr (!kTrack) {
+    scan_range(spts, b, e, qx, qy, qz, best, best_pos);
+  } else {
+    for (int j = b; j < e; j++) {
+      const float4 p = spts[j];
+      const float d = sqdist_rn(qx, qy, qz, p.x, p.y, p.z);
+      const unsigned long long key = pack_key(d, __float_as_int(p.w));
+      if (key < best) {
+        second2 = fminf(second2, __uint_as_float((unsigned)(best >> 32)));  // (no best yet: NaN, which fminf ignores)
+        best = key;
+        best_pos = j;
+      } else if (j != best_pos) {
+        second2 = fminf(second2, d);
+      }
+    }
+  }
+}
+
 // Exact nearest neighbour by (d2, original index). Expands Chebyshev shells of
 // cells until the best distance is provably final, or until every unscanned
 // point is farther than `limit` (then the caller rejects the match anyway).
@@ -171,8 +194,14 @@ __device__ __forceinline__ float slab_dist2(float q, float o, int c, float cell,
   const float d = fmaxf(0.f, fmaxf(lo - q, q - hi));
   return d * d;
 }
-__device__ __forceinline__ void nn_search_lane(const float4* spts, const uint32_t* cell_start, const GridDesc& g, float qx, float qy, float qz,
-                                               double limit_sq, unsigned long long& best, int& best_pos, int seed_pos, float& proven2) {
+// kTrack: also returns second2, a lower bound of the squared distance of EVERY target point other than the one returned —
+// the scanned ones by their distances, the rows / cells / slabs that were skipped by the bound they were skipped with, the
+// rest by proven2. It is what lets the next pass over the same clouds keep a match without searching (corr.cu).
+template <bool kTrack>
+__device__ __forceinline__ void nn_search_lane_t(const float4* spts, const uint32_t* cell_start, const GridDesc& g, float qx, float qy, float qz,
+                                                 double limit_sq, unsigned long long& best, int& best_pos, int seed_pos, float& proven2,
+                                                 float& second2) {
+  second2 = 3.4e38f;
   const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
   const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
   const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
@@ -197,12 +226,21 @@ __device__ __forceinline__ void nn_search_lane(const float4* spts, const uint32_
   auto scan_row = [&](int oy, int oz, float ryz, bool own) {
     const bool have = best != kInfKey;
     const float bd = __uint_as_float((unsigned)(best >> 32));
-    if (have && !own && ryz * 0.9999f > bd) return;  // even the row's nearest point cannot beat the current best
+    if (have && !own && ryz * 0.9999f > bd) {  // even the row's nearest point cannot beat the current best
+      if (kTrack) second2 = fminf(second2, ryz * 0.9999f);
+      return;
+    }
     // the end cells of the row are only read if their corner can
-    const int xa = (cx > 0 && !(have && (ryz + dx2[0]) * 0.9999f > bd)) ? cx - 1 : cx;
-    const int xb = (cx < g.nx - 1 && !(have && (ryz + dx2[2]) * 0.9999f > bd)) ? cx + 1 : cx;
+    const float ea = (ryz + dx2[0]) * 0.9999f, eb = (ryz + dx2[2]) * 0.9999f;
+    const bool skip_a = have && ea > bd, skip_b = have && eb > bd;
+    const int xa = (cx > 0 && !skip_a) ? cx - 1 : cx;
+    const int xb = (cx < g.nx - 1 && !skip_b) ? cx + 1 : cx;
+    if (kTrack) {
+      if (cx > 0 && skip_a) second2 = fminf(second2, ea);
+      if (cx < g.nx - 1 && skip_b) second2 = fminf(second2, eb);
+    }
     const int row = ((cz + oz - 1) * g.ny + (cy + oy - 1)) * g.nx;
-    scan_range(spts, (int)cell_start[row + xa], (int)cell_start[row + xb + 1], qx, qy, qz, best, best_pos);
+    scan_range_t<kTrack>(spts, (int)cell_start[row + xa], (int)cell_start[row + xb + 1], qx, qy, qz, best, best_pos, second2);
   };
   if (cy >= 0 && cy < g.ny && cz >= 0 && cz < g.nz) scan_row(1, 1, dy2[1] + dz2[1], true);
   unsigned m = 0;
@@ -213,8 +251,11 @@ __device__ __forceinline__ void nn_search_lane(const float4* spts, const uint32_
     for (int k = 0; k < 8; k++) {
       const int idx = k < 4 ? k : k + 1, oy = idx % 3, oz = idx / 3;  // (compile-time)
       const int y = cy + oy - 1, z = cz + oz - 1;
-      const bool keep = y >= 0 && y < g.ny && z >= 0 && z < g.nz && !(have && (dy2[oy] + dz2[oz]) * 0.9999f > bd);
-      m |= keep ? (1u << k) : 0u;
+      const bool inside = y >= 0 && y < g.ny && z >= 0 && z < g.nz;
+      const float rb = (dy2[oy] + dz2[oz]) * 0.9999f;
+      const bool far = have && rb > bd;
+      if (kTrack && inside && far) second2 = fminf(second2, rb);
+      m |= (inside && !far) ? (1u << k) : 0u;
     }
   }
   while (m) {
@@ -245,23 +286,35 @@ __device__ __forceinline__ void nn_search_lane(const float4* spts, const uint32_
     for (int z = max(cz - rr, 0); z <= min(cz + rr, g.nz - 1); z++) {
       const float sz2 = slab_dist2(qz, g.oz, z, g.cell, mg);
       if ((double)(sz2 * 0.9999f) >= prune_sq) continue;
-      if (best != kInfKey && sz2 * 0.9999f > __uint_as_float((unsigned)(best >> 32))) continue;  // the whole slab of rows
+      if (best != kInfKey && sz2 * 0.9999f > __uint_as_float((unsigned)(best >> 32))) {  // the whole slab of rows
+        if (kTrack) second2 = fminf(second2, sz2 * 0.9999f);
+        continue;
+      }
       const bool z_outer = z > cz + r || z < cz - r;
       for (int y = max(cy - rr, 0); y <= min(cy + rr, g.ny - 1); y++) {
         const float dyz2 = (slab_dist2(qy, g.oy, y, g.cell, mg) + sz2) * 0.9999f;
         if ((double)dyz2 >= prune_sq) continue;
-        if (best != kInfKey && dyz2 > __uint_as_float((unsigned)(best >> 32))) continue;
+        if (best != kInfKey && dyz2 > __uint_as_float((unsigned)(best >> 32))) {
+          if (kTrack) second2 = fminf(second2, dyz2);
+          continue;
+        }
         const int row = (z * g.ny + y) * g.nx;
         if (z_outer || y > cy + r || y < cy - r) {  // row outside the scanned cube: its whole x-range
-          scan_range(spts, (int)cell_start[row + x0], (int)cell_start[row + x1 + 1], qx, qy, qz, best, best_pos);
+          scan_range_t<kTrack>(spts, (int)cell_start[row + x0], (int)cell_start[row + x1 + 1], qx, qy, qz, best, best_pos, second2);
         } else {  // row crosses the scanned cube: the two end pieces
-          if (x0 <= xl) scan_range(spts, (int)cell_start[row + x0], (int)cell_start[row + xl + 1], qx, qy, qz, best, best_pos);
-          if (xr <= x1) scan_range(spts, (int)cell_start[row + xr], (int)cell_start[row + x1 + 1], qx, qy, qz, best, best_pos);
+          if (x0 <= xl) scan_range_t<kTrack>(spts, (int)cell_start[row + x0], (int)cell_start[row + xl + 1], qx, qy, qz, best, best_pos, second2);
+          if (xr <= x1) scan_range_t<kTrack>(spts, (int)cell_start[row + xr], (int)cell_start[row + x1 + 1], qx, qy, qz, best, best_pos, second2);
         }
       }
     }
     r = rr;
   }
+  if (kTrack) second2 = fminf(second2, proven2);  // everything that was never looked at
+}
+__device__ __forceinline__ void nn_search_lane(const float4* spts, const uint32_t* cell_start, const GridDesc& g, float qx, float qy, float qz,
+                                               double limit_sq, unsigned long long& best, int& best_pos, int seed_pos, float& proven2) {
+  float second2;
+  nn_search_lane_t<false>(spts, cell_start, g, qx, qy, qz, limit_sq, best, best_pos, seed_pos, proven2, second2);
 }
 
 // seed_pos >= 0: a target point (sorted position) to start from — the previous iteration's match. Its distance

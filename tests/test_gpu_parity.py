@@ -229,6 +229,34 @@ def test_update_correspondences_variants(gorio, synth, c2, monkeypatch, mode):
             assert rel(g.get_mahalanobis(), o.get_mahalanobis()) < 1e-10
 
 
+def test_kept_matches_equal_a_cold_search(gorio, synth, c2, monkeypatch):
+    """the single-lane search keeps a match without searching when the bound it stored for every OTHER target point
+    proves it (corr.cu): a chain of small motions — bounds carried from pass to pass, never refreshed for most points —
+    must give, at every pose, exactly what a fresh handle's cold search and the oracle give"""
+    src, tgt, Tgt = c2
+    monkeypatch.setenv("APD_CORR_MODE", "lane")
+    g, o = make(gorio, src, tgt, max_correspondence_distance=2.0, maha_fp64=1, host_loop=1)
+    T = Tgt.copy()
+    rng = np.random.default_rng(5)
+    for i in range(14):
+        step = synth.make_pose(rng.normal(0, 0.004, 3), rng.normal(0, 0.0004, 3)) if i % 5 != 4 else synth.make_pose([0.3, -0.2, 0.05], [0.0, 0.01, 0.02])
+        T = T @ step
+        g.update_correspondences(T); o.update_correspondences(T)
+        cg, sg = g.get_correspondences()
+        co, so = o.get_correspondences()
+        assert np.array_equal(cg, co), i
+        assert np.array_equal(sg[cg >= 0], so[co >= 0]), i
+        if i in (3, 13):
+            cold = gorio.FastAPDGICP(0)
+            cold.set_params(max_correspondence_distance=2.0, maha_fp64=1, host_loop=1)
+            cold.set_input_target(tgt); cold.set_input_source(src)
+            cold.update_correspondences(T)
+            cc, sc = cold.get_correspondences()
+            assert np.array_equal(cg, cc) and np.array_equal(sg[cg >= 0], sc[cc >= 0])
+            assert rel(g.get_mahalanobis(), cold.get_mahalanobis()) == 0.0
+            cold.close()
+
+
 def test_cluster_label_weight(gorio, synth, c1):
     """cl_weight = 1/N when source.normal_x == target.normal_x (:271-273)"""
     src, tgt, _ = c1

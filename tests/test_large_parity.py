@@ -52,6 +52,16 @@ def test_large_cloud_matches_the_oracle_fixture(gorio, big):
     g.linearize(d["T_trial"])
     e2, H2, _ = g.linearize(T)
     assert abs(e2 - float(d["err"])) / e2 < 1e-10 and rel(H2, d["H"]) < 1e-10
+    # a chain of millimetre motions and back (matches kept by their stored bounds, corr.cu): the same correspondences,
+    # distances and sums as the first, cold pass
+    Tk = T.copy()
+    for k in range(4):
+        Tk[:3, 3] += np.array([0.002, -0.001, 0.0015])
+        g.linearize(Tk)
+    e3, H3, b3 = g.linearize(T)
+    c3, sq3 = g.get_correspondences()
+    assert e3 == e2 and np.array_equal(H3, H2)
+    assert np.array_equal(c3, c) and np.array_equal(sq3[c3 >= 0], sq[c >= 0])
     g.close()
 
 
