@@ -328,10 +328,9 @@ struct apd_handle {
     ShardTable t;
     t.nsub = kShardSub;
     t.chunk = shard_chunk(n);
-    for (int j = 0; j < kShardSub; j++) {
-      t.begin[j] = sub_begin(n, j);
-      t.count[j] = sub_count(n, j);
-    }
+    t.first = comm_rank * t.chunk;
+    t.step = comm_size * t.chunk;
+    t.n = n;
     t.plane = (int)local_n(n);
     return t;
   }

@@ -96,25 +96,27 @@ void launch_cov_import(const CloudDev& c, const double* d_in4x4, cudaStream_t s,
 // The cell-sorted source points are cut into nranks * kShardSubMax equal chunks of `chunk` points (a multiple of 256, so
 // every chunk starts on a tile and on a 16-byte boundary of every per-point array); rank r owns chunks r, r + nranks, ...
 // (interleaved: the cost of a query varies across a scene). A kernel gets the rank's chunks as a table and serves all of
-// them in ONE launch. Per-cloud arrays (spts, label, cov, geo) are indexed by the global sorted position begin[j] + o,
+// them in ONE launch. Per-cloud arrays (spts, label, cov, geo) are indexed by the global sorted position begin_of(j) + o,
 // per-linearisation arrays (corr, sqd, Mahalanobis) by the rank-local slot j * chunk + o. Unsharded: one chunk,
 // begin 0, count n, chunk n — both indices are the sorted position.
-constexpr int kShardSubMax = 4;
+constexpr int kShardSubMax = 16;  // chunks per rank: in cell order consecutive chunks are horizontal slabs of the scene whose
+                                  // queries differ in cost; 4 per rank left the ranks ~8 % apart at the reduction's exchange
 struct ShardTable {
   int nsub = 1;
   int chunk = 0;
-  int begin[kShardSubMax] = {0, 0, 0, 0};
-  int count[kShardSubMax] = {0, 0, 0, 0};
+  int first = 0;  // sorted position of the rank's first chunk (rank * chunk)
+  int step = 0;   // distance between the rank's consecutive chunks (nranks * chunk)
+  int n = 0;      // points of the cloud
   int plane = 0;  // local slots in all (= stride between the planes of the fp64 Mahalanobis storage)
   __host__ __device__ int slots() const { return nsub * chunk; }
-  // begin / count of chunk j by constant indices: a kernel parameter indexed with a run-time value is copied to local
-  // memory first (the linearize kernel lost 13 % to that)
-  __host__ __device__ __forceinline__ int begin_of(int j) const { return j == 0 ? begin[0] : (j == 1 ? begin[1] : (j == 2 ? begin[2] : begin[3])); }
-  __host__ __device__ __forceinline__ int count_of(int j) const { return j == 0 ? count[0] : (j == 1 ? count[1] : (j == 2 ? count[2] : count[3])); }
+  // begin / count of chunk j (arithmetic, not a table: a kernel parameter array indexed with a run-time value is copied
+  // to local memory first — the linearize kernel lost 13 % to that)
+  __host__ __device__ __forceinline__ int begin_of(int j) const { const int b = first + j * step; return b < n ? b : n; }
+  __host__ __device__ __forceinline__ int count_of(int j) const { const int r = n - begin_of(j); return r < chunk ? r : chunk; }
 };
 inline ShardTable whole_cloud(int n) {
   ShardTable t;
-  t.nsub = 1; t.chunk = n; t.count[0] = n; t.plane = n;
+  t.nsub = 1; t.chunk = n; t.n = n; t.plane = n;
   return t;
 }
 

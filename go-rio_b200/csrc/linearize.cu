@@ -106,7 +106,7 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
   auto tile_span = [&](int tile, size_t& gbase, size_t& lbase) -> int {
     if (!kSharded) {
       gbase = lbase = (size_t)tile * kTile;
-      return min(kTile, sh.count[0] - tile * kTile);
+      return min(kTile, sh.n - tile * kTile);
     }
     const int j = tile / tpc;
     const int o = (tile - j * tpc) * kTile;

@@ -331,7 +331,7 @@ APD_API int apd_align_batch(int device, const apd_params* p, const apd_pair* pai
  * equivalent) -------------------------------------------------------------- */
 /* One process and one handle per GPU; EVERY rank makes the same calls with the
  * same FULL source and target clouds. After apd_comm_init the handle splits the
- * work by interleaved chunks of the cell-sorted points (nranks x 4 equal chunks
+ * work by interleaved chunks of the cell-sorted points (nranks x 16 equal chunks
  * of a multiple of 256 points; rank r owns chunks r, r + nranks, ...): each rank
  * searches the full grids for its chunks of the covariances (then
  * ncclAllGather), and runs update_correspondences / linearize / compute_error
