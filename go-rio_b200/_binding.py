@@ -35,6 +35,9 @@ class ApdParams(C.Structure):
         ("maha_fp64", C.c_int32),
         ("host_loop", C.c_int32),
         ("variant", C.c_int32),
+        ("voxel_search", C.c_int32),
+        ("voxel_resolution", C.c_double),
+        ("voxel_mode", C.c_int32),
         ("reserved_", C.c_int32),
     ]
 
@@ -279,6 +282,28 @@ class Registration:
 
     def get_mahalanobis(self):
         return self._get_covs("get_mahalanobis", self.n_source)
+
+    # -- FastVGICP parity hooks -------------------------------------------
+    N_OFFSETS = {0: 27, 1: 7, 2: 1}  # APD_VOXEL_DIRECT27 / 7 / 1
+
+    def vgicp_voxels(self):
+        """the Gaussian voxel map of the target: (coords int32[n,3], counts int32[n], means f64[n,3], covs f64[n,3,3])"""
+        n = C.c_int32()
+        self._call("vgicp_get_voxels", C.byref(n), None, None, None, None, C.c_int32(0))
+        m = n.value
+        coords, counts = np.zeros((m, 3), np.int32), np.zeros(m, np.int32)
+        means, covs = np.zeros((m, 3), np.float64), np.zeros((m, 3, 3), np.float64)
+        self._call("vgicp_get_voxels", C.byref(n), coords.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
+                   means.ctypes.data_as(C.c_void_p), covs.ctypes.data_as(C.c_void_p), C.c_int32(m))
+        return coords, counts, means, covs
+
+    def vgicp_correspondences(self):
+        """(voxel int32[n_source, n_offsets] (-1: none), maha f64[n_source, n_offsets, 3, 3]) of the last linearize"""
+        no = self.N_OFFSETS[self.get_params().voxel_search]
+        vox = np.zeros((self.n_source, no), np.int32)
+        maha = np.zeros((self.n_source, no, 3, 3), np.float64)
+        self._call("vgicp_get_correspondences", vox.ctypes.data_as(C.c_void_p), maha.ctypes.data_as(C.c_void_p), C.c_int32(self.n_source), C.c_int32(no))
+        return vox, maha
 
     def fitness(self, T=None, max_range=np.finfo(np.float64).max, inlier_sq_thr=0.25):
         t = None if T is None else _colmajor(T, np.float32)

@@ -196,6 +196,12 @@ struct apd_handle {
   std::string error;
   Cloud src, tgt;
   // per-linearisation state (sorted order of the source)
+  // FastVGICP (variant = APD_VARIANT_VGICP, vgicp.cu): the target's Gaussian voxel map and the correspondence table
+  DevBuf vkey, vcnt, vmean, vcov, vcorr, vmaha;
+  bool vox_valid = false;     // voxelmap_ != nullptr
+  int n_vox = 0;
+  VoxelGridDesc vgd{};
+  int vcorr_n = 0, vcorr_noff = 0;  // shape of the table the last update_correspondences wrote
   DevBuf corr, sqd, second, mahaA, mahaB;
   bool second_valid = false;  // `second` holds the bounds of the pass the warm start refers to (single-lane search)
   int corr_n = -1;          // number of source points the buffers describe (-1: none yet)
@@ -840,8 +846,12 @@ CorrOut corr_view(apd_handle* h) {
   return c;
 }
 
+int vgicp_update_correspondences(apd_handle* h, const hm::Pose& T);
+int vgicp_reduce(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, double* b6, double* err);
+
 // FastAPDGICP::update_correspondences (:160-220)
 int do_update_correspondences(apd_handle* h, const hm::Pose& T) {
+  if (h->params.variant == APD_VARIANT_VGICP) return vgicp_update_correspondences(h, T);
   int rc0 = ensure_corr_buffers(h);
   if (rc0 != APD_OK) return rc0;
   const NoiseParams np = noise_params(h->params);
@@ -864,6 +874,7 @@ int do_update_correspondences(apd_handle* h, const hm::Pose& T) {
 // Launches K4/K5, all-reduces across shards if a communicator is set, and
 // brings the 28 doubles back. out: H (row-major 36, optional), b (6, optional), err.
 int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, double* b6, double* err) {
+  if (h->params.variant == APD_VARIANT_VGICP) return vgicp_reduce(h, T, want_hb, H36, b6, err);
   int rc = ensure_small(h);
   if (rc != APD_OK) return rc;
   double* d_out = h->small.as<double>();
@@ -901,6 +912,138 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
   // (ranks of one process: nobody goes on — possibly to a call that synchronises the device — while a peer's kernel may
   // still be waiting inside the exchange for a rank whose launch has not gone through yet; see group_allgather_chunks)
   if (h->group && !h->group->host_barrier()) return fail(h, APD_ERR_COMM, "a rank of the group did not finish the reduction");
+  if (want_hb) {
+    if (H36) hm::unpack_upper(hs, H36);
+    if (b6) std::memcpy(b6, hs + 21, 6 * sizeof(double));
+  }
+  *err = hs[27];
+  return APD_OK;
+}
+
+// ---- FastVGICP (vgicp.cu) ----------------------------------------------------------------------------------------
+int vgicp_offsets(const apd_params& p) { return p.voxel_search == APD_VOXEL_DIRECT1 ? 1 : (p.voxel_search == APD_VOXEL_DIRECT7 ? 7 : 27); }
+
+VoxelMapDev voxel_view(const apd_handle* h) {
+  VoxelMapDev v;
+  v.n = h->n_vox;
+  v.g = h->vgd;
+  v.key = h->vkey.as<uint32_t>();
+  v.cnt = h->vcnt.as<int32_t>();
+  v.mean = h->vmean.as<double>();
+  v.cov = h->vcov.as<double>();
+  return v;
+}
+
+// GaussianVoxelMap::create_voxelmap (fast_vgicp_voxel.hpp:131-158) over the target and its covariances
+int vgicp_build_voxelmap(apd_handle* h) {
+  Cloud& t = h->tgt;
+  if (!t.present || t.n <= 0) return fail(h, APD_ERR_INVALID, "target cloud not set");
+  const int n = t.n;
+  int rc = ensure_small(h);
+  if (rc != APD_OK) return rc;
+  const CloudDev tv = t.view();
+  // the box of occupied voxel coordinates, from the box of the finite points (voxel_coord is monotone in x)
+  unsigned int* d_state = reinterpret_cast<unsigned int*>(h->small.as<double>() + 60);
+  const unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+  APD_CUDA(h, cudaMemcpyAsync(d_state, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  launch_voxel_bounds(tv.pts, n, d_state, h->stream, &h->launches);
+  unsigned int enc[6];
+  APD_CUDA(h, cudaMemcpyAsync(enc, d_state, sizeof(enc), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
+  if (enc[0] == 0xffffffffu) return fail(h, APD_ERR_INVALID, "the target holds no finite point");
+  const double res = h->params.voxel_resolution;
+  VoxelGridDesc vg;
+  vg.res = res;
+  long long cells = 1;
+  for (int a = 0; a < 3; a++) {
+    float lo, hi;
+    unsigned int u = enc[a];
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    std::memcpy(&lo, &u, 4);
+    u = enc[3 + a];
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    std::memcpy(&hi, &u, 4);
+    const double clo = std::floor((double)lo / res - 0.5), chi = std::floor((double)hi / res - 0.5);
+    if (!(std::fabs(clo) < 1e9) || !(std::fabs(chi) < 1e9)) return fail(h, APD_ERR_UNSUPPORTED, "voxel coordinates out of range");
+    vg.mn[a] = (int)clo;
+    vg.dim[a] = (int)(chi - clo) + 1;
+    cells *= vg.dim[a];
+    if (cells >= 0xffffffffll) return fail(h, APD_ERR_UNSUPPORTED, "voxel_resolution too small for the extent of the target (more than 2^32 voxel slots)");
+  }
+  int bits = 1;
+  while (bits < 32 && (1ll << bits) < cells) bits++;
+  bits = std::min(32, (bits + 7) / 8 * 8);
+  const int sblocks = (n + kSortTile - 1) / kSortTile;
+  const size_t hist_elems = (size_t)256 * sblocks;
+  const size_t scan_elems = std::max(scan_tmp_elems_for((size_t)n + 1), scan_tmp_elems_for(hist_elems));
+  const size_t kv = align_up((size_t)n * sizeof(uint32_t), 256);
+  APD_CUDA(h, h->work.ensure(5 * kv + 256 + align_up(hist_elems * 4, 256) + align_up(scan_elems * 4, 256)));
+  char* p = h->work.as<char>();
+  uint32_t* keys[2] = {(uint32_t*)p, (uint32_t*)(p + kv)};
+  uint32_t* vals[2] = {(uint32_t*)(p + 2 * kv), (uint32_t*)(p + 3 * kv)};
+  uint32_t* heads = (uint32_t*)(p + 4 * kv);
+  uint32_t* hist = (uint32_t*)(p + 5 * kv + 256);
+  uint32_t* scan_tmp = (uint32_t*)(p + 5 * kv + 256 + align_up(hist_elems * 4, 256));
+  launch_vgicp_keys(tv.pts, n, vg, keys[0], vals[0], h->stream, &h->launches);
+  const int cur = launch_sort_pairs_u32(keys, vals, n, 32, hist, scan_tmp, h->stream, &h->launches);
+  (void)bits;
+  launch_voxel_heads(keys[cur], n, heads, h->stream, &h->launches);
+  launch_exclusive_scan_u32(heads, (size_t)n + 1, scan_tmp, h->stream, &h->launches);
+  uint32_t nv = 0;
+  APD_CUDA(h, cudaMemcpyAsync(&nv, heads + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
+  APD_CUDA(h, h->vkey.ensure(std::max<size_t>(1, nv) * sizeof(uint32_t)));
+  APD_CUDA(h, h->vcnt.ensure(std::max<size_t>(1, nv) * sizeof(int32_t)));
+  APD_CUDA(h, h->vmean.ensure(std::max<size_t>(1, nv) * 3 * sizeof(double)));
+  APD_CUDA(h, h->vcov.ensure(std::max<size_t>(1, nv) * 6 * sizeof(double)));
+  launch_vgicp_voxels(tv, keys[cur], vals[cur], heads, h->params.voxel_mode == APD_VOXEL_MULTIPLICATIVE ? 1 : 0, h->vkey.as<uint32_t>(),
+                      h->vcnt.as<int32_t>(), h->vmean.as<double>(), h->vcov.as<double>(), h->stream, &h->launches);
+  APD_CUDA(h, cudaGetLastError());
+  h->n_vox = (int)nv;
+  h->vgd = vg;
+  h->vox_valid = true;
+  return APD_OK;
+}
+
+// FastVGICP::update_correspondences (fast_vgicp_impl.hpp:74-118); builds the voxel map first if there is none (:126-129)
+int vgicp_update_correspondences(apd_handle* h, const hm::Pose& T) {
+  if (h->sharded()) return fail(h, APD_ERR_UNSUPPORTED, "FastVGICP is not sharded");
+  if (!h->vox_valid) {
+    ProfScope ps(h, APD_K_GRID);
+    const int rc = vgicp_build_voxelmap(h);
+    if (rc != APD_OK) return rc;
+  }
+  const int no = vgicp_offsets(h->params);
+  const size_t slots = (size_t)std::max(1, h->src.n) * no;
+  APD_CUDA(h, h->vcorr.ensure(slots * sizeof(int32_t)));
+  APD_CUDA(h, h->vmaha.ensure(slots * 6 * sizeof(double)));
+  {
+    ProfScope ps(h, APD_K_CORR);
+    launch_vgicp_correspondences(h->src.view(), voxel_view(h), h->params.voxel_search, no, to_pose_d(T), h->vcorr.as<int32_t>(), h->vmaha.as<double>(),
+                                 h->stream, &h->launches);
+  }
+  APD_CUDA(h, cudaGetLastError());
+  h->vcorr_n = h->src.n;
+  h->vcorr_noff = no;
+  return APD_OK;
+}
+
+// the sums of FastVGICP::linearize (:141-181) / compute_error (:186-205) over the stored correspondence table
+int vgicp_reduce(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, double* b6, double* err) {
+  if (h->vcorr_n != h->src.n || h->vcorr_noff != vgicp_offsets(h->params) || !h->vox_valid)
+    return fail(h, APD_ERR_INVALID, "compute_error before linearize (no voxel correspondences)");
+  int rc = ensure_small(h);
+  if (rc != APD_OK) return rc;
+  double* d_out = h->small.as<double>();
+  {
+    ProfScope ps(h, want_hb ? APD_K_LINEARIZE : APD_K_ERROR);
+    launch_vgicp_reduce(h->src.view(), voxel_view(h), h->vcorr.as<int32_t>(), h->vmaha.as<double>(), h->vcorr_noff, to_pose_d(T), want_hb,
+                        h->partials.as<double>(), h->max_reduce_blocks, d_out, reinterpret_cast<unsigned int*>(d_out + 40), h->stream, &h->launches);
+  }
+  APD_CUDA(h, cudaGetLastError());
+  double* hs = reinterpret_cast<double*>(h->h_small.p);
+  APD_CUDA(h, cudaMemcpyAsync(hs, d_out, kReduceVals * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
   if (want_hb) {
     if (H36) hm::unpack_upper(hs, H36);
     if (b6) std::memcpy(b6, hs + 21, 6 * sizeof(double));
@@ -1237,6 +1380,10 @@ void default_params(apd_params* p) {
   p->lm_init_lambda_factor = 1e-9;
   p->maha_fp64 = 0;
   p->host_loop = 0;
+  p->variant = APD_VARIANT_APDGICP;
+  p->voxel_search = APD_VOXEL_DIRECT1;  // fast_vgicp_impl.hpp:22-24
+  p->voxel_resolution = 1.0;
+  p->voxel_mode = APD_VOXEL_ADDITIVE;
 }
 
 NoiseParams noise_params(const apd_params& p) {
@@ -1280,7 +1427,7 @@ LmConfig lm_config(const apd_params& p) {
 }
 
 bool use_device_loop(const apd_handle* h) {
-  return !h->params.host_loop && !h->sharded() && !h->params.lm_debug_print && h->src.n <= kLmMaxSource;
+  return h->params.variant != APD_VARIANT_VGICP && !h->params.host_loop && !h->sharded() && !h->params.lm_debug_print && h->src.n <= kLmMaxSource;
 }
 
 LmJob lm_job(apd_handle* h, const hm::Pose& x0, int prep_bits = 0) {
@@ -1473,6 +1620,10 @@ int do_align(apd_handle* h, const float* guess) {
     }
     return rc;
   }
+  if (h->params.variant == APD_VARIANT_VGICP) {
+    if (h->sharded()) return fail(h, APD_ERR_UNSUPPORTED, "FastVGICP is not sharded");
+    h->vox_valid = false;  // FastVGICP::computeTransformation (fast_vgicp_impl.hpp:66-71)
+  }
   int rc = ensure_covariances(h);  // FastAPDGICP::computeTransformation (:148-157)
   if (rc != APD_OK) return rc;
   h->fit_valid = false;
@@ -1642,6 +1793,7 @@ int apd_destroy(apd_handle* h) {
   if (h->done_ev) cudaEventDestroy(h->done_ev);
   h->src.release(); h->tgt.release();
   h->corr.release(); h->sqd.release(); h->second.release(); h->mahaA.release(); h->mahaB.release();
+  h->vkey.release(); h->vcnt.release(); h->vmean.release(); h->vcov.release(); h->vcorr.release(); h->vmaha.release();
   h->work.release(); h->scratch.release(); h->partials.release(); h->small.release();
   h->h_small.release();
   h->h_query.release();
@@ -1659,8 +1811,15 @@ int apd_set_params(apd_handle* h, const apd_params* p) {
   if (!h || !p) return APD_ERR_INVALID;
   const bool cov_dep = p->k_correspondences != h->params.k_correspondences || p->regularization != h->params.regularization;
   if (p->regularization < APD_REG_NONE || p->regularization > APD_REG_FROBENIUS) return fail(h, APD_ERR_INVALID, "bad regularization");
-  if (p->variant != APD_VARIANT_APDGICP && p->variant != APD_VARIANT_GICP) return fail(h, APD_ERR_INVALID, "bad variant");
+  if (p->variant != APD_VARIANT_APDGICP && p->variant != APD_VARIANT_GICP && p->variant != APD_VARIANT_VGICP) return fail(h, APD_ERR_INVALID, "bad variant");
+  if (p->variant == APD_VARIANT_VGICP) {
+    if (!(p->voxel_resolution > 0.0) || !std::isfinite(p->voxel_resolution)) return fail(h, APD_ERR_INVALID, "bad voxel_resolution");
+    if (p->voxel_search < APD_VOXEL_DIRECT27 || p->voxel_search > APD_VOXEL_DIRECT1) return fail(h, APD_ERR_INVALID, "bad voxel_search (DIRECT_RADIUS exists on the reference's VGICP_CUDA only)");
+    if (p->voxel_mode < APD_VOXEL_ADDITIVE || p->voxel_mode > APD_VOXEL_MULTIPLICATIVE) return fail(h, APD_ERR_INVALID, "bad voxel_mode");
+  }
   if (p->variant != h->params.variant) h->corr_warm = false;  // (the stored Mahalanobis matrices are the other variant's)
+  if (p->variant != h->params.variant || p->voxel_resolution != h->params.voxel_resolution || p->voxel_mode != h->params.voxel_mode) h->vox_valid = false;
+  if (p->variant != h->params.variant || p->voxel_search != h->params.voxel_search) h->vcorr_n = 0;
   h->params = *p;
   (void)cov_dep;  // reference: changing k / regularisation does NOT drop cached covariances either
   return APD_OK;
@@ -1677,6 +1836,7 @@ int apd_set_source(apd_handle* h, const void* pts, int32_t n, int32_t stride, in
 }
 int apd_set_target(apd_handle* h, const void* pts, int32_t n, int32_t stride, int32_t xyz_off, int32_t label_off, uint64_t key) {
   if (!h) return APD_ERR_INVALID;
+  h->vox_valid = false;  // FastVGICP::setInputTarget (fast_vgicp_impl.hpp:57-64)
   return set_cloud(h, h->tgt, pts, n, stride, xyz_off, label_off, key);
 }
 int apd_set_source_device(apd_handle* h, const void* d, int32_t n) {
@@ -1685,6 +1845,7 @@ int apd_set_source_device(apd_handle* h, const void* d, int32_t n) {
 }
 int apd_set_target_device(apd_handle* h, const void* d, int32_t n) {
   if (!h) return APD_ERR_INVALID;
+  h->vox_valid = false;
   return set_cloud_device(h, h->tgt, d, n);
 }
 
@@ -1696,6 +1857,8 @@ int apd_swap_source_and_target(apd_handle* h) {  // :89-98
     const int rc = (h->src.bbox_launched || h->tgt.bbox_launched) ? finish_bboxes(h) : APD_OK;
     if (rc != APD_OK) return rc;
   }
+  h->vox_valid = false;  // FastVGICP::swapSourceAndTarget (fast_vgicp_impl.hpp:46-54)
+  h->vcorr_n = 0;
   std::swap(h->src, h->tgt);
   if (h->src.grid_valid && !h->src.grid_ordered) h->src.drop_derived();  // (sums over source points follow the source's layout: rebuild it in order)
   h->corr_n = -1;  // correspondences_.clear()
@@ -1712,13 +1875,18 @@ int apd_clear_source(apd_handle* h) {  // :101-105
 int apd_clear_target(apd_handle* h) {  // :108-112
   if (!h) return APD_ERR_INVALID;
   h->corr_warm = false;
+  h->vox_valid = false;
   h->tgt.present = false; h->tgt.n = 0; h->tgt.key = 0; h->tgt.ext_pts = nullptr;
   h->tgt.drop_derived();
   return APD_OK;
 }
 
 int apd_set_source_covariances(apd_handle* h, const double* covs, int32_t n) { return h ? set_covs(h, h->src, covs, n) : APD_ERR_INVALID; }
-int apd_set_target_covariances(apd_handle* h, const double* covs, int32_t n) { return h ? set_covs(h, h->tgt, covs, n) : APD_ERR_INVALID; }
+int apd_set_target_covariances(apd_handle* h, const double* covs, int32_t n) {
+  if (!h) return APD_ERR_INVALID;
+  h->vox_valid = false;  // (the voxels average the target covariances)
+  return set_covs(h, h->tgt, covs, n);
+}
 int apd_get_source_covariances(apd_handle* h, double* covs, int32_t n) { return h ? get_covs(h, h->src, covs, n) : APD_ERR_INVALID; }
 int apd_get_target_covariances(apd_handle* h, double* covs, int32_t n) { return h ? get_covs(h, h->tgt, covs, n) : APD_ERR_INVALID; }
 
@@ -1784,7 +1952,8 @@ int apd_linearize(apd_handle* h, const double* T, double* H, double* b, double* 
 
 int apd_compute_error(apd_handle* h, const double* T, double* err) {
   if (!h || !T || !err) return APD_ERR_INVALID;
-  if (h->corr_n != h->src.n || !h->src.present) return fail(h, APD_ERR_INVALID, "compute_error needs a prior linearize on the same clouds");
+  if (h->params.variant != APD_VARIANT_VGICP && (h->corr_n != h->src.n || !h->src.present))
+    return fail(h, APD_ERR_INVALID, "compute_error needs a prior linearize on the same clouds");
   DeviceGuard dg(h->device);
   int rc = reduce_pass(h, hm::from_colmajor_f64(T), false, nullptr, nullptr, err);
   flush_prof(h);
@@ -1831,6 +2000,43 @@ int apd_get_mahalanobis(apd_handle* h, double* maha, int32_t n) {
   launch_corr_export(h->src.view(), h->tgt.view(), h->shard_table(h->src.n), corr_view(h), nullptr, nullptr, h->scratch.as<double>(), h->stream,
                      &h->launches);
   APD_CUDA(h, cudaMemcpyAsync(maha, h->scratch.p, (size_t)n * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
+  return APD_OK;
+}
+
+int apd_vgicp_get_voxels(apd_handle* h, int32_t* n_voxels, int32_t* coords, int32_t* counts, double* means, double* covs, int32_t capacity) {
+  if (!h) return APD_ERR_INVALID;
+  const int nv = h->vox_valid ? h->n_vox : 0;
+  if (n_voxels) *n_voxels = nv;
+  const int m = std::min(nv, std::max(capacity, 0));
+  if (m <= 0 || (!coords && !counts && !means && !covs)) return APD_OK;
+  DeviceGuard dg(h->device);
+  APD_CUDA(h, h->scratch.ensure((size_t)nv * (9 * sizeof(double) + 3 * sizeof(int32_t)) + 256));
+  double* d_covs = h->scratch.as<double>();
+  int32_t* d_coords = reinterpret_cast<int32_t*>(d_covs + (size_t)nv * 9);
+  launch_vgicp_export_voxels(voxel_view(h), coords ? d_coords : nullptr, covs ? d_covs : nullptr, h->stream, &h->launches);
+  APD_CUDA(h, cudaGetLastError());
+  if (coords) APD_CUDA(h, cudaMemcpyAsync(coords, d_coords, (size_t)m * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (covs) APD_CUDA(h, cudaMemcpyAsync(covs, d_covs, (size_t)m * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (counts) APD_CUDA(h, cudaMemcpyAsync(counts, h->vcnt.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (means) APD_CUDA(h, cudaMemcpyAsync(means, h->vmean.p, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
+  return APD_OK;
+}
+
+int apd_vgicp_get_correspondences(apd_handle* h, int32_t* voxel, double* maha3x3, int32_t n_source, int32_t n_offsets) {
+  if (!h) return APD_ERR_INVALID;
+  if (h->vcorr_n != n_source || n_source != h->src.n || h->vcorr_noff != n_offsets || n_source <= 0)
+    return fail(h, APD_ERR_INVALID, "no voxel correspondences of this shape");
+  DeviceGuard dg(h->device);
+  const size_t slots = (size_t)n_source * n_offsets;
+  if (voxel) APD_CUDA(h, cudaMemcpyAsync(voxel, h->vcorr.p, slots * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (maha3x3) {
+    APD_CUDA(h, h->scratch.ensure(slots * 9 * sizeof(double)));
+    launch_vgicp_export_maha(h->vcorr.as<int32_t>(), h->vmaha.as<double>(), (long long)slots, h->scratch.as<double>(), h->stream, &h->launches);
+    APD_CUDA(h, cudaGetLastError());
+    APD_CUDA(h, cudaMemcpyAsync(maha3x3, h->scratch.p, slots * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
   APD_CUDA(h, wait_stream(h));
   return APD_OK;
 }
@@ -2899,7 +3105,7 @@ int apd_group_create(apd_handle* const* handles, int32_t n, apd_group** out) {
   for (int r = 0; r < n; r++) {  // no kernel may be loaded lazily once ranks of this process wait for each other inside kernels
     DeviceGuard dg(handles[r]->device);
     preload_grid_kernels(); preload_knn_kernels(); preload_corr_kernels(); preload_linearize_kernels(); preload_lm_kernels();
-    preload_prep_kernels();
+    preload_prep_kernels(); preload_vgicp_kernels();
   }
   for (int r = 0; r < n; r++) {
     apd_handle* h = handles[r];

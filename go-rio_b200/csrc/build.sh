@@ -12,7 +12,7 @@ if [[ -n "${APD_EXTRA_FLAGS:-}" ]]; then FLAGS+=(${APD_EXTRA_FLAGS}); fi
 OUT="${APD_OUT:-${OUT}}"
 mkdir -p "${HERE}/_obj"
 pids=()
-for f in grid knn_cov corr linearize lm prep_ops apdgicp; do
+for f in grid knn_cov corr linearize lm prep_ops vgicp apdgicp; do
   "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${HERE}/_obj/${f}.o" &
   pids+=($!)
 done

@@ -203,6 +203,32 @@ void preload_corr_kernels();
 void preload_linearize_kernels();
 void preload_lm_kernels();
 void preload_prep_kernels();
+void preload_vgicp_kernels();
+
+// ---- vgicp.cu: FastVGICP (reference impl/fast_vgicp_impl.hpp, fast_vgicp_voxel.hpp) ---------------------------
+constexpr int kVoxelDirect27 = 0, kVoxelDirect7 = 1, kVoxelDirect1 = 2;  // = APD_VOXEL_* of include/apdgicp.h
+struct VoxelGridDesc {
+  double res;  // voxel_resolution_
+  int mn[3];   // smallest occupied voxel coordinate per axis
+  int dim[3];  // extent of the occupied box in voxels (key = x + y * dim0 + z * dim0 * dim1 < 2^32 - 1)
+};
+struct VoxelMapDev {
+  int n = 0;  // voxels
+  VoxelGridDesc g{};
+  const uint32_t* key = nullptr;  // ascending
+  const int32_t* cnt = nullptr;   // num_points
+  const double* mean = nullptr;   // 3 per voxel
+  const double* cov = nullptr;    // 6 per voxel (xx, xy, xz, yy, yz, zz)
+};
+void launch_vgicp_keys(const float4* pts, int n, const VoxelGridDesc& vg, uint32_t* keys, uint32_t* vals, cudaStream_t s, int64_t* launches);
+void launch_vgicp_voxels(const CloudDev& tgt, const uint32_t* keys, const uint32_t* vals, const uint32_t* voxel_of, int multiplicative,
+                         uint32_t* vkey, int32_t* vcnt, double* vmean, double* vcov, cudaStream_t s, int64_t* launches);
+void launch_vgicp_correspondences(const CloudDev& src, const VoxelMapDev& vm, int method, int n_off, const PoseD& T, int32_t* vcorr, double* vmaha,
+                                  cudaStream_t s, int64_t* launches);
+void launch_vgicp_reduce(const CloudDev& src, const VoxelMapDev& vm, const int32_t* vcorr, const double* vmaha, int n_off, const PoseD& T, bool want_hb,
+                         double* partials, int max_blocks, double* d_out28, unsigned int* ticket, cudaStream_t s, int64_t* launches);
+void launch_vgicp_export_voxels(const VoxelMapDev& vm, int32_t* d_coords, double* d_covs, cudaStream_t s, int64_t* launches);
+void launch_vgicp_export_maha(const int32_t* vcorr, const double* vmaha, long long slots, double* d_out, cudaStream_t s, int64_t* launches);
 
 // an empty kernel (launch-rate diagnostic)
 void launch_noop(cudaStream_t s, int64_t* launches);

@@ -250,6 +250,9 @@ private:
     p.lm_init_lambda_factor = lm_init_lambda_factor_;
     p.maha_fp64 = maha_fp64_ ? 1 : 0;
     p.variant = variant_;
+    p.voxel_resolution = voxel_resolution_;
+    p.voxel_search = voxel_search_;
+    p.voxel_mode = voxel_mode_;
     apd_set_params(handle_, &p);
   }
 
@@ -262,7 +265,10 @@ protected:
   double distance_variance_ = 0.86;
   mutable CovarianceVector source_covs_, target_covs_;
   mutable bool source_covs_valid_ = false, target_covs_valid_ = false;
-  int variant_ = APD_VARIANT_APDGICP;  // fast_gicp.hpp's FastGICP sets APD_VARIANT_GICP
+  int variant_ = APD_VARIANT_APDGICP;  // fast_gicp.hpp's FastGICP sets APD_VARIANT_GICP, fast_vgicp.hpp's FastVGICP APD_VARIANT_VGICP
+  double voxel_resolution_ = 1.0;      // FastVGICP only (fast_vgicp_impl.hpp:22-24)
+  int voxel_search_ = APD_VOXEL_DIRECT1;
+  int voxel_mode_ = APD_VOXEL_ADDITIVE;
 
 private:
   // ApdSearchOwner: what the installed search method asks of this object

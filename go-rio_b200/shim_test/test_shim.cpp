@@ -12,6 +12,7 @@
 
 #include <fast_gicp/gicp/fast_apdgicp.hpp>
 #include <fast_gicp/gicp/fast_gicp.hpp>
+#include <fast_gicp/gicp/fast_vgicp.hpp>
 
 using PointT = pcl::PointXYZINormal;
 
@@ -30,7 +31,18 @@ static pcl::PointCloud<PointT>::Ptr load(const char* path, int n) {
 }
 
 // the reference factory, registrations.cpp:38-51, with the deployed rosparam values (launch/ntu_loop2.launch:88-99)
-static pcl::Registration<PointT, PointT>::Ptr select_registration_method(bool fast_gicp_branch) {
+static pcl::Registration<PointT, PointT>::Ptr select_registration_method(const char* method) {
+  const bool fast_gicp_branch = std::strcmp(method, "gicp") == 0;
+  if (std::strcmp(method, "vgicp") == 0) {  // registrations.cpp:64-72 ("FAST_VGICP"; reg_resolution from the test)
+    fast_gicp::FastVGICP<PointT, PointT>::Ptr vgicp(new fast_gicp::FastVGICP<PointT, PointT>());
+    vgicp->setNumThreads(0);
+    vgicp->setResolution(2.0);
+    vgicp->setNeighborSearchMethod(fast_gicp::NeighborSearchMethod::DIRECT7);
+    vgicp->setTransformationEpsilon(0.1);
+    vgicp->setMaximumIterations(64);
+    vgicp->setCorrespondenceRandomness(20);
+    return vgicp;
+  }
   if (fast_gicp_branch) {  // registrations.cpp:28-37
     fast_gicp::FastGICP<PointT, PointT>::Ptr gicp(new fast_gicp::FastGICP<PointT, PointT>());
     gicp->setNumThreads(0);
@@ -63,7 +75,7 @@ int main(int argc, char** argv) {
   if (argc < 5) return 2;
   auto source = load(argv[1], std::atoi(argv[2]));
   auto target = load(argv[3], std::atoi(argv[4]));
-  pcl::Registration<PointT, PointT>::Ptr registration = select_registration_method(argc > 5 && std::strcmp(argv[5], "gicp") == 0);
+  pcl::Registration<PointT, PointT>::Ptr registration = select_registration_method(argc > 5 ? argv[5] : "apdgicp");
   auto* apd = dynamic_cast<fast_gicp::FastAPDGICP<PointT, PointT>*>(registration.get());
   const long long knn0 = knn_launches(apd->handle());
   registration->setInputTarget(target);
@@ -123,7 +135,7 @@ int main(int argc, char** argv) {
   const long long knn_promoted = knn_launches(apd->handle()) - knn1;
   const Eigen::Matrix4f Tp = registration->getFinalTransformation();
   // the same pair on a fresh object (nothing to adopt): must give the same pose
-  pcl::Registration<PointT, PointT>::Ptr fresh = select_registration_method(argc > 5 && std::strcmp(argv[5], "gicp") == 0);
+  pcl::Registration<PointT, PointT>::Ptr fresh = select_registration_method(argc > 5 ? argv[5] : "apdgicp");
   pcl::PointCloud<PointT>::Ptr source_copy(new pcl::PointCloud<PointT>(*source));
   fresh->setInputTarget(source_copy);
   fresh->setInputSource(scan2);

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define APD_ABI_VERSION 2
+#define APD_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define APD_API __attribute__((visibility("default")))
@@ -66,7 +66,10 @@ enum {
  * covariance, :194-215; per-point weight 1 + geometric + label weight, :266-276). GICP: the reference's FastGICP
  * (fast_gicp_impl.hpp:124-258, selected by registrations.cpp:28-37): the same covariances, correspondences and
  * optimizer, RCR = C_B + T C_A T^T (:157) and unit weights (:205) — dist/azimuth/elevation_var are not read. */
-enum { APD_VARIANT_APDGICP = 0, APD_VARIANT_GICP = 1 };
+enum { APD_VARIANT_APDGICP = 0, APD_VARIANT_GICP = 1, APD_VARIANT_VGICP = 2 };
+/* fast_gicp::NeighborSearchMethod / VoxelAccumulationMode (reference gicp_settings.hpp:10-12), FastVGICP only */
+enum { APD_VOXEL_DIRECT27 = 0, APD_VOXEL_DIRECT7 = 1, APD_VOXEL_DIRECT1 = 2 };
+enum { APD_VOXEL_ADDITIVE = 0, APD_VOXEL_ADDITIVE_WEIGHTED = 1, APD_VOXEL_MULTIPLICATIVE = 2 };
 
 /* reference lsq_registration.hpp:13 — same order */
 enum { APD_OPT_GAUSS_NEWTON = 0, APD_OPT_LEVENBERG_MARQUARDT = 1 };
@@ -100,7 +103,14 @@ typedef struct apd_params {
                                           not sharded; 1: always drive it from the
                                           host, one launch per stage (what large
                                           or sharded clouds use anyway).         */
-  int32_t variant;                     /* APD_VARIANT_APDGICP (default) / _GICP  */
+  int32_t variant;                     /* APD_VARIANT_APDGICP (default) / _GICP /
+                                          _VGICP (fast_gicp::FastVGICP, reference
+                                          impl/fast_vgicp_impl.hpp)              */
+  int32_t voxel_search;                /* FastVGICP setNeighborSearchMethod,
+                                          APD_VOXEL_DIRECT1 (fast_vgicp_impl.hpp:23) */
+  double voxel_resolution;             /* FastVGICP setResolution, 1.0 (:22)     */
+  int32_t voxel_mode;                  /* FastVGICP setVoxelAccumulationMode,
+                                          APD_VOXEL_ADDITIVE (:24)               */
   int32_t reserved_;                   /* 0                                      */
 } apd_params;
 
@@ -189,6 +199,22 @@ APD_API int apd_update_correspondences(apd_handle* h, const double* T);
 APD_API int apd_get_correspondences(apd_handle* h, int32_t* idx, float* sq_dist, int32_t n);
 /* parity hook: mahalanobis_ as n column-major 4x4 doubles */
 APD_API int apd_get_mahalanobis(apd_handle* h, double* maha4x4, int32_t n);
+
+/* ---- FastVGICP parity hooks (variant = APD_VARIANT_VGICP) -------------------
+ * The Gaussian voxel map of the target (reference fast_vgicp_voxel.hpp:127-185,
+ * built by the first linearize of an alignment, fast_vgicp_impl.hpp:126-129):
+ * voxels in ascending (z, y, x) order of their integer coordinates
+ * floor(p / resolution - 0.5). coords: int32[3 * n], counts: int32[n], means:
+ * double[3 * n], covs: double[9 * n] row-major 3x3; any may be NULL.
+ * *n_voxels receives the number of voxels; at most `capacity` are written. */
+APD_API int apd_vgicp_get_voxels(apd_handle* h, int32_t* n_voxels, int32_t* coords, int32_t* counts, double* means, double* covs,
+                                 int32_t capacity);
+/* voxel_correspondences_ / voxel_mahalanobis_ of the LAST linearize
+ * (fast_vgicp_impl.hpp:74-118), per source point (original order) and
+ * neighbour offset (the order of neighbor_offsets(), fast_vgicp_voxel.hpp:10-44):
+ * voxel[i * n_offsets + o] = index into the list of apd_vgicp_get_voxels or -1;
+ * maha: 9 doubles (row-major 3x3) per slot, zeros where there is no voxel. */
+APD_API int apd_vgicp_get_correspondences(apd_handle* h, int32_t* voxel, double* maha3x3, int32_t n_source, int32_t n_offsets);
 
 /* pcl::Registration::getFitnessScore(max_range) [PCL 1.10 registration.hpp]
  * over final_transformation_ (or T if not NULL, float[16]); also returns the

@@ -88,6 +88,9 @@ FastAPDGICP::FastAPDGICP() {
   params.maha_fp64 = 1;
   params.host_loop = 0;
   params.variant = APD_VARIANT_APDGICP;
+  params.voxel_search = APD_VOXEL_DIRECT1;   // fast_vgicp_impl.hpp:22-24
+  params.voxel_resolution = 1.0;
+  params.voxel_mode = APD_VOXEL_ADDITIVE;
   params.reserved_ = 0;
   final_pose_f64 = M4::identity();
   for (int i = 0; i < 16; i++) final_transformation[i] = (i % 5 == 0) ? 1.f : 0.f;
@@ -113,6 +116,7 @@ void FastAPDGICP::setInputTarget(const std::vector<PointXYZL>& cloud, uint64_t k
   target_search = make_search(target, search_kind);
   target_covs.clear();
   target_neighbors.clear();
+  voxelmap_valid = false;  // FastVGICP::setInputTarget (fast_vgicp_impl.hpp:57-64)
 }
 // fast_apdgicp_impl.hpp:89-98
 void FastAPDGICP::swapSourceAndTarget() {
@@ -126,6 +130,9 @@ void FastAPDGICP::swapSourceAndTarget() {
   source_neighbors.swap(target_neighbors);
   correspondences.clear();
   sq_distances.clear();
+  voxelmap_valid = false;  // FastVGICP::swapSourceAndTarget (fast_vgicp_impl.hpp:46-54)
+  voxel_correspondences.clear();
+  voxel_mahalanobis.clear();
 }
 // fast_apdgicp_impl.hpp:101-112
 void FastAPDGICP::clearSource() {
@@ -137,6 +144,7 @@ void FastAPDGICP::clearSource() {
   source_neighbors.clear();
 }
 void FastAPDGICP::clearTarget() {
+  voxelmap_valid = false;
   target.clear();
   has_target = false;
   target_key = 0;
@@ -393,6 +401,12 @@ inline bool point_terms(const FastAPDGICP& g, const M4& trans, int i, bool want_
 
 // fast_apdgicp_impl.hpp:224-307
 double FastAPDGICP::linearize(const M4& trans, double* H36, double* b6) {
+  if (params.variant == APD_VARIANT_VGICP) {  // FastVGICP::linearize (fast_vgicp_impl.hpp:121-181)
+    if (!voxelmap_valid) create_voxelmap();   // :126-129
+    vgicp_update_correspondences(trans);      // :131
+    n_linearize++;
+    return vgicp_sums(trans, H36, b6);
+  }
   update_correspondences(trans);  // :226
   n_linearize++;
   const int n = (int)source.size();
@@ -428,6 +442,10 @@ double FastAPDGICP::linearize(const M4& trans, double* H36, double* b6) {
 
 // fast_apdgicp_impl.hpp:310-346 — stale correspondences_ / mahalanobis_, trial transform in e only
 double FastAPDGICP::compute_error(const M4& trans) {
+  if (params.variant == APD_VARIANT_VGICP) {  // FastVGICP::compute_error (fast_vgicp_impl.hpp:184-205)
+    n_compute_error++;
+    return vgicp_sums(trans, nullptr, nullptr);
+  }
   n_compute_error++;
   const int n = (int)source.size();
   double sum_errors = 0.0;
@@ -533,6 +551,7 @@ bool FastAPDGICP::step_lm(M4& x0, M4& delta) {
 // (fast_apdgicp_impl.hpp:148-157) -> LsqRegistration::computeTransformation
 // (lsq_registration_impl.hpp:55-80)
 bool FastAPDGICP::align(const float* guess_colmajor) {
+  voxelmap_valid = false;  // FastVGICP::computeTransformation (fast_vgicp_impl.hpp:66-71)
   if (!ensure_covariances()) return false;
   M4 x0 = M4::identity();  // :56 Isometry3d(guess.cast<double>())
   if (guess_colmajor) {

@@ -261,6 +261,24 @@ class FastAPDGICP {
   std::vector<int> correspondences;
   std::vector<float> sq_distances;
 
+  // ---- FastVGICP (params.variant == APD_VARIANT_VGICP; oracle/apd_vgicp_oracle.cpp) ----
+  // GaussianVoxel (fast_vgicp_voxel.hpp:57-77) of the voxel map, kept in ascending (z, y, x) order of the coordinates
+  struct Voxel {
+    int coord[3];
+    int num_points;
+    double mean[3];
+    M3 cov;
+  };
+  std::vector<Voxel> voxels;
+  bool voxelmap_valid = false;                 // voxelmap_ != nullptr
+  std::vector<int> voxel_correspondences;      // [n_source * n_offsets] index into `voxels` or -1 (the reference keeps a list of pairs)
+  std::vector<M3> voxel_mahalanobis;           // same slots
+  int n_offsets() const;
+  void create_voxelmap();
+  int lookup_voxel(int cx, int cy, int cz) const;
+  void vgicp_update_correspondences(const M4& trans);
+  double vgicp_sums(const M4& trans, double* H36, double* b6);
+
   M4 final_pose_f64;           // x0 before the float cast
   float final_transformation[16];  // column-major, = float(x0) (lsq_registration_impl.hpp:78)
   double final_hessian[36];

@@ -189,13 +189,22 @@ int apdo_linearize(void* h, const double* T, double* Hm, double* b, double* err)
 }
 int apdo_compute_error(void* h, const double* T, double* err) {
   FastAPDGICP& g = H(h)->g;
-  if (g.correspondences.size() != g.source.size()) return APD_ERR_INVALID;
+  if (g.params.variant == APD_VARIANT_VGICP) {
+    if (g.voxel_correspondences.size() != g.source.size() * (size_t)g.n_offsets()) return APD_ERR_INVALID;
+  } else if (g.correspondences.size() != g.source.size()) {
+    return APD_ERR_INVALID;
+  }
   *err = g.compute_error(m4_from_colmajor(T));
   return APD_OK;
 }
 int apdo_update_correspondences(void* h, const double* T) {
   FastAPDGICP& g = H(h)->g;
   if (!g.ensure_covariances()) return g.error.find("fewer") != std::string::npos ? APD_ERR_TOO_FEW : APD_ERR_INVALID;
+  if (g.params.variant == APD_VARIANT_VGICP) {
+    if (!g.voxelmap_valid) g.create_voxelmap();
+    g.vgicp_update_correspondences(m4_from_colmajor(T));
+    return APD_OK;
+  }
   g.update_correspondences(m4_from_colmajor(T));
   return APD_OK;
 }
@@ -215,6 +224,29 @@ int apdo_get_mahalanobis(void* h, double* maha, int32_t n) {
     } else {
       cov_to_4x4(g.mahalanobis[i], maha + (size_t)i * 16);
     }
+  }
+  return APD_OK;
+}
+int apdo_vgicp_get_voxels(void* h, int32_t* n_voxels, int32_t* coords, int32_t* counts, double* means, double* covs, int32_t capacity) {
+  FastAPDGICP& g = H(h)->g;
+  const int n = g.voxelmap_valid ? (int)g.voxels.size() : 0;
+  if (n_voxels) *n_voxels = n;
+  for (int i = 0; i < n && i < capacity; i++) {
+    const FastAPDGICP::Voxel& v = g.voxels[i];
+    if (coords) for (int a = 0; a < 3; a++) coords[3 * i + a] = v.coord[a];
+    if (counts) counts[i] = v.num_points;
+    if (means) for (int a = 0; a < 3; a++) means[3 * i + a] = v.mean[a];
+    if (covs) for (int e = 0; e < 9; e++) covs[9 * (size_t)i + e] = v.cov.m[e];
+  }
+  return APD_OK;
+}
+int apdo_vgicp_get_correspondences(void* h, int32_t* voxel, double* maha, int32_t n_source, int32_t n_offsets) {
+  FastAPDGICP& g = H(h)->g;
+  const size_t n = (size_t)n_source * n_offsets;
+  if (n != g.voxel_correspondences.size() || n_offsets != g.n_offsets()) return APD_ERR_INVALID;
+  for (size_t i = 0; i < n; i++) {
+    if (voxel) voxel[i] = g.voxel_correspondences[i];
+    if (maha) for (int e = 0; e < 9; e++) maha[9 * i + e] = g.voxel_correspondences[i] >= 0 ? g.voxel_mahalanobis[i].m[e] : 0.0;
   }
   return APD_OK;
 }

@@ -114,3 +114,74 @@ def so3_exp(w):
         [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
         [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)],
     ])
+
+
+# ---- FastVGICP (fast_vgicp_impl.hpp, fast_vgicp_voxel.hpp), written from the reference source with a Python dict as
+# the voxel map and np.linalg.inv on the 4x4 matrices the reference inverts ----
+def vgicp_offsets(method):
+    if method == "DIRECT1":
+        return [(0, 0, 0)]
+    if method == "DIRECT7":
+        return [(0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+    return [(i - 1, j - 1, k - 1) for i in range(3) for j in range(3) for k in range(3)]
+
+
+def vgicp_voxelmap(tgt, cov_tgt, resolution, multiplicative=False):
+    """create_voxelmap (fast_vgicp_voxel.hpp:131-158): {coord: [n, mean4, cov4x4]}"""
+    vox = {}
+    P = np.concatenate([tgt[:, :3].astype(np.float64), np.ones((tgt.shape[0], 1))], axis=1)
+    coords = np.floor(P[:, :3] / resolution - 0.5).astype(np.int64)
+    for i in range(tgt.shape[0]):
+        C4 = np.zeros((4, 4)); C4[:3, :3] = cov_tgt[i]
+        v = vox.setdefault(tuple(coords[i]), [0, np.zeros(4), np.zeros((4, 4))])
+        v[0] += 1
+        if multiplicative:
+            Ci = C4.copy(); Ci[3, 3] = 1.0
+            Ci = np.linalg.inv(Ci)
+            v[2] += Ci
+            v[1] += Ci @ P[i]
+        else:
+            v[1] += P[i]
+            v[2] += C4
+    for v in vox.values():
+        if multiplicative:
+            v[2][3, 3] = 1.0
+            v[1][3] = 1.0
+            v[2] = np.linalg.inv(v[2])
+            v[1] = v[2] @ v[1]
+        else:
+            v[1] = v[1] / v[0]
+            v[2] = v[2] / v[0]
+    return vox
+
+
+def vgicp_linearize(T, src, cov_src, vox, resolution, method="DIRECT1", T_corr=None):
+    """update_correspondences at T_corr (default T) + the sums at T (fast_vgicp_impl.hpp:74-181).
+    Returns err, H, b, and the correspondence list [(i, coord)]."""
+    Tc = T if T_corr is None else T_corr
+    A = np.concatenate([src[:, :3].astype(np.float64), np.ones((src.shape[0], 1))], axis=1)
+    tc = A @ Tc.T
+    base = np.floor(tc[:, :3] / resolution - 0.5).astype(np.int64)
+    err, H, b, corr = 0.0, np.zeros((6, 6)), np.zeros(6), []
+    for i in range(src.shape[0]):
+        for off in vgicp_offsets(method):
+            c = tuple(base[i] + np.array(off))
+            if c not in vox:
+                continue
+            n, mean, cov = vox[c]
+            CA = np.zeros((4, 4)); CA[:3, :3] = cov_src[i]
+            RCR = cov + Tc @ CA @ Tc.T
+            RCR[3, 3] = 1.0
+            M = np.linalg.inv(RCR)
+            M[3, 3] = 0.0
+            tA = T @ A[i]
+            e = mean - tA
+            w = np.sqrt(n)
+            err += w * e @ M @ e
+            J = np.zeros((4, 6))
+            J[:3, :3] = np.array([[0, -tA[2], tA[1]], [tA[2], 0, -tA[0]], [-tA[1], tA[0], 0]])
+            J[:3, 3:] = -np.eye(3)
+            H += w * J.T @ M @ J
+            b += w * J.T @ M @ e
+            corr.append((i, c))
+    return err, H, b, corr

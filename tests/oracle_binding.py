@@ -15,7 +15,7 @@ _libs = {}
 
 
 def build_oracle():
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("apd_oracle.cpp", "apd_oracle_capi.cpp", "apd_prep_oracle.cpp", "apd_oracle.hpp", "apd_math.hpp")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("apd_oracle.cpp", "apd_oracle_capi.cpp", "apd_prep_oracle.cpp", "apd_vgicp_oracle.cpp", "apd_oracle.hpp", "apd_math.hpp")]
     stale = (not os.path.exists(ORACLE_SO)) or any(os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in srcs)
     if stale:
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"], env={**os.environ, "MAKEFLAGS": ""})

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(gorio):
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
     lib.apd_abi_version.restype = ctypes.c_int
-    assert lib.apd_abi_version() == 2  # 2: apd_params.variant (FastGICP behind the same kernels)
+    assert lib.apd_abi_version() == 3  # 2: apd_params.variant (FastGICP behind the same kernels); 3: FastVGICP (voxel_* fields, hooks)
 
 
 def test_default_params_match_reference_constructors(gorio):
@@ -48,7 +48,8 @@ def test_default_params_match_reference_constructors(gorio):
     assert p.max_iterations == 64 and p.optimizer == gorio.OPT_LM
     assert (p.rotation_epsilon, p.transformation_epsilon) == (2e-3, 5e-4)
     assert p.lm_max_iterations == 10 and p.lm_init_lambda_factor == 1e-9
-    assert p.variant == 0 and ctypes.sizeof(p) == 96  # APD_VARIANT_APDGICP; the struct the header declares
+    assert p.variant == 0 and ctypes.sizeof(p) == 112  # APD_VARIANT_APDGICP; the struct the header declares
+    assert p.voxel_search == 2 and p.voxel_resolution == 1.0 and p.voxel_mode == 0  # DIRECT1, 1.0, ADDITIVE (fast_vgicp_impl.hpp:22-24)
 
 
 def test_no_cpu_fallback_without_gpu(gorio):

@@ -414,6 +414,74 @@ def test_gicp_variant_in_a_pool(gorio, synth, monkeypatch):
         assert r["status"] == 0 and np.array_equal(r["T"], g.align()["T"])
 
 
+# ------------------------------------------------- FastVGICP (vgicp.cu) ----
+VOXEL_SEARCH = {"DIRECT27": 0, "DIRECT7": 1, "DIRECT1": 2}
+
+
+@pytest.mark.parametrize("method,mode,res", [("DIRECT1", 0, 1.0), ("DIRECT7", 0, 1.5), ("DIRECT27", 1, 2.0), ("DIRECT7", 2, 1.5)])
+def test_vgicp_voxelmap_correspondences_and_sums(gorio, synth, c1, c2_small, method, mode, res):
+    """fast_gicp::FastVGICP (reference impl/fast_vgicp_impl.hpp, fast_vgicp_voxel.hpp) against the oracle: the voxel map
+    (coordinates and counts exact), the voxel correspondence table (exact), Mahalanobis / H / b / err / stale compute_error"""
+    kw = dict(variant=2, voxel_resolution=res, voxel_search=VOXEL_SEARCH[method], voxel_mode=mode)
+    for src, tgt, Tgt in (c1, c2_small):
+        g, o = make(gorio, src, tgt, **kw)
+        T = Tgt @ synth.make_pose([0.05, -0.03, 0.01], [0.0, 0.002, 0.01])
+        eg, Hg, bg = g.linearize(T)
+        eo, Ho, bo = o.linearize(T)
+        cg, ng, mg, Cg = g.vgicp_voxels()
+        co, no, mo, Co = o.vgicp_voxels()
+        assert np.array_equal(cg, co) and np.array_equal(ng, no) and ng.sum() == tgt.shape[0]
+        assert rel(mg, mo) < (1e-9 if mode == 2 else 1e-13) and rel(Cg, Co) < (1e-8 if mode == 2 else 1e-12)
+        vg, Mg = g.vgicp_correspondences()
+        vo, Mo = o.vgicp_correspondences()
+        assert np.array_equal(vg, vo) and (vg >= 0).sum() > 50
+        assert rel(Mg, Mo) < 1e-9
+        assert abs(eg - eo) / eo < 1e-10 and rel(Hg, Ho) < 1e-10 and rel(bg, bo) < 1e-9
+        T2 = T @ synth.make_pose([0.02, 0.01, -0.01], [0.001, 0.0, -0.004])
+        assert abs(g.compute_error(T2) - o.compute_error(T2)) / eo < 1e-10
+        # a second pass at another pose: the table is rewritten, the voxel map is kept
+        e2g, e2o = g.linearize(T2, want_hb=False), o.linearize(T2, want_hb=False)
+        assert abs(e2g - e2o) / e2o < 1e-10 and np.array_equal(g.vgicp_correspondences()[0], o.vgicp_correspondences()[0])
+        g.close()
+
+
+@pytest.mark.parametrize("optimizer", [1, 0])
+def test_vgicp_align_parity(gorio, synth, c1, c2_small, optimizer):
+    """the whole FastVGICP registration (voxel map rebuilt per align, LM or GN on the host): same pose, converged flag,
+    iteration count and LM trace as the oracle"""
+    for (src, tgt, _), kw in ((c1, dict(voxel_resolution=2.0, voxel_search=0)), (c2_small, dict(voxel_resolution=1.0, voxel_search=1))):
+        g, o = make(gorio, src, tgt, variant=2, optimizer=optimizer, transformation_epsilon=0.01, **kw)
+        rg, ro = _check_align(g, o)
+        assert np.array_equal(g.vgicp_correspondences()[0], o.vgicp_correspondences()[0])
+        tg, to = g.lm_trace(), o.lm_trace()
+        assert tg.shape == to.shape and np.array_equal(tg[:, [0, 1, 7]], to[:, [0, 1, 7]])
+        # swapping rebuilds the voxel map over the new target (fast_vgicp_impl.hpp:46-54)
+        g.swap_source_and_target(); o.swap_source_and_target()
+        _check_align(g, o)
+        assert np.array_equal(g.vgicp_voxels()[0], o.vgicp_voxels()[0])
+        g.close()
+
+
+def test_vgicp_parameters_and_switching(gorio, synth, c1):
+    src, tgt, Tgt = c1
+    g, o = make(gorio, src, tgt, variant=2, voxel_resolution=1.5, voxel_search=1)
+    e0 = g.linearize(Tgt, want_hb=False)
+    for r in (g, o):
+        r.set_params(voxel_resolution=3.0)  # a new resolution rebuilds the map
+    e1 = g.linearize(Tgt, want_hb=False)
+    # (the oracle keeps its map until the target changes, as the reference does; a fresh oracle gives the comparison)
+    o2 = make(gorio, src, tgt, variant=2, voxel_resolution=3.0, voxel_search=1)[1]
+    assert e1 != e0 and abs(e1 - o2.linearize(Tgt, want_hb=False)) / e1 < 1e-10
+    for bad in (dict(voxel_resolution=0.0), dict(voxel_search=3), dict(voxel_mode=5)):
+        with pytest.raises(gorio.ApdError):
+            g.set_params(**bad)
+    # back to APDGICP on the live handle
+    g.set_params(variant=0, voxel_resolution=1.0, voxel_search=2, voxel_mode=0)
+    oa = make(gorio, src, tgt)[1]
+    assert abs(g.linearize(Tgt, want_hb=False) - oa.linearize(Tgt, want_hb=False)) < 1e-6 * abs(e0)  # (fp32 Mahalanobis storage)
+    g.close()
+
+
 def _handle(gorio, monkeypatch, lazy, src, tgt, **kw):
     monkeypatch.setenv("APD_LAZY_TARGET_COV", lazy)
     g = gorio.FastAPDGICP(0)

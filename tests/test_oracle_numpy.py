@@ -126,3 +126,61 @@ def test_lm_step_matches_numpy(pair):
         X = np.eye(4); X[:3, :3] = nr.so3_exp(d[:3]); X[:3, 3] = d[3:]
         assert np.abs(X - r["T64"]).max() < 1e-9
         assert np.abs(X.astype(np.float32) - r["T"]).max() == 0 or np.abs(X - r["T"]).max() < 1e-6
+
+
+# ---- FastVGICP ----
+VGICP = dict(variant=2)
+
+
+@pytest.mark.parametrize("method,mode", [("DIRECT1", 0), ("DIRECT7", 0), ("DIRECT27", 1), ("DIRECT7", 2)])
+def test_vgicp_voxelmap_correspondences_and_sums(pair, method, mode):
+    """the oracle's FastVGICP (voxel map, voxel correspondences, H / b / err, stale compute_error) against the NumPy
+    restatement with a dict as the voxel map"""
+    src, tgt, Tgt = pair
+    search = {"DIRECT27": 0, "DIRECT7": 1, "DIRECT1": 2}[method]
+    res = 1.5
+    o = Oracle(search=1)
+    o.set_params(**VGICP, voxel_resolution=res, voxel_search=search, voxel_mode=mode)
+    o.set_input_source(src); o.set_input_target(tgt)
+    cs, ct = o.get_source_covariances()[:, :3, :3], o.get_target_covariances()[:, :3, :3]
+    T = Tgt @ nr_pose(0.05, 0.01)
+    err, H, b = o.linearize(T)
+    vox = nr.vgicp_voxelmap(tgt, ct, res, multiplicative=(mode == 2))
+    coords, counts, means, covs = o.vgicp_voxels()
+    assert len(vox) == coords.shape[0] and counts.sum() == tgt.shape[0]
+    for c, n, m, C in zip(coords, counts, means, covs):
+        v = vox[tuple(int(x) for x in c)]
+        assert v[0] == n and _rel(m, v[1][:3]) < (1e-9 if mode == 2 else 1e-12) and _rel(C, v[2][:3, :3]) < 1e-9  # (multiplicative: sums of inverses of 1e-3-conditioned matrices)
+    # ascending (z, y, x)
+    key = (coords[:, 2].astype(np.int64) * 4096 + coords[:, 1]) * 4096 + coords[:, 0]
+    assert (np.diff(key) > 0).all()
+    e_n, H_n, b_n, corr_n = nr.vgicp_linearize(T, src, cs, vox, res, method)
+    vc, maha = o.vgicp_correspondences()
+    got = [(i, tuple(int(x) for x in coords[v])) for i in range(vc.shape[0]) for v in vc[i] if v >= 0]
+    assert got == corr_n and len(got) > 50
+    assert abs(err - e_n) / e_n < 1e-10 and _rel(H, H_n) < 1e-10 and _rel(b, b_n) < 1e-9
+    # compute_error at a trial pose: stale correspondences and Mahalanobis matrices
+    T2 = T @ nr_pose(0.02, 0.004)
+    e2 = o.compute_error(T2)
+    e2_n = nr.vgicp_linearize(T2, src, cs, vox, res, method, T_corr=T)[0]
+    assert abs(e2 - e2_n) / e2_n < 1e-10
+
+
+def nr_pose(t, r):
+    T = np.eye(4)
+    T[:3, :3] = nr.so3_exp(np.array([r, -0.5 * r, 2 * r]))
+    T[:3, 3] = [t, -t, 0.3 * t]
+    return T
+
+
+def test_vgicp_align_recovers_the_motion(pair):
+    """the whole FastVGICP registration in the oracle (2 m voxels, DIRECT27): converges, and lands within the noise of the
+    600-point scans of the true motion"""
+    src, tgt, Tgt = pair
+    o = Oracle(search=1)
+    o.set_params(variant=2, voxel_resolution=2.0, voxel_search=0)
+    o.set_input_source(src); o.set_input_target(tgt)
+    r = o.align()
+    assert r["converged"] and 1 < r["iterations"] < 40
+    d = np.linalg.inv(Tgt) @ r["T64"]
+    assert np.abs(d[:3, 3]).max() < 0.25 and np.abs(d[:3, :3] - np.eye(3)).max() < 0.02

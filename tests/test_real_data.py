@@ -112,3 +112,32 @@ def test_reference_alignment_bar_on_real_clouds(gorio, real):
     dt, dr = pose_err(fwd["T64"] @ bwd["T64"], np.eye(4))
     assert dt < t_tol and dr < r_tol
     g.close()
+
+
+@pytest.mark.gpu
+def test_vgicp_alignment_bar_on_real_clouds(gorio, real):
+    """gicp_test.cpp:141-166 runs the same forward / backward bar on FastVGICP: on the reference tree's real lidar pair the
+    voxelised registration lands within 5 cm / 1 degree of the pose FastAPDGICP's CPU restatement found, in both
+    directions, and the two directions are inverse to one another within the same bar"""
+    d, src, tgt = real
+    g = gorio.FastAPDGICP(0)
+    o = Oracle(search=1, threads=0)
+    for r in (g, o):
+        r.set_params(variant=2, voxel_resolution=1.0, voxel_search=2)  # the reference's defaults: 1 m voxels, DIRECT1
+        r.set_input_target(tgt); r.set_input_source(src)
+    fwd, fwd_o = g.align(), o.align()
+    coords, counts, _, _ = g.vgicp_voxels()
+    assert counts.sum() == tgt.shape[0] and coords.shape[0] > 1000
+    assert np.array_equal(coords, o.vgicp_voxels()[0]) and np.array_equal(counts, o.vgicp_voxels()[1])
+    assert np.array_equal(g.vgicp_correspondences()[0], o.vgicp_correspondences()[0])
+    dt, dr = pose_err(fwd["T64"], fwd_o["T64"])
+    assert dt < 1e-6 and dr < 1e-6 and fwd["iterations"] == fwd_o["iterations"]
+    g.swap_source_and_target()
+    bwd = g.align()
+    t_tol, r_tol = 0.05, np.pi / 180.0
+    for got, want in ((fwd, d["T64_deployed"]), (bwd, d["T64_deployed_backward"])):
+        dt, dr = pose_err(got["T64"], want)
+        assert got["converged"] and dt < t_tol and dr < r_tol, (dt, dr)
+    dt, dr = pose_err(fwd["T64"] @ bwd["T64"], np.eye(4))
+    assert dt < t_tol and dr < r_tol
+    g.close()

@@ -34,7 +34,7 @@ def test_shim_keeps_the_reference_surface():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["apdgicp", "gicp"])
+@pytest.mark.parametrize("variant", ["apdgicp", "gicp", "vgicp"])
 def test_shim_matches_the_c_abi(gorio, synth, tmp_path, variant):
     exe = os.path.join(SHIM_DIR, "test_shim")
     if not os.path.exists(exe):
@@ -45,7 +45,10 @@ def test_shim_matches_the_c_abi(gorio, synth, tmp_path, variant):
     out = subprocess.run([exe, fs, str(src.shape[0]), ft, str(tgt.shape[0]), variant], capture_output=True, text=True, check=True)
     r = json.loads(out.stdout.strip().splitlines()[-1])
     g = gorio.FastAPDGICP(0)
-    g.set_params(max_correspondence_distance=2.0, transformation_epsilon=0.1, variant=1 if variant == "gicp" else 0)
+    if variant == "vgicp":  # fast_gicp::FastVGICP as the shim test's factory sets it up (registrations.cpp:64-72)
+        g.set_params(transformation_epsilon=0.1, variant=2, voxel_resolution=2.0, voxel_search=1)
+    else:
+        g.set_params(max_correspondence_distance=2.0, transformation_epsilon=0.1, variant=1 if variant == "gicp" else 0)
     g.set_input_target(synth.to_pcl_xyzinormal(tgt)); g.set_input_source(synth.to_pcl_xyzinormal(src))
     ra = g.align(want_aligned=True)
     assert bool(r["converged"]) == ra["converged"]
@@ -67,4 +70,7 @@ def test_shim_matches_the_c_abi(gorio, synth, tmp_path, variant):
     assert r["knn_equal"] == 1  # an arbitrary query, k = 5: same indices and distances as brute force
     # --- keyframe promotion keeps grid + covariances on the device: only the new scan's covariances are computed — and with
     # every target covariance valid the loop kernel computes them itself (fused prologue): no kNN launch at all
+    if variant == "vgicp":  # (host-driven loop: covariances of both clouds up front; the promoted keyframe still brings its own along)
+        assert r["promoted_same_pose"] == 1 and r["knn_launches_promoted"] < r["knn_launches_first"]
+        return
     assert r["knn_launches_first"] == 4 and r["knn_launches_promoted"] == 0 and r["promoted_same_pose"] == 1
