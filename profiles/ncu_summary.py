@@ -8,7 +8,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
-        "l1tex__t_bytes.sum", "lts__t_bytes.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
+        "l1tex__t_bytes.sum", "lts__t_bytes.sum", "lts__t_sectors.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
 STALL = "smsp__average_warps_issue_stalled_"
 
 def main():

@@ -482,6 +482,22 @@ def test_vgicp_parameters_and_switching(gorio, synth, c1):
     g.close()
 
 
+def test_vgicp_in_a_pool(gorio, synth):
+    """a pool whose handles run FastVGICP (host-driven loop inside the workers) gives what lone handles give"""
+    pairs = [synth.submap_pair(3200 + i, n_source=600, n_frames=4, n_per_frame=1000)[:2] + (None,) for i in range(5)]
+    kw = dict(variant=2, voxel_resolution=1.5, voxel_search=1, transformation_epsilon=0.01)
+    b = gorio.Batch(0, n_workers=3, **kw)
+    res = b.align(b.prepare(pairs))
+    b.close()
+    for (s, t, _), r in zip(pairs, res):
+        g = gorio.FastAPDGICP(0)
+        g.set_params(**kw)
+        g.set_input_target(t); g.set_input_source(s)
+        ra = g.align()
+        assert r["status"] == 0 and np.array_equal(r["T"], ra["T"]) and r["iterations"] == ra["iterations"]
+        g.close()
+
+
 def _handle(gorio, monkeypatch, lazy, src, tgt, **kw):
     monkeypatch.setenv("APD_LAZY_TARGET_COV", lazy)
     g = gorio.FastAPDGICP(0)
