@@ -39,36 +39,73 @@ __global__ void __launch_bounds__(kThreads) corr_search_kernel(const float4* __r
                                                                int second_valid) {
   // kThreads and the warp size are multiples of G, so a group never straddles a warp; the lanes of a group share the
   // slot, so a padding slot retires its whole group (every shuffle below is masked to the group's own lanes)
-  const int l = (int)(((size_t)blockIdx.x * kThreads + threadIdx.x) / G);
+  int l = (int)(((size_t)blockIdx.x * kThreads + threadIdx.x) / G);
   int j, o;
-  if (!slot_of(sh, l, j, o)) return;
+  int seed = -1;
+  if (G == 1 && warm && second_valid) {
+    // ---- a pass that follows a single-lane pass over the same clouds: most points need no search ----
+    // The previous pass left, next to each match, a lower bound of the squared distance of every OTHER target point
+    // (second[l], nn_search_lane_t). The point has moved by delta since: every other target point is still at least
+    // sqrt(second) - delta away. If the old match, at its new exact distance, is closer than that (with margins far
+    // above the fp32 rounding of the distances), it is still THE nearest neighbour by (d2, index): no search. An
+    // unmatched point whose stored bound still clears the correspondence distance needs none either (warm_start).
+    // The points that do are then packed into the block's first warps (a warp with 11 searching lanes costs what one
+    // with 32 does: after a 5 mm move ~1/3 of the points search, and the search is bound by instruction issue).
+    bool need = false;
+    if (slot_of(sh, l, j, o)) {
+      const float4 a = s_spts[sh.begin_of(j) + o];
+      float px, py, pz;
+      transform_rn(Tf, a.x, a.y, a.z, px, py, pz);
+      const int pc = corr[l];
+      if (pc >= 0) {
+        const float4 p = t_spts[pc & kCorrIndexMask];
+        const float d1 = sqdist_rn(px, py, pz, p.x, p.y, p.z);
+        float ox, oy, oz;
+        transform_rn(Tpf, a.x, a.y, a.z, ox, oy, oz);
+        const float delta = sqrtf(sqdist_rn(px, py, pz, ox, oy, oz)) * 1.0001f;
+        const float lb = sqrtf(second[l]) * 0.9999f - delta;
+        if (lb > 0.f && d1 * 1.001f < lb * lb && (double)d1 < thr_sq) {
+          sqd[l] = d1;          // :180, the distance the search would have found
+          second[l] = lb * lb;  // the bound, carried to the new position; corr[l] (match + label bit) stays
+        } else {
+          need = true;
+        }
+      } else {
+        float kept;
+        int unused;
+        if (warm_start(Tpf, a, px, py, pz, pc, sqd[l], thr_sq, unused, kept)) need = true;
+        else sqd[l] = kept;  // provably still unmatched; corr[l] stays -1
+      }
+    }
+    __shared__ int warp_cnt[kThreads / 32];
+    __shared__ int list[kThreads];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) {
+      base += w < warp ? warp_cnt[w] : 0;
+      total += warp_cnt[w];
+    }
+    if (need) list[base + __popc(m & ((1u << lane) - 1u))] = l;
+    __syncthreads();
+    if ((int)threadIdx.x >= total) return;
+    l = list[threadIdx.x];
+    (void)slot_of(sh, l, j, o);
+    const int pc = corr[l];
+    seed = pc >= 0 ? (pc & kCorrIndexMask) : -1;
+    warm = 0;  // (decided above)
+  } else if (!slot_of(sh, l, j, o)) {
+    return;
+  }
   const int i = sh.begin_of(j) + o;
   const float4 a = s_spts[i];
   float px, py, pz;
   transform_rn(Tf, a.x, a.y, a.z, px, py, pz);  // :176
 
   // warm: corr / sqd still hold the previous pass over the same clouds (pose T_prev) — see warm_start
-  int seed = -1;
-  if (G == 1 && warm && second_valid) {
-    // The previous pass left, next to each match, a lower bound of the squared distance of every OTHER target point
-    // (second[l], nn_search_lane_t). The point has moved by delta since: every other target point is still at least
-    // sqrt(second) - delta away. If the old match, at its new exact distance, is closer than that (with margins far
-    // above the fp32 rounding of the distances), it is still THE nearest neighbour by (d2, index): no search.
-    const int pc = corr[l];
-    if (pc >= 0) {
-      const float4 p = t_spts[pc & kCorrIndexMask];
-      const float d1 = sqdist_rn(px, py, pz, p.x, p.y, p.z);
-      float ox, oy, oz;
-      transform_rn(Tpf, a.x, a.y, a.z, ox, oy, oz);
-      const float delta = sqrtf(sqdist_rn(px, py, pz, ox, oy, oz)) * 1.0001f;
-      const float lb = sqrtf(second[l]) * 0.9999f - delta;
-      if (lb > 0.f && d1 * 1.001f < lb * lb && (double)d1 < thr_sq) {
-        sqd[l] = d1;            // :180, the distance the search would have found
-        second[l] = lb * lb;    // the bound, carried to the new position
-        return;                 // corr[l] (match + label bit) stays
-      }
-    }
-  }
   if (warm) {
     float kept;
     if (!warm_start(Tpf, a, px, py, pz, corr[l], sqd[l], thr_sq, seed, kept)) {  // (uniform over the G lanes of a query)
