@@ -529,7 +529,9 @@ def main():
             return float(ms.item()), launches, gorio_mod._results(last), cpu_ms_per_pair, stable
 
         with ClockSampler(local_rank) as clocks:
+            batch.load_stats(reset=True)
             ms_dev, launches, results, cpu_dev, st0 = timed(batch, prep_dev, args.steps, args.warmup)
+            load = batch.load_stats(reset=True)  # the loop kernels' own %globaltimer stamps (warm-up + timed passes)
             ms_pcl, _, results_pcl, cpu_pcl, st1 = timed(batch, prep_pcl, args.steps, args.warmup)
             ms_packed, _, results_packed, cpu_packed, st2 = timed(batch, prep_packed, args.steps, args.warmup)
         value = args.pairs * args.steps / (ms_dev / 1e3)
@@ -618,11 +620,14 @@ def main():
         # live figure is how full it keeps the GPU; the ncu figures of the same kernel are in profiles/
         lm_ms = kms.get("lm", [0.0, 0])[0]
         ctas = 2 if "APD_LM_CLUSTER" not in os.environ else int(os.environ["APD_LM_CLUSTER"])  # (a pool's default cluster size)
+        under_load_ms = load["lm_kernel_ms"] / max(1.0, load["registrations"])  # mean duration of a loop kernel while the pool is full
         line["loop_kernel"] = {"kernel": "lm_kernel<fp32 maha, 2 CTAs/SM>", "share_of_step_kernel_time": round(lm_ms / tot, 4),
-                               "ms_per_registration": lm_ms / max(1, n_mine), "ctas_per_registration": ctas,
-                               "cta_slot_occupancy": round(lm_ms * ctas / (296.0 * (ms_dev / args.steps)), 4),
-                               "note": "CTA-slot occupancy = sum of loop-kernel time x CTAs / (148 SMs x 2 slots x step time), profiled pass over timed pass; "
-                                       "issue-slot %, L2 GB/s: profiles/r02_ncu_lm_kernel.txt"}
+                               "ms_per_registration_under_load": under_load_ms, "ms_per_registration_profiled_pass": lm_ms / max(1, n_mine),
+                               "ctas_per_registration": ctas,
+                               "cta_slot_occupancy": round(under_load_ms * ctas * n_mine / (296.0 * (ms_dev / args.steps)), 4),
+                               "note": "CTA-slot occupancy = mean loop-kernel duration under load (the kernels' own time stamps during the timed passes) x CTAs "
+                                       "x registrations per step / (148 SMs x 2 slots x step time); the profiled pass runs with timing events and less "
+                                       "concurrency; issue-slot %, L2 hit rate, stalls: profiles/r02_ncu_lm_kernel.txt"}
         del dev_all, flush
         torch.cuda.empty_cache()
 
