@@ -603,7 +603,11 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_pcl, "d2h_bytes_per_step": d2h,
                     "layout": "pageable 48-byte pcl::PointXYZINormal AoS (staged to pinned float4 by the pool, then copied)",
                     "same_result_as_device_resident": bool(same), "all_pairs_ok": bool(n_ok == n_all), "pairs_converged": n_conv, "pairs_run": n_all,
-                    "api": "apd_batch_align (host AoS clouds in, poses out)"},
+                    "api": "apd_batch_align (host AoS clouds in, poses out)",
+                    "host_cpu_ms_per_pair": round(cpu_pcl, 4), "host_cores": host_cores(),
+                    "host_staging_ceiling": round(host_cores() / max(cpu_pcl, 1e-6) * 1e3, 0),
+                    "host_note": "reading 2.9 MB of pageable 48-byte records per pair is host-core work (go-rio_b200/csrc/host_stage.hpp): the node's "
+                                 "cores stage host_staging_ceiling pairs/s whatever the number of GPUs; e2e_packed is the same run from packed pinned clouds"},
             "e2e_packed": {"value": packed_value, "unit": UNIT, "h2d_bytes_per_step": h2d_packed, "d2h_bytes_per_step": d2h,
                            "layout": "packed float4 {x,y,z,label} in page-locked memory (no staging pass)"},
             "eager": eager,

@@ -154,16 +154,37 @@ __device__ __forceinline__ void grids_phase(cg::cluster_group& cluster, PrepShar
     for (int j = gt; j < ncs; j += GT) __stcg(&job[c].cell_start[j], 0u);
   }
   cluster.sync();
+  // (kU points per thread and turn: the loads, then the atomics, then the stores — each step of a point waits a memory
+  // round trip for the one before, and under a pool's load a round trip is ~1 us; four in flight per thread instead of one)
+  constexpr int kU = 4;
   for (int c = first; c < last; c++) {
     const GridDesc g = ps.grid[c];
-    for (int i = gt; i < job[c].n; i += GT) {
-      const float4 p = job[c].pts[i];
-      const int cx = cell_coord(p.x, g.ox, g.inv_cell, g.nx);
-      const int cy = cell_coord(p.y, g.oy, g.inv_cell, g.ny);
-      const int cz = cell_coord(p.z, g.oz, g.inv_cell, g.nz);
-      const uint32_t key = (uint32_t)((cz * g.ny + cy) * g.nx + cx);
-      job[c].keys[i] = key;  // (read back by the same thread only)
-      job[c].rank[i] = atomicAdd(&job[c].cell_start[key], 1u);
+    const int n = job[c].n;
+    for (int i0 = gt; i0 < n; i0 += kU * GT) {
+      float4 p[kU];
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int i = i0 + u * GT;
+        p[u] = job[c].pts[i < n ? i : i0];
+      }
+      uint32_t key[kU], rk[kU];
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int cx = cell_coord(p[u].x, g.ox, g.inv_cell, g.nx);
+        const int cy = cell_coord(p[u].y, g.oy, g.inv_cell, g.ny);
+        const int cz = cell_coord(p[u].z, g.oz, g.inv_cell, g.nz);
+        key[u] = (uint32_t)((cz * g.ny + cy) * g.nx + cx);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) rk[u] = (i0 + u * GT < n) ? atomicAdd(&job[c].cell_start[key[u]], 1u) : 0u;
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int i = i0 + u * GT;
+        if (i < n) {
+          job[c].keys[i] = key[u];  // (read back by the same thread only)
+          job[c].rank[i] = rk[u];
+        }
+      }
     }
   }
   cluster.sync();
@@ -172,23 +193,49 @@ __device__ __forceinline__ void grids_phase(cg::cluster_group& cluster, PrepShar
     if (job[c].ordered)
       for (int i = gt; i < job[c].n; i += GT) __stcg(&job[c].tmp[__ldcg(&job[c].cell_start[job[c].keys[i]]) + job[c].rank[i]], (uint32_t)i);
   cluster.sync();
-  for (int c = first; c < last; c++)
-    for (int i = gt; i < job[c].n; i += GT) {
-      const uint32_t key = job[c].keys[i];
-      const uint32_t b = __ldcg(&job[c].cell_start[key]);
-      uint32_t r = job[c].rank[i];
-      if (job[c].ordered) {
+  for (int c = first; c < last; c++) {
+    const int n = job[c].n;
+    if (job[c].ordered) {
+      for (int i = gt; i < n; i += GT) {
+        const uint32_t key = job[c].keys[i];
+        const uint32_t b = __ldcg(&job[c].cell_start[key]);
         const uint32_t e = __ldcg(&job[c].cell_start[key + 1]);
-        r = 0;
+        uint32_t r = 0;
         for (uint32_t j = b; j < e; j++) r += (__ldcg(&job[c].tmp[j]) < (uint32_t)i) ? 1u : 0u;
+        const int sp = (int)(b + r);
+        const float4 p = job[c].pts[i];
+        job[c].spts[sp] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+        job[c].label[sp] = p.w;
+        job[c].inv_perm[i] = sp;
+        if (job[c].zero_flags) job[c].zero_flags[i] = 0;
       }
-      const int sp = (int)(b + r);
-      const float4 p = job[c].pts[i];
-      job[c].spts[sp] = make_float4(p.x, p.y, p.z, __int_as_float(i));
-      job[c].label[sp] = p.w;
-      job[c].inv_perm[i] = sp;
-      if (job[c].zero_flags) job[c].zero_flags[i] = 0;
+      continue;
     }
+    for (int i0 = gt; i0 < n; i0 += kU * GT) {  // (placed by the atomic ranks: kU points per thread and turn, see above)
+      uint32_t key[kU], r[kU], b[kU];
+      float4 p[kU];
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int i = i0 + u * GT < n ? i0 + u * GT : i0;
+        key[u] = job[c].keys[i];
+        r[u] = job[c].rank[i];
+        p[u] = job[c].pts[i];
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) b[u] = __ldcg(&job[c].cell_start[key[u]]);
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int i = i0 + u * GT;
+        if (i < n) {
+          const int sp = (int)(b[u] + r[u]);
+          job[c].spts[sp] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(i));
+          job[c].label[sp] = p[u].w;
+          job[c].inv_perm[i] = sp;
+          if (job[c].zero_flags) job[c].zero_flags[i] = 0;
+        }
+      }
+    }
+  }
   cluster.sync();
 }
 
