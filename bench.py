@@ -104,8 +104,8 @@ def _scene(seed):
 
 
 def pair_indices(rank, world, total):
-    """config C3's split: pair i -> rank i mod N"""
-    return list(range(rank, total, world))
+    """config C3's split: pair i -> rank i mod N (go-rio_b200/sharding.py: shard_pairs)"""
+    return importlib.import_module("go-rio_b200.sharding").shard_pairs(total, rank, world)
 
 
 def make_pairs(synth, rank, world, total, distinct=0, procs=None):
