@@ -349,6 +349,15 @@ class Registration:
                    C.c_int64(indices.shape[0]), C.c_int32(n))
         return counts, offsets, indices
 
+    def dbscan_labels(self, eps=0.9, core_min_pts=10, min_cluster=20, max_cluster=25000, which=0):
+        """(labels float32[n], n_clusters): DBSCANKdtreeCluster + the preprocessing nodelet's ranking of the clusters"""
+        n = self.n_source if which == 0 else self.n_target
+        labels = np.zeros(n, np.float32)
+        nc = C.c_int32()
+        self._call("dbscan_labels", C.c_int32(which), C.c_double(eps), C.c_int32(core_min_pts), C.c_int32(min_cluster), C.c_int32(max_cluster),
+                   labels.ctypes.data_as(C.c_void_p), C.byref(nc), C.c_int32(n))
+        return labels, nc.value
+
     def voxel_downsample(self, cloud, leaf):
         """pcl::VoxelGrid with a cubic leaf: float32 [m,4] {x,y,z,label}"""
         a, n, stride, xo, lo = self._layout(cloud)

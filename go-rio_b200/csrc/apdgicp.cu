@@ -2100,40 +2100,153 @@ int apd_source_nearest(apd_handle* h, const float* T, int32_t* idx, float* sq_di
 }
 
 // ---- the radius searches of the preprocessing stage on the cloud's grid ----
-int apd_radius_search(apd_handle* h, int32_t which, double radius, int32_t* counts, int64_t* offsets, int32_t* indices, int64_t capacity, int32_t n) {
-  if (!h || !(radius > 0.0) || (!counts && !offsets)) return APD_ERR_INVALID;
-  Cloud& c = which == 0 ? h->src : h->tgt;
-  if (!c.present || n != c.n || c.n <= 0) return fail(h, APD_ERR_INVALID, "cloud not set, or n is not its size");
-  DeviceGuard dg(h->device);
+}  // extern "C"
+
+namespace {
+
+// counts (and, with want_lists, CSR offsets + neighbour ids in ascending row order of the ORIGINAL index) of one radius
+// search per point of cloud c. mode 0: the fixed squared radius r2; 1 / 2: DBSCAN's range-dependent radii (prep_ops.cu)
+int radius_csr(apd_handle* h, Cloud& c, int mode, float r2, double eps, std::vector<int32_t>& hc, std::vector<long long>* ho, std::vector<int32_t>* lists_out) {
+  const int n = c.n;
   int rc = ensure_grid(h, c);
   if (rc != APD_OK) return rc;
   const size_t cb = align_up((size_t)n * sizeof(int32_t), 256), ob = align_up((size_t)n * sizeof(long long), 256);
   APD_CUDA(h, h->scratch.ensure(cb + ob));
   int32_t* d_counts = h->scratch.as<int32_t>();
   long long* d_off = reinterpret_cast<long long*>(h->scratch.as<char>() + cb);
-  launch_radius_search(c.view(), (float)radius, d_counts, nullptr, nullptr, h->stream, &h->launches);
+  launch_radius_search(c.view(), r2, mode, eps, d_counts, nullptr, nullptr, h->stream, &h->launches);
   APD_CUDA(h, cudaGetLastError());
-  std::vector<int32_t> hc((size_t)n);
+  hc.resize((size_t)n);
   APD_CUDA(h, cudaMemcpyAsync(hc.data(), d_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   APD_CUDA(h, wait_stream(h));
-  if (counts) std::memcpy(counts, hc.data(), (size_t)n * sizeof(int32_t));
-  if (!offsets) return APD_OK;
-  std::vector<long long> ho((size_t)n + 1);
-  ho[0] = 0;
-  for (int32_t i = 0; i < n; i++) ho[(size_t)i + 1] = ho[(size_t)i] + hc[(size_t)i];
-  for (int32_t i = 0; i <= n; i++) offsets[i] = ho[(size_t)i];
-  if (!indices) return APD_OK;
-  if (capacity < ho[(size_t)n]) return fail(h, APD_ERR_INVALID, "indices: capacity below offsets[n]");
-  if (ho[(size_t)n] == 0) return APD_OK;
+  if (!ho) return APD_OK;
+  ho->resize((size_t)n + 1);
+  (*ho)[0] = 0;
+  for (int32_t i = 0; i < n; i++) (*ho)[(size_t)i + 1] = (*ho)[(size_t)i] + hc[(size_t)i];
+  if (!lists_out) return APD_OK;
+  const long long total = (*ho)[(size_t)n];
+  lists_out->resize((size_t)total);
+  if (total == 0) return APD_OK;
   DevBuf lists;
-  APD_CUDA(h, lists.ensure((size_t)ho[(size_t)n] * sizeof(int32_t)));
-  APD_CUDA(h, cudaMemcpyAsync(d_off, ho.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-  launch_radius_search(c.view(), (float)radius, nullptr, d_off, lists.as<int32_t>(), h->stream, &h->launches);
+  APD_CUDA(h, lists.ensure((size_t)total * sizeof(int32_t)));
+  APD_CUDA(h, cudaMemcpyAsync(d_off, ho->data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  launch_radius_search(c.view(), r2, mode, eps, nullptr, d_off, lists.as<int32_t>(), h->stream, &h->launches);
   cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(indices, lists.p, (size_t)ho[(size_t)n] * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(lists_out->data(), lists.p, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = wait_stream(h);
   lists.release();
   APD_CUDA(h, e);
+  return APD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int apd_radius_search(apd_handle* h, int32_t which, double radius, int32_t* counts, int64_t* offsets, int32_t* indices, int64_t capacity, int32_t n) {
+  if (!h || !(radius > 0.0) || (!counts && !offsets)) return APD_ERR_INVALID;
+  Cloud& c = which == 0 ? h->src : h->tgt;
+  if (!c.present || n != c.n || c.n <= 0) return fail(h, APD_ERR_INVALID, "cloud not set, or n is not its size");
+  DeviceGuard dg(h->device);
+  const float r2 = (float)(radius * radius);  // pcl::KdTreeFLANN::radiusSearch: static_cast<float>(radius * radius)
+  std::vector<int32_t> hc, lists;
+  std::vector<long long> ho;
+  if (offsets && indices) {  // (learn the size first: the caller's capacity must hold offsets[n])
+    int rc = radius_csr(h, c, 0, r2, 0.0, hc, &ho, nullptr);
+    if (rc != APD_OK) return rc;
+    if (capacity < ho[(size_t)n]) return fail(h, APD_ERR_INVALID, "indices: capacity below offsets[n]");
+  }
+  int rc = radius_csr(h, c, 0, r2, 0.0, hc, offsets ? &ho : nullptr, (offsets && indices) ? &lists : nullptr);
+  if (rc != APD_OK) return rc;
+  if (counts) std::memcpy(counts, hc.data(), (size_t)n * sizeof(int32_t));
+  if (offsets) for (int32_t i = 0; i <= n; i++) offsets[i] = ho[(size_t)i];
+  if (offsets && indices && !lists.empty()) std::memcpy(indices, lists.data(), lists.size() * sizeof(int32_t));
+  return APD_OK;
+}
+
+// DBSCANKdtreeCluster::extract (4DRadarSLAM/include/dbscan/DBSCAN_simple.h:27-104) + the cluster labels of the
+// preprocessing nodelet (apps/preprocessing_nodelet_ntu.cpp:520-567): the two radius searches every point can be asked —
+// as a seed and as an expansion, with their range-dependent radii — run on the GPU grid, all points at once; the growth of
+// the clusters is the reference's sequential loop over those lists (its result does not depend on the order inside a
+// neighbour list), then clusters are ranked by the range of their centroid and every member gets rank + 1.
+int apd_dbscan_labels(apd_handle* h, int32_t which, double eps, int32_t core_min_pts, int32_t min_cluster, int32_t max_cluster, float* labels,
+                      int32_t* n_clusters, int32_t n) {
+  if (!h || !labels || !(eps >= 0.0)) return APD_ERR_INVALID;
+  Cloud& c = which == 0 ? h->src : h->tgt;
+  if (!c.present || n != c.n || c.n <= 0) return fail(h, APD_ERR_INVALID, "cloud not set, or n is not its size");
+  DeviceGuard dg(h->device);
+  std::vector<int32_t> cnt_seed, cnt_exp, nb_seed, nb_exp;
+  std::vector<long long> off_seed, off_exp;
+  int rc = radius_csr(h, c, 1, 0.f, eps, cnt_seed, &off_seed, &nb_seed);
+  if (rc != APD_OK) return rc;
+  rc = radius_csr(h, c, 2, 0.f, eps, cnt_exp, &off_exp, &nb_exp);
+  if (rc != APD_OK) return rc;
+  // the cloud itself (centroids)
+  std::vector<float> pts((size_t)n * 4);
+  APD_CUDA(h, cudaMemcpyAsync(pts.data(), c.view().pts, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  APD_CUDA(h, wait_stream(h));
+  enum { UN_PROCESSED = 0, PROCESSING = 1, PROCESSED = 2 };
+  std::vector<char> is_noise((size_t)n, 0), types((size_t)n, UN_PROCESSED);
+  std::vector<std::vector<int>> clusters;
+  std::vector<int> queue;
+  for (int i = 0; i < n; i++) {  // :32
+    if (types[(size_t)i] == PROCESSED) continue;
+    if (cnt_seed[(size_t)i] < core_min_pts) {  // :39-42
+      is_noise[(size_t)i] = 1;
+      continue;
+    }
+    queue.clear();
+    queue.push_back(i);
+    types[(size_t)i] = PROCESSED;
+    for (long long e = off_seed[(size_t)i]; e < off_seed[(size_t)i + 1]; e++) {  // :48-53 (whatever their type)
+      const int j = nb_seed[(size_t)e];
+      if (j != i) {
+        queue.push_back(j);
+        types[(size_t)j] = PROCESSING;
+      }
+    }
+    for (size_t sq = 1; sq < queue.size(); sq++) {  // :55-81
+      const int ci = queue[sq];
+      if (is_noise[(size_t)ci] || types[(size_t)ci] == PROCESSED) {
+        types[(size_t)ci] = PROCESSED;
+        continue;
+      }
+      if (cnt_exp[(size_t)ci] >= core_min_pts) {
+        for (long long e = off_exp[(size_t)ci]; e < off_exp[(size_t)ci + 1]; e++) {
+          const int j = nb_exp[(size_t)e];
+          if (types[(size_t)j] == UN_PROCESSED) {
+            queue.push_back(j);
+            types[(size_t)j] = PROCESSING;
+          }
+        }
+      }
+      types[(size_t)ci] = PROCESSED;
+    }
+    if ((long long)queue.size() >= min_cluster && (long long)queue.size() <= max_cluster) {  // :82-95
+      std::vector<int> r(queue);
+      std::sort(r.begin(), r.end());
+      r.erase(std::unique(r.begin(), r.end()), r.end());
+      clusters.push_back(std::move(r));
+    }
+  }
+  // preprocessing_nodelet_ntu.cpp:536-567: float centroid sums in index order, range by hypot, rank ascending, label rank + 1
+  // (later ranks overwrite earlier ones where clusters share a point)
+  std::vector<std::pair<float, int>> order;
+  for (size_t k = 0; k < clusters.size(); k++) {
+    float sx = 0, sy = 0, sz = 0;
+    for (int idx : clusters[k]) {
+      sx += pts[(size_t)idx * 4];
+      sy += pts[(size_t)idx * 4 + 1];
+      sz += pts[(size_t)idx * 4 + 2];
+    }
+    const int np = (int)clusters[k].size();
+    order.emplace_back(std::hypot(sx / np, sy / np, sz / np), (int)k);
+  }
+  std::stable_sort(order.begin(), order.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
+  std::fill(labels, labels + n, 0.f);
+  for (size_t rank = 0; rank < order.size(); rank++)
+    for (int idx : clusters[(size_t)order[rank].second]) labels[idx] = (float)(rank + 1);
+  if (n_clusters) *n_clusters = (int32_t)clusters.size();
   return APD_OK;
 }
 

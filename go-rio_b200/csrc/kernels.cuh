@@ -56,8 +56,8 @@ void launch_exclusive_scan_u32(uint32_t* data, size_t n, uint32_t* tmp, cudaStre
 // radius search of every point of a cloud on its own grid (pcl radiusSearch semantics: fp32 d2 STRICTLY below r^2, the
 // point itself included). counts: [n] at the ORIGINAL index. With offsets != nullptr (CSR, [n] at the original index) the
 // neighbours' original ids are written to indices[offsets[i] ...] (in the grid's scan order).
-void launch_radius_search(const CloudDev& c, float radius, int32_t* d_counts, const long long* d_offsets, int32_t* d_indices, cudaStream_t s,
-                          int64_t* launches);
+void launch_radius_search(const CloudDev& c, float r2_fixed, int mode, double eps, int32_t* d_counts, const long long* d_offsets, int32_t* d_indices,
+                          cudaStream_t s, int64_t* launches);
 // pcl::transformPointCloud(cloud, out, Eigen::Matrix4d): double arithmetic, cast to float; the label is carried over
 void launch_transform_cloud_d(const float4* in, int n, const double* T16_colmajor_host, float4* out, cudaStream_t s, int64_t* launches);
 // voxel grid pieces (pcl::VoxelGrid, see apd_voxel_downsample)

@@ -13,13 +13,33 @@ namespace {
 constexpr int kThreads = 256;
 
 // ---- radius search: one thread per (sorted) point; the cells within ceil(r / cell) of its own, row by row ----
+// mode 0: one radius for every query (r2 = float(radius * radius), as pcl::KdTreeFLANN::radiusSearch hands it to FLANN).
+// mode 1 / 2: the range-dependent radii of DBSCANSimpleCluster::extract (4DRadarSLAM/include/dbscan/DBSCAN_simple.h):
+//   1 (a seed, :35-38):      double norm = sqrt(x*x + y*y + z*z) [float expression, float sqrt]; |norm - 1| / 50 + eps
+//   2 (an expansion, :60-63): (sqrt(x*x + y*y + z*z) - 1) / 100 [all float] + eps
+__device__ __forceinline__ float query_r2(int mode, float r2_fixed, double eps, const float4& q, float& radius) {
+  if (mode == 0) {
+    radius = sqrtf(r2_fixed) * 1.0001f;  // (only sizes the reach in cells)
+    return r2_fixed;
+  }
+  const float nf = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)));
+  double rad;
+  if (mode == 1) rad = __dadd_rn(__ddiv_rn(fabs(__dsub_rn((double)nf, 1.0)), 50.0), eps);
+  else rad = __dadd_rn((double)__fdiv_rn(__fsub_rn(nf, 1.0f), 100.0f), eps);
+  radius = (float)rad * 1.0001f;
+  return (float)__dmul_rn(rad, rad);
+}
 __global__ void __launch_bounds__(kThreads) radius_search_kernel(const float4* __restrict__ spts, const uint32_t* __restrict__ cell_start, GridDesc g, int n,
-                                                                 float r2, int R, int32_t* __restrict__ counts, const long long* __restrict__ offsets,
-                                                                 int32_t* __restrict__ indices) {
+                                                                 float r2_fixed, int mode, double eps, int32_t* __restrict__ counts,
+                                                                 const long long* __restrict__ offsets, int32_t* __restrict__ indices) {
   const int w = blockIdx.x * kThreads + threadIdx.x;
   if (w >= n) return;
   const float4 q = spts[w];
   const int oi = __float_as_int(q.w);
+  float radius;
+  const float r2 = query_r2(mode, r2_fixed, eps, q, radius);
+  // every point within `radius` lies in a cell at most R away (the 0.01 covers the fp32 rounding of the cell coordinate)
+  const int R = radius > 0.f ? (int)floorf(radius * g.inv_cell + 0.01f) + 1 : 0;
   const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx), cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny), cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz);
   const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
   int c = 0;
@@ -139,12 +159,10 @@ __global__ void __launch_bounds__(kThreads) voxel_centroids_kernel(const float4*
 
 }  // namespace
 
-void launch_radius_search(const CloudDev& c, float radius, int32_t* d_counts, const long long* d_offsets, int32_t* d_indices, cudaStream_t s,
-                          int64_t* launches) {
+void launch_radius_search(const CloudDev& c, float r2_fixed, int mode, double eps, int32_t* d_counts, const long long* d_offsets, int32_t* d_indices,
+                          cudaStream_t s, int64_t* launches) {
   if (c.n <= 0) return;
-  // every point within `radius` lies in a cell at most R away (the 0.01 covers the fp32 rounding of the cell coordinate)
-  const int R = (int)floorf(radius * c.g.inv_cell + 0.01f) + 1;
-  radius_search_kernel<<<(c.n + kThreads - 1) / kThreads, kThreads, 0, s>>>(c.spts, c.cell_start, c.g, c.n, radius * radius, R, d_counts, d_offsets,
+  radius_search_kernel<<<(c.n + kThreads - 1) / kThreads, kThreads, 0, s>>>(c.spts, c.cell_start, c.g, c.n, r2_fixed, mode, eps, d_counts, d_offsets,
                                                                             d_indices);
   (*launches)++;
 }

@@ -247,6 +247,15 @@ APD_API int apd_source_nearest(apd_handle* h, const float* T, int32_t* idx, floa
  * entries — call once with indices = NULL to learn offsets[n], then again with the array. */
 APD_API int apd_radius_search(apd_handle* h, int32_t which, double radius, int32_t* counts, int64_t* offsets, int32_t* indices,
                       int64_t capacity, int32_t n);
+/* The cluster labels the registration reads in normal_x: DBSCANKdtreeCluster::extract
+ * (4DRadarSLAM/include/dbscan/DBSCAN_simple.h:27-104; eps, core_min_pts, min / max cluster size as
+ * preprocessing_nodelet_ntu.cpp:524-530 sets them: 0.9, 10, 20, 25000) followed by the nodelet's ranking (:536-567):
+ * clusters ordered by the range of their centroid, every member labelled rank + 1 (a point of several clusters keeps the
+ * last rank, as the nodelet's loop leaves it); labels[i] = 0 where the nodelet writes nothing. The radius searches — one
+ * per point as a seed (radius |norm - 1| / 50 + eps) and one as an expansion ((norm - 1) / 100 + eps) — run on the GPU
+ * grid of cloud `which`; the sequential growth over their lists runs on the host. labels: float[n]. */
+APD_API int apd_dbscan_labels(apd_handle* h, int32_t which, double eps, int32_t core_min_pts, int32_t min_cluster, int32_t max_cluster,
+                              float* labels, int32_t* n_clusters, int32_t n);
 /* pcl::VoxelGrid<PointT> with a cubic leaf (PCL 1.10 voxel_grid.hpp, downsample_all_data): one point per occupied voxel,
  * voxels in ascending voxel index; x, y, z are the float mean of the voxel's points; the cluster label (normal_x) goes
  * through PCL's normal accumulator — summed and normalised — so it becomes 1 where any member had a positive label, 0

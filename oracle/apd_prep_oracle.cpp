@@ -29,8 +29,8 @@
 extern "C" {
 
 // pass 1 (indices == nullptr): counts[i] = neighbours of point i; pass 2: indices[offsets[i] ...] in ascending index
-int apdo_radius_search(const float* xyzl, int32_t n, float radius, int32_t* counts, const int64_t* offsets, int32_t* indices) {
-  const float r2 = radius * radius;
+int apdo_radius_search(const float* xyzl, int32_t n, double radius, int32_t* counts, const int64_t* offsets, int32_t* indices) {
+  const float r2 = (float)(radius * radius);  // [ext] pcl::KdTreeFLANN::radiusSearch: static_cast<float>(radius * radius)
 #pragma omp parallel for schedule(dynamic, 64)
   for (int32_t i = 0; i < n; i++) {
     const float qx = xyzl[4 * (size_t)i], qy = xyzl[4 * (size_t)i + 1], qz = xyzl[4 * (size_t)i + 2];

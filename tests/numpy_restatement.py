@@ -185,3 +185,75 @@ def vgicp_linearize(T, src, cov_src, vox, resolution, method="DIRECT1", T_corr=N
             b += w * J.T @ M @ e
             corr.append((i, c))
     return err, H, b, corr
+
+
+# ---- DBSCANKdtreeCluster::extract + the preprocessing nodelet's cluster labels (4DRadarSLAM/include/dbscan/DBSCAN_simple.h:27-104,
+# apps/preprocessing_nodelet_ntu.cpp:520-567): a literal transcription, brute-force neighbour sets, small clouds only ----
+def dbscan_radius_lists(cloud, eps):
+    x = cloud[:, :3].astype(np.float32)
+    s = (x[:, 0] * x[:, 0] + x[:, 1] * x[:, 1]) + x[:, 2] * x[:, 2]        # float expression (:35-37)
+    nf = np.sqrt(s)                                                        # std::sqrt(float)
+    rad_seed = np.abs(nf.astype(np.float64) - 1.0) / 50.0 + eps            # double norm; std::abs(norm - 1)/50 + eps_ (:38)
+    rad_exp = ((nf - np.float32(1)) / np.float32(100)).astype(np.float64) + eps  # (float - 1)/100 + eps_ (:60-62)
+    out = []
+    for rad in (rad_seed, rad_exp):
+        r2 = (rad * rad).astype(np.float32)                                # [ext] pcl KdTreeFLANN: static_cast<float>(radius * radius)
+        lists = []
+        for i in range(x.shape[0]):
+            d = x[i] - x
+            d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+            lists.append(np.flatnonzero(d2 < r2[i]))                       # FLANN RadiusResultSet: dist < radius
+        out.append(lists)
+    return out
+
+
+def dbscan_labels(cloud, eps=0.9, min_pts=10, min_cluster=20, max_cluster=25000):
+    n = cloud.shape[0]
+    seed_nb, exp_nb = dbscan_radius_lists(cloud, eps)
+    UN, ING, DONE = 0, 1, 2
+    is_noise = [False] * n
+    types = [UN] * n
+    clusters = []
+    for i in range(n):
+        if types[i] == DONE:
+            continue
+        nn = seed_nb[i]
+        if len(nn) < min_pts:
+            is_noise[i] = True
+            continue
+        queue = [i]
+        types[i] = DONE
+        for j in nn:
+            if j != i:
+                queue.append(int(j))
+                types[j] = ING
+        sq = 1
+        while sq < len(queue):
+            ci = queue[sq]
+            if is_noise[ci] or types[ci] == DONE:
+                types[ci] = DONE
+                sq += 1
+                continue
+            nn = exp_nb[ci]
+            if len(nn) >= min_pts:
+                for j in nn:
+                    if types[j] == UN:
+                        queue.append(int(j))
+                        types[j] = ING
+            types[ci] = DONE
+            sq += 1
+        if min_cluster <= len(queue) <= max_cluster:
+            clusters.append(sorted(set(queue)))
+    x = cloud[:, :3].astype(np.float32)
+    dist = []
+    for c in clusters:
+        sx = sy = sz = np.float32(0)
+        for idx in c:
+            sx = np.float32(sx + x[idx, 0]); sy = np.float32(sy + x[idx, 1]); sz = np.float32(sz + x[idx, 2])
+        m = np.float32(len(c))
+        cx, cy, cz = np.float32(sx / m), np.float32(sy / m), np.float32(sz / m)
+        dist.append(float(np.sqrt(np.float64(cx) ** 2 + np.float64(cy) ** 2 + np.float64(cz) ** 2)))
+    labels = np.zeros(n, np.float32)
+    for rank, k in enumerate(np.argsort(np.array(dist), kind="stable")):
+        labels[clusters[k]] = rank + 1
+    return labels, len(clusters)

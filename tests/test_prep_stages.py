@@ -15,11 +15,11 @@ def o_radius(cloud, radius):
     n = cloud.shape[0]
     c = np.ascontiguousarray(cloud, np.float32)
     counts = np.empty(n, np.int32)
-    lib.apdo_radius_search(c.ctypes.data_as(C.c_void_p), C.c_int32(n), C.c_float(radius), counts.ctypes.data_as(C.c_void_p), None, None)
+    lib.apdo_radius_search(c.ctypes.data_as(C.c_void_p), C.c_int32(n), C.c_double(radius), counts.ctypes.data_as(C.c_void_p), None, None)
     offsets = np.zeros(n + 1, np.int64)
     offsets[1:] = np.cumsum(counts)
     idx = np.empty(int(offsets[-1]), np.int32)
-    lib.apdo_radius_search(c.ctypes.data_as(C.c_void_p), C.c_int32(n), C.c_float(radius), None, offsets.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p))
+    lib.apdo_radius_search(c.ctypes.data_as(C.c_void_p), C.c_int32(n), C.c_double(radius), None, offsets.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p))
     return counts, offsets, idx
 
 
@@ -75,6 +75,39 @@ def test_voxel_oracle_against_numpy(synth):
     wide = tgt.copy(); wide[0, 0] += 1e6
     out2, rc2 = o_voxel(wide, 0.001)
     assert rc2 == 1 and np.array_equal(out2, wide)
+
+
+def test_dbscan_restatement_is_sane(synth):
+    """the NumPy transcription of DBSCANKdtreeCluster + the nodelet's ranking: labels are 1 .. n_clusters, clusters nearer
+    to the sensor get the smaller label, members of a cluster are mutually reachable at the expansion radius"""
+    import numpy_restatement as nr
+
+    _, cloud, _ = synth.submap_pair(2500, n_source=500, n_frames=3, n_per_frame=1200)
+    labels, nc = nr.dbscan_labels(cloud)
+    assert nc >= 5 and set(np.unique(labels)) == set(range(nc + 1))
+    rng = [np.linalg.norm(cloud[labels == k, :3].mean(axis=0)) for k in range(1, nc + 1)]
+    assert all(a <= b + 1e-4 for a, b in zip(rng, rng[1:]))
+    assert min((labels == k).sum() for k in range(1, nc + 1)) >= 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("params", [dict(), dict(eps=1.2, core_min_pts=6, min_cluster=10, max_cluster=300)])
+def test_dbscan_labels_match_the_restatement(gorio, synth, params):
+    """the cluster labels the registration reads in normal_x (preprocessing_nodelet_ntu.cpp:520-567): GPU radius searches with
+    the reference's range-dependent radii + the reference's growth loop, against the literal NumPy transcription"""
+    import numpy_restatement as nr
+
+    src, tgt, _ = synth.submap_pair(2501, n_source=2500, n_frames=6, n_per_frame=1500)
+    g = gorio.FastAPDGICP(0)
+    g.set_input_target(tgt); g.set_input_source(src)
+    kw = dict(eps=0.9, min_pts=10, min_cluster=20, max_cluster=25000)
+    kw.update({{"core_min_pts": "min_pts"}.get(k, k): v for k, v in params.items()})
+    for which, cloud in ((0, src), (1, tgt)):
+        want, nc_want = nr.dbscan_labels(cloud, **kw)
+        got, nc = g.dbscan_labels(which=which, **params)
+        assert nc == nc_want and np.array_equal(got, want)
+    assert nc_want >= 5
+    g.close()
 
 
 @pytest.mark.gpu
