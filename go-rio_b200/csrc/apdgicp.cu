@@ -222,6 +222,7 @@ struct apd_handle {
   // registration this saves the D2H copies, the memsets of the box reduction and every cudaStreamQuery of the wait: a
   // batch pool of 32-64 host threads is bound by the rate of driver calls. APD_ZERO_COPY=0: copies + stream waits.
   bool zero_copy = true;
+  unsigned long long reduce_seq = 0;  // last sequence number a reduction kernel was asked to publish (h_small[kReduceSeqSlot])
   LmResult* h_lm_dev = nullptr;         // h_lm as the device sees it
   unsigned int* h_small_dev = nullptr;  // h_small as the device sees it
   unsigned long long seq = 0;           // last sequence number handed to a kernel
@@ -811,6 +812,7 @@ int prepare_fused(apd_handle* h, int bits) {
   return APD_OK;
 }
 
+constexpr int kReduceSeqSlot = 58;  // (double index into h_small: the sequence word of the zero-copy reductions)
 int ensure_small(apd_handle* h) {
   // [0..27] out28, [32..34] fitness out3, then tickets (uint) at double index 40, 41
   // device: [0..27] out28, [32..34] fitness out3, tickets (uint) at double index 40-42, the state of the bounding-box
@@ -878,6 +880,7 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
   int rc = ensure_small(h);
   if (rc != APD_OK) return rc;
   double* d_out = h->small.as<double>();
+  bool published = false;
   ReduceWork w;
   w.partials = h->partials.as<double>();
   w.ticket = reinterpret_cast<unsigned int*>(d_out + 40);
@@ -896,6 +899,13 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
       w.xchg.seq = ++h->xchg_seq;
       if (w.xchg.seq == 0) w.xchg.seq = h->xchg_seq = 2;  // (wrap-around: 0 means "no exchange"; keep the parity alternating)
     }
+    // the result goes straight into pinned host memory when nothing else has to happen to it on the stream first
+    published = h->zero_copy && h->h_small_dev && !h->profiling && !(h->comm && !h->peers_attached);
+    if (published) {
+      w.host_out = reinterpret_cast<double*>(h->h_small_dev);
+      w.host_seq_word = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(h->h_small_dev) + kReduceSeqSlot);
+      w.host_seq = ++h->reduce_seq;
+    }
     // ONE launch serves all the rank's chunks (a chunk table in the kernel; round 1 launched once per chunk)
     launch_linearize(h->src.view(), h->tgt.view(), h->shard_table(h->src.n), to_pose_d(T), corr_view(h), n_total, want_hb, w, d_out,
                      h->stream, &h->launches);
@@ -907,8 +917,12 @@ int reduce_pass(apd_handle* h, const hm::Pose& T, bool want_hb, double* H36, dou
     if (r != 0) return fail(h, APD_ERR_COMM, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclAllReduce failed");
   }
   double* hs = reinterpret_cast<double*>(h->h_small.p);
-  APD_CUDA(h, cudaMemcpyAsync(hs, d_out, kReduceVals * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  APD_CUDA(h, wait_stream(h));
+  if (published) {  // the kernel wrote the totals into hs itself: look at the sequence word (no copy, no stream wait)
+    APD_CUDA(h, wait_host_seq(h, reinterpret_cast<const volatile unsigned long long*>(hs + kReduceSeqSlot), h->reduce_seq));
+  } else {
+    APD_CUDA(h, cudaMemcpyAsync(hs, d_out, kReduceVals * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    APD_CUDA(h, wait_stream(h));
+  }
   // (ranks of one process: nobody goes on — possibly to a call that synchronises the device — while a peer's kernel may
   // still be waiting inside the exchange for a rank whose launch has not gone through yet; see group_allgather_chunks)
   if (h->group && !h->group->host_barrier()) return fail(h, APD_ERR_COMM, "a rank of the group did not finish the reduction");

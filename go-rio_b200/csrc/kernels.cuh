@@ -186,6 +186,11 @@ struct ReduceWork {
   unsigned int* ticket; // last-block-done counter (zeroed once; the kernel resets it)
   int max_blocks;
   PeerExchange xchg;    // seq != 0: exchange the totals with the peers in the kernel's tail
+  // zero-copy result: the last block also writes the totals into pinned host memory (as the device sees it) and then
+  // publishes host_seq there; the host polls that word instead of enqueueing a copy and waiting for the stream
+  double* host_out = nullptr;               // [28]
+  unsigned long long* host_seq_word = nullptr;
+  unsigned long long host_seq = 0;
 };
 // reference linearize (:247-304) / compute_error (:313-343) given the stored
 // correspondences and Mahalanobis matrices. out28 = 21 upper-triangular H

@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_geo, const double* __restrict__ s_geo64,
                  const int* __restrict__ corr, const void* __restrict__ mahaA, const void* __restrict__ mahaB,
                  const float4* __restrict__ t_spts, PoseD T, double cl_w, ShardTable sh, double* __restrict__ partials,
-                 double* __restrict__ out28, unsigned int* __restrict__ ticket, PeerExchange xchg) {
+                 double* __restrict__ out28, unsigned int* __restrict__ ticket, PeerExchange xchg, double* __restrict__ host_out,
+                 unsigned long long* __restrict__ host_seq_word, unsigned long long host_seq) {
   using L = StageLayout<kFp64>;
   constexpr int NV = kHB ? kReduceVals : 1;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -284,6 +285,12 @@ linearize_kernel(const float4* __restrict__ s_spts, const float* __restrict__ s_
     }
     if (tid < NV) *o = v;
     if (tid == 0) *ticket = 0;
+    if (host_out) {  // the totals straight into pinned host memory, then the sequence number the host is polling
+      if (tid < NV) host_out[kHB ? tid : 27] = v;
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(host_seq_word), "l"(host_seq) : "memory");
+    }
   }
 }
 
@@ -300,7 +307,7 @@ void launch_one(int blocks, cudaStream_t s, const CloudDev& src, const CloudDev&
     if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   linearize_kernel<kFp64, kHB, kSharded><<<blocks, kThreads, bytes, s>>>(src.spts, src.geo, src.geo64, c.corr, c.mahaA, c.mahaB, tgt.spts, T, cl_w,
-                                                                sh, w.partials, d_out28, w.ticket, w.xchg);
+                                                                sh, w.partials, d_out28, w.ticket, w.xchg, w.host_out, w.host_seq_word, w.host_seq);
 }
 
 // barrier of the ranks of a sharded registration (see launch_peer_barrier)
