@@ -979,10 +979,12 @@ int vgicp_build_voxelmap(apd_handle* h) {
     std::memcpy(&hi, &u, 4);
     const double clo = std::floor((double)lo / res - 0.5), chi = std::floor((double)hi / res - 0.5);
     if (!(std::fabs(clo) < 1e9) || !(std::fabs(chi) < 1e9)) return fail(h, APD_ERR_UNSUPPORTED, "voxel coordinates out of range");
+    const long long dim = (long long)(chi - clo) + 1;
     vg.mn[a] = (int)clo;
-    vg.dim[a] = (int)(chi - clo) + 1;
-    cells *= vg.dim[a];
-    if (cells >= 0xffffffffll) return fail(h, APD_ERR_UNSUPPORTED, "voxel_resolution too small for the extent of the target (more than 2^32 voxel slots)");
+    vg.dim[a] = (int)std::min<long long>(dim, 0x7fffffffll);
+    if (dim >= 0xffffffffll || cells * dim >= 0xffffffffll)
+      return fail(h, APD_ERR_UNSUPPORTED, "voxel_resolution too small for the extent of the target (more than 2^32 voxel slots)");
+    cells *= dim;
   }
   int bits = 1;
   while (bits < 32 && (1ll << bits) < cells) bits++;

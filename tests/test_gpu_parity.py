@@ -475,6 +475,10 @@ def test_vgicp_parameters_and_switching(gorio, synth, c1):
     for bad in (dict(voxel_resolution=0.0), dict(voxel_search=3), dict(voxel_mode=5)):
         with pytest.raises(gorio.ApdError):
             g.set_params(**bad)
+    # a resolution whose voxel grid over the target's extent would not fit 32-bit keys is refused, not wrapped
+    g.set_params(voxel_resolution=1e-8)
+    with pytest.raises(gorio.ApdError):
+        g.linearize(Tgt, want_hb=False)
     # back to APDGICP on the live handle
     g.set_params(variant=0, voxel_resolution=1.0, voxel_search=2, voxel_mode=0)
     oa = make(gorio, src, tgt)[1]
