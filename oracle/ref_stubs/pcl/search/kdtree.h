@@ -1,0 +1,58 @@
+// TEST INFRASTRUCTURE — stand-in for pcl::search::KdTree as the reference's headers use it. Brute force: the definition.
+// [ext] PCL 1.10 kdtree_flann.hpp + FLANN 1.9.1 (L2_Simple<float>): squared distances are fp32, (dx*dx + dy*dy) + dz*dz;
+//   nearestKSearch(point, k): the k nearest, ascending by distance — ties by lower index here (FLANN's tie order follows
+//     its tree layout and cannot be restated; the oracle and the CUDA library use the same (d2, index) rule);
+//   radiusSearch(index, radius): the squared radius handed to FLANN is static_cast<float>(radius * radius), a point is a
+//     neighbour when its squared distance is STRICTLY below it (RadiusResultSet), sorted by distance.
+#ifndef APDO_REF_STUB_PCL_SEARCH_KDTREE
+#define APDO_REF_STUB_PCL_SEARCH_KDTREE
+#include <pcl/point_types.h>
+namespace pcl {
+namespace search {
+template <typename PointT>
+class KdTree {
+public:
+  using Ptr = std::shared_ptr<KdTree<PointT>>;
+  using PointCloudConstPtr = typename pcl::PointCloud<PointT>::ConstPtr;
+  void setInputCloud(const PointCloudConstPtr& cloud) { input_ = cloud; }
+  PointCloudConstPtr getInputCloud() const { return input_; }
+  int nearestKSearch(const PointT& q, int k, std::vector<int>& k_indices, std::vector<float>& k_sqr_distances) const {
+    std::vector<std::pair<float, int>> all(input_->points.size());
+    for (std::size_t i = 0; i < input_->points.size(); i++) all[i] = std::make_pair(sqdist(q, input_->points[i]), (int)i);
+    const std::size_t kk = std::min<std::size_t>((std::size_t)k, all.size());
+    std::partial_sort(all.begin(), all.begin() + kk, all.end());
+    k_indices.resize(kk);
+    k_sqr_distances.resize(kk);
+    for (std::size_t i = 0; i < kk; i++) {
+      k_indices[i] = all[i].second;
+      k_sqr_distances[i] = all[i].first;
+    }
+    return (int)kk;
+  }
+  int radiusSearch(int index, double radius, std::vector<int>& k_indices, std::vector<float>& k_sqr_distances, unsigned int = 0) const {
+    const float r2 = static_cast<float>(radius * radius);
+    const PointT& q = input_->points[(std::size_t)index];
+    std::vector<std::pair<float, int>> found;
+    for (std::size_t i = 0; i < input_->points.size(); i++) {
+      const float d2 = sqdist(q, input_->points[i]);
+      if (d2 < r2) found.emplace_back(d2, (int)i);
+    }
+    std::sort(found.begin(), found.end());
+    k_indices.resize(found.size());
+    k_sqr_distances.resize(found.size());
+    for (std::size_t i = 0; i < found.size(); i++) {
+      k_indices[i] = found[i].second;
+      k_sqr_distances[i] = found[i].first;
+    }
+    return (int)found.size();
+  }
+private:
+  static float sqdist(const PointT& q, const PointT& p) {
+    const float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+    return (dx * dx + dy * dy) + dz * dz;
+  }
+  PointCloudConstPtr input_;
+};
+}  // namespace search
+}  // namespace pcl
+#endif

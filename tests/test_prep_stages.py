@@ -3,6 +3,7 @@ searches of the preprocessing nodelet (RadiusOutlierRemoval, DBSCAN's neighbour 
 pcl::VoxelGrid downsample of the scan-to-map branch — the CUDA library against the CPU restatement
 (oracle/apd_prep_oracle.cpp), bit for bit. CPU: the restatement against an independent NumPy computation."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -77,6 +78,36 @@ def test_voxel_oracle_against_numpy(synth):
     assert rc2 == 1 and np.array_equal(out2, wide)
 
 
+def _dbscan_cases():
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_dbscan_reference as m
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dbscan_reference.npz"))
+    return m, d
+
+
+def test_dbscan_restatement_equals_the_reference_code(synth):
+    """tests/golden/dbscan_reference.npz was written by the REFERENCE's own DBSCAN headers (DBSCAN_simple.h / DBSCAN_kdtree.h
+    compiled in place, oracle/ref_dbscan.cpp): the NumPy transcription gives the same labels and cluster counts on every
+    case — 1 to 154 clusters, both parameter sets; and, where oracle/_ref holds that build, so does a live run of it"""
+    import numpy_restatement as nr
+
+    m, d = _dbscan_cases()
+    lib_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libapd_ref_dbscan.so")
+    lib = C.CDLL(lib_path) if os.path.exists(lib_path) else None
+    for name, spec, params in m.CASES:
+        cloud = m.cloud_of(spec)
+        assert abs(cloud[:, :3].astype(np.float64).sum() - float(d[name + "_cloud_sum"])) < 1e-6  # the cloud the fixture was made on
+        eps, mp, lo, hi = params
+        labels, nc = nr.dbscan_labels(cloud, eps, int(mp), int(lo), int(hi))
+        assert nc == int(d[name + "_n_clusters"]) and np.array_equal(labels, d[name + "_labels"]), name
+        if lib is not None:
+            live, nc_live = m.reference_labels(lib, cloud, params)
+            assert nc_live == nc and np.array_equal(live, labels)
+
+
 def test_dbscan_restatement_is_sane(synth):
     """the NumPy transcription of DBSCANKdtreeCluster + the nodelet's ranking: labels are 1 .. n_clusters, clusters nearer
     to the sensor get the smaller label, members of a cluster are mutually reachable at the expansion radius"""
@@ -107,6 +138,20 @@ def test_dbscan_labels_match_the_restatement(gorio, synth, params):
         got, nc = g.dbscan_labels(which=which, **params)
         assert nc == nc_want and np.array_equal(got, want)
     assert nc_want >= 5
+    g.close()
+
+
+@pytest.mark.gpu
+def test_dbscan_labels_match_the_reference_code(gorio, synth):
+    """apd_dbscan_labels against the output of the reference's own DBSCAN headers (tests/golden/dbscan_reference.npz)"""
+    m, d = _dbscan_cases()
+    g = gorio.FastAPDGICP(0)
+    for name, spec, params in m.CASES:
+        cloud = m.cloud_of(spec)
+        g.set_input_source(cloud)
+        eps, mp, lo, hi = params
+        got, nc = g.dbscan_labels(eps=eps, core_min_pts=int(mp), min_cluster=int(lo), max_cluster=int(hi), which=0)
+        assert nc == int(d[name + "_n_clusters"]) and np.array_equal(got, d[name + "_labels"]), name
     g.close()
 
 
