@@ -196,3 +196,116 @@ def test_gpu_covariances_match_the_reference_code(gorio, fx, reg):
         scale = np.abs(want[ok]).max(axis=(1, 2), keepdims=True)
         assert (np.abs(got[ok] - want[ok]) / scale).max() < (1e-12 if reg == "NONE" else 1e-8)
     g.close()
+
+
+# =================================== FastGICP and FastVGICP: tests/golden/gicp_reference.npz (make_gicp_reference.py) ====
+import make_gicp_reference as mkg  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def gfx():
+    return np.load(os.path.join(HERE, "golden", "gicp_reference.npz"))
+
+
+def _check_gicp_sums(make, gfx, cname, thr_name, thr):
+    src, tgt, Tgt = mk.clouds(cname)
+    kw = dict(variant=1) if thr is None else dict(variant=1, max_correspondence_distance=thr)
+    r = make(src, tgt, **kw)
+    P = mk.poses(Tgt)
+    for pi, T in enumerate(P):
+        key = f"gicp_{cname}_{thr_name}_p{pi}"
+        e, H, b = r.linearize(T)
+        c, sq = r.get_correspondences()
+        assert np.array_equal(c, gfx[key + "_corr"]) and np.array_equal(sq[c >= 0], gfx[key + "_sqd"][c >= 0])
+        M = r.get_mahalanobis()[:, :3, :3]
+        assert _rel(M[c >= 0], gfx[key + "_maha"][c >= 0]) < 1e-9  # (no radar noise term: no atan2f anywhere)
+        assert abs(e - float(gfx[key + "_err"])) / float(gfx[key + "_err"]) < 1e-10
+        assert _rel(H, gfx[key + "_H"]) < 1e-10 and _rel(b, gfx[key + "_b"]) < 1e-9
+        e2 = r.compute_error(P[(pi + 1) % len(P)])
+        assert abs(e2 - float(gfx[key + "_err_trial_stale"])) / float(gfx[key + "_err_trial_stale"]) < 1e-10
+
+
+def _check_gicp_align(make, gfx, cname, aname, kw):
+    src, tgt, _ = mk.clouds(cname)
+    key = f"gicp_{cname}_align_{aname}"
+    r = make(src, tgt, variant=1, **kw)
+    a = r.align()
+    assert a["converged"] == bool(gfx[key + "_converged"]) and a["iterations"] == int(gfx[key + "_iterations"]), (a["iterations"], int(gfx[key + "_iterations"]))
+    assert np.abs(a["T"] - gfx[key + "_T"]).max() < 2e-6 and _rel(a["H"], gfx[key + "_H"]) < 1e-7
+    r.swap_source_and_target()
+    a2 = r.align()
+    assert a2["converged"] == bool(gfx[key + "_swapped_converged"]) and a2["iterations"] == int(gfx[key + "_swapped_iterations"])
+    assert np.abs(a2["T"] - gfx[key + "_swapped_T"]).max() < 2e-6
+
+
+def _check_vgicp(make, gfx, cname, vname, vkw):
+    src, tgt, Tgt = mk.clouds(cname)
+    P = mk.poses(Tgt)
+    r = make(src, tgt, variant=2, **vkw)
+    mult = vkw["voxel_mode"] == 2
+    for pi, T in enumerate(P[1:3]):
+        key = f"vgicp_{cname}_{vname}_p{pi}"
+        e, H, b = r.linearize(T)
+        vox, maha = r.vgicp_correspondences()
+        si, oi = np.nonzero(vox >= 0)  # (source index, offset) in table order = the order of the reference's list with one thread
+        assert np.array_equal(si.astype(np.int32), gfx[key + "_vsrc"]) and np.array_equal(vox[si, oi], gfx[key + "_vvox"])
+        assert _rel(maha[si, oi], gfx[key + "_vmaha"]) < (1e-7 if mult else 1e-9)
+        assert abs(e - float(gfx[key + "_err"])) / float(gfx[key + "_err"]) < (1e-8 if mult else 1e-10)
+        assert _rel(H, gfx[key + "_H"]) < (1e-8 if mult else 1e-10) and _rel(b, gfx[key + "_b"]) < (1e-7 if mult else 1e-9)
+        e2 = r.compute_error(P[3])
+        assert abs(e2 - float(gfx[key + "_err_trial_stale"])) / float(gfx[key + "_err_trial_stale"]) < (1e-8 if mult else 1e-10)
+    key = f"vgicp_{cname}_{vname}"
+    coords, counts, means, covs = r.vgicp_voxels()
+    assert np.array_equal(coords, gfx[key + "_coords"]) and np.array_equal(counts, gfx[key + "_counts"])
+    assert _rel(means, gfx[key + "_means"]) < (1e-9 if mult else 1e-13) and _rel(covs, gfx[key + "_covs"]) < (1e-8 if mult else 1e-12)
+    ra = make(src, tgt, variant=2, transformation_epsilon=0.01, **vkw)
+    a = ra.align()
+    assert a["converged"] == bool(gfx[key + "_align_converged"]) and a["iterations"] == int(gfx[key + "_align_iterations"])
+    assert np.abs(a["T"] - gfx[key + "_align_T"]).max() < 2e-6
+
+
+@pytest.mark.parametrize("cname", list(mk.CLOUDS))
+@pytest.mark.parametrize("thr_name,thr", [("thr2", 2.0), ("nothr", None)])
+def test_gicp_sums_match_the_reference_code(gfx, cname, thr_name, thr):
+    """fast_gicp::FastGICP (fast_gicp_impl.hpp:125-262) as the reference's own code computes it"""
+    _check_gicp_sums(_oracle, gfx, cname, thr_name, thr)
+
+
+GICP_ALIGNS = [("lm_default", {}), ("lm_deployed", dict(max_correspondence_distance=2.0, transformation_epsilon=0.1)),
+               ("gn_thr2", dict(max_correspondence_distance=2.0, optimizer=0))]
+
+
+@pytest.mark.parametrize("cname", list(mk.CLOUDS))
+@pytest.mark.parametrize("aname,kw", GICP_ALIGNS)
+def test_gicp_alignment_matches_the_reference_code(gfx, cname, aname, kw):
+    _check_gicp_align(_oracle, gfx, cname, aname, kw)
+
+
+@pytest.mark.parametrize("cname", list(mk.CLOUDS))
+@pytest.mark.parametrize("vname,vkw", mkg.VGICP_CASES)
+def test_vgicp_matches_the_reference_code(gfx, cname, vname, vkw):
+    """fast_gicp::FastVGICP (fast_vgicp_impl.hpp, fast_vgicp_voxel.hpp) as the reference's own code computes it: the voxel
+    map (coordinates and counts exact), the correspondence list (exact, in the reference's order), Mahalanobis / H / b / err,
+    stale compute_error, and whole alignments with the same iteration counts"""
+    _check_vgicp(_oracle, gfx, cname, vname, vkw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cname", list(mk.CLOUDS))
+@pytest.mark.parametrize("thr_name,thr", [("thr2", 2.0), ("nothr", None)])
+def test_gpu_gicp_sums_match_the_reference_code(gorio, gfx, cname, thr_name, thr):
+    _check_gicp_sums(lambda s, t, **kw: _gpu(gorio, s, t, **kw), gfx, cname, thr_name, thr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cname", list(mk.CLOUDS))
+@pytest.mark.parametrize("aname,kw", GICP_ALIGNS)
+def test_gpu_gicp_alignment_matches_the_reference_code(gorio, gfx, cname, aname, kw):
+    _check_gicp_align(lambda s, t, **k2: _gpu(gorio, s, t, **k2), gfx, cname, aname, kw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cname", list(mk.CLOUDS))
+@pytest.mark.parametrize("vname,vkw", mkg.VGICP_CASES)
+def test_gpu_vgicp_matches_the_reference_code(gorio, gfx, cname, vname, vkw):
+    _check_vgicp(lambda s, t, **k2: _gpu(gorio, s, t, **k2), gfx, cname, vname, vkw)
