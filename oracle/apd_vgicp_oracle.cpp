@@ -4,9 +4,10 @@
 //   /root/reference/fast_apdgicp/include/fast_gicp/gicp/fast_vgicp_voxel.hpp       (neighbor_offsets :10-44, the
 //       additive / multiplicative Gaussian voxels :79-124, create_voxelmap :131-158, voxel_coord :160-162)
 // FastVGICP derives from FastGICP: covariances (fast_gicp_impl.hpp:215-262, the same code as FastAPDGICP's), optimizer
-// and convergence test are the ones of apd_oracle.cpp. Parity unpinned by the reference (it holds no golden output for
-// this class either; gicp_test.cpp:148-166 states a 5 cm / 1 degree bar against a file that is absent) — pinned
-// against tests/numpy_restatement.py like the rest of the oracle.
+// and convergence test are the ones of apd_oracle.cpp. The reference holds no golden output for this class
+// (gicp_test.cpp:148-166 states a 5 cm / 1 degree bar against a file that is absent): pinned against what the
+// reference's own headers compute (ref_gicp.cpp -> tests/golden/gicp_reference.npz, tests/test_reference_code.py) and
+// against tests/numpy_restatement.py, like the rest of the oracle.
 // [ext] Eigen 3.3.7: `Vector4d / scalar` and `Matrix4d / scalar` divide element by element; Isometry3d * Vector4d is
 // ((r0 x + r1 y) + r2 z) + t w with w = 1; the 4x4 inverse of blockdiag(A, 1) is blockdiag(A^-1, 1) (closed-form adjugate
 // here, as everywhere in this oracle). The reference's correspondence LIST is in OpenMP thread order; here it is a table
