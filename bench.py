@@ -131,8 +131,19 @@ def make_pairs(synth, rank, world, total, distinct=0, procs=None):
 
 
 # ------------------------------------------------------------ reference arm ----
+REF_CODE_SO = os.path.join(REPO, "oracle", "_ref", "libapd_ref_apdgicp_nf.so")
+
+
 def load_cpu_impl():
+    """The CPU arm. Preferred: the REFERENCE'S OWN CODE (fast_apdgicp / lsq_registration headers compiled where they lie under
+    /root/reference against the stand-ins of oracle/ref_stubs, with the kd-tree the reference tree vendors; oracle/Makefile
+    -> oracle/_ref, which travels to the GPU box) — kind "reference". Else the oracle port."""
     from oracle_binding import ORACLE_REF_SO, oracle_lib  # tests/oracle_binding.py (checker side)
+    if os.path.exists(REF_CODE_SO):
+        lib = ctypes.CDLL(REF_CODE_SO)
+        lib.aref_create.restype = ctypes.c_void_p
+        return lib, "reference", -1, ("oracle/_ref/libapd_ref_apdgicp_nf.so: the reference's own FastAPDGICP / LsqRegistration headers compiled in place "
+                                     "(-O3, OpenMP) against stand-ins for Eigen / PCL, nearest neighbours through the reference tree's nanoflann kd-tree")
     if os.path.exists(ORACLE_REF_SO):
         return oracle_lib(ref=True), "port", 2, "oracle/_ref (reference loop structure + the reference tree's nanoflann kd-tree, OpenMP)"
     return oracle_lib(ref=False), "port", 1, "oracle port (own exact kd-tree, OpenMP)"
@@ -153,8 +164,32 @@ def cpu_handle(lib, search):
     return h
 
 
+def ref_code_registrations(lib, pairs, reps, want_poses=False):
+    """the reference's own code on `pairs` x reps, all host threads (setNumThreads as registrations.cpp:41 asks: all cores)"""
+    h = ctypes.c_void_p(lib.aref_create())
+    C = ctypes
+    lib.aref_set_params(h, C.c_int(20), C.c_int(3), C.c_double(DEPLOYED["max_correspondence_distance"]), C.c_double(0.86), C.c_double(0.5), C.c_double(1.0),
+                        C.c_int(64), C.c_int(0), C.c_double(2e-3), C.c_double(DEPLOYED["transformation_epsilon"]), C.c_int(10), C.c_double(1e-9),
+                        C.c_int(host_cores()))
+    ms = (C.c_double * reps)()
+    total, poses = 0.0, []
+    for s, t in pairs:
+        s32, t32 = np.ascontiguousarray(s, np.float32), np.ascontiguousarray(t, np.float32)
+        T = np.zeros(16, np.float32)
+        conv, it = C.c_int(), C.c_int()
+        rc = lib.aref_bench_align(h, s32.ctypes.data_as(C.c_void_p), C.c_int(s32.shape[0]), t32.ctypes.data_as(C.c_void_p), C.c_int(t32.shape[0]),
+                                  C.c_int(reps), ms, T.ctypes.data_as(C.c_void_p), C.byref(conv), C.byref(it))
+        assert rc == 0
+        total += sum(ms) / 1e3
+        poses.append((T.reshape(4, 4).T.copy(), bool(conv.value), it.value))
+    lib.aref_destroy(h)
+    return (total, len(pairs) * reps, poses) if want_poses else (total, len(pairs) * reps)
+
+
 def cpu_registrations(lib, search, pairs, reps):
-    """Runs the CPU restatement on `pairs` x reps with all host threads; returns (seconds, n)."""
+    """Runs the CPU arm on `pairs` x reps with all host threads; returns (seconds, n)."""
+    if search < 0:
+        return ref_code_registrations(lib, pairs, reps)
     h = cpu_handle(lib, search)
     ms = (ctypes.c_double * reps)()
     total = 0.0
@@ -580,7 +615,15 @@ def main():
                 k = min(8, n_mine)
                 cpu = cpu_poses(host_pairs[:k])
                 dT = max(float(np.abs(results_pcl[i]["T"].astype(np.float64) - cpu[i][0].astype(np.float64)).max()) for i in range(k))
-                parity = {"pairs": k, "max_abs_dT": dT,
+                ref_code = None
+                if os.path.exists(REF_CODE_SO):  # ... and against the reference's own code (oracle/_ref) on the same pairs
+                    rl = ctypes.CDLL(REF_CODE_SO)
+                    rl.aref_create.restype = ctypes.c_void_p
+                    _, _, rp = ref_code_registrations(rl, host_pairs[:k], 1, want_poses=True)
+                    ref_code = {"max_abs_dT": max(float(np.abs(results_pcl[i]["T"].astype(np.float64) - rp[i][0].astype(np.float64)).max()) for i in range(k)),
+                                "same_converged_and_iterations": all(bool(results_pcl[i]["converged"]) == rp[i][1] and results_pcl[i]["iterations"] == rp[i][2] for i in range(k)),
+                                "what": "oracle/_ref/libapd_ref_apdgicp_nf.so: the reference's own headers compiled in place (stand-in Eigen / PCL, nanoflann kd-tree)"}
+                parity = {"pairs": k, "max_abs_dT": dT, "vs_reference_code": ref_code,
                           "same_converged_and_iterations": all(bool(results_pcl[i]["converged"]) == bool(cpu[i][1]) and results_pcl[i]["iterations"] == cpu[i][2] for i in range(k)),
                           "against": "the CPU restatement (oracle), the first pairs of the batch — the pairs the reference arm times",
                           "bar": "float poses; fp32 Mahalanobis storage: within north_star's 1e-5 (the fp64 bar, 1e-6 m / 1e-6 rad, is held in tests/)"}

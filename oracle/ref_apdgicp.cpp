@@ -122,6 +122,33 @@ void aref_get_correspondences(void* h, int* idx, float* sqd, double* maha9) {
       for (int c = 0; c < 3; c++) maha9[9 * i + 3 * r + c] = idx[i] >= 0 ? p->maha()[i](r, c) : 0.0;
   }
 }
+// the timed protocol of bench.py (fast_apdgicp/src/align.cpp:57-83): clearTarget; clearSource; setInputTarget;
+// setInputSource; align — reps times, milliseconds of each into ms_out
+int aref_bench_align(void* h, const float* src_xyzl, int ns, const float* tgt_xyzl, int nt, int reps, double* ms_out, float* T_out, int* converged,
+                     int* iterations) {
+  Probe* p = static_cast<Probe*>(h);
+  for (int r = 0; r < reps; r++) {
+    const double t0 = omp_get_wtime();
+    p->clearTarget();
+    p->clearSource();
+    p->tgt.reset(new Cloud());
+    fill(*p->tgt, tgt_xyzl, nt);
+    p->setInputTarget(p->tgt);
+    p->src.reset(new Cloud());
+    fill(*p->src, src_xyzl, ns);
+    p->setInputSource(p->src);
+    Cloud out;
+    p->align(out, Eigen::Matrix4f::Identity());
+    ms_out[r] = 1e3 * (omp_get_wtime() - t0);
+  }
+  const Eigen::Matrix4f T = p->getFinalTransformation();
+  if (T_out)
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) T_out[c * 4 + r] = T(r, c);
+  if (converged) *converged = p->hasConverged() ? 1 : 0;
+  if (iterations) *iterations = p->iterations();
+  return 0;
+}
 // guess: float[16] column-major or NULL; T_out: float[16] column-major
 void aref_align(void* h, const float* guess, float* T_out, int* converged, int* iterations, double* H36) {
   Probe* p = static_cast<Probe*>(h);
