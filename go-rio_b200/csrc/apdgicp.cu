@@ -8,6 +8,7 @@
 #include <emmintrin.h>
 
 #include <atomic>
+#include <memory>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -253,6 +254,14 @@ struct apd_handle {
   bool pooled = false;  // a worker of a batch pool: throughput matters, not the latency of one registration
   int poll_wait_us = 0;
   cudaEvent_t done_ev = nullptr;
+  // Two pooled registrations per launch (batch_worker / PairSpot): a registration whose loop is ready to launch waits
+  // (at most pair_hold_us) in its device's spot for the next one that becomes ready, and that one's worker launches both.
+  // pair_state: 0 none, 1 waiting in the spot, 2 taken by a partner (launch in progress), 3 launched on launch_stream.
+  std::atomic<int> pair_state{0};
+  cudaEvent_t pair_ev = nullptr;          // what this handle's stream holds before the loop (cloud copies), for the partner's stream
+  cudaStream_t launch_stream = nullptr;   // the stream the loop in flight was launched on (this handle's own, or the partner's)
+  LmJob staged_job{};                     // the loop as prepared for launch
+  LmConfig staged_cfg{};
   // batch workers ask the device loop to append the getFitnessScore pass (saves a launch and a round trip per pair)
   bool fuse_fitness = false;
   double fuse_inlier_sq_thr = 0.25;
@@ -1552,7 +1561,7 @@ int finish_device_align(apd_handle* h, const LmResult* r) {
 }
 
 // LsqRegistration::computeTransformation (lsq :55-80) in one launch (lm.cu)
-int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg, int prep_bits = 0) {
+int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg, int prep_bits = 0, bool stage_only = false) {
   int rc = ensure_corr_buffers(h);
   if (rc != APD_OK) return rc;
   if (!h->lm_result.p) {
@@ -1571,6 +1580,12 @@ int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg,
   h->fused_inflight = prep_bits;
   job.seq = ++h->seq;
   job.host_result = h->zero_copy ? h->h_lm_dev : nullptr;
+  h->launch_stream = h->stream;
+  if (stage_only && h->zero_copy) {  // (a pool worker launches it, alone or with a partner: launch_staged)
+    h->staged_job = job;
+    h->staged_cfg = cfg;
+    return APD_OK;
+  }
   {
     ProfScope ps(h, APD_K_LM);
     launch_lm(&job, nullptr, 1, cfg, h->lm_cluster, h->lm_min_blocks, h->stream, &h->launches);
@@ -1582,7 +1597,7 @@ int enqueue_device_align(apd_handle* h, const float* guess, const LmConfig& cfg,
 
 // The device-resident loop in two halves, so that a pool worker can keep several registrations in flight:
 // begin_device_align enqueues covariances + the loop and returns; result_arrived polls; end_device_align unpacks.
-int begin_device_align(apd_handle* h, const float* guess) {
+int begin_device_align(apd_handle* h, const float* guess, bool stage_only = false) {
   const auto t_a = std::chrono::steady_clock::now();
   const double bbox_before = h->phase_s[1];
   // FastAPDGICP::computeTransformation (:148-157): the covariances — by the separate kernels, or (prep_bits) inside the loop's launch
@@ -1598,7 +1613,7 @@ int begin_device_align(apd_handle* h, const float* guess) {
     cfg.inlier_sq_thr = h->fuse_inlier_sq_thr;
   }
   h->pending_fitness = cfg.want_fitness != 0;
-  rc = enqueue_device_align(h, guess, cfg, prep_bits);
+  rc = enqueue_device_align(h, guess, cfg, prep_bits, stage_only);
   h->phase_s[3] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_b).count();
   return rc;
 }
@@ -1807,6 +1822,7 @@ int apd_destroy(apd_handle* h) {
   for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
   if (h->done_ev) cudaEventDestroy(h->done_ev);
+  if (h->pair_ev) cudaEventDestroy(h->pair_ev);
   h->src.release(); h->tgt.release();
   h->corr.release(); h->sqd.release(); h->second.release(); h->mahaA.release(); h->mahaB.release();
   h->vkey.release(); h->vcnt.release(); h->vmean.release(); h->vcov.release(); h->vcorr.release(); h->vmaha.release();
@@ -2472,9 +2488,40 @@ struct apd_batch {
   int n_pairs = 0, stride = 0, xyz_off = 0, label_off = 0, with_fitness = 0;
   bool device_clouds = false;
   std::atomic<int> next{0};
+  // Two registrations per launch. A device runs at most 128 grids at a time; the pool's build of the loop kernel has 148
+  // cluster slots (2 CTAs per SM, clusters of 2), so with one registration per launch 20 of them stay empty (CTA-slot
+  // occupancy 0.86 = 128 / 148, measured). One spot per device: the handle whose loop is ready and waits for a partner.
+  struct PairSpot {
+    std::mutex mu;
+    apd_handle* h = nullptr;
+  };
+  std::vector<std::unique_ptr<PairSpot>> spots;
+  int pair_hold_us = 200;  // how long a ready registration waits for a partner (APD_PAIR_HOLD_US; 0: one per launch)
 };
 
 namespace {
+
+// launch the staged loop of `h` — with the staged loop of `partner` in the same grid when there is one — on h's stream
+int launch_staged(apd_handle* h, apd_handle* partner) {
+  DeviceGuard dg(h->device);
+  if (partner) {
+    APD_CUDA(h, cudaStreamWaitEvent(h->stream, partner->pair_ev, 0));  // the partner's cloud copies
+    partner->launch_stream = h->stream;
+  }
+  launch_lm(&h->staged_job, nullptr, 1, h->staged_cfg, h->lm_cluster, h->lm_min_blocks, h->stream, &h->launches, partner ? &partner->staged_job : nullptr);
+  const cudaError_t e = cudaGetLastError();
+  h->k_launches[APD_K_LM]++;
+  if (partner) partner->pair_state.store(3, std::memory_order_release);
+  h->pair_state.store(0, std::memory_order_release);
+  APD_CUDA(h, e);
+  return APD_OK;
+}
+
+// can the staged loops of a and b share a launch? (same kernel build, cluster size and configuration — always, within a batch)
+bool pairable(const apd_handle* a, const apd_handle* b) {
+  return a->device == b->device && a->lm_cluster == b->lm_cluster && a->lm_min_blocks == b->lm_min_blocks &&
+         std::memcmp(&a->staged_cfg, &b->staged_cfg, sizeof(LmConfig)) == 0;
+}
 
 // result of pair i from the handle that has just finished it (rc: the status so far)
 void batch_fill_result(apd_batch* b, apd_handle* h, int i, int rc) {
@@ -2508,6 +2555,7 @@ struct PoolSlot {
   apd_handle* h = nullptr;
   int pair = -1;
   int state = kSlotIdle;
+  int di = 0;  // index of the handle's device in the batch
   std::chrono::steady_clock::time_point since;
 };
 
@@ -2523,7 +2571,31 @@ bool bboxes_arrived(const apd_handle* h) {
 // enqueue the registration of the slot's pair (the clouds are set, their boxes have arrived)
 void slot_enqueue(apd_batch* b, PoolSlot& sl) {
   apd_handle* h = sl.h;
-  int rc = begin_device_align(h, b->pairs[sl.pair].guess);
+  const bool pairing = b->pair_hold_us > 0 && h->zero_copy;
+  int rc = begin_device_align(h, b->pairs[sl.pair].guess, pairing);
+  if (rc == APD_OK && pairing && h->zero_copy) {
+    // ready to launch: with the registration waiting in the device's spot, or wait there for the next one
+    apd_batch::PairSpot& spot = *b->spots[(size_t)sl.di];
+    apd_handle* partner = nullptr;
+    bool waiting = false;
+    {
+      std::lock_guard<std::mutex> lk(spot.mu);
+      if (spot.h && pairable(h, spot.h)) {
+        partner = spot.h;
+        spot.h = nullptr;
+        partner->pair_state.store(2, std::memory_order_release);
+      } else if (!spot.h) {
+        if (!h->pair_ev) rc = cudaEventCreateWithFlags(&h->pair_ev, cudaEventDisableTiming) == cudaSuccess ? APD_OK : APD_ERR_CUDA;
+        if (rc == APD_OK) rc = cudaEventRecord(h->pair_ev, h->stream) == cudaSuccess ? APD_OK : APD_ERR_CUDA;
+        if (rc == APD_OK) {
+          h->pair_state.store(1, std::memory_order_release);
+          spot.h = h;
+          waiting = true;
+        }
+      }
+    }
+    if (rc == APD_OK && !waiting) rc = launch_staged(h, partner);
+  }
   if (rc == APD_OK && !h->zero_copy) rc = end_device_align(h);  // (no zero-copy mapping after all: finish it here)
   else if (rc == APD_OK) {
     sl.state = kSlotResult;
@@ -2586,7 +2658,9 @@ bool slot_stalled(PoolSlot& sl, bool arrived_now) {
   const auto now = std::chrono::steady_clock::now();
   if (now - sl.since < std::chrono::milliseconds(20)) return false;
   sl.since = now;
-  const cudaError_t e = cudaStreamQuery(sl.h->stream);
+  const int ps = sl.h->pair_state.load(std::memory_order_acquire);
+  if (ps == 1 || ps == 2) return false;  // not launched yet (waiting for a partner / the partner is launching it)
+  const cudaError_t e = cudaStreamQuery(ps == 3 ? sl.h->launch_stream : sl.h->stream);
   if (e == cudaErrorNotReady) return false;
   if (e == cudaSuccess && arrived_now) return false;
   sl.h->error = e == cudaSuccess ? "kernel finished without publishing its result" : cudaGetErrorString(e);
@@ -2640,6 +2714,7 @@ void batch_worker(apd_batch* b, int wi) {
   for (int s = ti; s < b->per_device; s += b->n_threads) {
     PoolSlot sl;
     sl.h = b->handles[(size_t)di * b->per_device + s];
+    sl.di = di;
     slots.push_back(sl);
   }
   int64_t taken = 0;
@@ -2681,6 +2756,28 @@ void batch_worker(apd_batch* b, int wi) {
             }
             break;
           case kSlotResult:
+            if (h->pair_state.load(std::memory_order_acquire) == 1 &&
+                std::chrono::steady_clock::now() - sl.since > std::chrono::microseconds(b->pair_hold_us)) {
+              // no partner came: launch it alone (unless one is taking it right now)
+              apd_batch::PairSpot& spot = *b->spots[(size_t)sl.di];
+              bool mine = false;
+              {
+                std::lock_guard<std::mutex> lk(spot.mu);
+                if (spot.h == h) {
+                  spot.h = nullptr;
+                  mine = true;
+                }
+              }
+              if (mine) {
+                const int rc = launch_staged(h, nullptr);
+                progressed = true;
+                if (rc != APD_OK) {
+                  batch_fill_result(b, h, sl.pair, rc);
+                  sl.state = kSlotIdle;
+                  break;
+                }
+              }
+            }
             if (result_arrived(h)) {
               DeviceGuard dg(h->device);
               int rc = end_device_align(h);
@@ -2805,6 +2902,8 @@ int apd_batch_create_multi(const int32_t* devices, int32_t n_devices, int32_t n_
   b->devices.assign(devices, devices + n_devices);
   b->per_device = n_workers;
   b->pairs_by_device.assign((size_t)n_devices, 0);
+  for (int d = 0; d < n_devices; d++) b->spots.emplace_back(new apd_batch::PairSpot());
+  if (const char* e = std::getenv("APD_PAIR_HOLD_US")) b->pair_hold_us = std::max(0, std::atoi(e));
   for (int d = 0; d < n_devices; d++)
     for (int s = 0; s < n_workers; s++) {
       apd_handle* h = nullptr;

@@ -312,7 +312,8 @@ constexpr int kLmMaxSource = 32768;  // larger source clouds use the streaming k
 // cluster: CTAs per registration (1, 2, 4 or 8).
 // min_blocks: 1 = the 128-register build of the kernel (one CTA per SM: a lone registration), 2 = the 64-register build
 // (two CTAs per SM: the workers of a batch pool)
+// two: a second job passed by value next to `one` (n_jobs becomes 2): two pooled registrations in one launch.
 void launch_lm(const LmJob* one, const LmJob* d_jobs, int n_jobs, const LmConfig& cfg, int cluster, int min_blocks, cudaStream_t s,
-               int64_t* launches);
+               int64_t* launches, const LmJob* two = nullptr);
 
 }  // namespace apd

@@ -427,11 +427,13 @@ __device__ __noinline__ void serial_lm_end(LmShared& s, const LmConfig& cfg, boo
 // pool is bound by the loop kernel's latency-limited SMs (35 % issue utilisation at 16 warps), and two resident CTAs of
 // different registrations hide each other's stalls: 20.7 k -> 26.3 k registrations/s on C2.
 template <bool kFp64, int kMinB>
-__global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const LmJob* __restrict__ jobs, LmConfig cfg) {
+__global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, LmJob two, const LmJob* __restrict__ jobs, LmConfig cfg) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned C = cluster.num_blocks();
   const unsigned rank = cluster.block_rank();
-  LmJob job = jobs ? jobs[blockIdx.x / C] : one;
+  // (two registrations of a pool may share a launch — by value, `two` is the second cluster's: a device runs at most 128
+  // grids at a time, fewer than the 148 cluster slots the pool's build of this kernel has)
+  LmJob job = jobs ? jobs[blockIdx.x / C] : (blockIdx.x < C ? one : two);
   __shared__ LmShared s;
   const int tid = threadIdx.x;
   const bool writer = (rank == 0 && tid == 0);  // the one thread that reports results
@@ -628,7 +630,8 @@ __global__ void __launch_bounds__(kLmThreads, kMinB) lm_kernel(LmJob one, const 
 }  // namespace
 
 void launch_lm(const LmJob* one, const LmJob* d_jobs, int n_jobs, const LmConfig& cfg, int cluster, int min_blocks, cudaStream_t s,
-               int64_t* launches) {
+               int64_t* launches, const LmJob* two) {
+  if (two && !d_jobs) n_jobs = 2;
   if (n_jobs <= 0) return;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)(n_jobs * cluster), 1, 1);
@@ -642,8 +645,9 @@ void launch_lm(const LmJob* one, const LmJob* d_jobs, int n_jobs, const LmConfig
   at[0].val.clusterDim.z = 1;
   lc.attrs = at;
   lc.numAttrs = 1;
-  LmJob byval{};
+  LmJob byval{}, byval2{};
   if (one) byval = *one;
+  if (two) byval2 = *two;
   if (cluster > 8) {  // beyond the portable cluster size: opt in once per kernel
     static bool allowed = [] {
       cudaFuncSetAttribute(lm_kernel<true, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -655,11 +659,11 @@ void launch_lm(const LmJob* one, const LmJob* d_jobs, int n_jobs, const LmConfig
     (void)allowed;
   }
   if (min_blocks >= 2) {
-    if (cfg.maha_fp64) cudaLaunchKernelEx(&lc, lm_kernel<true, 2>, byval, d_jobs, cfg);
-    else cudaLaunchKernelEx(&lc, lm_kernel<false, 2>, byval, d_jobs, cfg);
+    if (cfg.maha_fp64) cudaLaunchKernelEx(&lc, lm_kernel<true, 2>, byval, byval2, d_jobs, cfg);
+    else cudaLaunchKernelEx(&lc, lm_kernel<false, 2>, byval, byval2, d_jobs, cfg);
   } else {
-    if (cfg.maha_fp64) cudaLaunchKernelEx(&lc, lm_kernel<true, 1>, byval, d_jobs, cfg);
-    else cudaLaunchKernelEx(&lc, lm_kernel<false, 1>, byval, d_jobs, cfg);
+    if (cfg.maha_fp64) cudaLaunchKernelEx(&lc, lm_kernel<true, 1>, byval, byval2, d_jobs, cfg);
+    else cudaLaunchKernelEx(&lc, lm_kernel<false, 1>, byval, byval2, d_jobs, cfg);
   }
   (*launches)++;
 }
