@@ -636,7 +636,7 @@ def main():
             "config": {"workload": WORKLOAD, "pairs_per_step": args.pairs, "pairs_per_step_per_gpu": n_mine,
                        "distinct_scenes": args.pairs if args.distinct <= 0 else min(args.distinct, args.pairs),
                        "streams_per_gpu": args.streams, "api": "apd_batch_align_device (value) / apd_batch_align (e2e)",
-                       "optimizer_loop": "device-resident (lm.cu), one launch per registration",
+                       "optimizer_loop": "device-resident (lm.cu), one launch per registration or per two (a device runs at most 128 grids at a time: two ready registrations share a launch)",
                        "mahalanobis_storage": "fp32 (6 x 4 B per point; arithmetic fp64; within north_star's 1e-5, tests/test_gpu_parity.py)",
                        "protocol": "clearTarget;clearSource;setInputTarget;setInputSource;align",
                        "l2": "inputs larger than L2 (>= 512 MB of clouds per GPU per step against 126 MB); flushed (256 MiB write) before the timed region",

@@ -1289,7 +1289,10 @@ int set_cloud(apd_handle* h, Cloud& c, const void* pts, int32_t n, int32_t strid
     }
   }
   APD_CUDA(h, c.stage.ensure((size_t)std::max(n, 1) * sizeof(float4)));
-  stage_cloud(pts, n, stride, xyz_off, label_off, reinterpret_cast<float*>(c.stage.p), c.bbox);
+  // pool workers stage many clouds at once and the host's memory system is what bounds them: non-temporal stores
+  // (APD_STAGE_NT=0|1 overrides; a lone handle keeps ordinary stores — the buffer is small enough to stay in cache)
+  static const int nt_env = [] { const char* e = std::getenv("APD_STAGE_NT"); return e ? (std::atoi(e) != 0 ? 1 : 0) : -1; }();
+  stage_cloud(pts, n, stride, xyz_off, label_off, reinterpret_cast<float*>(c.stage.p), c.bbox, nt_env >= 0 ? nt_env != 0 : h->pooled);
   APD_CUDA(h, c.pts.ensure((size_t)std::max(n, 1) * sizeof(float4)));
   APD_CUDA(h, cudaMemcpyAsync(c.pts.p, c.stage.p, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
   if (h->zero_copy) {

@@ -25,7 +25,9 @@ inline __m128 pcl_xyz_label(const char* p) {
 
 // host AoS -> packed {x,y,z,label} staging + bounding box in one pass. The common layouts (packed float4; PCL's
 // PointXYZINormal: xyz at 0, label at 16, stride 48) take fixed-offset vector loads, anything else a gather per point.
-inline void stage_cloud(const void* pts, int n, int stride, int xyz_off, int label_off, float* dst, float bbox[6]) {
+// nt: the packed points go out with non-temporal stores (no read-for-ownership of the staging buffer, which only the DMA
+// engine reads next: one of the ~6 MB of host DRAM traffic a 60 k-point pair costs) — for many threads staging at once.
+inline void stage_cloud(const void* pts, int n, int stride, int xyz_off, int label_off, float* dst, float bbox[6], bool nt = false) {
   const char* base = reinterpret_cast<const char*>(pts);
   __m128 mn = _mm_set1_ps(FLT_MAX), mx = _mm_set1_ps(-FLT_MAX);
   if (stride == 16 && xyz_off == 0 && label_off == 12) {  // packed float4: one pass, copy + min / max
@@ -47,10 +49,17 @@ inline void stage_cloud(const void* pts, int n, int stride, int xyz_off, int lab
       _mm_prefetch(p + 1088, _MM_HINT_T0);
       _mm_prefetch(p + 1152, _MM_HINT_T0);
       const __m128 v0 = pcl_xyz_label(p), v1 = pcl_xyz_label(p + 48), v2 = pcl_xyz_label(p + 96), v3 = pcl_xyz_label(p + 144);
-      _mm_store_ps(dst + 4 * (size_t)i, v0);
-      _mm_store_ps(dst + 4 * (size_t)(i + 1), v1);
-      _mm_store_ps(dst + 4 * (size_t)(i + 2), v2);
-      _mm_store_ps(dst + 4 * (size_t)(i + 3), v3);
+      if (nt) {  // (four points = one 64-byte line of the staging buffer)
+        _mm_stream_ps(dst + 4 * (size_t)i, v0);
+        _mm_stream_ps(dst + 4 * (size_t)(i + 1), v1);
+        _mm_stream_ps(dst + 4 * (size_t)(i + 2), v2);
+        _mm_stream_ps(dst + 4 * (size_t)(i + 3), v3);
+      } else {
+        _mm_store_ps(dst + 4 * (size_t)i, v0);
+        _mm_store_ps(dst + 4 * (size_t)(i + 1), v1);
+        _mm_store_ps(dst + 4 * (size_t)(i + 2), v2);
+        _mm_store_ps(dst + 4 * (size_t)(i + 3), v3);
+      }
       mn = _mm_min_ps(v0, mn); mx = _mm_max_ps(v0, mx);
       mn1 = _mm_min_ps(v1, mn1); mx1 = _mm_max_ps(v1, mx1);
       mn2 = _mm_min_ps(v2, mn2); mx2 = _mm_max_ps(v2, mx2);
@@ -63,6 +72,7 @@ inline void stage_cloud(const void* pts, int n, int stride, int xyz_off, int lab
     }
     mn = _mm_min_ps(_mm_min_ps(mn, mn1), _mm_min_ps(mn2, mn3));
     mx = _mm_max_ps(_mm_max_ps(mx, mx1), _mm_max_ps(mx2, mx3));
+    if (nt) _mm_sfence();  // the copy engine reads the buffer next
   } else {
     for (int i = 0; i < n; i++) {
       const char* p = base + (size_t)i * stride;
