@@ -34,6 +34,35 @@ __device__ __forceinline__ unsigned long long bitonic_sort32(unsigned long long 
   }
   return key;
 }
+// ascending bitonic sort of one 32-bit key per lane (a stage is a shuffle and one predicated min / max: half the
+// instructions of the 64-bit stage above)
+__device__ __forceinline__ unsigned bitonic_sort32_u32(unsigned key, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const unsigned other = __shfl_xor_sync(kFull, key, stride);
+      const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
+      key = take_min ? min(key, other) : max(key, other);
+    }
+  }
+  return key;
+}
+// The buffered candidates (buf[0 .. n), n <= 32; one per lane, the other lanes infinite) in ascending key order, one per
+// lane. Sorted by a 32-bit stand-in — the upper 27 bits of the squared distance with the buffer slot in the lower five —
+// and fetched from the buffer by slot afterwards. Two candidates whose distances agree in those 27 bits (a relative
+// difference below 4e-6: about one flush in five hundred; exact ties of duplicated points) are not ordered by the
+// stand-in: then the exact 64-bit sort runs instead. The result is the same either way.
+__device__ __forceinline__ unsigned long long sort_buffer32(const unsigned long long* buf, int n, int lane) {
+  const unsigned long long mine = lane < n ? buf[lane] : kInfKey;
+  const unsigned coarse = (unsigned)(mine >> 32) & ~31u;
+  const unsigned pk = bitonic_sort32_u32(coarse | (unsigned)lane, lane);
+  const unsigned below = __shfl_up_sync(kFull, pk, 1);
+  const bool real = (pk | 31u) != 0xffffffffu;  // (the infinite keys sort last; they need no order among themselves)
+  const bool unsure = lane > 0 && real && ((pk ^ below) & ~31u) == 0;
+  if (__any_sync(kFull, unsure)) return bitonic_sort32(mine, lane);
+  return real ? buf[pk & 31u] : kInfKey;
+}
 // list (ascending, one key per lane) <- the 32 smallest of list U batch (batch ascending)
 __device__ __forceinline__ unsigned long long merge_keep32(unsigned long long list, unsigned long long batch, int lane) {
   const unsigned long long rb = shfl64(batch, 31 - lane);
@@ -81,9 +110,8 @@ static __device__ __noinline__ void kbest_flush(KBest& s, int lane, int k) {
     s.buf_n = 0;
     return;
   }
-  unsigned long long b = lane < s.buf_n ? s.buf[lane] : kInfKey;
+  const unsigned long long b = sort_buffer32(s.buf, s.buf_n, lane);
   __syncwarp();
-  b = bitonic_sort32(b, lane);
   s.list = s.empty ? b : merge_keep32(s.list, b, lane);  // nothing to merge with on the first flush
   s.empty = false;
   s.kth = shfl64(s.list, k - 1);
@@ -225,7 +253,7 @@ static __device__ __noinline__ unsigned long long knn_warp_query_at(const float4
       }
       if (__ballot_sync(kFull, cnt > 0)) scan_segments(spts, q.x, q.y, q.z, lane, k, b, cnt, st);
     }
-    kbest_flush(st, lane, k);
+    if (st.buf_n != 0) kbest_flush(st, lane, k);  // (a shell whose rows were all pruned leaves nothing: no call)
     r = rr;
   }
   return st.list;
