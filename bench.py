@@ -73,7 +73,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="scan/submap pairs per step over ALL GPUs (config C3: 4096)")
     ap.add_argument("--distinct", type=int, default=0, help="distinct scenes among the pairs (0: all; fewer are cycled — profiling aid)")
-    ap.add_argument("--streams", type=int, default=192, help="registrations in flight per GPU: handles (CUDA stream each) of the batch context, driven by a few host threads")
+    ap.add_argument("--streams", type=int, default=256, help="registrations in flight per GPU: handles (CUDA stream each) of the batch context, driven by a few host threads")
     ap.add_argument("--roofline-points", type=int, default=20_000_000)
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-c4", action="store_true")
