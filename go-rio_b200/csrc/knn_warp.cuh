@@ -94,10 +94,16 @@ __device__ __forceinline__ unsigned long long insert_keep32(unsigned long long l
 }
 constexpr int kInsertMax = 10;  // a flush of up to this many candidates inserts them one by one (~12 instructions each)
                                 // instead of the 32-key sort + merge (~180): most flushes at the end of a shell are small
-// (__noinline__: the flush is the bulk of the search's code and is reached from four places; one copy keeps the loop
+// (__noinline__: sort + merge are the bulk of the search's code and are reached from four places; one copy keeps the loop
 // kernel's hot path inside the instruction cache — under a pool's co-residency 8 % of its stall cycles were
-// instruction fetches)
-static __device__ __noinline__ void kbest_flush(KBest& s, int lane, int k) {
+// instruction fetches. Arguments and result by value: the search state stays in registers across the call — with the
+// state passed by reference every flush stored and re-loaded it through local memory, ~50 instructions per query.)
+static __device__ __noinline__ unsigned long long kbest_sort_merge(unsigned long long list, const unsigned long long* buf, int n, bool empty, int lane) {
+  const unsigned long long b = sort_buffer32(buf, n, lane);
+  __syncwarp();
+  return empty ? b : merge_keep32(list, b, lane);  // nothing to merge with on the first flush
+}
+__device__ __forceinline__ void kbest_flush(KBest& s, int lane, int k) {
   if (s.buf_n == 0) return;  // warp-uniform
   __syncwarp();
   if (!s.empty && s.buf_n <= kInsertMax) {
@@ -106,14 +112,10 @@ static __device__ __noinline__ void kbest_flush(KBest& s, int lane, int k) {
       if (c < s.kth) s.list = insert_keep32(s.list, c, lane);  // (uniform; kth only shrinks while inserting)
     }
     __syncwarp();
-    s.kth = shfl64(s.list, k - 1);
-    s.buf_n = 0;
-    return;
+  } else {
+    s.list = kbest_sort_merge(s.list, s.buf, s.buf_n, s.empty, lane);
+    s.empty = false;
   }
-  const unsigned long long b = sort_buffer32(s.buf, s.buf_n, lane);
-  __syncwarp();
-  s.list = s.empty ? b : merge_keep32(s.list, b, lane);  // nothing to merge with on the first flush
-  s.empty = false;
   s.kth = shfl64(s.list, k - 1);
   s.buf_n = 0;
 }
