@@ -171,8 +171,10 @@ __device__ __forceinline__ void scan_segments(const float4* spts, float qx, floa
 // (d2, original index) key per lane, ascending: lanes 0..k-1 hold the answer. kbuf: 32 keys of shared memory owned by
 // this warp. Replaces the nearestKSearch of reference fast_apdgicp_impl.hpp:364.
 // knn_warp_query_at: the same for an arbitrary query point q (not necessarily a point of the cloud).
+// (the grid by value: its eight words stay in registers across the out-of-line sort, which a reference into the job
+// structure in local memory would have to be re-read after)
 static __device__ __noinline__ unsigned long long knn_warp_query_at(const float4* spts, const uint32_t* cell_start,
-                                                                const GridDesc& g, int k, const float4 q, int lane, unsigned long long* kbuf) {
+                                                                const GridDesc g, int k, const float4 q, int lane, unsigned long long* kbuf) {
   const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
   const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
   const int cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz);
