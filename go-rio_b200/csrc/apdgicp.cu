@@ -298,11 +298,19 @@ struct apd_handle {
   // APD_CELLS_PER_POINT_SMALL overrides.
   double cells_per_point_small = 1.0;  // (measured on the C3 pool: 4 -> 29.8 k, 2 -> 30.5 k, 1 -> 31.2 k, 0.5 -> 31.5 k registrations/s)
   int small_cloud_n = 8192;
-  double cells_for(int n) const {
+  // Submaps (small_cloud_n < n < 500 k points): 4 cells per point when every point's k neighbours are searched (round 1, one
+  // B200: 0.5 / 1 / 2 / 4 / 8 -> 12.4 / 15.8 / 18.9 / 20.7 / 18.4 k registrations/s). A target whose covariances are
+  // computed on demand is searched ~15 k times, not 60 k + 11 k: half the cells — half the cell_start array every resident
+  // registration drags through L2, fewer rows per shell — is worth more than the shorter candidate lists (C3 probe,
+  // profiles/r02_run46.sh: 1 / 1.5 / 2 / 2.5 / 3 / 4 -> 37.5 / 39.3 / 40.0 / 39.4 / 38.9 / 38.3 k registrations/s).
+  // APD_CELLS_PER_POINT_MID / APD_CELLS_PER_POINT_MID_LAZY override. The resolution changes no result (exact searches).
+  double cells_per_point_mid = 4.0, cells_per_point_mid_lazy = 2.0;
+  double cells_for(int n, bool lazy_cov = false) const {
     if (cells_per_point > 0.0) return cells_per_point;
     if (n >= 500000) return 8.0;
-    return n <= small_cloud_n ? cells_per_point_small : 4.0;
+    return n <= small_cloud_n ? cells_per_point_small : (lazy_cov ? cells_per_point_mid_lazy : cells_per_point_mid);
   }
+  double max_cells_for(int n) const { return std::max(cells_for(n, false), cells_for(n, true)); }  // (what the arrays are sized for)
   // kNN kernel choice: 0 auto (warp-per-point below knn_thread_min_n points and k <= 32, thread-per-point
   // above: the warp kernel has the shorter critical path, the thread kernel the higher throughput),
   // 1 warp, 2 thread. Override with APD_KNN_MODE=warp|thread.
@@ -786,7 +794,7 @@ int prepare_fused(apd_handle* h, int bits) {
   Cloud& s = h->src;
   Cloud& t = h->tgt;
   const int k = h->params.k_correspondences;
-  const double s_cpp = h->cells_for(s.n), t_cpp = h->cells_for(t.n);
+  const double s_cpp = h->max_cells_for(s.n), t_cpp = h->max_cells_for(t.n);  // (capacities: whichever resolution the launch picks)
   if (bits & 1) {
     const size_t n = (size_t)s.n;
     APD_CUDA(h, s.spts.ensure(n * sizeof(float4)));
@@ -1488,7 +1496,7 @@ LmJob lm_job(apd_handle* h, const hm::Pose& x0, int prep_bits = 0) {
     j.s_scratch = h->work.as<uint32_t>();
     j.t_scratch = h->work.as<uint32_t>() + 3 * (size_t)s.n;
     j.s_cells_per_point = h->cells_for(s.n);
-    j.t_cells_per_point = h->cells_for(t.n);
+    j.t_cells_per_point = h->cells_for(t.n, h->tgt.cov_lazy && !h->tgt.cov_valid);
     j.s_k = h->params.k_correspondences;
     j.s_reg = h->params.regularization;
     j.gicp = h->params.variant == APD_VARIANT_GICP ? 1 : 0;
@@ -1791,6 +1799,14 @@ int apd_create(int device, apd_handle** out) {
   if (const char* e = std::getenv("APD_CELLS_PER_POINT_SMALL")) {
     const double v = std::atof(e);
     if (v > 0.01 && v < 1000.0) h->cells_per_point_small = v;
+  }
+  if (const char* e = std::getenv("APD_CELLS_PER_POINT_MID")) {
+    const double v = std::atof(e);
+    if (v > 0.01 && v < 1000.0) h->cells_per_point_mid = v;
+  }
+  if (const char* e = std::getenv("APD_CELLS_PER_POINT_MID_LAZY")) {
+    const double v = std::atof(e);
+    if (v > 0.01 && v < 1000.0) h->cells_per_point_mid_lazy = v;
   }
   if (const char* e = std::getenv("APD_LM_CLUSTER")) {
     const int v = std::atoi(e);
@@ -2835,7 +2851,7 @@ int reserve_pool_buffers(apd_handle* h, int ns, int nt, bool host_clouds) {
     APD_CUDA(h, cl.spts.ensure(n * sizeof(float4)));
     APD_CUDA(h, cl.label.ensure(n * sizeof(float)));
     APD_CUDA(h, cl.inv_perm.ensure(n * sizeof(int)));
-    APD_CUDA(h, cl.cell_start.ensure((size_t)grid_cell_capacity((int)n, h->cells_for((int)n)) * sizeof(uint32_t)));
+    APD_CUDA(h, cl.cell_start.ensure((size_t)grid_cell_capacity((int)n, h->max_cells_for((int)n)) * sizeof(uint32_t)));
     APD_CUDA(h, cl.cov.ensure(n * 6 * sizeof(double)));
   }
   APD_CUDA(h, s.geo.ensure(S * sizeof(float)));

@@ -92,7 +92,10 @@ __device__ __forceinline__ unsigned long long insert_keep32(unsigned long long l
   const unsigned long long up = shfl_up64(list, 1);
   return lane < pos ? list : (lane == pos ? c : up);
 }
-constexpr int kInsertMax = 10;  // a flush of up to this many candidates inserts them one by one (~12 instructions each)
+#ifndef APD_KNN_INSERT_MAX
+#define APD_KNN_INSERT_MAX 10
+#endif
+constexpr int kInsertMax = APD_KNN_INSERT_MAX;  // a flush of up to this many candidates inserts them one by one (~12 instructions each)
                                 // instead of the 32-key sort + merge (~180): most flushes at the end of a shell are small
 // (__noinline__: sort + merge are the bulk of the search's code and are reached from four places; one copy keeps the loop
 // kernel's hot path inside the instruction cache — under a pool's co-residency 8 % of its stall cycles were
@@ -173,6 +176,10 @@ __device__ __forceinline__ void scan_segments(const float4* spts, float qx, floa
 // knn_warp_query_at: the same for an arbitrary query point q (not necessarily a point of the cloud).
 // (the grid by value: its eight words stay in registers across the out-of-line sort, which a reference into the job
 // structure in local memory would have to be re-read after)
+#ifndef APD_KNN_THIN_SHELLS
+#define APD_KNN_THIN_SHELLS 3
+#endif
+constexpr int kThinShells = APD_KNN_THIN_SHELLS;  // shells grow one cell at a time below this radius (build-time knob)
 static __device__ __noinline__ unsigned long long knn_warp_query_at(const float4* spts, const uint32_t* cell_start,
                                                                 const GridDesc g, int k, const float4 q, int lane, unsigned long long* kbuf) {
   const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
@@ -214,7 +221,7 @@ static __device__ __noinline__ unsigned long long knn_warp_query_at(const float4
     const float kd2 = __uint_as_float((unsigned)(st.kth >> 32));
     if (st.kth != kInfKey && kd2 < lb * lb) break;
     if (cx - r <= 0 && cx + r >= g.nx - 1 && cy - r <= 0 && cy + r >= g.ny - 1 && cz - r <= 0 && cz + r >= g.nz - 1) break;
-    const int rr = r < 3 ? r + 1 : r + (r >> 1) + 1;  // outer radius of the shell to scan now
+    const int rr = r < kThinShells ? r + 1 : r + (r >> 1) + 1;  // outer radius of the shell to scan now
     const int side = 2 * rr + 1;
     const int nslots = 2 * side * side;
     const float inv_side = 1.0f / (float)side;
