@@ -20,32 +20,6 @@ namespace prep {
 
 namespace cg = cooperative_groups;
 
-// Read-once / write-once traffic of the prologue (the raw cloud's last read, the scratch keys and ranks, the labels and
-// the inverse permutation) marked evict-first so that it does not push the grids other resident registrations are
-// searching out of L2. Build-time knob (-DAPD_STREAM_HINTS=1) while it is being measured.
-#ifndef APD_SCAN_VEC
-#define APD_SCAN_VEC 0
-#endif
-#ifndef APD_STREAM_HINTS
-#define APD_STREAM_HINTS 0
-#endif
-template <typename T>
-__device__ __forceinline__ T ld_once(const T* p) {
-#if APD_STREAM_HINTS
-  return __ldcs(p);
-#else
-  return *p;
-#endif
-}
-template <typename T>
-__device__ __forceinline__ void st_once(T* p, T v) {
-#if APD_STREAM_HINTS
-  __stcs(p, v);
-#else
-  *p = v;
-#endif
-}
-
 __device__ __forceinline__ unsigned int f2ord(float f) {
   unsigned int u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -156,42 +130,6 @@ __device__ __forceinline__ void scan_phase(cg::cluster_group& cluster, PrepShare
   uint32_t carry = 0;
   for (unsigned r = 0; r < cluster.block_rank(); r++) carry += *cluster.map_shared_rank(&ps.cta_tot, r);
   for (int w = 0; w < warp; w++) carry += ps.warp_tot[w];
-#if APD_SCAN_VEC
-  // four consecutive counters per lane and turn (one 16-byte load, one 16-byte store): a turn is a dependent round trip
-  // through L2 (~1 us under a pool's load) and a 60 k-point submap's chunk is ~60 turns of 32 counters per warp
-  if ((reinterpret_cast<size_t>(data) & 15) == 0) {  // (chunks start at multiples of 32 counters)
-    for (int j0 = b; j0 < e; j0 += 128) {
-      const int j = j0 + 4 * lane;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (j + 3 < e) {
-        v = __ldcg(reinterpret_cast<const uint4*>(&data[j]));
-      } else {
-        if (j < e) v.x = __ldcg(&data[j]);
-        if (j + 1 < e) v.y = __ldcg(&data[j + 1]);
-        if (j + 2 < e) v.z = __ldcg(&data[j + 2]);
-      }
-      const uint32_t tot = v.x + v.y + v.z + v.w;
-      uint32_t inc = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      const uint32_t x0 = carry + inc - tot;
-      const uint4 out = make_uint4(x0, x0 + v.x, x0 + v.x + v.y, x0 + v.x + v.y + v.z);
-      if (j + 3 < e) {
-        __stcg(reinterpret_cast<uint4*>(&data[j]), out);
-      } else {
-        if (j < e) __stcg(&data[j], out.x);
-        if (j + 1 < e) __stcg(&data[j + 1], out.y);
-        if (j + 2 < e) __stcg(&data[j + 2], out.z);
-      }
-      carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    cluster.sync();
-    return;
-  }
-#endif
   for (int j0 = b; j0 < e; j0 += 32) {
     const int j = j0 + lane;
     const uint32_t v = j < e ? __ldcg(&data[j]) : 0u;
@@ -218,10 +156,7 @@ __device__ __forceinline__ void grids_phase(cg::cluster_group& cluster, PrepShar
   cluster.sync();
   // (kU points per thread and turn: the loads, then the atomics, then the stores — each step of a point waits a memory
   // round trip for the one before, and under a pool's load a round trip is ~1 us; four in flight per thread instead of one)
-#ifndef APD_GRID_UNROLL
-#define APD_GRID_UNROLL 4
-#endif
-  constexpr int kU = APD_GRID_UNROLL;
+  constexpr int kU = 4;
   for (int c = first; c < last; c++) {
     const GridDesc g = ps.grid[c];
     const int n = job[c].n;
@@ -246,8 +181,8 @@ __device__ __forceinline__ void grids_phase(cg::cluster_group& cluster, PrepShar
       for (int u = 0; u < kU; u++) {
         const int i = i0 + u * GT;
         if (i < n) {
-          st_once(&job[c].keys[i], key[u]);  // (read back by the same thread only)
-          st_once(&job[c].rank[i], rk[u]);
+          job[c].keys[i] = key[u];  // (read back by the same thread only)
+          job[c].rank[i] = rk[u];
         }
       }
     }
@@ -282,9 +217,9 @@ __device__ __forceinline__ void grids_phase(cg::cluster_group& cluster, PrepShar
 #pragma unroll
       for (int u = 0; u < kU; u++) {
         const int i = i0 + u * GT < n ? i0 + u * GT : i0;
-        key[u] = ld_once(&job[c].keys[i]);
-        r[u] = ld_once(&job[c].rank[i]);
-        p[u] = ld_once(&job[c].pts[i]);
+        key[u] = job[c].keys[i];
+        r[u] = job[c].rank[i];
+        p[u] = job[c].pts[i];
       }
 #pragma unroll
       for (int u = 0; u < kU; u++) b[u] = __ldcg(&job[c].cell_start[key[u]]);
@@ -294,8 +229,8 @@ __device__ __forceinline__ void grids_phase(cg::cluster_group& cluster, PrepShar
         if (i < n) {
           const int sp = (int)(b[u] + r[u]);
           job[c].spts[sp] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(i));
-          st_once(&job[c].label[sp], p[u].w);
-          st_once(&job[c].inv_perm[i], sp);
+          job[c].label[sp] = p[u].w;
+          job[c].inv_perm[i] = sp;
           if (job[c].zero_flags) job[c].zero_flags[i] = 0;
         }
       }
