@@ -2562,6 +2562,8 @@ void batch_fill_result(apd_batch* b, apd_handle* h, int i, int rc) {
   r.status = rc;
   // a failed pair may leave copies out of the caller's buffers in flight: they must not outlive apd_batch_align
   if (rc != APD_OK) cudaStreamSynchronize(h->stream);
+  if (rc == APD_ERR_CUDA || rc == APD_ERR_INVALID)  // (apd_result carries the code only: say what it was)
+    std::fprintf(stderr, "[apdgicp] batch pair %d failed (status %d): %s\n", i, rc, h->error.c_str());
 }
 
 // A pool worker drives several handles ("slots") and never blocks on one of them: a registration is a short state
@@ -2672,8 +2674,11 @@ void slot_begin(apd_batch* b, PoolSlot& sl, int i) {
   slot_enqueue(b, sl);  // (the fused kernel sizes its grids itself: one launch, no wait for the boxes)
 }
 
-// a slot has been waiting for 20 ms: make sure its stream is still alive (a failed launch or a faulting kernel publishes nothing)
-bool slot_stalled(PoolSlot& sl, bool arrived_now) {
+// a slot has been waiting for 20 ms: make sure its stream is still alive (a failed launch or a faulting kernel publishes nothing).
+// `arrived` is asked AFTER the stream was seen idle: a kernel that finishes between a first look at the result and the
+// stream query has published it (round 2: one pair in a thousand of a pool whose registrations take longer than the
+// 20 ms — 256 eager ones in flight — was reported as failed this way).
+bool slot_stalled(PoolSlot& sl, bool (*arrived)(const apd_handle*)) {
   const auto now = std::chrono::steady_clock::now();
   if (now - sl.since < std::chrono::milliseconds(20)) return false;
   sl.since = now;
@@ -2681,7 +2686,7 @@ bool slot_stalled(PoolSlot& sl, bool arrived_now) {
   if (ps == 1 || ps == 2) return false;  // not launched yet (waiting for a partner / the partner is launching it)
   const cudaError_t e = cudaStreamQuery(ps == 3 ? sl.h->launch_stream : sl.h->stream);
   if (e == cudaErrorNotReady) return false;
-  if (e == cudaSuccess && arrived_now) return false;
+  if (e == cudaSuccess && arrived(sl.h)) return false;
   sl.h->error = e == cudaSuccess ? "kernel finished without publishing its result" : cudaGetErrorString(e);
   return true;
 }
@@ -2769,7 +2774,7 @@ void batch_worker(apd_batch* b, int wi) {
               DeviceGuard dg(h->device);
               slot_enqueue(b, sl);
               progressed = true;
-            } else if (slot_stalled(sl, bboxes_arrived(h))) {
+            } else if (slot_stalled(sl, bboxes_arrived)) {
               batch_fill_result(b, h, sl.pair, APD_ERR_CUDA);
               sl.state = kSlotIdle;
             }
@@ -2808,7 +2813,7 @@ void batch_worker(apd_batch* b, int wi) {
               batch_fill_result(b, h, sl.pair, rc);
               sl.state = kSlotIdle;
               progressed = true;
-            } else if (slot_stalled(sl, result_arrived(h))) {
+            } else if (slot_stalled(sl, result_arrived)) {
               batch_fill_result(b, h, sl.pair, APD_ERR_CUDA);
               sl.state = kSlotIdle;
             }

@@ -889,6 +889,53 @@ def test_pool_two_registrations_per_launch(gorio, synth, monkeypatch):
         assert (r1["converged"], r1["iterations"], r1["n_inliers"]) == (r2["converged"], r2["iterations"], r2["n_inliers"])
 
 
+def test_pool_any_submap_grid_resolution(gorio, synth, monkeypatch):
+    """a submap whose covariances are computed on demand gets a coarser grid (2 cells per point instead of 4: fewer, longer
+    candidate lists); the resolution decides how the exact searches walk, never what they find — bit-identical poses,
+    fitness and iteration counts at 1 / 2 / 4 cells per point, and equal to the eager path"""
+    pairs = []
+    for seed in range(3150, 3154):
+        s, t, _ = synth.submap_pair(seed, n_source=600, n_frames=10, n_per_frame=1000)  # 10 000 points: above the scans' rule
+        pairs.append((s, t, None))
+    out = {}
+    for key, env in (("1", {"APD_CELLS_PER_POINT_MID_LAZY": "1"}), ("2", {}), ("4", {"APD_CELLS_PER_POINT_MID_LAZY": "4"}),
+                     ("eager", {"APD_LAZY_TARGET_COV": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        b = gorio.Batch(0, n_workers=4, max_correspondence_distance=2.0, transformation_epsilon=0.1)
+        out[key] = b.align(b.prepare(pairs))
+        b.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    for key in ("1", "4", "eager"):
+        for r1, r2 in zip(out["2"], out[key]):
+            assert r1["status"] == 0 and r2["status"] == 0
+            assert np.array_equal(r1["T"], r2["T"]) and r1["fitness"] == r2["fitness"]
+            assert (r1["converged"], r1["iterations"], r1["n_inliers"]) == (r2["converged"], r2["iterations"], r2["n_inliers"])
+
+
+def test_pool_registrations_longer_than_the_stall_check(gorio, synth, monkeypatch):
+    """256 eager registrations in flight take ~30 ms each — longer than the 20 ms after which a worker asks the stream whether
+    its kernel is still alive. A kernel that finished between the worker's look at the result and that stream query was
+    reported as "finished without publishing its result" (one pair in a thousand): every pair of every pass must succeed,
+    with the same pose each pass"""
+    monkeypatch.setenv("APD_LAZY_TARGET_COV", "0")
+    scenes = [synth.submap_pair(3300 + i)[:2] for i in range(4)]
+    pairs = [(scenes[i % 4][0], scenes[i % 4][1], None) for i in range(256)]
+    b = gorio.Batch(0, n_workers=256, max_correspondence_distance=2.0, transformation_epsilon=0.1)
+    prepared = b.prepare(pairs)
+    rep = b.repeat(prepared, 6)
+    b.align(rep, with_fitness=False, parse=False)
+    v = b.results_view(rep["res"])
+    assert not np.any(v["status"] != 0), np.nonzero(v["status"] != 0)[0][:10]
+    T = v["T"].reshape(6, 256, 16)
+    for j in range(1, 6):
+        assert np.array_equal(T[0], T[j])
+    for i in range(4, 256):
+        assert np.array_equal(T[0][i], T[0][i % 4])
+    b.close()
+
+
 def test_pool_reports_errors_per_pair(gorio, synth):
     """a pair that cannot be registered (fewer source points than k: APD_ERR_TOO_FEW, where the reference reads
     uninitialised memory) fails alone; the pool carries on with the others, call after call"""
