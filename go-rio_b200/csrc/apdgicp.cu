@@ -2632,6 +2632,13 @@ void slot_begin(apd_batch* b, PoolSlot& sl, int i) {
   sl.pair = i;
   const apd_pair& pr = b->pairs[i];
   std::memset(&b->results[i], 0, sizeof(apd_result));
+  // A registration whose loop a partner launched ends with pair_state 3 and launch_stream = the partner's stream. The next
+  // one must not inherit them: while it waits for its bounding boxes (device clouds, grids sized on the host — the eager
+  // path) the stall check would ask the PARTNER's old stream, find it idle and report a kernel that "finished without
+  // publishing its result" (round 2: ~1 pair in a thousand with 256 eager registrations in flight, where a bounds kernel
+  // queues for more than the check's 20 ms).
+  h->pair_state.store(0, std::memory_order_release);
+  h->launch_stream = h->stream;
   const auto t_set = std::chrono::steady_clock::now();
   // the reference benchmark protocol: clearTarget; clearSource; setInputTarget; setInputSource; align (align.cpp:57-83)
   apd_clear_target(h);

@@ -916,23 +916,32 @@ def test_pool_any_submap_grid_resolution(gorio, synth, monkeypatch):
 
 def test_pool_registrations_longer_than_the_stall_check(gorio, synth, monkeypatch):
     """256 eager registrations in flight take ~30 ms each — longer than the 20 ms after which a worker asks the stream whether
-    its kernel is still alive. A kernel that finished between the worker's look at the result and that stream query was
-    reported as "finished without publishing its result" (one pair in a thousand): every pair of every pass must succeed,
-    with the same pose each pass"""
+    its kernel is still alive. Two ways that check reported a healthy pair as "finished without publishing its result"
+    (one pair in a thousand of bench.py's eager block): the kernel finishing between the worker's look at the result and
+    the stream query, and — device clouds, whose boxes a kernel reduces first — a handle asking the stream of the PARTNER
+    that had launched its previous registration. Every pair of every pass must succeed, with the same pose each pass,
+    from HBM-resident and from host clouds"""
+    import torch
     monkeypatch.setenv("APD_LAZY_TARGET_COV", "0")
     scenes = [synth.submap_pair(3300 + i)[:2] for i in range(4)]
-    pairs = [(scenes[i % 4][0], scenes[i % 4][1], None) for i in range(256)]
+    dev = [(torch.from_numpy(np.ascontiguousarray(s)).cuda(), torch.from_numpy(np.ascontiguousarray(t)).cuda()) for s, t in scenes]
+    host_pairs = [(scenes[i % 4][0], scenes[i % 4][1], None) for i in range(256)]
+    dev_pairs = [((dev[i % 4][0].data_ptr(), scenes[i % 4][0].shape[0]), (dev[i % 4][1].data_ptr(), scenes[i % 4][1].shape[0]), None) for i in range(256)]
     b = gorio.Batch(0, n_workers=256, max_correspondence_distance=2.0, transformation_epsilon=0.1)
-    prepared = b.prepare(pairs)
-    rep = b.repeat(prepared, 6)
-    b.align(rep, with_fitness=False, parse=False)
-    v = b.results_view(rep["res"])
-    assert not np.any(v["status"] != 0), np.nonzero(v["status"] != 0)[0][:10]
-    T = v["T"].reshape(6, 256, 16)
-    for j in range(1, 6):
-        assert np.array_equal(T[0], T[j])
-    for i in range(4, 256):
-        assert np.array_equal(T[0][i], T[0][i % 4])
+    first = None
+    for pairs in (dev_pairs, host_pairs):
+        prepared = b.prepare(pairs)
+        rep = b.repeat(prepared, 6)
+        b.align(rep, with_fitness=False, parse=False)
+        v = b.results_view(rep["res"])
+        assert not np.any(v["status"] != 0), np.nonzero(v["status"] != 0)[0][:10]
+        T = v["T"].reshape(6, 256, 16)
+        for j in range(1, 6):
+            assert np.array_equal(T[0], T[j])
+        for i in range(4, 256):
+            assert np.array_equal(T[0][i], T[0][i % 4])
+        first = T[0].copy() if first is None else first
+        assert np.array_equal(first, T[0])
     b.close()
 
 
