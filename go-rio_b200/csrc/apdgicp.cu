@@ -2578,6 +2578,7 @@ struct PoolSlot {
   int state = kSlotIdle;
   int di = 0;  // index of the handle's device in the batch
   std::chrono::steady_clock::time_point since;
+  int idle_seen = 0;  // consecutive stall checks that found the stream idle and nothing published (slot_stalled)
 };
 
 bool bboxes_arrived(const apd_handle* h) {
@@ -2621,6 +2622,7 @@ void slot_enqueue(apd_batch* b, PoolSlot& sl) {
   else if (rc == APD_OK) {
     sl.state = kSlotResult;
     sl.since = std::chrono::steady_clock::now();
+    sl.idle_seen = 0;
     return;
   }
   batch_fill_result(b, h, sl.pair, rc);
@@ -2676,6 +2678,7 @@ void slot_begin(apd_batch* b, PoolSlot& sl, int i) {
     }
     sl.state = kSlotBbox;
     sl.since = std::chrono::steady_clock::now();
+    sl.idle_seen = 0;
     return;
   }
   slot_enqueue(b, sl);  // (the fused kernel sizes its grids itself: one launch, no wait for the boxes)
@@ -2692,8 +2695,14 @@ bool slot_stalled(PoolSlot& sl, bool (*arrived)(const apd_handle*)) {
   const int ps = sl.h->pair_state.load(std::memory_order_acquire);
   if (ps == 1 || ps == 2) return false;  // not launched yet (waiting for a partner / the partner is launching it)
   const cudaError_t e = cudaStreamQuery(ps == 3 ? sl.h->launch_stream : sl.h->stream);
-  if (e == cudaErrorNotReady) return false;
+  if (e == cudaErrorNotReady) {
+    sl.idle_seen = 0;
+    return false;
+  }
   if (e == cudaSuccess && arrived(sl.h)) return false;
+  // an idle stream with nothing published is a verdict only when the next check (20 ms later) finds the same: the state a
+  // worker reads here is written by other workers (a partner launching this handle's loop), and a false alarm fails a pair
+  if (e == cudaSuccess && ++sl.idle_seen < 2) return false;
   sl.h->error = e == cudaSuccess ? "kernel finished without publishing its result" : cudaGetErrorString(e);
   return true;
 }
