@@ -2523,13 +2523,17 @@ namespace {
 // launch the staged loop of `h` — with the staged loop of `partner` in the same grid when there is one — on h's stream
 int launch_staged(apd_handle* h, apd_handle* partner) {
   DeviceGuard dg(h->device);
+  cudaError_t e = cudaSuccess;
   if (partner) {
-    APD_CUDA(h, cudaStreamWaitEvent(h->stream, partner->pair_ev, 0));  // the partner's cloud copies
+    e = cudaStreamWaitEvent(h->stream, partner->pair_ev, 0);  // the partner's cloud copies
     partner->launch_stream = h->stream;
   }
-  launch_lm(&h->staged_job, nullptr, 1, h->staged_cfg, h->lm_cluster, h->lm_min_blocks, h->stream, &h->launches, partner ? &partner->staged_job : nullptr);
-  const cudaError_t e = cudaGetLastError();
-  h->k_launches[APD_K_LM]++;
+  if (e == cudaSuccess) {
+    launch_lm(&h->staged_job, nullptr, 1, h->staged_cfg, h->lm_cluster, h->lm_min_blocks, h->stream, &h->launches, partner ? &partner->staged_job : nullptr);
+    e = cudaGetLastError();
+    h->k_launches[APD_K_LM]++;
+  }
+  // (whatever happened, the partner leaves state 2: its own stall check then finds an idle stream with nothing published)
   if (partner) partner->pair_state.store(3, std::memory_order_release);
   h->pair_state.store(0, std::memory_order_release);
   APD_CUDA(h, e);
